@@ -1,0 +1,169 @@
+// Shared device/host helpers for the B200 (sm_100a) spin Monte Carlo library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define B200MC_OK 0
+#define B200MC_ERR_ARG 1      // invalid argument / invalid lattice shape
+#define B200MC_ERR_CUDA 2     // a CUDA runtime call failed (see b200mc_last_error)
+#define B200MC_ERR_STATE 3    // call not valid in the current state
+#define B200MC_ERR_UNSUPPORTED 4
+
+extern thread_local char g_b200mc_err[512];
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            snprintf(g_b200mc_err, sizeof(g_b200mc_err), "%s:%d: %s -> %s", __FILE__,     \
+                     __LINE__, #call, cudaGetErrorString(e_));                            \
+            return B200MC_ERR_CUDA;                                                       \
+        }                                                                                 \
+    } while (0)
+
+#define ARG_FAIL(...)                                                  \
+    do {                                                               \
+        snprintf(g_b200mc_err, sizeof(g_b200mc_err), __VA_ARGS__);     \
+        return B200MC_ERR_ARG;                                         \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), in registers.  Ten rounds of two
+// 32x32->64 multiplies (IMAD.WIDE.U32) and two three-input XORs (LOP3); the
+// round keys are uniform across the grid so their schedule costs nothing per
+// thread.  Pinned to the Random123 known-answer vectors by
+// tests/test_gpu_rng.py (through b200mc_debug_philox).
+// ---------------------------------------------------------------------------
+#define PHILOX_M0 0xD2511F53u
+#define PHILOX_M1 0xCD9E8D57u
+#define PHILOX_W0 0x9E3779B9u
+#define PHILOX_W1 0xBB67AE85u
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned long long p0 = (unsigned long long)PHILOX_M0 * c.x;
+        unsigned long long p1 = (unsigned long long)PHILOX_M1 * c.z;
+        uint4 n;
+        n.x = (uint32_t)(p1 >> 32) ^ c.y ^ k.x;
+        n.y = (uint32_t)p1;
+        n.z = (uint32_t)(p0 >> 32) ^ c.w ^ k.y;
+        n.w = (uint32_t)p0;
+        c = n;
+        k.x += PHILOX_W0;
+        k.y += PHILOX_W1;
+    }
+    return c;
+}
+
+// RNG contract (see DESIGN.md "RNG contract"; CPU restatement in
+// oracle/rng_contract.c): key = (seed, TAG), counter =
+// (block_lo, block_hi, draw_lo, draw[32..47] | colour << 16 | sub << 24).
+#define TAG_ISING 0x49534E47u
+#define TAG_INIT 0x494E4954u
+#define TAG_CLOCK 0x434C4F4Bu
+#define TAG_TORUS 0x544F5253u
+#define TAG_XY 0x58593244u
+
+__host__ __device__ __forceinline__ uint4 mk_ctr(uint64_t blk, uint64_t draw, uint32_t colour,
+                                                 uint32_t sub)
+{
+    uint4 c;
+    c.x = (uint32_t)blk;
+    c.y = (uint32_t)(blk >> 32);
+    c.z = (uint32_t)draw;
+    c.w = (uint32_t)((draw >> 32) & 0xFFFFu) | (colour << 16) | (sub << 24);
+    return c;
+}
+
+// ---------------------------------------------------------------------------
+// 128-bit global memory access with cache hints.
+//   ld_other : the colour that is read-only during this pass.  Neighbouring
+//              threads / later rows re-read it, so it goes through L1 (nc path).
+//   ld_own / st_own : streamed exactly once per pass -> no L1 allocation.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_other(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ld_own(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_own(uint4* p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// does the word contain a zero byte?
+__device__ __forceinline__ uint32_t zero_byte_mask(uint32_t v)
+{
+    return (v - 0x01010101u) & ~v & 0x80808080u;
+}
+
+// warp + block sum of up to NV 64-bit values, one atomic per block per value
+template <int NV>
+__device__ __forceinline__ void block_atomic_add(unsigned long long* dst, long long (&v)[NV])
+{
+    __shared__ long long sm[NV][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_down_sync(0xffffffffu, v[j], o);
+        if (lane == 0) sm[j][warp] = v[j];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            long long t = (lane < nw) ? sm[j][lane] : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+            if (lane == 0 && t != 0) atomicAdd(dst + j, (unsigned long long)t);
+        }
+    }
+}
+template <int NV>
+__device__ __forceinline__ void block_atomic_add_f64(double* dst, double (&v)[NV])
+{
+    __shared__ double smd[NV][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_down_sync(0xffffffffu, v[j], o);
+        if (lane == 0) smd[j][warp] = v[j];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            double t = (lane < nw) ? smd[j][lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+            if (lane == 0) atomicAdd(dst + j, t);
+        }
+    }
+}

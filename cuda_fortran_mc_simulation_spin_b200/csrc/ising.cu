@@ -1,0 +1,340 @@
+// Ising 2D / 3D (helical): host-side handle and C ABI.
+// Reference: type(ising2d_gpu) src/ising2d_gpu_m.f90:12-42,
+//            type(ising3d_gpu) src/ising3d_gpu_m.f90:15-48.
+#include <math.h>
+#include <new>
+#include "../../include/b200mc.h"
+#include "ising_kernels.cuh"
+#include "ring.cuh"
+
+namespace {
+
+struct Ising {
+    int ndim;  // 2 or 3
+    int64_t nx, ny, nz;
+    RingStore st;
+    cudaStream_t stream;
+    double beta;
+    uint32_t seed;
+    uint64_t draw;
+    int method;
+    double w[16];      // w[s*8 + S]: acceptance probability exactly as the reference builds it
+    double exparr[17]; // 2D: exparr(-8:8)
+    double ws3[14];    // 3D: ws(0:6, 0:1)
+    IsingTab tab;
+    IsingTabF64 tabf;
+    unsigned long long* d_acc;  // [X, sum s]
+    int64_t* d_off1;            // colour-1 offsets for the measure kernel
+    double* d_randoms;
+    int grid;
+    bool alive;
+};
+
+int build_tables(Ising* m)
+{
+    const double beta = m->beta;
+    for (int i = 0; i < 16; ++i) m->w[i] = 0.0;
+    if (m->ndim == 3) {
+        // update_ws_ising3d_gpu, src/ising3d_gpu_m.f90:138-172 (same loop nest and expression order)
+        static const int32_t spin_map[2] = {-1, 1};
+        int64_t et[4][2];
+        for (int i1 = 0; i1 <= 1; ++i1)
+            for (int i2 = 0; i2 <= 1; ++i2)
+                for (int i3 = 0; i3 <= 1; ++i3) {
+                    const int s1 = i1 + i2 + i3;
+                    const int32_t sum = spin_map[i1] + spin_map[i2] + spin_map[i3];
+                    et[s1][0] = -spin_map[0] * sum;
+                    et[s1][1] = -spin_map[1] * sum;
+                }
+        for (int s1 = 0; s1 <= 3; ++s1)
+            for (int s2 = 0; s2 <= 3; ++s2) {
+                const int64_t e1 = et[s1][0] + et[s2][0];
+                const int64_t e2 = et[s1][1] + et[s2][1];
+                m->ws3[s1 + s2 + 7 * 0] = fmin(1.0, exp(-beta * (double)(e2 - e1)));
+                m->ws3[s1 + s2 + 7 * 1] = fmin(1.0, exp(-beta * (double)(e1 - e2)));
+            }
+        for (int s = 0; s < 2; ++s)
+            for (int S = 0; S <= 6; ++S) m->w[s * 8 + S] = m->ws3[S + 7 * s];
+    } else {
+        // update_exparr_ising2d_gpu, src/ising2d_gpu_m.f90:122-131
+        for (int i = 0; i < 17; ++i) m->exparr[i] = 1.0;
+        for (int diff = 1; diff <= 8; ++diff) m->exparr[diff + 8] = exp(-beta * diff);
+        // calc_delta_energy :195 with sigma = 2s-1 and sum(sigma_nb) = 2S-4
+        for (int s = 0; s < 2; ++s)
+            for (int S = 0; S <= 4; ++S) {
+                const int de = 2 * (2 * s - 1) * (2 * S - 4);
+                m->w[s * 8 + S] = m->exparr[de + 8];
+            }
+    }
+    if (m->method == METHOD_HEATBATH) {
+        // SURVEY Q10 definition: p_up(S) = 1/(1+exp(-2 beta (2S - z))), new spin = up iff u <= p_up
+        const int z = m->ndim == 3 ? 6 : 4;
+        for (int i = 0; i < 16; ++i) m->w[i] = 0.0;
+        for (int S = 0; S <= z; ++S) {
+            const double p = 1.0 / (1.0 + exp(-2.0 * beta * (double)(2 * S - z)));
+            m->w[S] = p;
+            m->w[8 + S] = p;
+        }
+    }
+    // thresholds: u <= w  <=>  U < thr, thr = floor(w 2^32)
+    uint8_t tb[2][8];
+    for (int s = 0; s < 2; ++s)
+        for (int S = 0; S < 8; ++S) {
+            const double w = m->w[s * 8 + S];
+            uint64_t thr = (uint64_t)floor(w * 4294967296.0);
+            if (thr > 4294967296ull) thr = 4294967296ull;
+            const uint32_t t7 = (uint32_t)(thr >> 25);  // 0..128
+            tb[s][S] = (uint8_t)(128u - t7);
+            m->tab.low25[s][S] = (uint32_t)(thr & 0x1FFFFFFu);
+            m->tabf.w[s * 8 + S] = w;
+        }
+    for (int s = 0; s < 2; ++s) {
+        m->tab.tlo[s] = tb[s][0] | (tb[s][1] << 8) | (tb[s][2] << 16) | ((uint32_t)tb[s][3] << 24);
+        m->tab.thi[s] = tb[s][4] | (tb[s][5] << 8) | (tb[s][6] << 16) | ((uint32_t)tb[s][7] << 24);
+    }
+    return B200MC_OK;
+}
+
+template <int NNB>
+int launch_pass(Ising* m, int colour)
+{
+    const RingGeom& g = m->st.g;
+    RingPassArgs a;
+    a.own = m->st.vec[colour];
+    a.oth = m->st.vec[colour ^ 1];
+    a.nvec = g.L;
+    a.H = g.H;
+    a.p0 = 0;
+    for (int j = 0; j < 6; ++j) a.off[j] = g.off[colour][j];
+    a.seed = m->seed;
+    a.colour = (uint32_t)colour;
+    a.draw = m->draw;
+    if (m->method == METHOD_METROPOLIS)
+        ising_pass_kernel<NNB, METHOD_METROPOLIS><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+    else
+        ising_pass_kernel<NNB, METHOD_HEATBATH><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+    CK(cudaGetLastError());
+    return ring_halo(&m->st, colour, m->stream);
+}
+
+int sweep(Ising* m)
+{
+    int rc;
+    for (int colour = 0; colour < 2; ++colour) {
+        rc = m->ndim == 3 ? launch_pass<6>(m, colour) : launch_pass<4>(m, colour);
+        if (rc) return rc;
+    }
+    m->draw += 1;
+    return B200MC_OK;
+}
+
+template <int NNB>
+int launch_pass_randoms(Ising* m, int colour)
+{
+    const RingGeom& g = m->st.g;
+    RingPassArgs a;
+    a.own = m->st.vec[colour];
+    a.oth = m->st.vec[colour ^ 1];
+    a.nvec = g.L;
+    a.H = g.H;
+    a.p0 = 0;
+    for (int j = 0; j < 6; ++j) a.off[j] = g.off[colour][j];
+    a.seed = m->seed;
+    a.colour = (uint32_t)colour;
+    a.draw = m->draw;
+    const unsigned grid = (unsigned)((g.L + 255) / 256);
+    if (m->method == METHOD_METROPOLIS)
+        ising_pass_randoms_kernel<NNB, METHOD_METROPOLIS><<<grid, 256, 0, m->stream>>>(a, m->tabf, m->d_randoms, g.L, g.Nc);
+    else
+        ising_pass_randoms_kernel<NNB, METHOD_HEATBATH><<<grid, 256, 0, m->stream>>>(a, m->tabf, m->d_randoms, g.L, g.Nc);
+    CK(cudaGetLastError());
+    return ring_halo(&m->st, colour, m->stream);
+}
+
+int measure(Ising* m, int64_t* e, int64_t* mag)
+{
+    const RingGeom& g = m->st.g;
+    CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
+    if (m->ndim == 3)
+        ising_measure_kernel<6><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.L, g.H, 0, m->d_off1, g.L, g.Nc, g.ptail, m->d_acc);
+    else
+        ising_measure_kernel<4><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.L, g.H, 0, m->d_off1, g.L, g.Nc, g.ptail, m->d_acc);
+    CK(cudaGetLastError());
+    unsigned long long acc[2];
+    CK(cudaMemcpyAsync(acc, m->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    const int64_t X = (int64_t)acc[0], sum = (int64_t)acc[1];
+    // E = -(bonds) + 2 X with bonds = (nnb/2) N;   M = 2 sum(s) - N
+    if (e) *e = -(int64_t)(g.nnb / 2) * g.N + 2 * X;
+    if (mag) *mag = 2 * sum - g.N;
+    return B200MC_OK;
+}
+
+int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed)
+{
+    if (!out) ARG_FAIL("null handle pointer");
+    *out = nullptr;
+    if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        snprintf(g_b200mc_err, sizeof(g_b200mc_err), "no CUDA device: this library has no CPU fallback");
+        return B200MC_ERR_CUDA;
+    }
+    Ising* m = new (std::nothrow) Ising();
+    if (!m) ARG_FAIL("out of host memory");
+    m->ndim = ndim; m->nx = nx; m->ny = ny; m->nz = ndim == 3 ? nz : 0;
+    m->stream = 0; m->d_acc = nullptr; m->d_off1 = nullptr; m->d_randoms = nullptr;
+    m->method = METHOD_METROPOLIS; m->seed = (uint32_t)iseed; m->draw = 0; m->alive = true;
+    int rc = ring_geom_init(&m->st.g, nx, ny, m->nz);
+    if (rc) { delete m; return rc; }
+    rc = ring_alloc(&m->st);
+    if (rc) { ring_free(&m->st); delete m; return rc; }
+    if (cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&m->d_off1, 6 * sizeof(int64_t)) != cudaSuccess) {
+        snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed");
+        ring_free(&m->st); cudaFree(m->d_acc); cudaFree(m->d_off1); delete m; return B200MC_ERR_CUDA;
+    }
+    cudaMemcpy(m->d_off1, m->st.g.off[1], 6 * sizeof(int64_t), cudaMemcpyHostToDevice);
+    // persistent-style grid: SMs x resident blocks, grid-stride over the vectors
+    int dev = 0, sms = 148, occ = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (ndim == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ising_pass_kernel<6, METHOD_METROPOLIS>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ising_pass_kernel<4, METHOD_METROPOLIS>, 256, 0);
+    if (occ < 1) occ = 1;
+    int64_t need = (m->st.g.L + 255) / 256;
+    m->grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);
+    m->beta = 1 / kbt;
+    build_tables(m);
+    rc = ring_fill(&m->st, 1, m->stream);  // set_allup_spin
+    if (rc) { ring_free(&m->st); cudaFree(m->d_acc); cudaFree(m->d_off1); delete m; return rc; }
+    *out = m;
+    return B200MC_OK;
+}
+
+int destroy(Ising* m)
+{
+    if (!m) return B200MC_OK;
+    cudaStreamSynchronize(m->stream);
+    ring_free(&m->st);
+    cudaFree(m->d_acc);
+    cudaFree(m->d_off1);
+    cudaFree(m->d_randoms);
+    delete m;
+    return B200MC_OK;
+}
+
+int set_random(Ising* m)
+{
+    const RingGeom& g = m->st.g;
+    for (int c = 0; c < 2; ++c) {
+        ring_random_bits_kernel<<<(unsigned)((g.L + 255) / 256), 256, 0, m->stream>>>(m->st.vec[c], g.L, g.H, 0, m->seed, m->draw, (uint32_t)c);
+        CK(cudaGetLastError());
+    }
+    m->draw += 1;
+    int rc = ring_halo(&m->st, 0, m->stream);
+    if (rc) return rc;
+    return ring_halo(&m->st, 1, m->stream);
+}
+
+int update_with_randoms(Ising* m, const double* randoms)
+{
+    if (!randoms) ARG_FAIL("null randoms");
+    const RingGeom& g = m->st.g;
+    if (!m->d_randoms) CK(cudaMalloc(&m->d_randoms, (size_t)g.N * sizeof(double)));
+    CK(cudaMemcpyAsync(m->d_randoms, randoms, (size_t)g.N * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    for (int colour = 0; colour < 2; ++colour) {
+        int rc = m->ndim == 3 ? launch_pass_randoms<6>(m, colour) : launch_pass_randoms<4>(m, colour);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(m->stream));  // the host array may be reused by the caller
+    return B200MC_OK;
+}
+
+int skip(Ising* m, int64_t n_skip)
+{
+    if (n_skip < 0) ARG_FAIL("n_skip < 0");
+    // the reference offsets its XORWOW stream by n_skip uniforms (src/ising3d_gpu_m.f90:72-77);
+    // one generate call draws nall of them, so advance the draw counter by ceil(n_skip / nall)
+    m->draw += (uint64_t)((n_skip + m->st.g.N - 1) / m->st.g.N);
+    return B200MC_OK;
+}
+
+}  // namespace
+
+#define H(h) (reinterpret_cast<Ising*>(h))
+#define CHECK_H(h, nd)                                                              \
+    do {                                                                            \
+        if (!(h) || H(h)->ndim != (nd) || !H(h)->alive) ARG_FAIL("invalid handle"); \
+    } while (0)
+
+extern "C" {
+
+const char* b200mc_last_error(void) { return g_b200mc_err; }
+int b200mc_version(void) { return 100; }
+
+__global__ void philox_debug_kernel(uint4 c, uint2 k, uint4* out) { *out = philox4x32_10(c, k); }
+int b200mc_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint4* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(uint4)));
+    philox_debug_kernel<<<1, 1>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]), d);
+    uint4 r;
+    cudaError_t e = cudaMemcpy(&r, d, sizeof(r), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    CK(e);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+    return B200MC_OK;
+}
+
+#define DEFINE_COMMON(PFX, ND)                                                                    \
+    int PFX##_destroy(void* h) { if (!h) return B200MC_OK; CHECK_H(h, ND); return destroy(H(h)); } \
+    int PFX##_set_stream(void* h, void* s) { CHECK_H(h, ND); H(h)->stream = (cudaStream_t)s; return B200MC_OK; } \
+    int PFX##_skip_curand(void* h, int64_t n) { CHECK_H(h, ND); return skip(H(h), n); }           \
+    int PFX##_set_allup_spin(void* h) { CHECK_H(h, ND); return ring_fill(&H(h)->st, 1, H(h)->stream); } \
+    int PFX##_set_random_spin(void* h) { CHECK_H(h, ND); return set_random(H(h)); }               \
+    int PFX##_set_beta(void* h, double beta) { CHECK_H(h, ND); if (!(beta >= 0.0)) ARG_FAIL("beta must be >= 0"); H(h)->beta = beta; return build_tables(H(h)); } \
+    int PFX##_set_kbt(void* h, double kbt) { CHECK_H(h, ND); if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0"); H(h)->beta = 1 / kbt; return build_tables(H(h)); } \
+    int PFX##_set_method(void* h, int32_t method) { CHECK_H(h, ND); if (method != METHOD_METROPOLIS && method != METHOD_HEATBATH) ARG_FAIL("unknown method %d", method); H(h)->method = method; return build_tables(H(h)); } \
+    int PFX##_update(void* h) { CHECK_H(h, ND); return sweep(H(h)); }                             \
+    int PFX##_update_n(void* h, int32_t n) { CHECK_H(h, ND); for (int i = 0; i < n; ++i) { int rc = sweep(H(h)); if (rc) return rc; } return B200MC_OK; } \
+    int PFX##_update_with_randoms(void* h, const double* r) { CHECK_H(h, ND); return update_with_randoms(H(h), r); } \
+    int PFX##_calc_energy_sum(void* h, int64_t* e) { CHECK_H(h, ND); return measure(H(h), e, nullptr); } \
+    int PFX##_calc_magne_sum(void* h, int64_t* m) { CHECK_H(h, ND); return measure(H(h), nullptr, m); } \
+    int PFX##_measure(void* h, int64_t* e, int64_t* m) { CHECK_H(h, ND); return measure(H(h), e, m); } \
+    int PFX##_get_spins(void* h, int32_t* out) { CHECK_H(h, ND); if (!out) ARG_FAIL("null output"); return ring_export_i32(&H(h)->st, out, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream); } \
+    int PFX##_set_spins(void* h, const int32_t* in) { CHECK_H(h, ND); if (!in) ARG_FAIL("null input"); return ring_import_i32(&H(h)->st, in, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream); } \
+    int64_t PFX##_nx(void* h) { return h ? H(h)->nx : -1; }                                       \
+    int64_t PFX##_ny(void* h) { return h ? H(h)->ny : -1; }                                       \
+    int64_t PFX##_nall(void* h) { return h ? H(h)->st.g.N : -1; }                                 \
+    double PFX##_kbt(void* h) { return h ? 1 / H(h)->beta : 0.0; }                                \
+    double PFX##_beta(void* h) { return h ? H(h)->beta : 0.0; }                                   \
+    int PFX##_sync(void* h) { CHECK_H(h, ND); CK(cudaStreamSynchronize(H(h)->stream)); return B200MC_OK; }
+
+DEFINE_COMMON(b200mc_ising3d, 3)
+DEFINE_COMMON(b200mc_ising2d, 2)
+
+int b200mc_ising3d_create(void** h, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed)
+{
+    if (nz <= 0) ARG_FAIL("nz must be > 0");
+    return create(h, 3, nx, ny, nz, kbt, iseed);
+}
+int b200mc_ising2d_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed)
+{
+    return create(h, 2, nx, ny, 0, kbt, iseed);
+}
+int64_t b200mc_ising3d_nz(void* h) { return h ? H(h)->nz : -1; }
+int b200mc_ising3d_get_ws(void* h, double out[14])
+{
+    CHECK_H(h, 3);
+    for (int i = 0; i < 14; ++i) out[i] = H(h)->ws3[i];
+    return B200MC_OK;
+}
+int b200mc_ising2d_get_exparr(void* h, double out[17])
+{
+    CHECK_H(h, 2);
+    for (int i = 0; i < 17; ++i) out[i] = H(h)->exparr[i];
+    return B200MC_OK;
+}
+
+}  // extern "C"

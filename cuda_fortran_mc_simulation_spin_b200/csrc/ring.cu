@@ -1,0 +1,218 @@
+// Folded-ring storage: geometry, halo ("norishiro") refresh, import/export.
+// See ring.cuh for the layout.
+#include "ring.cuh"
+
+thread_local char g_b200mc_err[512] = {0};
+
+int ring_geom_init(RingGeom* g, int64_t nx, int64_t ny, int64_t nz)
+{
+    const bool is3d = nz > 0;
+    if (nx < 3 || ny < 2 || (is3d && nz < 2)) ARG_FAIL("lattice too small: %lld x %lld x %lld", (long long)nx, (long long)ny, (long long)nz);
+    // the reference colours by linear-index parity, which is a valid
+    // checkerboard only for nx odd and (2D) ny even / (3D) ny odd, nz even.
+    if ((nx & 1) == 0) ARG_FAIL("helical checkerboard needs odd nx (got %lld)", (long long)nx);
+    if (!is3d && (ny & 1)) ARG_FAIL("helical 2D checkerboard needs even ny (got %lld)", (long long)ny);
+    if (is3d && ((ny & 1) == 0 || (nz & 1))) ARG_FAIL("helical 3D checkerboard needs odd ny and even nz (got ny=%lld nz=%lld)", (long long)ny, (long long)nz);
+    const int64_t nxy = nx * ny;
+    g->N = is3d ? nxy * nz : nxy;
+    g->Nc = g->N / 2;
+    g->L = (g->Nc + 15) / 16;
+    g->P = is3d ? nxy : nx;
+    g->nnb = is3d ? 6 : 4;
+    const int64_t h = (nx - 1) / 2, gg = (nxy - 1) / 2;
+    g->H = (is3d ? gg : h) + 1;
+    for (int c = 0; c < 2; ++c) {
+        g->off[c][0] = -1 + c;      // i-1
+        g->off[c][1] = c;           // i+1
+        g->off[c][2] = h + c;       // i+nx
+        g->off[c][3] = -h - 1 + c;  // i-nx
+        g->off[c][4] = is3d ? gg + c : 0;       // i+nxy
+        g->off[c][5] = is3d ? -gg - 1 + c : 0;  // i-nxy
+    }
+    // lanes 0..14 are full; lane 15 holds Nc - 15 L sites (may be <= 0 for tiny rings)
+    int64_t l15 = g->Nc - 15 * g->L;
+    g->ptail = l15 < 0 ? 0 : l15;
+    if (g->N / g->P < 2) ARG_FAIL("lattice too small");
+    return B200MC_OK;
+}
+
+int ring_alloc(RingStore* s)
+{
+    const size_t nv = (size_t)(s->g.L + 2 * s->g.H);
+    s->vec[0] = s->vec[1] = nullptr;
+    s->stage = nullptr;
+    CK(cudaMalloc(&s->vec[0], nv * sizeof(uint4)));
+    CK(cudaMalloc(&s->vec[1], nv * sizeof(uint4)));
+    s->stage_elems = 1 << 24;
+    if (s->stage_elems > s->g.N + 2 * s->g.P) s->stage_elems = s->g.N + 2 * s->g.P;
+    CK(cudaMalloc(&s->stage, (size_t)s->stage_elems * sizeof(int32_t)));
+    return B200MC_OK;
+}
+
+void ring_free(RingStore* s)
+{
+    cudaFree(s->vec[0]);
+    cudaFree(s->vec[1]);
+    cudaFree(s->stage);
+    s->vec[0] = s->vec[1] = nullptr;
+    s->stage = nullptr;
+}
+
+int ring_fill(RingStore* s, uint8_t value, cudaStream_t st)
+{
+    const size_t nv = (size_t)(s->g.L + 2 * s->g.H);
+    CK(cudaMemsetAsync(s->vec[0], value, nv * sizeof(uint4), st));
+    CK(cudaMemsetAsync(s->vec[1], value, nv * sizeof(uint4), st));
+    return B200MC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// halo refresh
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int64_t pos_mod(int64_t a, int64_t m)
+{
+    int64_t r = a % m;
+    return r < 0 ? r + m : r;
+}
+
+// value of ring site k (of this colour) read from its owning (lane, position)
+__device__ __forceinline__ uint8_t ring_site(const uint8_t* base, int64_t L, int64_t H, int64_t k)
+{
+    const int64_t b = k / L, p = k - b * L;
+    return base[(p + H) * 16 + b];
+}
+
+// generic, byte-granular: one thread per (dirty vector, lane).  Dirty vectors
+// are the 2H halo vectors and the tail positions [ptail, L).
+__global__ void ring_halo_generic_kernel(uint8_t* base, int64_t L, int64_t H, int64_t Nc,
+                                         int64_t ptail, int64_t v_begin, int64_t n_items)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items) return;
+    const int b = (int)(t & 15);
+    int64_t v = v_begin + (t >> 4);  // dirty-vector ordinal
+    int64_t p;
+    if (v < H) p = v - H;
+    else if (v < 2 * H) p = L + (v - H);
+    else p = ptail + (v - 2 * H);
+    const int64_t kraw = (int64_t)b * L + p;
+    if (p >= 0 && p < L && kraw < Nc) return;  // a real site: owned, not a copy
+    base[(p + H) * 16 + b] = ring_site(base, L, H, pos_mod(kraw, Nc));
+}
+
+// fast path (needs H <= L): one thread per halo vector; a halo vector is the
+// source vector with its lanes rotated by one, plus one or two patched lanes.
+__global__ void ring_halo_fast_kernel(uint4* vec, int64_t L, int64_t H, int64_t Nc)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= 2 * H) return;
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(vec);
+    if (v < H) {
+        // low halo, p = v - H < 0: lane b <- lane b-1 at p + L; lane 0 <- site Nc + p
+        const int64_t p = v - H;
+        const uint4 s = vec[p + L + H];
+        uint4 o;
+        o.w = __funnelshift_l(s.z, s.w, 8);
+        o.z = __funnelshift_l(s.y, s.z, 8);
+        o.y = __funnelshift_l(s.x, s.y, 8);
+        o.x = (s.x << 8) | ring_site(base, L, H, pos_mod(p, Nc));
+        vec[v] = o;
+    } else {
+        // high halo, p = L + (v - H): lane b <- lane b+1 at p - L; lanes 14, 15 patched
+        const int64_t p = L + (v - H);
+        const uint4 s = vec[p - L + H];
+        uint4 o;
+        o.x = __funnelshift_r(s.x, s.y, 8);
+        o.y = __funnelshift_r(s.y, s.z, 8);
+        o.z = __funnelshift_r(s.z, s.w, 8);
+        const uint32_t b14 = ring_site(base, L, H, pos_mod(14 * L + p, Nc));
+        const uint32_t b15 = ring_site(base, L, H, pos_mod(15 * L + p, Nc));
+        o.w = ((s.w >> 8) & 0x0000FFFFu) | (b14 << 16) | (b15 << 24);
+        vec[p + H] = o;
+    }
+}
+
+int ring_halo(RingStore* s, int colour, cudaStream_t st)
+{
+    const RingGeom& g = s->g;
+    uint8_t* base = reinterpret_cast<uint8_t*>(s->vec[colour]);
+    const int64_t ntail = g.L - g.ptail;
+    if (g.H <= g.L && g.ptail >= g.H) {
+        const int64_t nv = 2 * g.H;
+        ring_halo_fast_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(s->vec[colour], g.L, g.H, g.Nc);
+        if (ntail > 0) {
+            const int64_t n_items = ntail * 16;  // tail vectors are ordinals [2H, 2H + ntail)
+            ring_halo_generic_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(
+                base, g.L, g.H, g.Nc, g.ptail, 2 * g.H, n_items);
+        }
+    } else {
+        const int64_t n_items = (2 * g.H + ntail) * 16;
+        ring_halo_generic_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(base, g.L, g.H, g.Nc, g.ptail, 0, n_items);
+    }
+    CK(cudaGetLastError());
+    return B200MC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// import / export in the reference layout spins(1-P : N+P), int32
+// (src/ising3d_gpu_m.f90:232-236 `spins()` returns the raw array, halo included)
+// ---------------------------------------------------------------------------
+__global__ void ring_export_kernel(const uint8_t* a, const uint8_t* b, int64_t N, int64_t L,
+                                   int64_t H, int64_t P, int64_t j0, int64_t n, int32_t* out,
+                                   int map)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t j = j0 + t;           // element of spins(1-P : N+P), 0-based
+    const int64_t i = pos_mod(j - P, N);  // ring site
+    const int64_t k = i >> 1;
+    const uint8_t v = ring_site((i & 1) ? b : a, L, H, k);
+    out[t] = map == RING_MAP_PM1 ? 2 * (int32_t)v - 1 : (int32_t)v;
+}
+
+__global__ void ring_import_kernel(uint8_t* a, uint8_t* b, int64_t N, int64_t L, int64_t H,
+                                   int64_t i0, int64_t n, const int32_t* in, int map)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t i = i0 + t;  // ring site; in[] holds sites i0 .. i0+n-1
+    const int64_t k = i >> 1;
+    const int64_t lane = k / L, p = k - lane * L;
+    int32_t v = in[t];
+    if (map == RING_MAP_PM1) v = (v + 1) >> 1;
+    ((i & 1) ? b : a)[(p + H) * 16 + lane] = (uint8_t)v;
+}
+
+int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st)
+{
+    const RingGeom& g = s->g;
+    // interior only (the halo cells of the host array are ignored and rebuilt)
+    for (int64_t i0 = 0; i0 < g.N; i0 += s->stage_elems) {
+        const int64_t n = (g.N - i0 < s->stage_elems) ? g.N - i0 : s->stage_elems;
+        CK(cudaMemcpyAsync(s->stage, host + g.P + i0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        ring_import_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<uint8_t*>(s->vec[0]), reinterpret_cast<uint8_t*>(s->vec[1]), g.N, g.L,
+            g.H, i0, n, s->stage, (int)map);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+    }
+    int rc = ring_halo(s, 0, st);
+    if (rc) return rc;
+    return ring_halo(s, 1, st);
+}
+
+int ring_export_i32(RingStore* s, int32_t* host, RingValueMap map, cudaStream_t st)
+{
+    const RingGeom& g = s->g;
+    const int64_t total = g.N + 2 * g.P;
+    for (int64_t j0 = 0; j0 < total; j0 += s->stage_elems) {
+        const int64_t n = (total - j0 < s->stage_elems) ? total - j0 : s->stage_elems;
+        ring_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const uint8_t*>(s->vec[0]), reinterpret_cast<const uint8_t*>(s->vec[1]),
+            g.N, g.L, g.H, g.P, j0, n, s->stage, (int)map);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(host + j0, s->stage, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return B200MC_OK;
+}

@@ -1,0 +1,53 @@
+// Folded-ring storage shared by the helical models (Ising 2D, Ising 3D, clock).
+//
+// The reference stores a helical lattice as ONE linear array spins(1-P : N+P)
+// (P = nx in 2D, nx*ny in 3D) and colours sites by the parity of the linear
+// index (src/ising3d_gpu_m.f90:60-62,196; src/ising2d_gpu_m.f90:52-54,155).
+// With 0-based i = idx-1 the lattice is a ring of N sites, colour = i & 1,
+// colour-site index k = i >> 1 (Nc = N/2 per colour), and with nx = 2h+1,
+// nx*ny = 2g+1 the neighbours of colour-c site k are the OTHER colour's sites
+//      k-1+c, k+c, k+h+c, k-h-1+c, (k+g+c, k-g-1+c)           (mod Nc)
+//
+// B200 layout: one int8 per site, the two colours in separate arrays, and each
+// colour ring FOLDED into 16 byte-lanes of L = ceil(Nc/16) positions:
+//      site k  ->  lane b = k / L,  position p = k % L,
+// stored as byte b of the 128-bit vector p.  Every neighbour offset is then a
+// whole-vector offset: all loads are aligned LDG.128 and the byte-parallel
+// arithmetic never shifts data across lanes.  Lane wrap-around (position p+d
+// beyond L belongs to lane b+1, and lane 15 wraps to lane 0) is materialised
+// once per colour pass in H = max|offset| halo vectors on each side -- the
+// counterpart of the reference's "norishiro" cells (src/ising3d_gpu_m.f90:
+// 111-122).  If 16 does not divide Nc the last positions of the high lanes
+// hold no site; they are kept equal to the ring continuation (so they behave
+// as halo) and are masked out of the reductions.
+#pragma once
+#include "common.cuh"
+
+struct RingGeom {
+    int64_t N;       // sites on the ring
+    int64_t Nc;      // sites per colour
+    int64_t L;       // fold length = vectors per colour
+    int64_t H;       // halo vectors on each side
+    int64_t P;       // reference halo width (nx or nx*ny), for import/export
+    int64_t ptail;   // first position that holds a non-site lane (== L if none)
+    int64_t off[2][6];  // neighbour vector offsets per colour: x-,x+,y+,y-,z+,z-
+    int nnb;         // 4 (2D) or 6 (3D)
+};
+
+struct RingStore {
+    RingGeom g;
+    uint4* vec[2];   // [colour] -> (L + 2H) vectors; position p lives at index p + H
+    int32_t* stage;  // staging buffer for import/export
+    int64_t stage_elems;
+};
+
+enum RingValueMap { RING_MAP_IDENTITY = 0, RING_MAP_PM1 = 1 };  // PM1: stored 0/1 <-> -1/+1
+
+int ring_geom_init(RingGeom* g, int64_t nx, int64_t ny, int64_t nz /*0 for 2D*/);
+int ring_alloc(RingStore* s);
+void ring_free(RingStore* s);
+int ring_fill(RingStore* s, uint8_t value, cudaStream_t st);
+int ring_halo(RingStore* s, int colour, cudaStream_t st);
+// host int32 arrays in the reference layout spins(1-P : N+P)
+int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st);
+int ring_export_i32(RingStore* s, int32_t* host, RingValueMap map, cudaStream_t st);

@@ -1,0 +1,118 @@
+/* b200mc -- C ABI of the B200-native checkerboard spin Monte Carlo library
+ * (libb200mc.so, built from cuda_fortran_mc_simulation_spin_b200/csrc).
+ *
+ * This is the drop-in boundary for the hot path of
+ * osada-yum/CUDA_Fortran_MC_simulation_spin.  The reference has no FFI: its
+ * callers (the app/ *_relaxation.f90 programs) `use` a Fortran module and call type-bound
+ * procedures of a derived type.  Every entry point below replaces one such
+ * procedure (cited as file:line of /root/reference) and is what the
+ * ISO_C_BINDING shim modules in cuda_fortran_mc_simulation_spin_b200/fortran/
+ * bind.
+ *
+ * Conventions
+ *  - plain C types only; `void*` opaque handles own all device memory;
+ *  - every function returns 0 on success, non-zero on error (B200MC_ERR_*);
+ *    b200mc_last_error() returns the message of the last failure on the
+ *    calling thread.  The reference stores cuRAND/CUDA codes in a public
+ *    `*_stat` variable and never checks them (src/ising2d_gpu_m.f90:8); the
+ *    Fortran shims mirror our return code into that same variable;
+ *  - one handle is used by one host thread at a time;
+ *  - host arrays use the REFERENCE's layouts (halo cells included);
+ *  - `update` is asynchronous on the handle's stream; every function that
+ *    returns data to the host synchronises.
+ *  - there is no CPU fallback: without a CUDA device `create` fails.
+ */
+#ifndef B200MC_H
+#define B200MC_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+#pragma GCC visibility push(default)
+
+#define B200MC_OK 0
+#define B200MC_ERR_ARG 1
+#define B200MC_ERR_CUDA 2
+#define B200MC_ERR_STATE 3
+#define B200MC_ERR_UNSUPPORTED 4
+
+#define B200MC_METROPOLIS 0 /* the reference's only Ising update */
+#define B200MC_HEATBATH 1   /* north-star addition, no reference symbol */
+
+const char* b200mc_last_error(void);
+int b200mc_version(void);
+/* run the handle's kernels on a caller-provided CUDA stream (cudaStream_t as void*) */
+int b200mc_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]); /* device Philox, for KAT tests */
+
+/* ------------------------------------------------------------------------
+ * Ising 3D -- type(ising3d_gpu), src/ising3d_gpu_m.f90:15-48
+ * ------------------------------------------------------------------------ */
+/* init, :50-71.  Helical boundary; nx, ny odd and nz even are REQUIRED (the
+ * reference silently races otherwise) -> B200MC_ERR_ARG. */
+int b200mc_ising3d_create(void** h, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed);
+int b200mc_ising3d_destroy(void* h);
+int b200mc_ising3d_set_stream(void* h, void* cuda_stream);
+/* skip_curand, :72-77: n_skip counts uniforms; advances the draw counter by ceil(n_skip / nall) */
+int b200mc_ising3d_skip_curand(void* h, int64_t n_skip);
+int b200mc_ising3d_set_allup_spin(void* h);              /* :79-82 */
+int b200mc_ising3d_set_random_spin(void* h);             /* :84-100 */
+int b200mc_ising3d_set_kbt(void* h, double kbt);         /* :124-128 */
+int b200mc_ising3d_set_beta(void* h, double beta);       /* :130-135 (+ update_ws :138-172) */
+int b200mc_ising3d_set_method(void* h, int32_t method);  /* B200MC_METROPOLIS (default) | B200MC_HEATBATH */
+int b200mc_ising3d_update(void* h);                      /* one MCS, :174-206 */
+int b200mc_ising3d_update_n(void* h, int32_t n_sweeps);  /* n MCS back to back */
+/* one MCS reading uniforms from a host array randoms(1:nall) in the reference's
+ * index order instead of the built-in generator (parity / cuRAND-stream mode) */
+int b200mc_ising3d_update_with_randoms(void* h, const double* randoms);
+int b200mc_ising3d_calc_energy_sum(void* h, int64_t* e); /* :239-257 */
+int b200mc_ising3d_calc_magne_sum(void* h, int64_t* m);  /* :259-276 */
+int b200mc_ising3d_measure(void* h, int64_t* e, int64_t* m); /* both, one pass */
+/* spins(), :232-236: int32 0/1, layout spins(1-nxy : nall+nxy) -> nall + 2 nxy elements */
+int b200mc_ising3d_get_spins(void* h, int32_t* out);
+int b200mc_ising3d_set_spins(void* h, const int32_t* in); /* inverse (halo cells of `in` ignored) */
+int64_t b200mc_ising3d_nx(void* h);   /* :208-223 */
+int64_t b200mc_ising3d_ny(void* h);
+int64_t b200mc_ising3d_nz(void* h);
+int64_t b200mc_ising3d_nall(void* h);
+double b200mc_ising3d_kbt(void* h);   /* :224-227 */
+double b200mc_ising3d_beta(void* h);  /* :228-231 */
+/* host copy of ws(0:6, 0:1) as built by update_ws (:153-171): out[S + 7*s] */
+int b200mc_ising3d_get_ws(void* h, double out[14]);
+int b200mc_ising3d_sync(void* h);
+
+/* ------------------------------------------------------------------------
+ * Ising 2D -- type(ising2d_gpu), src/ising2d_gpu_m.f90:12-42
+ * ------------------------------------------------------------------------ */
+/* init, :44-61.  nx odd, ny even REQUIRED. */
+int b200mc_ising2d_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed);
+int b200mc_ising2d_destroy(void* h);
+int b200mc_ising2d_set_stream(void* h, void* cuda_stream);
+int b200mc_ising2d_skip_curand(void* h, int64_t n_skip); /* not in the 2D reference type; same meaning as 3D */
+int b200mc_ising2d_set_allup_spin(void* h);              /* :63-66 */
+int b200mc_ising2d_set_random_spin(void* h);             /* :68-84 */
+int b200mc_ising2d_set_kbt(void* h, double kbt);         /* :108-112 */
+int b200mc_ising2d_set_beta(void* h, double beta);       /* :114-119 (+ update_exparr :122-131) */
+int b200mc_ising2d_set_method(void* h, int32_t method);
+int b200mc_ising2d_update(void* h);                      /* :133-162 */
+int b200mc_ising2d_update_n(void* h, int32_t n_sweeps);
+int b200mc_ising2d_update_with_randoms(void* h, const double* randoms);
+int b200mc_ising2d_calc_energy_sum(void* h, int64_t* e); /* :198-212 */
+int b200mc_ising2d_calc_magne_sum(void* h, int64_t* m);  /* :214-228 */
+int b200mc_ising2d_measure(void* h, int64_t* e, int64_t* m);
+/* spins(), :184-188: int32 +1/-1, layout spins(1-nx : nall+nx) -> nall + 2 nx elements */
+int b200mc_ising2d_get_spins(void* h, int32_t* out);
+int b200mc_ising2d_set_spins(void* h, const int32_t* in);
+int64_t b200mc_ising2d_nx(void* h);
+int64_t b200mc_ising2d_ny(void* h);
+int64_t b200mc_ising2d_nall(void* h);
+double b200mc_ising2d_kbt(void* h);
+double b200mc_ising2d_beta(void* h);
+/* host copy of exparr(-8:8) as built by update_exparr (:126-130): out[d + 8] */
+int b200mc_ising2d_get_exparr(void* h, double out[17]);
+int b200mc_ising2d_sync(void* h);
+
+#pragma GCC visibility pop
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MC_H */

@@ -1,0 +1,139 @@
+/* ==========================================================================
+ * ORACLE -- TEST INFRASTRUCTURE ONLY.  NOT PART OF THE PRODUCT PATH.
+ *
+ * The RNG CONTRACT of the B200 build, restated on the CPU.
+ *
+ * The reference fills a device array with cuRAND XORWOW uniforms once per
+ * sweep and the kernels index it by site (src/ising3d_gpu_m.f90:179,203;
+ * src/ising2d_gpu_m.f90:138,159; src/clock_gpu_m.f90:188-189,211-212;
+ * src/xy2d_periodic_gpu_m.f90:355-356,382-384).  The B200 build never
+ * materialises that array: each uniform is a pure function
+ *      u = f(seed, draw, site[, stream])
+ * evaluated in registers with Philox4x32-10.  The functions below evaluate
+ * the SAME function on the CPU and write the array the reference would have
+ * read, in the reference's own index order, so that oracle.c (which consumes
+ * arrays exactly like the reference) and the CUDA kernels see one stream.
+ *
+ * Written independently of the device code (csrc/rng.cuh): agreement of the
+ * two is what the GPU parity tests establish.
+ * ========================================================================== */
+#include <math.h>
+#include <stdint.h>
+#include "philox.h"
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* key[1] domain tags */
+#define TAG_ISING 0x49534E47u /* "ISNG": accept uniforms of Ising 2D/3D     */
+#define TAG_INIT  0x494E4954u /* "INIT": set_random_spin of every model     */
+#define TAG_CLOCK 0x434C4F4Bu /* "CLOK": clock (helical) accept + proposal  */
+#define TAG_TORUS 0x544F5253u /* "TORS": periodic clock (tableall)          */
+#define TAG_XY    0x58593244u /* "XY2D": XY accept + candidate              */
+
+/* counter layout (all models):
+ *   c0 = block index, low 32      c1 = block index, high 32
+ *   c2 = draw index, low 32       c3 = draw[32..47] | colour << 16 | sub << 24
+ * "draw" counts generate calls (one per sweep / per set_random_spin);
+ * skip_curand(n) advances it. */
+static inline void mk_ctr(uint32_t c[4], uint64_t blk, uint64_t draw, uint32_t colour, uint32_t sub)
+{
+    c[0] = (uint32_t)blk;
+    c[1] = (uint32_t)(blk >> 32);
+    c[2] = (uint32_t)draw;
+    c[3] = (uint32_t)((draw >> 32) & 0xFFFFu) | (colour << 16) | (sub << 24);
+}
+
+/* --------------------------------------------------------------------------
+ * Ring models (Ising 2D, Ising 3D): the helical lattice is a ring of N sites
+ * with 0-based linear index i = idx - 1, colour = i & 1, colour-site index
+ * k = i >> 1 (Nc = N/2 per colour).  The build folds each colour ring into
+ * 16 byte-lanes of L = ceil(Nc/16) positions: lane = k / L, p = k % L, so one
+ * 128-bit vector (index p) holds 16 sites that are L apart.
+ *
+ * Accept uniform, 32-bit resolution, evaluated lazily on the GPU in two stages:
+ *   stage 1  R  = philox(ctr(p, draw, colour, 0), (seed, TAG_ISING)); 16 bytes
+ *            lane -> byte position m = BYTEPOS[lane];  b7 = byte_m(R) & 0x7F
+ *   stage 2  R2 = philox(ctr(p, draw, colour, 1 + (m >> 2)), same key)
+ *            low25 = R2[m & 3] & 0x1FFFFFF
+ *   U = b7 << 25 | low25 ;  u = (U + 1) * 2^-32  in (0, 1]
+ * (the GPU only evaluates stage 2 when b7 equals the top 7 bits of the
+ * acceptance threshold; the value is the same either way).
+ * -------------------------------------------------------------------------- */
+static const int BYTEPOS[16] = {0, 2, 4, 6, 1, 3, 5, 7, 8, 10, 12, 14, 9, 11, 13, 15};
+/* inverse view: byte position m of the Philox output serves lane
+ *   {0,4,1,5, 2,6,3,7, 8,12,9,13, 10,14,11,15}[m]                         */
+
+ORC_API int64_t orc_ring_fold_len(int64_t n_sites)
+{
+    int64_t nc = n_sites / 2;
+    return (nc + 15) / 16;
+}
+
+static inline uint32_t ring_U(uint32_t seed, uint32_t tag, uint64_t draw, int64_t L, int64_t i)
+{
+    uint32_t colour = (uint32_t)(i & 1);
+    int64_t k = i >> 1;
+    int lane = (int)(k / L);
+    uint64_t p = (uint64_t)(k % L);
+    int m = BYTEPOS[lane];
+    uint32_t key[2] = {seed, tag}, c[4], r[4], r2[4];
+    mk_ctr(c, p, draw, colour, 0);
+    orc_philox4x32_10(c, key, r);
+    uint32_t b7 = (r[m >> 2] >> (8 * (m & 3))) & 0x7Fu;
+    mk_ctr(c, p, draw, colour, 1u + (uint32_t)(m >> 2));
+    orc_philox4x32_10(c, key, r2);
+    uint32_t low25 = r2[m & 3] & 0x1FFFFFFu;
+    return (b7 << 25) | low25;
+}
+
+/* out[i] = u(site i), i = 0..N-1 (== randoms(idx), idx = i+1, of the reference) */
+ORC_API void orc_ising_uniforms(uint32_t seed, uint64_t draw, int64_t n_sites, double *out)
+{
+    const int64_t L = orc_ring_fold_len(n_sites);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_sites; ++i)
+        out[i] = ((double)ring_U(seed, TAG_ISING, draw, L, i) + 1.0) * 0x1p-32;
+}
+
+/* set_random_spin uniforms (one 32-bit uniform per site, ring models):
+ *   R = philox(ctr(p, draw, colour, lane >> 2), (seed, TAG_INIT)); U = R[lane & 3] */
+ORC_API void orc_ring_init_uniforms(uint32_t seed, uint64_t draw, int64_t n_sites, double *out)
+{
+    const int64_t L = orc_ring_fold_len(n_sites);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_sites; ++i) {
+        uint32_t colour = (uint32_t)(i & 1);
+        int64_t k = i >> 1;
+        int lane = (int)(k / L);
+        uint64_t p = (uint64_t)(k % L);
+        uint32_t key[2] = {seed, TAG_INIT}, c[4], r[4];
+        mk_ctr(c, p, draw, colour, (uint32_t)(lane >> 2));
+        orc_philox4x32_10(c, key, r);
+        out[i] = ((double)r[lane & 3] + 1.0) * 0x1p-32;
+    }
+}
+
+/* --------------------------------------------------------------------------
+ * Clock, helical ring (clock_gpu_m / clock_gpu_multi_m): two 32-bit uniforms
+ * per site and sweep, same fold.  For vector p, colour c, replica j:
+ *   R = philox(ctr(p, draw, c, lane >> 1), (seed, TAG_CLOCK + j))
+ *   accept   U_r = R[2*(lane & 1)]      -> randoms(idx)
+ *   proposal U_p = R[2*(lane & 1) + 1]  -> next_states(idx)
+ * -------------------------------------------------------------------------- */
+ORC_API void orc_clock_uniforms(uint32_t seed, uint64_t draw, int32_t replica, int64_t n_sites,
+                                double *randoms, double *next_states)
+{
+    const int64_t L = orc_ring_fold_len(n_sites);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_sites; ++i) {
+        uint32_t colour = (uint32_t)(i & 1);
+        int64_t k = i >> 1;
+        int lane = (int)(k / L);
+        uint64_t p = (uint64_t)(k % L);
+        uint32_t key[2] = {seed, TAG_CLOCK + (uint32_t)replica}, c[4], r[4];
+        mk_ctr(c, p, draw, colour, (uint32_t)(lane >> 1));
+        orc_philox4x32_10(c, key, r);
+        randoms[i] = ((double)r[2 * (lane & 1)] + 1.0) * 0x1p-32;
+        next_states[i] = ((double)r[2 * (lane & 1) + 1] + 1.0) * 0x1p-32;
+    }
+}

@@ -1,0 +1,211 @@
+"""GPU parity: Ising 2D / 3D CUDA path (through the C ABI) vs the CPU oracle.
+
+Bar (BASELINE.json north_star): spin configurations and the int64 energy /
+magnetisation sums are BIT-EXACT.  The oracle consumes the same uniforms the
+kernels generate in registers (oracle/rng_contract.c) or an explicit array
+(update_with_randoms), in the reference's own layouts (halo cells included).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+KBT3 = 4.51152          # app/ising3d_gpu_relaxation.f90:12
+KBT2 = 2.26918531421    # app/ising2d_gpu_relaxation.f90:11
+
+
+def _mods():
+    from cuda_fortran_mc_simulation_spin_b200 import ising2d_gpu_m, ising3d_gpu_m
+    return ising2d_gpu_m, ising3d_gpu_m
+
+
+def test_device_philox_kat():
+    """Random123 known-answer vectors for Philox4x32-10, on the device."""
+    import ctypes as C
+    from cuda_fortran_mc_simulation_spin_b200 import _lib
+    f = _lib.fn("b200mc_debug_philox", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
+    kats = [
+        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for ctr, key, want in kats:
+        c = np.array(ctr, dtype=np.uint32)
+        k = np.array(key, dtype=np.uint32)
+        o = np.zeros(4, dtype=np.uint32)
+        _lib.check(f(c.ctypes.data, k.ctypes.data, o.ctypes.data))
+        assert o.tolist() == want
+
+
+SHAPES3 = [(3, 3, 2), (5, 5, 4), (7, 5, 6), (31, 31, 30), (33, 31, 34), (63, 65, 64), (101, 101, 100)]
+
+
+@pytest.mark.parametrize("shape", SHAPES3)
+@pytest.mark.parametrize("start", ["allup", "random"])
+def test_ising3d_trajectory_bit_exact(oracle, shape, start):
+    _, i3 = _mods()
+    nx, ny, nz = shape
+    g = i3.ising3d_gpu().init(nx, ny, nz, KBT3, 42)
+    o = oracle.ising3d_gpu().init(nx, ny, nz, KBT3, 42)
+    assert np.array_equal(g.ws(), o.ws.reshape(2, 7))
+    if start == "random":
+        g.set_random_spin()
+        o.set_random_spin()
+    assert np.array_equal(g.spins(), o.spins())
+    for sweep in range(6):
+        g.update()
+        o.update()
+        assert np.array_equal(g.spins(), o.spins()), f"spins differ after sweep {sweep + 1}"
+        assert g.calc_energy_sum() == o.calc_energy_sum()
+        assert g.calc_magne_sum() == o.calc_magne_sum()
+        assert g.measure() == (o.calc_energy_sum(), o.calc_magne_sum())
+
+
+@pytest.mark.parametrize("shape", [(5, 4), (7, 6), (33, 32), (255, 256), (1001, 1000)])
+@pytest.mark.parametrize("start", ["allup", "random"])
+def test_ising2d_trajectory_bit_exact(oracle, shape, start):
+    i2, _ = _mods()
+    nx, ny = shape
+    g = i2.ising2d_gpu().init(nx, ny, KBT2, 42)
+    o = oracle.ising2d_gpu().init(nx, ny, KBT2, 42)
+    assert np.array_equal(g.exparr(), o.exparr)
+    if start == "random":
+        g.set_random_spin()
+        o.set_random_spin()
+    assert np.array_equal(g.spins(), o.spins())
+    for sweep in range(6):
+        g.update()
+        o.update()
+        assert np.array_equal(g.spins(), o.spins()), f"spins differ after sweep {sweep + 1}"
+        assert g.calc_energy_sum() == o.calc_energy_sum()
+        assert g.calc_magne_sum() == o.calc_magne_sum()
+
+
+def test_ising3d_update_with_randoms_edge_uniforms(oracle):
+    """explicit uniform arrays, including u == 1.0, u == table entries and tiny u"""
+    _, i3 = _mods()
+    nx, ny, nz = 15, 13, 12
+    g = i3.ising3d_gpu().init(nx, ny, nz, KBT3, 1)
+    o = oracle.ising3d_gpu().init(nx, ny, nz, KBT3, 1)
+    rng = np.random.default_rng(7)
+    g.set_random_spin(); o.set_random_spin()
+    for it in range(4):
+        u = 1.0 - rng.random(g.nall())           # (0, 1]
+        u[::17] = 1.0
+        u[1::19] = o.ws[0]                        # exactly on a table entry: accepted (<=)
+        u[2::23] = np.nextafter(o.ws[1], 2.0)     # just above: rejected
+        u[3::29] = 1e-300
+        g.update_with_randoms(u)
+        o.update(randoms=u)
+        assert np.array_equal(g.spins(), o.spins())
+        assert g.measure() == (o.calc_energy_sum(), o.calc_magne_sum())
+
+
+def test_ising2d_update_with_randoms(oracle):
+    i2, _ = _mods()
+    g = i2.ising2d_gpu().init(101, 100, KBT2, 3)
+    o = oracle.ising2d_gpu().init(101, 100, KBT2, 3)
+    rng = np.random.default_rng(11)
+    for it in range(4):
+        u = 1.0 - rng.random(g.nall())
+        u[::13] = 1.0
+        g.update_with_randoms(u)
+        o.update(randoms=u)
+        assert np.array_equal(g.spins(), o.spins())
+        assert g.calc_energy_sum() == o.calc_energy_sum()
+
+
+def test_spins_roundtrip_and_observables(oracle):
+    i2, i3 = _mods()
+    rng = np.random.default_rng(5)
+    g = i3.ising3d_gpu().init(21, 19, 18, KBT3, 9)
+    o = oracle.ising3d_gpu().init(21, 19, 18, KBT3, 9)
+    s = o.spins()
+    nxy = 21 * 19
+    s[nxy:-nxy] = rng.integers(0, 2, size=o.nall())
+    o.s[...] = s
+    oracle.lib().orc_ising3d_norishiro(21, 19, 18, o.s.ctypes.data)
+    g.set_spins(o.spins())
+    assert np.array_equal(g.spins(), o.spins())          # halo cells rebuilt identically
+    assert g.measure() == (o.calc_energy_sum(), o.calc_magne_sum())
+    g2 = i2.ising2d_gpu().init(51, 50, KBT2, 9)
+    o2 = oracle.ising2d_gpu().init(51, 50, KBT2, 9)
+    o2.s[51:-51] = rng.integers(0, 2, size=o2.nall()) * 2 - 1
+    oracle.lib().orc_ising2d_norishiro(51, 50, o2.s.ctypes.data)
+    g2.set_spins(o2.spins())
+    assert np.array_equal(g2.spins(), o2.spins())
+    assert g2.measure() == (o2.calc_energy_sum(), o2.calc_magne_sum())
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_heatbath_bit_exact(oracle, dim):
+    """heat-bath has no reference symbol: kernel vs our own oracle definition"""
+    i2, i3 = _mods()
+    if dim == 3:
+        g = i3.ising3d_gpu().init(31, 31, 30, KBT3, 42); o = oracle.ising3d_gpu().init(31, 31, 30, KBT3, 42)
+    else:
+        g = i2.ising2d_gpu().init(101, 100, KBT2, 42); o = oracle.ising2d_gpu().init(101, 100, KBT2, 42)
+    g.set_method(1)
+    for sweep in range(5):
+        g.update(); o.update_heatbath()
+        assert np.array_equal(g.spins(), o.spins())
+        assert g.measure() == (o.calc_energy_sum(), o.calc_magne_sum())
+
+
+def test_known_answers_small():
+    i2, i3 = _mods()
+    g = i3.ising3d_gpu().init(31, 31, 30, KBT3, 42)
+    n = g.nall()
+    assert g.measure() == (-3 * n, n)                    # all-up: E = -3N, M = N
+    g.set_beta(1e6)                                      # beta -> inf from all-up: nothing flips
+    g.update_n(3)
+    assert g.measure() == (-3 * n, n)
+    g.set_beta(0.0)                                      # beta = 0: every proposal accepted
+    g.update()
+    assert g.measure() == (-3 * n, -n)
+    g.update()
+    assert g.measure() == (-3 * n, n)
+    g2 = i2.ising2d_gpu().init(1001, 1000, KBT2, 42)
+    n2 = g2.nall()
+    assert g2.measure() == (-2 * n2, n2)
+    g2.set_beta(0.0); g2.update()
+    assert g2.measure() == (-2 * n2, -n2)
+
+
+def test_invalid_shapes_rejected():
+    from cuda_fortran_mc_simulation_spin_b200 import B200MCError
+    i2, i3 = _mods()
+    with pytest.raises(B200MCError):
+        i3.ising3d_gpu().init(1001, 1000, 1000, KBT3, 42)   # the app default races in the reference (Q1)
+    with pytest.raises(B200MCError):
+        i3.ising3d_gpu().init(32, 31, 30, KBT3, 42)
+    with pytest.raises(B200MCError):
+        i2.ising2d_gpu().init(1000, 1000, KBT2, 42)
+    with pytest.raises(B200MCError):
+        i2.ising2d_gpu().init(1001, 1001, KBT2, 42)
+
+
+def test_skip_curand_disjoint_streams(oracle):
+    _, i3 = _mods()
+    g = i3.ising3d_gpu().init(31, 31, 30, KBT3, 42)
+    o = oracle.ising3d_gpu().init(31, 31, 30, KBT3, 42)
+    g.skip_curand(5 * g.nall()); o.skip_draws(5)
+    g.update(); o.update()
+    assert np.array_equal(g.spins(), o.spins())
+
+
+def test_full_size_properties_headline():
+    """BASELINE config 2 at the reference-valid shape next to 1024^3: size-independent checks"""
+    _, i3 = _mods()
+    g = i3.ising3d_gpu().init(1023, 1023, 1024, KBT3, 42)
+    n = g.nall()
+    assert n == 1023 * 1023 * 1024
+    assert g.measure() == (-3 * n, n)
+    g.set_beta(0.0); g.update()
+    assert g.measure() == (-3 * n, -n)                    # every spin flipped exactly once
+    g.set_kbt(KBT3); g.set_allup_spin()
+    g.update_n(2)
+    e, m = g.measure()
+    assert -3 * n < e < -2 * n and 0.5 * n < m < n        # two sweeps from all-up at Tc
+    assert (e + 3 * n) % 4 == 0                            # E + 3N = 2X with X even on a bipartite ring? (X counts anti-aligned bonds)
