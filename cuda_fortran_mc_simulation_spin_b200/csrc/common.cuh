@@ -40,17 +40,25 @@ extern thread_local char g_b200mc_err[512];
 #define PHILOX_W0 0x9E3779B9u
 #define PHILOX_W1 0xBB67AE85u
 
-__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+__device__ __forceinline__ void mulwide(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi)
+{
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0,%1}, t;\n\t}"
+        : "=r"(lo), "=r"(hi)
+        : "r"(a), "r"(b));
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        unsigned long long p0 = (unsigned long long)PHILOX_M0 * c.x;
-        unsigned long long p1 = (unsigned long long)PHILOX_M1 * c.z;
+        uint32_t lo0, hi0, lo1, hi1;
+        mulwide(PHILOX_M0, c.x, lo0, hi0);
+        mulwide(PHILOX_M1, c.z, lo1, hi1);
         uint4 n;
-        n.x = (uint32_t)(p1 >> 32) ^ c.y ^ k.x;
-        n.y = (uint32_t)p1;
-        n.z = (uint32_t)(p0 >> 32) ^ c.w ^ k.y;
-        n.w = (uint32_t)p0;
+        n.x = hi1 ^ c.y ^ k.x;
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ k.y;
+        n.w = lo0;
         c = n;
         k.x += PHILOX_W0;
         k.y += PHILOX_W1;
@@ -67,7 +75,7 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
 #define TAG_TORUS 0x544F5253u
 #define TAG_XY 0x58593244u
 
-__host__ __device__ __forceinline__ uint4 mk_ctr(uint64_t blk, uint64_t draw, uint32_t colour,
+__device__ __forceinline__ uint4 mk_ctr(uint64_t blk, uint64_t draw, uint32_t colour,
                                                  uint32_t sub)
 {
     uint4 c;
@@ -92,18 +100,30 @@ __device__ __forceinline__ uint4 ld_other(const uint4* p)
                  : "l"(p));
     return r;
 }
-__device__ __forceinline__ uint4 ld_own(const uint4* p)
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ld_own(const uint4* p, uint64_t pol)
 {
     uint4 r;
-    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
+                 : "l"(p), "l"(pol));
     return r;
 }
-__device__ __forceinline__ void st_own(uint4* p, uint4 v)
+__device__ __forceinline__ void st_own(uint4* p, uint4 v, uint64_t pol)
 {
-    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
-                 "r"(v.y), "r"(v.z), "r"(v.w)
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
                  : "memory");
 }
 

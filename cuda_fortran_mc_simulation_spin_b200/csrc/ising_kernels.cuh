@@ -28,7 +28,7 @@ struct IsingTab {
 struct RingPassArgs {
     uint4* own;         // colour being updated, vector index 0 = position -H
     const uint4* oth;   // the other colour
-    int64_t nvec;       // owned positions (L)
+    int64_t nvec;       // owned positions (L); L + 2H < 2^31 is checked at create
     int64_t H;
     int64_t p0;         // global position of the first owned vector
     int64_t off[6];     // neighbour vector offsets for this colour
@@ -39,17 +39,35 @@ struct RingPassArgs {
 
 enum { METHOD_METROPOLIS = 0, METHOD_HEATBATH = 1 };
 
-// 8 sites: own words (w0 = lanes 0-3, w1 = lanes 4-7 of the group), neighbour
-// sums (s0, s1), random words (ra -> lanes (0,4,1,5), rb -> lanes (2,6,3,7)).
+// Deferred tie resolution.  A tie (b7 == thr >> 25) happens for 1 site in 128,
+// i.e. in almost every warp-iteration, so resolving it inline would make every
+// warp pay for a second Philox block.  Instead the (rare) lane that sees a tie
+// treats it as "reject", pushes a 32-byte record into a per-warp shared-memory
+// queue and goes on; when the queue is half full (and at kernel end) the warp
+// drains it with all 32 lanes busy, one record per lane, and patches the
+// accepted bytes in global memory.
+#define TQ_CAP 64
+struct TieRec {
+    uint32_t v;       // vector index (relative to the first owned vector)
+    uint32_t z[4];    // stage-1 compare words, byte == 0x80 marks a tie
+    uint32_t sps[2];  // per group: nibble-packed S | s << 3, in selector order
+    uint32_t pad;
+};
+
+// stage 1 for 8 sites: own words (w0 = lanes 0-3, w1 = lanes 4-7 of the group),
+// neighbour sums (s0, s1), random words (ra -> lanes (0,4,1,5), rb -> lanes (2,6,3,7)).
+// Returns the compare words zA, zB (bit 7 of a byte clear <=> accept) and leaves the
+// permuted own words in oA, oB.
 template <int METHOD>
-__device__ __forceinline__ void ising_group(uint32_t& w0, uint32_t& w1, uint32_t s0, uint32_t s1,
-                                            uint32_t ra, uint32_t rb, const IsingTab& tab,
-                                            const RingPassArgs& a, uint64_t pglob, int group)
+__device__ __forceinline__ void ising_stage1(uint32_t w0, uint32_t w1, uint32_t s0, uint32_t s1,
+                                             uint32_t ra, uint32_t rb, const IsingTab& tab,
+                                             uint32_t& sp, uint32_t& oA, uint32_t& oB,
+                                             uint32_t& zA, uint32_t& zB)
 {
-    const uint32_t sp = s0 + (s1 << 4);  // nibble-packed sums: byte j = S(lane j) | S(lane 4+j) << 4
+    sp = s0 + (s1 << 4);  // nibble-packed sums: byte j = S(lane j) | S(lane 4+j) << 4
     const uint32_t selA = sp, selB = sp >> 16;
-    const uint32_t oA = prmt(w0, w1, 0x5140u);  // lanes (0,4,1,5)
-    const uint32_t oB = prmt(w0, w1, 0x7362u);  // lanes (2,6,3,7)
+    oA = prmt(w0, w1, 0x5140u);  // lanes (0,4,1,5)
+    oB = prmt(w0, w1, 0x7362u);  // lanes (2,6,3,7)
     uint32_t tA, tB;
     if (METHOD == METHOD_METROPOLIS) {
         const uint32_t mA = oA * 0xFFu, mB = oB * 0xFFu;  // 0xFF where the spin is up
@@ -62,33 +80,14 @@ __device__ __forceinline__ void ising_group(uint32_t& w0, uint32_t& w1, uint32_t
         tB = prmt(tab.tlo[0], tab.thi[0], selB);
     }
     // z = b7 + 128 - T7 per byte (no carries: <= 255).  bit 7 clear <=> b7 < T7 <=> accept.
-    uint32_t zA = (ra & 0x7F7F7F7Fu) + tA;
-    uint32_t zB = (rb & 0x7F7F7F7Fu) + tB;
-    // ties (byte == 0x80 <=> b7 == T7): decide with 25 more bits.  Rare.
-    const uint32_t tieA = zero_byte_mask(zA ^ 0x80808080u);
-    const uint32_t tieB = zero_byte_mask(zB ^ 0x80808080u);
-    if (tieA | tieB) {
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            uint32_t tie = half ? tieB : tieA;
-            if (!tie) continue;
-            const uint32_t o = half ? oB : oA, sel = half ? selB : selA;
-            const uint4 r2 = philox4x32_10(mk_ctr(pglob, a.draw, a.colour, 1u + 2u * group + half),
-                                           make_uint2(a.seed, TAG_ISING));
-            const uint32_t rr[4] = {r2.x, r2.y, r2.z, r2.w};
-            uint32_t clr = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                // zero_byte_mask can flag a byte above a true zero byte; re-test exactly
-                const uint32_t zb = ((half ? zB : zA) >> (8 * j)) & 0xFFu;
-                if (zb != 0x80u) continue;
-                const uint32_t S = (sel >> (4 * j)) & 0xFu;
-                const uint32_t s = (METHOD == METHOD_METROPOLIS) ? ((o >> (8 * j)) & 1u) : 0u;
-                if ((rr[j] & 0x1FFFFFFu) < tab.low25[s][S & 7u]) clr |= 0x80u << (8 * j);
-            }
-            if (half) zB &= ~clr; else zA &= ~clr;
-        }
-    }
+    zA = (ra & 0x7F7F7F7Fu) + tA;
+    zB = (rb & 0x7F7F7F7Fu) + tB;
+}
+
+template <int METHOD>
+__device__ __forceinline__ void ising_finish(uint32_t& w0, uint32_t& w1, uint32_t oA, uint32_t oB,
+                                             uint32_t zA, uint32_t zB)
+{
     const uint32_t fA = (~zA >> 7) & 0x01010101u;
     const uint32_t fB = (~zB >> 7) & 0x01010101u;
     uint32_t nA, nB;
@@ -98,29 +97,102 @@ __device__ __forceinline__ void ising_group(uint32_t& w0, uint32_t& w1, uint32_t
     w1 = prmt(nA, nB, 0x7531u);
 }
 
+template <int METHOD>
+__device__ __noinline__ void ising_drain(uint4 (*q)[2], uint32_t* cnt, uint4* own, const RingPassArgs& a,
+                                         const IsingTab& tab)
+{
+    __syncwarp();
+    const uint32_t n = *cnt;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t r = lane; r < n; r += 32) {
+        const uint4 r0 = q[r][0], r1 = q[r][1];
+        const uint32_t v = r0.x;
+        const uint32_t z[4] = {r0.y, r0.z, r0.w, r1.x};
+        const uint32_t sps[2] = {r1.y, r1.z};
+        uint8_t* bytes = reinterpret_cast<uint8_t*>(own + v);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t t = z[w] ^ 0x80808080u;
+            const uint32_t e = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;  // exact zero bytes
+            if (!e) continue;
+            const uint4 R = philox4x32_10(mk_ctr((uint64_t)(a.p0 + v), a.draw, a.colour, 1u + w),
+                                          make_uint2(a.seed, TAG_ISING));
+            const uint32_t rr[4] = {R.x, R.y, R.z, R.w};
+            const uint32_t sel = (w & 1) ? (sps[w >> 1] >> 16) : sps[w >> 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!((e >> (8 * j + 7)) & 1u)) continue;
+                const uint32_t nib = (sel >> (4 * j)) & 0xFu;
+                const uint32_t S = nib & 7u;
+                const uint32_t s = (METHOD == METHOD_METROPOLIS) ? (nib >> 3) : 0u;
+                if ((rr[j] & 0x1FFFFFFu) < tab.low25[s][S]) {
+                    const int m = 4 * w + j;  // byte position in the Philox block -> lane
+                    const int lb = (m & 8) | ((m & 7) >> 1) | ((m & 1) << 2);
+                    bytes[lb] = (METHOD == METHOD_METROPOLIS) ? (uint8_t)(s ^ 1u) : (uint8_t)1;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *cnt = 0;
+    __syncwarp();
+}
+
 template <int NNB, int METHOD>
 __global__ void __launch_bounds__(256)
 ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant__ IsingTab tab)
 {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < a.nvec; v += stride) {
-        const int64_t q = v + a.H;
-        uint4 o = ld_own(a.own + q);
-        uint4 n = ld_other(a.oth + q + a.off[0]);
-        uint4 m = ld_other(a.oth + q + a.off[1]);
-        uint4 S = make_uint4(n.x + m.x, n.y + m.y, n.z + m.z, n.w + m.w);
+    __shared__ uint4 tq[8][TQ_CAP][2];
+    __shared__ uint32_t tq_cnt[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) tq_cnt[warp] = 0;
+    __syncwarp();
+    const uint64_t pol = l2_policy_evict_first();
+    uint4* own = a.own + a.H;
+    const uint4* oth = a.oth + a.H;
+    const int nvec = (int)a.nvec;
+    const int stride = gridDim.x * blockDim.x;
+    int off[NNB];
 #pragma unroll
-        for (int j = 2; j < NNB; j += 2) {
-            n = ld_other(a.oth + q + a.off[j]);
-            m = ld_other(a.oth + q + a.off[j + 1]);
-            S.x += n.x + m.x; S.y += n.y + m.y; S.z += n.z + m.z; S.w += n.w + m.w;
+    for (int j = 0; j < NNB; ++j) off[j] = (int)a.off[j];
+    const uint2 key = make_uint2(a.seed, TAG_ISING);
+
+    for (int vb = blockIdx.x * blockDim.x + warp * 32; vb < nvec; vb += stride) {
+        const int v = vb + lane;
+        if (v < nvec) {
+            const uint4* po = oth + v;
+            uint4 o = ld_own(own + v, pol);
+            uint4 nb[NNB];
+#pragma unroll
+            for (int j = 0; j < NNB; ++j) nb[j] = ld_other(po + off[j]);
+            const uint64_t pglob = (uint64_t)(a.p0 + v);
+            const uint4 r = philox4x32_10(mk_ctr(pglob, a.draw, a.colour, 0u), key);
+            uint4 S = make_uint4(nb[0].x + nb[1].x, nb[0].y + nb[1].y, nb[0].z + nb[1].z, nb[0].w + nb[1].w);
+#pragma unroll
+            for (int j = 2; j < NNB; ++j) { S.x += nb[j].x; S.y += nb[j].y; S.z += nb[j].z; S.w += nb[j].w; }
+            uint32_t sp0, sp1, oA0, oB0, oA1, oB1, zA0, zB0, zA1, zB1;
+            ising_stage1<METHOD>(o.x, o.y, S.x, S.y, r.x, r.y, tab, sp0, oA0, oB0, zA0, zB0);
+            ising_stage1<METHOD>(o.z, o.w, S.z, S.w, r.z, r.w, tab, sp1, oA1, oB1, zA1, zB1);
+            const uint32_t tie = zero_byte_mask(zA0 ^ 0x80808080u) | zero_byte_mask(zB0 ^ 0x80808080u) |
+                                 zero_byte_mask(zA1 ^ 0x80808080u) | zero_byte_mask(zB1 ^ 0x80808080u);
+            if (tie) {  // rare per lane: park the record, resolve later (ties count as reject below)
+                uint32_t sps0 = sp0, sps1 = sp1;
+                if (METHOD == METHOD_METROPOLIS) {
+                    sps0 += 8u * (o.x + (o.y << 4));
+                    sps1 += 8u * (o.z + (o.w << 4));
+                }
+                const uint32_t slot = atomicAdd(&tq_cnt[warp], 1u);
+                tq[warp][slot][0] = make_uint4((uint32_t)v, zA0, zB0, zA1);
+                tq[warp][slot][1] = make_uint4(zB1, sps0, sps1, 0u);
+            }
+            ising_finish<METHOD>(o.x, o.y, oA0, oB0, zA0, zB0);
+            ising_finish<METHOD>(o.z, o.w, oA1, oB1, zA1, zB1);
+            st_own(own + v, o, pol);
         }
-        const uint64_t pglob = (uint64_t)(a.p0 + v);
-        const uint4 r = philox4x32_10(mk_ctr(pglob, a.draw, a.colour, 0u), make_uint2(a.seed, TAG_ISING));
-        ising_group<METHOD>(o.x, o.y, S.x, S.y, r.x, r.y, tab, a, pglob, 0);
-        ising_group<METHOD>(o.z, o.w, S.z, S.w, r.z, r.w, tab, a, pglob, 1);
-        st_own(a.own + q, o);
+        __syncwarp();
+        if (tq_cnt[warp] > TQ_CAP - 32) ising_drain<METHOD>(tq[warp], &tq_cnt[warp], own, a, tab);
     }
+    ising_drain<METHOD>(tq[warp], &tq_cnt[warp], own, a, tab);
 }
 
 // ---------------------------------------------------------------------------

@@ -207,5 +207,5 @@ def test_full_size_properties_headline():
     g.set_kbt(KBT3); g.set_allup_spin()
     g.update_n(2)
     e, m = g.measure()
-    assert -3 * n < e < -2 * n and 0.5 * n < m < n        # two sweeps from all-up at Tc
-    assert (e + 3 * n) % 4 == 0                            # E + 3N = 2X with X even on a bipartite ring? (X counts anti-aligned bonds)
+    assert -3 * n < e < -n and 0.5 * n < m < n            # two sweeps from all-up at Tc
+    assert (e + 3 * n) % 4 == 0                            # E = -3N + 2X, and X (anti-aligned bonds) is even: every flip toggles 6 bonds
