@@ -2,6 +2,7 @@
 // Reference: type(ising2d_gpu) src/ising2d_gpu_m.f90:12-42,
 //            type(ising3d_gpu) src/ising3d_gpu_m.f90:15-48.
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include "../../include/b200mc.h"
 #include "ising_kernels.cuh"
@@ -26,6 +27,8 @@ struct Ising {
     unsigned long long* d_acc;  // [X, sum s]
     int64_t* d_off1;            // colour-1 offsets for the measure kernel
     double* d_randoms;
+    unsigned int* d_ticket;
+    int tune;  // debug knobs from env B200MC_TUNE: bit0 = static grid-stride (no ticket)
     int grid;
     bool alive;
 };
@@ -88,6 +91,7 @@ int build_tables(Ising* m)
             m->tab.low25[s][S] = (uint32_t)(thr & 0x1FFFFFFu);
             m->tabf.w[s * 8 + S] = w;
         }
+    for (int r = 0; r < 10; ++r) m->tab.rk0[r] = m->seed + (uint32_t)r * PHILOX_W0;
     for (int s = 0; s < 2; ++s) {
         m->tab.tlo[s] = tb[s][0] | (tb[s][1] << 8) | (tb[s][2] << 16) | ((uint32_t)tb[s][3] << 24);
         m->tab.thi[s] = tb[s][4] | (tb[s][5] << 8) | (tb[s][6] << 16) | ((uint32_t)tb[s][7] << 24);
@@ -109,6 +113,11 @@ int launch_pass(Ising* m, int colour)
     a.seed = m->seed;
     a.colour = (uint32_t)colour;
     a.draw = m->draw;
+    a.ticket = nullptr;
+    if (!(m->tune & 1) && g.L > (int64_t)m->grid * 256 * 4) {
+        a.ticket = m->d_ticket;
+        CK(cudaMemsetAsync(m->d_ticket, 0, sizeof(unsigned int), m->stream));
+    }
     if (m->method == METHOD_METROPOLIS)
         ising_pass_kernel<NNB, METHOD_METROPOLIS><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
     else
@@ -142,6 +151,7 @@ int launch_pass_randoms(Ising* m, int colour)
     a.seed = m->seed;
     a.colour = (uint32_t)colour;
     a.draw = m->draw;
+    a.ticket = nullptr;
     const unsigned grid = (unsigned)((g.L + 255) / 256);
     if (m->method == METHOD_METROPOLIS)
         ising_pass_randoms_kernel<NNB, METHOD_METROPOLIS><<<grid, 256, 0, m->stream>>>(a, m->tabf, m->d_randoms, g.L, g.Nc);
@@ -183,13 +193,15 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     Ising* m = new (std::nothrow) Ising();
     if (!m) ARG_FAIL("out of host memory");
     m->ndim = ndim; m->nx = nx; m->ny = ny; m->nz = ndim == 3 ? nz : 0;
-    m->stream = 0; m->d_acc = nullptr; m->d_off1 = nullptr; m->d_randoms = nullptr;
+    m->stream = 0; m->d_acc = nullptr; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
+    { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; }
     m->method = METHOD_METROPOLIS; m->seed = (uint32_t)iseed; m->draw = 0; m->alive = true;
     int rc = ring_geom_init(&m->st.g, nx, ny, m->nz);
     if (rc) { delete m; return rc; }
     rc = ring_alloc(&m->st);
     if (rc) { ring_free(&m->st); delete m; return rc; }
-    if (cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+    if (cudaMalloc(&m->d_ticket, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&m->d_off1, 6 * sizeof(int64_t)) != cudaSuccess) {
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed");
         ring_free(&m->st); cudaFree(m->d_acc); cudaFree(m->d_off1); delete m; return B200MC_ERR_CUDA;
@@ -220,6 +232,7 @@ int destroy(Ising* m)
     cudaFree(m->d_acc);
     cudaFree(m->d_off1);
     cudaFree(m->d_randoms);
+    cudaFree(m->d_ticket);
     delete m;
     return B200MC_OK;
 }

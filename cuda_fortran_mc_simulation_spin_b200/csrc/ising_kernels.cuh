@@ -23,7 +23,28 @@
 struct IsingTab {
     uint32_t tlo[2], thi[2];  // [s]: bytes T'(S) for S = 0..3 / S = 4..7
     uint32_t low25[2][8];     // [s][S]
+    uint32_t rk0[10];         // Philox round keys seed + r*W0 (uniform: precomputed on the host)
 };
+
+// Philox4x32-10 with the key schedule supplied as constants (rk0 from the host,
+// k1 = tag + r*W1 folded at compile time): 20 IMAD.WIDE + 20 LOP3 per block.
+template <uint32_t TAG>
+__device__ __forceinline__ uint4 philox_rk(uint4 c, const uint32_t (&rk0)[10])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t lo0, hi0, lo1, hi1;
+        mulwide(PHILOX_M0, c.x, lo0, hi0);
+        mulwide(PHILOX_M1, c.z, lo1, hi1);
+        uint4 n;
+        n.x = hi1 ^ c.y ^ rk0[r];
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ (TAG + (uint32_t)r * PHILOX_W1);
+        n.w = lo0;
+        c = n;
+    }
+    return c;
+}
 
 struct RingPassArgs {
     uint4* own;         // colour being updated, vector index 0 = position -H
@@ -35,6 +56,7 @@ struct RingPassArgs {
     uint32_t seed;
     uint32_t colour;
     uint64_t draw;
+    unsigned int* ticket;  // work counter for ordered block scheduling (nullptr: static grid-stride)
 };
 
 enum { METHOD_METROPOLIS = 0, METHOD_HEATBATH = 1 };
@@ -97,6 +119,14 @@ __device__ __forceinline__ void ising_finish(uint32_t& w0, uint32_t& w1, uint32_
     w1 = prmt(nA, nB, 0x7531u);
 }
 
+// exact per-byte "== 0x80" test -> 4-bit mask
+__device__ __forceinline__ uint32_t tie_bits(uint32_t z)
+{
+    const uint32_t t = z ^ 0x80808080u;
+    const uint32_t e = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;  // 0x80 where byte == 0
+    return ((e >> 7) * 0x00204081u) >> 21 & 0xFu;  // gather bits 0,8,16,24 -> 0..3
+}
+
 template <int METHOD>
 __device__ __noinline__ void ising_drain(uint4 (*q)[2], uint32_t* cnt, uint4* own, const RingPassArgs& a,
                                          const IsingTab& tab)
@@ -107,29 +137,24 @@ __device__ __noinline__ void ising_drain(uint4 (*q)[2], uint32_t* cnt, uint4* ow
     for (uint32_t r = lane; r < n; r += 32) {
         const uint4 r0 = q[r][0], r1 = q[r][1];
         const uint32_t v = r0.x;
-        const uint32_t z[4] = {r0.y, r0.z, r0.w, r1.x};
-        const uint32_t sps[2] = {r1.y, r1.z};
         uint8_t* bytes = reinterpret_cast<uint8_t*>(own + v);
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const uint32_t t = z[w] ^ 0x80808080u;
-            const uint32_t e = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;  // exact zero bytes
-            if (!e) continue;
-            const uint4 R = philox4x32_10(mk_ctr((uint64_t)(a.p0 + v), a.draw, a.colour, 1u + w),
-                                          make_uint2(a.seed, TAG_ISING));
-            const uint32_t rr[4] = {R.x, R.y, R.z, R.w};
-            const uint32_t sel = (w & 1) ? (sps[w >> 1] >> 16) : sps[w >> 1];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (!((e >> (8 * j + 7)) & 1u)) continue;
-                const uint32_t nib = (sel >> (4 * j)) & 0xFu;
-                const uint32_t S = nib & 7u;
-                const uint32_t s = (METHOD == METHOD_METROPOLIS) ? (nib >> 3) : 0u;
-                if ((rr[j] & 0x1FFFFFFu) < tab.low25[s][S]) {
-                    const int m = 4 * w + j;  // byte position in the Philox block -> lane
-                    const int lb = (m & 8) | ((m & 7) >> 1) | ((m & 1) << 2);
-                    bytes[lb] = (METHOD == METHOD_METROPOLIS) ? (uint8_t)(s ^ 1u) : (uint8_t)1;
-                }
+        // 16-bit tie mask, bit m = byte position m of the stage-1 Philox block
+        uint32_t mask = tie_bits(r0.y) | (tie_bits(r0.z) << 4) | (tie_bits(r0.w) << 8) | (tie_bits(r1.x) << 12);
+        const uint64_t pglob = (uint64_t)(a.p0 + v);
+        while (mask) {
+            const int m = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int w = m >> 2, j = m & 3;
+            uint4 c = mk_ctr(pglob, a.draw, a.colour, 1u + w);
+            const uint4 R = philox_rk<TAG_ISING>(c, tab.rk0);
+            const uint32_t rj = j == 0 ? R.x : j == 1 ? R.y : j == 2 ? R.z : R.w;
+            const uint32_t spw = (w >> 1) ? r1.z : r1.y;
+            const uint32_t nib = (spw >> (16 * (w & 1) + 4 * j)) & 0xFu;
+            const uint32_t S = nib & 7u;
+            const uint32_t s = (METHOD == METHOD_METROPOLIS) ? (nib >> 3) : 0u;
+            if ((rj & 0x1FFFFFFu) < tab.low25[s][S]) {
+                const int lb = (m & 8) | ((m & 7) >> 1) | ((m & 1) << 2);  // byte position -> lane
+                bytes[lb] = (METHOD == METHOD_METROPOLIS) ? (uint8_t)(s ^ 1u) : (uint8_t)1;
             }
         }
     }
@@ -144,29 +169,39 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
 {
     __shared__ uint4 tq[8][TQ_CAP][2];
     __shared__ uint32_t tq_cnt[8];
+    __shared__ int s_vb[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) tq_cnt[warp] = 0;
+    uint4 (*myq)[2] = tq[warp];
+    uint32_t* mycnt = &tq_cnt[warp];
+    if (lane == 0) *mycnt = 0;
     __syncwarp();
     const uint64_t pol = l2_policy_evict_first();
     uint4* own = a.own + a.H;
-    const uint4* oth = a.oth + a.H;
     const int nvec = (int)a.nvec;
-    const int stride = gridDim.x * blockDim.x;
-    int off[NNB];
+    const uint4* pn[NNB];
 #pragma unroll
-    for (int j = 0; j < NNB; ++j) off[j] = (int)a.off[j];
-    const uint2 key = make_uint2(a.seed, TAG_ISING);
-
-    for (int vb = blockIdx.x * blockDim.x + warp * 32; vb < nvec; vb += stride) {
-        const int v = vb + lane;
+    for (int j = 0; j < NNB; ++j) pn[j] = a.oth + (a.H + a.off[j]);
+    const bool ordered = a.ticket != nullptr;
+    const int stride = gridDim.x * blockDim.x;
+    // ordered mode: blocks take 256-vector chunks from a global counter so that all resident
+    // blocks work inside one narrow window of the lattice (keeps the z-neighbour planes in L2)
+    int vb0 = blockIdx.x * blockDim.x;
+    int it = 0;
+    if (ordered) {
+        if (threadIdx.x == 0) s_vb[0] = (int)atomicAdd(a.ticket, 256u);
+        __syncthreads();
+        vb0 = s_vb[0];
+    }
+    while (vb0 < nvec) {
+        if (ordered && threadIdx.x == 0) s_vb[(it + 1) & 1] = (int)atomicAdd(a.ticket, 256u);  // prefetch next chunk
+        const int v = vb0 + warp * 32 + lane;
         if (v < nvec) {
-            const uint4* po = oth + v;
             uint4 o = ld_own(own + v, pol);
             uint4 nb[NNB];
 #pragma unroll
-            for (int j = 0; j < NNB; ++j) nb[j] = ld_other(po + off[j]);
+            for (int j = 0; j < NNB; ++j) nb[j] = ld_other(pn[j] + v);
             const uint64_t pglob = (uint64_t)(a.p0 + v);
-            const uint4 r = philox4x32_10(mk_ctr(pglob, a.draw, a.colour, 0u), key);
+            const uint4 r = philox_rk<TAG_ISING>(mk_ctr(pglob, a.draw, a.colour, 0u), tab.rk0);
             uint4 S = make_uint4(nb[0].x + nb[1].x, nb[0].y + nb[1].y, nb[0].z + nb[1].z, nb[0].w + nb[1].w);
 #pragma unroll
             for (int j = 2; j < NNB; ++j) { S.x += nb[j].x; S.y += nb[j].y; S.z += nb[j].z; S.w += nb[j].w; }
@@ -181,18 +216,25 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
                     sps0 += 8u * (o.x + (o.y << 4));
                     sps1 += 8u * (o.z + (o.w << 4));
                 }
-                const uint32_t slot = atomicAdd(&tq_cnt[warp], 1u);
-                tq[warp][slot][0] = make_uint4((uint32_t)v, zA0, zB0, zA1);
-                tq[warp][slot][1] = make_uint4(zB1, sps0, sps1, 0u);
+                const uint32_t slot = atomicAdd(mycnt, 1u);
+                myq[slot][0] = make_uint4((uint32_t)v, zA0, zB0, zA1);
+                myq[slot][1] = make_uint4(zB1, sps0, sps1, 0u);
             }
             ising_finish<METHOD>(o.x, o.y, oA0, oB0, zA0, zB0);
             ising_finish<METHOD>(o.z, o.w, oA1, oB1, zA1, zB1);
             st_own(own + v, o, pol);
         }
         __syncwarp();
-        if (tq_cnt[warp] > TQ_CAP - 32) ising_drain<METHOD>(tq[warp], &tq_cnt[warp], own, a, tab);
+        if (*mycnt > TQ_CAP - 32) ising_drain<METHOD>(myq, mycnt, own, a, tab);
+        ++it;
+        if (ordered) {
+            __syncthreads();
+            vb0 = s_vb[it & 1];
+        } else {
+            vb0 += stride;
+        }
     }
-    ising_drain<METHOD>(tq[warp], &tq_cnt[warp], own, a, tab);
+    ising_drain<METHOD>(myq, mycnt, own, a, tab);
 }
 
 // ---------------------------------------------------------------------------
