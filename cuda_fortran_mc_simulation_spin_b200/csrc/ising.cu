@@ -80,22 +80,30 @@ int build_tables(Ising* m)
         }
     }
     // thresholds: u <= w  <=>  U < thr, thr = floor(w 2^32)
-    uint8_t tb[2][8];
-    for (int s = 0; s < 2; ++s)
-        for (int S = 0; S < 8; ++S) {
-            const double w = m->w[s * 8 + S];
-            uint64_t thr = (uint64_t)floor(w * 4294967296.0);
-            if (thr > 4294967296ull) thr = 4294967296ull;
-            const uint32_t t7 = (uint32_t)(thr >> 25);  // 0..128
-            tb[s][S] = (uint8_t)(128u - t7);
-            m->tab.low25[s][S] = (uint32_t)(thr & 0x1FFFFFFu);
-            m->tabf.w[s * 8 + S] = w;
+    // kernel table index: Metropolis k' = number of aligned neighbours (w(S, s) = w(k') for the
+    // zero-field model: verified below), heat-bath S
+    const int z = m->ndim == 3 ? 6 : 4;
+    uint8_t tb[8];
+    for (int idx = 0; idx < 8; ++idx) {
+        double w = 0.0;
+        if (idx <= z) {
+            if (m->method == METHOD_METROPOLIS) {
+                w = m->w[1 * 8 + idx];                      // s = 1: k' = S
+                if (m->w[0 * 8 + (z - idx)] != w) ARG_FAIL("internal: acceptance table is not symmetric");
+            } else {
+                w = m->w[idx];
+            }
         }
-    for (int r = 0; r < 10; ++r) m->tab.rk0[r] = m->seed + (uint32_t)r * PHILOX_W0;
-    for (int s = 0; s < 2; ++s) {
-        m->tab.tlo[s] = tb[s][0] | (tb[s][1] << 8) | (tb[s][2] << 16) | ((uint32_t)tb[s][3] << 24);
-        m->tab.thi[s] = tb[s][4] | (tb[s][5] << 8) | (tb[s][6] << 16) | ((uint32_t)tb[s][7] << 24);
+        uint64_t thr = (uint64_t)floor(w * 4294967296.0);
+        if (thr > 4294967296ull) thr = 4294967296ull;
+        const uint32_t t7 = (uint32_t)(thr >> 25);  // 0..128
+        tb[idx] = (uint8_t)(128u - t7);
+        m->tab.low25[idx] = (uint32_t)(thr & 0x1FFFFFFu);
     }
+    for (int i = 0; i < 16; ++i) m->tabf.w[i] = m->w[i];
+    for (int r = 0; r < 10; ++r) m->tab.rk0[r] = m->seed + (uint32_t)r * PHILOX_W0;
+    m->tab.tlo = tb[0] | (tb[1] << 8) | (tb[2] << 16) | ((uint32_t)tb[3] << 24);
+    m->tab.thi = tb[4] | (tb[5] << 8) | (tb[6] << 16) | ((uint32_t)tb[7] << 24);
     return B200MC_OK;
 }
 
@@ -118,10 +126,13 @@ int launch_pass(Ising* m, int colour)
         a.ticket = m->d_ticket;
         CK(cudaMemsetAsync(m->d_ticket, 0, sizeof(unsigned int), m->stream));
     }
-    if (m->method == METHOD_METROPOLIS)
-        ising_pass_kernel<NNB, METHOD_METROPOLIS><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
-    else
-        ising_pass_kernel<NNB, METHOD_HEATBATH><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+    if (m->method == METHOD_METROPOLIS) {
+        if (a.ticket) ising_pass_kernel<NNB, METHOD_METROPOLIS, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+        else ising_pass_kernel<NNB, METHOD_METROPOLIS, false><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+    } else {
+        if (a.ticket) ising_pass_kernel<NNB, METHOD_HEATBATH, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+        else ising_pass_kernel<NNB, METHOD_HEATBATH, false><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+    }
     CK(cudaGetLastError());
     return ring_halo(&m->st, colour, m->stream);
 }
@@ -211,8 +222,8 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     int dev = 0, sms = 148, occ = 4;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (ndim == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ising_pass_kernel<6, METHOD_METROPOLIS>, 256, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ising_pass_kernel<4, METHOD_METROPOLIS>, 256, 0);
+    if (ndim == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ising_pass_kernel<6, METHOD_METROPOLIS, true>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ising_pass_kernel<4, METHOD_METROPOLIS, true>, 256, 0);
     if (occ < 1) occ = 1;
     int64_t need = (m->st.g.L + 255) / 256;
     m->grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);

@@ -21,10 +21,13 @@
 #include "common.cuh"
 
 struct IsingTab {
-    uint32_t tlo[2], thi[2];  // [s]: bytes T'(S) for S = 0..3 / S = 4..7
-    uint32_t low25[2][8];     // [s][S]
-    uint32_t rk0[10];         // Philox round keys seed + r*W0 (uniform: precomputed on the host)
+    uint32_t tlo, thi;     // bytes T'(idx) for idx = 0..3 / 4..7
+    uint32_t low25[8];     // thr & (2^25-1) per idx
+    uint32_t rk0[10];      // Philox round keys seed + r*W0 (uniform: precomputed on the host)
 };
+// Table index: METROPOLIS idx = number of neighbours ALIGNED with the site's own spin
+// (k' = s ? S : nnb - S; the zero-field acceptance ws(S, s) only depends on it),
+// HEATBATH idx = S (number of up neighbours).
 
 // Philox4x32-10 with the key schedule supplied as constants (rk0 from the host,
 // k1 = tag + r*W1 folded at compile time): 20 IMAD.WIDE + 20 LOP3 per block.
@@ -66,41 +69,47 @@ enum { METHOD_METROPOLIS = 0, METHOD_HEATBATH = 1 };
 // warp pay for a second Philox block.  Instead the (rare) lane that sees a tie
 // treats it as "reject", pushes a 32-byte record into a per-warp shared-memory
 // queue and goes on; when the queue is half full (and at kernel end) the warp
-// drains it with all 32 lanes busy, one record per lane, and patches the
-// accepted bytes in global memory.
+// drains it with all 32 lanes busy and patches the accepted bytes in global memory.
 #define TQ_CAP 64
-struct TieRec {
-    uint32_t v;       // vector index (relative to the first owned vector)
-    uint32_t z[4];    // stage-1 compare words, byte == 0x80 marks a tie
-    uint32_t sps[2];  // per group: nibble-packed S | s << 3, in selector order
-    uint32_t pad;
-};
+
+// keep a value in a register: stops the compiler from rematerialising address
+// arithmetic from kernel parameters inside the hot loop
+template <typename T>
+__device__ __forceinline__ void pin64(T*& p) { asm volatile("" : "+l"(p)); }
+__device__ __forceinline__ void pin32(uint32_t& x) { asm volatile("" : "+r"(x)); }
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
 // stage 1 for 8 sites: own words (w0 = lanes 0-3, w1 = lanes 4-7 of the group),
 // neighbour sums (s0, s1), random words (ra -> lanes (0,4,1,5), rb -> lanes (2,6,3,7)).
-// Returns the compare words zA, zB (bit 7 of a byte clear <=> accept) and leaves the
-// permuted own words in oA, oB.
-template <int METHOD>
+// Returns the compare words zA, zB (bit 7 of a byte clear <=> accept), the permuted own
+// words oA, oB and ix = nibble-packed table indices | own spin << 3 (selector order).
+template <int NNB, int METHOD>
 __device__ __forceinline__ void ising_stage1(uint32_t w0, uint32_t w1, uint32_t s0, uint32_t s1,
                                              uint32_t ra, uint32_t rb, const IsingTab& tab,
-                                             uint32_t& sp, uint32_t& oA, uint32_t& oB,
+                                             uint32_t& ix, uint32_t& oA, uint32_t& oB,
                                              uint32_t& zA, uint32_t& zB)
 {
-    sp = s0 + (s1 << 4);  // nibble-packed sums: byte j = S(lane j) | S(lane 4+j) << 4
-    const uint32_t selA = sp, selB = sp >> 16;
+    const uint32_t sp = s0 + (s1 << 4);  // nibble-packed sums: byte j = S(lane j) | S(lane 4+j) << 4
+    const uint32_t op = w0 + (w1 << 4);  // nibble-packed own spins, same order
+    uint32_t idx;
+    if (METHOD == METHOD_METROPOLIS) {
+        // k' = s ? S : nnb - S, per nibble:  nnb - S = (S ^ 7) - (7 - nnb)   (no borrows: S <= nnb)
+        const uint32_t t = op ^ 0x11111111u;        // 1 where the spin is down
+        idx = (sp ^ (t * 7u)) - t * (uint32_t)(7 - NNB);
+    } else {
+        idx = sp;
+    }
+    ix = idx + op * 8u;
     oA = prmt(w0, w1, 0x5140u);  // lanes (0,4,1,5)
     oB = prmt(w0, w1, 0x7362u);  // lanes (2,6,3,7)
-    uint32_t tA, tB;
-    if (METHOD == METHOD_METROPOLIS) {
-        const uint32_t mA = oA * 0xFFu, mB = oB * 0xFFu;  // 0xFF where the spin is up
-        const uint32_t uA = prmt(tab.tlo[1], tab.thi[1], selA), dA = prmt(tab.tlo[0], tab.thi[0], selA);
-        const uint32_t uB = prmt(tab.tlo[1], tab.thi[1], selB), dB = prmt(tab.tlo[0], tab.thi[0], selB);
-        tA = (uA & mA) | (dA & ~mA);
-        tB = (uB & mB) | (dB & ~mB);
-    } else {
-        tA = prmt(tab.tlo[0], tab.thi[0], selA);
-        tB = prmt(tab.tlo[0], tab.thi[0], selB);
-    }
+    const uint32_t tA = prmt(tab.tlo, tab.thi, idx);
+    const uint32_t tB = prmt(tab.tlo, tab.thi, idx >> 16);
     // z = b7 + 128 - T7 per byte (no carries: <= 255).  bit 7 clear <=> b7 < T7 <=> accept.
     zA = (ra & 0x7F7F7F7Fu) + tA;
     zB = (rb & 0x7F7F7F7Fu) + tB;
@@ -110,14 +119,17 @@ template <int METHOD>
 __device__ __forceinline__ void ising_finish(uint32_t& w0, uint32_t& w1, uint32_t oA, uint32_t oB,
                                              uint32_t zA, uint32_t zB)
 {
-    const uint32_t fA = (~zA >> 7) & 0x01010101u;
-    const uint32_t fB = (~zB >> 7) & 0x01010101u;
+    const uint32_t sA = zA >> 7, sB = zB >> 7;
     uint32_t nA, nB;
-    if (METHOD == METHOD_METROPOLIS) { nA = oA ^ fA; nB = oB ^ fB; }
-    else { nA = fA; nB = fB; }
+    if (METHOD == METHOD_METROPOLIS) { nA = oA ^ (~sA & 0x01010101u); nB = oB ^ (~sB & 0x01010101u); }
+    else { nA = ~sA & 0x01010101u; nB = ~sB & 0x01010101u; }
     w0 = prmt(nA, nB, 0x6420u);
     w1 = prmt(nA, nB, 0x7531u);
 }
+
+// conservative tie flags: bit 7 set in every byte equal to 0x80 (may also flag the byte
+// above a 0x00 byte; the drain re-tests exactly)
+__device__ __forceinline__ uint32_t tie_flags(uint32_t z) { return z & ~(z - 0x01010101u); }
 
 // exact per-byte "== 0x80" test -> 4-bit mask
 __device__ __forceinline__ uint32_t tie_bits(uint32_t z)
@@ -128,14 +140,16 @@ __device__ __forceinline__ uint32_t tie_bits(uint32_t z)
 }
 
 template <int METHOD>
-__device__ __noinline__ void ising_drain(uint4 (*q)[2], uint32_t* cnt, uint4* own, const RingPassArgs& a,
+__device__ __noinline__ void ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4* own, const RingPassArgs& a,
                                          const IsingTab& tab)
 {
     __syncwarp();
-    const uint32_t n = *cnt;
+    const uint32_t n = lds32(cntaddr);
     const int lane = threadIdx.x & 31;
     for (uint32_t r = lane; r < n; r += 32) {
-        const uint4 r0 = q[r][0], r1 = q[r][1];
+        uint4 r0, r1;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(qaddr + r * 32));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(qaddr + r * 32 + 16));
         const uint32_t v = r0.x;
         uint8_t* bytes = reinterpret_cast<uint8_t*>(own + v);
         // 16-bit tie mask, bit m = byte position m of the stage-1 Philox block
@@ -145,25 +159,22 @@ __device__ __noinline__ void ising_drain(uint4 (*q)[2], uint32_t* cnt, uint4* ow
             const int m = __ffs(mask) - 1;
             mask &= mask - 1;
             const int w = m >> 2, j = m & 3;
-            uint4 c = mk_ctr(pglob, a.draw, a.colour, 1u + w);
-            const uint4 R = philox_rk<TAG_ISING>(c, tab.rk0);
+            const uint4 R = philox_rk<TAG_ISING>(mk_ctr(pglob, a.draw, a.colour, 1u + w), tab.rk0);
             const uint32_t rj = j == 0 ? R.x : j == 1 ? R.y : j == 2 ? R.z : R.w;
-            const uint32_t spw = (w >> 1) ? r1.z : r1.y;
-            const uint32_t nib = (spw >> (16 * (w & 1) + 4 * j)) & 0xFu;
-            const uint32_t S = nib & 7u;
-            const uint32_t s = (METHOD == METHOD_METROPOLIS) ? (nib >> 3) : 0u;
-            if ((rj & 0x1FFFFFFu) < tab.low25[s][S]) {
+            const uint32_t ixw = (w >> 1) ? r1.z : r1.y;
+            const uint32_t nib = (ixw >> (16 * (w & 1) + 4 * j)) & 0xFu;
+            if ((rj & 0x1FFFFFFu) < tab.low25[nib & 7u]) {
                 const int lb = (m & 8) | ((m & 7) >> 1) | ((m & 1) << 2);  // byte position -> lane
-                bytes[lb] = (METHOD == METHOD_METROPOLIS) ? (uint8_t)(s ^ 1u) : (uint8_t)1;
+                bytes[lb] = (METHOD == METHOD_METROPOLIS) ? (uint8_t)((nib >> 3) ^ 1u) : (uint8_t)1;
             }
         }
     }
     __syncwarp();
-    if (lane == 0) *cnt = 0;
+    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(cntaddr), "r"(0u) : "memory");
     __syncwarp();
 }
 
-template <int NNB, int METHOD>
+template <int NNB, int METHOD, bool ORDERED>
 __global__ void __launch_bounds__(256)
 ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant__ IsingTab tab)
 {
@@ -171,30 +182,33 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
     __shared__ uint32_t tq_cnt[8];
     __shared__ int s_vb[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4 (*myq)[2] = tq[warp];
-    uint32_t* mycnt = &tq_cnt[warp];
-    if (lane == 0) *mycnt = 0;
+    uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(&tq[warp][0][0]);
+    uint32_t cntaddr = (uint32_t)__cvta_generic_to_shared(&tq_cnt[warp]);
+    pin32(qaddr);
+    pin32(cntaddr);
+    if (lane == 0) tq_cnt[warp] = 0;
     __syncwarp();
     const uint64_t pol = l2_policy_evict_first();
     uint4* own = a.own + a.H;
+    pin64(own);
     const int nvec = (int)a.nvec;
     const uint4* pn[NNB];
 #pragma unroll
-    for (int j = 0; j < NNB; ++j) pn[j] = a.oth + (a.H + a.off[j]);
-    const bool ordered = a.ticket != nullptr;
+    for (int j = 0; j < NNB; ++j) { pn[j] = a.oth + (a.H + a.off[j]); pin64(pn[j]); }
     const int stride = gridDim.x * blockDim.x;
     // ordered mode: blocks take 256-vector chunks from a global counter so that all resident
     // blocks work inside one narrow window of the lattice (keeps the z-neighbour planes in L2)
     int vb0 = blockIdx.x * blockDim.x;
     int it = 0;
-    if (ordered) {
+    if (ORDERED) {
         if (threadIdx.x == 0) s_vb[0] = (int)atomicAdd(a.ticket, 256u);
         __syncthreads();
         vb0 = s_vb[0];
     }
+    const int tofs = warp * 32 + lane;
     while (vb0 < nvec) {
-        if (ordered && threadIdx.x == 0) s_vb[(it + 1) & 1] = (int)atomicAdd(a.ticket, 256u);  // prefetch next chunk
-        const int v = vb0 + warp * 32 + lane;
+        if (ORDERED && threadIdx.x == 0) s_vb[(it + 1) & 1] = (int)atomicAdd(a.ticket, 256u);  // prefetch next chunk
+        const int v = vb0 + tofs;
         if (v < nvec) {
             uint4 o = ld_own(own + v, pol);
             uint4 nb[NNB];
@@ -205,36 +219,32 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
             uint4 S = make_uint4(nb[0].x + nb[1].x, nb[0].y + nb[1].y, nb[0].z + nb[1].z, nb[0].w + nb[1].w);
 #pragma unroll
             for (int j = 2; j < NNB; ++j) { S.x += nb[j].x; S.y += nb[j].y; S.z += nb[j].z; S.w += nb[j].w; }
-            uint32_t sp0, sp1, oA0, oB0, oA1, oB1, zA0, zB0, zA1, zB1;
-            ising_stage1<METHOD>(o.x, o.y, S.x, S.y, r.x, r.y, tab, sp0, oA0, oB0, zA0, zB0);
-            ising_stage1<METHOD>(o.z, o.w, S.z, S.w, r.z, r.w, tab, sp1, oA1, oB1, zA1, zB1);
-            const uint32_t tie = zero_byte_mask(zA0 ^ 0x80808080u) | zero_byte_mask(zB0 ^ 0x80808080u) |
-                                 zero_byte_mask(zA1 ^ 0x80808080u) | zero_byte_mask(zB1 ^ 0x80808080u);
+            uint32_t ix0, ix1, oA0, oB0, oA1, oB1, zA0, zB0, zA1, zB1;
+            ising_stage1<NNB, METHOD>(o.x, o.y, S.x, S.y, r.x, r.y, tab, ix0, oA0, oB0, zA0, zB0);
+            ising_stage1<NNB, METHOD>(o.z, o.w, S.z, S.w, r.z, r.w, tab, ix1, oA1, oB1, zA1, zB1);
+            const uint32_t tie = (tie_flags(zA0) | tie_flags(zB0) | tie_flags(zA1) | tie_flags(zB1)) & 0x80808080u;
             if (tie) {  // rare per lane: park the record, resolve later (ties count as reject below)
-                uint32_t sps0 = sp0, sps1 = sp1;
-                if (METHOD == METHOD_METROPOLIS) {
-                    sps0 += 8u * (o.x + (o.y << 4));
-                    sps1 += 8u * (o.z + (o.w << 4));
-                }
-                const uint32_t slot = atomicAdd(mycnt, 1u);
-                myq[slot][0] = make_uint4((uint32_t)v, zA0, zB0, zA1);
-                myq[slot][1] = make_uint4(zB1, sps0, sps1, 0u);
+                uint32_t slot;
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(cntaddr) : "memory");
+                const uint32_t ra = qaddr + slot * 32;
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "r"((uint32_t)v), "r"(zA0), "r"(zB0), "r"(zA1) : "memory");
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ra + 16), "r"(zB1), "r"(ix0), "r"(ix1), "r"(0u) : "memory");
             }
             ising_finish<METHOD>(o.x, o.y, oA0, oB0, zA0, zB0);
             ising_finish<METHOD>(o.z, o.w, oA1, oB1, zA1, zB1);
             st_own(own + v, o, pol);
         }
         __syncwarp();
-        if (*mycnt > TQ_CAP - 32) ising_drain<METHOD>(myq, mycnt, own, a, tab);
+        if (lds32(cntaddr) > TQ_CAP - 32) ising_drain<METHOD>(qaddr, cntaddr, own, a, tab);
         ++it;
-        if (ordered) {
+        if (ORDERED) {
             __syncthreads();
             vb0 = s_vb[it & 1];
         } else {
             vb0 += stride;
         }
     }
-    ising_drain<METHOD>(myq, mycnt, own, a, tab);
+    ising_drain<METHOD>(qaddr, cntaddr, own, a, tab);
 }
 
 // ---------------------------------------------------------------------------
