@@ -116,5 +116,14 @@ class _IsingBase:
     def sync(self):
         self._call("sync")
 
+    def set_timing(self, on=True):
+        """per-launch CUDA-event timing of the colour-pass kernel (bench.py roofline leg)"""
+        self._call("set_timing", 1 if on else 0, argtypes=(i32,))
+
+    def get_timing(self):
+        n, ms = C.c_int64(0), C.c_double(0.0)
+        self._call("get_timing", C.byref(n), C.byref(ms), argtypes=(C.POINTER(C.c_int64), C.POINTER(C.c_double)))
+        return int(n.value), float(ms.value)
+
     def set_stream(self, cuda_stream: int):
         self._call("set_stream", C.c_void_p(cuda_stream), argtypes=(P,))

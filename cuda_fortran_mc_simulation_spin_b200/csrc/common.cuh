@@ -11,6 +11,8 @@
 #define B200MC_ERR_UNSUPPORTED 4
 
 extern thread_local char g_b200mc_err[512];
+extern unsigned long long g_b200mc_launches;  // kernels launched by this library (all handles)
+#define COUNT_LAUNCH() (++g_b200mc_launches)
 
 #define CK(call)                                                                          \
     do {                                                                                  \

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <new>
+#include <vector>
 #include "../../include/b200mc.h"
 #include "ising_kernels.cuh"
 #include "ring.cuh"
@@ -31,6 +32,13 @@ struct Ising {
     int tune;  // debug knobs from env B200MC_TUNE: bit0 = static grid-stride (no ticket)
     int grid;
     bool alive;
+    // observables cache: valid until the configuration changes
+    bool obs_valid;
+    int64_t obs_e, obs_m;
+    // optional per-launch timing of the pass kernel (CUDA events on the handle's stream)
+    bool timing;
+    std::vector<cudaEvent_t> evs;  // event pool: pair (2i, 2i+1) brackets the i-th timed launch
+    size_t ev_used;
 };
 
 int build_tables(Ising* m)
@@ -126,6 +134,12 @@ int launch_pass(Ising* m, int colour)
         a.ticket = m->d_ticket;
         CK(cudaMemsetAsync(m->d_ticket, 0, sizeof(unsigned int), m->stream));
     }
+    m->obs_valid = false;
+    if (m->timing) {
+        while (m->evs.size() < m->ev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); m->evs.push_back(e); }
+        CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
+    }
+    COUNT_LAUNCH();
     if (m->method == METHOD_METROPOLIS) {
         if (a.ticket) ising_pass_kernel<NNB, METHOD_METROPOLIS, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
         else ising_pass_kernel<NNB, METHOD_METROPOLIS, false><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
@@ -133,6 +147,7 @@ int launch_pass(Ising* m, int colour)
         if (a.ticket) ising_pass_kernel<NNB, METHOD_HEATBATH, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
         else ising_pass_kernel<NNB, METHOD_HEATBATH, false><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
     }
+    if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
     CK(cudaGetLastError());
     return ring_halo(&m->st, colour, m->stream);
 }
@@ -164,6 +179,8 @@ int launch_pass_randoms(Ising* m, int colour)
     a.draw = m->draw;
     a.ticket = nullptr;
     const unsigned grid = (unsigned)((g.L + 255) / 256);
+    m->obs_valid = false;
+    COUNT_LAUNCH();
     if (m->method == METHOD_METROPOLIS)
         ising_pass_randoms_kernel<NNB, METHOD_METROPOLIS><<<grid, 256, 0, m->stream>>>(a, m->tabf, m->d_randoms, g.L, g.Nc);
     else
@@ -175,6 +192,12 @@ int launch_pass_randoms(Ising* m, int colour)
 int measure(Ising* m, int64_t* e, int64_t* mag)
 {
     const RingGeom& g = m->st.g;
+    if (m->obs_valid) {  // update -> calc_magne_sum -> calc_energy_sum (the drivers' loop) costs one pass
+        if (e) *e = m->obs_e;
+        if (mag) *mag = m->obs_m;
+        return B200MC_OK;
+    }
+    COUNT_LAUNCH();
     CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
     if (m->ndim == 3)
         ising_measure_kernel<6><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.L, g.H, 0, m->d_off1, g.L, g.Nc, g.ptail, m->d_acc);
@@ -186,8 +209,11 @@ int measure(Ising* m, int64_t* e, int64_t* mag)
     CK(cudaStreamSynchronize(m->stream));
     const int64_t X = (int64_t)acc[0], sum = (int64_t)acc[1];
     // E = -(bonds) + 2 X with bonds = (nnb/2) N;   M = 2 sum(s) - N
-    if (e) *e = -(int64_t)(g.nnb / 2) * g.N + 2 * X;
-    if (mag) *mag = 2 * sum - g.N;
+    m->obs_e = -(int64_t)(g.nnb / 2) * g.N + 2 * X;
+    m->obs_m = 2 * sum - g.N;
+    m->obs_valid = true;
+    if (e) *e = m->obs_e;
+    if (mag) *mag = m->obs_m;
     return B200MC_OK;
 }
 
@@ -207,6 +233,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     m->stream = 0; m->d_acc = nullptr; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
     { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; }
     m->method = METHOD_METROPOLIS; m->seed = (uint32_t)iseed; m->draw = 0; m->alive = true;
+    m->obs_valid = false; m->timing = false; m->ev_used = 0;
     int rc = ring_geom_init(&m->st.g, nx, ny, m->nz);
     if (rc) { delete m; return rc; }
     rc = ring_alloc(&m->st);
@@ -244,6 +271,7 @@ int destroy(Ising* m)
     cudaFree(m->d_off1);
     cudaFree(m->d_randoms);
     cudaFree(m->d_ticket);
+    for (cudaEvent_t e : m->evs) cudaEventDestroy(e);
     delete m;
     return B200MC_OK;
 }
@@ -251,7 +279,9 @@ int destroy(Ising* m)
 int set_random(Ising* m)
 {
     const RingGeom& g = m->st.g;
+    m->obs_valid = false;
     for (int c = 0; c < 2; ++c) {
+        COUNT_LAUNCH();
         ring_random_bits_kernel<<<(unsigned)((g.L + 255) / 256), 256, 0, m->stream>>>(m->st.vec[c], g.L, g.H, 0, m->seed, m->draw, (uint32_t)c);
         CK(cudaGetLastError());
     }
@@ -272,6 +302,20 @@ int update_with_randoms(Ising* m, const double* randoms)
         if (rc) return rc;
     }
     CK(cudaStreamSynchronize(m->stream));  // the host array may be reused by the caller
+    return B200MC_OK;
+}
+
+int get_timing(Ising* m, int64_t* launches, double* total_ms)
+{
+    CK(cudaStreamSynchronize(m->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < m->ev_used; i += 2) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, m->evs[i], m->evs[i + 1]));
+        tot += ms;
+    }
+    if (launches) *launches = (int64_t)(m->ev_used / 2);
+    if (total_ms) *total_ms = tot;
     return B200MC_OK;
 }
 
@@ -296,6 +340,7 @@ extern "C" {
 
 const char* b200mc_last_error(void) { return g_b200mc_err; }
 int b200mc_version(void) { return 100; }
+unsigned long long b200mc_launch_count(void) { return g_b200mc_launches; }
 
 __global__ void philox_debug_kernel(uint4 c, uint2 k, uint4* out) { *out = philox4x32_10(c, k); }
 int b200mc_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
@@ -315,7 +360,7 @@ int b200mc_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
     int PFX##_destroy(void* h) { if (!h) return B200MC_OK; CHECK_H(h, ND); return destroy(H(h)); } \
     int PFX##_set_stream(void* h, void* s) { CHECK_H(h, ND); H(h)->stream = (cudaStream_t)s; return B200MC_OK; } \
     int PFX##_skip_curand(void* h, int64_t n) { CHECK_H(h, ND); return skip(H(h), n); }           \
-    int PFX##_set_allup_spin(void* h) { CHECK_H(h, ND); return ring_fill(&H(h)->st, 1, H(h)->stream); } \
+    int PFX##_set_allup_spin(void* h) { CHECK_H(h, ND); H(h)->obs_valid = false; return ring_fill(&H(h)->st, 1, H(h)->stream); } \
     int PFX##_set_random_spin(void* h) { CHECK_H(h, ND); return set_random(H(h)); }               \
     int PFX##_set_beta(void* h, double beta) { CHECK_H(h, ND); if (!(beta >= 0.0)) ARG_FAIL("beta must be >= 0"); H(h)->beta = beta; return build_tables(H(h)); } \
     int PFX##_set_kbt(void* h, double kbt) { CHECK_H(h, ND); if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0"); H(h)->beta = 1 / kbt; return build_tables(H(h)); } \
@@ -327,12 +372,14 @@ int b200mc_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
     int PFX##_calc_magne_sum(void* h, int64_t* m) { CHECK_H(h, ND); return measure(H(h), nullptr, m); } \
     int PFX##_measure(void* h, int64_t* e, int64_t* m) { CHECK_H(h, ND); return measure(H(h), e, m); } \
     int PFX##_get_spins(void* h, int32_t* out) { CHECK_H(h, ND); if (!out) ARG_FAIL("null output"); return ring_export_i32(&H(h)->st, out, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream); } \
-    int PFX##_set_spins(void* h, const int32_t* in) { CHECK_H(h, ND); if (!in) ARG_FAIL("null input"); return ring_import_i32(&H(h)->st, in, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream); } \
+    int PFX##_set_spins(void* h, const int32_t* in) { CHECK_H(h, ND); if (!in) ARG_FAIL("null input"); H(h)->obs_valid = false; return ring_import_i32(&H(h)->st, in, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream); } \
     int64_t PFX##_nx(void* h) { return h ? H(h)->nx : -1; }                                       \
     int64_t PFX##_ny(void* h) { return h ? H(h)->ny : -1; }                                       \
     int64_t PFX##_nall(void* h) { return h ? H(h)->st.g.N : -1; }                                 \
     double PFX##_kbt(void* h) { return h ? 1 / H(h)->beta : 0.0; }                                \
     double PFX##_beta(void* h) { return h ? H(h)->beta : 0.0; }                                   \
+    int PFX##_set_timing(void* h, int32_t on) { CHECK_H(h, ND); H(h)->timing = on != 0; H(h)->ev_used = 0; return B200MC_OK; } \
+    int PFX##_get_timing(void* h, int64_t* launches, double* total_ms) { CHECK_H(h, ND); return get_timing(H(h), launches, total_ms); } \
     int PFX##_sync(void* h) { CHECK_H(h, ND); CK(cudaStreamSynchronize(H(h)->stream)); return B200MC_OK; }
 
 DEFINE_COMMON(b200mc_ising3d, 3)

@@ -3,6 +3,7 @@
 #include "ring.cuh"
 
 thread_local char g_b200mc_err[512] = {0};
+unsigned long long g_b200mc_launches = 0;
 
 int ring_geom_init(RingGeom* g, int64_t nx, int64_t ny, int64_t nz)
 {
@@ -141,14 +142,17 @@ int ring_halo(RingStore* s, int colour, cudaStream_t st)
     if (g.H <= g.L && g.ptail >= g.H) {
         const int64_t nv = 2 * g.H;
         ring_halo_fast_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(s->vec[colour], g.L, g.H, g.Nc);
+        COUNT_LAUNCH();
         if (ntail > 0) {
             const int64_t n_items = ntail * 16;  // tail vectors are ordinals [2H, 2H + ntail)
             ring_halo_generic_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(
                 base, g.L, g.H, g.Nc, g.ptail, 2 * g.H, n_items);
+            COUNT_LAUNCH();
         }
     } else {
         const int64_t n_items = (2 * g.H + ntail) * 16;
         ring_halo_generic_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(base, g.L, g.H, g.Nc, g.ptail, 0, n_items);
+        COUNT_LAUNCH();
     }
     CK(cudaGetLastError());
     return B200MC_OK;

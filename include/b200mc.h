@@ -41,6 +41,8 @@ extern "C" {
 
 const char* b200mc_last_error(void);
 int b200mc_version(void);
+/* number of CUDA kernels this library has launched so far in this process (all handles) */
+unsigned long long b200mc_launch_count(void);
 /* run the handle's kernels on a caller-provided CUDA stream (cudaStream_t as void*) */
 int b200mc_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]); /* device Philox, for KAT tests */
 
@@ -78,6 +80,10 @@ double b200mc_ising3d_kbt(void* h);   /* :224-227 */
 double b200mc_ising3d_beta(void* h);  /* :228-231 */
 /* host copy of ws(0:6, 0:1) as built by update_ws (:153-171): out[S + 7*s] */
 int b200mc_ising3d_get_ws(void* h, double out[14]);
+/* per-launch device timing of the colour-pass kernel (CUDA events on the handle's stream):
+ * set_timing(1) resets and enables; get_timing returns the launches seen and their summed duration */
+int b200mc_ising3d_set_timing(void* h, int32_t on);
+int b200mc_ising3d_get_timing(void* h, int64_t* launches, double* total_ms);
 int b200mc_ising3d_sync(void* h);
 
 /* ------------------------------------------------------------------------
@@ -109,6 +115,8 @@ double b200mc_ising2d_kbt(void* h);
 double b200mc_ising2d_beta(void* h);
 /* host copy of exparr(-8:8) as built by update_exparr (:126-130): out[d + 8] */
 int b200mc_ising2d_get_exparr(void* h, double out[17]);
+int b200mc_ising2d_set_timing(void* h, int32_t on);
+int b200mc_ising2d_get_timing(void* h, int64_t* launches, double* total_ms);
 int b200mc_ising2d_sync(void* h);
 
 #pragma GCC visibility pop

@@ -104,6 +104,7 @@ def _declare(L):
     d("orc_xy_metropolis_by_field", None, i64, i64, P, P, P, f64, f64)
     d("orc_ring_fold_len", i64, i64)
     d("orc_ising_uniforms", None, u32, u64, i64, P)
+    d("orc_ising_uniforms_fast", None, u32, u64, i64, P)
     d("orc_ring_init_uniforms", None, u32, u64, i64, P)
     d("orc_clock_uniforms", None, u32, u64, i32, i64, P, P)
     for name in ("orc_torus_clock_uniforms", "orc_xy_uniforms", "orc_xy_init_uniforms"):
@@ -138,6 +139,13 @@ def set_threads(n: int) -> None:
 def ising_uniforms(seed: int, draw: int, n_sites: int) -> np.ndarray:
     out = np.empty(n_sites, dtype=np.float64)
     lib().orc_ising_uniforms(seed & 0xFFFFFFFF, draw, n_sites, _p(out))
+    return out
+
+
+def ising_uniforms_fast(seed: int, draw: int, n_sites: int, out=None) -> np.ndarray:
+    if out is None:
+        out = np.empty(n_sites, dtype=np.float64)
+    lib().orc_ising_uniforms_fast(seed & 0xFFFFFFFF, draw, n_sites, _p(out))
     return out
 
 

@@ -137,3 +137,34 @@ ORC_API void orc_clock_uniforms(uint32_t seed, uint64_t draw, int32_t replica, i
         next_states[i] = ((double)r[2 * (lane & 1) + 1] + 1.0) * 0x1p-32;
     }
 }
+
+/* block-wise evaluation of orc_ising_uniforms (same values, 5 Philox calls per
+ * 16 sites instead of 2 per site): used where generation speed matters
+ * (bench.py's CPU baseline, which like the reference draws a fresh array of
+ * nall uniforms every sweep, src/ising3d_gpu_m.f90:179). */
+ORC_API void orc_ising_uniforms_fast(uint32_t seed, uint64_t draw, int64_t n_sites, double *out)
+{
+    const int64_t L = orc_ring_fold_len(n_sites);
+    const int64_t nc = n_sites / 2;
+    const uint32_t key[2] = {seed, TAG_ISING};
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < L; ++p) {
+        for (uint32_t colour = 0; colour < 2; ++colour) {
+            uint32_t c[4], r[4], r2[4][4];
+            mk_ctr(c, (uint64_t)p, draw, colour, 0);
+            orc_philox4x32_10(c, key, r);
+            for (uint32_t sub = 0; sub < 4; ++sub) {
+                mk_ctr(c, (uint64_t)p, draw, colour, 1u + sub);
+                orc_philox4x32_10(c, key, r2[sub]);
+            }
+            for (int lane = 0; lane < 16; ++lane) {
+                const int64_t k = (int64_t)lane * L + p;
+                if (k >= nc) continue;
+                const int m = BYTEPOS[lane];
+                const uint32_t b7 = (r[m >> 2] >> (8 * (m & 3))) & 0x7Fu;
+                const uint32_t low25 = r2[m >> 2][m & 3] & 0x1FFFFFFu;
+                out[2 * k + colour] = ((double)((b7 << 25) | low25) + 1.0) * 0x1p-32;
+            }
+        }
+    }
+}
