@@ -29,7 +29,8 @@ struct Ising {
     int64_t* d_off1;            // colour-1 offsets for the measure kernel
     double* d_randoms;
     unsigned int* d_ticket;
-    int tune;  // debug knobs from env B200MC_TUNE: bit0 = static grid-stride (no ticket)
+    int tune;  // debug knobs from env B200MC_TUNE: bit0 = static round-robin (no ticket)
+    int chunk; // vectors per ticket (env B200MC_CHUNK, default 128)
     int grid;
     bool alive;
     // observables cache: valid until the configuration changes
@@ -130,9 +131,10 @@ int launch_pass(Ising* m, int colour)
     a.colour = (uint32_t)colour;
     a.draw = m->draw;
     a.ticket = nullptr;
+    a.chunk = m->chunk;
     if (!(m->tune & 1) && g.L > (int64_t)m->grid * 256 * 4) {
         a.ticket = m->d_ticket;
-        CK(cudaMemsetAsync(m->d_ticket, 0, sizeof(unsigned int), m->stream));
+        CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
     }
     m->obs_valid = false;
     if (m->timing) {
@@ -178,6 +180,7 @@ int launch_pass_randoms(Ising* m, int colour)
     a.colour = (uint32_t)colour;
     a.draw = m->draw;
     a.ticket = nullptr;
+    a.chunk = 128;
     const unsigned grid = (unsigned)((g.L + 255) / 256);
     m->obs_valid = false;
     COUNT_LAUNCH();
@@ -231,14 +234,14 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     if (!m) ARG_FAIL("out of host memory");
     m->ndim = ndim; m->nx = nx; m->ny = ny; m->nz = ndim == 3 ? nz : 0;
     m->stream = 0; m->d_acc = nullptr; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
-    { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; }
+    { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; t = getenv("B200MC_CHUNK"); m->chunk = t ? atoi(t) : 128; if (m->chunk < 32 || (m->chunk & 31)) m->chunk = 128; }
     m->method = METHOD_METROPOLIS; m->seed = (uint32_t)iseed; m->draw = 0; m->alive = true;
     m->obs_valid = false; m->timing = false; m->ev_used = 0;
     int rc = ring_geom_init(&m->st.g, nx, ny, m->nz);
     if (rc) { delete m; return rc; }
     rc = ring_alloc(&m->st);
     if (rc) { ring_free(&m->st); delete m; return rc; }
-    if (cudaMalloc(&m->d_ticket, sizeof(unsigned int)) != cudaSuccess ||
+    if (cudaMalloc(&m->d_ticket, TK_NCNT * 64 * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&m->d_off1, 6 * sizeof(int64_t)) != cudaSuccess) {
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed");

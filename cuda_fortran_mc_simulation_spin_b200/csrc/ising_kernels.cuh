@@ -59,7 +59,8 @@ struct RingPassArgs {
     uint32_t seed;
     uint32_t colour;
     uint64_t draw;
-    unsigned int* ticket;  // work counter for ordered block scheduling (nullptr: static grid-stride)
+    unsigned int* ticket;  // work counter for ordered scheduling (nullptr: static round-robin)
+    int chunk;             // vectors per ticket (multiple of 32)
 };
 
 enum { METHOD_METROPOLIS = 0, METHOD_HEATBATH = 1 };
@@ -71,6 +72,7 @@ enum { METHOD_METROPOLIS = 0, METHOD_HEATBATH = 1 };
 // queue and goes on; when the queue is half full (and at kernel end) the warp
 // drains it with all 32 lanes busy and patches the accepted bytes in global memory.
 #define TQ_CAP 64
+#define TK_NCNT 8
 
 // keep a value in a register: stops the compiler from rematerialising address
 // arithmetic from kernel parameters inside the hot loop
@@ -180,7 +182,6 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
 {
     __shared__ uint4 tq[8][TQ_CAP][2];
     __shared__ uint32_t tq_cnt[8];
-    __shared__ int s_vb[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(&tq[warp][0][0]);
     uint32_t cntaddr = (uint32_t)__cvta_generic_to_shared(&tq_cnt[warp]);
@@ -195,54 +196,59 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
     const uint4* pn[NNB];
 #pragma unroll
     for (int j = 0; j < NNB; ++j) { pn[j] = a.oth + (a.H + a.off[j]); pin64(pn[j]); }
-    const int stride = gridDim.x * blockDim.x;
-    // ordered mode: blocks take 256-vector chunks from a global counter so that all resident
-    // blocks work inside one narrow window of the lattice (keeps the z-neighbour planes in L2)
-    int vb0 = blockIdx.x * blockDim.x;
-    int it = 0;
+    // ordered mode: every warp takes TK_CHUNK-vector chunks from a global counter, so that all
+    // resident warps work inside one narrow, advancing window of the lattice (the z-neighbour
+    // planes then stay in L2 between their three uses).  The next ticket is fetched one chunk
+    // ahead; no block-level synchronisation anywhere in the loop.
+    const int TK_CHUNK = a.chunk;
+    const int nwarps_grid = gridDim.x * (blockDim.x >> 5);
+    // TK_NCNT interleaved counters (256 B apart -> different L2 slices): counter c hands out the
+    // chunks c, c + NCNT, c + 2 NCNT, ...; one same-address atomic stream would cap the ticket rate
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+    unsigned int* tk = a.ticket + (gwarp % TK_NCNT) * 64;
+    const int tk_base = (gwarp % TK_NCNT) * TK_CHUNK, tk_scale = TK_NCNT;
+    int cur, nxt = 0;
     if (ORDERED) {
-        if (threadIdx.x == 0) s_vb[0] = (int)atomicAdd(a.ticket, 256u);
-        __syncthreads();
-        vb0 = s_vb[0];
+        if (lane == 0) nxt = (int)atomicAdd(tk, (unsigned)TK_CHUNK) * tk_scale + tk_base;
+        cur = __shfl_sync(0xffffffffu, nxt, 0);
+    } else {
+        cur = gwarp * TK_CHUNK;
     }
-    const int tofs = warp * 32 + lane;
-    while (vb0 < nvec) {
-        if (ORDERED && threadIdx.x == 0) s_vb[(it + 1) & 1] = (int)atomicAdd(a.ticket, 256u);  // prefetch next chunk
-        const int v = vb0 + tofs;
-        if (v < nvec) {
-            uint4 o = ld_own(own + v, pol);
-            uint4 nb[NNB];
+    while (cur < nvec) {
+        if (ORDERED && lane == 0) nxt = (int)atomicAdd(tk, (unsigned)TK_CHUNK) * tk_scale + tk_base;  // prefetch
+#pragma unroll 1
+        for (int sub = 0; sub < TK_CHUNK; sub += 32) {
+            const int v = cur + sub + lane;
+            if (v < nvec) {
+                uint4 o = ld_own(own + v, pol);
+                uint4 nb[NNB];
 #pragma unroll
-            for (int j = 0; j < NNB; ++j) nb[j] = ld_other(pn[j] + v);
-            const uint64_t pglob = (uint64_t)(a.p0 + v);
-            const uint4 r = philox_rk<TAG_ISING>(mk_ctr(pglob, a.draw, a.colour, 0u), tab.rk0);
-            uint4 S = make_uint4(nb[0].x + nb[1].x, nb[0].y + nb[1].y, nb[0].z + nb[1].z, nb[0].w + nb[1].w);
+                for (int j = 0; j < NNB; ++j) nb[j] = ld_other(pn[j] + v);
+                const uint64_t pglob = (uint64_t)(a.p0 + v);
+                const uint4 r = philox_rk<TAG_ISING>(mk_ctr(pglob, a.draw, a.colour, 0u), tab.rk0);
+                uint4 S = make_uint4(nb[0].x + nb[1].x, nb[0].y + nb[1].y, nb[0].z + nb[1].z, nb[0].w + nb[1].w);
 #pragma unroll
-            for (int j = 2; j < NNB; ++j) { S.x += nb[j].x; S.y += nb[j].y; S.z += nb[j].z; S.w += nb[j].w; }
-            uint32_t ix0, ix1, oA0, oB0, oA1, oB1, zA0, zB0, zA1, zB1;
-            ising_stage1<NNB, METHOD>(o.x, o.y, S.x, S.y, r.x, r.y, tab, ix0, oA0, oB0, zA0, zB0);
-            ising_stage1<NNB, METHOD>(o.z, o.w, S.z, S.w, r.z, r.w, tab, ix1, oA1, oB1, zA1, zB1);
-            const uint32_t tie = (tie_flags(zA0) | tie_flags(zB0) | tie_flags(zA1) | tie_flags(zB1)) & 0x80808080u;
-            if (tie) {  // rare per lane: park the record, resolve later (ties count as reject below)
-                uint32_t slot;
-                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(cntaddr) : "memory");
-                const uint32_t ra = qaddr + slot * 32;
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "r"((uint32_t)v), "r"(zA0), "r"(zB0), "r"(zA1) : "memory");
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ra + 16), "r"(zB1), "r"(ix0), "r"(ix1), "r"(0u) : "memory");
+                for (int j = 2; j < NNB; ++j) { S.x += nb[j].x; S.y += nb[j].y; S.z += nb[j].z; S.w += nb[j].w; }
+                uint32_t ix0, ix1, oA0, oB0, oA1, oB1, zA0, zB0, zA1, zB1;
+                ising_stage1<NNB, METHOD>(o.x, o.y, S.x, S.y, r.x, r.y, tab, ix0, oA0, oB0, zA0, zB0);
+                ising_stage1<NNB, METHOD>(o.z, o.w, S.z, S.w, r.z, r.w, tab, ix1, oA1, oB1, zA1, zB1);
+                const uint32_t tie = (tie_flags(zA0) | tie_flags(zB0) | tie_flags(zA1) | tie_flags(zB1)) & 0x80808080u;
+                if (tie) {  // rare per lane: park the record, resolve later (ties count as reject below)
+                    uint32_t slot;
+                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(cntaddr) : "memory");
+                    const uint32_t ra = qaddr + slot * 32;
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "r"((uint32_t)v), "r"(zA0), "r"(zB0), "r"(zA1) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ra + 16), "r"(zB1), "r"(ix0), "r"(ix1), "r"(0u) : "memory");
+                }
+                ising_finish<METHOD>(o.x, o.y, oA0, oB0, zA0, zB0);
+                ising_finish<METHOD>(o.z, o.w, oA1, oB1, zA1, zB1);
+                st_own(own + v, o, pol);
             }
-            ising_finish<METHOD>(o.x, o.y, oA0, oB0, zA0, zB0);
-            ising_finish<METHOD>(o.z, o.w, oA1, oB1, zA1, zB1);
-            st_own(own + v, o, pol);
+            __syncwarp();
+            if (lds32(cntaddr) > TQ_CAP - 32) ising_drain<METHOD>(qaddr, cntaddr, own, a, tab);
         }
-        __syncwarp();
-        if (lds32(cntaddr) > TQ_CAP - 32) ising_drain<METHOD>(qaddr, cntaddr, own, a, tab);
-        ++it;
-        if (ORDERED) {
-            __syncthreads();
-            vb0 = s_vb[it & 1];
-        } else {
-            vb0 += stride;
-        }
+        if (ORDERED) cur = __shfl_sync(0xffffffffu, nxt, 0);
+        else cur += nwarps_grid * TK_CHUNK;
     }
     ising_drain<METHOD>(qaddr, cntaddr, own, a, tab);
 }

@@ -34,7 +34,7 @@ int ring_geom_init(RingGeom* g, int64_t nx, int64_t ny, int64_t nz)
     int64_t l15 = g->Nc - 15 * g->L;
     g->ptail = l15 < 0 ? 0 : l15;
     if (g->N / g->P < 2) ARG_FAIL("lattice too small");
-    if (g->L + 2 * g->H >= (int64_t)0x7FF00000) ARG_FAIL("lattice too large for 32-bit vector indices (%lld vectors per colour)", (long long)g->L);
+    if (g->L + 2 * g->H >= (int64_t)0x7C000000) ARG_FAIL("lattice too large for 32-bit vector indices (%lld vectors per colour)", (long long)g->L);
     return B200MC_OK;
 }
 
