@@ -360,7 +360,7 @@ ising_measure_kernel(const uint4* __restrict__ c0, const uint4* __restrict__ c1,
 // set_random_spin (reference: set_random_spin_sub, src/ising3d_gpu_m.f90:91-100):
 // s = (u < 0.5) with u = (U+1) 2^-32, U = R[lane & 3] of
 // philox(ctr(p, draw, colour, lane >> 2), (seed, TAG_INIT)).
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 ring_random_bits_kernel(uint4* own, int64_t nvec, int64_t H, int64_t p0, uint32_t seed,
                         uint64_t draw, uint32_t colour)
 {

@@ -119,6 +119,46 @@ int b200mc_ising2d_set_timing(void* h, int32_t on);
 int b200mc_ising2d_get_timing(void* h, int64_t* launches, double* total_ms);
 int b200mc_ising2d_sync(void* h);
 
+/* ------------------------------------------------------------------------
+ * q-state clock, helical -- type(clock_gpu), src/clock_gpu_m.f90:13-47, and its
+ * batched twin src/clock_gpu_multi_m.f90:13-48 (n_multi independent replicas,
+ * strict accept test r < w instead of r <= w, :230-235).
+ * Observables are REAL64 in the reference (sums of table values, :245-280); here
+ * they are computed from exact integer histograms (get_histograms) on the host.
+ * Arrays over replicas are replica-major: element (site, j) at j * stride + site.
+ * ------------------------------------------------------------------------ */
+int b200mc_clock_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t state, int32_t iseed);   /* init, clock_gpu_m :49-79 */
+int b200mc_clock_multi_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t state, int32_t n_multi, int32_t iseed); /* clock_gpu_multi_m :50-83 */
+int b200mc_clock_destroy(void* h);
+int b200mc_clock_set_stream(void* h, void* cuda_stream);
+int b200mc_clock_skip_curand(void* h, int64_t n_skip);
+int b200mc_clock_set_allup_spin(void* h);            /* :81-84 (all states 0) */
+int b200mc_clock_set_random_spin(void* h);           /* :86-104 */
+int b200mc_clock_set_kbt(void* h, double kbt);       /* :169-173 */
+int b200mc_clock_set_beta(void* h, double beta);     /* :175-181 (+ update_ws :105-146) */
+int b200mc_clock_update(void* h);                    /* :183-216 */
+int b200mc_clock_update_n(void* h, int32_t n_sweeps);
+/* randoms(1:nall[, n_multi]) and next_states(...) in the reference's index order */
+int b200mc_clock_update_with_randoms(void* h, const double* randoms, const double* next_states);
+int b200mc_clock_calc_energy_sum(void* h, double* res /* n_multi values */); /* :245-262 / multi :265-289 */
+int b200mc_clock_calc_magne_sum(void* h, double* res);                       /* :264-280 / multi :291-315 */
+/* exact integer observables per replica: hist[j*q + c] = #{s = c}; bond_left[j*q + d] = #{(s(i-1) - s(i)) mod q = d};
+ * bond_down: same for (s(i-nx) - s(i)) */
+int b200mc_clock_get_histograms(void* h, int64_t* hist, int64_t* bond_left, int64_t* bond_down);
+/* spins(), :238-242: int32 0..q-1, layout spins(1-nx : nall+nx[, n_multi]) */
+int b200mc_clock_get_spins(void* h, int32_t* out);
+int b200mc_clock_set_spins(void* h, const int32_t* in);
+/* host copy of ws(0:q-1, ...) (q^6 doubles) exactly as update_ws builds it */
+int b200mc_clock_get_ws(void* h, double* out);
+int64_t b200mc_clock_nx(void* h);
+int64_t b200mc_clock_ny(void* h);
+int64_t b200mc_clock_nall(void* h);
+int32_t b200mc_clock_state(void* h);
+int32_t b200mc_clock_n_multi(void* h);
+double b200mc_clock_kbt(void* h);
+double b200mc_clock_beta(void* h);
+int b200mc_clock_sync(void* h);
+
 #pragma GCC visibility pop
 #ifdef __cplusplus
 }

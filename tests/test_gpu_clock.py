@@ -1,0 +1,109 @@
+"""GPU parity: q-state clock (helical; clock_gpu_m and clock_gpu_multi_m) vs the CPU oracle.
+States bit-exact; integer histograms exact; real64 E and M within 1e-12 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _hist_from_oracle(o, j=0):
+    """(hist, bond_left, bond_down) from the oracle's pair histogram: pair[a, b] counts bonds with
+    neighbour state a and centre state b; ours are binned by (a - b) mod q and split by direction"""
+    q, nx = o.q_, o.nx_
+    s = o.s[j]
+    n = o.nall_
+    c = s[nx:nx + n]
+    left = s[nx - 1:nx - 1 + n]
+    down = s[0:n]
+    hist = np.bincount(c, minlength=q)
+    bl = np.bincount((left - c) % q, minlength=q)
+    bd = np.bincount((down - c) % q, minlength=q)
+    return hist, bl, bd
+
+
+@pytest.mark.parametrize("shape,q,kbt", [((5, 4), 6, 0.8), ((33, 32), 6, 0.91), ((501, 500), 6, 0.8), ((65, 64), 4, 1.0),
+                                         ((33, 32), 3, 0.7), ((33, 32), 8, 0.6), ((31, 30), 5, 0.9)])
+@pytest.mark.parametrize("start", ["allup", "random"])
+def test_clock_trajectory_bit_exact(oracle, shape, q, kbt, start):
+    from cuda_fortran_mc_simulation_spin_b200 import clock_gpu_m
+    nx, ny = shape
+    g = clock_gpu_m.clock_gpu().init(nx, ny, kbt, q, 42)
+    o = oracle.clock_gpu().init(nx, ny, kbt, q, 42)
+    assert np.array_equal(g.ws(), o.ws)                       # q^6 real64 table, bit for bit
+    if start == "random":
+        g.set_random_spin(); o.set_random_spin()
+    assert np.array_equal(g.spins(), o.spins())
+    for sweep in range(5):
+        g.update(); o.update()
+        assert np.array_equal(g.spins(), o.spins()), f"states differ after sweep {sweep + 1}"
+        h, bl, bd = g.histograms()
+        oh, obl, obd = _hist_from_oracle(o)
+        assert np.array_equal(h[0], oh) and np.array_equal(bl[0], obl) and np.array_equal(bd[0], obd)
+        e, m = g.calc_energy_sum(), g.calc_magne_sum()
+        assert abs(e - o.calc_energy_sum()) <= 1e-12 * max(1.0, abs(o.calc_energy_sum())) * 10
+        assert abs(m - o.calc_magne_sum()) <= 1e-12 * g.nall()
+
+
+def test_clock_multi_bit_exact(oracle):
+    from cuda_fortran_mc_simulation_spin_b200 import clock_gpu_multi_m
+    g = clock_gpu_multi_m.clock_gpu().init(101, 100, 0.8, 6, 3, 42)
+    o = oracle.clock_gpu().init(101, 100, 0.8, 6, 42, n_multi=3)
+    g.set_random_spin(); o.set_random_spin()
+    assert np.array_equal(g.spins(), o.spins())
+    for sweep in range(4):
+        g.update(); o.update()
+        assert np.array_equal(g.spins(), o.spins())
+        assert np.allclose(g.calc_energy_sum(), o.calc_energy_sum(), rtol=1e-12, atol=1e-9)
+        assert np.allclose(g.calc_magne_sum(), o.calc_magne_sum(), rtol=1e-12, atol=1e-9)
+    # replicas are independent streams
+    s = g.spins()
+    assert not np.array_equal(s[0], s[1])
+
+
+def test_clock_update_with_randoms_comparators(oracle):
+    """explicit uniforms incl. u == w exactly: accepted by clock_gpu_m (<=), rejected by the multi twin (<)"""
+    from cuda_fortran_mc_simulation_spin_b200 import clock_gpu_m, clock_gpu_multi_m
+    rng = np.random.default_rng(3)
+    nx, ny, q = 33, 32, 6
+    for multi in (False, True):
+        if multi:
+            g = clock_gpu_multi_m.clock_gpu().init(nx, ny, 0.8, q, 2, 5)
+            o = oracle.clock_gpu().init(nx, ny, 0.8, q, 5, n_multi=2)
+        else:
+            g = clock_gpu_m.clock_gpu().init(nx, ny, 0.8, q, 5)
+            o = oracle.clock_gpu().init(nx, ny, 0.8, q, 5)
+        nm = 2 if multi else 1
+        vals = np.unique(o.ws)
+        for it in range(4):
+            r = 1.0 - rng.random(nm * nx * ny)
+            p = 1.0 - rng.random(nm * nx * ny)
+            r[::7] = rng.choice(vals, size=r[::7].size)        # exactly on table entries
+            r[1::11] = 1.0
+            p[::13] = 1.0                                      # floor(1.0 * q) = q: clamped
+            g.update_with_randoms(r, p)
+            o.update(randoms=r, next_states=p)
+            assert np.array_equal(g.spins(), o.spins())
+
+
+def test_clock_known_answers():
+    from cuda_fortran_mc_simulation_spin_b200 import clock_gpu_m
+    g = clock_gpu_m.clock_gpu().init(1001, 1000, 0.8, 6, 42)
+    n = g.nall()
+    assert abs(g.calc_energy_sum() + 2 * n) < 1e-6 and abs(g.calc_magne_sum() - n) < 1e-6   # ordered: E = -2N, M = N
+    g.set_beta(1e9)
+    g.update_n(2)
+    assert abs(g.calc_energy_sum() + 2 * n) < 1e-6                                           # beta -> inf: nothing moves
+    h, bl, bd = g.histograms()
+    assert h[0, 0] == n and bl[0, 0] == n and bd[0, 0] == n
+
+
+def test_clock_full_size_properties():
+    """BASELINE config 4 size (16384^2 class): helical 16385 x 16384, n_multi = 2"""
+    from cuda_fortran_mc_simulation_spin_b200 import clock_gpu_multi_m
+    g = clock_gpu_multi_m.clock_gpu().init(16385, 16384, 0.91, 6, 2, 42)
+    n = g.nall()
+    g.update_n(2)
+    h, bl, bd = g.histograms()
+    assert (h.sum(axis=1) == n).all() and (bl.sum(axis=1) == n).all() and (bd.sum(axis=1) == n).all()
+    e = g.calc_energy_sum()
+    assert ((-2 * n < e) & (e < -1.0 * n)).all()
