@@ -1,0 +1,547 @@
+// XY 2D periodic (xy2d_periodic_gpu_m): kernels, host-side handle and C ABI.
+// Reference: type(xy2d_gpu) src/xy2d_periodic_gpu_m.f90:14-59.
+//
+// Layout: the reference stores (cos, sin) as real64 SoA with a one-cell halo frame,
+// spins(0:nx+1, 0:ny+1, 1:2) (16 B/site + two real64 uniform arrays).  Here a spin is ONE
+// fp32 angle in TURNS (theta / 2 pi), colours split into compact arrays [ny][nx/2]
+// (4 B/site); the periodic wrap is index arithmetic, so there is no halo to refresh on one GPU.
+// A thread owns 4 consecutive colour-compact sites of one row (one aligned 128-bit load) and
+// reads 3 aligned float4 + 1 scalar of the other colour.  cos/sin come from the SFU
+// (MUFU.SIN/COS after reduction to [-1/2, 1/2) turns); uniforms from Philox in registers.
+#include <math.h>
+#include <stdlib.h>
+#include <new>
+#include "../../include/b200mc.h"
+#include "common.cuh"
+
+namespace {
+
+#define TWO_PI_F 6.283185307179586f
+#define INV_TWO_PI_F 0.15915494309189535f
+
+struct XYArgs {
+    float* own;
+    const float* oth;
+    int nxh, ny, gpr;  // sites per row per colour, rows, float4 groups per row
+    int colour;
+    float beta;
+    uint64_t draw;
+    uint32_t rk0[10];
+};
+
+__device__ __forceinline__ void sincos_turns(float t, float& s, float& c)
+{
+    const float r = t - rintf(t);           // [-1/2, 1/2]
+    __sincosf(r * TWO_PI_F, &s, &c);        // MUFU.SIN / MUFU.COS, |x| <= pi
+}
+
+template <uint32_t TAG>
+__device__ __forceinline__ uint4 philox_tag(uint4 c, const uint32_t (&rk0)[10])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t lo0, hi0, lo1, hi1;
+        mulwide(PHILOX_M0, c.x, lo0, hi0);
+        mulwide(PHILOX_M1, c.z, lo1, hi1);
+        uint4 n;
+        n.x = hi1 ^ c.y ^ rk0[r];
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ (TAG + (uint32_t)r * PHILOX_W1);
+        n.w = lo0;
+        c = n;
+    }
+    return c;
+}
+
+// neighbour field (sum of the four neighbour spins) for the 4 sites of group (y, g), colour a.colour
+__device__ __forceinline__ void xy_field(const XYArgs& a, int y, int g, float (&hx)[4], float (&hy)[4])
+{
+    const int nxh = a.nxh;
+    const int p = (y + a.colour) & 1;  // x0 = 2 xi + p
+    const int xi0 = 4 * g;
+    const float* row = a.oth + (size_t)y * nxh;
+    const int yu = (y + 1 == a.ny) ? 0 : y + 1, yd = (y == 0) ? a.ny - 1 : y - 1;
+    const float4 b = *reinterpret_cast<const float4*>(row + xi0);
+    const float4 u = *reinterpret_cast<const float4*>(a.oth + (size_t)yu * nxh + xi0);
+    const float4 d = *reinterpret_cast<const float4*>(a.oth + (size_t)yd * nxh + xi0);
+    // the fifth same-row value: left of the group (p = 0) or right of it (p = 1), periodic in x
+    const int xe = p ? (xi0 + 4 == nxh ? 0 : xi0 + 4) : (xi0 == 0 ? nxh - 1 : xi0 - 1);
+    const float e = row[xe];
+    float bs[5], bc[5];
+    // ordered left to right: p = 0: e, b.x, b.y, b.z, b.w ; p = 1: b.x, b.y, b.z, b.w, e
+    const float bv[5] = {p ? b.x : e, p ? b.y : b.x, p ? b.z : b.y, p ? b.w : b.z, p ? e : b.w};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) sincos_turns(bv[j], bs[j], bc[j]);
+    const float uv[4] = {u.x, u.y, u.z, u.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float us, uc, ds, dc;
+        sincos_turns(uv[j], us, uc);
+        sincos_turns(dv[j], ds, dc);
+        // site j (x0 = 2 (xi0 + j) + p): x-1 neighbour is bv[j], x+1 neighbour is bv[j + 1]
+        // (same summation order as calc_delta_energy, src/xy2d_periodic_gpu_m.f90:395: x+1, x-1, y+1, y-1)
+        hx[j] = bc[j + 1] + bc[j] + uc + dc;
+        hy[j] = bs[j + 1] + bs[j] + us + ds;
+    }
+}
+
+// update_sub + calc_delta_energy, src/xy2d_periodic_gpu_m.f90:368-397
+__global__ void __launch_bounds__(256)
+xy_metropolis_kernel(const __grid_constant__ XYArgs a)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.ny * a.gpr) return;
+    const int y = idx / a.gpr, g = idx - y * a.gpr;
+    float hx[4], hy[4];
+    xy_field(a, y, g, hx, hy);
+    float4* po = reinterpret_cast<float4*>(a.own + (size_t)y * a.nxh + 4 * g);
+    const float4 o = *po;
+    float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+        const uint4 R = philox_tag<TAG_XY>(mk_ctr((uint64_t)idx, a.draw, (uint32_t)a.colour, (uint32_t)sub), a.rk0);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int j = 2 * sub + e;
+            const uint32_t Ur = e ? R.z : R.x, Uc = e ? R.w : R.y;
+            const float r = ((float)Ur + 1.0f) * 0x1p-32f;       // (0, 1]
+            const float ct = ((float)Uc + 1.0f) * 0x1p-32f;      // candidate angle in turns
+            float cs, cc, ss, sc;
+            sincos_turns(ct, cs, cc);
+            sincos_turns(ov[j], ss, sc);
+            const float de = -((cc - sc) * hx[j] + (cs - ss) * hy[j]);
+            if (!(r > __expf(-a.beta * de))) ov[j] = ct;          // accept iff r <= exp(-beta dE), :384
+        }
+    }
+    *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
+}
+
+// over_relaxation_sub, :418-439: reflect the spin about the local field.  In angles:
+// theta' = 2 phi - theta with phi = atan2(h_y, h_x) (the reference's renormalisation is the identity here)
+__global__ void __launch_bounds__(256)
+xy_overrelax_kernel(const __grid_constant__ XYArgs a)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.ny * a.gpr) return;
+    const int y = idx / a.gpr, g = idx - y * a.gpr;
+    float hx[4], hy[4];
+    xy_field(a, y, g, hx, hy);
+    float4* po = reinterpret_cast<float4*>(a.own + (size_t)y * a.nxh + 4 * g);
+    const float4 o = *po;
+    float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float phi = atan2f(hy[j], hx[j]) * INV_TWO_PI_F;
+        const float t = 2.0f * phi - ov[j];
+        ov[j] = t - floorf(t);
+    }
+    *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
+}
+
+// fused E, Mx, My (three OpenACC reductions in the reference, :496-534), real64 accumulation.
+// acc[0] += -sum s . (s_{x+1} + s_{y+1}), acc[1] += sum cos, acc[2] += sum sin
+__global__ void __launch_bounds__(256)
+xy_measure_kernel(const float* __restrict__ c0, const float* __restrict__ c1, int nxh, int ny, int gpr, double* acc)
+{
+    double part[3] = {0.0, 0.0, 0.0};
+    const int total = ny * gpr;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int y = idx / gpr, g = idx - y * gpr, xi0 = 4 * g;
+        const int yu = (y + 1 == ny) ? 0 : y + 1;
+#pragma unroll
+        for (int colour = 0; colour < 2; ++colour) {
+            const float* own = colour ? c1 : c0;
+            const float* oth = colour ? c0 : c1;
+            const int p = (y + colour) & 1;
+            const float4 o = *reinterpret_cast<const float4*>(own + (size_t)y * nxh + xi0);
+            const float4 b = *reinterpret_cast<const float4*>(oth + (size_t)y * nxh + xi0);
+            const float4 u = *reinterpret_cast<const float4*>(oth + (size_t)yu * nxh + xi0);
+            // x+1 neighbour of site j: p = 0 -> b[j]; p = 1 -> b[j+1] (wraps to column 0)
+            const float e = p ? oth[(size_t)y * nxh + (xi0 + 4 == nxh ? 0 : xi0 + 4)] : 0.0f;
+            const float rv[4] = {p ? b.y : b.x, p ? b.z : b.y, p ? b.w : b.z, p ? e : b.w};
+            const float ov[4] = {o.x, o.y, o.z, o.w}, uv[4] = {u.x, u.y, u.z, u.w};
+            float es = 0.f, mx = 0.f, my = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float s, c, rs, rc, us, uc;
+                sincos_turns(ov[j], s, c);
+                sincos_turns(rv[j], rs, rc);
+                sincos_turns(uv[j], us, uc);
+                es -= c * (rc + uc) + s * (rs + us);
+                mx += c;
+                my += s;
+            }
+            part[0] += (double)es; part[1] += (double)mx; part[2] += (double)my;
+        }
+    }
+    block_atomic_add_f64<3>(acc, part);
+}
+
+// autocorrelation with the stored snapshot (:536-549) and the fixed-distance correlation (:551-567)
+// acc[0] += sum s . s0 ; acc[1] += sum s(x, y) . s(x + nx/2 - 1, y + ny/2 - 1)
+__global__ void __launch_bounds__(256)
+xy_corr_kernel(const float* __restrict__ c0, const float* __restrict__ c1, const float* __restrict__ z0,
+               const float* __restrict__ z1, int nx, int ny, double* acc)
+{
+    const int nxh = nx / 2;
+    double part[2] = {0.0, 0.0};
+    const long long total = (long long)nx * ny;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y0 = (int)(i / nx), x0 = (int)(i - (long long)y0 * nx);
+        const int col = (x0 + y0) & 1;
+        const float t = (col ? c1 : c0)[(size_t)y0 * nxh + (x0 >> 1)];
+        float s, c;
+        sincos_turns(t, s, c);
+        if (z0) {
+            const float t0 = (col ? z1 : z0)[(size_t)y0 * nxh + (x0 >> 1)];
+            float s0, cc0;
+            sincos_turns(t0, s0, cc0);
+            part[0] += (double)(c * cc0 + s * s0);
+        }
+        int xn = x0 + (nx / 2 - 1); if (xn >= nx) xn -= nx;
+        int yn = y0 + (ny / 2 - 1); if (yn >= ny) yn -= ny;
+        const int coln = (xn + yn) & 1;
+        const float tn = (coln ? c1 : c0)[(size_t)yn * nxh + (xn >> 1)];
+        float sn, cn;
+        sincos_turns(tn, sn, cn);
+        part[1] += (double)(c * cn + s * sn);
+    }
+    block_atomic_add_f64<2>(acc, part);
+}
+
+// set_random_spin_sub (:112-122): theta = 2 pi u  ->  turns = u
+__global__ void __launch_bounds__(256)
+xy_random_kernel(float* own, int nxh, int ny, int gpr, int colour, uint32_t seed, uint64_t draw)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ny * gpr) return;
+    const int y = idx / gpr, g = idx - y * gpr;
+    const uint4 R = philox4x32_10(mk_ctr((uint64_t)idx, draw, (uint32_t)colour, 0u), make_uint2(seed, TAG_INIT));
+    *reinterpret_cast<float4*>(own + (size_t)y * nxh + 4 * g) =
+        make_float4(((float)R.x + 1.0f) * 0x1p-32f, ((float)R.y + 1.0f) * 0x1p-32f, ((float)R.z + 1.0f) * 0x1p-32f, ((float)R.w + 1.0f) * 0x1p-32f);
+}
+
+__global__ void xy_fill_kernel(float* a, float* b, size_t n, float v)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { a[i] = v; b[i] = v; }
+}
+
+// rotate_whole_spin_theta_sub (:281-293): add a constant angle (turns)
+__global__ void xy_rotate_kernel(float* a, float* b, size_t n, float dt)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float t = a[i] + dt; a[i] = t - floorf(t);
+        t = b[i] + dt; b[i] = t - floorf(t);
+    }
+}
+
+// spins() in the reference layout spins(0:nx+1, 0:ny+1, 1:2), real64, halo frame refreshed, corners 0
+__global__ void xy_export_kernel(const float* c0, const float* c1, int nx, int ny, double* out)
+{
+    const long long W = nx + 2, Ht = ny + 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * Ht) return;
+    const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+    const bool xh = (x == 0 || x == nx + 1), yh = (y == 0 || y == ny + 1);
+    double c = 0.0, s = 0.0;
+    if (!(xh && yh)) {
+        const int x0 = x == 0 ? nx - 1 : (x == nx + 1 ? 0 : x - 1);
+        const int y0 = y == 0 ? ny - 1 : (y == ny + 1 ? 0 : y - 1);
+        const float t = (((x0 + y0) & 1) ? c1 : c0)[(size_t)y0 * (nx / 2) + (x0 >> 1)];
+        sincospi(2.0 * (double)t, &s, &c);
+    }
+    out[i] = c;
+    out[W * Ht + i] = s;
+}
+__global__ void xy_export_turns_kernel(const float* c0, const float* c1, int nx, int ny, float* out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nx * ny) return;
+    const int y0 = (int)(i / nx), x0 = (int)(i - (long long)y0 * nx);
+    out[i] = (((x0 + y0) & 1) ? c1 : c0)[(size_t)y0 * (nx / 2) + (x0 >> 1)];
+}
+__global__ void xy_import_turns_kernel(float* c0, float* c1, int nx, int ny, const float* in)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nx * ny) return;
+    const int y0 = (int)(i / nx), x0 = (int)(i - (long long)y0 * nx);
+    (((x0 + y0) & 1) ? c1 : c0)[(size_t)y0 * (nx / 2) + (x0 >> 1)] = in[i];
+}
+
+struct XY {
+    int64_t nx, ny;
+    int nxh, gpr;
+    float* c[2];   // colour arrays
+    float* z[2];   // autocorrelation snapshot (allocated on first use)
+    float* stage;  // nx*ny floats / export staging
+    double* d_acc;
+    cudaStream_t stream;
+    double beta;
+    uint32_t seed;
+    uint64_t draw;
+    bool obs_valid;
+    double obs[3];
+    int sms;
+};
+
+void fill_args(XY* m, int colour, XYArgs* a)
+{
+    a->own = m->c[colour]; a->oth = m->c[colour ^ 1];
+    a->nxh = m->nxh; a->ny = (int)m->ny; a->gpr = m->gpr; a->colour = colour;
+    a->beta = (float)m->beta; a->draw = m->draw;
+    for (int r = 0; r < 10; ++r) a->rk0[r] = m->seed + (uint32_t)r * PHILOX_W0;
+}
+
+int sweep(XY* m)
+{
+    m->obs_valid = false;
+    const int total = (int)m->ny * m->gpr;
+    for (int colour = 0; colour < 2; ++colour) {
+        XYArgs a;
+        fill_args(m, colour, &a);
+        COUNT_LAUNCH();
+        xy_metropolis_kernel<<<(total + 255) / 256, 256, 0, m->stream>>>(a);
+        CK(cudaGetLastError());
+    }
+    m->draw += 1;
+    return B200MC_OK;
+}
+
+int over_relax(XY* m, int n_steps)
+{
+    m->obs_valid = false;
+    const int total = (int)m->ny * m->gpr;
+    for (int i = 0; i < n_steps; ++i)
+        for (int colour = 0; colour < 2; ++colour) {
+            XYArgs a;
+            fill_args(m, colour, &a);
+            COUNT_LAUNCH();
+            xy_overrelax_kernel<<<(total + 255) / 256, 256, 0, m->stream>>>(a);
+            CK(cudaGetLastError());
+        }
+    return B200MC_OK;
+}
+
+int measure(XY* m)
+{
+    if (m->obs_valid) return B200MC_OK;
+    CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
+    COUNT_LAUNCH();
+    xy_measure_kernel<<<m->sms * 8, 256, 0, m->stream>>>(m->c[0], m->c[1], m->nxh, (int)m->ny, m->gpr, m->d_acc);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(m->obs, m->d_acc, 3 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->obs_valid = true;
+    return B200MC_OK;
+}
+
+int corr(XY* m, bool autoc, double* out)
+{
+    if (autoc && !m->z[0]) ARG_FAIL("calc_autocorrelation_sum before set_initial_magne_autocorrelation_state");
+    CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
+    COUNT_LAUNCH();
+    xy_corr_kernel<<<m->sms * 8, 256, 0, m->stream>>>(m->c[0], m->c[1], autoc ? m->z[0] : nullptr, autoc ? m->z[1] : nullptr, (int)m->nx, (int)m->ny, m->d_acc);
+    CK(cudaGetLastError());
+    double r[2];
+    CK(cudaMemcpyAsync(r, m->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->obs_valid = false;  // d_acc reused
+    *out = autoc ? r[0] : r[1];
+    return B200MC_OK;
+}
+
+void destroy(XY* m)
+{
+    cudaStreamSynchronize(m->stream);
+    cudaFree(m->c[0]); cudaFree(m->c[1]); cudaFree(m->z[0]); cudaFree(m->z[1]); cudaFree(m->stage); cudaFree(m->d_acc);
+    delete m;
+}
+
+int fill(XY* m, float v)
+{
+    const size_t n = (size_t)m->nxh * m->ny;
+    m->obs_valid = false;
+    COUNT_LAUNCH();
+    xy_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], n, v);
+    CK(cudaGetLastError());
+    return B200MC_OK;
+}
+
+int ensure_stage(XY* m)
+{
+    if (!m->stage) CK(cudaMalloc(&m->stage, (size_t)2 * (m->nx + 2) * (m->ny + 2) * sizeof(double)));
+    return B200MC_OK;
+}
+
+}  // namespace
+
+#define HX(h) (reinterpret_cast<XY*>(h))
+#define CHECK_X(h) do { if (!(h)) ARG_FAIL("invalid handle"); } while (0)
+
+extern "C" {
+
+int b200mc_xy2d_create(void** out, int64_t nx, int64_t ny, double kbt, int32_t iseed)
+{
+    if (!out) ARG_FAIL("null handle pointer");
+    *out = nullptr;
+    if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0");
+    // the reference needs nx, ny even (colouring, src/xy2d_periodic_gpu_m.f90:377-380); the float4 layout needs nx % 8 == 0
+    if (nx < 8 || ny < 2 || (ny & 1)) ARG_FAIL("xy2d: need nx >= 8, ny >= 2 even (got %lld x %lld)", (long long)nx, (long long)ny);
+    if (nx % 8) { snprintf(g_b200mc_err, sizeof(g_b200mc_err), "xy2d: nx must be a multiple of 8 in this build (got %lld)", (long long)nx); return B200MC_ERR_UNSUPPORTED; }
+    if ((nx / 2) * ny / 4 >= (int64_t)0x7FFFFFFF) ARG_FAIL("xy2d: lattice too large");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        snprintf(g_b200mc_err, sizeof(g_b200mc_err), "no CUDA device: this library has no CPU fallback");
+        return B200MC_ERR_CUDA;
+    }
+    XY* m = new (std::nothrow) XY();
+    if (!m) ARG_FAIL("out of host memory");
+    m->nx = nx; m->ny = ny; m->nxh = (int)(nx / 2); m->gpr = m->nxh / 4; m->stream = 0;
+    m->beta = 1 / kbt; m->seed = (uint32_t)iseed; m->draw = 0; m->obs_valid = false;
+    m->c[0] = m->c[1] = m->z[0] = m->z[1] = m->stage = nullptr; m->d_acc = nullptr;
+    int dev = 0; m->sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&m->sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t n = (size_t)m->nxh * ny;
+    if (cudaMalloc(&m->c[0], n * sizeof(float)) != cudaSuccess || cudaMalloc(&m->c[1], n * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&m->d_acc, 3 * sizeof(double)) != cudaSuccess) {
+        snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed");
+        destroy(m); return B200MC_ERR_CUDA;
+    }
+    int rc = fill(m, 0.0f);  // set_allup_spin: all along +x
+    if (rc) { destroy(m); return rc; }
+    *out = m;
+    return B200MC_OK;
+}
+int b200mc_xy2d_destroy(void* h) { if (h) destroy(HX(h)); return B200MC_OK; }
+int b200mc_xy2d_set_stream(void* h, void* s) { CHECK_X(h); HX(h)->stream = (cudaStream_t)s; return B200MC_OK; }
+int b200mc_xy2d_skip_curand(void* h, int64_t n)
+{
+    CHECK_X(h);
+    if (n < 0) ARG_FAIL("n_skip < 0");
+    const int64_t per = HX(h)->nx * HX(h)->ny;  // one generate call draws nall uniforms
+    HX(h)->draw += (uint64_t)((n + per - 1) / per);
+    return B200MC_OK;
+}
+int b200mc_xy2d_set_allup_spin(void* h) { CHECK_X(h); return fill(HX(h), 0.0f); }
+int b200mc_xy2d_set_random_spin(void* h)
+{
+    CHECK_X(h);
+    XY* m = HX(h);
+    m->obs_valid = false;
+    const int total = (int)m->ny * m->gpr;
+    for (int c = 0; c < 2; ++c) {
+        COUNT_LAUNCH();
+        xy_random_kernel<<<(total + 255) / 256, 256, 0, m->stream>>>(m->c[c], m->nxh, (int)m->ny, m->gpr, c, m->seed, m->draw);
+        CK(cudaGetLastError());
+    }
+    m->draw += 1;
+    return B200MC_OK;
+}
+int b200mc_xy2d_set_kbt(void* h, double kbt) { CHECK_X(h); if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0"); HX(h)->beta = 1 / kbt; return B200MC_OK; }
+int b200mc_xy2d_set_beta(void* h, double beta) { CHECK_X(h); HX(h)->beta = beta; return B200MC_OK; }
+int b200mc_xy2d_update(void* h) { CHECK_X(h); return sweep(HX(h)); }
+int b200mc_xy2d_update_n(void* h, int32_t n) { CHECK_X(h); for (int i = 0; i < n; ++i) { int rc = sweep(HX(h)); if (rc) return rc; } return B200MC_OK; }
+int b200mc_xy2d_update_over_relaxation(void* h, int32_t n_steps) { CHECK_X(h); return over_relax(HX(h), n_steps); }
+int b200mc_xy2d_calc_energy_sum(void* h, double* e) { CHECK_X(h); int rc = measure(HX(h)); if (rc) return rc; *e = HX(h)->obs[0]; return B200MC_OK; }
+int b200mc_xy2d_calc_magne_sum(void* h, double* m) { CHECK_X(h); int rc = measure(HX(h)); if (rc) return rc; *m = HX(h)->obs[1]; return B200MC_OK; }
+int b200mc_xy2d_calc_magne_y_sum(void* h, double* m) { CHECK_X(h); int rc = measure(HX(h)); if (rc) return rc; *m = HX(h)->obs[2]; return B200MC_OK; }
+int b200mc_xy2d_measure(void* h, double* e, double* mx, double* my)
+{
+    CHECK_X(h);
+    int rc = measure(HX(h));
+    if (rc) return rc;
+    if (e) *e = HX(h)->obs[0];
+    if (mx) *mx = HX(h)->obs[1];
+    if (my) *my = HX(h)->obs[2];
+    return B200MC_OK;
+}
+int b200mc_xy2d_set_initial_magne_autocorrelation_state(void* h)
+{
+    CHECK_X(h);
+    XY* m = HX(h);
+    const size_t n = (size_t)m->nxh * m->ny;
+    if (!m->z[0]) { CK(cudaMalloc(&m->z[0], n * sizeof(float))); CK(cudaMalloc(&m->z[1], n * sizeof(float))); }
+    CK(cudaMemcpyAsync(m->z[0], m->c[0], n * sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
+    CK(cudaMemcpyAsync(m->z[1], m->c[1], n * sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
+    return B200MC_OK;
+}
+int b200mc_xy2d_calc_autocorrelation_sum(void* h, double* r) { CHECK_X(h); return corr(HX(h), true, r); }
+int b200mc_xy2d_calc_correlation_sum(void* h, double* r) { CHECK_X(h); return corr(HX(h), false, r); }
+// rotate_summation_magne_toward_xaxis (:219-232): theta = atan2(My, Mx); rotate every spin by -theta
+int b200mc_xy2d_rotate_summation_magne_toward_xaxis(void* h, int32_t with_autocorrelation)
+{
+    CHECK_X(h);
+    XY* m = HX(h);
+    int rc = measure(m);
+    if (rc) return rc;
+    const double theta = atan2(m->obs[2], m->obs[1]);
+    const float dt = (float)(-theta / (2 * 3.14159265358979323846));
+    const size_t n = (size_t)m->nxh * m->ny;
+    m->obs_valid = false;
+    COUNT_LAUNCH();
+    xy_rotate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], n, dt);
+    if (with_autocorrelation && m->z[0]) {
+        COUNT_LAUNCH();
+        xy_rotate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->z[0], m->z[1], n, dt);
+    }
+    CK(cudaGetLastError());
+    return B200MC_OK;
+}
+int b200mc_xy2d_get_spins(void* h, double* out)
+{
+    CHECK_X(h);
+    if (!out) ARG_FAIL("null output");
+    XY* m = HX(h);
+    int rc = ensure_stage(m);
+    if (rc) return rc;
+    const long long n = (long long)(m->nx + 2) * (m->ny + 2);
+    COUNT_LAUNCH();
+    xy_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], (int)m->nx, (int)m->ny, reinterpret_cast<double*>(m->stage));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, m->stage, (size_t)2 * n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    return B200MC_OK;
+}
+// angles in turns (theta / 2 pi), fp32, row-major [ny][nx]: the build's native state (exact round trip)
+int b200mc_xy2d_get_angles(void* h, float* out)
+{
+    CHECK_X(h);
+    if (!out) ARG_FAIL("null output");
+    XY* m = HX(h);
+    int rc = ensure_stage(m);
+    if (rc) return rc;
+    const long long n = (long long)m->nx * m->ny;
+    COUNT_LAUNCH();
+    xy_export_turns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], (int)m->nx, (int)m->ny, m->stage);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, m->stage, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    return B200MC_OK;
+}
+int b200mc_xy2d_set_angles(void* h, const float* in)
+{
+    CHECK_X(h);
+    if (!in) ARG_FAIL("null input");
+    XY* m = HX(h);
+    int rc = ensure_stage(m);
+    if (rc) return rc;
+    const long long n = (long long)m->nx * m->ny;
+    m->obs_valid = false;
+    CK(cudaMemcpyAsync(m->stage, in, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    COUNT_LAUNCH();
+    xy_import_turns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], (int)m->nx, (int)m->ny, m->stage);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(m->stream));
+    return B200MC_OK;
+}
+int64_t b200mc_xy2d_nx(void* h) { return h ? HX(h)->nx : -1; }
+int64_t b200mc_xy2d_ny(void* h) { return h ? HX(h)->ny : -1; }
+int64_t b200mc_xy2d_nall(void* h) { return h ? HX(h)->nx * HX(h)->ny : -1; }
+double b200mc_xy2d_kbt(void* h) { return h ? 1 / HX(h)->beta : 0.0; }
+double b200mc_xy2d_beta(void* h) { return h ? HX(h)->beta : 0.0; }
+int b200mc_xy2d_sync(void* h) { CHECK_X(h); CK(cudaStreamSynchronize(HX(h)->stream)); return B200MC_OK; }
+
+}  // extern "C"

@@ -159,6 +159,46 @@ double b200mc_clock_kbt(void* h);
 double b200mc_clock_beta(void* h);
 int b200mc_clock_sync(void* h);
 
+/* ------------------------------------------------------------------------
+ * XY 2D, periodic -- type(xy2d_gpu), src/xy2d_periodic_gpu_m.f90:14-59.
+ * State: one fp32 angle per site (turns); energy / magnetisation are real64
+ * sums, compared with the reference at 1e-5 relative (BASELINE north_star).
+ * nx must be a multiple of 8 and ny even in this build (the reference needs both even).
+ * ------------------------------------------------------------------------ */
+int b200mc_xy2d_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed);  /* init, :61-78 */
+int b200mc_xy2d_destroy(void* h);
+int b200mc_xy2d_set_stream(void* h, void* cuda_stream);
+int b200mc_xy2d_skip_curand(void* h, int64_t n_skip);                 /* :79-84 */
+int b200mc_xy2d_set_allup_spin(void* h);                              /* :86-101 */
+int b200mc_xy2d_set_random_spin(void* h);                             /* :105-122 */
+int b200mc_xy2d_set_kbt(void* h, double kbt);                         /* :329-333 */
+int b200mc_xy2d_set_beta(void* h, double beta);                       /* :335-339 */
+int b200mc_xy2d_update(void* h);                                      /* Metropolis MCS, :353-397 */
+int b200mc_xy2d_update_n(void* h, int32_t n_sweeps);
+int b200mc_xy2d_update_over_relaxation(void* h, int32_t n_steps);     /* :400-439 */
+int b200mc_xy2d_calc_energy_sum(void* h, double* e);                  /* :469-472,496-508 */
+int b200mc_xy2d_calc_magne_sum(void* h, double* mx);                  /* :474-477,510-521 */
+int b200mc_xy2d_calc_magne_y_sum(void* h, double* my);                /* :479-482,523-534 */
+int b200mc_xy2d_measure(void* h, double* e, double* mx, double* my);  /* all three, one pass */
+int b200mc_xy2d_set_initial_magne_autocorrelation_state(void* h);     /* :342-350 */
+int b200mc_xy2d_calc_autocorrelation_sum(void* h, double* r);         /* :484-487,536-549 */
+int b200mc_xy2d_calc_correlation_sum(void* h, double* r);             /* :489-492,551-567 */
+/* rotate_summation_magne_toward_xaxis (:219-232); with_autocorrelation != 0 also rotates the
+ * stored snapshot (rotate_summation_magne_and_autocorrelation_toward_xaxis, :235-250) */
+int b200mc_xy2d_rotate_summation_magne_toward_xaxis(void* h, int32_t with_autocorrelation);
+/* spins(), :461-465: real64 (cos, sin), layout spins(0:nx+1, 0:ny+1, 1:2) -> 2 (nx+2)(ny+2) doubles;
+ * the halo frame is returned refreshed, corners 0 */
+int b200mc_xy2d_get_spins(void* h, double* out);
+/* native state: angles in turns, fp32, [ny][nx] row-major (exact round trip; used by the parity tests) */
+int b200mc_xy2d_get_angles(void* h, float* out);
+int b200mc_xy2d_set_angles(void* h, const float* in);
+int64_t b200mc_xy2d_nx(void* h);
+int64_t b200mc_xy2d_ny(void* h);
+int64_t b200mc_xy2d_nall(void* h);
+double b200mc_xy2d_kbt(void* h);
+double b200mc_xy2d_beta(void* h);
+int b200mc_xy2d_sync(void* h);
+
 #pragma GCC visibility pop
 #ifdef __cplusplus
 }

@@ -107,9 +107,8 @@ def _declare(L):
     d("orc_ising_uniforms_fast", None, u32, u64, i64, P)
     d("orc_ring_init_uniforms", None, u32, u64, i64, P)
     d("orc_clock_uniforms", None, u32, u64, i32, i64, P, P)
-    for name in ("orc_torus_clock_uniforms", "orc_xy_uniforms", "orc_xy_init_uniforms"):
-        if hasattr(L, name):
-            pass
+    d("orc_xy_uniforms", None, u32, u64, i64, i64, P, P)
+    d("orc_xy_init_uniforms", None, u32, u64, i64, i64, P)
 
 
 def _p(a: np.ndarray):
@@ -160,6 +159,19 @@ def clock_uniforms(seed: int, draw: int, replica: int, n_sites: int):
     p = np.empty(n_sites, dtype=np.float64)
     lib().orc_clock_uniforms(seed & 0xFFFFFFFF, draw, replica, n_sites, _p(r), _p(p))
     return r, p
+
+
+def xy_uniforms(seed: int, draw: int, nx: int, ny: int):
+    r = np.empty(nx * ny, dtype=np.float64)
+    c = np.empty(nx * ny, dtype=np.float64)
+    lib().orc_xy_uniforms(seed & 0xFFFFFFFF, draw, nx, ny, _p(r), _p(c))
+    return r, c
+
+
+def xy_init_uniforms(seed: int, draw: int, nx: int, ny: int):
+    r = np.empty(nx * ny, dtype=np.float64)
+    lib().orc_xy_init_uniforms(seed & 0xFFFFFFFF, draw, nx, ny, _p(r))
+    return r
 
 
 # --------------------------------------------------------------------------

@@ -168,3 +168,49 @@ ORC_API void orc_ising_uniforms_fast(uint32_t seed, uint64_t draw, int64_t n_sit
         }
     }
 }
+
+/* --------------------------------------------------------------------------
+ * XY periodic (xy2d_periodic_gpu_m): true torus, colour = (x0 + y0) & 1 with
+ * 0-based x0, y0 (== the reference's (x + y) parity).  Colour-compact index
+ * xi = x0 >> 1; a "group" is 4 consecutive xi of one row: blk = y0 * gpr + (xi >> 2),
+ * gpr = ceil((nx/2) / 4).  Two 32-bit uniforms per site and sweep:
+ *   R = philox(ctr(blk, draw, colour, (xi & 3) >> 1), (seed, TAG_XY))
+ *   accept    U_r = R[2 * (xi & 1)]      -> randoms(x, y)
+ *   candidate U_c = R[2 * (xi & 1) + 1]  -> candidates(x, y)
+ * u = (U + 1) 2^-32.  The GPU rounds both to fp32 (XY section).
+ * set_random_spin: R = philox(ctr(blk, draw, colour, 0), (seed, TAG_INIT)), U = R[xi & 3].
+ * Arrays are written in the reference's order randoms(nx, ny): out[x0 + nx * y0].
+ * -------------------------------------------------------------------------- */
+ORC_API void orc_xy_uniforms(uint32_t seed, uint64_t draw, int64_t nx, int64_t ny, double *randoms,
+                             double *candidates)
+{
+    const int64_t nxh = nx / 2, gpr = (nxh + 3) / 4;
+    const uint32_t key[2] = {seed, TAG_XY};
+#pragma omp parallel for schedule(static)
+    for (int64_t y0 = 0; y0 < ny; ++y0)
+        for (int64_t x0 = 0; x0 < nx; ++x0) {
+            const uint32_t colour = (uint32_t)((x0 + y0) & 1);
+            const int64_t xi = x0 >> 1;
+            uint32_t c[4], r[4];
+            mk_ctr(c, (uint64_t)(y0 * gpr + (xi >> 2)), draw, colour, (uint32_t)((xi & 3) >> 1));
+            orc_philox4x32_10(c, key, r);
+            randoms[x0 + nx * y0] = ((double)r[2 * (xi & 1)] + 1.0) * 0x1p-32;
+            candidates[x0 + nx * y0] = ((double)r[2 * (xi & 1) + 1] + 1.0) * 0x1p-32;
+        }
+}
+
+ORC_API void orc_xy_init_uniforms(uint32_t seed, uint64_t draw, int64_t nx, int64_t ny, double *out)
+{
+    const int64_t nxh = nx / 2, gpr = (nxh + 3) / 4;
+    const uint32_t key[2] = {seed, TAG_INIT};
+#pragma omp parallel for schedule(static)
+    for (int64_t y0 = 0; y0 < ny; ++y0)
+        for (int64_t x0 = 0; x0 < nx; ++x0) {
+            const uint32_t colour = (uint32_t)((x0 + y0) & 1);
+            const int64_t xi = x0 >> 1;
+            uint32_t c[4], r[4];
+            mk_ctr(c, (uint64_t)(y0 * gpr + (xi >> 2)), draw, colour, 0);
+            orc_philox4x32_10(c, key, r);
+            out[x0 + nx * y0] = ((double)r[xi & 3] + 1.0) * 0x1p-32;
+        }
+}

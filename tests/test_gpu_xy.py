@@ -1,0 +1,131 @@
+"""GPU parity: XY periodic (Metropolis + over-relaxation) vs the real64 CPU oracle.
+
+Bar (BASELINE north_star): energy and magnetisation within 1e-5 RELATIVE TOLERANCE, per sweep from
+identical input state and identical uniforms (the GPU keeps fp32 angles and fp32 SFU math; long
+trajectories are chaotic, so the state is re-synchronised to the GPU's after every sweep)."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _sync_oracle(o, g):
+    o.set_angles(2 * math.pi * g.angles().astype(np.float64))
+
+
+def _close(a, b, scale):
+    return abs(a - b) <= RTOL * scale
+
+
+@pytest.mark.parametrize("shape,kbt", [((16, 8), 0.89), ((64, 64), 0.895), ((256, 128), 0.5), ((1024, 512), 0.89), ((40, 30), 1.5)])
+def test_xy_metropolis_per_sweep(oracle, shape, kbt):
+    from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
+    nx, ny = shape
+    g = xm.xy2d_gpu().init(nx, ny, kbt, 42)
+    o = oracle.xy2d_gpu().init(nx, ny, kbt, 42)
+    n = nx * ny
+    assert g.measure() == (-2.0 * n, 1.0 * n, 0.0)                         # all-up known answer
+    g.set_random_spin()
+    # set_random_spin: theta = 2 pi u with the contract's init uniforms
+    u = oracle.xy_init_uniforms(42, 0, nx, ny).reshape(ny, nx)
+    assert np.allclose(g.angles(), u, atol=2 ** -24)
+    for sweep in range(5):
+        _sync_oracle(o, g)
+        e0, mx0, my0 = g.measure()
+        assert _close(e0, o.calc_energy_sum(), n) and _close(mx0, o.calc_magne_sum(), n) and _close(my0, o.calc_magne_y_sum(), n)
+        r, c = oracle.xy_uniforms(42, 1 + sweep, nx, ny)
+        g.update()
+        o.update(r, c)
+        e, mx, my = g.measure()
+        assert _close(e, o.calc_energy_sum(), max(abs(o.calc_energy_sum()), 0.05 * n)), (e, o.calc_energy_sum())
+        assert _close(mx, o.calc_magne_sum(), n) and _close(my, o.calc_magne_y_sum(), n)
+        # site-level: all but a handful of borderline accept decisions agree
+        go = g.angles().astype(np.float64)
+        oo = np.arctan2(o.sp[1, 1:-1, 1:-1], o.sp[0, 1:-1, 1:-1]) / (2 * math.pi)
+        d = np.abs(((go - oo + 0.5) % 1.0) - 0.5)
+        assert (d > 1e-5).mean() < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(16, 8), (128, 64), (1024, 512)])
+def test_xy_over_relaxation(oracle, shape):
+    from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
+    nx, ny = shape
+    g = xm.xy2d_gpu().init(nx, ny, 0.89, 7)
+    o = oracle.xy2d_gpu().init(nx, ny, 0.89, 7)
+    n = nx * ny
+    g.set_random_spin()
+    g.update_n(3)                                   # some local order so the local fields are not tiny
+    for it in range(3):
+        _sync_oracle(o, g)
+        e_before = g.calc_energy_sum()
+        g.update_over_relaxation(1)
+        o.update_over_relaxation(1)
+        e, mx, my = g.measure()
+        assert abs(e - e_before) / n < 1e-5         # microcanonical: energy conserved
+        assert _close(e, o.calc_energy_sum(), max(abs(o.calc_energy_sum()), 0.05 * n))
+        assert _close(mx, o.calc_magne_sum(), n) and _close(my, o.calc_magne_y_sum(), n)
+        go = g.angles().astype(np.float64)
+        oo = np.arctan2(o.sp[1, 1:-1, 1:-1], o.sp[0, 1:-1, 1:-1]) / (2 * math.pi)
+        d = np.abs(((go - oo + 0.5) % 1.0) - 0.5)
+        assert d.max() < 5e-5                        # a reflection amplifies angle error by < 3; SFU sincos is ~1e-7 turns
+
+
+def test_xy_spins_layout_and_helpers(oracle):
+    from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
+    nx, ny = 32, 16
+    g = xm.xy2d_gpu().init(nx, ny, 0.89, 3)
+    o = oracle.xy2d_gpu().init(nx, ny, 0.89, 3)
+    g.set_random_spin()
+    _sync_oracle(o, g)
+    s = g.spins()
+    assert s.shape == o.sp.shape
+    assert np.allclose(s, o.sp, atol=1e-12)          # interior, halo frame and zero corners
+    # autocorrelation / correlation / rotation helpers
+    g.set_initial_magne_autocorrelation_state(); o.set_initial_magne_autocorrelation_state()
+    assert _close(g.calc_autocorrelation_sum(), nx * ny, nx * ny)
+    g.update_n(2)
+    _sync_oracle(o, g)
+    assert _close(g.calc_autocorrelation_sum(), o.calc_autocorrelation_sum(), nx * ny)
+    assert _close(g.calc_correlation_sum(), o.calc_correlation_sum(), nx * ny)
+    g.rotate_summation_magne_toward_xaxis()
+    e, mx, my = g.measure()
+    assert abs(my) < 1e-4 * nx * ny and mx > 0
+    # round trip of the native state
+    a = g.angles()
+    g.set_angles(a)
+    assert np.array_equal(g.angles(), a)
+
+
+def test_xy_limits_and_statistics():
+    from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
+    g = xm.xy2d_gpu().init(256, 256, 0.89, 11)
+    n = g.nall()
+    g.set_beta(1e9)                                  # beta -> inf from all-up: every candidate raises E, none accepted
+    g.update_n(2)
+    assert g.measure()[0] == -2.0 * n
+    g.set_beta(0.0)                                  # beta = 0: everything accepted -> uniform angles, E ~ 0
+    g.update()
+    e, mx, my = g.measure()
+    assert abs(e) < 0.05 * n and abs(mx) < 0.05 * n and abs(my) < 0.05 * n
+    # low-temperature energy: spin-wave result e ~ -2 + kbt/2 per site
+    g.set_allup_spin(); g.set_kbt(0.2)
+    for _ in range(300):
+        g.update(); g.update_over_relaxation(1)
+    e = g.calc_energy_sum() / n
+    assert abs(e - (-2 + 0.1)) < 0.02, e
+
+
+def test_xy_full_size_properties():
+    """BASELINE config 3: 16384 x 16384"""
+    from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
+    g = xm.xy2d_gpu().init(16384, 16384, 0.89, 42)
+    n = g.nall()
+    assert g.measure() == (-2.0 * n, 1.0 * n, 0.0)
+    g.set_random_spin()
+    g.update(); e1 = g.calc_energy_sum()
+    g.update_over_relaxation(1); e2 = g.calc_energy_sum()
+    assert abs(e2 - e1) / n < 1e-5                   # over-relaxation conserves energy
+    assert -2.0 * n < e1 < 0
