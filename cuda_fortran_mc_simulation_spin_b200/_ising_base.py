@@ -12,6 +12,21 @@ METROPOLIS = 0
 HEATBATH = 1
 
 
+def unique_id() -> bytes:
+    """NCCL unique id for a slab-decomposed job (call on rank 0, broadcast to the others)"""
+    buf = C.create_string_buffer(128)
+    _lib.check(_lib.fn("b200mc_dist_unique_id", C.c_int, C.c_char_p)(buf))
+    return buf.raw
+
+
+def slab_geometry(nx, ny, nz, rank, nranks):
+    """host-only: {Nc, L, H, p0, Lloc, ptail} of the slab `rank` of `nranks` would own (nz = 0: 2D)"""
+    out = (C.c_int64 * 6)()
+    _lib.check(_lib.fn("b200mc_ring_slab_geometry", C.c_int, i64, i64, i64, i32, i32, C.POINTER(C.c_int64))(
+        int(nx), int(ny), int(nz), int(rank), int(nranks), out))
+    return dict(zip(("Nc", "L", "H", "p0", "Lloc", "ptail"), [int(x) for x in out]))
+
+
 class _IsingBase:
     _pfx = ""      # "b200mc_ising2d" / "b200mc_ising3d"
     _ndim = 0
@@ -34,6 +49,41 @@ class _IsingBase:
                 self._h = C.c_void_p(None)
         except Exception:
             pass
+
+    # -- slab decomposition over ranks (one process per GPU) ----
+    def _init_slab(self, dims, kbt, iseed, rank, nranks, nccl_id):
+        if self._h:
+            self._f("destroy", C.c_int, P)(self._h)
+            self._h = C.c_void_p(None)
+        if len(nccl_id) != 128:
+            raise ValueError("nccl_id must be the 128 bytes of b200mc_dist_unique_id")
+        f = self._f("create_slab", C.c_int, PP, *([i64] * len(dims)), f64, i32, i32, i32, C.c_char_p)
+        _lib.check(f(C.byref(self._h), *[int(d) for d in dims], float(kbt), int(iseed), int(rank), int(nranks),
+                     bytes(nccl_id)))
+        self._rank, self._nranks = int(rank), int(nranks)
+        return self
+
+    def _init_torch_distributed(self, dims, kbt, iseed, group=None):
+        """slab mode driven by an initialised torch.distributed job: rank 0 draws the NCCL id of the
+        library's own communicator, the job's process group only broadcasts those 128 bytes"""
+        import torch.distributed as dist
+
+        rank, nranks = dist.get_rank(group), dist.get_world_size(group)
+        box = [unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self._group = group
+        return self._init_slab(dims, kbt, iseed, rank, nranks, box[0])
+
+    def rank_info(self):
+        r, n = C.c_int32(0), C.c_int32(1)
+        self._call("rank_info", C.byref(r), C.byref(n), argtypes=(C.POINTER(C.c_int32), C.POINTER(C.c_int32)))
+        return int(r.value), int(n.value)
+
+    def spins_local(self):
+        """spins() of this rank only: sites owned by other ranks read INT32_MIN"""
+        out = np.empty(self.nall() + 2 * self._halo(), dtype=np.int32)
+        self._call("get_spins", out.ctypes.data_as(P), argtypes=(P,))
+        return out
 
     # -- setters (reference names) ---------------------------------------
     def set_allup_spin(self):
@@ -87,8 +137,16 @@ class _IsingBase:
         raise NotImplementedError
 
     def spins(self):
-        out = np.empty(self.nall() + 2 * self._halo(), dtype=np.int32)
-        self._call("get_spins", out.ctypes.data_as(P), argtypes=(P,))
+        out = self.spins_local()
+        if getattr(self, "_nranks", 1) > 1:
+            import torch
+            import torch.distributed as dist
+
+            t = torch.from_numpy(out)
+            if dist.get_backend(getattr(self, "_group", None)) == "nccl":
+                t = t.cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=getattr(self, "_group", None))
+            out = t.cpu().numpy()
         return out
 
     def set_spins(self, spins):

@@ -16,6 +16,8 @@ struct Ising {
     int64_t nx, ny, nz;
     RingStore st;
     cudaStream_t stream;
+    cudaStream_t comm_stream;          // slab mode: halo exchange overlapped with the interior launch
+    cudaEvent_t ev_boundary, ev_halo;  // boundary vectors written / halo blocks received
     double beta;
     uint32_t seed;
     uint64_t draw;
@@ -117,41 +119,76 @@ int build_tables(Ising* m)
 }
 
 template <int NNB>
-int launch_pass(Ising* m, int colour)
+int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered)
 {
     const RingGeom& g = m->st.g;
     RingPassArgs a;
-    a.own = m->st.vec[colour];
-    a.oth = m->st.vec[colour ^ 1];
-    a.nvec = g.L;
+    a.own = m->st.vec[colour] + vbeg;
+    a.oth = m->st.vec[colour ^ 1] + vbeg;
+    a.nvec = n;
     a.H = g.H;
-    a.p0 = 0;
+    a.p0 = g.p0 + vbeg;
     for (int j = 0; j < 6; ++j) a.off[j] = g.off[colour][j];
     a.seed = m->seed;
     a.colour = (uint32_t)colour;
     a.draw = m->draw;
     a.ticket = nullptr;
     a.chunk = m->chunk;
-    if (!(m->tune & 1) && g.L > (int64_t)m->grid * 256 * 4) {
+    int64_t need = (n + 255) / 256;
+    const int grid = (int)(need < (int64_t)m->grid ? need : (int64_t)m->grid);
+    if (ordered && !(m->tune & 1) && n > (int64_t)m->grid * 256 * 4) {
         a.ticket = m->d_ticket;
         CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
     }
+    COUNT_LAUNCH();
+    if (m->method == METHOD_METROPOLIS) {
+        if (a.ticket) ising_pass_kernel<NNB, METHOD_METROPOLIS, true><<<grid, 256, 0, m->stream>>>(a, m->tab);
+        else ising_pass_kernel<NNB, METHOD_METROPOLIS, false><<<grid, 256, 0, m->stream>>>(a, m->tab);
+    } else {
+        if (a.ticket) ising_pass_kernel<NNB, METHOD_HEATBATH, true><<<grid, 256, 0, m->stream>>>(a, m->tab);
+        else ising_pass_kernel<NNB, METHOD_HEATBATH, false><<<grid, 256, 0, m->stream>>>(a, m->tab);
+    }
+    CK(cudaGetLastError());
+    return B200MC_OK;
+}
+
+// One colour pass + halo refresh.  Single GPU: one launch over the whole fold, then the halo kernel.
+// Slab mode: the first and last H owned vectors (what the neighbouring ranks need) are updated first,
+// their exchange runs on the comm stream while the interior launch runs on the compute stream.
+template <int NNB>
+int launch_pass(Ising* m, int colour)
+{
+    const RingGeom& g = m->st.g;
     m->obs_valid = false;
     if (m->timing) {
         while (m->evs.size() < m->ev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); m->evs.push_back(e); }
         CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
     }
-    COUNT_LAUNCH();
-    if (m->method == METHOD_METROPOLIS) {
-        if (a.ticket) ising_pass_kernel<NNB, METHOD_METROPOLIS, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
-        else ising_pass_kernel<NNB, METHOD_METROPOLIS, false><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
-    } else {
-        if (a.ticket) ising_pass_kernel<NNB, METHOD_HEATBATH, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
-        else ising_pass_kernel<NNB, METHOD_HEATBATH, false><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+    int rc;
+    if (g.nranks == 1) {
+        rc = launch_range<NNB>(m, colour, 0, g.Lloc, true);
+        if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
+        if (rc) return rc;
+        return ring_halo(&m->st, colour, m->stream);
     }
+    const bool split = g.Lloc >= 4 * g.H && !(m->tune & 2);
+    if (!split) {
+        rc = launch_range<NNB>(m, colour, 0, g.Lloc, true);
+        if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
+        if (rc) return rc;
+        return ring_halo(&m->st, colour, m->stream);
+    }
+    if ((rc = launch_range<NNB>(m, colour, 0, g.H, false))) return rc;
+    if ((rc = launch_range<NNB>(m, colour, g.Lloc - g.H, g.H, false))) return rc;
+    CK(cudaEventRecord(m->ev_boundary, m->stream));
+    CK(cudaStreamWaitEvent(m->comm_stream, m->ev_boundary, 0));
+    if ((rc = ring_halo(&m->st, colour, m->comm_stream))) return rc;
+    CK(cudaEventRecord(m->ev_halo, m->comm_stream));
+    rc = launch_range<NNB>(m, colour, g.H, g.Lloc - 2 * g.H, true);
     if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
-    CK(cudaGetLastError());
-    return ring_halo(&m->st, colour, m->stream);
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(m->stream, m->ev_halo, 0));
+    return B200MC_OK;
 }
 
 int sweep(Ising* m)
@@ -172,16 +209,16 @@ int launch_pass_randoms(Ising* m, int colour)
     RingPassArgs a;
     a.own = m->st.vec[colour];
     a.oth = m->st.vec[colour ^ 1];
-    a.nvec = g.L;
+    a.nvec = g.Lloc;
     a.H = g.H;
-    a.p0 = 0;
+    a.p0 = g.p0;
     for (int j = 0; j < 6; ++j) a.off[j] = g.off[colour][j];
     a.seed = m->seed;
     a.colour = (uint32_t)colour;
     a.draw = m->draw;
     a.ticket = nullptr;
     a.chunk = 128;
-    const unsigned grid = (unsigned)((g.L + 255) / 256);
+    const unsigned grid = (unsigned)((g.Lloc + 255) / 256);
     m->obs_valid = false;
     COUNT_LAUNCH();
     if (m->method == METHOD_METROPOLIS)
@@ -203,10 +240,14 @@ int measure(Ising* m, int64_t* e, int64_t* mag)
     COUNT_LAUNCH();
     CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
     if (m->ndim == 3)
-        ising_measure_kernel<6><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.L, g.H, 0, m->d_off1, g.L, g.Nc, g.ptail, m->d_acc);
+        ising_measure_kernel<6><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, m->d_acc);
     else
-        ising_measure_kernel<4><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.L, g.H, 0, m->d_off1, g.L, g.Nc, g.ptail, m->d_acc);
+        ising_measure_kernel<4><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, m->d_acc);
     CK(cudaGetLastError());
+    if (g.nranks > 1) {  // every rank gets the global sums (allreduce of {X, sum s})
+        int rc = dist_allreduce_u64(m->st.comm, m->d_acc, 2, m->stream);
+        if (rc) return rc;
+    }
     unsigned long long acc[2];
     CK(cudaMemcpyAsync(acc, m->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
@@ -220,7 +261,10 @@ int measure(Ising* m, int64_t* e, int64_t* mag)
     return B200MC_OK;
 }
 
-int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed)
+int destroy(struct Ising* m);
+
+int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed,
+           int rank = 0, int nranks = 1, const char* nccl_id = nullptr)
 {
     if (!out) ARG_FAIL("null handle pointer");
     *out = nullptr;
@@ -237,15 +281,30 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; t = getenv("B200MC_CHUNK"); m->chunk = t ? atoi(t) : 128; if (m->chunk < 32 || (m->chunk & 31)) m->chunk = 128; }
     m->method = METHOD_METROPOLIS; m->seed = (uint32_t)iseed; m->draw = 0; m->alive = true;
     m->obs_valid = false; m->timing = false; m->ev_used = 0;
+    m->comm_stream = nullptr; m->ev_boundary = m->ev_halo = nullptr; m->st.comm = nullptr;
     int rc = ring_geom_init(&m->st.g, nx, ny, m->nz);
     if (rc) { delete m; return rc; }
+    rc = ring_geom_set_slab(&m->st.g, rank, nranks);
+    if (rc) { delete m; return rc; }
+    if (nranks > 1) {
+        if (!nccl_id) { delete m; ARG_FAIL("slab mode needs the NCCL unique id of the job (b200mc_dist_unique_id on rank 0, broadcast by the caller)"); }
+        rc = dist_comm_init(&m->st.comm, rank, nranks, nccl_id);
+        if (rc) { delete m; return rc; }
+        if (cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_boundary, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_halo, cudaEventDisableTiming) != cudaSuccess) {
+            snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cannot create the comm stream / events");
+            dist_comm_destroy(m->st.comm); delete m; return B200MC_ERR_CUDA;
+        }
+    }
     rc = ring_alloc(&m->st);
-    if (rc) { ring_free(&m->st); delete m; return rc; }
+    if (rc) { destroy(m); return rc; }
     if (cudaMalloc(&m->d_ticket, TK_NCNT * 64 * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&m->d_off1, 6 * sizeof(int64_t)) != cudaSuccess) {
+        destroy(m);
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed");
-        ring_free(&m->st); cudaFree(m->d_acc); cudaFree(m->d_off1); delete m; return B200MC_ERR_CUDA;
+        return B200MC_ERR_CUDA;
     }
     cudaMemcpy(m->d_off1, m->st.g.off[1], 6 * sizeof(int64_t), cudaMemcpyHostToDevice);
     // persistent-style grid: SMs x resident blocks, grid-stride over the vectors
@@ -255,12 +314,12 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     if (ndim == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ising_pass_kernel<6, METHOD_METROPOLIS, true>, 256, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ising_pass_kernel<4, METHOD_METROPOLIS, true>, 256, 0);
     if (occ < 1) occ = 1;
-    int64_t need = (m->st.g.L + 255) / 256;
+    int64_t need = (m->st.g.Lloc + 255) / 256;
     m->grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);
     m->beta = 1 / kbt;
     build_tables(m);
     rc = ring_fill(&m->st, 1, m->stream);  // set_allup_spin
-    if (rc) { ring_free(&m->st); cudaFree(m->d_acc); cudaFree(m->d_off1); delete m; return rc; }
+    if (rc) { destroy(m); return rc; }
     *out = m;
     return B200MC_OK;
 }
@@ -275,6 +334,10 @@ int destroy(Ising* m)
     cudaFree(m->d_randoms);
     cudaFree(m->d_ticket);
     for (cudaEvent_t e : m->evs) cudaEventDestroy(e);
+    if (m->comm_stream) { cudaStreamSynchronize(m->comm_stream); cudaStreamDestroy(m->comm_stream); }
+    if (m->ev_boundary) cudaEventDestroy(m->ev_boundary);
+    if (m->ev_halo) cudaEventDestroy(m->ev_halo);
+    dist_comm_destroy(m->st.comm);
     delete m;
     return B200MC_OK;
 }
@@ -285,7 +348,7 @@ int set_random(Ising* m)
     m->obs_valid = false;
     for (int c = 0; c < 2; ++c) {
         COUNT_LAUNCH();
-        ring_random_bits_kernel<<<(unsigned)((g.L + 255) / 256), 256, 0, m->stream>>>(m->st.vec[c], g.L, g.H, 0, m->seed, m->draw, (uint32_t)c);
+        ring_random_bits_kernel<<<(unsigned)((g.Lloc + 255) / 256), 256, 0, m->stream>>>(m->st.vec[c], g.Lloc, g.H, g.p0, m->seed, m->draw, (uint32_t)c);
         CK(cudaGetLastError());
     }
     m->draw += 1;
@@ -397,6 +460,30 @@ int b200mc_ising2d_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t 
 {
     return create(h, 2, nx, ny, 0, kbt, iseed);
 }
+int b200mc_dist_unique_id(char out[128]) { return dist_unique_id(out); }
+int b200mc_ising3d_create_slab(void** h, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed,
+                               int32_t rank, int32_t nranks, const char nccl_id[128])
+{
+    if (nz <= 0) ARG_FAIL("nz must be > 0");
+    return create(h, 3, nx, ny, nz, kbt, iseed, rank, nranks, nccl_id);
+}
+int b200mc_ising2d_create_slab(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed,
+                               int32_t rank, int32_t nranks, const char nccl_id[128])
+{
+    return create(h, 2, nx, ny, 0, kbt, iseed, rank, nranks, nccl_id);
+}
+int b200mc_ring_slab_geometry(int64_t nx, int64_t ny, int64_t nz, int32_t rank, int32_t nranks, int64_t out[6])
+{
+    RingGeom g;
+    int rc = ring_geom_init(&g, nx, ny, nz);
+    if (rc) return rc;
+    rc = ring_geom_set_slab(&g, rank, nranks);
+    if (rc) return rc;
+    out[0] = g.Nc; out[1] = g.L; out[2] = g.H; out[3] = g.p0; out[4] = g.Lloc; out[5] = g.ptail;
+    return B200MC_OK;
+}
+int b200mc_ising3d_rank_info(void* h, int32_t* rank, int32_t* nranks) { CHECK_H(h, 3); *rank = H(h)->st.g.rank; *nranks = H(h)->st.g.nranks; return B200MC_OK; }
+int b200mc_ising2d_rank_info(void* h, int32_t* rank, int32_t* nranks) { CHECK_H(h, 2); *rank = H(h)->st.g.rank; *nranks = H(h)->st.g.nranks; return B200MC_OK; }
 int64_t b200mc_ising3d_nz(void* h) { return h ? H(h)->nz : -1; }
 int b200mc_ising3d_get_ws(void* h, double out[14])
 {

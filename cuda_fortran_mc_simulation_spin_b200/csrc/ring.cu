@@ -1,6 +1,10 @@
 // Folded-ring storage: geometry, halo ("norishiro") refresh, import/export.
 // See ring.cuh for the layout.
 #include "ring.cuh"
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+#include <limits.h>
 
 thread_local char g_b200mc_err[512] = {0};
 unsigned long long g_b200mc_launches = 0;
@@ -33,14 +37,28 @@ int ring_geom_init(RingGeom* g, int64_t nx, int64_t ny, int64_t nz)
     // lanes 0..14 are full; lane 15 holds Nc - 15 L sites (may be <= 0 for tiny rings)
     int64_t l15 = g->Nc - 15 * g->L;
     g->ptail = l15 < 0 ? 0 : l15;
+    g->p0 = 0; g->Lloc = g->L; g->rank = 0; g->nranks = 1;
     if (g->N / g->P < 2) ARG_FAIL("lattice too small");
     if (g->L + 2 * g->H >= (int64_t)0x7C000000) ARG_FAIL("lattice too large for 32-bit vector indices (%lld vectors per colour)", (long long)g->L);
     return B200MC_OK;
 }
 
+int ring_geom_set_slab(RingGeom* g, int rank, int nranks)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks) ARG_FAIL("bad rank %d / %d", rank, nranks);
+    if (nranks == 1) return B200MC_OK;
+    if (g->Nc % 16) ARG_FAIL("slab decomposition needs the number of sites per colour (%lld) to be a multiple of 16", (long long)g->Nc);
+    const int64_t base = g->L / nranks, rem = g->L % nranks;
+    g->Lloc = base + (rank < rem ? 1 : 0);
+    g->p0 = rank * base + (rank < rem ? rank : rem);
+    g->rank = rank; g->nranks = nranks;
+    if (base < g->H) ARG_FAIL("slab too thin: %lld positions per rank < halo %lld", (long long)base, (long long)g->H);
+    return B200MC_OK;
+}
+
 int ring_alloc(RingStore* s)
 {
-    const size_t nv = (size_t)(s->g.L + 2 * s->g.H);
+    const size_t nv = (size_t)(s->g.Lloc + 2 * s->g.H);
     s->vec[0] = s->vec[1] = nullptr;
     s->stage = nullptr;
     CK(cudaMalloc(&s->vec[0], nv * sizeof(uint4)));
@@ -62,7 +80,7 @@ void ring_free(RingStore* s)
 
 int ring_fill(RingStore* s, uint8_t value, cudaStream_t st)
 {
-    const size_t nv = (size_t)(s->g.L + 2 * s->g.H);
+    const size_t nv = (size_t)(s->g.Lloc + 2 * s->g.H);
     CK(cudaMemsetAsync(s->vec[0], value, nv * sizeof(uint4), st));
     CK(cudaMemsetAsync(s->vec[1], value, nv * sizeof(uint4), st));
     return B200MC_OK;
@@ -134,9 +152,123 @@ __global__ void ring_halo_fast_kernel(uint4* vec, int64_t L, int64_t H, int64_t 
     }
 }
 
+// ---- NCCL through dlsym -------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+} g_nccl;
+
+int nccl_load()
+{
+    if (g_nccl.lib) return B200MC_OK;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cannot load libnccl.so.2: %s", dlerror()); return B200MC_ERR_UNSUPPORTED; }
+#define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(lib, name); if (!g_nccl.field) { snprintf(g_b200mc_err, sizeof(g_b200mc_err), "libnccl: missing %s", name); return B200MC_ERR_UNSUPPORTED; }
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+    SYM(AllReduce, "ncclAllReduce") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.lib = lib;
+    return B200MC_OK;
+}
+#define NK(call)                                                                                      \
+    do {                                                                                              \
+        ncclResult_t r_ = (call);                                                                     \
+        if (r_ != ncclSuccess) {                                                                      \
+            snprintf(g_b200mc_err, sizeof(g_b200mc_err), "%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+            return B200MC_ERR_CUDA;                                                                   \
+        }                                                                                             \
+    } while (0)
+}  // namespace
+
+int dist_unique_id(char out[128])
+{
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(out, &id, 128);
+    return B200MC_OK;
+}
+int dist_comm_init(void** comm, int rank, int nranks, const char idb[128])
+{
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId id;
+    memcpy(&id, idb, 128);
+    ncclComm_t c;
+    NK(g_nccl.CommInitRank(&c, nranks, id, rank));
+    *comm = c;
+    return B200MC_OK;
+}
+void dist_comm_destroy(void* comm) { if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)comm); }
+int dist_allreduce_u64(void* comm, unsigned long long* buf, int n, cudaStream_t st)
+{
+    NK(g_nccl.AllReduce(buf, buf, (size_t)n, ncclUint64, ncclSum, (ncclComm_t)comm, st));
+    return B200MC_OK;
+}
+
+// rotate every vector of a halo block by one byte-lane: dir = +1: lane b <- lane b-1 (lane 0 <- 15),
+// dir = -1: lane b <- lane b+1 (lane 15 <- 0)
+__global__ void ring_rotate_kernel(uint4* v, int64_t n, int dir)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 s = v[i];
+    uint4 o;
+    if (dir > 0) {
+        o.x = __funnelshift_l(s.w, s.x, 8); o.y = __funnelshift_l(s.x, s.y, 8);
+        o.z = __funnelshift_l(s.y, s.z, 8); o.w = __funnelshift_l(s.z, s.w, 8);
+    } else {
+        o.x = __funnelshift_r(s.x, s.y, 8); o.y = __funnelshift_r(s.y, s.z, 8);
+        o.z = __funnelshift_r(s.z, s.w, 8); o.w = __funnelshift_r(s.w, s.x, 8);
+    }
+    v[i] = o;
+}
+
+// Slab halo exchange (one per colour pass): my first H owned vectors become the HIGH halo of rank-1,
+// my last H owned vectors the LOW halo of rank+1 (ring of ranks).  Rank 0 / rank P-1 then rotate the
+// received block by one lane: crossing the end of the fold moves a site to the next byte-lane.
+static int ring_halo_dist(RingStore* s, int colour, cudaStream_t st)
+{
+    const RingGeom& g = s->g;
+    ncclComm_t comm = (ncclComm_t)s->comm;
+    const int prev = (g.rank + g.nranks - 1) % g.nranks, next = (g.rank + 1) % g.nranks;
+    uint4* v = s->vec[colour];
+    const size_t bytes = (size_t)g.H * sizeof(uint4);
+    NK(g_nccl.GroupStart());
+    NK(g_nccl.Send(v + g.H, bytes, ncclUint8, prev, comm, st));                 // first owned -> prev's high halo
+    NK(g_nccl.Send(v + g.Lloc, bytes, ncclUint8, next, comm, st));              // last owned  -> next's low halo
+    NK(g_nccl.Recv(v + g.H + g.Lloc, bytes, ncclUint8, next, comm, st));        // high halo <- next's first
+    NK(g_nccl.Recv(v, bytes, ncclUint8, prev, comm, st));                       // low halo  <- prev's last
+    NK(g_nccl.GroupEnd());
+    if (g.rank == 0) {
+        ring_rotate_kernel<<<(unsigned)((g.H + 255) / 256), 256, 0, st>>>(v, g.H, +1);
+        COUNT_LAUNCH();
+    }
+    if (g.rank == g.nranks - 1) {
+        ring_rotate_kernel<<<(unsigned)((g.H + 255) / 256), 256, 0, st>>>(v + g.H + g.Lloc, g.H, -1);
+        COUNT_LAUNCH();
+    }
+    CK(cudaGetLastError());
+    return B200MC_OK;
+}
+
 int ring_halo(RingStore* s, int colour, cudaStream_t st)
 {
     const RingGeom& g = s->g;
+    if (g.nranks > 1) return ring_halo_dist(s, colour, st);
     uint8_t* base = reinterpret_cast<uint8_t*>(s->vec[colour]);
     const int64_t ntail = g.L - g.ptail;
     if (g.H <= g.L && g.ptail >= g.H) {
@@ -164,28 +296,31 @@ int ring_halo(RingStore* s, int colour, cudaStream_t st)
 // ---------------------------------------------------------------------------
 __global__ void ring_export_kernel(const uint8_t* a, const uint8_t* b, int64_t N, int64_t L,
                                    int64_t H, int64_t P, int64_t j0, int64_t n, int32_t* out,
-                                   int map)
+                                   int map, int64_t p0, int64_t Lloc)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int64_t j = j0 + t;           // element of spins(1-P : N+P), 0-based
     const int64_t i = pos_mod(j - P, N);  // ring site
     const int64_t k = i >> 1;
-    const uint8_t v = ring_site((i & 1) ? b : a, L, H, k);
+    const int64_t lane = k / L, p = k - lane * L;
+    if (p < p0 || p >= p0 + Lloc) { out[t] = INT32_MIN; return; }  // owned by another rank
+    const uint8_t v = ((i & 1) ? b : a)[(p - p0 + H) * 16 + lane];
     out[t] = map == RING_MAP_PM1 ? 2 * (int32_t)v - 1 : (int32_t)v;
 }
 
 __global__ void ring_import_kernel(uint8_t* a, uint8_t* b, int64_t N, int64_t L, int64_t H,
-                                   int64_t i0, int64_t n, const int32_t* in, int map)
+                                   int64_t i0, int64_t n, const int32_t* in, int map, int64_t p0, int64_t Lloc)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int64_t i = i0 + t;  // ring site; in[] holds sites i0 .. i0+n-1
     const int64_t k = i >> 1;
     const int64_t lane = k / L, p = k - lane * L;
+    if (p < p0 || p >= p0 + Lloc) return;  // owned by another rank
     int32_t v = in[t];
     if (map == RING_MAP_PM1) v = (v + 1) >> 1;
-    ((i & 1) ? b : a)[(p + H) * 16 + lane] = (uint8_t)v;
+    ((i & 1) ? b : a)[(p - p0 + H) * 16 + lane] = (uint8_t)v;
 }
 
 int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st)
@@ -197,7 +332,7 @@ int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStr
         CK(cudaMemcpyAsync(s->stage, host + g.P + i0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         ring_import_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
             reinterpret_cast<uint8_t*>(s->vec[0]), reinterpret_cast<uint8_t*>(s->vec[1]), g.N, g.L,
-            g.H, i0, n, s->stage, (int)map);
+            g.H, i0, n, s->stage, (int)map, g.p0, g.Lloc);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));
     }
@@ -214,7 +349,7 @@ int ring_export_i32(RingStore* s, int32_t* host, RingValueMap map, cudaStream_t 
         const int64_t n = (total - j0 < s->stage_elems) ? total - j0 : s->stage_elems;
         ring_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
             reinterpret_cast<const uint8_t*>(s->vec[0]), reinterpret_cast<const uint8_t*>(s->vec[1]),
-            g.N, g.L, g.H, g.P, j0, n, s->stage, (int)map);
+            g.N, g.L, g.H, g.P, j0, n, s->stage, (int)map, g.p0, g.Lloc);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(host + j0, s->stage, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

@@ -32,6 +32,9 @@ struct RingGeom {
     int64_t ptail;   // first position that holds a non-site lane (== L if none)
     int64_t off[2][6];  // neighbour vector offsets per colour: x-,x+,y+,y-,z+,z-
     int nnb;         // 4 (2D) or 6 (3D)
+    // slab decomposition: this rank owns positions [p0, p0 + Lloc) of every lane (single GPU: 0, L)
+    int64_t p0, Lloc;
+    int rank, nranks;
 };
 
 struct RingStore {
@@ -39,11 +42,14 @@ struct RingStore {
     uint4* vec[2];   // [colour] -> (L + 2H) vectors; position p lives at index p + H
     int32_t* stage;  // staging buffer for import/export
     int64_t stage_elems;
+    void* comm;      // ncclComm_t when nranks > 1
 };
 
 enum RingValueMap { RING_MAP_IDENTITY = 0, RING_MAP_PM1 = 1 };  // PM1: stored 0/1 <-> -1/+1
 
 int ring_geom_init(RingGeom* g, int64_t nx, int64_t ny, int64_t nz /*0 for 2D*/);
+// split the fold across ranks (needs 16 | Nc and Lloc >= H on every rank)
+int ring_geom_set_slab(RingGeom* g, int rank, int nranks);
 int ring_alloc(RingStore* s);
 void ring_free(RingStore* s);
 int ring_fill(RingStore* s, uint8_t value, cudaStream_t st);
@@ -51,3 +57,9 @@ int ring_halo(RingStore* s, int colour, cudaStream_t st);
 // host int32 arrays in the reference layout spins(1-P : N+P)
 int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st);
 int ring_export_i32(RingStore* s, int32_t* host, RingValueMap map, cudaStream_t st);
+
+// NCCL, resolved at run time with dlopen("libnccl.so.2") so that single-GPU use has no NCCL dependency
+int dist_unique_id(char out[128]);
+int dist_comm_init(void** comm, int rank, int nranks, const char id[128]);
+void dist_comm_destroy(void* comm);
+int dist_allreduce_u64(void* comm, unsigned long long* buf, int n, cudaStream_t st);

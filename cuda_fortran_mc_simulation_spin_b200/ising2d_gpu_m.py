@@ -26,6 +26,13 @@ class ising2d_gpu(_IsingBase):
         _lib.check(f(C.byref(self._h), int(nx), int(ny), float(kbt), int(iseed)))
         return self
 
+    def init_slab(self, nx, ny, kbt, iseed, rank, nranks, nccl_id):
+        """the global nx x ny lattice, this process owning slab `rank` of `nranks` (one GPU each)"""
+        return self._init_slab((nx, ny), kbt, iseed, rank, nranks, nccl_id)
+
+    def init_distributed(self, nx, ny, kbt, iseed, group=None):
+        return self._init_torch_distributed((nx, ny), kbt, iseed, group)
+
     def _halo(self):
         return self.nx()
 

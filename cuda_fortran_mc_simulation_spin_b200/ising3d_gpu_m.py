@@ -26,6 +26,13 @@ class ising3d_gpu(_IsingBase):
         _lib.check(f(C.byref(self._h), int(nx), int(ny), int(nz), float(kbt), int(iseed)))
         return self
 
+    def init_slab(self, nx, ny, nz, kbt, iseed, rank, nranks, nccl_id):
+        """the global nx x ny x nz lattice, this process owning slab `rank` of `nranks` (one GPU each)"""
+        return self._init_slab((nx, ny, nz), kbt, iseed, rank, nranks, nccl_id)
+
+    def init_distributed(self, nx, ny, nz, kbt, iseed, group=None):
+        return self._init_torch_distributed((nx, ny, nz), kbt, iseed, group)
+
     def nz(self):
         return int(self._f("nz", i64, P)(self._h))
 

@@ -87,6 +87,30 @@ int b200mc_ising3d_get_timing(void* h, int64_t* launches, double* total_ms);
 int b200mc_ising3d_sync(void* h);
 
 /* ------------------------------------------------------------------------
+ * Slab decomposition over several GPUs, one process (rank) per GPU (the
+ * reference is single-GPU, its `norishiro` halo, src/ising3d_gpu_m.f90:102-122, is the
+ * cell set a rank boundary exchanges).  The helical lattice is a ring of linear indices;
+ * every rank owns an equal share of each of the 16 byte-lanes of the folded ring, so a
+ * site's (lane, position) -- and with it its random stream -- does not depend on the
+ * number of ranks: an N-rank run is bit-identical to the 1-GPU run of the same lattice.
+ * After each colour pass the first / last H owned vectors go to the neighbouring ranks
+ * (NCCL send/recv on a second stream, overlapped with the interior launch); observables
+ * are all-reduced, every rank gets the global value.  get_spins returns INT32_MIN for
+ * sites owned by another rank (merge with an elementwise max); set_spins takes the
+ * full array on every rank.  Needs (sites per colour) % 16 == 0.
+ * ------------------------------------------------------------------------ */
+/* NCCL unique id of the job: call on rank 0, broadcast the 128 bytes to the other ranks */
+int b200mc_dist_unique_id(char out[128]);
+int b200mc_ising3d_create_slab(void** h, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed,
+                               int32_t rank, int32_t nranks, const char nccl_id[128]);
+int b200mc_ising2d_create_slab(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed,
+                               int32_t rank, int32_t nranks, const char nccl_id[128]);
+int b200mc_ising3d_rank_info(void* h, int32_t* rank, int32_t* nranks);
+int b200mc_ising2d_rank_info(void* h, int32_t* rank, int32_t* nranks);
+/* host-only: the slab a rank would own. out = {Nc, L, H, p0, Lloc, ptail} (nz = 0 for 2D) */
+int b200mc_ring_slab_geometry(int64_t nx, int64_t ny, int64_t nz, int32_t rank, int32_t nranks, int64_t out[6]);
+
+/* ------------------------------------------------------------------------
  * Ising 2D -- type(ising2d_gpu), src/ising2d_gpu_m.f90:12-42
  * ------------------------------------------------------------------------ */
 /* init, :44-61.  nx odd, ny even REQUIRED. */
