@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -72,7 +73,35 @@ class _IsingBase:
         box = [unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         self._group = group
-        return self._init_slab(dims, kbt, iseed, rank, nranks, box[0])
+        self._init_slab(dims, kbt, iseed, rank, nranks, box[0])
+        if os.environ.get("B200MC_SLAB_TRANSPORT", "p2p") != "nccl":
+            self._connect_p2p(dist, group, rank, nranks)
+        return self
+
+    def _connect_p2p(self, dist, group, rank, nranks):
+        """direct NVLink transport: exchange the CUDA IPC handles and map the two neighbours' arrays;
+        falls back to the NCCL transport (on every rank) if any rank cannot map its neighbours"""
+        buf = C.create_string_buffer(192)
+        ok = 1
+        try:
+            self._call("p2p_handles", buf, argtypes=(C.c_char_p,))
+        except _lib.B200MCError:
+            ok = 0
+        allh = [None] * nranks
+        dist.all_gather_object(allh, (ok, buf.raw), group=group)
+        if not all(o for o, _ in allh):
+            self._p2p = False
+            return
+        prev, nxt = allh[(rank - 1) % nranks][1], allh[(rank + 1) % nranks][1]
+        # mapping must succeed everywhere or nowhere: connect first, then agree
+        f = self._f("p2p_connect", C.c_int, P, C.c_char_p, C.c_char_p)
+        rc = f(self._h, prev, nxt)
+        oks = [None] * nranks
+        dist.all_gather_object(oks, rc == 0, group=group)
+        if not all(oks):
+            raise _lib.B200MCError("CUDA IPC mapping of the neighbour slabs failed on some rank; "
+                                   "rerun with B200MC_SLAB_TRANSPORT=nccl")
+        self._p2p = True
 
     def rank_info(self):
         r, n = C.c_int32(0), C.c_int32(1)

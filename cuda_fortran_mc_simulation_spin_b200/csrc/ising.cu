@@ -33,6 +33,7 @@ struct Ising {
     unsigned int* d_ticket;
     int tune;  // debug knobs from env B200MC_TUNE: bit0 = static round-robin (no ticket)
     int chunk; // vectors per ticket (env B200MC_CHUNK, default 128)
+    int ileave; // slab mode: one high-boundary chunk in every `ileave` tickets at the start of a pass (env B200MC_ILEAVE)
     int grid;
     bool alive;
     // observables cache: valid until the configuration changes
@@ -152,6 +153,53 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered)
     return B200MC_OK;
 }
 
+// slab mode with the direct transport: ONE launch per colour pass (update + halo push fused)
+template <int NNB>
+int launch_push(Ising* m, int colour)
+{
+    RingStore& st = m->st;
+    const RingGeom& g = st.g;
+    RingPassArgs a;
+    a.own = st.vec[colour];
+    a.oth = st.vec[colour ^ 1];
+    a.nvec = g.Lloc;
+    a.H = g.H;
+    a.p0 = g.p0;
+    for (int j = 0; j < 6; ++j) a.off[j] = g.off[colour][j];
+    a.seed = m->seed;
+    a.colour = (uint32_t)colour;
+    a.draw = m->draw;
+    a.ticket = m->d_ticket;
+    a.chunk = m->chunk;
+    a.peer_lo = st.peer_vec[0][colour] + g.H + st.Lloc_prev;  // rank-1's high halo
+    a.peer_hi = st.peer_vec[1][colour];                       // rank+1's low halo
+    a.rot_lo = g.rank == 0 ? -1 : 0;              // the ring closes between rank 0 and rank P-1:
+    a.rot_hi = g.rank == g.nranks - 1 ? +1 : 0;   // crossing the end of the fold moves a site to the next lane
+    a.nb = (int)g.H;
+    a.hi_start = (int)(g.Lloc - g.H);
+    const int64_t nchunks = (g.Lloc + a.chunk - 1) / a.chunk;
+    a.blo = (int)((g.H + a.chunk - 1) / a.chunk);
+    a.jhi = (int)((g.Lloc - g.H) / a.chunk);
+    a.nbchunks = a.blo + (int)(nchunks - a.jhi);
+    const int64_t nbhi = nchunks - a.jhi;
+    a.ileave = m->ileave;
+    a.nopush = (m->tune & 4) ? 1 : 0;  // debug: skip the NVLink stores (wrong results, timing only)
+    a.q_total = (int)(a.ileave * nbhi > nchunks ? a.ileave * nbhi : nchunks);
+    a.done = st.flags + 32;
+    a.sig_prev = st.peer_flags[0] + 16;  // I am rank-1's "next"
+    a.sig_next = st.peer_flags[1] + 0;   // and rank+1's "prev"
+    a.wait_prev = st.flags + 0;
+    a.wait_next = st.flags + 16;
+    a.wait_seq = st.push_seq;
+    a.sig_seq = ++st.push_seq;
+    CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
+    COUNT_LAUNCH();
+    if (m->method == METHOD_METROPOLIS) ising_pass_kernel<NNB, METHOD_METROPOLIS, true, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+    else ising_pass_kernel<NNB, METHOD_HEATBATH, true, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+    CK(cudaGetLastError());
+    return B200MC_OK;
+}
+
 // One colour pass + halo refresh.  Single GPU: one launch over the whole fold, then the halo kernel.
 // Slab mode: the first and last H owned vectors (what the neighbouring ranks need) are updated first,
 // their exchange runs on the comm stream while the interior launch runs on the compute stream.
@@ -177,6 +225,14 @@ int launch_pass(Ising* m, int colour)
         if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
         if (rc) return rc;
         return ring_halo(&m->st, colour, m->stream);
+    }
+    if (m->st.p2p) {
+        // direct transport: one launch updates the whole slab, boundary chunks first, and stores their
+        // results straight into the neighbours' halos over NVLink; the next pass waits (in the
+        // kernel) for the neighbours' flags
+        rc = launch_push<NNB>(m, colour);
+        if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
+        return rc;
     }
     if ((rc = launch_range<NNB>(m, colour, 0, g.H, false))) return rc;
     if ((rc = launch_range<NNB>(m, colour, g.Lloc - g.H, g.H, false))) return rc;
@@ -237,6 +293,7 @@ int measure(Ising* m, int64_t* e, int64_t* mag)
         if (mag) *mag = m->obs_m;
         return B200MC_OK;
     }
+    { int rcq = ring_p2p_quiesce(&m->st, m->stream); if (rcq) return rcq; }
     COUNT_LAUNCH();
     CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
     if (m->ndim == 3)
@@ -278,7 +335,8 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     if (!m) ARG_FAIL("out of host memory");
     m->ndim = ndim; m->nx = nx; m->ny = ny; m->nz = ndim == 3 ? nz : 0;
     m->stream = 0; m->d_acc = nullptr; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
-    { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; t = getenv("B200MC_CHUNK"); m->chunk = t ? atoi(t) : 128; if (m->chunk < 32 || (m->chunk & 31)) m->chunk = 128; }
+    { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; t = getenv("B200MC_CHUNK"); m->chunk = t ? atoi(t) : 128; if (m->chunk < 32 || (m->chunk & 31)) m->chunk = 128;
+      t = getenv("B200MC_ILEAVE"); m->ileave = t ? atoi(t) : 1; if (m->ileave < 1 || m->ileave > 64) m->ileave = 1; }
     m->method = METHOD_METROPOLIS; m->seed = (uint32_t)iseed; m->draw = 0; m->alive = true;
     m->obs_valid = false; m->timing = false; m->ev_used = 0;
     m->comm_stream = nullptr; m->ev_boundary = m->ev_halo = nullptr; m->st.comm = nullptr;
@@ -327,6 +385,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
 int destroy(Ising* m)
 {
     if (!m) return B200MC_OK;
+    ring_p2p_quiesce(&m->st, m->stream);  // the neighbours' last pushes have landed before the arrays go away
     cudaStreamSynchronize(m->stream);
     ring_free(&m->st);
     cudaFree(m->d_acc);
@@ -346,6 +405,7 @@ int set_random(Ising* m)
 {
     const RingGeom& g = m->st.g;
     m->obs_valid = false;
+    { int rcq = ring_p2p_quiesce(&m->st, m->stream); if (rcq) return rcq; }
     for (int c = 0; c < 2; ++c) {
         COUNT_LAUNCH();
         ring_random_bits_kernel<<<(unsigned)((g.Lloc + 255) / 256), 256, 0, m->stream>>>(m->st.vec[c], g.Lloc, g.H, g.p0, m->seed, m->draw, (uint32_t)c);
@@ -361,6 +421,7 @@ int update_with_randoms(Ising* m, const double* randoms)
 {
     if (!randoms) ARG_FAIL("null randoms");
     const RingGeom& g = m->st.g;
+    { int rcq = ring_p2p_quiesce(&m->st, m->stream); if (rcq) return rcq; }
     if (!m->d_randoms) CK(cudaMalloc(&m->d_randoms, (size_t)g.N * sizeof(double)));
     CK(cudaMemcpyAsync(m->d_randoms, randoms, (size_t)g.N * sizeof(double), cudaMemcpyHostToDevice, m->stream));
     for (int colour = 0; colour < 2; ++colour) {
@@ -482,6 +543,10 @@ int b200mc_ring_slab_geometry(int64_t nx, int64_t ny, int64_t nz, int32_t rank, 
     out[0] = g.Nc; out[1] = g.L; out[2] = g.H; out[3] = g.p0; out[4] = g.Lloc; out[5] = g.ptail;
     return B200MC_OK;
 }
+int b200mc_ising3d_p2p_handles(void* h, char out[192]) { CHECK_H(h, 3); return ring_p2p_export(&H(h)->st, out); }
+int b200mc_ising2d_p2p_handles(void* h, char out[192]) { CHECK_H(h, 2); return ring_p2p_export(&H(h)->st, out); }
+int b200mc_ising3d_p2p_connect(void* h, const char prev[192], const char next[192]) { CHECK_H(h, 3); return ring_p2p_connect(&H(h)->st, prev, next); }
+int b200mc_ising2d_p2p_connect(void* h, const char prev[192], const char next[192]) { CHECK_H(h, 2); return ring_p2p_connect(&H(h)->st, prev, next); }
 int b200mc_ising3d_rank_info(void* h, int32_t* rank, int32_t* nranks) { CHECK_H(h, 3); *rank = H(h)->st.g.rank; *nranks = H(h)->st.g.nranks; return B200MC_OK; }
 int b200mc_ising2d_rank_info(void* h, int32_t* rank, int32_t* nranks) { CHECK_H(h, 2); *rank = H(h)->st.g.rank; *nranks = H(h)->st.g.nranks; return B200MC_OK; }
 int64_t b200mc_ising3d_nz(void* h) { return h ? H(h)->nz : -1; }

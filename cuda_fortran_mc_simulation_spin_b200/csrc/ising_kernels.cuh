@@ -61,7 +61,48 @@ struct RingPassArgs {
     uint64_t draw;
     unsigned int* ticket;  // work counter for ordered scheduling (nullptr: static round-robin)
     int chunk;             // vectors per ticket (multiple of 32)
+    // PUSH variant (slab mode: colour pass fused with the halo exchange).  The first nb owned vectors
+    // are the HIGH halo of rank-1, the vectors from hi_start on the LOW halo of rank+1: the kernel
+    // stores those results a second time straight into the neighbour's halo over NVLink (peer pointers
+    // from cudaIpcOpenMemHandle), rotated by one byte-lane where the ring closes (rank 0 <-> rank P-1).
+    // Chunks [0, blo) and [jhi, nchunks) hold them ("boundary chunks", nbchunks in all); the other
+    // chunks are interior.  q_total = number of tickets (virtual chunks) of the launch.
+    uint4* peer_lo;        // rank-1's high halo of this colour
+    uint4* peer_hi;        // rank+1's low halo of this colour
+    int rot_lo, rot_hi;    // lane rotation of the pushed copy: +1 lane b <- b-1, -1 lane b <- b+1, 0 none
+    int nb;                // H
+    int hi_start;          // Lloc - H
+    int blo, jhi, nbchunks, q_total, ileave, nopush;
+    unsigned int* done;    // completed boundary chunks of this launch (local)
+    unsigned int* sig_prev;       // rank-1's "from next" flag, rank+1's "from prev" flag (peer memory)
+    unsigned int* sig_next;
+    const unsigned int* wait_prev;  // my flags: pushes received so far from rank-1 / rank+1
+    const unsigned int* wait_next;
+    unsigned int wait_seq, sig_seq;
 };
+
+__device__ __forceinline__ uint4 rot_lanes(uint4 s, int dir)
+{
+    uint4 o = s;
+    if (dir > 0) {
+        o.x = __funnelshift_l(s.w, s.x, 8); o.y = __funnelshift_l(s.x, s.y, 8);
+        o.z = __funnelshift_l(s.y, s.z, 8); o.w = __funnelshift_l(s.z, s.w, 8);
+    } else if (dir < 0) {
+        o.x = __funnelshift_r(s.x, s.y, 8); o.y = __funnelshift_r(s.y, s.z, 8);
+        o.z = __funnelshift_r(s.z, s.w, 8); o.w = __funnelshift_r(s.w, s.x, 8);
+    }
+    return o;
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 enum { METHOD_METROPOLIS = 0, METHOD_HEATBATH = 1 };
 
@@ -141,7 +182,7 @@ __device__ __forceinline__ uint32_t tie_bits(uint32_t z)
     return ((e >> 7) * 0x00204081u) >> 21 & 0xFu;  // gather bits 0,8,16,24 -> 0..3
 }
 
-template <int METHOD>
+template <int METHOD, bool PUSH>
 __device__ __noinline__ void ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4* own, const RingPassArgs& a,
                                          const IsingTab& tab)
 {
@@ -153,6 +194,12 @@ __device__ __noinline__ void ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(qaddr + r * 32));
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(qaddr + r * 32 + 16));
         const uint32_t v = r0.x;
+        uint8_t* rbytes = nullptr;  // PUSH: the pushed copy of this vector in the neighbour's halo
+        int rrot = 0;
+        if (PUSH) {
+            if ((int)v < a.nb) { rbytes = reinterpret_cast<uint8_t*>(a.peer_lo + v); rrot = a.rot_lo; }
+            else if ((int)v >= a.hi_start) { rbytes = reinterpret_cast<uint8_t*>(a.peer_hi + ((int)v - a.hi_start)); rrot = a.rot_hi; }
+        }
         uint8_t* bytes = reinterpret_cast<uint8_t*>(own + v);
         // 16-bit tie mask, bit m = byte position m of the stage-1 Philox block
         uint32_t mask = tie_bits(r0.y) | (tie_bits(r0.z) << 4) | (tie_bits(r0.w) << 8) | (tie_bits(r1.x) << 12);
@@ -167,7 +214,9 @@ __device__ __noinline__ void ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4
             const uint32_t nib = (ixw >> (16 * (w & 1) + 4 * j)) & 0xFu;
             if ((rj & 0x1FFFFFFu) < tab.low25[nib & 7u]) {
                 const int lb = (m & 8) | ((m & 7) >> 1) | ((m & 1) << 2);  // byte position -> lane
-                bytes[lb] = (METHOD == METHOD_METROPOLIS) ? (uint8_t)((nib >> 3) ^ 1u) : (uint8_t)1;
+                const uint8_t nv = (METHOD == METHOD_METROPOLIS) ? (uint8_t)((nib >> 3) ^ 1u) : (uint8_t)1;
+                bytes[lb] = nv;
+                if (PUSH && rbytes) rbytes[(lb + rrot) & 15] = nv;
             }
         }
     }
@@ -176,10 +225,11 @@ __device__ __noinline__ void ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4
     __syncwarp();
 }
 
-template <int NNB, int METHOD, bool ORDERED>
+template <int NNB, int METHOD, bool ORDERED, bool PUSH = false>
 __global__ void __launch_bounds__(256)
 ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant__ IsingTab tab)
 {
+    static_assert(!PUSH || ORDERED, "the fused update + halo push kernel uses ticket scheduling");
     __shared__ uint4 tq[8][TQ_CAP][2];
     __shared__ uint32_t tq_cnt[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -189,6 +239,14 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
     pin32(cntaddr);
     if (lane == 0) tq_cnt[warp] = 0;
     __syncwarp();
+    if (PUSH) {
+        // the halo cells this pass reads were pushed by the neighbours during their previous pass
+        if (threadIdx.x == 0) {
+            while ((int)(ld_acquire_sys(a.wait_prev) - a.wait_seq) < 0) __nanosleep(100);
+            while ((int)(ld_acquire_sys(a.wait_next) - a.wait_seq) < 0) __nanosleep(100);
+        }
+        __syncthreads();
+    }
     const uint64_t pol = l2_policy_evict_first();
     uint4* own = a.own + a.H;
     pin64(own);
@@ -207,6 +265,7 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
     unsigned int* tk = a.ticket + (gwarp % TK_NCNT) * 64;
     const int tk_base = (gwarp % TK_NCNT) * TK_CHUNK, tk_scale = TK_NCNT;
+    const int vlimit = PUSH ? a.q_total * TK_CHUNK : nvec;  // PUSH: tickets count VIRTUAL chunks
     int cur, nxt = 0;
     if (ORDERED) {
         if (lane == 0) nxt = (int)atomicAdd(tk, (unsigned)TK_CHUNK) * tk_scale + tk_base;
@@ -214,11 +273,33 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
     } else {
         cur = gwarp * TK_CHUNK;
     }
-    while (cur < nvec) {
+    while (cur < vlimit) {
         if (ORDERED && lane == 0) nxt = (int)atomicAdd(tk, (unsigned)TK_CHUNK) * tk_scale + tk_base;  // prefetch
+        int base = cur;
+        bool is_b = false;
+        if (PUSH) {
+            // Slab mode.  The chunks holding the LAST H owned vectors (the low halo of rank+1) are handed
+            // out first, one in every `ileave` tickets; all other chunks follow in natural order, which
+            // starts with the first H owned vectors (the high halo of rank-1).  Both halo blocks are thus
+            // on their way over NVLink early in the pass and land while the interior is being updated.
+            const int q = cur / TK_CHUNK;
+            const int nbhi = a.nbchunks - a.blo;
+            int j;
+            if (q < a.ileave * nbhi) {
+                const int k = q / a.ileave;
+                if (q - k * a.ileave == 0) j = a.jhi + k;
+                else { j = q - k - 1; if (j >= a.jhi) j = -1; }
+            } else {
+                j = q - nbhi;
+                if (j >= a.jhi) j = -1;
+            }
+            is_b = j >= 0 && (j < a.blo || j >= a.jhi);
+            base = j * TK_CHUNK;
+            if (j < 0) { cur = __shfl_sync(0xffffffffu, nxt, 0); continue; }
+        }
 #pragma unroll 1
         for (int sub = 0; sub < TK_CHUNK; sub += 32) {
-            const int v = cur + sub + lane;
+            const int v = base + sub + lane;
             if (v < nvec) {
                 uint4 o = ld_own(own + v, pol);
                 uint4 nb[NNB];
@@ -243,14 +324,32 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
                 ising_finish<METHOD>(o.x, o.y, oA0, oB0, zA0, zB0);
                 ising_finish<METHOD>(o.z, o.w, oA1, oB1, zA1, zB1);
                 st_own(own + v, o, pol);
+                if (PUSH && is_b && !a.nopush) {  // second copy straight into the neighbour's halo (NVLink store)
+                    if (v < a.nb) a.peer_lo[v] = rot_lanes(o, a.rot_lo);
+                    else if (v >= a.hi_start) a.peer_hi[v - a.hi_start] = rot_lanes(o, a.rot_hi);
+                }
             }
             __syncwarp();
-            if (lds32(cntaddr) > TQ_CAP - 32) ising_drain<METHOD>(qaddr, cntaddr, own, a, tab);
+            if (lds32(cntaddr) > TQ_CAP - 32) ising_drain<METHOD, PUSH>(qaddr, cntaddr, own, a, tab);
+        }
+        if (PUSH && is_b) {
+            // this chunk's ties are resolved (remote copies patched too), its stores are performed
+            // system-wide, and the warp that completes the LAST boundary chunk of the launch tells both
+            // neighbours that their halo of this colour is complete
+            ising_drain<METHOD, PUSH>(qaddr, cntaddr, own, a, tab);
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0 && atomicAdd(a.done, 1u) == (unsigned)a.nbchunks - 1u) {
+                *a.done = 0;
+                __threadfence_system();
+                st_release_sys(a.sig_prev, a.sig_seq);
+                st_release_sys(a.sig_next, a.sig_seq);
+            }
         }
         if (ORDERED) cur = __shfl_sync(0xffffffffu, nxt, 0);
         else cur += nwarps_grid * TK_CHUNK;
     }
-    ising_drain<METHOD>(qaddr, cntaddr, own, a, tab);
+    ising_drain<METHOD, PUSH>(qaddr, cntaddr, own, a, tab);
 }
 
 // ---------------------------------------------------------------------------

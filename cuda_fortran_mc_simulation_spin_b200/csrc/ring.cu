@@ -61,6 +61,7 @@ int ring_alloc(RingStore* s)
     const size_t nv = (size_t)(s->g.Lloc + 2 * s->g.H);
     s->vec[0] = s->vec[1] = nullptr;
     s->stage = nullptr;
+    s->p2p = false; s->flags = nullptr; s->n_peer_maps = 0; s->push_seq = 0; s->Lloc_prev = 0;
     CK(cudaMalloc(&s->vec[0], nv * sizeof(uint4)));
     CK(cudaMalloc(&s->vec[1], nv * sizeof(uint4)));
     s->stage_elems = 1 << 24;
@@ -71,6 +72,9 @@ int ring_alloc(RingStore* s)
 
 void ring_free(RingStore* s)
 {
+    ring_p2p_close(s);
+    cudaFree(s->flags);
+    s->flags = nullptr;
     cudaFree(s->vec[0]);
     cudaFree(s->vec[1]);
     cudaFree(s->stage);
@@ -80,6 +84,8 @@ void ring_free(RingStore* s)
 
 int ring_fill(RingStore* s, uint8_t value, cudaStream_t st)
 {
+    int rcq = ring_p2p_quiesce(s, st);
+    if (rcq) return rcq;
     const size_t nv = (size_t)(s->g.Lloc + 2 * s->g.H);
     CK(cudaMemsetAsync(s->vec[0], value, nv * sizeof(uint4), st));
     CK(cudaMemsetAsync(s->vec[1], value, nv * sizeof(uint4), st));
@@ -265,6 +271,82 @@ static int ring_halo_dist(RingStore* s, int colour, cudaStream_t st)
     return B200MC_OK;
 }
 
+// ---- direct NVLink transport: IPC-mapped neighbour arrays ------------------------------------
+int ring_p2p_export(RingStore* s, char out[RING_IPC_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) * 3 == RING_IPC_BYTES, "cudaIpcMemHandle_t size");
+    if (!s->flags) {
+        CK(cudaMalloc(&s->flags, 64 * sizeof(unsigned int)));
+        CK(cudaMemset(s->flags, 0, 64 * sizeof(unsigned int)));
+    }
+    cudaIpcMemHandle_t h[3];
+    CK(cudaIpcGetMemHandle(&h[0], s->vec[0]));
+    CK(cudaIpcGetMemHandle(&h[1], s->vec[1]));
+    CK(cudaIpcGetMemHandle(&h[2], s->flags));
+    memcpy(out, h, RING_IPC_BYTES);
+    return B200MC_OK;
+}
+
+int ring_p2p_connect(RingStore* s, const char prev[RING_IPC_BYTES], const char next[RING_IPC_BYTES])
+{
+    const RingGeom& g = s->g;
+    if (g.nranks < 2) ARG_FAIL("p2p_connect: not a slab handle");
+    if (!s->flags) ARG_FAIL("p2p_connect: call p2p_handles first");
+    const char* src[2] = {prev, next};
+    const int nopen = (g.nranks == 2) ? 1 : 2;  // with two ranks both neighbours are the same process
+    for (int side = 0; side < nopen; ++side) {
+        cudaIpcMemHandle_t h[3];
+        memcpy(h, src[side], RING_IPC_BYTES);
+        void* ptr[3] = {nullptr, nullptr, nullptr};
+        for (int j = 0; j < 3; ++j) {
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr[j], h[j], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+                cudaGetLastError();
+                ring_p2p_close(s);
+                return B200MC_ERR_UNSUPPORTED;
+            }
+            s->peer_maps[s->n_peer_maps++] = ptr[j];
+        }
+        s->peer_vec[side][0] = (uint4*)ptr[0];
+        s->peer_vec[side][1] = (uint4*)ptr[1];
+        s->peer_flags[side] = (unsigned int*)ptr[2];
+    }
+    if (nopen == 1) {
+        s->peer_vec[1][0] = s->peer_vec[0][0];
+        s->peer_vec[1][1] = s->peer_vec[0][1];
+        s->peer_flags[1] = s->peer_flags[0];
+    }
+    const int prev_rank = (g.rank + g.nranks - 1) % g.nranks;
+    const int64_t base = g.L / g.nranks, rem = g.L % g.nranks;
+    s->Lloc_prev = base + (prev_rank < rem ? 1 : 0);
+    s->p2p = true;
+    return B200MC_OK;
+}
+
+void ring_p2p_close(RingStore* s)
+{
+    for (int i = 0; i < s->n_peer_maps; ++i) cudaIpcCloseMemHandle(s->peer_maps[i]);
+    s->n_peer_maps = 0;
+    s->p2p = false;
+}
+
+__global__ void ring_wait_flags_kernel(const unsigned int* flags, unsigned int seq)
+{
+    unsigned int v;
+    do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags) : "memory"); } while ((int)(v - seq) < 0);
+    do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + 16) : "memory"); } while ((int)(v - seq) < 0);
+}
+
+int ring_p2p_quiesce(RingStore* s, cudaStream_t st)
+{
+    if (!s->p2p || s->push_seq == 0) return B200MC_OK;
+    ring_wait_flags_kernel<<<1, 1, 0, st>>>(s->flags, s->push_seq);
+    COUNT_LAUNCH();
+    CK(cudaGetLastError());
+    return B200MC_OK;
+}
+
 int ring_halo(RingStore* s, int colour, cudaStream_t st)
 {
     const RingGeom& g = s->g;
@@ -326,6 +408,8 @@ __global__ void ring_import_kernel(uint8_t* a, uint8_t* b, int64_t N, int64_t L,
 int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st)
 {
     const RingGeom& g = s->g;
+    int rcq = ring_p2p_quiesce(s, st);
+    if (rcq) return rcq;
     // interior only (the halo cells of the host array are ignored and rebuilt)
     for (int64_t i0 = 0; i0 < g.N; i0 += s->stage_elems) {
         const int64_t n = (g.N - i0 < s->stage_elems) ? g.N - i0 : s->stage_elems;

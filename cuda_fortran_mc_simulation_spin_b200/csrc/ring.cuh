@@ -43,7 +43,18 @@ struct RingStore {
     int32_t* stage;  // staging buffer for import/export
     int64_t stage_elems;
     void* comm;      // ncclComm_t when nranks > 1
+    // direct NVLink transport (slab mode): the neighbours' colour arrays and flag words mapped with
+    // cudaIpcOpenMemHandle; the boundary launch of a colour pass stores into them (ising_kernels.cuh, PUSH)
+    bool p2p;
+    unsigned int* flags;         // mine: [0] pushes received from rank-1, [16] from rank+1, [32] CTA counter
+    uint4* peer_vec[2][2];       // [0 = rank-1, 1 = rank+1][colour]
+    unsigned int* peer_flags[2];
+    void* peer_maps[6];          // what cudaIpcCloseMemHandle must be called on
+    int n_peer_maps;
+    int64_t Lloc_prev;           // owned vectors of rank-1 (its high halo starts at H + Lloc_prev)
+    unsigned int push_seq;       // boundary pushes issued so far (same on every rank: SPMD)
 };
+#define RING_IPC_BYTES 192       // three cudaIpcMemHandle_t: colour 0, colour 1, flags
 
 enum RingValueMap { RING_MAP_IDENTITY = 0, RING_MAP_PM1 = 1 };  // PM1: stored 0/1 <-> -1/+1
 
@@ -57,6 +68,13 @@ int ring_halo(RingStore* s, int colour, cudaStream_t st);
 // host int32 arrays in the reference layout spins(1-P : N+P)
 int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st);
 int ring_export_i32(RingStore* s, int32_t* host, RingValueMap map, cudaStream_t st);
+
+// direct transport set-up: export my handles, map the two neighbours' (prev == next when nranks == 2)
+int ring_p2p_export(RingStore* s, char out[RING_IPC_BYTES]);
+int ring_p2p_connect(RingStore* s, const char prev[RING_IPC_BYTES], const char next[RING_IPC_BYTES]);
+void ring_p2p_close(RingStore* s);
+// stream-ordered wait until every push issued so far by both neighbours has landed
+int ring_p2p_quiesce(RingStore* s, cudaStream_t st);
 
 // NCCL, resolved at run time with dlopen("libnccl.so.2") so that single-GPU use has no NCCL dependency
 int dist_unique_id(char out[128]);

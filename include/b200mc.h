@@ -105,6 +105,16 @@ int b200mc_ising3d_create_slab(void** h, int64_t nx, int64_t ny, int64_t nz, dou
                                int32_t rank, int32_t nranks, const char nccl_id[128]);
 int b200mc_ising2d_create_slab(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed,
                                int32_t rank, int32_t nranks, const char nccl_id[128]);
+/* optional direct NVLink transport for the per-pass halo exchange: every rank exports three
+ * cudaIpcMemHandle_t (192 bytes), the caller hands each rank the bytes of rank-1 and rank+1 (ring);
+ * afterwards the boundary launch of a colour pass stores its results straight into the neighbours'
+ * halo cells (one fused kernel: update + transfer) instead of NCCL send/recv.  B200MC_ERR_UNSUPPORTED
+ * if CUDA IPC is not available between the two processes (keep using the NCCL transport then --
+ * all ranks must take the same decision). */
+int b200mc_ising3d_p2p_handles(void* h, char out[192]);
+int b200mc_ising2d_p2p_handles(void* h, char out[192]);
+int b200mc_ising3d_p2p_connect(void* h, const char prev[192], const char next[192]);
+int b200mc_ising2d_p2p_connect(void* h, const char prev[192], const char next[192]);
 int b200mc_ising3d_rank_info(void* h, int32_t* rank, int32_t* nranks);
 int b200mc_ising2d_rank_info(void* h, int32_t* rank, int32_t* nranks);
 /* host-only: the slab a rank would own. out = {Nc, L, H, p0, Lloc, ptail} (nz = 0 for 2D) */

@@ -68,6 +68,32 @@ def main():
         g1.update_n(5)
         assert g1.measure() == em
         print("slab ok: N-rank run == 1-GPU run", em, flush=True)
+    # longer asynchronous run through the overlapped path (boundary launch + interior launch per colour):
+    # sweeps, re-initialisation and measurements interleaved, against the 1-GPU run of the same lattice
+    g = ising3d_gpu_m.ising3d_gpu().init_distributed(127, 127, 96 * world, KBT3, 11)
+    log = []
+    for rep in range(3):
+        g.update_n(20)
+        log.append(g.measure())
+        g.set_random_spin()
+        g.update_n(7)
+        log.append(g.measure())
+        g.set_allup_spin()
+    sp = g.spins()
+    if rank == 0:
+        g1 = ising3d_gpu_m.ising3d_gpu().init(127, 127, 96 * world, KBT3, 11)
+        log1 = []
+        for rep in range(3):
+            g1.update_n(20)
+            log1.append(g1.measure())
+            g1.set_random_spin()
+            g1.update_n(7)
+            log1.append(g1.measure())
+            g1.set_allup_spin()
+        assert log == log1, (log, log1)
+        assert np.array_equal(sp, g1.spins())
+        print("slab ok: interleaved run == 1-GPU run, transport", os.environ.get("B200MC_SLAB_TRANSPORT", "p2p"),
+              "p2p active:", getattr(g, "_p2p", False), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
