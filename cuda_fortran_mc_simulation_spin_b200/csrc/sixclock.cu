@@ -1,0 +1,799 @@
+// Periodic q-state clock with the full q^6 acceptance table ("tableall") and its compact
+// two-colour storage ("dual lattice"): kernels, host-side handle and C ABI.
+// Reference: module clock_tableall_gpu_m, src/clock/clock_tableall_gpu_m.f90:1-182, and module
+// clock_dual_lattice_tableall_gpu_m, src/clock/clock_dual_lattice_tableall_m.f90:1-202 (the
+// y-compacted twin clock_dual_lattice_yhalf_tableall_m.f90 differs in index arithmetic only).
+//
+// Layout.  The reference stores sixclock(nx, ny) int32 (tableall) or two int32 colour arrays
+// sixclock_even/odd(nx/2, ny) (dual lattice) plus rnds(2, nx, ny) real64 = 20 B/site.  Here a
+// state is one byte, colours split as in the dual-lattice module: colour c = (x0 + y0) & 1,
+// compact index xi = x0 >> 1 (x0 = 2 xi + ((y0 + c) & 1)), rows padded to a multiple of 16
+// bytes, replicas ("multi-sample batch") stacked: [replica][y0][pitch].  A thread owns one
+// aligned 16-byte vector of one row; its neighbours are three aligned 16-byte vectors of the
+// other colour (same row, row above, row below) plus one byte of the adjacent vector; the
+// periodic wrap is index arithmetic (no halo).  Pad bytes (xi >= nx/2) always hold valid states
+// and are masked out of the observables.
+//
+// RNG contract (CPU restatement: oracle/rng_contract.c, orc_torus_uniforms).  Site j = xi & 15
+// of vector v = xi >> 4 of row y0: block = y0 * nvr + v,
+//   W  = philox(ctr(block, draw, colour,     j >> 2), (seed, TAG_TORUS + replica))[j & 3]
+//   W2 = philox(ctr(block, draw, colour, 4 + (j >> 2)), same key)[j & 3]
+//   accept   U_a = (W & 0xFFFF0000) | (W2 >> 16)        -> rnds(2, x, y) = (U_a + 1) 2^-32
+//   proposal U_p = (W << 16)        | (W2 & 0xFFFF)     -> rnds(1, x, y) = (U_p + 1) 2^-32
+// W2 is only evaluated when the 16 bits of W do not decide (about 5 sites in 65536), so the
+// hot loop costs one Philox block per 4 sites and is still exact at 32-bit resolution:
+//   new = c + ceiling(rnds1 (q-1))  (:142)   <=>  k = ceil((U_p + 1)(q-1) / 2^32)
+//   rnds2 <= prob                  (:146)   <=>  U_a < thr = floor(prob 2^32)
+#include <math.h>
+#include <stdlib.h>
+#include <map>
+#include <new>
+#include <vector>
+#include "../../include/b200mc.h"
+#include "common.cuh"
+
+namespace {
+
+#define SIX_MAX_CLASSES 256
+
+struct SixArgs {
+    uint8_t* own;            // colour being updated, all replicas
+    const uint8_t* oth;
+    int nxh, ny, nvr;        // sites per row per colour, rows, 16-byte vectors per row
+    int nrows;               // n_multi * ny
+    int colour;
+    uint32_t q;
+    const uint8_t* cls;      // q^6 class ids: c + q(new + q(r + q(u + q(l + q d))))   (states_to_prob index order, :72-80)
+    const uint32_t* thi;     // per class: thr >> 16  (0 .. 65536)
+    const uint32_t* tlo;     // per class: thr & 0xFFFF
+    uint32_t tab_bytes;
+    int cls_in_smem;
+    uint64_t draw;
+    uint32_t rk0[10];        // Philox round keys seed + r W0
+};
+
+__device__ __forceinline__ uint4 philox_k1(uint4 c, const uint32_t (&rk0)[10], uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t lo0, hi0, lo1, hi1;
+        mulwide(PHILOX_M0, c.x, lo0, hi0);
+        mulwide(PHILOX_M1, c.z, lo1, hi1);
+        uint4 n;
+        n.x = hi1 ^ c.y ^ rk0[r];
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ (k1 + (uint32_t)r * PHILOX_W1);
+        n.w = lo0;
+        c = n;
+    }
+    return c;
+}
+
+__device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t word_of(const uint4& v, int w) { return w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w; }
+__device__ __forceinline__ uint32_t byte_of(const uint4& v, int j) { return (word_of(v, j >> 2) >> (8 * (j & 3))) & 0xFFu; }
+
+// the other colour's same-row values one compact position to the left (p == 0: x0 - 1) or to
+// the right (p == 1: x0 + 1) of the 16 sites of vector v, periodic in x
+__device__ __forceinline__ uint4 six_shifted(const uint8_t* row, const uint4& b, int v, int nvr, int nxh, int p)
+{
+    uint4 s;
+    if (p == 0) {
+        const uint32_t e = ldg_u8(row + (v == 0 ? nxh - 1 : 16 * v - 1));
+        s.x = (b.x << 8) | e;
+        s.y = __funnelshift_l(b.x, b.y, 8);
+        s.z = __funnelshift_l(b.y, b.z, 8);
+        s.w = __funnelshift_l(b.z, b.w, 8);
+    } else {
+        const bool last = v == nvr - 1;
+        const uint32_t e = ldg_u8(row + (last ? 0 : 16 * v + 16));
+        s.x = __funnelshift_r(b.x, b.y, 8);
+        s.y = __funnelshift_r(b.y, b.z, 8);
+        s.z = __funnelshift_r(b.z, b.w, 8);
+        s.w = (b.w >> 8) | (e << 24);
+        if (last) {  // the row's last site sits at local position lp (< 15 when the row is padded)
+            const int lp = nxh - 1 - 16 * v, wi = lp >> 2, sh = 8 * (lp & 3);
+            const uint32_t keep = ~(0xFFu << sh), ins = e << sh;
+            if (wi == 0) s.x = (s.x & keep) | ins;
+            if (wi == 1) s.y = (s.y & keep) | ins;
+            if (wi == 2) s.z = (s.z & keep) | ins;
+            if (wi == 3) s.w = (s.w & keep) | ins;
+        }
+    }
+    return s;
+}
+
+// exact (32-bit) evaluation of one site: second Philox block for the low halves
+__device__ __noinline__ uint32_t six_site_exact(const SixArgs& a, const uint8_t* cls, uint32_t W, uint32_t blk, uint32_t k1,
+                                                int j, uint32_t c, uint32_t r, uint32_t u, uint32_t l, uint32_t d)
+{
+    const uint4 R2 = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, 4u + (uint32_t)(j >> 2)), a.rk0, k1);
+    const uint32_t W2 = word_of(R2, j & 3);
+    const uint32_t Ua = (W & 0xFFFF0000u) | (W2 >> 16);
+    const uint32_t Up = (W << 16) | (W2 & 0xFFFFu);
+    const uint32_t q = a.q;
+    const uint32_t k = (uint32_t)((((unsigned long long)Up + 1ull) * (q - 1) + 0xFFFFFFFFull) >> 32);
+    uint32_t nw = c + k;
+    if (nw >= q) nw -= q;
+    const uint32_t idx = c + q * (nw + q * (r + q * (u + q * (l + q * d))));
+    const uint32_t cl = cls[idx];
+    const unsigned long long thr = ((unsigned long long)a.thi[cl] << 16) | a.tlo[cl];
+    return ((unsigned long long)Ua < thr) ? nw : c;
+}
+
+// update_sub, src/clock/clock_tableall_gpu_m.f90:107-152 (dual lattice: :110-155), one colour
+template <bool SMEM>
+__global__ void __launch_bounds__(256)
+sixclock_pass_kernel(const __grid_constant__ SixArgs a)
+{
+    extern __shared__ __align__(16) uint8_t sm[];
+    uint32_t* sthi = reinterpret_cast<uint32_t*>(sm);            // SIX_MAX_CLASSES words
+    uint8_t* scls = sm + SIX_MAX_CLASSES * sizeof(uint32_t);     // q^6 bytes (if cls_in_smem)
+    for (int i = threadIdx.x; i < SIX_MAX_CLASSES; i += blockDim.x) sthi[i] = a.thi[i];
+    if (SMEM) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.cls);
+        uint4* dst = reinterpret_cast<uint4*>(scls);
+        for (uint32_t i = threadIdx.x; i < (a.tab_bytes + 15) / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint8_t* cls = SMEM ? scls : a.cls;
+    const uint32_t scls_addr = (uint32_t)__cvta_generic_to_shared(scls);
+    const uint32_t q = a.q, qm1 = q - 1, q2 = q * q;
+    const uint32_t tie_lim = 65537u - qm1;
+    const int nvr = a.nvr, ny = a.ny;
+    const size_t pitch = (size_t)nvr * 16;
+    const int total = a.nrows * nvr;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int Y = idx / nvr, v = idx - Y * nvr;       // Y = replica * ny + y0
+        const int rep = Y / ny, y = Y - rep * ny;
+        const int p = (y + a.colour) & 1;
+        const int Yu = (y + 1 == ny) ? Y + 1 - ny : Y + 1, Yd = (y == 0) ? Y + ny - 1 : Y - 1;
+        const uint8_t* row = a.oth + (size_t)Y * pitch;
+        uint4* po = reinterpret_cast<uint4*>(a.own + (size_t)Y * pitch) + v;
+        const uint4 o = *po;
+        const uint4 b = ld_other(reinterpret_cast<const uint4*>(row) + v);
+        const uint4 up = ld_other(reinterpret_cast<const uint4*>(a.oth + (size_t)Yu * pitch) + v);
+        const uint4 dn = ld_other(reinterpret_cast<const uint4*>(a.oth + (size_t)Yd * pitch) + v);
+        const uint4 s = six_shifted(row, b, v, nvr, a.nxh, p);
+        // right = x0 + 1, left = x0 - 1
+        const uint4 rt = p ? s : b, lf = p ? b : s;
+        const uint32_t k1 = TAG_TORUS + (uint32_t)rep;
+        const uint32_t blk = (uint32_t)(y * nvr + v);
+        uint32_t outw[4];
+        uint32_t ties = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t ow = word_of(o, w);
+            // byte-parallel partial indices: A = r + q u, B = l + q d (< q^2 <= 225)
+            const uint32_t A = word_of(rt, w) + q * word_of(up, w);
+            const uint32_t B = word_of(lf, w) + q * word_of(dn, w);
+            // AB = A + q^2 B in 16-bit fields (< q^4): sites (0, 2) and (1, 3) of the word
+            const uint32_t ABe = (A & 0x00FF00FFu) + q2 * (B & 0x00FF00FFu);
+            const uint32_t ABo = ((A >> 8) & 0x00FF00FFu) + q2 * ((B >> 8) & 0x00FF00FFu);
+            const uint4 R = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, (uint32_t)w), a.rk0, k1);
+            uint32_t res = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t W = word_of(R, e);
+                const uint32_t c = (ow >> (8 * e)) & 0xFFu;
+                const uint32_t ab = ((e & 1) ? ABo : ABe) >> (16 * (e >> 1)) & 0xFFFFu;
+                const uint32_t t = (W & 0xFFFFu) * qm1;          // proposal: k = (t >> 16) + 1 unless the low half decides
+                uint32_t nw = c + 1u + (t >> 16);
+                nw = min(nw, nw - q);                            // unsigned: nw - q wraps when nw < q
+                const uint32_t ix = c + q * nw + q2 * ab;
+                uint32_t cl;
+                if (SMEM) asm("ld.shared.u8 %0, [%1];" : "=r"(cl) : "r"(scls_addr + ix));
+                else cl = a.cls[ix];
+                const uint32_t th = sthi[cl];
+                const uint32_t ha = W >> 16;
+                res |= (ha < th ? nw : c) << (8 * e);
+                if ((t & 0xFFFFu) >= tie_lim || ha == th) ties |= 1u << (4 * w + e);
+            }
+            outw[w] = res;
+        }
+        while (ties) {  // rare: redo the undecided sites with the full 32-bit uniforms
+            const int j = __ffs(ties) - 1;
+            ties &= ties - 1;
+            const uint4 R = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, (uint32_t)(j >> 2)), a.rk0, k1);
+            const uint32_t ns = six_site_exact(a, cls, word_of(R, j & 3), blk, k1, j, byte_of(o, j), byte_of(rt, j),
+                                               byte_of(up, j), byte_of(lf, j), byte_of(dn, j));
+            const int wi = j >> 2, sh = 8 * (j & 3);
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+                if (w == wi) outw[w] = (outw[w] & ~(0xFFu << sh)) | (ns << sh);
+        }
+        *po = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+    }
+}
+
+// reference-stream pass: rnds(2, nx, ny) real64 from a device array, real64 compare against the
+// real64 table, exactly like update_sub (:142-150)
+__global__ void __launch_bounds__(256)
+sixclock_pass_rnds_kernel(const __grid_constant__ SixArgs a, const double* __restrict__ rnds, const double* __restrict__ prob, int rep)
+{
+    const int nx = 2 * a.nxh;
+    const long long total = (long long)a.nxh * a.ny;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int y = (int)(i / a.nxh), xi = (int)(i - (long long)y * a.nxh);
+    const size_t pitch = (size_t)a.nvr * 16;
+    const int Y = rep * a.ny + y;
+    const int p = (y + a.colour) & 1;
+    const int x0 = 2 * xi + p;
+    const int yu = (y + 1 == a.ny) ? 0 : y + 1, yd = (y == 0) ? a.ny - 1 : y - 1;
+    const uint8_t* base = a.oth + (size_t)rep * a.ny * pitch;
+    const int xr = (x0 + 1 == nx) ? 0 : x0 + 1, xl = (x0 == 0) ? nx - 1 : x0 - 1;
+    const uint32_t q = a.q;
+    const uint32_t r = base[(size_t)y * pitch + (xr >> 1)], l = base[(size_t)y * pitch + (xl >> 1)];
+    const uint32_t u = base[(size_t)yu * pitch + xi], d = base[(size_t)yd * pitch + xi];
+    uint8_t* po = a.own + (size_t)Y * pitch + xi;
+    const uint32_t c = *po;
+    const size_t at = (size_t)x0 + (size_t)nx * y;
+    int nw = (int)c + (int)ceil(rnds[2 * at] * (double)(q - 1));
+    if (nw >= (int)q) nw -= (int)q;
+    if (nw < 0 || nw >= (int)q) return;  // rnds outside (0, 1]
+    const size_t ix = (size_t)c + q * ((size_t)nw + q * ((size_t)r + q * ((size_t)u + q * ((size_t)l + (size_t)q * d))));
+    if (rnds[2 * at + 1] <= prob[ix]) *po = (uint8_t)nw;
+}
+
+// (a - b) mod q per byte, a, b in [0, q)
+__device__ __forceinline__ uint32_t six_submod(uint32_t a, uint32_t b, uint32_t q)
+{
+    const uint32_t d = a + q * 0x01010101u - b;
+    const uint32_t ge = ((d + (0x80u - q) * 0x01010101u) >> 7) & 0x01010101u;
+    return d - ge * q;
+}
+__device__ __forceinline__ void six_onehot8(uint32_t w0, uint32_t w1, uint32_t keep0, uint32_t keep1, uint32_t& hA, uint32_t& hB)
+{
+    const uint32_t pk = w0 + (w1 << 4);
+    hA = prmt(0x08040201u, 0x80402010u, pk) & prmt(keep0, keep1, 0x5140u);
+    hB = prmt(0x08040201u, 0x80402010u, pk >> 16) & prmt(keep0, keep1, 0x7362u);
+}
+
+// Exact integer observables per replica (calc_magne :155-165 and calc_energy :167-181 only depend
+// on them): acc[rep*192 + c] += #{state c}; acc[rep*192 + 64 + d] += #{(s(x+1, y) - s(x, y)) mod q = d};
+// acc[rep*192 + 128 + d] += same for (x, y+1).   q <= 8: SWAR one-hot + POPC; else shared atomics.
+__global__ void __launch_bounds__(256)
+sixclock_measure_kernel(const uint8_t* __restrict__ c0, const uint8_t* __restrict__ c1, int nxh, int ny, int nvr, int rep,
+                        uint32_t q, unsigned long long* acc)
+{
+    __shared__ unsigned long long sacc[3 * 64];
+    for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) sacc[i] = 0;
+    __syncthreads();
+    uint32_t cnt[3][8];
+#pragma unroll
+    for (int h = 0; h < 3; ++h)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) cnt[h][c] = 0;
+    const size_t pitch = (size_t)nvr * 16;
+    const int total = ny * nvr;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int y = idx / nvr, v = idx - y * nvr;
+        const int Y = rep * ny + y, Yu = rep * ny + ((y + 1 == ny) ? 0 : y + 1);
+        uint32_t keep[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            keep[w] = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (16 * v + 4 * w + j < nxh) keep[w] |= 0xFFu << (8 * j);
+        }
+#pragma unroll
+        for (int colour = 0; colour < 2; ++colour) {
+            const uint8_t* own = colour ? c1 : c0;
+            const uint8_t* oth = colour ? c0 : c1;
+            const int p = (y + colour) & 1;
+            const uint8_t* row = oth + (size_t)Y * pitch;
+            const uint4 o = *(reinterpret_cast<const uint4*>(own + (size_t)Y * pitch) + v);
+            const uint4 b = *(reinterpret_cast<const uint4*>(row) + v);
+            const uint4 u = *(reinterpret_cast<const uint4*>(oth + (size_t)Yu * pitch) + v);
+            const uint4 r = p ? six_shifted(row, b, v, nvr, nxh, 1) : b;   // x0 + 1
+            const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, rw[4] = {r.x, r.y, r.z, r.w}, uw[4] = {u.x, u.y, u.z, u.w};
+            if (q <= 8) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    uint32_t hs[2], hr[2], hu[2];
+                    six_onehot8(ow[2 * g], ow[2 * g + 1], keep[2 * g], keep[2 * g + 1], hs[0], hs[1]);
+                    six_onehot8(six_submod(rw[2 * g], ow[2 * g], q), six_submod(rw[2 * g + 1], ow[2 * g + 1], q),
+                                keep[2 * g], keep[2 * g + 1], hr[0], hr[1]);
+                    six_onehot8(six_submod(uw[2 * g], ow[2 * g], q), six_submod(uw[2 * g + 1], ow[2 * g + 1], q),
+                                keep[2 * g], keep[2 * g + 1], hu[0], hu[1]);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t m = 0x01010101u << c;
+                        cnt[0][c] += __popc(hs[0] & m) + __popc(hs[1] & m);
+                        cnt[1][c] += __popc(hr[0] & m) + __popc(hr[1] & m);
+                        cnt[2][c] += __popc(hu[0] & m) + __popc(hu[1] & m);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (!((keep[j >> 2] >> (8 * (j & 3))) & 1u)) continue;
+                    const uint32_t s = (ow[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                    const uint32_t rr = (rw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                    const uint32_t uu = (uw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                    uint32_t dr = rr + q - s; if (dr >= q) dr -= q;
+                    uint32_t du = uu + q - s; if (du >= q) du -= q;
+                    atomicAdd(&sacc[s], 1ull);
+                    atomicAdd(&sacc[64 + dr], 1ull);
+                    atomicAdd(&sacc[128 + du], 1ull);
+                }
+            }
+        }
+    }
+    if (q <= 8) {
+#pragma unroll
+        for (int h = 0; h < 3; ++h)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint32_t t = cnt[h][c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+                if ((threadIdx.x & 31) == 0 && t) atomicAdd(&sacc[h * 64 + c], (unsigned long long)t);
+            }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x)
+        if (sacc[i]) atomicAdd(&acc[(size_t)rep * 192 + i], sacc[i]);
+}
+
+// sixclock(nx, ny) int32 (column-major: x fastest) <-> the two byte colour arrays of one replica
+__global__ void sixclock_export_kernel(const uint8_t* c0, const uint8_t* c1, int nx, int ny, size_t pitch, int32_t* out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nx * ny) return;
+    const int y0 = (int)(i / nx), x0 = (int)(i - (long long)y0 * nx);
+    out[i] = (((x0 + y0) & 1) ? c1 : c0)[(size_t)y0 * pitch + (x0 >> 1)];
+}
+__global__ void sixclock_import_kernel(uint8_t* c0, uint8_t* c1, int nx, int ny, size_t pitch, const int32_t* in)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nx * ny) return;
+    const int y0 = (int)(i / nx), x0 = (int)(i - (long long)y0 * nx);
+    (((x0 + y0) & 1) ? c1 : c0)[(size_t)y0 * pitch + (x0 >> 1)] = (uint8_t)in[i];
+}
+// sixclock_even / sixclock_odd (nx/2, ny) int32 <-> one colour array of one replica
+__global__ void sixclock_export_half_kernel(const uint8_t* c, int nxh, int ny, size_t pitch, int32_t* out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nxh * ny) return;
+    const int y0 = (int)(i / nxh), xi = (int)(i - (long long)y0 * nxh);
+    out[i] = c[(size_t)y0 * pitch + xi];
+}
+__global__ void sixclock_import_half_kernel(uint8_t* c, int nxh, int ny, size_t pitch, const int32_t* in)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nxh * ny) return;
+    const int y0 = (int)(i / nxh), xi = (int)(i - (long long)y0 * nxh);
+    c[(size_t)y0 * pitch + xi] = (uint8_t)in[i];
+}
+
+struct Six {
+    int64_t nx, ny;
+    int32_t q, n_multi;
+    int nxh, nvr;
+    size_t pitch, rep_bytes;     // bytes per row / per replica per colour
+    uint8_t* c[2];
+    cudaStream_t stream;
+    double beta;
+    uint32_t seed;
+    uint64_t draw;
+    std::vector<double> magne, e3, prob;  // host tables exactly as the reference builds them
+    uint8_t* d_cls;
+    uint32_t *d_thi, *d_tlo;
+    double* d_prob;
+    double* d_rnds;
+    int32_t* d_stage;
+    unsigned long long* d_acc;
+    int grid, smem_bytes, cls_in_smem, sms;
+    bool obs_valid;
+    std::vector<long long> obs;  // n_multi x 192
+    // optional per-launch timing of the pass kernel
+    bool timing;
+    std::vector<cudaEvent_t> evs;
+    size_t ev_used;
+};
+
+int build_tables(Six* m)
+{
+    const int q = m->q;
+    const double pi = 4 * atan(1.0);
+    const double psi = 2 * pi / q;  // pi_state_inv, :11
+    const size_t q3 = (size_t)q * q * q, q6 = q3 * q3;
+    m->magne.resize(q); m->e3.resize(q3); m->prob.resize(q6);
+    for (int c = 0; c < q; ++c) m->magne[c] = cos(c * psi);  // state_to_magne, :26
+    // state_center_right_up_to_energy, :27-33: the constructor runs global_c fastest, then global_u,
+    // then global_r, so element (i1, i2, i3) was computed with global_c = i1, global_u = i2, global_r = i3
+    for (int i3 = 0; i3 < q; ++i3)
+        for (int i2 = 0; i2 < q; ++i2)
+            for (int i1 = 0; i1 < q; ++i1)
+                m->e3[i1 + q * (i2 + q * i3)] = -cos((i2 - i1) * psi) - cos((i3 - i1) * psi);
+#define E3(i1, i2, i3) m->e3[(i1) + q * ((i2) + q * (i3))]
+    std::map<uint64_t, int> classes;
+    std::vector<uint8_t> cls(q6);
+    std::vector<uint32_t> thi, tlo;
+    // init_sixclock, :66-86 (same loop nest, same expression order)
+    for (int d = 0; d < q; ++d)
+        for (int l = 0; l < q; ++l)
+            for (int u = 0; u < q; ++u)
+                for (int r = 0; r < q; ++r)
+                    for (int nc = 0; nc < q; ++nc)
+                        for (int c = 0; c < q; ++c) {
+                            const double de = E3(nc, r, u) - E3(c, r, u) + E3(nc, l, d) - E3(c, l, d);
+                            const double w = (de <= 0.0) ? 1.0 : exp(-m->beta * de);
+                            const size_t at = (size_t)c + (size_t)q * (nc + (size_t)q * (r + (size_t)q * (u + (size_t)q * (l + (size_t)q * d))));
+                            m->prob[at] = w;
+                            uint64_t t = (uint64_t)floor(w * 4294967296.0);  // rnds2 <= w  <=>  U_a < floor(w 2^32)
+                            if (t > 4294967296ull) t = 4294967296ull;
+                            auto it = classes.find(t);
+                            int id;
+                            if (it == classes.end()) {
+                                id = (int)thi.size();
+                                if (id >= SIX_MAX_CLASSES) {
+                                    snprintf(g_b200mc_err, sizeof(g_b200mc_err), "sixclock: more than %d distinct acceptance thresholds (mstate = %d)", SIX_MAX_CLASSES, q);
+                                    return B200MC_ERR_UNSUPPORTED;
+                                }
+                                classes[t] = id;
+                                thi.push_back((uint32_t)(t >> 16));
+                                tlo.push_back((uint32_t)(t & 0xFFFFu));
+                            } else id = it->second;
+                            cls[at] = (uint8_t)id;
+                        }
+#undef E3
+    thi.resize(SIX_MAX_CLASSES, 0); tlo.resize(SIX_MAX_CLASSES, 0);
+    CK(cudaMemcpyAsync(m->d_cls, cls.data(), q6, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemcpyAsync(m->d_thi, thi.data(), SIX_MAX_CLASSES * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemcpyAsync(m->d_tlo, tlo.data(), SIX_MAX_CLASSES * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
+    if (m->d_prob) CK(cudaMemcpyAsync(m->d_prob, m->prob.data(), q6 * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    return B200MC_OK;
+}
+
+void fill_args(Six* m, int colour, SixArgs* a)
+{
+    a->own = m->c[colour]; a->oth = m->c[colour ^ 1];
+    a->nxh = m->nxh; a->ny = (int)m->ny; a->nvr = m->nvr; a->nrows = (int)(m->n_multi * m->ny);
+    a->colour = colour; a->q = (uint32_t)m->q;
+    a->cls = m->d_cls; a->thi = m->d_thi; a->tlo = m->d_tlo;
+    a->tab_bytes = (uint32_t)m->prob.size(); a->cls_in_smem = m->cls_in_smem;
+    a->draw = m->draw;
+    for (int r = 0; r < 10; ++r) a->rk0[r] = m->seed + (uint32_t)r * PHILOX_W0;
+}
+
+int sweep(Six* m)
+{
+    m->obs_valid = false;
+    for (int colour = 0; colour < 2; ++colour) {  // parity 0 = even sites first, :96-101
+        SixArgs a;
+        fill_args(m, colour, &a);
+        if (m->timing) {
+            while (m->evs.size() < m->ev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); m->evs.push_back(e); }
+            CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
+        }
+        COUNT_LAUNCH();
+        if (m->cls_in_smem) sixclock_pass_kernel<true><<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
+        else sixclock_pass_kernel<false><<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
+        CK(cudaGetLastError());
+        if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
+    }
+    m->draw += 1;
+    return B200MC_OK;
+}
+
+int update_with_rnds(Six* m, const double* rnds)
+{
+    if (!rnds) ARG_FAIL("null rnds");
+    const size_t N = (size_t)m->nx * m->ny, q6 = m->prob.size();
+    if (!m->d_prob) {
+        CK(cudaMalloc(&m->d_prob, q6 * sizeof(double)));
+        CK(cudaMemcpy(m->d_prob, m->prob.data(), q6 * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&m->d_rnds, 2 * N * sizeof(double)));
+    }
+    m->obs_valid = false;
+    const unsigned grid = (unsigned)(((size_t)m->nxh * m->ny + 255) / 256);
+    for (int rep = 0; rep < m->n_multi; ++rep) {
+        CK(cudaMemcpyAsync(m->d_rnds, rnds + (size_t)rep * 2 * N, 2 * N * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+        for (int colour = 0; colour < 2; ++colour) {
+            SixArgs a;
+            fill_args(m, colour, &a);
+            COUNT_LAUNCH();
+            sixclock_pass_rnds_kernel<<<grid, 256, 0, m->stream>>>(a, m->d_rnds, m->d_prob, rep);
+            CK(cudaGetLastError());
+        }
+        CK(cudaStreamSynchronize(m->stream));
+    }
+    return B200MC_OK;
+}
+
+int measure(Six* m)
+{
+    if (m->obs_valid) return B200MC_OK;
+    CK(cudaMemsetAsync(m->d_acc, 0, (size_t)m->n_multi * 192 * sizeof(unsigned long long), m->stream));
+    const int need = (int)(((size_t)m->ny * m->nvr + 255) / 256);
+    const int grid = need < m->sms * 8 ? need : m->sms * 8;
+    for (int rep = 0; rep < m->n_multi; ++rep) {
+        COUNT_LAUNCH();
+        sixclock_measure_kernel<<<grid, 256, 0, m->stream>>>(m->c[0], m->c[1], m->nxh, (int)m->ny, m->nvr, rep, (uint32_t)m->q, m->d_acc);
+        CK(cudaGetLastError());
+    }
+    m->obs.resize((size_t)m->n_multi * 192);
+    CK(cudaMemcpyAsync(m->obs.data(), m->d_acc, m->obs.size() * sizeof(long long), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->obs_valid = true;
+    return B200MC_OK;
+}
+
+void destroy(Six* m)
+{
+    cudaStreamSynchronize(m->stream);
+    cudaFree(m->c[0]); cudaFree(m->c[1]); cudaFree(m->d_cls); cudaFree(m->d_thi); cudaFree(m->d_tlo);
+    cudaFree(m->d_prob); cudaFree(m->d_rnds); cudaFree(m->d_stage); cudaFree(m->d_acc);
+    for (cudaEvent_t e : m->evs) cudaEventDestroy(e);
+    delete m;
+}
+
+int stage(Six* m)
+{
+    if (!m->d_stage) CK(cudaMalloc(&m->d_stage, (size_t)m->nx * m->ny * sizeof(int32_t)));
+    return B200MC_OK;
+}
+
+}  // namespace
+
+#define HS(h) (reinterpret_cast<Six*>(h))
+#define CHECK_S(h) do { if (!(h)) ARG_FAIL("invalid handle"); } while (0)
+
+extern "C" {
+
+int b200mc_sixclock_create(void** out, int64_t nx, int64_t ny, double kbt, int32_t mstate, int32_t n_multi, int32_t iseed)
+{
+    if (!out) ARG_FAIL("null handle pointer");
+    *out = nullptr;
+    if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0");
+    if (mstate < 2) ARG_FAIL("mstate must be >= 2");
+    if (mstate > 12) { snprintf(g_b200mc_err, sizeof(g_b200mc_err), "sixclock: mstate = %d not supported (q^6 table; max 12)", mstate); return B200MC_ERR_UNSUPPORTED; }
+    if (n_multi < 1) ARG_FAIL("n_multi must be >= 1");
+    // (x + y) parity colouring on a torus needs both extents even (the reference races otherwise)
+    if (nx < 2 || ny < 2 || (nx & 1) || (ny & 1)) ARG_FAIL("sixclock: nx and ny must be even and >= 2 (got %lld x %lld)", (long long)nx, (long long)ny);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        snprintf(g_b200mc_err, sizeof(g_b200mc_err), "no CUDA device: this library has no CPU fallback");
+        return B200MC_ERR_CUDA;
+    }
+    const int64_t nxh = nx / 2, nvr = (nxh + 15) / 16;
+    if ((double)n_multi * (double)ny * (double)nvr >= 2147483000.0) ARG_FAIL("sixclock: lattice x batch too large for 32-bit vector indices");
+    Six* m = new (std::nothrow) Six();
+    if (!m) ARG_FAIL("out of host memory");
+    m->nx = nx; m->ny = ny; m->q = mstate; m->n_multi = n_multi; m->nxh = (int)nxh; m->nvr = (int)nvr;
+    m->pitch = (size_t)nvr * 16; m->rep_bytes = m->pitch * (size_t)ny;
+    m->stream = 0; m->seed = (uint32_t)iseed; m->draw = 0; m->beta = 1 / kbt; m->obs_valid = false;
+    m->c[0] = m->c[1] = nullptr; m->d_cls = nullptr; m->d_thi = m->d_tlo = nullptr; m->d_prob = nullptr; m->d_rnds = nullptr;
+    m->d_stage = nullptr; m->d_acc = nullptr; m->timing = false; m->ev_used = 0;
+    const size_t q6 = (size_t)mstate * mstate * mstate * mstate * mstate * mstate;
+    const size_t bytes = m->rep_bytes * (size_t)n_multi;
+    if (cudaMalloc(&m->c[0], bytes) != cudaSuccess || cudaMalloc(&m->c[1], bytes) != cudaSuccess ||
+        cudaMalloc(&m->d_cls, (q6 + 15) / 16 * 16) != cudaSuccess || cudaMalloc(&m->d_thi, SIX_MAX_CLASSES * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&m->d_tlo, SIX_MAX_CLASSES * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&m->d_acc, (size_t)n_multi * 192 * sizeof(unsigned long long)) != cudaSuccess) {
+        snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed (%zu bytes per colour)", bytes);
+        cudaGetLastError();
+        destroy(m); return B200MC_ERR_CUDA;
+    }
+    cudaMemsetAsync(m->c[0], 0, bytes, m->stream);   // init_sixclock_order: all states 0 (pad bytes too)
+    cudaMemsetAsync(m->c[1], 0, bytes, m->stream);
+    const size_t want = SIX_MAX_CLASSES * sizeof(uint32_t) + (q6 + 15) / 16 * 16;
+    int dev = 0, maxsm = 0, occ = 1;
+    m->sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&m->sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    m->cls_in_smem = want <= (size_t)maxsm ? 1 : 0;
+    m->smem_bytes = (int)(m->cls_in_smem ? want : SIX_MAX_CLASSES * sizeof(uint32_t));
+    if ((m->cls_in_smem ? cudaFuncSetAttribute(sixclock_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes)
+                        : cudaFuncSetAttribute(sixclock_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes)) != cudaSuccess) {
+        snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaFuncSetAttribute(smem) failed");
+        destroy(m); return B200MC_ERR_CUDA;
+    }
+    if (m->cls_in_smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sixclock_pass_kernel<true>, 256, m->smem_bytes);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sixclock_pass_kernel<false>, 256, m->smem_bytes);
+    if (occ < 1) occ = 1;
+    const int64_t need = ((int64_t)n_multi * ny * nvr + 255) / 256;
+    m->grid = (int)(need < (int64_t)m->sms * occ ? need : (int64_t)m->sms * occ);
+    int rc = build_tables(m);
+    if (rc) { destroy(m); return rc; }
+    *out = m;
+    return B200MC_OK;
+}
+int b200mc_sixclock_destroy(void* h) { if (h) destroy(HS(h)); return B200MC_OK; }
+int b200mc_sixclock_set_stream(void* h, void* s) { CHECK_S(h); HS(h)->stream = (cudaStream_t)s; return B200MC_OK; }
+int b200mc_sixclock_skip_curand_clock(void* h, int64_t n_skip)
+{
+    CHECK_S(h);
+    if (n_skip < 0) ARG_FAIL("n_skip < 0");
+    const int64_t per = 2 * HS(h)->nx * HS(h)->ny;  // uniforms per update_metropolis, :95
+    HS(h)->draw += (uint64_t)((n_skip + per - 1) / per);
+    return B200MC_OK;
+}
+int b200mc_sixclock_init_sixclock_order(void* h)
+{
+    CHECK_S(h);
+    Six* m = HS(h);
+    m->obs_valid = false;
+    const size_t bytes = m->rep_bytes * (size_t)m->n_multi;
+    CK(cudaMemsetAsync(m->c[0], 0, bytes, m->stream));
+    CK(cudaMemsetAsync(m->c[1], 0, bytes, m->stream));
+    return B200MC_OK;
+}
+int b200mc_sixclock_set_kbt(void* h, double kbt) { CHECK_S(h); if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0"); HS(h)->beta = 1 / kbt; return build_tables(HS(h)); }
+int b200mc_sixclock_update_metropolis(void* h) { CHECK_S(h); return sweep(HS(h)); }
+int b200mc_sixclock_update_metropolis_n(void* h, int32_t n) { CHECK_S(h); for (int i = 0; i < n; ++i) { int rc = sweep(HS(h)); if (rc) return rc; } return B200MC_OK; }
+int b200mc_sixclock_update_with_rnds(void* h, const double* rnds) { CHECK_S(h); return update_with_rnds(HS(h), rnds); }
+int b200mc_sixclock_get_histograms(void* h, int64_t* hist, int64_t* bond_right, int64_t* bond_up)
+{
+    CHECK_S(h);
+    Six* m = HS(h);
+    int rc = measure(m);
+    if (rc) return rc;
+    for (int j = 0; j < m->n_multi; ++j)
+        for (int c = 0; c < m->q; ++c) {
+            if (hist) hist[j * m->q + c] = m->obs[(size_t)j * 192 + c];
+            if (bond_right) bond_right[j * m->q + c] = m->obs[(size_t)j * 192 + 64 + c];
+            if (bond_up) bond_up[j * m->q + c] = m->obs[(size_t)j * 192 + 128 + c];
+        }
+    return B200MC_OK;
+}
+int b200mc_sixclock_calc_energy(void* h, double* res)
+{
+    CHECK_S(h);
+    Six* m = HS(h);
+    if (!res) ARG_FAIL("null output");
+    int rc = measure(m);
+    if (rc) return rc;
+    const double nall_inv = 1.0 / (double)(m->nx * m->ny);  // :13
+    for (int j = 0; j < m->n_multi; ++j) {
+        // sum of state_center_right_up_to_energy(c, r, u) = -cos((r - c) psi) - cos((u - c) psi), :177
+        double e = 0.0;
+        for (int d = 0; d < m->q; ++d)
+            e -= (double)(m->obs[(size_t)j * 192 + 64 + d] + m->obs[(size_t)j * 192 + 128 + d]) * m->magne[d];
+        res[j] = e * nall_inv;
+    }
+    return B200MC_OK;
+}
+int b200mc_sixclock_calc_magne(void* h, double* res)
+{
+    CHECK_S(h);
+    Six* m = HS(h);
+    if (!res) ARG_FAIL("null output");
+    int rc = measure(m);
+    if (rc) return rc;
+    const double nall_inv = 1.0 / (double)(m->nx * m->ny);
+    for (int j = 0; j < m->n_multi; ++j) {
+        double s = 0.0;
+        for (int c = 0; c < m->q; ++c) s += (double)m->obs[(size_t)j * 192 + c] * m->magne[c];
+        res[j] = s * nall_inv;
+    }
+    return B200MC_OK;
+}
+int b200mc_sixclock_get_sixclock(void* h, int32_t* out)
+{
+    CHECK_S(h);
+    if (!out) ARG_FAIL("null output");
+    Six* m = HS(h);
+    int rc = stage(m);
+    if (rc) return rc;
+    const size_t N = (size_t)m->nx * m->ny;
+    for (int j = 0; j < m->n_multi; ++j) {
+        COUNT_LAUNCH();
+        sixclock_export_kernel<<<(unsigned)((N + 255) / 256), 256, 0, m->stream>>>(m->c[0] + j * m->rep_bytes, m->c[1] + j * m->rep_bytes, (int)m->nx, (int)m->ny, m->pitch, m->d_stage);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out + (size_t)j * N, m->d_stage, N * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+    }
+    return B200MC_OK;
+}
+int b200mc_sixclock_set_sixclock(void* h, const int32_t* in)
+{
+    CHECK_S(h);
+    if (!in) ARG_FAIL("null input");
+    Six* m = HS(h);
+    const size_t N = (size_t)m->nx * m->ny;
+    for (size_t i = 0; i < N * (size_t)m->n_multi; ++i)
+        if (in[i] < 0 || in[i] >= m->q) ARG_FAIL("sixclock: state %d at element %zu outside 0..%d", in[i], i, m->q - 1);
+    int rc = stage(m);
+    if (rc) return rc;
+    m->obs_valid = false;
+    for (int j = 0; j < m->n_multi; ++j) {
+        CK(cudaMemcpyAsync(m->d_stage, in + (size_t)j * N, N * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
+        COUNT_LAUNCH();
+        sixclock_import_kernel<<<(unsigned)((N + 255) / 256), 256, 0, m->stream>>>(m->c[0] + j * m->rep_bytes, m->c[1] + j * m->rep_bytes, (int)m->nx, (int)m->ny, m->pitch, m->d_stage);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(m->stream));
+    }
+    return B200MC_OK;
+}
+int b200mc_sixclock_get_dual(void* h, int32_t* even, int32_t* odd)
+{
+    CHECK_S(h);
+    if (!even || !odd) ARG_FAIL("null output");
+    Six* m = HS(h);
+    int rc = stage(m);
+    if (rc) return rc;
+    const size_t Nh = (size_t)m->nxh * m->ny;
+    int32_t* dst[2] = {even, odd};
+    for (int j = 0; j < m->n_multi; ++j)
+        for (int c = 0; c < 2; ++c) {
+            COUNT_LAUNCH();
+            sixclock_export_half_kernel<<<(unsigned)((Nh + 255) / 256), 256, 0, m->stream>>>(m->c[c] + j * m->rep_bytes, m->nxh, (int)m->ny, m->pitch, m->d_stage);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(dst[c] + (size_t)j * Nh, m->d_stage, Nh * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+            CK(cudaStreamSynchronize(m->stream));
+        }
+    return B200MC_OK;
+}
+int b200mc_sixclock_set_dual(void* h, const int32_t* even, const int32_t* odd)
+{
+    CHECK_S(h);
+    if (!even || !odd) ARG_FAIL("null input");
+    Six* m = HS(h);
+    const size_t Nh = (size_t)m->nxh * m->ny;
+    const int32_t* src[2] = {even, odd};
+    for (int c = 0; c < 2; ++c)
+        for (size_t i = 0; i < Nh * (size_t)m->n_multi; ++i)
+            if (src[c][i] < 0 || src[c][i] >= m->q) ARG_FAIL("sixclock: state %d outside 0..%d", src[c][i], m->q - 1);
+    int rc = stage(m);
+    if (rc) return rc;
+    m->obs_valid = false;
+    for (int j = 0; j < m->n_multi; ++j)
+        for (int c = 0; c < 2; ++c) {
+            CK(cudaMemcpyAsync(m->d_stage, src[c] + (size_t)j * Nh, Nh * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
+            COUNT_LAUNCH();
+            sixclock_import_half_kernel<<<(unsigned)((Nh + 255) / 256), 256, 0, m->stream>>>(m->c[c] + j * m->rep_bytes, m->nxh, (int)m->ny, m->pitch, m->d_stage);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(m->stream));
+        }
+    return B200MC_OK;
+}
+int b200mc_sixclock_get_states_to_prob(void* h, double* out)
+{
+    CHECK_S(h);
+    for (size_t i = 0; i < HS(h)->prob.size(); ++i) out[i] = HS(h)->prob[i];
+    return B200MC_OK;
+}
+int b200mc_sixclock_get_energy_table(void* h, double* out)
+{
+    CHECK_S(h);
+    for (size_t i = 0; i < HS(h)->e3.size(); ++i) out[i] = HS(h)->e3[i];
+    return B200MC_OK;
+}
+int64_t b200mc_sixclock_nx(void* h) { return h ? HS(h)->nx : -1; }
+int64_t b200mc_sixclock_ny(void* h) { return h ? HS(h)->ny : -1; }
+int64_t b200mc_sixclock_nall(void* h) { return h ? HS(h)->nx * HS(h)->ny : -1; }
+int32_t b200mc_sixclock_mstate(void* h) { return h ? HS(h)->q : -1; }
+int32_t b200mc_sixclock_n_multi(void* h) { return h ? HS(h)->n_multi : -1; }
+double b200mc_sixclock_kbt(void* h) { return h ? 1 / HS(h)->beta : 0.0; }
+double b200mc_sixclock_beta(void* h) { return h ? HS(h)->beta : 0.0; }
+int b200mc_sixclock_set_timing(void* h, int32_t on) { CHECK_S(h); HS(h)->timing = on != 0; HS(h)->ev_used = 0; return B200MC_OK; }
+int b200mc_sixclock_get_timing(void* h, int64_t* launches, double* total_ms)
+{
+    CHECK_S(h);
+    Six* m = HS(h);
+    CK(cudaStreamSynchronize(m->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < m->ev_used; i += 2) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, m->evs[i], m->evs[i + 1]));
+        tot += ms;
+    }
+    if (launches) *launches = (int64_t)(m->ev_used / 2);
+    if (total_ms) *total_ms = tot;
+    return B200MC_OK;
+}
+int b200mc_sixclock_sync(void* h) { CHECK_S(h); CK(cudaStreamSynchronize(HS(h)->stream)); return B200MC_OK; }
+
+}  // extern "C"

@@ -194,6 +194,53 @@ double b200mc_clock_beta(void* h);
 int b200mc_clock_sync(void* h);
 
 /* ------------------------------------------------------------------------
+ * Periodic q-state clock with the full q^6 table -- module clock_tableall_gpu_m,
+ * src/clock/clock_tableall_gpu_m.f90:43-45 (module procedures, module-global state), and its
+ * compact two-colour twin module clock_dual_lattice_tableall_gpu_m,
+ * src/clock/clock_dual_lattice_tableall_m.f90:43-45 (same trajectory: its randoms are indexed
+ * by the full-lattice coordinate, :144-152).  One handle serves both: the state is stored as
+ * the dual-lattice colour arrays; get/set_sixclock convert to the tableall array.
+ * nx, ny, kbt, mstate are compile-time parameters in the reference (:10-15), run-time here;
+ * n_multi independent samples ("multi-sample batch") are updated by one launch per colour,
+ * arrays over samples are sample-major.  True periodic boundary, colour = (x + y) parity;
+ * nx and ny must be even.
+ * ------------------------------------------------------------------------ */
+int b200mc_sixclock_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t mstate, int32_t n_multi, int32_t iseed); /* init_sixclock :57-88 */
+int b200mc_sixclock_destroy(void* h);
+int b200mc_sixclock_set_stream(void* h, void* cuda_stream);
+int b200mc_sixclock_skip_curand_clock(void* h, int64_t n_skip);   /* :51-55 */
+int b200mc_sixclock_init_sixclock_order(void* h);                 /* :90-92 */
+int b200mc_sixclock_set_kbt(void* h, double kbt);                 /* rebuilds states_to_prob (:66-86) */
+int b200mc_sixclock_update_metropolis(void* h);                   /* one MCS, :94-152 */
+int b200mc_sixclock_update_metropolis_n(void* h, int32_t n_sweeps);
+/* one MCS reading rnds(2, nx, ny[, n_multi]) from the host in the reference's order (:95) */
+int b200mc_sixclock_update_with_rnds(void* h, const double* rnds);
+int b200mc_sixclock_calc_energy(void* h, double* res /* n_multi per-site values */); /* :167-181 */
+int b200mc_sixclock_calc_magne(void* h, double* res);                                /* :155-165 */
+/* exact integer observables per sample: hist[j*q + c] = #{s = c}; bond_right[j*q + d] =
+ * #{(s(x+1, y) - s(x, y)) mod q = d}; bond_up: same for (x, y+1) */
+int b200mc_sixclock_get_histograms(void* h, int64_t* hist, int64_t* bond_right, int64_t* bond_up);
+/* sixclock(nx, ny[, n_multi]) int32, Fortran order (tableall :22) */
+int b200mc_sixclock_get_sixclock(void* h, int32_t* out);
+int b200mc_sixclock_set_sixclock(void* h, const int32_t* in);
+/* sixclock_even / sixclock_odd (nx/2, ny[, n_multi]) int32 (dual lattice :22) */
+int b200mc_sixclock_get_dual(void* h, int32_t* even, int32_t* odd);
+int b200mc_sixclock_set_dual(void* h, const int32_t* even, const int32_t* odd);
+/* host copies of states_to_prob(c, new_c, r, u, l, d) (q^6) and state_center_right_up_to_energy (q^3) */
+int b200mc_sixclock_get_states_to_prob(void* h, double* out);
+int b200mc_sixclock_get_energy_table(void* h, double* out);
+int64_t b200mc_sixclock_nx(void* h);
+int64_t b200mc_sixclock_ny(void* h);
+int64_t b200mc_sixclock_nall(void* h);
+int32_t b200mc_sixclock_mstate(void* h);
+int32_t b200mc_sixclock_n_multi(void* h);
+double b200mc_sixclock_kbt(void* h);
+double b200mc_sixclock_beta(void* h);
+int b200mc_sixclock_set_timing(void* h, int32_t on);
+int b200mc_sixclock_get_timing(void* h, int64_t* launches, double* total_ms);
+int b200mc_sixclock_sync(void* h);
+
+/* ------------------------------------------------------------------------
  * XY 2D, periodic -- type(xy2d_gpu), src/xy2d_periodic_gpu_m.f90:14-59.
  * State: one fp32 angle per site (turns); energy / magnetisation are real64
  * sums, compared with the reference at 1e-5 relative (BASELINE north_star).

@@ -109,6 +109,7 @@ def _declare(L):
     d("orc_clock_uniforms", None, u32, u64, i32, i64, P, P)
     d("orc_xy_uniforms", None, u32, u64, i64, i64, P, P)
     d("orc_xy_init_uniforms", None, u32, u64, i64, i64, P)
+    d("orc_torus_uniforms", None, u32, u64, i32, i64, i64, P)
 
 
 def _p(a: np.ndarray):
@@ -166,6 +167,13 @@ def xy_uniforms(seed: int, draw: int, nx: int, ny: int):
     c = np.empty(nx * ny, dtype=np.float64)
     lib().orc_xy_uniforms(seed & 0xFFFFFFFF, draw, nx, ny, _p(r), _p(c))
     return r, c
+
+
+def torus_uniforms(seed: int, draw: int, replica: int, nx: int, ny: int) -> np.ndarray:
+    """rnds(2, nx, ny) of update_metropolis (src/clock/clock_tableall_gpu_m.f90:95), flat"""
+    out = np.empty(2 * nx * ny, dtype=np.float64)
+    lib().orc_torus_uniforms(seed & 0xFFFFFFFF, draw, replica, nx, ny, _p(out))
+    return out
 
 
 def xy_init_uniforms(seed: int, draw: int, nx: int, ny: int):

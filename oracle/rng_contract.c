@@ -214,3 +214,41 @@ ORC_API void orc_xy_init_uniforms(uint32_t seed, uint64_t draw, int64_t nx, int6
             out[x0 + nx * y0] = ((double)r[xi & 3] + 1.0) * 0x1p-32;
         }
 }
+
+/* --------------------------------------------------------------------------
+ * Periodic clock (clock_tableall_gpu_m / clock_dual_lattice_tableall_gpu_m): true torus,
+ * colour = (x0 + y0) & 1, colour-compact index xi = x0 >> 1; rows are cut into vectors of 16
+ * compact sites: v = xi >> 4, j = xi & 15, nvr = ceil((nx/2) / 16), block = y0 * nvr + v.
+ * Two 32-bit uniforms per site and sweep, assembled from two Philox words (the GPU evaluates
+ * the second one only when the 16 bits of the first do not decide; the value is the same):
+ *   W  = philox(ctr(block, draw, colour,     j >> 2), (seed, TAG_TORUS + replica))[j & 3]
+ *   W2 = philox(ctr(block, draw, colour, 4 + (j >> 2)), same key)[j & 3]
+ *   accept   U_a = (W & 0xFFFF0000) | (W2 >> 16)      -> rnds(2, x, y)
+ *   proposal U_p = (W << 16)        | (W2 & 0xFFFF)   -> rnds(1, x, y)
+ * u = (U + 1) 2^-32.  Written in the reference's order rnds(2, nx, ny)
+ * (src/clock/clock_tableall_gpu_m.f90:95): out[(j-1) + 2*(x0 + nx*y0)].
+ * -------------------------------------------------------------------------- */
+ORC_API void orc_torus_uniforms(uint32_t seed, uint64_t draw, int32_t replica, int64_t nx, int64_t ny,
+                                double *rnds)
+{
+    const int64_t nxh = nx / 2, nvr = (nxh + 15) / 16;
+    const uint32_t key[2] = {seed, TAG_TORUS + (uint32_t)replica};
+#pragma omp parallel for schedule(static)
+    for (int64_t y0 = 0; y0 < ny; ++y0)
+        for (int64_t x0 = 0; x0 < nx; ++x0) {
+            const uint32_t colour = (uint32_t)((x0 + y0) & 1);
+            const int64_t xi = x0 >> 1;
+            const int j = (int)(xi & 15);
+            const uint64_t blk = (uint64_t)(y0 * nvr + (xi >> 4));
+            uint32_t c[4], r[4], r2[4];
+            mk_ctr(c, blk, draw, colour, (uint32_t)(j >> 2));
+            orc_philox4x32_10(c, key, r);
+            mk_ctr(c, blk, draw, colour, 4u + (uint32_t)(j >> 2));
+            orc_philox4x32_10(c, key, r2);
+            const uint32_t W = r[j & 3], W2 = r2[j & 3];
+            const uint32_t Ua = (W & 0xFFFF0000u) | (W2 >> 16);
+            const uint32_t Up = (W << 16) | (W2 & 0xFFFFu);
+            rnds[0 + 2 * (x0 + nx * y0)] = ((double)Up + 1.0) * 0x1p-32;
+            rnds[1 + 2 * (x0 + nx * y0)] = ((double)Ua + 1.0) * 0x1p-32;
+        }
+}
