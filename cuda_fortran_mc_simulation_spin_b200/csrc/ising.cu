@@ -39,6 +39,11 @@ struct Ising {
     // observables cache: valid until the configuration changes
     bool obs_valid;
     int64_t obs_e, obs_m;
+    // fused measurement: when the caller measures after every update (the drivers' loop), the second
+    // colour pass of the next sweep accumulates X and sum(s) itself and measure() only reads them back
+    bool fuse_ok;        // layout allows it (no site-less tail positions)
+    bool want_fused;     // the last sweep was followed by a measurement
+    bool fused_pending;  // d_acc holds the sums of the current configuration
     // optional per-launch timing of the pass kernel (CUDA events on the handle's stream)
     bool timing;
     std::vector<cudaEvent_t> evs;  // event pool: pair (2i, 2i+1) brackets the i-th timed launch
@@ -120,7 +125,7 @@ int build_tables(Ising* m)
 }
 
 template <int NNB>
-int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered)
+int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bool fuse)
 {
     const RingGeom& g = m->st.g;
     RingPassArgs a;
@@ -135,6 +140,7 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered)
     a.draw = m->draw;
     a.ticket = nullptr;
     a.chunk = m->chunk;
+    a.acc = m->d_acc;
     int64_t need = (n + 255) / 256;
     const int grid = (int)(need < (int64_t)m->grid ? need : (int64_t)m->grid);
     if (ordered && !(m->tune & 1) && n > (int64_t)m->grid * 256 * 4) {
@@ -142,20 +148,22 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered)
         CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
     }
     COUNT_LAUNCH();
+#define PASS(METHOD, ORD, MEAS) ising_pass_kernel<NNB, METHOD, ORD, false, MEAS><<<grid, 256, 0, m->stream>>>(a, m->tab)
     if (m->method == METHOD_METROPOLIS) {
-        if (a.ticket) ising_pass_kernel<NNB, METHOD_METROPOLIS, true><<<grid, 256, 0, m->stream>>>(a, m->tab);
-        else ising_pass_kernel<NNB, METHOD_METROPOLIS, false><<<grid, 256, 0, m->stream>>>(a, m->tab);
+        if (a.ticket) { if (fuse) PASS(METHOD_METROPOLIS, true, true); else PASS(METHOD_METROPOLIS, true, false); }
+        else { if (fuse) PASS(METHOD_METROPOLIS, false, true); else PASS(METHOD_METROPOLIS, false, false); }
     } else {
-        if (a.ticket) ising_pass_kernel<NNB, METHOD_HEATBATH, true><<<grid, 256, 0, m->stream>>>(a, m->tab);
-        else ising_pass_kernel<NNB, METHOD_HEATBATH, false><<<grid, 256, 0, m->stream>>>(a, m->tab);
+        if (a.ticket) { if (fuse) PASS(METHOD_HEATBATH, true, true); else PASS(METHOD_HEATBATH, true, false); }
+        else { if (fuse) PASS(METHOD_HEATBATH, false, true); else PASS(METHOD_HEATBATH, false, false); }
     }
+#undef PASS
     CK(cudaGetLastError());
     return B200MC_OK;
 }
 
 // slab mode with the direct transport: ONE launch per colour pass (update + halo push fused)
 template <int NNB>
-int launch_push(Ising* m, int colour)
+int launch_push(Ising* m, int colour, bool fuse)
 {
     RingStore& st = m->st;
     const RingGeom& g = st.g;
@@ -192,10 +200,16 @@ int launch_push(Ising* m, int colour)
     a.wait_next = st.flags + 16;
     a.wait_seq = st.push_seq;
     a.sig_seq = ++st.push_seq;
+    a.acc = m->d_acc;
     CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
     COUNT_LAUNCH();
-    if (m->method == METHOD_METROPOLIS) ising_pass_kernel<NNB, METHOD_METROPOLIS, true, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
-    else ising_pass_kernel<NNB, METHOD_HEATBATH, true, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+    if (m->method == METHOD_METROPOLIS) {
+        if (fuse) ising_pass_kernel<NNB, METHOD_METROPOLIS, true, true, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+        else ising_pass_kernel<NNB, METHOD_METROPOLIS, true, true, false><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+    } else {
+        if (fuse) ising_pass_kernel<NNB, METHOD_HEATBATH, true, true, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+        else ising_pass_kernel<NNB, METHOD_HEATBATH, true, true, false><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+    }
     CK(cudaGetLastError());
     return B200MC_OK;
 }
@@ -204,24 +218,26 @@ int launch_push(Ising* m, int colour)
 // Slab mode: the first and last H owned vectors (what the neighbouring ranks need) are updated first,
 // their exchange runs on the comm stream while the interior launch runs on the compute stream.
 template <int NNB>
-int launch_pass(Ising* m, int colour)
+int launch_pass(Ising* m, int colour, bool fuse)
 {
     const RingGeom& g = m->st.g;
     m->obs_valid = false;
+    m->fused_pending = false;
+    if (fuse) CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
     if (m->timing) {
         while (m->evs.size() < m->ev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); m->evs.push_back(e); }
         CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
     }
     int rc;
     if (g.nranks == 1) {
-        rc = launch_range<NNB>(m, colour, 0, g.Lloc, true);
+        rc = launch_range<NNB>(m, colour, 0, g.Lloc, true, fuse);
         if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
         if (rc) return rc;
         return ring_halo(&m->st, colour, m->stream);
     }
     const bool split = g.Lloc >= 4 * g.H && !(m->tune & 2);
     if (!split) {
-        rc = launch_range<NNB>(m, colour, 0, g.Lloc, true);
+        rc = launch_range<NNB>(m, colour, 0, g.Lloc, true, fuse);
         if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
         if (rc) return rc;
         return ring_halo(&m->st, colour, m->stream);
@@ -230,30 +246,34 @@ int launch_pass(Ising* m, int colour)
         // direct transport: one launch updates the whole slab, boundary chunks first, and stores their
         // results straight into the neighbours' halos over NVLink; the next pass waits (in the
         // kernel) for the neighbours' flags
-        rc = launch_push<NNB>(m, colour);
+        rc = launch_push<NNB>(m, colour, fuse);
         if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
         return rc;
     }
-    if ((rc = launch_range<NNB>(m, colour, 0, g.H, false))) return rc;
-    if ((rc = launch_range<NNB>(m, colour, g.Lloc - g.H, g.H, false))) return rc;
+    if ((rc = launch_range<NNB>(m, colour, 0, g.H, false, fuse))) return rc;
+    if ((rc = launch_range<NNB>(m, colour, g.Lloc - g.H, g.H, false, fuse))) return rc;
     CK(cudaEventRecord(m->ev_boundary, m->stream));
     CK(cudaStreamWaitEvent(m->comm_stream, m->ev_boundary, 0));
     if ((rc = ring_halo(&m->st, colour, m->comm_stream))) return rc;
     CK(cudaEventRecord(m->ev_halo, m->comm_stream));
-    rc = launch_range<NNB>(m, colour, g.H, g.Lloc - 2 * g.H, true);
+    rc = launch_range<NNB>(m, colour, g.H, g.Lloc - 2 * g.H, true, fuse);
     if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
     if (rc) return rc;
     CK(cudaStreamWaitEvent(m->stream, m->ev_halo, 0));
     return B200MC_OK;
 }
 
-int sweep(Ising* m)
+// One MCS.  allow_fuse: this is the last sweep before control returns to the caller.
+int sweep(Ising* m, bool allow_fuse = true)
 {
     int rc;
+    if (m->fused_pending) m->want_fused = false;  // the sums of the previous sweep were never asked for
+    const bool fuse = allow_fuse && m->want_fused && m->fuse_ok && !(m->tune & 8);
     for (int colour = 0; colour < 2; ++colour) {
-        rc = m->ndim == 3 ? launch_pass<6>(m, colour) : launch_pass<4>(m, colour);
+        rc = m->ndim == 3 ? launch_pass<6>(m, colour, fuse && colour == 1) : launch_pass<4>(m, colour, fuse && colour == 1);
         if (rc) return rc;
     }
+    m->fused_pending = fuse;
     m->draw += 1;
     return B200MC_OK;
 }
@@ -275,7 +295,7 @@ int launch_pass_randoms(Ising* m, int colour)
     a.ticket = nullptr;
     a.chunk = 128;
     const unsigned grid = (unsigned)((g.Lloc + 255) / 256);
-    m->obs_valid = false;
+    m->obs_valid = false; m->fused_pending = false;
     COUNT_LAUNCH();
     if (m->method == METHOD_METROPOLIS)
         ising_pass_randoms_kernel<NNB, METHOD_METROPOLIS><<<grid, 256, 0, m->stream>>>(a, m->tabf, m->d_randoms, g.L, g.Nc);
@@ -293,14 +313,18 @@ int measure(Ising* m, int64_t* e, int64_t* mag)
         if (mag) *mag = m->obs_m;
         return B200MC_OK;
     }
-    { int rcq = ring_p2p_quiesce(&m->st, m->stream); if (rcq) return rcq; }
-    COUNT_LAUNCH();
-    CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
-    if (m->ndim == 3)
-        ising_measure_kernel<6><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, m->d_acc);
-    else
-        ising_measure_kernel<4><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, m->d_acc);
-    CK(cudaGetLastError());
+    if (!m->fused_pending) {
+        { int rcq = ring_p2p_quiesce(&m->st, m->stream); if (rcq) return rcq; }
+        COUNT_LAUNCH();
+        CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
+        if (m->ndim == 3)
+            ising_measure_kernel<6><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, m->d_acc);
+        else
+            ising_measure_kernel<4><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, m->d_acc);
+        CK(cudaGetLastError());
+    }
+    m->fused_pending = false;  // the all-reduce below turns d_acc into global sums; they are cached in obs_*
+    m->want_fused = true;
     if (g.nranks > 1) {  // every rank gets the global sums (allreduce of {X, sum s})
         int rc = dist_allreduce_u64(m->st.comm, m->d_acc, 2, m->stream);
         if (rc) return rc;
@@ -339,6 +363,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
       t = getenv("B200MC_ILEAVE"); m->ileave = t ? atoi(t) : 1; if (m->ileave < 1 || m->ileave > 64) m->ileave = 1; }
     m->method = METHOD_METROPOLIS; m->seed = (uint32_t)iseed; m->draw = 0; m->alive = true;
     m->obs_valid = false; m->timing = false; m->ev_used = 0;
+    m->fuse_ok = false; m->want_fused = false; m->fused_pending = false;
     m->comm_stream = nullptr; m->ev_boundary = m->ev_halo = nullptr; m->st.comm = nullptr;
     int rc = ring_geom_init(&m->st.g, nx, ny, m->nz);
     if (rc) { delete m; return rc; }
@@ -375,6 +400,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     int64_t need = (m->st.g.Lloc + 255) / 256;
     m->grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);
     m->beta = 1 / kbt;
+    m->fuse_ok = m->st.g.ptail >= m->st.g.L && m->st.g.off[1][0] == 0;
     build_tables(m);
     rc = ring_fill(&m->st, 1, m->stream);  // set_allup_spin
     if (rc) { destroy(m); return rc; }
@@ -404,7 +430,7 @@ int destroy(Ising* m)
 int set_random(Ising* m)
 {
     const RingGeom& g = m->st.g;
-    m->obs_valid = false;
+    m->obs_valid = false; m->fused_pending = false;
     { int rcq = ring_p2p_quiesce(&m->st, m->stream); if (rcq) return rcq; }
     for (int c = 0; c < 2; ++c) {
         COUNT_LAUNCH();
@@ -487,19 +513,19 @@ int b200mc_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
     int PFX##_destroy(void* h) { if (!h) return B200MC_OK; CHECK_H(h, ND); return destroy(H(h)); } \
     int PFX##_set_stream(void* h, void* s) { CHECK_H(h, ND); H(h)->stream = (cudaStream_t)s; return B200MC_OK; } \
     int PFX##_skip_curand(void* h, int64_t n) { CHECK_H(h, ND); return skip(H(h), n); }           \
-    int PFX##_set_allup_spin(void* h) { CHECK_H(h, ND); H(h)->obs_valid = false; return ring_fill(&H(h)->st, 1, H(h)->stream); } \
+    int PFX##_set_allup_spin(void* h) { CHECK_H(h, ND); H(h)->obs_valid = false; H(h)->fused_pending = false; return ring_fill(&H(h)->st, 1, H(h)->stream); } \
     int PFX##_set_random_spin(void* h) { CHECK_H(h, ND); return set_random(H(h)); }               \
     int PFX##_set_beta(void* h, double beta) { CHECK_H(h, ND); if (!(beta >= 0.0)) ARG_FAIL("beta must be >= 0"); H(h)->beta = beta; return build_tables(H(h)); } \
     int PFX##_set_kbt(void* h, double kbt) { CHECK_H(h, ND); if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0"); H(h)->beta = 1 / kbt; return build_tables(H(h)); } \
     int PFX##_set_method(void* h, int32_t method) { CHECK_H(h, ND); if (method != METHOD_METROPOLIS && method != METHOD_HEATBATH) ARG_FAIL("unknown method %d", method); H(h)->method = method; return build_tables(H(h)); } \
     int PFX##_update(void* h) { CHECK_H(h, ND); return sweep(H(h)); }                             \
-    int PFX##_update_n(void* h, int32_t n) { CHECK_H(h, ND); for (int i = 0; i < n; ++i) { int rc = sweep(H(h)); if (rc) return rc; } return B200MC_OK; } \
+    int PFX##_update_n(void* h, int32_t n) { CHECK_H(h, ND); for (int i = 0; i < n; ++i) { int rc = sweep(H(h), i == n - 1); if (rc) return rc; } return B200MC_OK; } \
     int PFX##_update_with_randoms(void* h, const double* r) { CHECK_H(h, ND); return update_with_randoms(H(h), r); } \
     int PFX##_calc_energy_sum(void* h, int64_t* e) { CHECK_H(h, ND); return measure(H(h), e, nullptr); } \
     int PFX##_calc_magne_sum(void* h, int64_t* m) { CHECK_H(h, ND); return measure(H(h), nullptr, m); } \
     int PFX##_measure(void* h, int64_t* e, int64_t* m) { CHECK_H(h, ND); return measure(H(h), e, m); } \
     int PFX##_get_spins(void* h, int32_t* out) { CHECK_H(h, ND); if (!out) ARG_FAIL("null output"); return ring_export_i32(&H(h)->st, out, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream); } \
-    int PFX##_set_spins(void* h, const int32_t* in) { CHECK_H(h, ND); if (!in) ARG_FAIL("null input"); H(h)->obs_valid = false; return ring_import_i32(&H(h)->st, in, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream); } \
+    int PFX##_set_spins(void* h, const int32_t* in) { CHECK_H(h, ND); if (!in) ARG_FAIL("null input"); H(h)->obs_valid = false; H(h)->fused_pending = false; return ring_import_i32(&H(h)->st, in, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream); } \
     int64_t PFX##_nx(void* h) { return h ? H(h)->nx : -1; }                                       \
     int64_t PFX##_ny(void* h) { return h ? H(h)->ny : -1; }                                       \
     int64_t PFX##_nall(void* h) { return h ? H(h)->st.g.N : -1; }                                 \

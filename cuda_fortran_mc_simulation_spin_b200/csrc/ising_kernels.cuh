@@ -79,6 +79,8 @@ struct RingPassArgs {
     const unsigned int* wait_prev;  // my flags: pushes received so far from rank-1 / rank+1
     const unsigned int* wait_next;
     unsigned int wait_seq, sig_seq;
+    // MEASURE variant (second colour pass of a sweep): acc[0] += X, acc[1] += sum(s) as ising_measure_kernel
+    unsigned long long* acc;
 };
 
 __device__ __forceinline__ uint4 rot_lanes(uint4 s, int dir)
@@ -182,10 +184,13 @@ __device__ __forceinline__ uint32_t tie_bits(uint32_t z)
     return ((e >> 7) * 0x00204081u) >> 21 & 0xFu;  // gather bits 0,8,16,24 -> 0..3
 }
 
-template <int METHOD, bool PUSH>
-__device__ __noinline__ void ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4* own, const RingPassArgs& a,
+// Returns (dX, dM): what the ties accepted here add to this lane's running sums of the MEASURE
+// variant (the main loop counted them as rejected).  NNB = 0: not measuring.
+template <int METHOD, bool PUSH, int NNB>
+__device__ __noinline__ int2 ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4* own, const RingPassArgs& a,
                                          const IsingTab& tab)
 {
+    int2 delta = make_int2(0, 0);
     __syncwarp();
     const uint32_t n = lds32(cntaddr);
     const int lane = threadIdx.x & 31;
@@ -217,15 +222,23 @@ __device__ __noinline__ void ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4
                 const uint8_t nv = (METHOD == METHOD_METROPOLIS) ? (uint8_t)((nib >> 3) ^ 1u) : (uint8_t)1;
                 bytes[lb] = nv;
                 if (PUSH && rbytes) rbytes[(lb + rrot) & 15] = nv;
+                if (NNB) {
+                    // Metropolis: nib & 7 = k' aligned neighbours of the old spin; counted NNB - k' unequal, now k'.
+                    // Heat-bath: nib & 7 = S up neighbours; counted as down (S unequal), now up (NNB - S).
+                    const int t = (int)(nib & 7u);
+                    delta.x += (METHOD == METHOD_METROPOLIS) ? 2 * t - NNB : NNB - 2 * t;
+                    delta.y += (METHOD == METHOD_METROPOLIS) ? (nv ? 1 : -1) : 1;
+                }
             }
         }
     }
     __syncwarp();
     if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(cntaddr), "r"(0u) : "memory");
     __syncwarp();
+    return delta;
 }
 
-template <int NNB, int METHOD, bool ORDERED, bool PUSH = false>
+template <int NNB, int METHOD, bool ORDERED, bool PUSH = false, bool MEASURE = false>
 __global__ void __launch_bounds__(256)
 ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant__ IsingTab tab)
 {
@@ -266,6 +279,9 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
     unsigned int* tk = a.ticket + (gwarp % TK_NCNT) * 64;
     const int tk_base = (gwarp % TK_NCNT) * TK_CHUNK, tk_scale = TK_NCNT;
     const int vlimit = PUSH ? a.q_total * TK_CHUNK : nvec;  // PUSH: tickets count VIRTUAL chunks
+    uint32_t accX = 0, accM = 0;  // MEASURE: this lane's sums (< 2^31: at most ~10^5 sites per lane and launch)
+    int corrX = 0, corrM = 0;
+    constexpr int DN = MEASURE ? NNB : 0;
     int cur, nxt = 0;
     if (ORDERED) {
         if (lane == 0) nxt = (int)atomicAdd(tk, (unsigned)TK_CHUNK) * tk_scale + tk_base;
@@ -324,19 +340,36 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
                 ising_finish<METHOD>(o.x, o.y, oA0, oB0, zA0, zB0);
                 ising_finish<METHOD>(o.z, o.w, oA1, oB1, zA1, zB1);
                 st_own(own + v, o, pol);
+                if (MEASURE) {
+                    // fused E + M (ising_measure_kernel's sums) on the values this pass leaves behind:
+                    // unequal neighbours of a site = s ? NNB - S : S, bytewise (S ^ 7s) - (7 - NNB) s
+                    accX = __dp4a((S.x ^ (o.x * 7u)) - o.x * (uint32_t)(7 - NNB), 0x01010101u, accX);
+                    accX = __dp4a((S.y ^ (o.y * 7u)) - o.y * (uint32_t)(7 - NNB), 0x01010101u, accX);
+                    accX = __dp4a((S.z ^ (o.z * 7u)) - o.z * (uint32_t)(7 - NNB), 0x01010101u, accX);
+                    accX = __dp4a((S.w ^ (o.w * 7u)) - o.w * (uint32_t)(7 - NNB), 0x01010101u, accX);
+                    // sum(s): own vector + the other colour's vector at the same position (offset 0 = nb[0])
+                    accM = __dp4a(o.x + nb[0].x, 0x01010101u, accM);
+                    accM = __dp4a(o.y + nb[0].y, 0x01010101u, accM);
+                    accM = __dp4a(o.z + nb[0].z, 0x01010101u, accM);
+                    accM = __dp4a(o.w + nb[0].w, 0x01010101u, accM);
+                }
                 if (PUSH && is_b && !a.nopush) {  // second copy straight into the neighbour's halo (NVLink store)
                     if (v < a.nb) a.peer_lo[v] = rot_lanes(o, a.rot_lo);
                     else if (v >= a.hi_start) a.peer_hi[v - a.hi_start] = rot_lanes(o, a.rot_hi);
                 }
             }
             __syncwarp();
-            if (lds32(cntaddr) > TQ_CAP - 32) ising_drain<METHOD, PUSH>(qaddr, cntaddr, own, a, tab);
+            if (lds32(cntaddr) > TQ_CAP - 32) {
+                const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab);
+                corrX += d.x; corrM += d.y;
+            }
         }
         if (PUSH && is_b) {
             // this chunk's ties are resolved (remote copies patched too), its stores are performed
             // system-wide, and the warp that completes the LAST boundary chunk of the launch tells both
             // neighbours that their halo of this colour is complete
-            ising_drain<METHOD, PUSH>(qaddr, cntaddr, own, a, tab);
+            const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab);
+            corrX += d.x; corrM += d.y;
             __threadfence_system();
             __syncwarp();
             if (lane == 0 && atomicAdd(a.done, 1u) == (unsigned)a.nbchunks - 1u) {
@@ -349,7 +382,19 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
         if (ORDERED) cur = __shfl_sync(0xffffffffu, nxt, 0);
         else cur += nwarps_grid * TK_CHUNK;
     }
-    ising_drain<METHOD, PUSH>(qaddr, cntaddr, own, a, tab);
+    const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab);
+    if (MEASURE) {
+        long long x = (long long)accX + corrX + d.x, mm = (long long)accM + corrM + d.y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x += __shfl_down_sync(0xffffffffu, x, o);
+            mm += __shfl_down_sync(0xffffffffu, mm, o);
+        }
+        if (lane == 0) {
+            if (x) atomicAdd(a.acc, (unsigned long long)x);
+            if (mm) atomicAdd(a.acc + 1, (unsigned long long)mm);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -209,3 +209,31 @@ def test_full_size_properties_headline():
     e, m = g.measure()
     assert -3 * n < e < -n and 0.5 * n < m < n            # two sweeps from all-up at Tc
     assert (e + 3 * n) % 4 == 0                            # E = -3N + 2X, and X (anti-aligned bonds) is even: every flip toggles 6 bonds
+
+
+@pytest.mark.parametrize("dim,method", [(3, 0), (3, 1), (2, 0), (2, 1)])
+def test_fused_measurement_equals_separate_pass(oracle, dim, method):
+    """Once the caller measures after an update, the second colour pass of the following sweeps
+    accumulates X and sum(s) itself (deferred tie accepts included).  Shapes without site-less tail
+    positions (Nc % 16 == 0) take that path; the sums must equal the oracle's and a recount of the
+    same configuration by the separate kernel."""
+    i2, i3 = _mods()
+    if dim == 3:
+        g = i3.ising3d_gpu().init(63, 65, 64, KBT3, 5); o = oracle.ising3d_gpu().init(63, 65, 64, KBT3, 5)
+    else:
+        g = i2.ising2d_gpu().init(255, 256, KBT2, 5); o = oracle.ising2d_gpu().init(255, 256, KBT2, 5)
+    assert (g.nall() // 2) % 16 == 0
+    g.set_method(method)
+    step = o.update_heatbath if method else o.update
+    g.set_random_spin(); o.set_random_spin()
+    for sweep in range(8):
+        if sweep == 5:
+            g.update_n(3); step(); step(); step()      # only the last of n sweeps is fused
+        else:
+            g.update(); step()
+        em = g.measure()
+        assert em == (o.calc_energy_sum(), o.calc_magne_sum()), sweep
+        g.set_spins(g.spins())                         # invalidates: next measure recounts with the separate kernel
+        assert g.measure() == em
+    g.update(); g.update(); step(); step()             # first result never read: no stale sums afterwards
+    assert g.measure() == (o.calc_energy_sum(), o.calc_magne_sum())
