@@ -1,0 +1,20 @@
+"""CPU, world_size 2 over gloo: host-side logic of the N > 1 path (slab geometry, ownership, the spins()
+merge protocol, the partition of the all-reduced observable sums, rendezvous plumbing, loud failure
+without a device).  The GPU twin is tests/test_gpu_slab.py."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_slab_host_logic_two_gloo_ranks():
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    r = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+         "--master-port", "29547", os.path.join(ROOT, "tests", "_dist_cpu_worker.py")],
+        capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    sys.stdout.write(r.stdout[-3000:])
+    sys.stderr.write(r.stderr[-3000:])
+    assert r.returncode == 0
+    assert "dist cpu ok world=2" in r.stdout
