@@ -116,6 +116,38 @@ xy_metropolis_kernel(const __grid_constant__ XYArgs a)
     *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
 }
 
+// metropolis_by_field_sub, :198-216 (initial-state preparation): every site, no coupling.
+// candidate (cos 2 pi c, sin 2 pi c); dE = -(h . (cand - s)); accepted iff r <= 1 - exp(dE)
+// (the reference's test is `randoms > 1 - exp(delta_energy) -> return`, :213).
+// Uniforms: the Metropolis contract (same counters as xy_metropolis_kernel, both colours).
+__global__ void __launch_bounds__(256)
+xy_field_kernel(const __grid_constant__ XYArgs a, float hx, float hy)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.ny * a.gpr) return;
+    const int y = idx / a.gpr, g = idx - y * a.gpr;
+    float4* po = reinterpret_cast<float4*>(a.own + (size_t)y * a.nxh + 4 * g);
+    const float4 o = *po;
+    float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+        const uint4 R = philox_tag<TAG_XY>(mk_ctr((uint64_t)idx, a.draw, (uint32_t)a.colour, (uint32_t)sub), a.rk0);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int j = 2 * sub + e;
+            const uint32_t Ur = e ? R.z : R.x, Uc = e ? R.w : R.y;
+            const float r = ((float)Ur + 1.0f) * 0x1p-32f;
+            const float ct = ((float)Uc + 1.0f) * 0x1p-32f;
+            float cs, cc, ss, sc;
+            sincos_turns(ct, cs, cc);
+            sincos_turns(ov[j], ss, sc);
+            const float de = -(hx * (cc - sc) + hy * (cs - ss));
+            if (!(r > 1.0f - __expf(de))) ov[j] = ct;
+        }
+    }
+    *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
+}
+
 // over_relaxation_sub, :418-439: reflect the spin about the local field.  In angles:
 // theta' = 2 phi - theta with phi = atan2(h_y, h_x) (the reference's renormalisation is the identity here)
 __global__ void __launch_bounds__(256)
@@ -324,6 +356,21 @@ int over_relax(XY* m, int n_steps)
     return B200MC_OK;
 }
 
+int by_field(XY* m, double hx, double hy)
+{
+    m->obs_valid = false;
+    const int total = (int)m->ny * m->gpr;
+    for (int colour = 0; colour < 2; ++colour) {
+        XYArgs a;
+        fill_args(m, colour, &a);
+        COUNT_LAUNCH();
+        xy_field_kernel<<<(total + 255) / 256, 256, 0, m->stream>>>(a, (float)hx, (float)hy);
+        CK(cudaGetLastError());
+    }
+    m->draw += 1;
+    return B200MC_OK;
+}
+
 int measure(XY* m)
 {
     if (m->obs_valid) return B200MC_OK;
@@ -490,6 +537,43 @@ int b200mc_xy2d_rotate_summation_magne_toward_xaxis(void* h, int32_t with_autoco
     CK(cudaGetLastError());
     return B200MC_OK;
 }
+int b200mc_xy2d_metropolis_by_field(void* h, double hx, double hy) { CHECK_X(h); return by_field(HX(h), hx, hy); }
+
+namespace {
+enum { PREP_FINITE = 0, PREP_SMALL = 1, PREP_NEAR = 2 };
+// the three initial-state loops (:126-196): random start, then field sweeps until |m| meets the
+// criterion, then rotate the total magnetisation onto the x axis
+int prepare(XY* m, int kind, double target, double pct)
+{
+    int rc = b200mc_xy2d_set_random_spin(m);
+    if (rc) return rc;
+    double field_x = 1.0;
+    for (int it = 0;; ++it) {
+        if ((rc = measure(m))) return rc;
+        const double n = (double)(m->nx * m->ny);
+        const double mx = m->obs[1] / n, my = m->obs[2] / n, mabs = hypot(mx, my);
+        if (kind == PREP_FINITE) {
+            if (fabs(mabs - target) / target < 1e-2) break;   // epsilon, :130
+            if (mabs > target) field_x = -field_x / 2; else field_x = field_x * 2;
+        } else if (kind == PREP_SMALL) {
+            if (mabs < target) break;
+        } else {
+            if (fabs(mabs - target) / target <= pct) break;
+        }
+        if (it >= 100000) {   // the reference loops for ever when the criterion cannot be met
+            snprintf(g_b200mc_err, sizeof(g_b200mc_err), "xy2d: initial-state loop did not reach |m| = %g after %d field sweeps (last %g)", target, it, mabs);
+            return B200MC_ERR_STATE;
+        }
+        rc = kind == PREP_FINITE ? by_field(m, field_x, 0.0) : by_field(m, -mx, -my);
+        if (rc) return rc;
+    }
+    return b200mc_xy2d_rotate_summation_magne_toward_xaxis(m, 0);
+}
+}  // namespace
+int b200mc_xy2d_set_finite_magne_spin(void* h, double init_magne) { CHECK_X(h); if (!(init_magne > 0.0)) ARG_FAIL("init_magne must be > 0"); return prepare(HX(h), PREP_FINITE, init_magne, 0.0); }
+int b200mc_xy2d_set_random_small_spin(void* h, double near_magne) { CHECK_X(h); if (!(near_magne > 0.0)) ARG_FAIL("near_magne must be > 0"); return prepare(HX(h), PREP_SMALL, near_magne, 0.0); }
+int b200mc_xy2d_set_random_near_spin(void* h, double near_magne, double diff_parcent) { CHECK_X(h); if (!(near_magne > 0.0)) ARG_FAIL("near_magne must be > 0"); return prepare(HX(h), PREP_NEAR, near_magne, diff_parcent); }
+
 int b200mc_xy2d_get_spins(void* h, double* out)
 {
     CHECK_X(h);

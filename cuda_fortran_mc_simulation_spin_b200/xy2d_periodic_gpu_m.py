@@ -48,6 +48,10 @@ class xy2d_gpu:
     def skip_curand(self, n_skip): self._call("skip_curand", int(n_skip), argtypes=(i64,))
     def set_allup_spin(self): self._call("set_allup_spin")
     def set_random_spin(self): self._call("set_random_spin")
+    def set_random_small_spin(self, near_magne): self._call("set_random_small_spin", float(near_magne), argtypes=(f64,))  # :158-175
+    def set_random_near_spin(self, near_magne, diff_parcent): self._call("set_random_near_spin", float(near_magne), float(diff_parcent), argtypes=(f64, f64))  # :179-196
+    def set_finite_magne_spin(self, init_magne): self._call("set_finite_magne_spin", float(init_magne), argtypes=(f64,))  # :126-154
+    def metropolis_by_field(self, hx, hy): self._call("metropolis_by_field", float(hx), float(hy), argtypes=(f64, f64))  # one launch of :198-216
     def set_kbt(self, kbt): self._call("set_kbt", float(kbt), argtypes=(f64,))
     def set_beta(self, beta): self._call("set_beta", float(beta), argtypes=(f64,))
     def update(self): self._call("update")

@@ -267,6 +267,16 @@ int b200mc_xy2d_calc_correlation_sum(void* h, double* r);             /* :489-49
 /* rotate_summation_magne_toward_xaxis (:219-232); with_autocorrelation != 0 also rotates the
  * stored snapshot (rotate_summation_magne_and_autocorrelation_toward_xaxis, :235-250) */
 int b200mc_xy2d_rotate_summation_magne_toward_xaxis(void* h, int32_t with_autocorrelation);
+/* one application of metropolis_by_field_sub (:198-216) to every site: candidate accepted iff
+ * r <= 1 - exp(dE), dE = -(h . (cand - s)); draws one (randoms, candidates) pair of arrays */
+int b200mc_xy2d_metropolis_by_field(void* h, double hx, double hy);
+/* initial-state preparation (random start, field sweeps until |m| meets the criterion, rotate M onto
+ * the x axis): set_finite_magne_spin :126-154, set_random_small_spin :158-175, set_random_near_spin
+ * :179-196.  B200MC_ERR_STATE if the criterion is not met after 100000 field sweeps (the reference
+ * loops for ever). */
+int b200mc_xy2d_set_finite_magne_spin(void* h, double init_magne);
+int b200mc_xy2d_set_random_small_spin(void* h, double near_magne);
+int b200mc_xy2d_set_random_near_spin(void* h, double near_magne, double diff_parcent);
 /* spins(), :461-465: real64 (cos, sin), layout spins(0:nx+1, 0:ny+1, 1:2) -> 2 (nx+2)(ny+2) doubles;
  * the halo frame is returned refreshed, corners 0 */
 int b200mc_xy2d_get_spins(void* h, double* out);

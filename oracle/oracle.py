@@ -515,6 +515,12 @@ class xy2d_gpu:
         candidates = np.ascontiguousarray(candidates, dtype=np.float64)
         lib().orc_xy_update(self.nx_, self.ny_, _p(self.sp), self.beta_, _p(randoms), _p(candidates))
 
+    def metropolis_by_field(self, randoms, candidates, hx, hy):
+        """metropolis_by_field_sub, src/xy2d_periodic_gpu_m.f90:198-216 (no halo refresh, like the reference)"""
+        randoms = np.ascontiguousarray(randoms, dtype=np.float64)
+        candidates = np.ascontiguousarray(candidates, dtype=np.float64)
+        lib().orc_xy_metropolis_by_field(self.nx_, self.ny_, _p(self.sp), _p(randoms), _p(candidates), float(hx), float(hy))
+
     def update_over_relaxation(self, n_steps):
         lib().orc_xy_over_relaxation(self.nx_, self.ny_, _p(self.sp), int(n_steps))
 

@@ -130,3 +130,41 @@ def test_xy_full_size_properties():
     g.update_over_relaxation(1); e2 = g.calc_energy_sum()
     assert abs(e2 - e1) / n < 1e-5                   # over-relaxation conserves energy
     assert -2.0 * n < e1 < 0
+
+
+def test_xy_metropolis_by_field_per_application(oracle):
+    """metropolis_by_field_sub (src/xy2d_periodic_gpu_m.f90:198-216): accepted iff r <= 1 - exp(dE)"""
+    from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
+    nx, ny = 128, 64
+    n = nx * ny
+    g = xm.xy2d_gpu().init(nx, ny, 0.89, 13)
+    o = oracle.xy2d_gpu().init(nx, ny, 0.89, 13)
+    g.set_random_spin()
+    for it, (hx, hy) in enumerate([(1.0, 0.0), (-0.5, 0.25), (2.0, -1.0)]):
+        _sync_oracle(o, g)
+        r, c = oracle.xy_uniforms(13, 1 + it, nx, ny)
+        g.metropolis_by_field(hx, hy)
+        o.metropolis_by_field(r, c, hx, hy)
+        _, mx, my = g.measure()
+        assert _close(mx, o.calc_magne_sum(), n) and _close(my, o.calc_magne_y_sum(), n)
+        go = g.angles().astype(np.float64)
+        oo = np.arctan2(o.sp[1, 1:-1, 1:-1], o.sp[0, 1:-1, 1:-1]) / (2 * math.pi)
+        d = np.abs(((go - oo + 0.5) % 1.0) - 0.5)
+        assert (d > 1e-5).mean() < 1e-4
+
+
+def test_xy_initial_state_preparation():
+    """set_finite_magne_spin / set_random_small_spin / set_random_near_spin (:126-196): the documented
+    post-conditions -- |m| meets the criterion and M points along +x"""
+    from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
+    g = xm.xy2d_gpu().init(512, 512, 0.89, 21)
+    n = g.nall()
+    g.set_finite_magne_spin(0.3)
+    _, mx, my = g.measure()
+    assert abs(math.hypot(mx, my) / n - 0.3) / 0.3 < 1e-2 + 1e-4 and abs(my) < 1e-4 * n and mx > 0
+    g.set_random_small_spin(1e-3)
+    _, mx, my = g.measure()
+    assert math.hypot(mx, my) / n < 1e-3 + 1e-5 and abs(my) < 1e-4 * n
+    g.set_random_near_spin(0.01, 0.5)
+    _, mx, my = g.measure()
+    assert abs(math.hypot(mx, my) / n - 0.01) / 0.01 <= 0.5 + 1e-3
