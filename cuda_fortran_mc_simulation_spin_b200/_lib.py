@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_PKG, "libb200mc.so")
+SO_PATH = os.environ.get("B200MC_SO") or os.path.join(_PKG, "libb200mc.so")  # B200MC_SO: A/B-test another build of the same library
 CSRC = os.path.join(_PKG, "csrc")
 
 i64, i32, u32, f64, P = C.c_int64, C.c_int32, C.c_uint32, C.c_double, C.c_void_p

@@ -33,7 +33,7 @@ struct Ising {
     unsigned int* d_ticket;
     int tune;  // debug knobs from env B200MC_TUNE: bit0 = static round-robin (no ticket)
     int chunk; // vectors per ticket (env B200MC_CHUNK, default 128)
-    int ileave; // slab mode: one high-boundary chunk in every `ileave` tickets at the start of a pass (env B200MC_ILEAVE)
+    int ileave; // slab mode: one high-boundary chunk in every 2^ileave tickets at the start of a pass (env B200MC_ILEAVE, log2)
     int grid;
     bool alive;
     // observables cache: valid until the configuration changes
@@ -141,6 +141,7 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bo
     a.ticket = nullptr;
     a.chunk = m->chunk;
     a.acc = m->d_acc;
+    a.nopush = (m->tune & 32) ? 2 : 0;  // debug bit 5: no L2 prefetch
     int64_t need = (n + 255) / 256;
     const int grid = (int)(need < (int64_t)m->grid ? need : (int64_t)m->grid);
     if (ordered && !(m->tune & 1) && n > (int64_t)m->grid * 256 * 4) {
@@ -190,9 +191,12 @@ int launch_push(Ising* m, int colour, bool fuse)
     a.jhi = (int)((g.Lloc - g.H) / a.chunk);
     a.nbchunks = a.blo + (int)(nchunks - a.jhi);
     const int64_t nbhi = nchunks - a.jhi;
-    a.ileave = m->ileave;
-    a.nopush = (m->tune & 4) ? 1 : 0;  // debug: skip the NVLink stores (wrong results, timing only)
-    a.q_total = (int)(a.ileave * nbhi > nchunks ? a.ileave * nbhi : nchunks);
+    a.ileave = m->ileave;              // log2: one high-boundary chunk in every 2^ileave tickets at the start of the pass
+    a.chunk_shift = 0;
+    while ((1 << a.chunk_shift) < a.chunk) ++a.chunk_shift;
+    a.nopush = ((m->tune & 4) ? 1 : 0) | ((m->tune & 32) ? 2 : 0);  // debug: bit 0 skip the NVLink stores (wrong results, timing only), bit 1 no L2 prefetch
+    a.q_total = (int)((nbhi << a.ileave) > nchunks ? (nbhi << a.ileave) : nchunks);
+    a.dbg_wait = reinterpret_cast<unsigned long long*>(st.flags + 48);
     a.done = st.flags + 32;
     a.sig_prev = st.peer_flags[0] + 16;  // I am rank-1's "next"
     a.sig_next = st.peer_flags[1] + 0;   // and rank+1's "prev"
@@ -229,13 +233,14 @@ int launch_pass(Ising* m, int colour, bool fuse)
         CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
     }
     int rc;
-    if (g.nranks == 1) {
+    if (g.nranks == 1 && !m->st.p2p) {
         rc = launch_range<NNB>(m, colour, 0, g.Lloc, true, fuse);
         if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
         if (rc) return rc;
         return ring_halo(&m->st, colour, m->stream);
     }
     const bool split = g.Lloc >= 4 * g.H && !(m->tune & 2);
+    if (!split && g.nranks == 1) m->st.p2p = false;
     if (!split) {
         rc = launch_range<NNB>(m, colour, 0, g.Lloc, true, fuse);
         if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
@@ -359,8 +364,8 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     if (!m) ARG_FAIL("out of host memory");
     m->ndim = ndim; m->nx = nx; m->ny = ny; m->nz = ndim == 3 ? nz : 0;
     m->stream = 0; m->d_acc = nullptr; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
-    { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; t = getenv("B200MC_CHUNK"); m->chunk = t ? atoi(t) : 128; if (m->chunk < 32 || (m->chunk & 31)) m->chunk = 128;
-      t = getenv("B200MC_ILEAVE"); m->ileave = t ? atoi(t) : 1; if (m->ileave < 1 || m->ileave > 64) m->ileave = 1; }
+    { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; t = getenv("B200MC_CHUNK"); m->chunk = t ? atoi(t) : 128; m->chunk = TK_CHUNK;  /* compile-time now */
+      t = getenv("B200MC_ILEAVE"); m->ileave = t ? atoi(t) : 0; if (m->ileave < 0 || m->ileave > 6) m->ileave = 0; }
     m->method = METHOD_METROPOLIS; m->seed = (uint32_t)iseed; m->draw = 0; m->alive = true;
     m->obs_valid = false; m->timing = false; m->ev_used = 0;
     m->fuse_ok = false; m->want_fused = false; m->fused_pending = false;
@@ -404,6 +409,11 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     build_tables(m);
     rc = ring_fill(&m->st, 1, m->stream);  // set_allup_spin
     if (rc) { destroy(m); return rc; }
+    if (nranks == 1 && (m->tune & 16) && m->st.g.Nc % 16 == 0 && m->st.g.Lloc >= 4 * m->st.g.H) {
+        // experiment (B200MC_TUNE bit 4): one GPU runs the fused update + halo kernel against its own arrays
+        rc = ring_p2p_connect_self(&m->st);
+        if (rc) { destroy(m); return rc; }
+    }
     *out = m;
     return B200MC_OK;
 }
@@ -576,6 +586,15 @@ int b200mc_ising2d_p2p_connect(void* h, const char prev[192], const char next[19
 int b200mc_ising3d_rank_info(void* h, int32_t* rank, int32_t* nranks) { CHECK_H(h, 3); *rank = H(h)->st.g.rank; *nranks = H(h)->st.g.nranks; return B200MC_OK; }
 int b200mc_ising2d_rank_info(void* h, int32_t* rank, int32_t* nranks) { CHECK_H(h, 2); *rank = H(h)->st.g.rank; *nranks = H(h)->st.g.nranks; return B200MC_OK; }
 int64_t b200mc_ising3d_nz(void* h) { return h ? H(h)->nz : -1; }
+// debug: ns block 0 of the fused colour-pass kernels has spent waiting for the neighbours' flags so far
+unsigned long long b200mc_debug_slab_wait_ns(void* h)
+{
+    if (!h || !H(h)->st.flags) return 0;
+    unsigned long long v = 0;
+    cudaStreamSynchronize(H(h)->stream);
+    cudaMemcpy(&v, H(h)->st.flags + 48, sizeof(v), cudaMemcpyDeviceToHost);
+    return v;
+}
 int b200mc_ising3d_get_ws(void* h, double out[14])
 {
     CHECK_H(h, 3);

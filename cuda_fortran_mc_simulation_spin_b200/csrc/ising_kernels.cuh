@@ -72,7 +72,8 @@ struct RingPassArgs {
     int rot_lo, rot_hi;    // lane rotation of the pushed copy: +1 lane b <- b-1, -1 lane b <- b+1, 0 none
     int nb;                // H
     int hi_start;          // Lloc - H
-    int blo, jhi, nbchunks, q_total, ileave, nopush;
+    int blo, jhi, nbchunks, q_total, ileave /* log2 */, nopush, chunk_shift;
+    unsigned long long* dbg_wait;  // debug: ns block 0 spent waiting for the neighbours' flags (summed over launches)
     unsigned int* done;    // completed boundary chunks of this launch (local)
     unsigned int* sig_prev;       // rank-1's "from next" flag, rank+1's "from prev" flag (peer memory)
     unsigned int* sig_next;
@@ -114,7 +115,7 @@ enum { METHOD_METROPOLIS = 0, METHOD_HEATBATH = 1 };
 // treats it as "reject", pushes a 32-byte record into a per-warp shared-memory
 // queue and goes on; when the queue is half full (and at kernel end) the warp
 // drains it with all 32 lanes busy and patches the accepted bytes in global memory.
-#define TQ_CAP 64
+#define TQ_CAP 96   // records per warp: drained when more than TQ_CAP - 64 are parked, checked every second vector
 #define TK_NCNT 8
 
 // keep a value in a register: stops the compiler from rematerialising address
@@ -238,8 +239,63 @@ __device__ __noinline__ int2 ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4
     return delta;
 }
 
+// One vector (16 sites of the colour being updated) of one lane: loads, Philox block, byte-parallel
+// accept test, store; ties parked in the warp's queue; optional halo push and fused E/M sums.
+template <int NNB, int METHOD, bool PUSH, bool MEASURE>
+__device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (&q)[NNB], uint32_t cx, uint32_t cz, uint32_t cw,
+                                          const RingPassArgs& a, const IsingTab& tab, uint64_t pol, uint32_t qaddr,
+                                          uint32_t cntaddr, bool is_b, uint32_t& accX, uint32_t& accM)
+{
+    uint4 o = ld_own(po, pol);
+    uint4 nb[NNB];
+#pragma unroll
+    for (int j = 0; j < NNB; ++j) nb[j] = ld_other(q[j]);
+    // counter (p0 + v, 0, draw_lo, draw_hi | colour << 16 | sub << 24): positions are < 2^31
+    const uint4 r = philox_rk<TAG_ISING>(make_uint4(cx, 0u, cz, cw), tab.rk0);
+    uint4 S = make_uint4(nb[0].x + nb[1].x, nb[0].y + nb[1].y, nb[0].z + nb[1].z, nb[0].w + nb[1].w);
+#pragma unroll
+    for (int j = 2; j < NNB; ++j) { S.x += nb[j].x; S.y += nb[j].y; S.z += nb[j].z; S.w += nb[j].w; }
+    uint32_t ix0, ix1, oA0, oB0, oA1, oB1, zA0, zB0, zA1, zB1;
+    ising_stage1<NNB, METHOD>(o.x, o.y, S.x, S.y, r.x, r.y, tab, ix0, oA0, oB0, zA0, zB0);
+    ising_stage1<NNB, METHOD>(o.z, o.w, S.z, S.w, r.z, r.w, tab, ix1, oA1, oB1, zA1, zB1);
+    const uint32_t tie = (tie_flags(zA0) | tie_flags(zB0) | tie_flags(zA1) | tie_flags(zB1)) & 0x80808080u;
+    if (tie) {  // rare per lane: park the record, resolve later (ties count as reject below)
+        uint32_t slot;
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(cntaddr) : "memory");
+        const uint32_t ra = qaddr + slot * 32;
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "r"((uint32_t)v), "r"(zA0), "r"(zB0), "r"(zA1) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ra + 16), "r"(zB1), "r"(ix0), "r"(ix1), "r"(0u) : "memory");
+    }
+    ising_finish<METHOD>(o.x, o.y, oA0, oB0, zA0, zB0);
+    ising_finish<METHOD>(o.z, o.w, oA1, oB1, zA1, zB1);
+    st_own(po, o, pol);
+    if (MEASURE) {
+        // fused E + M (ising_measure_kernel's sums) on the values this pass leaves behind:
+        // unequal neighbours of a site = s ? NNB - S : S, bytewise (S ^ 7s) - (7 - NNB) s
+        accX = __dp4a((S.x ^ (o.x * 7u)) - o.x * (uint32_t)(7 - NNB), 0x01010101u, accX);
+        accX = __dp4a((S.y ^ (o.y * 7u)) - o.y * (uint32_t)(7 - NNB), 0x01010101u, accX);
+        accX = __dp4a((S.z ^ (o.z * 7u)) - o.z * (uint32_t)(7 - NNB), 0x01010101u, accX);
+        accX = __dp4a((S.w ^ (o.w * 7u)) - o.w * (uint32_t)(7 - NNB), 0x01010101u, accX);
+        // sum(s): own vector + the other colour's vector at the same position (offset 0 = nb[0])
+        accM = __dp4a(o.x + nb[0].x, 0x01010101u, accM);
+        accM = __dp4a(o.y + nb[0].y, 0x01010101u, accM);
+        accM = __dp4a(o.z + nb[0].z, 0x01010101u, accM);
+        accM = __dp4a(o.w + nb[0].w, 0x01010101u, accM);
+    }
+    if (PUSH && is_b && !(a.nopush & 1)) {  // second copy straight into the neighbour's halo (NVLink store)
+        if (v < a.nb) a.peer_lo[v] = rot_lanes(o, a.rot_lo);
+        else if (v >= a.hi_start) a.peer_hi[v - a.hi_start] = rot_lanes(o, a.rot_hi);
+    }
+}
+
+#define TK_CHUNK 128  // vectors per ticket: 4 warp-iterations, unrolled so that the 8 stream addresses are
+                      // computed once per ticket and reached with immediate offsets (+512 B per iteration)
+
+#ifndef PASS_MINB
+#define PASS_MINB 4
+#endif
 template <int NNB, int METHOD, bool ORDERED, bool PUSH = false, bool MEASURE = false>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PASS_MINB)
 ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant__ IsingTab tab)
 {
     static_assert(!PUSH || ORDERED, "the fused update + halo push kernel uses ticket scheduling");
@@ -255,23 +311,26 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
     if (PUSH) {
         // the halo cells this pass reads were pushed by the neighbours during their previous pass
         if (threadIdx.x == 0) {
+            unsigned long long t0 = 0, t1 = 0;
+            if (blockIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
             while ((int)(ld_acquire_sys(a.wait_prev) - a.wait_seq) < 0) __nanosleep(100);
             while ((int)(ld_acquire_sys(a.wait_next) - a.wait_seq) < 0) __nanosleep(100);
+            if (blockIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); atomicAdd(a.dbg_wait, t1 - t0); }
         }
         __syncthreads();
     }
     const uint64_t pol = l2_policy_evict_first();
     uint4* own = a.own + a.H;
-    pin64(own);
     const int nvec = (int)a.nvec;
     const uint4* pn[NNB];
 #pragma unroll
-    for (int j = 0; j < NNB; ++j) { pn[j] = a.oth + (a.H + a.off[j]); pin64(pn[j]); }
+    for (int j = 0; j < NNB; ++j) pn[j] = a.oth + (a.H + a.off[j]);
+    const uint32_t cx0 = (uint32_t)a.p0, cz = (uint32_t)a.draw;
+    const uint32_t cw = (uint32_t)((a.draw >> 32) & 0xFFFFu) | (a.colour << 16);
     // ordered mode: every warp takes TK_CHUNK-vector chunks from a global counter, so that all
     // resident warps work inside one narrow, advancing window of the lattice (the z-neighbour
     // planes then stay in L2 between their three uses).  The next ticket is fetched one chunk
     // ahead; no block-level synchronisation anywhere in the loop.
-    const int TK_CHUNK = a.chunk;
     const int nwarps_grid = gridDim.x * (blockDim.x >> 5);
     // TK_NCNT interleaved counters (256 B apart -> different L2 slices): counter c hands out the
     // chunks c, c + NCNT, c + 2 NCNT, ...; one same-address atomic stream would cap the ticket rate
@@ -282,86 +341,94 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
     uint32_t accX = 0, accM = 0;  // MEASURE: this lane's sums (< 2^31: at most ~10^5 sites per lane and launch)
     int corrX = 0, corrM = 0;
     constexpr int DN = MEASURE ? NNB : 0;
-    int cur, nxt = 0;
+    // ticket -> first vector of the chunk (-1: a virtual chunk of the PUSH schedule that maps to nothing)
+    auto chunk_base = [&](int t, bool& boundary) -> int {
+        boundary = false;
+        if (!PUSH) return t;
+        // Slab mode.  The chunks holding the LAST H owned vectors (the low halo of rank+1) are handed
+        // out first, one in every 2^ileave tickets; all other chunks follow in natural order, which
+        // starts with the first H owned vectors (the high halo of rank-1).  Both halo blocks are thus
+        // on their way over NVLink early in the pass and land while the interior is being updated.
+        const int q = t / TK_CHUNK;
+        const int nbhi = a.nbchunks - a.blo;
+        int j;
+        if (q < (nbhi << a.ileave)) {
+            const int k = q >> a.ileave;
+            if ((q & ((1 << a.ileave) - 1)) == 0) j = a.jhi + k;
+            else { j = q - k - 1; if (j >= a.jhi) j = -1; }
+        } else {
+            j = q - nbhi;
+            if (j >= a.jhi) j = -1;
+        }
+        boundary = j >= 0 && (j < a.blo || j >= a.jhi);
+        return j < 0 ? -1 : j * TK_CHUNK;
+    };
+    // The two streams of a chunk that come from DRAM (the own colour, read once per pass, and the leading
+    // z / y neighbour plane, touched for the first time) are prefetched into L2 one ticket ahead: lanes
+    // 0-15 fetch the 16 lines of the own chunk, lanes 16-31 those of the leading neighbour chunk.
+    const char* pf_base = (lane < 16) ? reinterpret_cast<const char*>(own) : reinterpret_cast<const char*>(pn[NNB - 2]);
+    pf_base += (lane & 15) * 128;
+    int cur, nxt = 0, nx2 = 0;
     if (ORDERED) {
-        if (lane == 0) nxt = (int)atomicAdd(tk, (unsigned)TK_CHUNK) * tk_scale + tk_base;
+        if (lane == 0) {
+            nxt = (int)atomicAdd(tk, (unsigned)TK_CHUNK) * tk_scale + tk_base;
+            nx2 = (int)atomicAdd(tk, (unsigned)TK_CHUNK) * tk_scale + tk_base;
+        }
         cur = __shfl_sync(0xffffffffu, nxt, 0);
+        nxt = __shfl_sync(0xffffffffu, nx2, 0);
     } else {
         cur = gwarp * TK_CHUNK;
+        nxt = cur + nwarps_grid * TK_CHUNK;
     }
     while (cur < vlimit) {
-        if (ORDERED && lane == 0) nxt = (int)atomicAdd(tk, (unsigned)TK_CHUNK) * tk_scale + tk_base;  // prefetch
-        int base = cur;
-        bool is_b = false;
-        if (PUSH) {
-            // Slab mode.  The chunks holding the LAST H owned vectors (the low halo of rank+1) are handed
-            // out first, one in every `ileave` tickets; all other chunks follow in natural order, which
-            // starts with the first H owned vectors (the high halo of rank-1).  Both halo blocks are thus
-            // on their way over NVLink early in the pass and land while the interior is being updated.
-            const int q = cur / TK_CHUNK;
-            const int nbhi = a.nbchunks - a.blo;
-            int j;
-            if (q < a.ileave * nbhi) {
-                const int k = q / a.ileave;
-                if (q - k * a.ileave == 0) j = a.jhi + k;
-                else { j = q - k - 1; if (j >= a.jhi) j = -1; }
-            } else {
-                j = q - nbhi;
-                if (j >= a.jhi) j = -1;
-            }
-            is_b = j >= 0 && (j < a.blo || j >= a.jhi);
-            base = j * TK_CHUNK;
-            if (j < 0) { cur = __shfl_sync(0xffffffffu, nxt, 0); continue; }
+        if (ORDERED && lane == 0) nx2 = (int)atomicAdd(tk, (unsigned)TK_CHUNK) * tk_scale + tk_base;  // two tickets ahead
+        if (nxt < vlimit) {
+            bool bn;
+            const int bnext = chunk_base(nxt, bn);
+            if (bnext >= 0 && bnext + TK_CHUNK <= nvec && !(a.nopush & 2))
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + (size_t)bnext * 16));
         }
-#pragma unroll 1
-        for (int sub = 0; sub < TK_CHUNK; sub += 32) {
-            const int v = base + sub + lane;
-            if (v < nvec) {
-                uint4 o = ld_own(own + v, pol);
-                uint4 nb[NNB];
+        bool is_b;
+        const int base = chunk_base(cur, is_b);
+        if (PUSH && base < 0) { cur = nxt; nxt = __shfl_sync(0xffffffffu, nx2, 0); continue; }
+        const int v0 = base + lane;
+        uint4* po = own + v0;
+        const uint4* q[NNB];
 #pragma unroll
-                for (int j = 0; j < NNB; ++j) nb[j] = ld_other(pn[j] + v);
-                const uint64_t pglob = (uint64_t)(a.p0 + v);
-                const uint4 r = philox_rk<TAG_ISING>(mk_ctr(pglob, a.draw, a.colour, 0u), tab.rk0);
-                uint4 S = make_uint4(nb[0].x + nb[1].x, nb[0].y + nb[1].y, nb[0].z + nb[1].z, nb[0].w + nb[1].w);
+        for (int j = 0; j < NNB; ++j) q[j] = pn[j] + v0;
+        const uint32_t cx = cx0 + (uint32_t)v0;
+        if (base + TK_CHUNK <= nvec) {
+            // full chunk: no bounds checks, the queue is looked at every second vector
 #pragma unroll
-                for (int j = 2; j < NNB; ++j) { S.x += nb[j].x; S.y += nb[j].y; S.z += nb[j].z; S.w += nb[j].w; }
-                uint32_t ix0, ix1, oA0, oB0, oA1, oB1, zA0, zB0, zA1, zB1;
-                ising_stage1<NNB, METHOD>(o.x, o.y, S.x, S.y, r.x, r.y, tab, ix0, oA0, oB0, zA0, zB0);
-                ising_stage1<NNB, METHOD>(o.z, o.w, S.z, S.w, r.z, r.w, tab, ix1, oA1, oB1, zA1, zB1);
-                const uint32_t tie = (tie_flags(zA0) | tie_flags(zB0) | tie_flags(zA1) | tie_flags(zB1)) & 0x80808080u;
-                if (tie) {  // rare per lane: park the record, resolve later (ties count as reject below)
-                    uint32_t slot;
-                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(cntaddr) : "memory");
-                    const uint32_t ra = qaddr + slot * 32;
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "r"((uint32_t)v), "r"(zA0), "r"(zB0), "r"(zA1) : "memory");
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ra + 16), "r"(zB1), "r"(ix0), "r"(ix1), "r"(0u) : "memory");
-                }
-                ising_finish<METHOD>(o.x, o.y, oA0, oB0, zA0, zB0);
-                ising_finish<METHOD>(o.z, o.w, oA1, oB1, zA1, zB1);
-                st_own(own + v, o, pol);
-                if (MEASURE) {
-                    // fused E + M (ising_measure_kernel's sums) on the values this pass leaves behind:
-                    // unequal neighbours of a site = s ? NNB - S : S, bytewise (S ^ 7s) - (7 - NNB) s
-                    accX = __dp4a((S.x ^ (o.x * 7u)) - o.x * (uint32_t)(7 - NNB), 0x01010101u, accX);
-                    accX = __dp4a((S.y ^ (o.y * 7u)) - o.y * (uint32_t)(7 - NNB), 0x01010101u, accX);
-                    accX = __dp4a((S.z ^ (o.z * 7u)) - o.z * (uint32_t)(7 - NNB), 0x01010101u, accX);
-                    accX = __dp4a((S.w ^ (o.w * 7u)) - o.w * (uint32_t)(7 - NNB), 0x01010101u, accX);
-                    // sum(s): own vector + the other colour's vector at the same position (offset 0 = nb[0])
-                    accM = __dp4a(o.x + nb[0].x, 0x01010101u, accM);
-                    accM = __dp4a(o.y + nb[0].y, 0x01010101u, accM);
-                    accM = __dp4a(o.z + nb[0].z, 0x01010101u, accM);
-                    accM = __dp4a(o.w + nb[0].w, 0x01010101u, accM);
-                }
-                if (PUSH && is_b && !a.nopush) {  // second copy straight into the neighbour's halo (NVLink store)
-                    if (v < a.nb) a.peer_lo[v] = rot_lanes(o, a.rot_lo);
-                    else if (v >= a.hi_start) a.peer_hi[v - a.hi_start] = rot_lanes(o, a.rot_hi);
+            for (int u = 0; u < TK_CHUNK / 32; ++u) {
+                const uint4* qu[NNB];
+#pragma unroll
+                for (int j = 0; j < NNB; ++j) qu[j] = q[j] + 32 * u;
+                ising_vec<NNB, METHOD, PUSH, MEASURE>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr, cntaddr,
+                                                      is_b, accX, accM);
+                if (u & 1) {
+                    __syncwarp();
+                    if (lds32(cntaddr) > TQ_CAP - 64) {
+                        const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab);
+                        corrX += d.x; corrM += d.y;
+                    }
                 }
             }
-            __syncwarp();
-            if (lds32(cntaddr) > TQ_CAP - 32) {
-                const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab);
-                corrX += d.x; corrM += d.y;
+        } else {
+#pragma unroll 1
+            for (int u = 0; u < TK_CHUNK / 32; ++u) {
+                if (v0 + 32 * u < nvec) {
+                    const uint4* qu[NNB];
+#pragma unroll
+                    for (int j = 0; j < NNB; ++j) qu[j] = q[j] + 32 * u;
+                    ising_vec<NNB, METHOD, PUSH, MEASURE>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
+                                                          cntaddr, is_b, accX, accM);
+                }
+                __syncwarp();
+                if (lds32(cntaddr) > TQ_CAP - 64) {
+                    const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab);
+                    corrX += d.x; corrM += d.y;
+                }
             }
         }
         if (PUSH && is_b) {
@@ -379,8 +446,9 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
                 st_release_sys(a.sig_next, a.sig_seq);
             }
         }
-        if (ORDERED) cur = __shfl_sync(0xffffffffu, nxt, 0);
-        else cur += nwarps_grid * TK_CHUNK;
+        cur = nxt;
+        if (ORDERED) nxt = __shfl_sync(0xffffffffu, nx2, 0);
+        else nxt += nwarps_grid * TK_CHUNK;
     }
     const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab);
     if (MEASURE) {

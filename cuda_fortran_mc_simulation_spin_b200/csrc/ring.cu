@@ -324,6 +324,27 @@ int ring_p2p_connect(RingStore* s, const char prev[RING_IPC_BYTES], const char n
     return B200MC_OK;
 }
 
+// single GPU: the ring closes on itself, so the "neighbours" are this rank's own arrays -- the fused
+// update + halo kernel then replaces the separate halo-refresh launch
+int ring_p2p_connect_self(RingStore* s)
+{
+    const RingGeom& g = s->g;
+    if (g.nranks != 1) ARG_FAIL("connect_self: slab handle");
+    if (g.Nc % 16) ARG_FAIL("connect_self: sites per colour must be a multiple of 16");
+    if (!s->flags) {
+        CK(cudaMalloc(&s->flags, 64 * sizeof(unsigned int)));
+        CK(cudaMemset(s->flags, 0, 64 * sizeof(unsigned int)));
+    }
+    for (int side = 0; side < 2; ++side) {
+        s->peer_vec[side][0] = s->vec[0];
+        s->peer_vec[side][1] = s->vec[1];
+        s->peer_flags[side] = s->flags;
+    }
+    s->Lloc_prev = g.Lloc;
+    s->p2p = true;
+    return B200MC_OK;
+}
+
 void ring_p2p_close(RingStore* s)
 {
     for (int i = 0; i < s->n_peer_maps; ++i) cudaIpcCloseMemHandle(s->peer_maps[i]);

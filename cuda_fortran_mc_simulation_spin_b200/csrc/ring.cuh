@@ -72,6 +72,7 @@ int ring_export_i32(RingStore* s, int32_t* host, RingValueMap map, cudaStream_t 
 // direct transport set-up: export my handles, map the two neighbours' (prev == next when nranks == 2)
 int ring_p2p_export(RingStore* s, char out[RING_IPC_BYTES]);
 int ring_p2p_connect(RingStore* s, const char prev[RING_IPC_BYTES], const char next[RING_IPC_BYTES]);
+int ring_p2p_connect_self(RingStore* s);
 void ring_p2p_close(RingStore* s);
 // stream-ordered wait until every push issued so far by both neighbours has landed
 int ring_p2p_quiesce(RingStore* s, cudaStream_t st);

@@ -560,7 +560,7 @@ int prepare(XY* m, int kind, double target, double pct)
         } else {
             if (fabs(mabs - target) / target <= pct) break;
         }
-        if (it >= 100000) {   // the reference loops for ever when the criterion cannot be met
+        if (it >= 4096) {   // the reference loops for ever when its heuristic cycles (it does for most targets of set_finite_magne_spin)
             snprintf(g_b200mc_err, sizeof(g_b200mc_err), "xy2d: initial-state loop did not reach |m| = %g after %d field sweeps (last %g)", target, it, mabs);
             return B200MC_ERR_STATE;
         }

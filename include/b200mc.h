@@ -44,6 +44,7 @@ int b200mc_version(void);
 /* number of CUDA kernels this library has launched so far in this process (all handles) */
 unsigned long long b200mc_launch_count(void);
 /* run the handle's kernels on a caller-provided CUDA stream (cudaStream_t as void*) */
+unsigned long long b200mc_debug_slab_wait_ns(void* h); /* slab mode: ns spent waiting for neighbour flags (block 0) */
 int b200mc_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]); /* device Philox, for KAT tests */
 
 /* ------------------------------------------------------------------------
@@ -272,8 +273,9 @@ int b200mc_xy2d_rotate_summation_magne_toward_xaxis(void* h, int32_t with_autoco
 int b200mc_xy2d_metropolis_by_field(void* h, double hx, double hy);
 /* initial-state preparation (random start, field sweeps until |m| meets the criterion, rotate M onto
  * the x axis): set_finite_magne_spin :126-154, set_random_small_spin :158-175, set_random_near_spin
- * :179-196.  B200MC_ERR_STATE if the criterion is not met after 100000 field sweeps (the reference
- * loops for ever). */
+ * :179-196.  B200MC_ERR_STATE if the criterion is not met after 4096 field sweeps: the reference
+ * loops for ever then, and its set_finite_magne_spin heuristic (field doubled / halved-and-reversed)
+ * does cycle for most targets. */
 int b200mc_xy2d_set_finite_magne_spin(void* h, double init_magne);
 int b200mc_xy2d_set_random_small_spin(void* h, double near_magne);
 int b200mc_xy2d_set_random_near_spin(void* h, double near_magne, double diff_parcent);

@@ -44,3 +44,21 @@ def test_product_does_not_import_oracle():
                 assert "oracle" not in txt.replace("oracle/", "ORACLE_PATH_MENTION").replace("the oracle", "").lower() or \
                     "import oracle" not in txt and "from oracle" not in txt, f
                 assert "from oracle" not in txt and "import oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_fortran_shims_bind_only_exported_symbols():
+    """every bind(C, name="...") in the ISO_C_BINDING shim modules is declared in include/b200mc.h and exported"""
+    from cuda_fortran_mc_simulation_spin_b200 import _lib
+    lib = C.CDLL(_lib.SO_PATH)
+    declared = set(_declared())
+    fdir = os.path.join(ROOT, "cuda_fortran_mc_simulation_spin_b200", "fortran")
+    seen = 0
+    for dp, _, fs in os.walk(fdir):
+        for f in fs:
+            if not f.endswith(".f90"):
+                continue
+            for name in re.findall(r'bind\(C,\s*name="(b200mc_[a-z0-9_]+)"\)', open(os.path.join(dp, f)).read()):
+                seen += 1
+                assert name in declared, (f, name)
+                assert hasattr(lib, name), (f, name)
+    assert seen > 100

@@ -17,7 +17,12 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); g.update_n(n); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+import ctypes as C
+from cuda_fortran_mc_simulation_spin_b200 import _lib
+w = _lib.fn("b200mc_debug_slab_wait_ns", C.c_ulonglong, C.c_void_p)(g._h)
+tw = torch.tensor([float(w)], device="cuda"); dist.all_reduce(tw, op=dist.ReduceOp.MAX)
 if rank == 0:
+    print(f"  max flag-wait per pass {tw.item() / (2 * (n + 5)) / 1e3:.1f} us;", end=" ")
     print(f"{kind} world={world} TUNE={os.environ.get('B200MC_TUNE','0')} ILEAVE={os.environ.get('B200MC_ILEAVE','1')} "
           f"TRANSPORT={os.environ.get('B200MC_SLAB_TRANSPORT','p2p')}: {t.item():.4f} ms/MCS  {g.nall()/t.item()/1e6:.1f} flips/ns", flush=True)
 dist.barrier(); dist.destroy_process_group()
