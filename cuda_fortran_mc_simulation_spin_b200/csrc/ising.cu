@@ -33,7 +33,6 @@ struct Ising {
     unsigned int* d_ticket;
     int tune;  // debug knobs from env B200MC_TUNE: bit0 = static round-robin (no ticket)
     int chunk; // vectors per ticket (env B200MC_CHUNK, default 128)
-    int ileave; // slab mode: one high-boundary chunk in every 2^ileave tickets at the start of a pass (env B200MC_ILEAVE, log2)
     int grid;
     bool alive;
     // observables cache: valid until the configuration changes
@@ -186,16 +185,15 @@ int launch_push(Ising* m, int colour, bool fuse)
     a.rot_hi = g.rank == g.nranks - 1 ? +1 : 0;   // crossing the end of the fold moves a site to the next lane
     a.nb = (int)g.H;
     a.hi_start = (int)(g.Lloc - g.H);
-    const int64_t nchunks = (g.Lloc + a.chunk - 1) / a.chunk;
-    a.blo = (int)((g.H + a.chunk - 1) / a.chunk);
-    a.jhi = (int)((g.Lloc - g.H) / a.chunk);
-    a.nbchunks = a.blo + (int)(nchunks - a.jhi);
-    const int64_t nbhi = nchunks - a.jhi;
-    a.ileave = m->ileave;              // log2: one high-boundary chunk in every 2^ileave tickets at the start of the pass
-    a.chunk_shift = 0;
-    while ((1 << a.chunk_shift) < a.chunk) ++a.chunk_shift;
+    const int64_t nchunks = (g.Lloc + TK_CHUNK - 1) / TK_CHUNK;
+    const int64_t blo = (g.H + TK_CHUNK - 1) / TK_CHUNK;      // chunks [0, blo) hold the first H owned vectors
+    const int64_t jhi = (g.Lloc - g.H) / TK_CHUNK;            // chunks [jhi, nchunks) the last H
+    a.nbchunks = (int)(blo + (nchunks - jhi));
+    a.hi_tickets = (int)((nchunks - jhi) * TK_CHUNK);
+    a.hi_first = (int)(jhi * TK_CHUNK);
+    a.lo_end = (int)(blo * TK_CHUNK);
     a.nopush = ((m->tune & 4) ? 1 : 0) | ((m->tune & 32) ? 2 : 0);  // debug: bit 0 skip the NVLink stores (wrong results, timing only), bit 1 no L2 prefetch
-    a.q_total = (int)((nbhi << a.ileave) > nchunks ? (nbhi << a.ileave) : nchunks);
+    a.q_total = (int)nchunks;
     a.dbg_wait = reinterpret_cast<unsigned long long*>(st.flags + 48);
     a.done = st.flags + 32;
     a.sig_prev = st.peer_flags[0] + 16;  // I am rank-1's "next"
@@ -365,7 +363,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     m->ndim = ndim; m->nx = nx; m->ny = ny; m->nz = ndim == 3 ? nz : 0;
     m->stream = 0; m->d_acc = nullptr; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
     { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; t = getenv("B200MC_CHUNK"); m->chunk = t ? atoi(t) : 128; m->chunk = TK_CHUNK;  /* compile-time now */
-      t = getenv("B200MC_ILEAVE"); m->ileave = t ? atoi(t) : 0; if (m->ileave < 0 || m->ileave > 6) m->ileave = 0; }
+    }
     m->method = METHOD_METROPOLIS; m->seed = (uint32_t)iseed; m->draw = 0; m->alive = true;
     m->obs_valid = false; m->timing = false; m->ev_used = 0;
     m->fuse_ok = false; m->want_fused = false; m->fused_pending = false;

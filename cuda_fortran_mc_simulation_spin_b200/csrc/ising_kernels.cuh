@@ -72,7 +72,8 @@ struct RingPassArgs {
     int rot_lo, rot_hi;    // lane rotation of the pushed copy: +1 lane b <- b-1, -1 lane b <- b+1, 0 none
     int nb;                // H
     int hi_start;          // Lloc - H
-    int blo, jhi, nbchunks, q_total, ileave /* log2 */, nopush, chunk_shift;
+    int nbchunks, q_total, nopush;
+    int hi_tickets, hi_first, lo_end;  // in vectors: 128 * (chunks from jhi on), 128 * jhi, 128 * blo
     unsigned long long* dbg_wait;  // debug: ns block 0 spent waiting for the neighbours' flags (summed over launches)
     unsigned int* done;    // completed boundary chunks of this launch (local)
     unsigned int* sig_prev;       // rank-1's "from next" flag, rank+1's "from prev" flag (peer memory)
@@ -241,13 +242,15 @@ __device__ __noinline__ int2 ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4
 
 // One vector (16 sites of the colour being updated) of one lane: loads, Philox block, byte-parallel
 // accept test, store; ties parked in the warp's queue; optional halo push and fused E/M sums.
-template <int NNB, int METHOD, bool PUSH, bool MEASURE>
+template <int NNB, int METHOD, bool PUSH, bool MEASURE, bool FULLWARP>
 __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (&q)[NNB], uint32_t cx, uint32_t cz, uint32_t cw,
                                           const RingPassArgs& a, const IsingTab& tab, uint64_t pol, uint32_t qaddr,
                                           uint32_t cntaddr, bool is_b, uint32_t& accX, uint32_t& accM)
 {
     uint4 o = ld_own(po, pol);
     uint4 nb[NNB];
+    // (loading the x+ vector as a shuffle of the neighbouring lane's x- vector instead of a second, overlapping
+    // 512-byte load was tried: 4 SHFL + a one-lane load made the pass 20 % slower -- the MIO queue is the busiest unit)
 #pragma unroll
     for (int j = 0; j < NNB; ++j) nb[j] = ld_other(q[j]);
     // counter (p0 + v, 0, draw_lo, draw_hi | colour << 16 | sub << 24): positions are < 2^31
@@ -346,22 +349,12 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
         boundary = false;
         if (!PUSH) return t;
         // Slab mode.  The chunks holding the LAST H owned vectors (the low halo of rank+1) are handed
-        // out first, one in every 2^ileave tickets; all other chunks follow in natural order, which
+        // out first; all other chunks follow in natural order, which
         // starts with the first H owned vectors (the high halo of rank-1).  Both halo blocks are thus
         // on their way over NVLink early in the pass and land while the interior is being updated.
-        const int q = t / TK_CHUNK;
-        const int nbhi = a.nbchunks - a.blo;
-        int j;
-        if (q < (nbhi << a.ileave)) {
-            const int k = q >> a.ileave;
-            if ((q & ((1 << a.ileave) - 1)) == 0) j = a.jhi + k;
-            else { j = q - k - 1; if (j >= a.jhi) j = -1; }
-        } else {
-            j = q - nbhi;
-            if (j >= a.jhi) j = -1;
-        }
-        boundary = j >= 0 && (j < a.blo || j >= a.jhi);
-        return j < 0 ? -1 : j * TK_CHUNK;
+        const int vb = t >= a.hi_tickets ? t - a.hi_tickets : t + a.hi_first;   // hi_tickets = 128 nbhi, hi_first = 128 jhi
+        boundary = vb < a.lo_end || vb >= a.hi_first;
+        return vb;
     };
     // The two streams of a chunk that come from DRAM (the own colour, read once per pass, and the leading
     // z / y neighbour plane, touched for the first time) are prefetched into L2 one ticket ahead: lanes
@@ -404,8 +397,8 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
                 const uint4* qu[NNB];
 #pragma unroll
                 for (int j = 0; j < NNB; ++j) qu[j] = q[j] + 32 * u;
-                ising_vec<NNB, METHOD, PUSH, MEASURE>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr, cntaddr,
-                                                      is_b, accX, accM);
+                ising_vec<NNB, METHOD, PUSH, MEASURE, true>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
+                                                            cntaddr, is_b, accX, accM);
                 if (u & 1) {
                     __syncwarp();
                     if (lds32(cntaddr) > TQ_CAP - 64) {
@@ -421,8 +414,8 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
                     const uint4* qu[NNB];
 #pragma unroll
                     for (int j = 0; j < NNB; ++j) qu[j] = q[j] + 32 * u;
-                    ising_vec<NNB, METHOD, PUSH, MEASURE>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
-                                                          cntaddr, is_b, accX, accM);
+                    ising_vec<NNB, METHOD, PUSH, MEASURE, false>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
+                                                                 cntaddr, is_b, accX, accM);
                 }
                 __syncwarp();
                 if (lds32(cntaddr) > TQ_CAP - 64) {
