@@ -28,6 +28,7 @@ struct Ising {
     IsingTab tab;
     IsingTabF64 tabf;
     unsigned long long* d_acc;  // [X, sum s]
+    unsigned long long* h_acc;  // pinned host copy (device -> host read of every measurement)
     int64_t* d_off1;            // colour-1 offsets for the measure kernel
     double* d_randoms;
     unsigned int* d_ticket;
@@ -332,8 +333,8 @@ int measure(Ising* m, int64_t* e, int64_t* mag)
         int rc = dist_allreduce_u64(m->st.comm, m->d_acc, 2, m->stream);
         if (rc) return rc;
     }
-    unsigned long long acc[2];
-    CK(cudaMemcpyAsync(acc, m->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, m->stream));
+    unsigned long long* acc = m->h_acc;
+    CK(cudaMemcpyAsync(acc, m->d_acc, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
     const int64_t X = (int64_t)acc[0], sum = (int64_t)acc[1];
     // E = -(bonds) + 2 X with bonds = (nnb/2) N;   M = 2 sum(s) - N
@@ -361,7 +362,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     Ising* m = new (std::nothrow) Ising();
     if (!m) ARG_FAIL("out of host memory");
     m->ndim = ndim; m->nx = nx; m->ny = ny; m->nz = ndim == 3 ? nz : 0;
-    m->stream = 0; m->d_acc = nullptr; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
+    m->stream = 0; m->d_acc = nullptr; m->h_acc = nullptr; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
     { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; t = getenv("B200MC_CHUNK"); m->chunk = t ? atoi(t) : 128; m->chunk = TK_CHUNK;  /* compile-time now */
     }
     m->method = METHOD_METROPOLIS; m->seed = (uint32_t)iseed; m->draw = 0; m->alive = true;
@@ -387,6 +388,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     if (rc) { destroy(m); return rc; }
     if (cudaMalloc(&m->d_ticket, TK_NCNT * 64 * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaHostAlloc(&m->h_acc, 2 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess ||
         cudaMalloc(&m->d_off1, 6 * sizeof(int64_t)) != cudaSuccess) {
         destroy(m);
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed");
@@ -423,6 +425,7 @@ int destroy(Ising* m)
     cudaStreamSynchronize(m->stream);
     ring_free(&m->st);
     cudaFree(m->d_acc);
+    cudaFreeHost(m->h_acc);
     cudaFree(m->d_off1);
     cudaFree(m->d_randoms);
     cudaFree(m->d_ticket);

@@ -273,17 +273,15 @@ __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (
     ising_finish<METHOD>(o.z, o.w, oA1, oB1, zA1, zB1);
     st_own(po, o, pol);
     if (MEASURE) {
-        // fused E + M (ising_measure_kernel's sums) on the values this pass leaves behind:
-        // unequal neighbours of a site = s ? NNB - S : S, bytewise (S ^ 7s) - (7 - NNB) s
-        accX = __dp4a((S.x ^ (o.x * 7u)) - o.x * (uint32_t)(7 - NNB), 0x01010101u, accX);
-        accX = __dp4a((S.y ^ (o.y * 7u)) - o.y * (uint32_t)(7 - NNB), 0x01010101u, accX);
-        accX = __dp4a((S.z ^ (o.z * 7u)) - o.z * (uint32_t)(7 - NNB), 0x01010101u, accX);
-        accX = __dp4a((S.w ^ (o.w * 7u)) - o.w * (uint32_t)(7 - NNB), 0x01010101u, accX);
-        // sum(s): own vector + the other colour's vector at the same position (offset 0 = nb[0])
-        accM = __dp4a(o.x + nb[0].x, 0x01010101u, accM);
-        accM = __dp4a(o.y + nb[0].y, 0x01010101u, accM);
-        accM = __dp4a(o.z + nb[0].z, 0x01010101u, accM);
-        accM = __dp4a(o.w + nb[0].w, 0x01010101u, accM);
+        // fused E + M on the values this pass leaves behind.  With s the new spins of this colour and S the number
+        // of up neighbours, the unequal-neighbour count is  X = sum_{s=0} S + sum_{s=1} (NNB - S)
+        //   = sum S - 2 sum S s + NNB sum s,  and  sum S (over all sites of this colour) = NNB sum(s of the other colour),
+        // so the launch only accumulates  accX = sum S s  and  accM = sum s (both colours):  X = NNB accM - 2 accX.
+        // (IDP.4A is a slow pipe on sm_100: the byte sums use full-rate IMAD / LOP3 / IADD3 instead.)
+        const uint32_t so = ((S.x & (o.x * 255u)) + (S.y & (o.y * 255u))) + ((S.z & (o.z * 255u)) + (S.w & (o.w * 255u)));  // bytes <= 24
+        const uint32_t sm = ((o.x + o.y) + (o.z + o.w)) + ((nb[0].x + nb[0].y) + (nb[0].z + nb[0].w));                       // bytes <= 8
+        accX += (so * 0x01010101u) >> 24;   // byte sum (< 256)
+        accM += (sm * 0x01010101u) >> 24;
     }
     if (PUSH && is_b && !(a.nopush & 1)) {  // second copy straight into the neighbour's halo (NVLink store)
         if (v < a.nb) a.peer_lo[v] = rot_lanes(o, a.rot_lo);
@@ -445,7 +443,7 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
     }
     const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab);
     if (MEASURE) {
-        long long x = (long long)accX + corrX + d.x, mm = (long long)accM + corrM + d.y;
+        long long x = (long long)NNB * accM - 2ll * accX + corrX + d.x, mm = (long long)accM + corrM + d.y;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             x += __shfl_down_sync(0xffffffffu, x, o);
@@ -548,14 +546,9 @@ ising_measure_kernel(const uint4* __restrict__ c0, const uint4* __restrict__ c1,
             o.x &= keep[0]; o.y &= keep[1]; o.z &= keep[2]; o.w &= keep[3];
             a0.x &= keep[0]; a0.y &= keep[1]; a0.z &= keep[2]; a0.w &= keep[3];
         }
-        uint32_t x = __dp4a(X.x, 0x01010101u, 0u);
-        x = __dp4a(X.y, 0x01010101u, x);
-        x = __dp4a(X.z, 0x01010101u, x);
-        x = __dp4a(X.w, 0x01010101u, x);
-        uint32_t m = __dp4a(o.x + a0.x, 0x01010101u, 0u);
-        m = __dp4a(o.y + a0.y, 0x01010101u, m);
-        m = __dp4a(o.z + a0.z, 0x01010101u, m);
-        m = __dp4a(o.w + a0.w, 0x01010101u, m);
+        // byte sums with a full-rate multiply (IDP.4A is a slow pipe on sm_100): bytes of the word sums are <= 24 / <= 8
+        const uint32_t x = (((X.x + X.y) + (X.z + X.w)) * 0x01010101u) >> 24;
+        const uint32_t m = ((((o.x + a0.x) + (o.y + a0.y)) + ((o.z + a0.z) + (o.w + a0.w))) * 0x01010101u) >> 24;
         part[0] += x;
         part[1] += m;
     }
