@@ -53,73 +53,103 @@ __device__ __forceinline__ uint4 philox_tag(uint4 c, const uint32_t (&rk0)[10])
     return c;
 }
 
-// neighbour field (sum of the four neighbour spins) for the 4 sites of group (y, g), colour a.colour
-__device__ __forceinline__ void xy_field(const XYArgs& a, int y, int g, float (&hx)[4], float (&hy)[4])
+// Column-strip traversal.  A thread owns the 4 colour-compact sites of group g and walks XY_ROWS consecutive
+// rows.  The cos / sin of the other colour's row y (4 values) serve three updates: the same-row neighbours of
+// row y, the "up" neighbours of row y - 1 and the "down" neighbours of row y + 1 -- so they are computed once
+// and kept in a rolling three-row register window.  Per 4 sites and row that is 13 sincos (4 new neighbour
+// values, the fifth same-row value, 4 own, 4 candidates) instead of 21: the kernel is bound by the SFU queue.
+#define XY_ROWS 16
+
+struct XYRow { float c[4], s[4]; };
+
+__device__ __forceinline__ void xy_load_row(const XYArgs& a, int y, int g, XYRow& r)
 {
-    const int nxh = a.nxh;
+    const float4 raw = *reinterpret_cast<const float4*>(a.oth + (size_t)y * a.nxh + 4 * g);
+    sincos_turns(raw.x, r.s[0], r.c[0]);
+    sincos_turns(raw.y, r.s[1], r.c[1]);
+    sincos_turns(raw.z, r.s[2], r.c[2]);
+    sincos_turns(raw.w, r.s[3], r.c[3]);
+}
+
+// local field of the 4 sites of row y: same-row values `mid` (+ the fifth one across the group edge), up, down
+// (same summation order as calc_delta_energy, src/xy2d_periodic_gpu_m.f90:395: x+1, x-1, y+1, y-1)
+__device__ __forceinline__ void xy_strip_field(const XYArgs& a, int y, int g, const XYRow& dn, const XYRow& mid, const XYRow& up,
+                                               float (&hx)[4], float (&hy)[4])
+{
+    const int nxh = a.nxh, xi0 = 4 * g;
     const int p = (y + a.colour) & 1;  // x0 = 2 xi + p
-    const int xi0 = 4 * g;
-    const float* row = a.oth + (size_t)y * nxh;
-    const int yu = (y + 1 == a.ny) ? 0 : y + 1, yd = (y == 0) ? a.ny - 1 : y - 1;
-    const float4 b = *reinterpret_cast<const float4*>(row + xi0);
-    const float4 u = *reinterpret_cast<const float4*>(a.oth + (size_t)yu * nxh + xi0);
-    const float4 d = *reinterpret_cast<const float4*>(a.oth + (size_t)yd * nxh + xi0);
-    // the fifth same-row value: left of the group (p = 0) or right of it (p = 1), periodic in x
     const int xe = p ? (xi0 + 4 == nxh ? 0 : xi0 + 4) : (xi0 == 0 ? nxh - 1 : xi0 - 1);
-    const float e = row[xe];
-    float bs[5], bc[5];
-    // ordered left to right: p = 0: e, b.x, b.y, b.z, b.w ; p = 1: b.x, b.y, b.z, b.w, e
-    const float bv[5] = {p ? b.x : e, p ? b.y : b.x, p ? b.z : b.y, p ? b.w : b.z, p ? e : b.w};
-#pragma unroll
-    for (int j = 0; j < 5; ++j) sincos_turns(bv[j], bs[j], bc[j]);
-    const float uv[4] = {u.x, u.y, u.z, u.w}, dv[4] = {d.x, d.y, d.z, d.w};
+    float es, ec;
+    sincos_turns(a.oth[(size_t)y * nxh + xe], es, ec);
+    // ordered left to right: p = 0: e, m0, m1, m2, m3 ; p = 1: m0, m1, m2, m3, e
+    const float bc[5] = {p ? mid.c[0] : ec, p ? mid.c[1] : mid.c[0], p ? mid.c[2] : mid.c[1], p ? mid.c[3] : mid.c[2], p ? ec : mid.c[3]};
+    const float bs[5] = {p ? mid.s[0] : es, p ? mid.s[1] : mid.s[0], p ? mid.s[2] : mid.s[1], p ? mid.s[3] : mid.s[2], p ? es : mid.s[3]};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float us, uc, ds, dc;
-        sincos_turns(uv[j], us, uc);
-        sincos_turns(dv[j], ds, dc);
-        // site j (x0 = 2 (xi0 + j) + p): x-1 neighbour is bv[j], x+1 neighbour is bv[j + 1]
-        // (same summation order as calc_delta_energy, src/xy2d_periodic_gpu_m.f90:395: x+1, x-1, y+1, y-1)
-        hx[j] = bc[j + 1] + bc[j] + uc + dc;
-        hy[j] = bs[j + 1] + bs[j] + us + ds;
+        hx[j] = bc[j + 1] + bc[j] + up.c[j] + dn.c[j];
+        hy[j] = bs[j + 1] + bs[j] + up.s[j] + dn.s[j];
     }
 }
 
-// update_sub + calc_delta_energy, src/xy2d_periodic_gpu_m.f90:368-397
+// OVERRELAX = false: update_sub + calc_delta_energy, src/xy2d_periodic_gpu_m.f90:368-397
+// OVERRELAX = true : over_relaxation_sub, :418-439: reflect the spin about the local field.  In angles:
+//                    theta' = 2 phi - theta with phi = atan2(h_y, h_x) (the reference's renormalisation is the identity here)
+template <bool OVERRELAX>
 __global__ void __launch_bounds__(256)
-xy_metropolis_kernel(const __grid_constant__ XYArgs a)
+xy_strip_kernel(const __grid_constant__ XYArgs a)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.ny * a.gpr) return;
-    const int y = idx / a.gpr, g = idx - y * a.gpr;
-    float hx[4], hy[4];
-    xy_field(a, y, g, hx, hy);
-    float4* po = reinterpret_cast<float4*>(a.own + (size_t)y * a.nxh + 4 * g);
-    const float4 o = *po;
-    float ov[4] = {o.x, o.y, o.z, o.w};
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nblk = (a.ny + XY_ROWS - 1) / XY_ROWS;
+    if (tid >= nblk * a.gpr) return;
+    const int rb = tid / a.gpr, g = tid - rb * a.gpr;
+    const int y0 = rb * XY_ROWS, y1 = min(y0 + XY_ROWS, a.ny);
+    XYRow dn, mid, up;
+    xy_load_row(a, y0 == 0 ? a.ny - 1 : y0 - 1, g, dn);
+    xy_load_row(a, y0, g, mid);
+#pragma unroll 2
+    for (int y = y0; y < y1; ++y) {
+        xy_load_row(a, y + 1 == a.ny ? 0 : y + 1, g, up);
+        float hx[4], hy[4];
+        xy_strip_field(a, y, g, dn, mid, up, hx, hy);
+        float4* po = reinterpret_cast<float4*>(a.own + (size_t)y * a.nxh + 4 * g);
+        const float4 o = *po;
+        float ov[4] = {o.x, o.y, o.z, o.w};
+        if (OVERRELAX) {
 #pragma unroll
-    for (int sub = 0; sub < 2; ++sub) {
-        const uint4 R = philox_tag<TAG_XY>(mk_ctr((uint64_t)idx, a.draw, (uint32_t)a.colour, (uint32_t)sub), a.rk0);
+            for (int j = 0; j < 4; ++j) {
+                const float phi = atan2f(hy[j], hx[j]) * INV_TWO_PI_F;
+                const float t = 2.0f * phi - ov[j];
+                ov[j] = t - floorf(t);
+            }
+        } else {
+            const int idx = y * a.gpr + g;   // the RNG block of this group (contract: oracle/rng_contract.c)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int j = 2 * sub + e;
-            const uint32_t Ur = e ? R.z : R.x, Uc = e ? R.w : R.y;
-            const float r = ((float)Ur + 1.0f) * 0x1p-32f;       // (0, 1]
-            const float ct = ((float)Uc + 1.0f) * 0x1p-32f;      // candidate angle in turns
-            float cs, cc, ss, sc;
-            sincos_turns(ct, cs, cc);
-            sincos_turns(ov[j], ss, sc);
-            const float de = -((cc - sc) * hx[j] + (cs - ss) * hy[j]);
-            if (!(r > __expf(-a.beta * de))) ov[j] = ct;          // accept iff r <= exp(-beta dE), :384
+            for (int sub = 0; sub < 2; ++sub) {
+                const uint4 R = philox_tag<TAG_XY>(mk_ctr((uint64_t)idx, a.draw, (uint32_t)a.colour, (uint32_t)sub), a.rk0);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 2 * sub + e;
+                    const uint32_t Ur = e ? R.z : R.x, Uc = e ? R.w : R.y;
+                    const float r = ((float)Ur + 1.0f) * 0x1p-32f;       // (0, 1]
+                    const float ct = ((float)Uc + 1.0f) * 0x1p-32f;      // candidate angle in turns
+                    float cs, cc, ss, sc;
+                    sincos_turns(ct, cs, cc);
+                    sincos_turns(ov[j], ss, sc);
+                    const float de = -((cc - sc) * hx[j] + (cs - ss) * hy[j]);
+                    if (!(r > __expf(-a.beta * de))) ov[j] = ct;          // accept iff r <= exp(-beta dE), :384
+                }
+            }
         }
+        *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
+        dn = mid;
+        mid = up;
     }
-    *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
 }
 
 // metropolis_by_field_sub, :198-216 (initial-state preparation): every site, no coupling.
 // candidate (cos 2 pi c, sin 2 pi c); dE = -(h . (cand - s)); accepted iff r <= 1 - exp(dE)
 // (the reference's test is `randoms > 1 - exp(delta_energy) -> return`, :213).
-// Uniforms: the Metropolis contract (same counters as xy_metropolis_kernel, both colours).
+// Uniforms: the Metropolis contract (same counters as the Metropolis kernel, both colours).
 __global__ void __launch_bounds__(256)
 xy_field_kernel(const __grid_constant__ XYArgs a, float hx, float hy)
 {
@@ -144,28 +174,6 @@ xy_field_kernel(const __grid_constant__ XYArgs a, float hx, float hy)
             const float de = -(hx * (cc - sc) + hy * (cs - ss));
             if (!(r > 1.0f - __expf(de))) ov[j] = ct;
         }
-    }
-    *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
-}
-
-// over_relaxation_sub, :418-439: reflect the spin about the local field.  In angles:
-// theta' = 2 phi - theta with phi = atan2(h_y, h_x) (the reference's renormalisation is the identity here)
-__global__ void __launch_bounds__(256)
-xy_overrelax_kernel(const __grid_constant__ XYArgs a)
-{
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.ny * a.gpr) return;
-    const int y = idx / a.gpr, g = idx - y * a.gpr;
-    float hx[4], hy[4];
-    xy_field(a, y, g, hx, hy);
-    float4* po = reinterpret_cast<float4*>(a.own + (size_t)y * a.nxh + 4 * g);
-    const float4 o = *po;
-    float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float phi = atan2f(hy[j], hx[j]) * INV_TWO_PI_F;
-        const float t = 2.0f * phi - ov[j];
-        ov[j] = t - floorf(t);
     }
     *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
 }
@@ -329,12 +337,12 @@ void fill_args(XY* m, int colour, XYArgs* a)
 int sweep(XY* m)
 {
     m->obs_valid = false;
-    const int total = (int)m->ny * m->gpr;
+    const int strips = (int)((m->ny + XY_ROWS - 1) / XY_ROWS) * m->gpr;
     for (int colour = 0; colour < 2; ++colour) {
         XYArgs a;
         fill_args(m, colour, &a);
         COUNT_LAUNCH();
-        xy_metropolis_kernel<<<(total + 255) / 256, 256, 0, m->stream>>>(a);
+        xy_strip_kernel<false><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
         CK(cudaGetLastError());
     }
     m->draw += 1;
@@ -344,13 +352,13 @@ int sweep(XY* m)
 int over_relax(XY* m, int n_steps)
 {
     m->obs_valid = false;
-    const int total = (int)m->ny * m->gpr;
+    const int strips = (int)((m->ny + XY_ROWS - 1) / XY_ROWS) * m->gpr;
     for (int i = 0; i < n_steps; ++i)
         for (int colour = 0; colour < 2; ++colour) {
             XYArgs a;
             fill_args(m, colour, &a);
             COUNT_LAUNCH();
-            xy_overrelax_kernel<<<(total + 255) / 256, 256, 0, m->stream>>>(a);
+            xy_strip_kernel<true><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
             CK(cudaGetLastError());
         }
     return B200MC_OK;
