@@ -200,6 +200,13 @@ class _IsingBase:
         self._call("measure", C.byref(e), C.byref(m), argtypes=(C.POINTER(C.c_int64), C.POINTER(C.c_int64)))
         return int(e.value), int(m.value)
 
+    def run_relaxation(self, mcs):
+        """mcs x [update; calc_magne_sum; calc_energy_sum] on the device; returns (E[mcs], M[mcs]) int64 arrays"""
+        e = np.empty(int(mcs), dtype=np.int64)
+        m = np.empty(int(mcs), dtype=np.int64)
+        self._call("run_relaxation", int(mcs), e.ctypes.data_as(P), m.ctypes.data_as(P), argtypes=(i32, P, P))
+        return e, m
+
     def sync(self):
         self._call("sync")
 

@@ -29,6 +29,9 @@ struct Ising {
     IsingTabF64 tabf;
     unsigned long long* d_acc;  // [X, sum s]
     unsigned long long* h_acc;  // pinned host copy (device -> host read of every measurement)
+    unsigned long long* acc_target;  // where the fused pass / the measure kernel add their sums (d_acc, or a slot of d_series)
+    unsigned long long* d_series;    // run_relaxation: [mcs][2] sums, one slot per MCS
+    int64_t series_cap;
     int64_t* d_off1;            // colour-1 offsets for the measure kernel
     double* d_randoms;
     unsigned int* d_ticket;
@@ -140,7 +143,7 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bo
     a.draw = m->draw;
     a.ticket = nullptr;
     a.chunk = m->chunk;
-    a.acc = m->d_acc;
+    a.acc = m->acc_target;
     a.nopush = (m->tune & 32) ? 2 : 0;  // debug bit 5: no L2 prefetch
     int64_t need = (n + 255) / 256;
     const int grid = (int)(need < (int64_t)m->grid ? need : (int64_t)m->grid);
@@ -203,7 +206,7 @@ int launch_push(Ising* m, int colour, bool fuse)
     a.wait_next = st.flags + 16;
     a.wait_seq = st.push_seq;
     a.sig_seq = ++st.push_seq;
-    a.acc = m->d_acc;
+    a.acc = m->acc_target;
     CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
     COUNT_LAUNCH();
     if (m->method == METHOD_METROPOLIS) {
@@ -226,7 +229,7 @@ int launch_pass(Ising* m, int colour, bool fuse)
     const RingGeom& g = m->st.g;
     m->obs_valid = false;
     m->fused_pending = false;
-    if (fuse) CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
+    if (fuse && m->acc_target == m->d_acc) CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
     if (m->timing) {
         while (m->evs.size() < m->ev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); m->evs.push_back(e); }
         CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
@@ -268,11 +271,11 @@ int launch_pass(Ising* m, int colour, bool fuse)
 }
 
 // One MCS.  allow_fuse: this is the last sweep before control returns to the caller.
-int sweep(Ising* m, bool allow_fuse = true)
+int sweep(Ising* m, bool allow_fuse = true, bool force_fuse = false)
 {
     int rc;
     if (m->fused_pending) m->want_fused = false;  // the sums of the previous sweep were never asked for
-    const bool fuse = allow_fuse && m->want_fused && m->fuse_ok && !(m->tune & 8);
+    const bool fuse = force_fuse || (allow_fuse && m->want_fused && m->fuse_ok && !(m->tune & 8));
     for (int colour = 0; colour < 2; ++colour) {
         rc = m->ndim == 3 ? launch_pass<6>(m, colour, fuse && colour == 1) : launch_pass<4>(m, colour, fuse && colour == 1);
         if (rc) return rc;
@@ -309,6 +312,8 @@ int launch_pass_randoms(Ising* m, int colour)
     return ring_halo(&m->st, colour, m->stream);
 }
 
+int launch_measure(Ising* m, unsigned long long* acc);
+
 int measure(Ising* m, int64_t* e, int64_t* mag)
 {
     const RingGeom& g = m->st.g;
@@ -319,13 +324,8 @@ int measure(Ising* m, int64_t* e, int64_t* mag)
     }
     if (!m->fused_pending) {
         { int rcq = ring_p2p_quiesce(&m->st, m->stream); if (rcq) return rcq; }
-        COUNT_LAUNCH();
         CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
-        if (m->ndim == 3)
-            ising_measure_kernel<6><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, m->d_acc);
-        else
-            ising_measure_kernel<4><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, m->d_acc);
-        CK(cudaGetLastError());
+        { int rcm = launch_measure(m, m->d_acc); if (rcm) return rcm; }
     }
     m->fused_pending = false;  // the all-reduce below turns d_acc into global sums; they are cached in obs_*
     m->want_fused = true;
@@ -348,6 +348,63 @@ int measure(Ising* m, int64_t* e, int64_t* mag)
 
 int destroy(struct Ising* m);
 
+int launch_measure(Ising* m, unsigned long long* acc)
+{
+    const RingGeom& g = m->st.g;
+    COUNT_LAUNCH();
+    if (m->ndim == 3)
+        ising_measure_kernel<6><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, acc);
+    else
+        ising_measure_kernel<4><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, acc);
+    CK(cudaGetLastError());
+    return B200MC_OK;
+}
+
+// The drivers' inner loop on the device: mcs x [update; calc_magne_sum; calc_energy_sum]
+// (app/ising3d_gpu_relaxation.f90:40-46) without a host round trip per MCS.  Every sweep adds its sums to its
+// own slot of a device series (fused into the second colour pass where the layout allows, else by the measure
+// kernel); one all-reduce (slab mode), one copy and one synchronisation at the end.
+int run_relaxation(Ising* m, int32_t mcs, int64_t* e, int64_t* mag)
+{
+    const RingGeom& g = m->st.g;
+    if (mcs < 0) ARG_FAIL("mcs < 0");
+    if (mcs == 0) return B200MC_OK;
+    if (m->series_cap < mcs) {
+        cudaFree(m->d_series);
+        m->d_series = nullptr; m->series_cap = 0;
+        CK(cudaMalloc(&m->d_series, (size_t)mcs * 2 * sizeof(unsigned long long)));
+        m->series_cap = mcs;
+    }
+    CK(cudaMemsetAsync(m->d_series, 0, (size_t)mcs * 2 * sizeof(unsigned long long), m->stream));
+    const bool fuse = m->fuse_ok && !(m->tune & 8);
+    int rc = B200MC_OK;
+    for (int32_t i = 0; i < mcs && !rc; ++i) {
+        m->acc_target = m->d_series + 2 * (size_t)i;
+        m->fused_pending = false;
+        rc = sweep(m, true, fuse);
+        if (!rc && !fuse) {
+            rc = ring_p2p_quiesce(&m->st, m->stream);
+            if (!rc) rc = launch_measure(m, m->acc_target);
+        }
+    }
+    m->acc_target = m->d_acc;
+    m->fused_pending = false;
+    m->want_fused = false;
+    if (rc) return rc;
+    if (g.nranks > 1 && (rc = dist_allreduce_u64(m->st.comm, m->d_series, 2 * (int)mcs, m->stream))) return rc;
+    std::vector<unsigned long long> host((size_t)mcs * 2);
+    CK(cudaMemcpyAsync(host.data(), m->d_series, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    for (int32_t i = 0; i < mcs; ++i) {
+        const int64_t X = (int64_t)host[2 * (size_t)i], sum = (int64_t)host[2 * (size_t)i + 1];
+        const int64_t ei = -(int64_t)(g.nnb / 2) * g.N + 2 * X, mi = 2 * sum - g.N;
+        if (e) e[i] = ei;
+        if (mag) mag[i] = mi;
+        if (i == mcs - 1) { m->obs_e = ei; m->obs_m = mi; m->obs_valid = true; }
+    }
+    return B200MC_OK;
+}
+
 int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed,
            int rank = 0, int nranks = 1, const char* nccl_id = nullptr)
 {
@@ -362,7 +419,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     Ising* m = new (std::nothrow) Ising();
     if (!m) ARG_FAIL("out of host memory");
     m->ndim = ndim; m->nx = nx; m->ny = ny; m->nz = ndim == 3 ? nz : 0;
-    m->stream = 0; m->d_acc = nullptr; m->h_acc = nullptr; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
+    m->stream = 0; m->d_acc = nullptr; m->h_acc = nullptr; m->acc_target = nullptr; m->d_series = nullptr; m->series_cap = 0; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
     { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; t = getenv("B200MC_CHUNK"); m->chunk = t ? atoi(t) : 128; m->chunk = TK_CHUNK;  /* compile-time now */
     }
     m->method = METHOD_METROPOLIS; m->seed = (uint32_t)iseed; m->draw = 0; m->alive = true;
@@ -394,6 +451,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed");
         return B200MC_ERR_CUDA;
     }
+    m->acc_target = m->d_acc;
     cudaMemcpy(m->d_off1, m->st.g.off[1], 6 * sizeof(int64_t), cudaMemcpyHostToDevice);
     // persistent-style grid: SMs x resident blocks, grid-stride over the vectors
     int dev = 0, sms = 148, occ = 4;
@@ -426,6 +484,7 @@ int destroy(Ising* m)
     ring_free(&m->st);
     cudaFree(m->d_acc);
     cudaFreeHost(m->h_acc);
+    cudaFree(m->d_series);
     cudaFree(m->d_off1);
     cudaFree(m->d_randoms);
     cudaFree(m->d_ticket);
@@ -535,6 +594,7 @@ int b200mc_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
     int PFX##_calc_energy_sum(void* h, int64_t* e) { CHECK_H(h, ND); return measure(H(h), e, nullptr); } \
     int PFX##_calc_magne_sum(void* h, int64_t* m) { CHECK_H(h, ND); return measure(H(h), nullptr, m); } \
     int PFX##_measure(void* h, int64_t* e, int64_t* m) { CHECK_H(h, ND); return measure(H(h), e, m); } \
+    int PFX##_run_relaxation(void* h, int32_t mcs, int64_t* e, int64_t* m) { CHECK_H(h, ND); return run_relaxation(H(h), mcs, e, m); } \
     int PFX##_get_spins(void* h, int32_t* out) { CHECK_H(h, ND); if (!out) ARG_FAIL("null output"); return ring_export_i32(&H(h)->st, out, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream); } \
     int PFX##_set_spins(void* h, const int32_t* in) { CHECK_H(h, ND); if (!in) ARG_FAIL("null input"); H(h)->obs_valid = false; H(h)->fused_pending = false; return ring_import_i32(&H(h)->st, in, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream); } \
     int64_t PFX##_nx(void* h) { return h ? H(h)->nx : -1; }                                       \

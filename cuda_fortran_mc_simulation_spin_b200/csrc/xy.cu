@@ -180,39 +180,50 @@ xy_field_kernel(const __grid_constant__ XYArgs a, float hx, float hy)
 
 // fused E, Mx, My (three OpenACC reductions in the reference, :496-534), real64 accumulation.
 // acc[0] += -sum s . (s_{x+1} + s_{y+1}), acc[1] += sum cos, acc[2] += sum sin
+// Column strip like the update: a thread owns 8 consecutive lattice sites of a row (4 of each colour), walks
+// XY_ROWS rows and keeps the previous row's cos/sin, so every site costs one sincos (+ 1/8 for the group edge)
+// instead of three.  Bonds: (x, x+1) inside the row, (y-1, y) against the previous row.
 __global__ void __launch_bounds__(256)
 xy_measure_kernel(const float* __restrict__ c0, const float* __restrict__ c1, int nxh, int ny, int gpr, double* acc)
 {
     double part[3] = {0.0, 0.0, 0.0};
-    const int total = ny * gpr;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int y = idx / gpr, g = idx - y * gpr, xi0 = 4 * g;
-        const int yu = (y + 1 == ny) ? 0 : y + 1;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nblk = (ny + XY_ROWS - 1) / XY_ROWS;
+    if (tid < nblk * gpr) {
+        const int rb = tid / gpr, g = tid - rb * gpr;
+        const int y0 = rb * XY_ROWS, y1 = min(y0 + XY_ROWS, ny);
+        float pc[8], ps[8], qc[8], qs[8];
+        float es = 0.f, mx = 0.f, my = 0.f;
+        // cos / sin of the 8 sites x0 = 8 g .. 8 g + 7 of row y, in lattice order: even x0 belong to colour (y & 1)
+        auto load_row = [&](int y, float (&c)[8], float (&sn)[8]) {
+            const float4 a = *reinterpret_cast<const float4*>(((y & 1) ? c1 : c0) + (size_t)y * nxh + 4 * g);
+            const float4 b = *reinterpret_cast<const float4*>(((y & 1) ? c0 : c1) + (size_t)y * nxh + 4 * g);
+            sincos_turns(a.x, sn[0], c[0]); sincos_turns(b.x, sn[1], c[1]);
+            sincos_turns(a.y, sn[2], c[2]); sincos_turns(b.y, sn[3], c[3]);
+            sincos_turns(a.z, sn[4], c[4]); sincos_turns(b.z, sn[5], c[5]);
+            sincos_turns(a.w, sn[6], c[6]); sincos_turns(b.w, sn[7], c[7]);
+        };
+        load_row(y0 == 0 ? ny - 1 : y0 - 1, pc, ps);
+        for (int y = y0; y < y1; ++y) {
+            load_row(y, qc, qs);
+            // the site right of the group: x0 = 8 g + 8 (periodic), an even x0 -> colour (y & 1), xi = 4 g + 4
+            const int xe = (4 * g + 4 == nxh) ? 0 : 4 * g + 4;
+            float ec, esn;
+            sincos_turns(((y & 1) ? c1 : c0)[(size_t)y * nxh + xe], esn, ec);
+            float e = qc[7] * ec + qs[7] * esn;
 #pragma unroll
-        for (int colour = 0; colour < 2; ++colour) {
-            const float* own = colour ? c1 : c0;
-            const float* oth = colour ? c0 : c1;
-            const int p = (y + colour) & 1;
-            const float4 o = *reinterpret_cast<const float4*>(own + (size_t)y * nxh + xi0);
-            const float4 b = *reinterpret_cast<const float4*>(oth + (size_t)y * nxh + xi0);
-            const float4 u = *reinterpret_cast<const float4*>(oth + (size_t)yu * nxh + xi0);
-            // x+1 neighbour of site j: p = 0 -> b[j]; p = 1 -> b[j+1] (wraps to column 0)
-            const float e = p ? oth[(size_t)y * nxh + (xi0 + 4 == nxh ? 0 : xi0 + 4)] : 0.0f;
-            const float rv[4] = {p ? b.y : b.x, p ? b.z : b.y, p ? b.w : b.z, p ? e : b.w};
-            const float ov[4] = {o.x, o.y, o.z, o.w}, uv[4] = {u.x, u.y, u.z, u.w};
-            float es = 0.f, mx = 0.f, my = 0.f;
+            for (int k = 0; k < 7; ++k) e += qc[k] * qc[k + 1] + qs[k] * qs[k + 1];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float s, c, rs, rc, us, uc;
-                sincos_turns(ov[j], s, c);
-                sincos_turns(rv[j], rs, rc);
-                sincos_turns(uv[j], us, uc);
-                es -= c * (rc + uc) + s * (rs + us);
-                mx += c;
-                my += s;
+            for (int k = 0; k < 8; ++k) {
+                e += pc[k] * qc[k] + ps[k] * qs[k];
+                mx += qc[k];
+                my += qs[k];
+                pc[k] = qc[k];
+                ps[k] = qs[k];
             }
-            part[0] += (double)es; part[1] += (double)mx; part[2] += (double)my;
+            es -= e;
         }
+        part[0] = (double)es; part[1] = (double)mx; part[2] = (double)my;
     }
     block_atomic_add_f64<3>(acc, part);
 }
@@ -384,7 +395,8 @@ int measure(XY* m)
     if (m->obs_valid) return B200MC_OK;
     CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
     COUNT_LAUNCH();
-    xy_measure_kernel<<<m->sms * 8, 256, 0, m->stream>>>(m->c[0], m->c[1], m->nxh, (int)m->ny, m->gpr, m->d_acc);
+    const int strips = (int)((m->ny + XY_ROWS - 1) / XY_ROWS) * m->gpr;
+    xy_measure_kernel<<<(strips + 255) / 256, 256, 0, m->stream>>>(m->c[0], m->c[1], m->nxh, (int)m->ny, m->gpr, m->d_acc);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(m->obs, m->d_acc, 3 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));

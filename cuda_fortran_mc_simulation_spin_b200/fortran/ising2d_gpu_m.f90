@@ -34,6 +34,7 @@ module ising2d_gpu_m
      !> additions (not in the reference type)
      procedure, pass :: set_method => set_method_ising2d_gpu   !< 0 Metropolis (default), 1 heat-bath
      procedure, pass :: update_n => update_n_ising2d_gpu       !< n MCS back to back
+     procedure, pass :: run_relaxation => run_relaxation_ising2d_gpu  !< mcs x [update; calc_magne_sum; calc_energy_sum] on the device
      final :: destroy_ising2d_gpu
   end type ising2d_gpu
 
@@ -68,6 +69,9 @@ module ising2d_gpu_m
      end function
      integer(c_int) function b200mc_ising2d_update_n(h, n) bind(C, name="b200mc_ising2d_update_n")
        import; type(c_ptr), value :: h; integer(c_int32_t), value :: n
+     end function
+     integer(c_int) function b200mc_ising2d_run_relaxation(h, mcs, e, m) bind(C, name="b200mc_ising2d_run_relaxation")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: mcs; integer(c_int64_t), intent(out) :: e(*), m(*)
      end function
      integer(c_int) function b200mc_ising2d_calc_energy_sum(h, e) bind(C, name="b200mc_ising2d_calc_energy_sum")
        import; type(c_ptr), value :: h; integer(c_int64_t), intent(out) :: e
@@ -148,6 +152,14 @@ contains
     class(ising2d_gpu), intent(inout) :: this
     ising2d_gpu_stat = b200mc_ising2d_update(this%h_)
   end subroutine update_ising2d_gpu
+  !> the drivers' inner loop (app/ising2d_gpu_relaxation.f90) without a host round trip per MCS:
+  !> e(i), m(i) = calc_energy_sum(), calc_magne_sum() after MCS i
+  impure subroutine run_relaxation_ising2d_gpu(this, mcs, e, m)
+    class(ising2d_gpu), intent(inout) :: this
+    integer(int32), intent(in) :: mcs
+    integer(int64), intent(out) :: e(mcs), m(mcs)
+    ising2d_gpu_stat = b200mc_ising2d_run_relaxation(this%h_, mcs, e, m)
+  end subroutine run_relaxation_ising2d_gpu
   impure subroutine update_n_ising2d_gpu(this, n_sweeps)
     class(ising2d_gpu), intent(inout) :: this
     integer(int32), intent(in) :: n_sweeps

@@ -70,6 +70,9 @@ int b200mc_ising3d_update_with_randoms(void* h, const double* randoms);
 int b200mc_ising3d_calc_energy_sum(void* h, int64_t* e); /* :239-257 */
 int b200mc_ising3d_calc_magne_sum(void* h, int64_t* m);  /* :259-276 */
 int b200mc_ising3d_measure(void* h, int64_t* e, int64_t* m); /* both, one pass */
+/* the drivers' inner loop (app/ising3d_gpu_relaxation.f90:40-46) on the device: mcs x [update; calc_magne_sum;
+ * calc_energy_sum]; e[i], m[i] = the sums after MCS i+1 (either may be NULL).  One host synchronisation in all. */
+int b200mc_ising3d_run_relaxation(void* h, int32_t mcs, int64_t* e, int64_t* m);
 /* spins(), :232-236: int32 0/1, layout spins(1-nxy : nall+nxy) -> nall + 2 nxy elements */
 int b200mc_ising3d_get_spins(void* h, int32_t* out);
 int b200mc_ising3d_set_spins(void* h, const int32_t* in); /* inverse (halo cells of `in` ignored) */
@@ -140,6 +143,7 @@ int b200mc_ising2d_update_with_randoms(void* h, const double* randoms);
 int b200mc_ising2d_calc_energy_sum(void* h, int64_t* e); /* :198-212 */
 int b200mc_ising2d_calc_magne_sum(void* h, int64_t* m);  /* :214-228 */
 int b200mc_ising2d_measure(void* h, int64_t* e, int64_t* m);
+int b200mc_ising2d_run_relaxation(void* h, int32_t mcs, int64_t* e, int64_t* m); /* app/ising2d_gpu_relaxation.f90:38-43 */
 /* spins(), :184-188: int32 +1/-1, layout spins(1-nx : nall+nx) -> nall + 2 nx elements */
 int b200mc_ising2d_get_spins(void* h, int32_t* out);
 int b200mc_ising2d_set_spins(void* h, const int32_t* in);

@@ -94,6 +94,14 @@ def main():
         assert np.array_equal(sp, g1.spins())
         print("slab ok: interleaved run == 1-GPU run, transport", os.environ.get("B200MC_SLAB_TRANSPORT", "p2p"),
               "p2p active:", getattr(g, "_p2p", False), flush=True)
+    # the device-side driver loop through the slab path: one all-reduce of the whole series
+    g = ising3d_gpu_m.ising3d_gpu().init_distributed(31, 31, 64 * world, KBT3, 3)
+    e, m = g.run_relaxation(5)
+    o = O.ising3d_gpu().init(31, 31, 64 * world, KBT3, 3)
+    for i in range(5):
+        o.update()
+        assert (int(e[i]), int(m[i])) == (o.calc_energy_sum(), o.calc_magne_sum()), i
+    assert np.array_equal(g.spins(), o.spins())
     dist.barrier()
     dist.destroy_process_group()
 

@@ -237,3 +237,22 @@ def test_fused_measurement_equals_separate_pass(oracle, dim, method):
         assert g.measure() == em
     g.update(); g.update(); step(); step()             # first result never read: no stale sums afterwards
     assert g.measure() == (o.calc_energy_sum(), o.calc_magne_sum())
+
+
+@pytest.mark.parametrize("dim,shape", [(3, (63, 65, 64)), (3, (31, 31, 30)), (2, (255, 256)), (2, (1001, 1000))])
+def test_run_relaxation_series(oracle, dim, shape):
+    """the drivers' loop on the device: per-MCS E and M series == update + measure step by step (fused second-pass
+    sums where Nc % 16 == 0, the measure kernel otherwise), and the state afterwards is the same"""
+    i2, i3 = _mods()
+    if dim == 3:
+        g = i3.ising3d_gpu().init(*shape, KBT3, 9); o = oracle.ising3d_gpu().init(*shape, KBT3, 9)
+    else:
+        g = i2.ising2d_gpu().init(*shape, KBT2, 9); o = oracle.ising2d_gpu().init(*shape, KBT2, 9)
+    e, m = g.run_relaxation(6)
+    for i in range(6):
+        o.update()
+        assert (int(e[i]), int(m[i])) == (o.calc_energy_sum(), o.calc_magne_sum()), i
+    assert np.array_equal(g.spins(), o.spins())
+    assert g.measure() == (int(e[-1]), int(m[-1]))
+    g.update(); o.update()
+    assert g.measure() == (o.calc_energy_sum(), o.calc_magne_sum())
