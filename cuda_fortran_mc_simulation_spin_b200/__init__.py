@@ -9,6 +9,9 @@ procedure names) over the C ABI of ``libb200mc.so``:
     clock_gpu_m.clock_gpu            src/clock_gpu_m.f90
     clock_gpu_multi_m.clock_gpu      src/clock_gpu_multi_m.f90
     clock_tableall_gpu_m             src/clock/clock_tableall_gpu_m.f90
+    clock_dual_lattice_tableall_gpu_m  src/clock/clock_dual_lattice_tableall_m.f90
+    clock_table_gpu_m, clock_simple_gpu_m  src/clock/clock_table_gpu_m.f90, clock_simple_gpu_m.f90
     xy2d_periodic_gpu_m.xy2d_gpu     src/xy2d_periodic_gpu_m.f90
+    xy2d_gpu_m.xy2d_gpu              src/xy2d_gpu_m.f90 (helical boundary)
 """
 from ._lib import B200MCError, SO_PATH, build  # noqa: F401

@@ -11,10 +11,10 @@ from ._lib import P, PP, f64, i32, i64
 
 
 class sixclock:
-    def __init__(self, nx, ny, kbt, mstate=6, n_multi=1, iseed=42):
+    def __init__(self, nx, ny, kbt, mstate=6, n_multi=1, iseed=42, variant=0):
         self._h = C.c_void_p(None)
-        f = _lib.fn("b200mc_sixclock_create", C.c_int, PP, i64, i64, f64, i32, i32, i32)
-        _lib.check(f(C.byref(self._h), int(nx), int(ny), float(kbt), int(mstate), int(n_multi), int(iseed)))
+        f = _lib.fn("b200mc_sixclock_create_variant", C.c_int, PP, i64, i64, f64, i32, i32, i32, i32)
+        _lib.check(f(C.byref(self._h), int(nx), int(ny), float(kbt), int(mstate), int(n_multi), int(iseed), int(variant)))
 
     def _call(self, name, *args, argtypes=()):
         f = _lib.fn(f"b200mc_sixclock_{name}", C.c_int, P, *argtypes)

@@ -377,6 +377,7 @@ __global__ void sixclock_import_half_kernel(uint8_t* c, int nxh, int ny, size_t 
 struct Six {
     int64_t nx, ny;
     int32_t q, n_multi;
+    int variant;                 // 0: tableall / table delta-E expression, 1: clock_simple's
     int nxh, nvr;
     size_t pitch, rep_bytes;     // bytes per row / per replica per colour
     uint8_t* c[2];
@@ -425,7 +426,18 @@ int build_tables(Six* m)
                 for (int r = 0; r < q; ++r)
                     for (int nc = 0; nc < q; ++nc)
                         for (int c = 0; c < q; ++c) {
-                            const double de = E3(nc, r, u) - E3(c, r, u) + E3(nc, l, d) - E3(c, l, d);
+                            double de;
+                            if (m->variant == 0) {
+                                de = E3(nc, r, u) - E3(c, r, u) + E3(nc, l, d) - E3(c, l, d);
+                            } else {
+                                // clock_simple_gpu_m update_sub, src/clock/clock_simple_gpu_m.f90:108-113: no tables, the
+                                // four neighbours in the order right, left, up, down (nearest_spins(1:4), :83-99)
+                                const int nbv[4] = {r, l, u, d};
+                                de = 0.0;
+                                for (int i = 0; i < 4; ++i) de = de + (-cos((nbv[i] - nc) * psi) + cos((nbv[i] - c) * psi));
+                            }
+                            // tableall: prob = 1 if dE <= 0 (:76-80); table / simple: accepted outright unless dE > 0
+                            // (clock_table_gpu_m.f90:123-125) -- the same predicate
                             const double w = (de <= 0.0) ? 1.0 : exp(-m->beta * de);
                             const size_t at = (size_t)c + (size_t)q * (nc + (size_t)q * (r + (size_t)q * (u + (size_t)q * (l + (size_t)q * d))));
                             m->prob[at] = w;
@@ -553,6 +565,12 @@ extern "C" {
 
 int b200mc_sixclock_create(void** out, int64_t nx, int64_t ny, double kbt, int32_t mstate, int32_t n_multi, int32_t iseed)
 {
+    return b200mc_sixclock_create_variant(out, nx, ny, kbt, mstate, n_multi, iseed, 0);
+}
+int b200mc_sixclock_create_variant(void** out, int64_t nx, int64_t ny, double kbt, int32_t mstate, int32_t n_multi, int32_t iseed,
+                                   int32_t variant)
+{
+    if (variant != 0 && variant != 1) ARG_FAIL("sixclock: unknown variant %d", variant);
     if (!out) ARG_FAIL("null handle pointer");
     *out = nullptr;
     if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0");
@@ -570,7 +588,7 @@ int b200mc_sixclock_create(void** out, int64_t nx, int64_t ny, double kbt, int32
     if ((double)n_multi * (double)ny * (double)nvr >= 2147483000.0) ARG_FAIL("sixclock: lattice x batch too large for 32-bit vector indices");
     Six* m = new (std::nothrow) Six();
     if (!m) ARG_FAIL("out of host memory");
-    m->nx = nx; m->ny = ny; m->q = mstate; m->n_multi = n_multi; m->nxh = (int)nxh; m->nvr = (int)nvr;
+    m->nx = nx; m->ny = ny; m->q = mstate; m->n_multi = n_multi; m->nxh = (int)nxh; m->nvr = (int)nvr; m->variant = variant;
     m->pitch = (size_t)nvr * 16; m->rep_bytes = m->pitch * (size_t)ny;
     m->stream = 0; m->seed = (uint32_t)iseed; m->draw = 0; m->beta = 1 / kbt; m->obs_valid = false;
     m->c[0] = m->c[1] = nullptr; m->d_cls = nullptr; m->d_thi = m->d_tlo = nullptr; m->d_prob = nullptr; m->d_rnds = nullptr;

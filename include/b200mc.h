@@ -211,6 +211,10 @@ int b200mc_clock_sync(void* h);
  * nx and ny must be even.
  * ------------------------------------------------------------------------ */
 int b200mc_sixclock_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t mstate, int32_t n_multi, int32_t iseed); /* init_sixclock :57-88 */
+/* variant 0: the delta-E expression of clock_tableall_gpu_m (:72-75) and clock_table_gpu_m (src/clock/clock_table_gpu_m.f90:
+ * 119-122, same expression evaluated per site); variant 1: clock_simple_gpu_m's sum over the four neighbours
+ * (src/clock/clock_simple_gpu_m.f90:108-113) -- the two differ in the last bits of delta-E, hence in the table */
+int b200mc_sixclock_create_variant(void** h, int64_t nx, int64_t ny, double kbt, int32_t mstate, int32_t n_multi, int32_t iseed, int32_t variant);
 int b200mc_sixclock_destroy(void* h);
 int b200mc_sixclock_set_stream(void* h, void* cuda_stream);
 int b200mc_sixclock_skip_curand_clock(void* h, int64_t n_skip);   /* :51-55 */
@@ -295,6 +299,36 @@ int64_t b200mc_xy2d_nall(void* h);
 double b200mc_xy2d_kbt(void* h);
 double b200mc_xy2d_beta(void* h);
 int b200mc_xy2d_sync(void* h);
+
+/* ------------------------------------------------------------------------
+ * XY 2D, helical boundary -- type(xy2d_gpu) of module xy2d_gpu_m, src/xy2d_gpu_m.f90:12-43
+ * (SURVEY 8 f3).  Linear-index colouring like ising2d_gpu_m: nx odd, ny even REQUIRED.
+ * State: one fp32 angle (turns) per site; E and Mx are real64 sums (1e-5 relative vs the reference).
+ * ------------------------------------------------------------------------ */
+int b200mc_xy2dh_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed);  /* init, :45-62 */
+int b200mc_xy2dh_destroy(void* h);
+int b200mc_xy2dh_set_stream(void* h, void* cuda_stream);
+int b200mc_xy2dh_skip_curand(void* h, int64_t n_skip);                /* :63-68 */
+int b200mc_xy2dh_set_allup_spin(void* h);                             /* :70-88 */
+int b200mc_xy2dh_set_random_spin(void* h);                            /* :90-105 */
+int b200mc_xy2dh_set_kbt(void* h, double kbt);                        /* :127-131 */
+int b200mc_xy2dh_set_beta(void* h, double beta);                      /* :133-137 */
+int b200mc_xy2dh_update(void* h);                                     /* :138-174 */
+int b200mc_xy2dh_update_n(void* h, int32_t n_sweeps);
+int b200mc_xy2dh_update_over_relaxation(void* h, int32_t n_steps);    /* :176-213 */
+int b200mc_xy2dh_calc_energy_sum(void* h, double* e);                 /* :259-276 */
+int b200mc_xy2dh_calc_magne_sum(void* h, double* mx);                 /* :278-291 */
+/* spins(), :236-240: real64 (cos, sin), layout spins(1-nx : nall+nx, 1:2) -> 2 (nall + 2 nx) doubles, halo refreshed */
+int b200mc_xy2dh_get_spins(void* h, double* out);
+/* native state: angles in turns, fp32, linear index order [nall] */
+int b200mc_xy2dh_get_angles(void* h, float* out);
+int b200mc_xy2dh_set_angles(void* h, const float* in);
+int64_t b200mc_xy2dh_nx(void* h);
+int64_t b200mc_xy2dh_ny(void* h);
+int64_t b200mc_xy2dh_nall(void* h);
+double b200mc_xy2dh_kbt(void* h);
+double b200mc_xy2dh_beta(void* h);
+int b200mc_xy2dh_sync(void* h);
 
 #pragma GCC visibility pop
 #ifdef __cplusplus

@@ -402,6 +402,7 @@ ORC_API double orc_clock_energy(int64_t nx, int64_t ny, int32_t q, const int32_t
 ORC_API double orc_clock_magne(int64_t nx, int64_t ny, int32_t q, const int32_t *s,
                                const double *magne)
 {
+    (void)q;
     const int64_t nall = nx * ny;
     double res = 0.0;
     for (int64_t i = 1; i <= nall; ++i) res += magne[CK(i)];
@@ -462,6 +463,29 @@ ORC_API void orc_tableall_tables(int32_t q, double beta, double *magne, double *
                             prob[at] = (de <= 0.0) ? 1.0 : exp(-beta * de);
                         }
 #undef E3
+}
+
+/* clock_simple_gpu_m: no tables; delta_e accumulated over nearest_spins(1:4) = right, left, up, down
+ * (src/clock/clock_simple_gpu_m.f90:83-113).  Tabulated here in the states_to_prob index order so that
+ * orc_tableall_update can consume it: prob[c + q*(n + q*(r + q*(u + q*(l + q*d))))]. */
+ORC_API void orc_clock_simple_prob(int32_t q, double beta, double *prob)
+{
+    const double pi = 4 * atan(1.0);
+    const double psi = 2 * pi / q;
+    for (int d = 0; d < q; ++d)
+        for (int l = 0; l < q; ++l)
+            for (int u = 0; u < q; ++u)
+                for (int r = 0; r < q; ++r)
+                    for (int n = 0; n < q; ++n)
+                        for (int c = 0; c < q; ++c) {
+                            const int nb[4] = {r, l, u, d};
+                            double de = 0.0;
+                            for (int i = 0; i < 4; ++i)
+                                de = de + (-cos((nb[i] - n) * psi) + cos((nb[i] - c) * psi));
+                            size_t at = (size_t)c +
+                                        (size_t)q * (n + (size_t)q * (r + (size_t)q * (u + (size_t)q * (l + (size_t)q * d))));
+                            prob[at] = (de > 0) ? exp(-beta * de) : 1.0;
+                        }
 }
 
 #define TA(x, y) c[((x)-1) + nx * ((y)-1)]
@@ -784,3 +808,118 @@ ORC_API void orc_xy_metropolis_by_field(int64_t nx, int64_t ny, double *sp, cons
 }
 #undef XS
 #undef XR
+
+/* ==========================================================================
+ * XY 2D helical  (src/xy2d_gpu_m.f90, module xy2d_gpu_m): the XY analogue of ising2d_gpu_m.
+ * storage: spins(1-nx : nall+nx, 1:2) real64 (cos, sin), column-major:
+ *   S(i, k) = sp[(i - 1 + nx) + len*(k-1)],  len = nall + 2 nx;  colour = parity of the linear index i.
+ * randoms(1:nall), candidates(1:nall): r[i-1].
+ * ========================================================================== */
+#define HS(i, k) sp[((i)-1 + nx) + len * ((k)-1)]
+
+/* update_norishiro_sub, :114-125 */
+ORC_API void orc_xyh_norishiro(int64_t nx, int64_t ny, double *sp)
+{
+    const int64_t nall = nx * ny, len = nall + 2 * nx;
+    for (int k = 1; k <= 2; ++k)
+        for (int64_t idx = 1; idx <= nx; ++idx) {
+            HS(nall + idx, k) = HS(idx, k);
+            HS(idx - nx, k) = HS(nall - nx + idx, k);
+        }
+}
+
+/* set_allup_spin_sub, :79-88 (halo cells included) */
+ORC_API void orc_xyh_set_allup(int64_t nx, int64_t ny, double *sp)
+{
+    const int64_t len = nx * ny + 2 * nx;
+    for (int64_t j = 0; j < len; ++j) { sp[j] = 1.0; sp[len + j] = 0.0; }
+}
+
+/* set_random_spin_xy2d_gpu, :90-105 */
+ORC_API void orc_xyh_set_random(int64_t nx, int64_t ny, double *sp, const double *randoms)
+{
+    const int64_t nall = nx * ny, len = nall + 2 * nx;
+    const double pi = 4 * atan(1.0);
+    for (int64_t idx = 1; idx <= nall; ++idx) {
+        HS(idx, 1) = cos(2 * pi * randoms[idx - 1]);
+        HS(idx, 2) = sin(2 * pi * randoms[idx - 1]);
+    }
+    orc_xyh_norishiro(nx, ny, sp);
+}
+
+/* update_sub :157-174 with calc_delta_energy :243-252; offset 1 = odd linear indices, 2 = even */
+static void xyh_pass(int64_t nx, int64_t ny, double *sp, double beta, const double *randoms,
+                     const double *candidates, int offset)
+{
+    const int64_t nall = nx * ny, len = nall + 2 * nx;
+    const double pi = 4 * atan(1.0);
+#pragma omp parallel for schedule(static)
+    for (int64_t idx = offset; idx <= nall; idx += 2) {
+        double c1 = cos(2 * pi * candidates[idx - 1]);
+        double c2 = sin(2 * pi * candidates[idx - 1]);
+        double d1 = c1 - HS(idx, 1), d2 = c2 - HS(idx, 2);
+        double n1 = HS(idx - 1, 1) + HS(idx + 1, 1) + HS(idx + nx, 1) + HS(idx - nx, 1);
+        double n2 = HS(idx - 1, 2) + HS(idx + 1, 2) + HS(idx + nx, 2) + HS(idx - nx, 2);
+        double de = -(d1 * n1 + d2 * n2);
+        if (randoms[idx - 1] > exp(-beta * de)) continue;
+        HS(idx, 1) = c1;
+        HS(idx, 2) = c2;
+    }
+}
+
+/* update_xy2d_gpu, :138-156 */
+ORC_API void orc_xyh_update(int64_t nx, int64_t ny, double *sp, double beta, const double *randoms,
+                            const double *candidates)
+{
+    xyh_pass(nx, ny, sp, beta, randoms, candidates, 1);
+    orc_xyh_norishiro(nx, ny, sp);
+    xyh_pass(nx, ny, sp, beta, randoms, candidates, 2);
+    orc_xyh_norishiro(nx, ny, sp);
+}
+
+/* over_relaxation_sub, :198-213 (no renormalisation in this module) */
+static void xyh_or_pass(int64_t nx, int64_t ny, double *sp, int offset)
+{
+    const int64_t nall = nx * ny, len = nall + 2 * nx;
+#pragma omp parallel for schedule(static)
+    for (int64_t idx = offset; idx <= nall; idx += 2) {
+        double h1 = HS(idx - 1, 1) + HS(idx + 1, 1) + HS(idx + nx, 1) + HS(idx - nx, 1);
+        double h2 = HS(idx - 1, 2) + HS(idx + 1, 2) + HS(idx + nx, 2) + HS(idx - nx, 2);
+        double inv = 1 / hypot(h1, h2);
+        h1 = h1 * inv;
+        h2 = h2 * inv;
+        double dot2 = 2 * (h1 * HS(idx, 1) + h2 * HS(idx, 2));
+        double s1 = dot2 * h1 - HS(idx, 1), s2 = dot2 * h2 - HS(idx, 2);
+        HS(idx, 1) = s1;
+        HS(idx, 2) = s2;
+    }
+}
+
+/* update_over_relaxation_xy2d_gpu, :176-196 */
+ORC_API void orc_xyh_over_relaxation(int64_t nx, int64_t ny, double *sp, int32_t n_steps)
+{
+    for (int i = 0; i < n_steps; ++i) {
+        xyh_or_pass(nx, ny, sp, 1);
+        orc_xyh_norishiro(nx, ny, sp);
+        xyh_or_pass(nx, ny, sp, 2);
+        orc_xyh_norishiro(nx, ny, sp);
+    }
+}
+
+/* calc_energy_sum :259-276, calc_magne_sum :278-291 */
+ORC_API double orc_xyh_energy(int64_t nx, int64_t ny, const double *sp)
+{
+    const int64_t nall = nx * ny, len = nall + 2 * nx;
+    double res = 0.0;
+    for (int k = 1; k <= 2; ++k)
+        for (int64_t i = 1; i <= nall; ++i) res -= HS(i, k) * (HS(i + 1, k) + HS(i + nx, k));
+    return res;
+}
+ORC_API double orc_xyh_magne(int64_t nx, int64_t ny, const double *sp)
+{
+    const int64_t nall = nx * ny, len = nall + 2 * nx;
+    double res = 0.0;
+    for (int64_t i = 1; i <= nall; ++i) res += HS(i, 1);
+    return res;
+}
+#undef HS

@@ -86,6 +86,7 @@ def _declare(L):
     d("orc_clock_histograms", None, i64, i64, i32, P, P, P)
     d("orc_tableall_tables", None, i32, f64, P, P, P)
     d("orc_tableall_update", None, i64, i64, i32, P, P, P)
+    d("orc_clock_simple_prob", None, i32, f64, P)
     d("orc_tableall_magne", f64, i64, i64, i32, P, P)
     d("orc_tableall_energy", f64, i64, i64, i32, P, P)
     d("orc_tableall_histograms", None, i64, i64, i32, P, P, P)
@@ -110,6 +111,15 @@ def _declare(L):
     d("orc_xy_uniforms", None, u32, u64, i64, i64, P, P)
     d("orc_xy_init_uniforms", None, u32, u64, i64, i64, P)
     d("orc_torus_uniforms", None, u32, u64, i32, i64, i64, P)
+    d("orc_xyh_norishiro", None, i64, i64, P)
+    d("orc_xyh_set_allup", None, i64, i64, P)
+    d("orc_xyh_set_random", None, i64, i64, P, P)
+    d("orc_xyh_update", None, i64, i64, P, f64, P, P)
+    d("orc_xyh_over_relaxation", None, i64, i64, P, i32)
+    d("orc_xyh_energy", f64, i64, i64, P)
+    d("orc_xyh_magne", f64, i64, i64, P)
+    d("orc_xyh_uniforms", None, u32, u64, i64, P, P)
+    d("orc_xyh_init_uniforms", None, u32, u64, i64, P)
 
 
 def _p(a: np.ndarray):
@@ -174,6 +184,19 @@ def torus_uniforms(seed: int, draw: int, replica: int, nx: int, ny: int) -> np.n
     out = np.empty(2 * nx * ny, dtype=np.float64)
     lib().orc_torus_uniforms(seed & 0xFFFFFFFF, draw, replica, nx, ny, _p(out))
     return out
+
+
+def xyh_uniforms(seed: int, draw: int, n_sites: int):
+    r = np.empty(n_sites, dtype=np.float64)
+    c = np.empty(n_sites, dtype=np.float64)
+    lib().orc_xyh_uniforms(seed & 0xFFFFFFFF, draw, n_sites, _p(r), _p(c))
+    return r, c
+
+
+def xyh_init_uniforms(seed: int, draw: int, n_sites: int):
+    r = np.empty(n_sites, dtype=np.float64)
+    lib().orc_xyh_init_uniforms(seed & 0xFFFFFFFF, draw, n_sites, _p(r))
+    return r
 
 
 def xy_init_uniforms(seed: int, draw: int, nx: int, ny: int):
@@ -438,6 +461,14 @@ class clock_tableall:
         return hist, pair.reshape(q, q)
 
 
+class clock_simple(clock_tableall):
+    """src/clock/clock_simple_gpu_m.f90: same model, delta-E summed over the four neighbours on the fly"""
+
+    def __init__(self, nx, ny, kbt, mstate=6):
+        super().__init__(nx, ny, kbt, mstate)
+        lib().orc_clock_simple_prob(self.q, self.beta, _p(self.prob))
+
+
 class clock_dual_lattice(clock_tableall):
     """src/clock/clock_dual_lattice_tableall_m.f90: same model, compact colour arrays."""
 
@@ -539,3 +570,52 @@ class xy2d_gpu:
     def calc_magne_y_sum(self): return lib().orc_xy_magne(self.nx_, self.ny_, _p(self.sp), 2)
     def calc_autocorrelation_sum(self): return lib().orc_xy_autocorrelation(self.nx_, self.ny_, _p(self.sp), _p(self.sp0))
     def calc_correlation_sum(self): return lib().orc_xy_correlation(self.nx_, self.ny_, _p(self.sp))
+
+
+# --------------------------------------------------------------------------
+# XY helical (module xy2d_gpu_m, src/xy2d_gpu_m.f90:12-43)
+# --------------------------------------------------------------------------
+class xy2d_helical_gpu:
+    def init(self, nx, ny, kbt, iseed):
+        self.nx_, self.ny_ = int(nx), int(ny)
+        self.nall_ = self.nx_ * self.ny_
+        self.seed_ = int(iseed)
+        # spins(1-nx : nall+nx, 1:2) column-major == C array [2][nall + 2 nx]
+        self.sp = np.zeros((2, self.nall_ + 2 * self.nx_), dtype=np.float64)
+        self.set_allup_spin()
+        self.set_kbt(kbt)
+        return self
+
+    def set_allup_spin(self): lib().orc_xyh_set_allup(self.nx_, self.ny_, _p(self.sp))
+
+    def set_random_spin(self, randoms):
+        randoms = np.ascontiguousarray(randoms, dtype=np.float64)
+        lib().orc_xyh_set_random(self.nx_, self.ny_, _p(self.sp), _p(randoms))
+
+    def set_angles(self, theta):
+        """test helper: interior spins from nall angles (linear index order), halo refreshed"""
+        th = np.asarray(theta, dtype=np.float64).reshape(-1)
+        nx = self.nx_
+        self.sp[0, nx:nx + self.nall_] = np.cos(th)
+        self.sp[1, nx:nx + self.nall_] = np.sin(th)
+        lib().orc_xyh_norishiro(self.nx_, self.ny_, _p(self.sp))
+
+    def set_kbt(self, kbt): self.beta_ = 1 / float(kbt)
+    def set_beta(self, beta): self.beta_ = float(beta)
+
+    def update(self, randoms, candidates):
+        randoms = np.ascontiguousarray(randoms, dtype=np.float64)
+        candidates = np.ascontiguousarray(candidates, dtype=np.float64)
+        lib().orc_xyh_update(self.nx_, self.ny_, _p(self.sp), self.beta_, _p(randoms), _p(candidates))
+
+    def update_over_relaxation(self, n_steps):
+        lib().orc_xyh_over_relaxation(self.nx_, self.ny_, _p(self.sp), int(n_steps))
+
+    def nx(self): return self.nx_
+    def ny(self): return self.ny_
+    def nall(self): return self.nall_
+    def kbt(self): return 1 / self.beta_
+    def beta(self): return self.beta_
+    def spins(self): return self.sp.copy()
+    def calc_energy_sum(self): return lib().orc_xyh_energy(self.nx_, self.ny_, _p(self.sp))
+    def calc_magne_sum(self): return lib().orc_xyh_magne(self.nx_, self.ny_, _p(self.sp))

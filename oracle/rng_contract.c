@@ -252,3 +252,39 @@ ORC_API void orc_torus_uniforms(uint32_t seed, uint64_t draw, int32_t replica, i
             rnds[1 + 2 * (x0 + nx * y0)] = ((double)Ua + 1.0) * 0x1p-32;
         }
 }
+
+/* --------------------------------------------------------------------------
+ * XY helical (xy2d_gpu_m): ring of N sites, colour = i & 1 (i = idx - 1), colour-site index k = i >> 1;
+ * a group is 4 consecutive k: blk = k >> 2.  Two 32-bit uniforms per site and sweep:
+ *   R = philox(ctr(blk, draw, colour, (k & 3) >> 1), (seed, TAG_XYH))
+ *   accept U_r = R[2 * (k & 1)] -> randoms(idx) ;  candidate U_c = R[2 * (k & 1) + 1] -> candidates(idx)
+ * set_random_spin: R = philox(ctr(blk, draw, colour, 0), (seed, TAG_INIT)), U = R[k & 3].
+ * -------------------------------------------------------------------------- */
+#define TAG_XYH 0x5859484Cu /* "XYHL" */
+ORC_API void orc_xyh_uniforms(uint32_t seed, uint64_t draw, int64_t n_sites, double *randoms, double *candidates)
+{
+    const uint32_t key[2] = {seed, TAG_XYH};
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_sites; ++i) {
+        const uint32_t colour = (uint32_t)(i & 1);
+        const int64_t k = i >> 1;
+        uint32_t c[4], r[4];
+        mk_ctr(c, (uint64_t)(k >> 2), draw, colour, (uint32_t)((k & 3) >> 1));
+        orc_philox4x32_10(c, key, r);
+        randoms[i] = ((double)r[2 * (k & 1)] + 1.0) * 0x1p-32;
+        candidates[i] = ((double)r[2 * (k & 1) + 1] + 1.0) * 0x1p-32;
+    }
+}
+ORC_API void orc_xyh_init_uniforms(uint32_t seed, uint64_t draw, int64_t n_sites, double *out)
+{
+    const uint32_t key[2] = {seed, TAG_INIT};
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_sites; ++i) {
+        const uint32_t colour = (uint32_t)(i & 1);
+        const int64_t k = i >> 1;
+        uint32_t c[4], r[4];
+        mk_ctr(c, (uint64_t)(k >> 2), draw, colour, 0);
+        orc_philox4x32_10(c, key, r);
+        out[i] = ((double)r[k & 3] + 1.0) * 0x1p-32;
+    }
+}

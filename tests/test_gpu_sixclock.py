@@ -141,3 +141,26 @@ def test_module_procedure_mirrors(oracle):
         assert abs(T.calc_magne() - o.calc_magne()) <= 1e-12 and abs(T.calc_energy() - o.calc_energy()) <= 1e-12
         assert T.calc_magne() == D.calc_magne() and T.calc_energy() == D.calc_energy()
     assert np.array_equal(T.sixclock(), o.c)
+
+
+def test_clock_table_and_simple_variants(oracle):
+    """f4: clock_table_gpu_m evaluates tableall's delta-E expression per site (same decisions);
+    clock_simple_gpu_m sums over the four neighbours (src/clock/clock_simple_gpu_m.f90:108-113) -- a table
+    that differs from tableall's in the last bits, reproduced bit for bit"""
+    from cuda_fortran_mc_simulation_spin_b200 import clock_simple_gpu_m as S
+    from cuda_fortran_mc_simulation_spin_b200 import clock_table_gpu_m as T
+    nx, ny = 72, 20
+    for mod in (S, T):
+        mod.configure(nx_=nx, ny_=ny, kbt_=0.91)
+        mod.init_sixclock(42)
+        mod.init_sixclock_order()
+    os_, ot = oracle.clock_simple(nx, ny, 0.91, 6), oracle.clock_tableall(nx, ny, 0.91, 6)
+    assert np.array_equal(S.handle().states_to_prob(), os_.prob)
+    assert np.array_equal(T.handle().states_to_prob(), ot.prob)
+    assert not np.array_equal(os_.prob, ot.prob) and np.allclose(os_.prob, ot.prob, rtol=1e-14, atol=0)
+    for i in range(4):
+        r = oracle.torus_uniforms(42, i, 0, nx, ny)
+        S.update_metropolis(); T.update_metropolis()
+        os_.update_metropolis(r); ot.update_metropolis(r)
+        assert np.array_equal(S.sixclock(), os_.c) and np.array_equal(T.sixclock(), ot.c)
+        assert abs(S.calc_energy() - os_.calc_energy()) <= 1e-12 and abs(S.calc_magne() - os_.calc_magne()) <= 1e-12
