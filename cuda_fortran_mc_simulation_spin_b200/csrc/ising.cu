@@ -38,6 +38,8 @@ struct Ising {
     int tune;  // debug knobs from env B200MC_TUNE: bit0 = static round-robin (no ticket)
     int chunk; // vectors per ticket (env B200MC_CHUNK, default 128)
     int grid;
+    bool use_tma;   // single-GPU launches go through the copy-engine staged kernel
+    int tma_grid;
     bool alive;
     // observables cache: valid until the configuration changes
     bool obs_valid;
@@ -153,7 +155,15 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bo
     }
     COUNT_LAUNCH();
 #define PASS(METHOD, ORD, MEAS) ising_pass_kernel<NNB, METHOD, ORD, false, MEAS><<<grid, 256, 0, m->stream>>>(a, m->tab)
-    if (m->method == METHOD_METROPOLIS) {
+    if (a.ticket && m->use_tma) {
+        // copy-engine staging (ising_pass_tma_kernel): full tickets through cp.async.bulk, 2 blocks per SM
+        const size_t smem = (size_t)TMA_STAGES * NNB * TMA_SLOT;
+        const int tgrid = (int)(need < (int64_t)m->tma_grid ? need : (int64_t)m->tma_grid);  // 256 vectors per block and tile
+#define TPASS(METHOD, MEAS) ising_pass_tma_kernel<NNB, METHOD, MEAS><<<tgrid, 288, smem, m->stream>>>(a, m->tab)
+        if (m->method == METHOD_METROPOLIS) { if (fuse) TPASS(METHOD_METROPOLIS, true); else TPASS(METHOD_METROPOLIS, false); }
+        else { if (fuse) TPASS(METHOD_HEATBATH, true); else TPASS(METHOD_HEATBATH, false); }
+#undef TPASS
+    } else if (m->method == METHOD_METROPOLIS) {
         if (a.ticket) { if (fuse) PASS(METHOD_METROPOLIS, true, true); else PASS(METHOD_METROPOLIS, true, false); }
         else { if (fuse) PASS(METHOD_METROPOLIS, false, true); else PASS(METHOD_METROPOLIS, false, false); }
     } else {
@@ -462,6 +472,28 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     if (occ < 1) occ = 1;
     int64_t need = (m->st.g.Lloc + 255) / 256;
     m->grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);
+    m->use_tma = false; m->tma_grid = 0;
+    if (nranks == 1 && (m->tune & 128)) {
+        // opt in to the maximum dynamic shared memory of the staged kernels and size their grid
+        const int smem = TMA_STAGES * m->st.g.nnb * TMA_SLOT;
+        cudaError_t e;
+        int tocc = 0;
+        if (ndim == 3) {
+            e = cudaFuncSetAttribute(ising_pass_tma_kernel<6, METHOD_METROPOLIS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(ising_pass_tma_kernel<6, METHOD_METROPOLIS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(ising_pass_tma_kernel<6, METHOD_HEATBATH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(ising_pass_tma_kernel<6, METHOD_HEATBATH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e == cudaSuccess) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tocc, ising_pass_tma_kernel<6, METHOD_METROPOLIS, false>, 288, smem);
+        } else {
+            e = cudaFuncSetAttribute(ising_pass_tma_kernel<4, METHOD_METROPOLIS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(ising_pass_tma_kernel<4, METHOD_METROPOLIS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(ising_pass_tma_kernel<4, METHOD_HEATBATH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(ising_pass_tma_kernel<4, METHOD_HEATBATH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e == cudaSuccess) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tocc, ising_pass_tma_kernel<4, METHOD_METROPOLIS, false>, 288, smem);
+        }
+        if (e == cudaSuccess && tocc >= 1) { m->use_tma = true; m->tma_grid = sms * tocc; }
+        else cudaGetLastError();
+    }
     m->beta = 1 / kbt;
     m->fuse_ok = m->st.g.ptail >= m->st.g.L && m->st.g.off[1][0] == 0;
     build_tables(m);

@@ -242,17 +242,12 @@ __device__ __noinline__ int2 ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4
 
 // One vector (16 sites of the colour being updated) of one lane: loads, Philox block, byte-parallel
 // accept test, store; ties parked in the warp's queue; optional halo push and fused E/M sums.
-template <int NNB, int METHOD, bool PUSH, bool MEASURE, bool FULLWARP>
-__device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (&q)[NNB], uint32_t cx, uint32_t cz, uint32_t cw,
-                                          const RingPassArgs& a, const IsingTab& tab, uint64_t pol, uint32_t qaddr,
-                                          uint32_t cntaddr, bool is_b, uint32_t& accX, uint32_t& accM)
+// everything after the loads: o = own vector, nb = the NNB neighbour vectors
+template <int NNB, int METHOD, bool PUSH, bool MEASURE>
+__device__ __forceinline__ void ising_core(int v, uint4* po, uint4 o, const uint4 (&nb)[NNB], uint32_t cx, uint32_t cz, uint32_t cw,
+                                           const RingPassArgs& a, const IsingTab& tab, uint64_t pol, uint32_t qaddr,
+                                           uint32_t cntaddr, bool is_b, uint32_t& accX, uint32_t& accM)
 {
-    uint4 o = ld_own(po, pol);
-    uint4 nb[NNB];
-    // (loading the x+ vector as a shuffle of the neighbouring lane's x- vector instead of a second, overlapping
-    // 512-byte load was tried: 4 SHFL + a one-lane load made the pass 20 % slower -- the MIO queue is the busiest unit)
-#pragma unroll
-    for (int j = 0; j < NNB; ++j) nb[j] = ld_other(q[j]);
     // counter (p0 + v, 0, draw_lo, draw_hi | colour << 16 | sub << 24): positions are < 2^31
     const uint4 r = philox_rk<TAG_ISING>(make_uint4(cx, 0u, cz, cw), tab.rk0);
     uint4 S = make_uint4(nb[0].x + nb[1].x, nb[0].y + nb[1].y, nb[0].z + nb[1].z, nb[0].w + nb[1].w);
@@ -287,6 +282,20 @@ __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (
         if (v < a.nb) a.peer_lo[v] = rot_lanes(o, a.rot_lo);
         else if (v >= a.hi_start) a.peer_hi[v - a.hi_start] = rot_lanes(o, a.rot_hi);
     }
+}
+
+template <int NNB, int METHOD, bool PUSH, bool MEASURE, bool FULLWARP>
+__device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (&q)[NNB], uint32_t cx, uint32_t cz, uint32_t cw,
+                                          const RingPassArgs& a, const IsingTab& tab, uint64_t pol, uint32_t qaddr,
+                                          uint32_t cntaddr, bool is_b, uint32_t& accX, uint32_t& accM)
+{
+    const uint4 o = ld_own(po, pol);
+    uint4 nb[NNB];
+    // (loading the x+ vector as a shuffle of the neighbouring lane's x- vector instead of a second, overlapping
+    // 512-byte load was tried: 4 SHFL + a one-lane load made the pass 20 % slower -- the MIO queue is the busiest unit)
+#pragma unroll
+    for (int j = 0; j < NNB; ++j) nb[j] = ld_other(q[j]);
+    ising_core<NNB, METHOD, PUSH, MEASURE>(v, po, o, nb, cx, cz, cw, a, tab, pol, qaddr, cntaddr, is_b, accX, accM);
 }
 
 #define TK_CHUNK 128  // vectors per ticket: 4 warp-iterations, unrolled so that the 8 stream addresses are
@@ -442,6 +451,179 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
         else nxt += nwarps_grid * TK_CHUNK;
     }
     const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab);
+    if (MEASURE) {
+        long long x = (long long)NNB * accM - 2ll * accX + corrX + d.x, mm = (long long)accM + corrM + d.y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x += __shfl_down_sync(0xffffffffu, x, o);
+            mm += __shfl_down_sync(0xffffffffu, mm, o);
+        }
+        if (lane == 0) {
+            if (x) atomicAdd(a.acc, (unsigned long long)x);
+            if (mm) atomicAdd(a.acc + 1, (unsigned long long)mm);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// TMA-staged colour pass (single-GPU launches; experiment, B200MC_TUNE bit 7).
+// ising_pass_kernel is bound by the L1TEX request path: eight 512-byte requests per warp-step (a coalesced
+// LDG.128 is 4 wavefronts).  Here a ninth warp of the block feeds the copy engine: per tile of 256 vectors
+// one `cp.async.bulk` per input stream (1-D, no tensor map: every stream is a contiguous run of vectors in
+// the folded layout; the x- / x+ windows overlap in all but one vector and are fetched once, 257 vectors) into
+// a ring of TMA_STAGES shared-memory stages, completion on a "full" mbarrier per stage; the eight consumer
+// warps read their 32 vectors back with LDS.128, update, store with STG and release the stage on an "empty"
+// mbarrier.  Tiles are drawn from the same interleaved ticket counters as the plain kernel.
+// ---------------------------------------------------------------------------
+#define TMA_STAGES 2
+#define TMA_TILE 256                 // vectors per tile (8 consumer warps x 32)
+#define TMA_SLOT (16 * (TMA_TILE + 2))   // bytes per stream slot (257 vectors used by the x window)
+
+__device__ __forceinline__ void mbar_init(uint32_t mb, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mb, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mb)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t mb, uint32_t phase)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(mb), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t phase)
+{
+    int spins = 0;
+    while (!mbar_try_wait(mb, phase)) { if (++spins > (1 << 22)) __trap(); }   // a lost arrival aborts instead of hanging the GPU
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mb)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(mb)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+
+template <int NNB, int METHOD, bool MEASURE>
+__global__ void __launch_bounds__(288)
+ising_pass_tma_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant__ IsingTab tab)
+{
+    constexpr int NSTREAM = NNB;                   // own, x window, y+, y- (, z+, z-)
+    constexpr uint32_t STAGE_BYTES = NSTREAM * TMA_SLOT;
+    constexpr uint32_t TX_BYTES = (NSTREAM - 1) * (16u * TMA_TILE) + 16u * (TMA_TILE + 1);
+    extern __shared__ __align__(128) uint8_t tma_smem[];
+    __shared__ uint4 tq[8][64][2];   // drained when more than 32 records are parked, checked every step
+    __shared__ uint32_t tq_cnt[8];
+    __shared__ __align__(8) unsigned long long mb_full[TMA_STAGES], mb_empty[TMA_STAGES];
+    __shared__ int tile_base[TMA_STAGES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(tma_smem);
+    const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(&mb_full[0]);
+    const uint32_t empty0 = (uint32_t)__cvta_generic_to_shared(&mb_empty[0]);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp < 8 && lane == 0) tq_cnt[warp] = 0;
+    __syncthreads();
+    uint4* own = a.own + a.H;
+    const int nvec = (int)a.nvec;
+    if (warp == 8) {
+        // ---- producer: one lane feeds the copy engine ----
+        if (lane == 0) {
+            const uint4* src[NSTREAM];
+            src[0] = own;
+            src[1] = a.oth + (a.H + a.off[0]);     // 257-vector x window: x- = [v], x+ = [v + 1]
+#pragma unroll
+            for (int j = 2; j < NSTREAM; ++j) src[j] = a.oth + (a.H + a.off[j]);
+            unsigned int* tk = a.ticket + (blockIdx.x % TK_NCNT) * 64;
+            const int tk_base = (blockIdx.x % TK_NCNT) * TMA_TILE;
+            int base_next = (int)atomicAdd(tk, (unsigned)TMA_TILE) * TK_NCNT + tk_base;
+            for (uint32_t it = 0;; ++it) {
+                const uint32_t st = it % TMA_STAGES, round = it / TMA_STAGES;
+                const int base = base_next;
+                if (base < nvec) base_next = (int)atomicAdd(tk, (unsigned)TMA_TILE) * TK_NCNT + tk_base;   // one tile ahead: its latency hides behind this tile
+                if (round > 0) mbar_wait(empty0 + 8 * st, (round - 1) & 1u);   // the consumers have released this stage
+                tile_base[st] = base < nvec ? base : -1;
+                const uint32_t mb = full0 + 8 * st, dst = buf0 + st * STAGE_BYTES;
+                if (base + TMA_TILE <= nvec) {
+                    mbar_expect_tx(mb, TX_BYTES);
+                    bulk_g2s(dst, src[0] + base, 16u * TMA_TILE, mb);
+                    bulk_g2s(dst + TMA_SLOT, src[1] + base, 16u * (TMA_TILE + 1), mb);
+#pragma unroll
+                    for (int j = 2; j < NSTREAM; ++j) bulk_g2s(dst + j * TMA_SLOT, src[j] + base, 16u * TMA_TILE, mb);
+                } else {
+                    mbar_arrive(mb);   // partial last tile (plain loads) or the end marker
+                }
+                if (base >= nvec) break;
+            }
+        }
+        return;
+    }
+    // ---- consumers ----
+    uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(&tq[warp][0][0]);
+    uint32_t cntaddr = (uint32_t)__cvta_generic_to_shared(&tq_cnt[warp]);
+    const uint64_t pol = l2_policy_evict_first();
+    const uint32_t cx0 = (uint32_t)a.p0, cz = (uint32_t)a.draw;
+    const uint32_t cw = (uint32_t)((a.draw >> 32) & 0xFFFFu) | (a.colour << 16);
+    uint32_t accX = 0, accM = 0;
+    int corrX = 0, corrM = 0;
+    constexpr int DN = MEASURE ? NNB : 0;
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t st = it % TMA_STAGES, round = it / TMA_STAGES;
+        mbar_wait(full0 + 8 * st, round & 1u);
+        const int base = tile_base[st];
+        if (base < 0) break;
+        const int v = base + 32 * warp + lane;
+        if (base + TMA_TILE <= nvec) {
+            const uint32_t bufs = buf0 + st * STAGE_BYTES + 16u * (32 * warp + lane);
+            const uint4 o = lds128(bufs);
+            uint4 nb[NNB];
+            nb[0] = lds128(bufs + TMA_SLOT);
+            nb[1] = lds128(bufs + TMA_SLOT + 16u);
+#pragma unroll
+            for (int j = 2; j < NNB; ++j) nb[j] = lds128(bufs + j * TMA_SLOT);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * st);   // this warp's 32 vectors are in registers
+            ising_core<NNB, METHOD, false, MEASURE>(v, own + v, o, nb, cx0 + (uint32_t)v, cz, cw, a, tab, pol, qaddr, cntaddr, false,
+                                                    accX, accM);
+        } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * st);
+            if (v < nvec) {
+                const uint4* qu[NNB];
+#pragma unroll
+                for (int j = 0; j < NNB; ++j) qu[j] = a.oth + (a.H + a.off[j]) + v;
+                ising_vec<NNB, METHOD, false, MEASURE, false>(v, own + v, qu, cx0 + (uint32_t)v, cz, cw, a, tab, pol, qaddr, cntaddr,
+                                                              false, accX, accM);
+            }
+        }
+        __syncwarp();
+        if (lds32(cntaddr) > 32) {
+            const int2 d = ising_drain<METHOD, false, DN>(qaddr, cntaddr, own, a, tab);
+            corrX += d.x; corrM += d.y;
+        }
+    }
+    const int2 d = ising_drain<METHOD, false, DN>(qaddr, cntaddr, own, a, tab);
     if (MEASURE) {
         long long x = (long long)NNB * accM - 2ll * accX + corrX + d.x, mm = (long long)accM + corrM + d.y;
 #pragma unroll

@@ -256,3 +256,18 @@ def test_run_relaxation_series(oracle, dim, shape):
     assert g.measure() == (int(e[-1]), int(m[-1]))
     g.update(); o.update()
     assert g.measure() == (o.calc_energy_sum(), o.calc_magne_sum())
+
+
+def test_tma_staged_pass_bit_exact(oracle, monkeypatch):
+    """the copy-engine staged colour pass (ising_pass_tma_kernel, opt-in with B200MC_TUNE bit 7: cp.async.bulk into a
+    shared-memory ring, producer warp + 8 consumer warps) on a lattice large enough for the ticket path"""
+    i2, i3 = _mods()
+    monkeypatch.setenv("B200MC_TUNE", "128")
+    shape = (255, 257, 322)
+    g = i3.ising3d_gpu().init(*shape, KBT3, 42)
+    o = oracle.ising3d_gpu().init(*shape, KBT3, 42)
+    g.set_random_spin(); o.set_random_spin()
+    for sweep in range(2):
+        g.update(); o.update()
+        assert np.array_equal(g.spins(), o.spins()), sweep
+        assert g.measure() == (o.calc_energy_sum(), o.calc_magne_sum())
