@@ -201,11 +201,45 @@ class _IsingBase:
         return int(e.value), int(m.value)
 
     def run_relaxation(self, mcs):
-        """mcs x [update; calc_magne_sum; calc_energy_sum] on the device; returns (E[mcs], M[mcs]) int64 arrays"""
-        e = np.empty(int(mcs), dtype=np.int64)
-        m = np.empty(int(mcs), dtype=np.int64)
+        """mcs x [update; calc_magne_sum; calc_energy_sum] on the device; returns (E, M) int64 arrays of shape
+        (mcs,) -- or (n_multi, mcs) for a batch of samples"""
+        n = self.n_multi()
+        e = np.empty((n, int(mcs)), dtype=np.int64)
+        m = np.empty((n, int(mcs)), dtype=np.int64)
         self._call("run_relaxation", int(mcs), e.ctypes.data_as(P), m.ctypes.data_as(P), argtypes=(i32, P, P))
+        return (e[0], m[0]) if n == 1 else (e, m)
+
+    # -- batch of independent samples (one launch per colour pass for all of them) --
+    def init_multi(self, *dims_kbt_iseed_nmulti):
+        """init(nx, ny[, nz], kbt, iseed) for n_multi samples: init_multi(nx, ny[, nz], kbt, iseed, n_multi)"""
+        *dims, kbt, iseed, n_multi = dims_kbt_iseed_nmulti
+        if self._h:
+            self._f("destroy", C.c_int, P)(self._h)
+            self._h = C.c_void_p(None)
+        f = self._f("create_multi", C.c_int, PP, *([i64] * len(dims)), f64, i32, i32)
+        _lib.check(f(C.byref(self._h), *[int(d) for d in dims], float(kbt), int(iseed), int(n_multi)))
+        return self
+
+    def n_multi(self):
+        return int(self._f("n_multi", i32, P)(self._h))
+
+    def measure_multi(self):
+        n = self.n_multi()
+        e = np.empty(n, dtype=np.int64)
+        m = np.empty(n, dtype=np.int64)
+        self._call("measure_multi", e.ctypes.data_as(P), m.ctypes.data_as(P), argtypes=(P, P))
         return e, m
+
+    def spins_multi(self, sample):
+        out = np.empty(self.nall() + 2 * self._halo(), dtype=np.int32)
+        self._call("get_spins_multi", int(sample), out.ctypes.data_as(P), argtypes=(i32, P))
+        return out
+
+    def set_spins_multi(self, sample, spins):
+        s = np.ascontiguousarray(spins, dtype=np.int32)
+        if s.size != self.nall() + 2 * self._halo():
+            raise ValueError("spins must use the reference layout, halo cells included")
+        self._call("set_spins_multi", int(sample), s.ctypes.data_as(P), argtypes=(i32, P))
 
     def sync(self):
         self._call("sync")

@@ -43,7 +43,9 @@ struct Ising {
     bool alive;
     // observables cache: valid until the configuration changes
     bool obs_valid;
-    int64_t obs_e, obs_m;
+    int64_t obs_e, obs_m;        // sample 0
+    int n_multi;                 // batch of independent samples updated by the same launches (single GPU)
+    std::vector<int64_t> obs_ev, obs_mv;   // all samples
     // fused measurement: when the caller measures after every update (the drivers' loop), the second
     // colour pass of the next sweep accumulates X and sum(s) itself and measure() only reads them back
     bool fuse_ok;        // layout allows it (no site-less tail positions)
@@ -146,15 +148,16 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bo
     a.ticket = nullptr;
     a.chunk = m->chunk;
     a.acc = m->acc_target;
+    a.rstride = m->st.rstride;
     a.nopush = (m->tune & 32) ? 2 : 0;  // debug bit 5: no L2 prefetch
     int64_t need = (n + 255) / 256;
     const int grid = (int)(need < (int64_t)m->grid ? need : (int64_t)m->grid);
-    if (ordered && !(m->tune & 1) && n > (int64_t)m->grid * 256 * 4) {
+    if (ordered && !(m->tune & 1) && n > (int64_t)m->grid * 256 * 4 && m->n_multi == 1) {
         a.ticket = m->d_ticket;
         CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
     }
     COUNT_LAUNCH();
-#define PASS(METHOD, ORD, MEAS) ising_pass_kernel<NNB, METHOD, ORD, false, MEAS><<<grid, 256, 0, m->stream>>>(a, m->tab)
+#define PASS(METHOD, ORD, MEAS) ising_pass_kernel<NNB, METHOD, ORD, false, MEAS><<<dim3(grid, m->n_multi), 256, 0, m->stream>>>(a, m->tab)
     if (a.ticket && m->use_tma) {
         // copy-engine staging (ising_pass_tma_kernel): full tickets through cp.async.bulk, 2 blocks per SM
         const size_t smem = (size_t)TMA_STAGES * NNB * TMA_SLOT;
@@ -217,6 +220,7 @@ int launch_push(Ising* m, int colour, bool fuse)
     a.wait_seq = st.push_seq;
     a.sig_seq = ++st.push_seq;
     a.acc = m->acc_target;
+    a.rstride = 0;
     CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
     COUNT_LAUNCH();
     if (m->method == METHOD_METROPOLIS) {
@@ -239,7 +243,7 @@ int launch_pass(Ising* m, int colour, bool fuse)
     const RingGeom& g = m->st.g;
     m->obs_valid = false;
     m->fused_pending = false;
-    if (fuse && m->acc_target == m->d_acc) CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
+    if (fuse && m->acc_target == m->d_acc) CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long) * m->n_multi, m->stream));
     if (m->timing) {
         while (m->evs.size() < m->ev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); m->evs.push_back(e); }
         CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
@@ -334,7 +338,7 @@ int measure(Ising* m, int64_t* e, int64_t* mag)
     }
     if (!m->fused_pending) {
         { int rcq = ring_p2p_quiesce(&m->st, m->stream); if (rcq) return rcq; }
-        CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
+        CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long) * m->n_multi, m->stream));
         { int rcm = launch_measure(m, m->d_acc); if (rcm) return rcm; }
     }
     m->fused_pending = false;  // the all-reduce below turns d_acc into global sums; they are cached in obs_*
@@ -344,12 +348,17 @@ int measure(Ising* m, int64_t* e, int64_t* mag)
         if (rc) return rc;
     }
     unsigned long long* acc = m->h_acc;
-    CK(cudaMemcpyAsync(acc, m->d_acc, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaMemcpyAsync(acc, m->d_acc, 2 * sizeof(unsigned long long) * m->n_multi, cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
-    const int64_t X = (int64_t)acc[0], sum = (int64_t)acc[1];
-    // E = -(bonds) + 2 X with bonds = (nnb/2) N;   M = 2 sum(s) - N
-    m->obs_e = -(int64_t)(g.nnb / 2) * g.N + 2 * X;
-    m->obs_m = 2 * sum - g.N;
+    m->obs_ev.resize(m->n_multi); m->obs_mv.resize(m->n_multi);
+    for (int j = 0; j < m->n_multi; ++j) {
+        const int64_t X = (int64_t)acc[2 * j], sum = (int64_t)acc[2 * j + 1];
+        // E = -(bonds) + 2 X with bonds = (nnb/2) N;   M = 2 sum(s) - N
+        m->obs_ev[j] = -(int64_t)(g.nnb / 2) * g.N + 2 * X;
+        m->obs_mv[j] = 2 * sum - g.N;
+    }
+    m->obs_e = m->obs_ev[0];
+    m->obs_m = m->obs_mv[0];
     m->obs_valid = true;
     if (e) *e = m->obs_e;
     if (mag) *mag = m->obs_m;
@@ -363,9 +372,9 @@ int launch_measure(Ising* m, unsigned long long* acc)
     const RingGeom& g = m->st.g;
     COUNT_LAUNCH();
     if (m->ndim == 3)
-        ising_measure_kernel<6><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, acc);
+        ising_measure_kernel<6><<<dim3(m->grid, m->n_multi), 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, acc, m->st.rstride);
     else
-        ising_measure_kernel<4><<<m->grid, 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, acc);
+        ising_measure_kernel<4><<<dim3(m->grid, m->n_multi), 256, 0, m->stream>>>(m->st.vec[0], m->st.vec[1], g.Lloc, g.H, g.p0, m->d_off1, g.L, g.Nc, g.ptail, acc, m->st.rstride);
     CK(cudaGetLastError());
     return B200MC_OK;
 }
@@ -379,17 +388,18 @@ int run_relaxation(Ising* m, int32_t mcs, int64_t* e, int64_t* mag)
     const RingGeom& g = m->st.g;
     if (mcs < 0) ARG_FAIL("mcs < 0");
     if (mcs == 0) return B200MC_OK;
-    if (m->series_cap < mcs) {
+    const size_t per = 2 * (size_t)m->n_multi;   // sums per MCS: [sample][X, sum s]
+    if (m->series_cap < (int64_t)mcs) {
         cudaFree(m->d_series);
         m->d_series = nullptr; m->series_cap = 0;
-        CK(cudaMalloc(&m->d_series, (size_t)mcs * 2 * sizeof(unsigned long long)));
+        CK(cudaMalloc(&m->d_series, (size_t)mcs * per * sizeof(unsigned long long)));
         m->series_cap = mcs;
     }
-    CK(cudaMemsetAsync(m->d_series, 0, (size_t)mcs * 2 * sizeof(unsigned long long), m->stream));
+    CK(cudaMemsetAsync(m->d_series, 0, (size_t)mcs * per * sizeof(unsigned long long), m->stream));
     const bool fuse = m->fuse_ok && !(m->tune & 8);
     int rc = B200MC_OK;
     for (int32_t i = 0; i < mcs && !rc; ++i) {
-        m->acc_target = m->d_series + 2 * (size_t)i;
+        m->acc_target = m->d_series + per * (size_t)i;
         m->fused_pending = false;
         rc = sweep(m, true, fuse);
         if (!rc && !fuse) {
@@ -401,23 +411,29 @@ int run_relaxation(Ising* m, int32_t mcs, int64_t* e, int64_t* mag)
     m->fused_pending = false;
     m->want_fused = false;
     if (rc) return rc;
-    if (g.nranks > 1 && (rc = dist_allreduce_u64(m->st.comm, m->d_series, 2 * (int)mcs, m->stream))) return rc;
-    std::vector<unsigned long long> host((size_t)mcs * 2);
+    if (g.nranks > 1 && (rc = dist_allreduce_u64(m->st.comm, m->d_series, (int)(per * (size_t)mcs), m->stream))) return rc;
+    std::vector<unsigned long long> host((size_t)mcs * per);
     CK(cudaMemcpyAsync(host.data(), m->d_series, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
-    for (int32_t i = 0; i < mcs; ++i) {
-        const int64_t X = (int64_t)host[2 * (size_t)i], sum = (int64_t)host[2 * (size_t)i + 1];
-        const int64_t ei = -(int64_t)(g.nnb / 2) * g.N + 2 * X, mi = 2 * sum - g.N;
-        if (e) e[i] = ei;
-        if (mag) mag[i] = mi;
-        if (i == mcs - 1) { m->obs_e = ei; m->obs_m = mi; m->obs_valid = true; }
-    }
+    m->obs_ev.resize(m->n_multi); m->obs_mv.resize(m->n_multi);
+    for (int32_t i = 0; i < mcs; ++i)
+        for (int j = 0; j < m->n_multi; ++j) {
+            const int64_t X = (int64_t)host[per * (size_t)i + 2 * j], sum = (int64_t)host[per * (size_t)i + 2 * j + 1];
+            const int64_t ei = -(int64_t)(g.nnb / 2) * g.N + 2 * X, mi = 2 * sum - g.N;
+            if (e) e[(size_t)j * mcs + i] = ei;       // sample-major: sample j, MCS i
+            if (mag) mag[(size_t)j * mcs + i] = mi;
+            if (i == mcs - 1) { m->obs_ev[j] = ei; m->obs_mv[j] = mi; }
+        }
+    m->obs_e = m->obs_ev[0]; m->obs_m = m->obs_mv[0]; m->obs_valid = true;
     return B200MC_OK;
 }
 
 int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed,
-           int rank = 0, int nranks = 1, const char* nccl_id = nullptr)
+           int rank = 0, int nranks = 1, const char* nccl_id = nullptr, int n_multi = 1)
 {
+    if (n_multi < 1) ARG_FAIL("n_multi must be >= 1");
+    if (n_multi > 1 && nranks > 1) ARG_FAIL("a batch of samples and a slab decomposition cannot be combined");
+    if (n_multi > 65535) ARG_FAIL("n_multi too large");
     if (!out) ARG_FAIL("null handle pointer");
     *out = nullptr;
     if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0");
@@ -451,11 +467,13 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
             dist_comm_destroy(m->st.comm); delete m; return B200MC_ERR_CUDA;
         }
     }
+    m->n_multi = n_multi;
+    m->st.n_rep = n_multi;
     rc = ring_alloc(&m->st);
     if (rc) { destroy(m); return rc; }
     if (cudaMalloc(&m->d_ticket, TK_NCNT * 64 * sizeof(unsigned int)) != cudaSuccess ||
-        cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaHostAlloc(&m->h_acc, 2 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess ||
+        cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long) * n_multi) != cudaSuccess ||
+        cudaHostAlloc(&m->h_acc, 2 * sizeof(unsigned long long) * n_multi, cudaHostAllocDefault) != cudaSuccess ||
         cudaMalloc(&m->d_off1, 6 * sizeof(int64_t)) != cudaSuccess) {
         destroy(m);
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed");
@@ -473,7 +491,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     int64_t need = (m->st.g.Lloc + 255) / 256;
     m->grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);
     m->use_tma = false; m->tma_grid = 0;
-    if (nranks == 1 && (m->tune & 128)) {
+    if (nranks == 1 && n_multi == 1 && (m->tune & 128)) {
         // opt in to the maximum dynamic shared memory of the staged kernels and size their grid
         const int smem = TMA_STAGES * m->st.g.nnb * TMA_SLOT;
         cudaError_t e;
@@ -499,7 +517,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     build_tables(m);
     rc = ring_fill(&m->st, 1, m->stream);  // set_allup_spin
     if (rc) { destroy(m); return rc; }
-    if (nranks == 1 && (m->tune & 16) && m->st.g.Nc % 16 == 0 && m->st.g.Lloc >= 4 * m->st.g.H) {
+    if (nranks == 1 && n_multi == 1 && (m->tune & 16) && m->st.g.Nc % 16 == 0 && m->st.g.Lloc >= 4 * m->st.g.H) {
         // experiment (B200MC_TUNE bit 4): one GPU runs the fused update + halo kernel against its own arrays
         rc = ring_p2p_connect_self(&m->st);
         if (rc) { destroy(m); return rc; }
@@ -536,7 +554,7 @@ int set_random(Ising* m)
     { int rcq = ring_p2p_quiesce(&m->st, m->stream); if (rcq) return rcq; }
     for (int c = 0; c < 2; ++c) {
         COUNT_LAUNCH();
-        ring_random_bits_kernel<<<(unsigned)((g.Lloc + 255) / 256), 256, 0, m->stream>>>(m->st.vec[c], g.Lloc, g.H, g.p0, m->seed, m->draw, (uint32_t)c);
+        ring_random_bits_kernel<<<dim3((unsigned)((g.Lloc + 255) / 256), (unsigned)m->n_multi), 256, 0, m->stream>>>(m->st.vec[c], g.Lloc, g.H, g.p0, m->seed, m->draw, (uint32_t)c, m->st.rstride);
         CK(cudaGetLastError());
     }
     m->draw += 1;
@@ -548,6 +566,7 @@ int set_random(Ising* m)
 int update_with_randoms(Ising* m, const double* randoms)
 {
     if (!randoms) ARG_FAIL("null randoms");
+    if (m->n_multi > 1) { snprintf(g_b200mc_err, sizeof(g_b200mc_err), "update_with_randoms: not available for a batch of samples"); return B200MC_ERR_UNSUPPORTED; }
     const RingGeom& g = m->st.g;
     { int rcq = ring_p2p_quiesce(&m->st, m->stream); if (rcq) return rcq; }
     if (!m->d_randoms) CK(cudaMalloc(&m->d_randoms, (size_t)g.N * sizeof(double)));
@@ -627,6 +646,11 @@ int b200mc_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
     int PFX##_calc_magne_sum(void* h, int64_t* m) { CHECK_H(h, ND); return measure(H(h), nullptr, m); } \
     int PFX##_measure(void* h, int64_t* e, int64_t* m) { CHECK_H(h, ND); return measure(H(h), e, m); } \
     int PFX##_run_relaxation(void* h, int32_t mcs, int64_t* e, int64_t* m) { CHECK_H(h, ND); return run_relaxation(H(h), mcs, e, m); } \
+    int32_t PFX##_n_multi(void* h) { return h ? H(h)->n_multi : -1; }                              \
+    int PFX##_measure_multi(void* h, int64_t* e, int64_t* m) { CHECK_H(h, ND); int rc = measure(H(h), nullptr, nullptr); if (rc) return rc; \
+        for (int j = 0; j < H(h)->n_multi; ++j) { if (e) e[j] = H(h)->obs_ev[j]; if (m) m[j] = H(h)->obs_mv[j]; } return B200MC_OK; } \
+    int PFX##_get_spins_multi(void* h, int32_t sample, int32_t* out) { CHECK_H(h, ND); if (!out) ARG_FAIL("null output"); return ring_export_i32(&H(h)->st, out, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream, sample); } \
+    int PFX##_set_spins_multi(void* h, int32_t sample, const int32_t* in) { CHECK_H(h, ND); if (!in) ARG_FAIL("null input"); H(h)->obs_valid = false; H(h)->fused_pending = false; return ring_import_i32(&H(h)->st, in, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream, sample); } \
     int PFX##_get_spins(void* h, int32_t* out) { CHECK_H(h, ND); if (!out) ARG_FAIL("null output"); return ring_export_i32(&H(h)->st, out, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream); } \
     int PFX##_set_spins(void* h, const int32_t* in) { CHECK_H(h, ND); if (!in) ARG_FAIL("null input"); H(h)->obs_valid = false; H(h)->fused_pending = false; return ring_import_i32(&H(h)->st, in, ND == 2 ? RING_MAP_PM1 : RING_MAP_IDENTITY, H(h)->stream); } \
     int64_t PFX##_nx(void* h) { return h ? H(h)->nx : -1; }                                       \
@@ -649,6 +673,16 @@ int b200mc_ising3d_create(void** h, int64_t nx, int64_t ny, int64_t nz, double k
 int b200mc_ising2d_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed)
 {
     return create(h, 2, nx, ny, 0, kbt, iseed);
+}
+// batch of independent samples ("multi-sample batch": the drivers' tot_sample loop, n_multi samples at a time)
+int b200mc_ising3d_create_multi(void** h, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed, int32_t n_multi)
+{
+    if (nz <= 0) ARG_FAIL("nz must be > 0");
+    return create(h, 3, nx, ny, nz, kbt, iseed, 0, 1, nullptr, n_multi);
+}
+int b200mc_ising2d_create_multi(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed, int32_t n_multi)
+{
+    return create(h, 2, nx, ny, 0, kbt, iseed, 0, 1, nullptr, n_multi);
 }
 int b200mc_dist_unique_id(char out[128]) { return dist_unique_id(out); }
 int b200mc_ising3d_create_slab(void** h, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed,

@@ -83,6 +83,9 @@ struct RingPassArgs {
     unsigned int wait_seq, sig_seq;
     // MEASURE variant (second colour pass of a sweep): acc[0] += X, acc[1] += sum(s) as ising_measure_kernel
     unsigned long long* acc;
+    // batch of independent samples (blockIdx.y): sample j lives rstride vectors further in both colour arrays,
+    // draws the counters (position, j, draw, ...) and adds its sums to acc[2 j], acc[2 j + 1]
+    int64_t rstride;
 };
 
 __device__ __forceinline__ uint4 rot_lanes(uint4 s, int dir)
@@ -190,7 +193,7 @@ __device__ __forceinline__ uint32_t tie_bits(uint32_t z)
 // variant (the main loop counted them as rejected).  NNB = 0: not measuring.
 template <int METHOD, bool PUSH, int NNB>
 __device__ __noinline__ int2 ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4* own, const RingPassArgs& a,
-                                         const IsingTab& tab)
+                                         const IsingTab& tab, uint32_t rep = 0)
 {
     int2 delta = make_int2(0, 0);
     __syncwarp();
@@ -210,7 +213,7 @@ __device__ __noinline__ int2 ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4
         uint8_t* bytes = reinterpret_cast<uint8_t*>(own + v);
         // 16-bit tie mask, bit m = byte position m of the stage-1 Philox block
         uint32_t mask = tie_bits(r0.y) | (tie_bits(r0.z) << 4) | (tie_bits(r0.w) << 8) | (tie_bits(r1.x) << 12);
-        const uint64_t pglob = (uint64_t)(a.p0 + v);
+        const uint64_t pglob = (uint64_t)(a.p0 + v) | ((uint64_t)rep << 32);
         while (mask) {
             const int m = __ffs(mask) - 1;
             mask &= mask - 1;
@@ -246,10 +249,10 @@ __device__ __noinline__ int2 ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4
 template <int NNB, int METHOD, bool PUSH, bool MEASURE>
 __device__ __forceinline__ void ising_core(int v, uint4* po, uint4 o, const uint4 (&nb)[NNB], uint32_t cx, uint32_t cz, uint32_t cw,
                                            const RingPassArgs& a, const IsingTab& tab, uint64_t pol, uint32_t qaddr,
-                                           uint32_t cntaddr, bool is_b, uint32_t& accX, uint32_t& accM)
+                                           uint32_t cntaddr, bool is_b, uint32_t& accX, uint32_t& accM, uint32_t cy = 0u)
 {
     // counter (p0 + v, 0, draw_lo, draw_hi | colour << 16 | sub << 24): positions are < 2^31
-    const uint4 r = philox_rk<TAG_ISING>(make_uint4(cx, 0u, cz, cw), tab.rk0);
+    const uint4 r = philox_rk<TAG_ISING>(make_uint4(cx, cy, cz, cw), tab.rk0);
     uint4 S = make_uint4(nb[0].x + nb[1].x, nb[0].y + nb[1].y, nb[0].z + nb[1].z, nb[0].w + nb[1].w);
 #pragma unroll
     for (int j = 2; j < NNB; ++j) { S.x += nb[j].x; S.y += nb[j].y; S.z += nb[j].z; S.w += nb[j].w; }
@@ -287,7 +290,7 @@ __device__ __forceinline__ void ising_core(int v, uint4* po, uint4 o, const uint
 template <int NNB, int METHOD, bool PUSH, bool MEASURE, bool FULLWARP>
 __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (&q)[NNB], uint32_t cx, uint32_t cz, uint32_t cw,
                                           const RingPassArgs& a, const IsingTab& tab, uint64_t pol, uint32_t qaddr,
-                                          uint32_t cntaddr, bool is_b, uint32_t& accX, uint32_t& accM)
+                                          uint32_t cntaddr, bool is_b, uint32_t& accX, uint32_t& accM, uint32_t cy = 0u)
 {
     const uint4 o = ld_own(po, pol);
     uint4 nb[NNB];
@@ -295,7 +298,7 @@ __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (
     // 512-byte load was tried: 4 SHFL + a one-lane load made the pass 20 % slower -- the MIO queue is the busiest unit)
 #pragma unroll
     for (int j = 0; j < NNB; ++j) nb[j] = ld_other(q[j]);
-    ising_core<NNB, METHOD, PUSH, MEASURE>(v, po, o, nb, cx, cz, cw, a, tab, pol, qaddr, cntaddr, is_b, accX, accM);
+    ising_core<NNB, METHOD, PUSH, MEASURE>(v, po, o, nb, cx, cz, cw, a, tab, pol, qaddr, cntaddr, is_b, accX, accM, cy);
 }
 
 #define TK_CHUNK 128  // vectors per ticket: 4 warp-iterations, unrolled so that the 8 stream addresses are
@@ -330,11 +333,12 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
         __syncthreads();
     }
     const uint64_t pol = l2_policy_evict_first();
-    uint4* own = a.own + a.H;
+    const uint32_t rep = blockIdx.y;                       // sample of the batch (static round-robin launches only)
+    uint4* own = a.own + (a.H + (int64_t)rep * a.rstride);
     const int nvec = (int)a.nvec;
     const uint4* pn[NNB];
 #pragma unroll
-    for (int j = 0; j < NNB; ++j) pn[j] = a.oth + (a.H + a.off[j]);
+    for (int j = 0; j < NNB; ++j) pn[j] = a.oth + (a.H + a.off[j] + (int64_t)rep * a.rstride);
     const uint32_t cx0 = (uint32_t)a.p0, cz = (uint32_t)a.draw;
     const uint32_t cw = (uint32_t)((a.draw >> 32) & 0xFFFFu) | (a.colour << 16);
     // ordered mode: every warp takes TK_CHUNK-vector chunks from a global counter, so that all
@@ -405,11 +409,11 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < NNB; ++j) qu[j] = q[j] + 32 * u;
                 ising_vec<NNB, METHOD, PUSH, MEASURE, true>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
-                                                            cntaddr, is_b, accX, accM);
+                                                            cntaddr, is_b, accX, accM, rep);
                 if (u & 1) {
                     __syncwarp();
                     if (lds32(cntaddr) > TQ_CAP - 64) {
-                        const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab);
+                        const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab, rep);
                         corrX += d.x; corrM += d.y;
                     }
                 }
@@ -422,11 +426,11 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < NNB; ++j) qu[j] = q[j] + 32 * u;
                     ising_vec<NNB, METHOD, PUSH, MEASURE, false>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
-                                                                 cntaddr, is_b, accX, accM);
+                                                                 cntaddr, is_b, accX, accM, rep);
                 }
                 __syncwarp();
                 if (lds32(cntaddr) > TQ_CAP - 64) {
-                    const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab);
+                    const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab, rep);
                     corrX += d.x; corrM += d.y;
                 }
             }
@@ -435,7 +439,7 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
             // this chunk's ties are resolved (remote copies patched too), its stores are performed
             // system-wide, and the warp that completes the LAST boundary chunk of the launch tells both
             // neighbours that their halo of this colour is complete
-            const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab);
+            const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab, rep);
             corrX += d.x; corrM += d.y;
             __threadfence_system();
             __syncwarp();
@@ -450,7 +454,7 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
         if (ORDERED) nxt = __shfl_sync(0xffffffffu, nx2, 0);
         else nxt += nwarps_grid * TK_CHUNK;
     }
-    const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab);
+    const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab, rep);
     if (MEASURE) {
         long long x = (long long)NNB * accM - 2ll * accX + corrX + d.x, mm = (long long)accM + corrM + d.y;
 #pragma unroll
@@ -459,8 +463,8 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
             mm += __shfl_down_sync(0xffffffffu, mm, o);
         }
         if (lane == 0) {
-            if (x) atomicAdd(a.acc, (unsigned long long)x);
-            if (mm) atomicAdd(a.acc + 1, (unsigned long long)mm);
+            if (x) atomicAdd(a.acc + 2 * rep, (unsigned long long)x);
+            if (mm) atomicAdd(a.acc + 2 * rep + 1, (unsigned long long)mm);
         }
     }
 }
@@ -696,8 +700,11 @@ template <int NNB>
 __global__ void __launch_bounds__(256)
 ising_measure_kernel(const uint4* __restrict__ c0, const uint4* __restrict__ c1, int64_t nvec,
                      int64_t H, int64_t p0, const int64_t* offs /* colour-1 offsets */, int64_t L,
-                     int64_t Nc, int64_t ptail, unsigned long long* acc)
+                     int64_t Nc, int64_t ptail, unsigned long long* acc, int64_t rstride = 0)
 {
+    c0 += (size_t)blockIdx.y * (size_t)rstride;   // sample of the batch
+    c1 += (size_t)blockIdx.y * (size_t)rstride;
+    acc += 2 * blockIdx.y;
     __shared__ int64_t off[6];
     if (threadIdx.x < 6) off[threadIdx.x] = offs[threadIdx.x];
     __syncthreads();
@@ -742,14 +749,15 @@ ising_measure_kernel(const uint4* __restrict__ c0, const uint4* __restrict__ c1,
 // philox(ctr(p, draw, colour, lane >> 2), (seed, TAG_INIT)).
 static __global__ void __launch_bounds__(256)
 ring_random_bits_kernel(uint4* own, int64_t nvec, int64_t H, int64_t p0, uint32_t seed,
-                        uint64_t draw, uint32_t colour)
+                        uint64_t draw, uint32_t colour, int64_t rstride = 0)
 {
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nvec) return;
+    own += (size_t)blockIdx.y * (size_t)rstride;   // sample of the batch: counters (position | sample << 32, ...)
     uint32_t w[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        const uint4 r = philox4x32_10(mk_ctr((uint64_t)(p0 + v), draw, colour, g), make_uint2(seed, TAG_INIT));
+        const uint4 r = philox4x32_10(mk_ctr((uint64_t)(p0 + v) | ((uint64_t)blockIdx.y << 32), draw, colour, g), make_uint2(seed, TAG_INIT));
         // (U+1) 2^-32 < 0.5  <=>  U < 2^31 - 1
         w[g] = (r.x < 0x7FFFFFFFu ? 1u : 0u) | (r.y < 0x7FFFFFFFu ? 0x100u : 0u) |
                (r.z < 0x7FFFFFFFu ? 0x10000u : 0u) | (r.w < 0x7FFFFFFFu ? 0x1000000u : 0u);

@@ -58,7 +58,9 @@ int ring_geom_set_slab(RingGeom* g, int rank, int nranks)
 
 int ring_alloc(RingStore* s)
 {
-    const size_t nv = (size_t)(s->g.Lloc + 2 * s->g.H);
+    if (s->n_rep < 1) s->n_rep = 1;
+    s->rstride = s->g.Lloc + 2 * s->g.H;
+    const size_t nv = (size_t)s->rstride * (size_t)s->n_rep;
     s->vec[0] = s->vec[1] = nullptr;
     s->stage = nullptr;
     s->p2p = false; s->flags = nullptr; s->n_peer_maps = 0; s->push_seq = 0; s->Lloc_prev = 0;
@@ -86,7 +88,7 @@ int ring_fill(RingStore* s, uint8_t value, cudaStream_t st)
 {
     int rcq = ring_p2p_quiesce(s, st);
     if (rcq) return rcq;
-    const size_t nv = (size_t)(s->g.Lloc + 2 * s->g.H);
+    const size_t nv = (size_t)s->rstride * (size_t)s->n_rep;
     CK(cudaMemsetAsync(s->vec[0], value, nv * sizeof(uint4), st));
     CK(cudaMemsetAsync(s->vec[1], value, nv * sizeof(uint4), st));
     return B200MC_OK;
@@ -111,10 +113,11 @@ __device__ __forceinline__ uint8_t ring_site(const uint8_t* base, int64_t L, int
 // generic, byte-granular: one thread per (dirty vector, lane).  Dirty vectors
 // are the 2H halo vectors and the tail positions [ptail, L).
 __global__ void ring_halo_generic_kernel(uint8_t* base, int64_t L, int64_t H, int64_t Nc,
-                                         int64_t ptail, int64_t v_begin, int64_t n_items)
+                                         int64_t ptail, int64_t v_begin, int64_t n_items, int64_t rstride = 0)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_items) return;
+    base += (size_t)blockIdx.y * (size_t)rstride * 16;   // sample of the batch
     const int b = (int)(t & 15);
     int64_t v = v_begin + (t >> 4);  // dirty-vector ordinal
     int64_t p;
@@ -128,10 +131,11 @@ __global__ void ring_halo_generic_kernel(uint8_t* base, int64_t L, int64_t H, in
 
 // fast path (needs H <= L): one thread per halo vector; a halo vector is the
 // source vector with its lanes rotated by one, plus one or two patched lanes.
-__global__ void ring_halo_fast_kernel(uint4* vec, int64_t L, int64_t H, int64_t Nc)
+__global__ void ring_halo_fast_kernel(uint4* vec, int64_t L, int64_t H, int64_t Nc, int64_t rstride = 0)
 {
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= 2 * H) return;
+    vec += (size_t)blockIdx.y * (size_t)rstride;         // sample of the batch
     const uint8_t* base = reinterpret_cast<const uint8_t*>(vec);
     if (v < H) {
         // low halo, p = v - H < 0: lane b <- lane b-1 at p + L; lane 0 <- site Nc + p
@@ -376,17 +380,17 @@ int ring_halo(RingStore* s, int colour, cudaStream_t st)
     const int64_t ntail = g.L - g.ptail;
     if (g.H <= g.L && g.ptail >= g.H) {
         const int64_t nv = 2 * g.H;
-        ring_halo_fast_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(s->vec[colour], g.L, g.H, g.Nc);
+        ring_halo_fast_kernel<<<dim3((unsigned)((nv + 255) / 256), (unsigned)s->n_rep), 256, 0, st>>>(s->vec[colour], g.L, g.H, g.Nc, s->rstride);
         COUNT_LAUNCH();
         if (ntail > 0) {
             const int64_t n_items = ntail * 16;  // tail vectors are ordinals [2H, 2H + ntail)
-            ring_halo_generic_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(
-                base, g.L, g.H, g.Nc, g.ptail, 2 * g.H, n_items);
+            ring_halo_generic_kernel<<<dim3((unsigned)((n_items + 255) / 256), (unsigned)s->n_rep), 256, 0, st>>>(
+                base, g.L, g.H, g.Nc, g.ptail, 2 * g.H, n_items, s->rstride);
             COUNT_LAUNCH();
         }
     } else {
         const int64_t n_items = (2 * g.H + ntail) * 16;
-        ring_halo_generic_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(base, g.L, g.H, g.Nc, g.ptail, 0, n_items);
+        ring_halo_generic_kernel<<<dim3((unsigned)((n_items + 255) / 256), (unsigned)s->n_rep), 256, 0, st>>>(base, g.L, g.H, g.Nc, g.ptail, 0, n_items, s->rstride);
         COUNT_LAUNCH();
     }
     CK(cudaGetLastError());
@@ -426,9 +430,12 @@ __global__ void ring_import_kernel(uint8_t* a, uint8_t* b, int64_t N, int64_t L,
     ((i & 1) ? b : a)[(p - p0 + H) * 16 + lane] = (uint8_t)v;
 }
 
-int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st)
+int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st, int rep)
 {
     const RingGeom& g = s->g;
+    if (rep < 0 || rep >= s->n_rep) ARG_FAIL("sample %d outside the batch of %d", rep, s->n_rep);
+    uint4* const v0 = s->vec[0] + (size_t)rep * s->rstride;
+    uint4* const v1 = s->vec[1] + (size_t)rep * s->rstride;
     int rcq = ring_p2p_quiesce(s, st);
     if (rcq) return rcq;
     // interior only (the halo cells of the host array are ignored and rebuilt)
@@ -436,7 +443,7 @@ int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStr
         const int64_t n = (g.N - i0 < s->stage_elems) ? g.N - i0 : s->stage_elems;
         CK(cudaMemcpyAsync(s->stage, host + g.P + i0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         ring_import_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-            reinterpret_cast<uint8_t*>(s->vec[0]), reinterpret_cast<uint8_t*>(s->vec[1]), g.N, g.L,
+            reinterpret_cast<uint8_t*>(v0), reinterpret_cast<uint8_t*>(v1), g.N, g.L,
             g.H, i0, n, s->stage, (int)map, g.p0, g.Lloc);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));
@@ -446,14 +453,17 @@ int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStr
     return ring_halo(s, 1, st);
 }
 
-int ring_export_i32(RingStore* s, int32_t* host, RingValueMap map, cudaStream_t st)
+int ring_export_i32(RingStore* s, int32_t* host, RingValueMap map, cudaStream_t st, int rep)
 {
     const RingGeom& g = s->g;
+    if (rep < 0 || rep >= s->n_rep) ARG_FAIL("sample %d outside the batch of %d", rep, s->n_rep);
+    const uint4* const v0 = s->vec[0] + (size_t)rep * s->rstride;
+    const uint4* const v1 = s->vec[1] + (size_t)rep * s->rstride;
     const int64_t total = g.N + 2 * g.P;
     for (int64_t j0 = 0; j0 < total; j0 += s->stage_elems) {
         const int64_t n = (total - j0 < s->stage_elems) ? total - j0 : s->stage_elems;
         ring_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-            reinterpret_cast<const uint8_t*>(s->vec[0]), reinterpret_cast<const uint8_t*>(s->vec[1]),
+            reinterpret_cast<const uint8_t*>(v0), reinterpret_cast<const uint8_t*>(v1),
             g.N, g.L, g.H, g.P, j0, n, s->stage, (int)map, g.p0, g.Lloc);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(host + j0, s->stage, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

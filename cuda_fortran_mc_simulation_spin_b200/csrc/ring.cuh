@@ -43,6 +43,9 @@ struct RingStore {
     int32_t* stage;  // staging buffer for import/export
     int64_t stage_elems;
     void* comm;      // ncclComm_t when nranks > 1
+    // batch of independent samples (single GPU only): sample j of colour c starts at vec[c] + j * rstride
+    int n_rep;
+    int64_t rstride;  // vectors per sample and colour (Lloc + 2H)
     // direct NVLink transport (slab mode): the neighbours' colour arrays and flag words mapped with
     // cudaIpcOpenMemHandle; the boundary launch of a colour pass stores into them (ising_kernels.cuh, PUSH)
     bool p2p;
@@ -66,8 +69,8 @@ void ring_free(RingStore* s);
 int ring_fill(RingStore* s, uint8_t value, cudaStream_t st);
 int ring_halo(RingStore* s, int colour, cudaStream_t st);
 // host int32 arrays in the reference layout spins(1-P : N+P)
-int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st);
-int ring_export_i32(RingStore* s, int32_t* host, RingValueMap map, cudaStream_t st);
+int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st, int rep = 0);
+int ring_export_i32(RingStore* s, int32_t* host, RingValueMap map, cudaStream_t st, int rep = 0);
 
 // direct transport set-up: export my handles, map the two neighbours' (prev == next when nranks == 2)
 int ring_p2p_export(RingStore* s, char out[RING_IPC_BYTES]);

@@ -91,6 +91,26 @@ int b200mc_ising3d_get_timing(void* h, int64_t* launches, double* total_ms);
 int b200mc_ising3d_sync(void* h);
 
 /* ------------------------------------------------------------------------
+ * Batch of independent samples (single GPU): n_multi lattices with the same parameters, updated by the same
+ * launches (one launch per colour pass for the whole batch) -- the drivers' `do sample = 1, tot_sample` loop
+ * (app/ising3d_gpu_relaxation.f90:38) n_multi samples at a time, which is what fills a B200 at the reference's
+ * default lattice sizes (~10^6 sites).  Not a reference symbol for the Ising types (the reference batches only its
+ * clock model, src/clock_gpu_multi_m.f90).  Sample j draws the counters (position, j, ...): sample 0 of a batch
+ * equals the plain handle.  update / update_n / set_* act on all samples; calc_*_sum / measure / get_spins /
+ * set_spins act on sample 0; run_relaxation fills e[j * mcs + i], m[j * mcs + i] (sample-major).
+ * ------------------------------------------------------------------------ */
+int b200mc_ising3d_create_multi(void** h, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed, int32_t n_multi);
+int b200mc_ising2d_create_multi(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed, int32_t n_multi);
+int32_t b200mc_ising3d_n_multi(void* h);
+int32_t b200mc_ising2d_n_multi(void* h);
+int b200mc_ising3d_measure_multi(void* h, int64_t* e, int64_t* m);   /* n_multi values each */
+int b200mc_ising2d_measure_multi(void* h, int64_t* e, int64_t* m);
+int b200mc_ising3d_get_spins_multi(void* h, int32_t sample, int32_t* out);
+int b200mc_ising2d_get_spins_multi(void* h, int32_t sample, int32_t* out);
+int b200mc_ising3d_set_spins_multi(void* h, int32_t sample, const int32_t* in);
+int b200mc_ising2d_set_spins_multi(void* h, int32_t sample, const int32_t* in);
+
+/* ------------------------------------------------------------------------
  * Slab decomposition over several GPUs, one process (rank) per GPU (the
  * reference is single-GPU, its `norishiro` halo, src/ising3d_gpu_m.f90:102-122, is the
  * cell set a rank boundary exchanges).  The helical lattice is a ring of linear indices;

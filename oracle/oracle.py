@@ -106,6 +106,8 @@ def _declare(L):
     d("orc_ring_fold_len", i64, i64)
     d("orc_ising_uniforms", None, u32, u64, i64, P)
     d("orc_ising_uniforms_fast", None, u32, u64, i64, P)
+    d("orc_ising_uniforms_rep", None, u32, u64, u32, i64, P)
+    d("orc_ring_init_uniforms_rep", None, u32, u64, u32, i64, P)
     d("orc_ring_init_uniforms", None, u32, u64, i64, P)
     d("orc_clock_uniforms", None, u32, u64, i32, i64, P, P)
     d("orc_xy_uniforms", None, u32, u64, i64, i64, P, P)
@@ -156,6 +158,19 @@ def ising_uniforms_fast(seed: int, draw: int, n_sites: int, out=None) -> np.ndar
     if out is None:
         out = np.empty(n_sites, dtype=np.float64)
     lib().orc_ising_uniforms_fast(seed & 0xFFFFFFFF, draw, n_sites, _p(out))
+    return out
+
+
+def ising_uniforms_rep(seed: int, draw: int, rep: int, n_sites: int) -> np.ndarray:
+    """accept uniforms of sample `rep` of a batch (b200mc_ising*_create_multi)"""
+    out = np.empty(n_sites, dtype=np.float64)
+    lib().orc_ising_uniforms_rep(seed & 0xFFFFFFFF, draw, rep, n_sites, _p(out))
+    return out
+
+
+def ring_init_uniforms_rep(seed: int, draw: int, rep: int, n_sites: int) -> np.ndarray:
+    out = np.empty(n_sites, dtype=np.float64)
+    lib().orc_ring_init_uniforms_rep(seed & 0xFFFFFFFF, draw, rep, n_sites, _p(out))
     return out
 
 

@@ -69,12 +69,18 @@ ORC_API int64_t orc_ring_fold_len(int64_t n_sites)
     return (nc + 15) / 16;
 }
 
+static inline uint32_t ring_U_rep(uint32_t seed, uint32_t tag, uint64_t draw, int64_t L, int64_t i, uint32_t rep);
 static inline uint32_t ring_U(uint32_t seed, uint32_t tag, uint64_t draw, int64_t L, int64_t i)
+{
+    return ring_U_rep(seed, tag, draw, L, i, 0);
+}
+/* sample `rep` of a batch (b200mc_ising*_create_multi): the sample index is the high word of the block counter */
+static inline uint32_t ring_U_rep(uint32_t seed, uint32_t tag, uint64_t draw, int64_t L, int64_t i, uint32_t rep)
 {
     uint32_t colour = (uint32_t)(i & 1);
     int64_t k = i >> 1;
     int lane = (int)(k / L);
-    uint64_t p = (uint64_t)(k % L);
+    uint64_t p = (uint64_t)(k % L) | ((uint64_t)rep << 32);
     int m = BYTEPOS[lane];
     uint32_t key[2] = {seed, tag}, c[4], r[4], r2[4];
     mk_ctr(c, p, draw, colour, 0);
@@ -93,6 +99,30 @@ ORC_API void orc_ising_uniforms(uint32_t seed, uint64_t draw, int64_t n_sites, d
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n_sites; ++i)
         out[i] = ((double)ring_U(seed, TAG_ISING, draw, L, i) + 1.0) * 0x1p-32;
+}
+
+ORC_API void orc_ising_uniforms_rep(uint32_t seed, uint64_t draw, uint32_t rep, int64_t n_sites, double *out)
+{
+    const int64_t L = orc_ring_fold_len(n_sites);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_sites; ++i)
+        out[i] = ((double)ring_U_rep(seed, TAG_ISING, draw, L, i, rep) + 1.0) * 0x1p-32;
+}
+
+ORC_API void orc_ring_init_uniforms_rep(uint32_t seed, uint64_t draw, uint32_t rep, int64_t n_sites, double *out)
+{
+    const int64_t L = orc_ring_fold_len(n_sites);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_sites; ++i) {
+        uint32_t colour = (uint32_t)(i & 1);
+        int64_t k = i >> 1;
+        int lane = (int)(k / L);
+        uint64_t p = (uint64_t)(k % L) | ((uint64_t)rep << 32);
+        uint32_t key[2] = {seed, TAG_INIT}, c[4], r[4];
+        mk_ctr(c, p, draw, colour, (uint32_t)(lane >> 2));
+        orc_philox4x32_10(c, key, r);
+        out[i] = ((double)r[lane & 3] + 1.0) * 0x1p-32;
+    }
 }
 
 /* set_random_spin uniforms (one 32-bit uniform per site, ring models):

@@ -271,3 +271,41 @@ def test_tma_staged_pass_bit_exact(oracle, monkeypatch):
         g.update(); o.update()
         assert np.array_equal(g.spins(), o.spins()), sweep
         assert g.measure() == (o.calc_energy_sum(), o.calc_magne_sum())
+
+
+@pytest.mark.parametrize("dim,shape", [(3, (31, 31, 30)), (3, (63, 65, 64)), (2, (255, 256)), (2, (101, 100))])
+def test_batch_of_samples_bit_exact(oracle, dim, shape):
+    """n_multi independent samples updated by the same launches: sample j == a CPU oracle fed the uniforms of
+    sample j (counter high word = j); sample 0 == the plain handle; per-sample E/M and the run_relaxation series"""
+    i2, i3 = _mods()
+    n = 3
+    mod, kbt = (i3.ising3d_gpu, KBT3) if dim == 3 else (i2.ising2d_gpu, KBT2)
+    omod = oracle.ising3d_gpu if dim == 3 else oracle.ising2d_gpu
+    g = mod().init_multi(*shape, kbt, 42, n)
+    assert g.n_multi() == n
+    os_ = [omod().init(*shape, kbt, 42) for _ in range(n)]
+    nall = g.nall()
+    g.set_random_spin()
+    for j, o in enumerate(os_):
+        o.set_random_spin(oracle.ring_init_uniforms_rep(42, 0, j, nall))
+        assert np.array_equal(g.spins_multi(j), o.spins())
+    for sweep in range(4):
+        g.update()
+        e, m = g.measure_multi()
+        for j, o in enumerate(os_):
+            o.update(randoms=oracle.ising_uniforms_rep(42, 1 + sweep, j, nall))
+            assert np.array_equal(g.spins_multi(j), o.spins()), (j, sweep)
+            assert (int(e[j]), int(m[j])) == (o.calc_energy_sum(), o.calc_magne_sum()), (j, sweep)
+    es, ms = g.run_relaxation(3)
+    assert es.shape == (n, 3)
+    for i in range(3):
+        for j, o in enumerate(os_):
+            o.update(randoms=oracle.ising_uniforms_rep(42, 5 + i, j, nall))
+            assert (int(es[j, i]), int(ms[j, i])) == (o.calc_energy_sum(), o.calc_magne_sum()), (i, j)
+    assert not np.array_equal(g.spins_multi(0), g.spins_multi(1))
+    # sample 0 of a batch is the plain handle's trajectory
+    p = mod().init(*shape, kbt, 42)
+    p.set_random_spin(); p.update_n(7)
+    assert np.array_equal(p.spins(), g.spins_multi(0))
+    s = os_[2].spins(); g.set_spins_multi(1, s)
+    assert np.array_equal(g.spins_multi(1), s)

@@ -17,3 +17,8 @@ g = ising3d_gpu_m.ising3d_gpu().init(101, 101, 100, 4.51152, 42)
 g.run_relaxation(50); n = 1000
 t0 = time.perf_counter(); e, m = g.run_relaxation(n); dt = time.perf_counter() - t0
 print(f"ising3d 101x101x100 run_relaxation: {dt/n*1e6:.1f} us/MCS  {g.nall()*n/dt/1e9:.1f} flips/ns", flush=True)
+for nm in (8, 32, 128):
+    g = ising2d_gpu_m.ising2d_gpu().init_multi(1001, 1000, 2.26918531421, 42, nm)
+    g.run_relaxation(20); n = 200
+    t0 = time.perf_counter(); e, m = g.run_relaxation(n); dt = time.perf_counter() - t0
+    print(f"ising2d 1001x1000 x {nm} samples run_relaxation: {dt/n*1e6:.1f} us/MCS  {g.nall()*nm*n/dt/1e9:.1f} flips/ns  <m(200)>={m[:, -1].mean()/g.nall():.4f}", flush=True)
