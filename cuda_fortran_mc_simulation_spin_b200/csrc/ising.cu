@@ -149,6 +149,8 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bo
     a.chunk = m->chunk;
     a.acc = m->acc_target;
     a.rstride = m->st.rstride;
+    a.Lfold = g.L; a.Nc = g.Nc;
+    a.mask_from = g.ptail < g.L ? (int)(g.ptail - a.p0 > 0 ? g.ptail - a.p0 : 0) : 0x7FFFFFFF;
     a.nopush = (m->tune & 32) ? 2 : 0;  // debug bit 5: no L2 prefetch
     int64_t need = (n + 255) / 256;
     const int grid = (int)(need < (int64_t)m->grid ? need : (int64_t)m->grid);
@@ -157,8 +159,12 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bo
         CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
     }
     COUNT_LAUNCH();
-#define PASS(METHOD, ORD, MEAS) ising_pass_kernel<NNB, METHOD, ORD, false, MEAS><<<dim3(grid, m->n_multi), 256, 0, m->stream>>>(a, m->tab)
-    if (a.ticket && m->use_tma) {
+#define PASS(METHOD, ORD, MEAS) ising_pass_kernel<NNB, METHOD, ORD, false, MEAS><<<grid, 256, 0, m->stream>>>(a, m->tab)
+#define BPASS(METHOD, MEAS) ising_pass_kernel<NNB, METHOD, false, false, MEAS, true><<<dim3(grid, m->n_multi), 256, 0, m->stream>>>(a, m->tab)
+    if (m->n_multi > 1) {
+        if (m->method == METHOD_METROPOLIS) { if (fuse) BPASS(METHOD_METROPOLIS, true); else BPASS(METHOD_METROPOLIS, false); }
+        else { if (fuse) BPASS(METHOD_HEATBATH, true); else BPASS(METHOD_HEATBATH, false); }
+    } else if (a.ticket && m->use_tma) {
         // copy-engine staging (ising_pass_tma_kernel): full tickets through cp.async.bulk, 2 blocks per SM
         const size_t smem = (size_t)TMA_STAGES * NNB * TMA_SLOT;
         const int tgrid = (int)(need < (int64_t)m->tma_grid ? need : (int64_t)m->tma_grid);  // 256 vectors per block and tile
@@ -173,6 +179,7 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bo
         if (a.ticket) { if (fuse) PASS(METHOD_HEATBATH, true, true); else PASS(METHOD_HEATBATH, true, false); }
         else { if (fuse) PASS(METHOD_HEATBATH, false, true); else PASS(METHOD_HEATBATH, false, false); }
     }
+#undef BPASS
 #undef PASS
     CK(cudaGetLastError());
     return B200MC_OK;
@@ -221,6 +228,7 @@ int launch_push(Ising* m, int colour, bool fuse)
     a.sig_seq = ++st.push_seq;
     a.acc = m->acc_target;
     a.rstride = 0;
+    a.Lfold = g.L; a.Nc = g.Nc; a.mask_from = 0x7FFFFFFF;   // slabs need Nc % 16 == 0: no tail
     CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
     COUNT_LAUNCH();
     if (m->method == METHOD_METROPOLIS) {
@@ -513,7 +521,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
         else cudaGetLastError();
     }
     m->beta = 1 / kbt;
-    m->fuse_ok = m->st.g.ptail >= m->st.g.L && m->st.g.off[1][0] == 0;
+    m->fuse_ok = m->st.g.off[1][0] == 0;
     build_tables(m);
     rc = ring_fill(&m->st, 1, m->stream);  // set_allup_spin
     if (rc) { destroy(m); return rc; }

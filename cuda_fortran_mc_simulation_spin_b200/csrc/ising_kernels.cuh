@@ -86,6 +86,10 @@ struct RingPassArgs {
     // batch of independent samples (blockIdx.y): sample j lives rstride vectors further in both colour arrays,
     // draws the counters (position, j, draw, ...) and adds its sums to acc[2 j], acc[2 j + 1]
     int64_t rstride;
+    // MEASURE on folds whose last positions hold no site in the high lanes (16 does not divide Nc): vectors from
+    // mask_from on (local index) keep only the lanes b with b * Lfold + position < Nc in the sums
+    int mask_from;
+    int64_t Lfold, Nc;
 };
 
 __device__ __forceinline__ uint4 rot_lanes(uint4 s, int dir)
@@ -227,7 +231,7 @@ __device__ __noinline__ int2 ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4
                 const uint8_t nv = (METHOD == METHOD_METROPOLIS) ? (uint8_t)((nib >> 3) ^ 1u) : (uint8_t)1;
                 bytes[lb] = nv;
                 if (PUSH && rbytes) rbytes[(lb + rrot) & 15] = nv;
-                if (NNB) {
+                if (NNB && (int64_t)lb * a.Lfold + (a.p0 + v) < a.Nc) {   // (a site-less tail lane is not part of the sums)
                     // Metropolis: nib & 7 = k' aligned neighbours of the old spin; counted NNB - k' unequal, now k'.
                     // Heat-bath: nib & 7 = S up neighbours; counted as down (S unequal), now up (NNB - S).
                     const int t = (int)(nib & 7u);
@@ -245,6 +249,20 @@ __device__ __noinline__ int2 ising_drain(uint32_t qaddr, uint32_t cntaddr, uint4
 
 // One vector (16 sites of the colour being updated) of one lane: loads, Philox block, byte-parallel
 // accept test, store; ties parked in the warp's queue; optional halo push and fused E/M sums.
+// MEASURE on a fold with site-less tail positions: byte mask of the lanes of vector v that hold a site
+static __device__ __noinline__ uint4 ising_tail_keep(int64_t pg, int64_t Lfold, int64_t Nc)
+{
+    uint32_t keep[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        keep[w] = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if ((int64_t)(4 * w + j) * Lfold + pg < Nc) keep[w] |= 0xFFu << (8 * j);
+    }
+    return make_uint4(keep[0], keep[1], keep[2], keep[3]);
+}
+
 // everything after the loads: o = own vector, nb = the NNB neighbour vectors
 template <int NNB, int METHOD, bool PUSH, bool MEASURE>
 __device__ __forceinline__ void ising_core(int v, uint4* po, uint4 o, const uint4 (&nb)[NNB], uint32_t cx, uint32_t cz, uint32_t cw,
@@ -276,8 +294,14 @@ __device__ __forceinline__ void ising_core(int v, uint4* po, uint4 o, const uint
         //   = sum S - 2 sum S s + NNB sum s,  and  sum S (over all sites of this colour) = NNB sum(s of the other colour),
         // so the launch only accumulates  accX = sum S s  and  accM = sum s (both colours):  X = NNB accM - 2 accX.
         // (IDP.4A is a slow pipe on sm_100: the byte sums use full-rate IMAD / LOP3 / IADD3 instead.)
-        const uint32_t so = ((S.x & (o.x * 255u)) + (S.y & (o.y * 255u))) + ((S.z & (o.z * 255u)) + (S.w & (o.w * 255u)));  // bytes <= 24
-        const uint32_t sm = ((o.x + o.y) + (o.z + o.w)) + ((nb[0].x + nb[0].y) + (nb[0].z + nb[0].w));                       // bytes <= 8
+        uint4 om = o, n0 = nb[0];
+        if (v >= a.mask_from) {   // rare: the few tail positions of the fold
+            const uint4 keep = ising_tail_keep(a.p0 + v, a.Lfold, a.Nc);
+            om.x &= keep.x; om.y &= keep.y; om.z &= keep.z; om.w &= keep.w;
+            n0.x &= keep.x; n0.y &= keep.y; n0.z &= keep.z; n0.w &= keep.w;
+        }
+        const uint32_t so = ((S.x & (om.x * 255u)) + (S.y & (om.y * 255u))) + ((S.z & (om.z * 255u)) + (S.w & (om.w * 255u)));  // bytes <= 24
+        const uint32_t sm = ((om.x + om.y) + (om.z + om.w)) + ((n0.x + n0.y) + (n0.z + n0.w));                                   // bytes <= 8
         accX += (so * 0x01010101u) >> 24;   // byte sum (< 256)
         accM += (sm * 0x01010101u) >> 24;
     }
@@ -307,7 +331,7 @@ __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (
 #ifndef PASS_MINB
 #define PASS_MINB 4
 #endif
-template <int NNB, int METHOD, bool ORDERED, bool PUSH = false, bool MEASURE = false>
+template <int NNB, int METHOD, bool ORDERED, bool PUSH = false, bool MEASURE = false, bool BATCH = false>
 __global__ void __launch_bounds__(256, PASS_MINB)
 ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant__ IsingTab tab)
 {
@@ -333,7 +357,8 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
         __syncthreads();
     }
     const uint64_t pol = l2_policy_evict_first();
-    const uint32_t rep = blockIdx.y;                       // sample of the batch (static round-robin launches only)
+    static_assert(!BATCH || (!ORDERED && !PUSH), "batches of samples use the static round-robin launch");
+    const uint32_t rep = BATCH ? blockIdx.y : 0u;          // sample of the batch (a constant 0 keeps the single-sample code unchanged)
     uint4* own = a.own + (a.H + (int64_t)rep * a.rstride);
     const int nvec = (int)a.nvec;
     const uint4* pn[NNB];
