@@ -117,6 +117,10 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last()
 __device__ __forceinline__ uint4 ld_own(const uint4* p, uint64_t pol)
 {
     uint4 r;
+#ifdef OWN_PLAIN
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+#endif
     asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p), "l"(pol));
@@ -124,6 +128,10 @@ __device__ __forceinline__ uint4 ld_own(const uint4* p, uint64_t pol)
 }
 __device__ __forceinline__ void st_own(uint4* p, uint4 v, uint64_t pol)
 {
+#ifdef OWN_PLAIN
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    return;
+#endif
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p),
                  "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
                  : "memory");

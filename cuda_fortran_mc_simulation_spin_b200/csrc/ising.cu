@@ -38,6 +38,7 @@ struct Ising {
     int tune;  // debug knobs from env B200MC_TUNE: bit0 = static round-robin (no ticket)
     int chunk; // vectors per ticket (env B200MC_CHUNK, default 128)
     int grid;
+    int grid_push;  // resident grid of the fused update + halo-push kernel (its register budget differs)
     bool use_tma;   // single-GPU launches go through the copy-engine staged kernel
     int tma_grid;
     bool alive;
@@ -187,7 +188,7 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bo
 
 // slab mode with the direct transport: ONE launch per colour pass (update + halo push fused)
 template <int NNB>
-int launch_push(Ising* m, int colour, bool fuse)
+int launch_push(Ising* m, int colour, bool fuse, bool boundary_only, cudaStream_t stream, unsigned int* ticket)
 {
     RingStore& st = m->st;
     const RingGeom& g = st.g;
@@ -201,7 +202,7 @@ int launch_push(Ising* m, int colour, bool fuse)
     a.seed = m->seed;
     a.colour = (uint32_t)colour;
     a.draw = m->draw;
-    a.ticket = m->d_ticket;
+    a.ticket = ticket;
     a.chunk = m->chunk;
     a.peer_lo = st.peer_vec[0][colour] + g.H + st.Lloc_prev;  // rank-1's high halo
     a.peer_hi = st.peer_vec[1][colour];                       // rank+1's low halo
@@ -217,7 +218,8 @@ int launch_push(Ising* m, int colour, bool fuse)
     a.hi_first = (int)(jhi * TK_CHUNK);
     a.lo_end = (int)(blo * TK_CHUNK);
     a.nopush = ((m->tune & 4) ? 1 : 0) | ((m->tune & 32) ? 2 : 0);  // debug: bit 0 skip the NVLink stores (wrong results, timing only), bit 1 no L2 prefetch
-    a.q_total = (int)nchunks;
+    // boundary_only: just the tickets of the two boundary blocks (the interior follows as a plain launch)
+    a.q_total = boundary_only ? a.nbchunks : (int)nchunks;
     a.dbg_wait = reinterpret_cast<unsigned long long*>(st.flags + 48);
     a.done = st.flags + 32;
     a.sig_prev = st.peer_flags[0] + 16;  // I am rank-1's "next"
@@ -229,14 +231,14 @@ int launch_push(Ising* m, int colour, bool fuse)
     a.acc = m->acc_target;
     a.rstride = 0;
     a.Lfold = g.L; a.Nc = g.Nc; a.mask_from = 0x7FFFFFFF;   // slabs need Nc % 16 == 0: no tail
-    CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
+    CK(cudaMemsetAsync(ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), stream));
     COUNT_LAUNCH();
     if (m->method == METHOD_METROPOLIS) {
-        if (fuse) ising_pass_kernel<NNB, METHOD_METROPOLIS, true, true, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
-        else ising_pass_kernel<NNB, METHOD_METROPOLIS, true, true, false><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+        if (fuse) ising_pass_kernel<NNB, METHOD_METROPOLIS, true, true, true><<<m->grid_push, 256, 0, stream>>>(a, m->tab);
+        else ising_pass_kernel<NNB, METHOD_METROPOLIS, true, true, false><<<m->grid_push, 256, 0, stream>>>(a, m->tab);
     } else {
-        if (fuse) ising_pass_kernel<NNB, METHOD_HEATBATH, true, true, true><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
-        else ising_pass_kernel<NNB, METHOD_HEATBATH, true, true, false><<<m->grid, 256, 0, m->stream>>>(a, m->tab);
+        if (fuse) ising_pass_kernel<NNB, METHOD_HEATBATH, true, true, true><<<m->grid_push, 256, 0, stream>>>(a, m->tab);
+        else ising_pass_kernel<NNB, METHOD_HEATBATH, true, true, false><<<m->grid_push, 256, 0, stream>>>(a, m->tab);
     }
     CK(cudaGetLastError());
     return B200MC_OK;
@@ -275,7 +277,25 @@ int launch_pass(Ising* m, int colour, bool fuse)
         // direct transport: one launch updates the whole slab, boundary chunks first, and stores their
         // results straight into the neighbours' halos over NVLink; the next pass waits (in the
         // kernel) for the neighbours' flags
-        rc = launch_push<NNB>(m, colour, fuse);
+        // The boundary tickets (first / last H owned vectors, ~3 % of a 1023 x 1023 x 1024 slab) run in the fused
+        // update + push kernel; the interior -- which reads no halo cell -- runs in the plain kernel, whose
+        // register budget and unrolled body are tuned for exactly that (B200MC_TUNE bit 8: everything in the fused kernel).
+        const int64_t blo = (g.H + TK_CHUNK - 1) / TK_CHUNK, jhi = (g.Lloc - g.H) / TK_CHUNK;
+        const bool two = jhi > blo + 64 && !(m->tune & 256) && m->comm_stream;
+        if (two) {
+            // the two launches are independent of each other: the small boundary launch runs on the second stream,
+            // concurrently with the interior launch; both see everything enqueued before this pass, and the compute
+            // stream joins at the end
+            CK(cudaEventRecord(m->ev_boundary, m->stream));
+            CK(cudaStreamWaitEvent(m->comm_stream, m->ev_boundary, 0));
+            rc = launch_push<NNB>(m, colour, fuse, true, m->comm_stream, m->d_ticket + TK_NCNT * 64);
+            if (rc) return rc;
+            CK(cudaEventRecord(m->ev_halo, m->comm_stream));
+            rc = launch_range<NNB>(m, colour, blo * TK_CHUNK, (jhi - blo) * TK_CHUNK, true, fuse);
+            CK(cudaStreamWaitEvent(m->stream, m->ev_halo, 0));
+        } else {
+            rc = launch_push<NNB>(m, colour, fuse, false, m->stream, m->d_ticket);
+        }
         if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
         return rc;
     }
@@ -464,6 +484,14 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     if (rc) { delete m; return rc; }
     rc = ring_geom_set_slab(&m->st.g, rank, nranks);
     if (rc) { delete m; return rc; }
+    if (nranks == 1 && n_multi == 1 && (m->tune & 16)) {
+        if (cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_boundary, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_halo, cudaEventDisableTiming) != cudaSuccess) {
+            snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cannot create the second stream / events");
+            delete m; return B200MC_ERR_CUDA;
+        }
+    }
     if (nranks > 1) {
         if (!nccl_id) { delete m; ARG_FAIL("slab mode needs the NCCL unique id of the job (b200mc_dist_unique_id on rank 0, broadcast by the caller)"); }
         rc = dist_comm_init(&m->st.comm, rank, nranks, nccl_id);
@@ -479,7 +507,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     m->st.n_rep = n_multi;
     rc = ring_alloc(&m->st);
     if (rc) { destroy(m); return rc; }
-    if (cudaMalloc(&m->d_ticket, TK_NCNT * 64 * sizeof(unsigned int)) != cudaSuccess ||
+    if (cudaMalloc(&m->d_ticket, 2 * TK_NCNT * 64 * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long) * n_multi) != cudaSuccess ||
         cudaHostAlloc(&m->h_acc, 2 * sizeof(unsigned long long) * n_multi, cudaHostAllocDefault) != cudaSuccess ||
         cudaMalloc(&m->d_off1, 6 * sizeof(int64_t)) != cudaSuccess) {
@@ -498,6 +526,11 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     if (occ < 1) occ = 1;
     int64_t need = (m->st.g.Lloc + 255) / 256;
     m->grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);
+    int occp = occ;
+    if (ndim == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, ising_pass_kernel<6, METHOD_METROPOLIS, true, true>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, ising_pass_kernel<4, METHOD_METROPOLIS, true, true>, 256, 0);
+    if (occp < 1) occp = 1;
+    m->grid_push = (int)(need < (int64_t)sms * occp ? need : (int64_t)sms * occp);
     m->use_tma = false; m->tma_grid = 0;
     if (nranks == 1 && n_multi == 1 && (m->tune & 128)) {
         // opt in to the maximum dynamic shared memory of the staged kernels and size their grid

@@ -325,14 +325,20 @@ __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (
     ising_core<NNB, METHOD, PUSH, MEASURE>(v, po, o, nb, cx, cz, cw, a, tab, pol, qaddr, cntaddr, is_b, accX, accM, cy);
 }
 
-#define TK_CHUNK 128  // vectors per ticket: 4 warp-iterations, unrolled so that the 8 stream addresses are
+#ifndef TK_CHUNK
+#define TK_CHUNK 128
+#endif
+// vectors per ticket: 4 warp-iterations, unrolled so that the 8 stream addresses are
                       // computed once per ticket and reached with immediate offsets (+512 B per iteration)
 
+// resident blocks per SM the register allocation is tuned for (measured, profiles/r01_history.md): the 3D
+// kernels are fastest with ~80 registers and 3 blocks (1646 vs 1505 flips/ns with 64 registers and 4 blocks),
+// the 2D kernels with 64 registers and 4 blocks
 #ifndef PASS_MINB
-#define PASS_MINB 4
+#define PASS_MINB(NNB, PUSH) (((NNB) == 6) ? 3 : 4)
 #endif
 template <int NNB, int METHOD, bool ORDERED, bool PUSH = false, bool MEASURE = false, bool BATCH = false>
-__global__ void __launch_bounds__(256, PASS_MINB)
+__global__ void __launch_bounds__(256, PASS_MINB(NNB, PUSH))
 ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant__ IsingTab tab)
 {
     static_assert(!PUSH || ORDERED, "the fused update + halo push kernel uses ticket scheduling");
@@ -426,15 +432,15 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < NNB; ++j) q[j] = pn[j] + v0;
         const uint32_t cx = cx0 + (uint32_t)v0;
-        if (base + TK_CHUNK <= nvec) {
-            // full chunk: no bounds checks, the queue is looked at every second vector
+        if (base + TK_CHUNK <= nvec && !(PUSH && is_b)) {
+            // full (interior) chunk: no bounds checks, no halo push, the queue is looked at every second vector
 #pragma unroll
             for (int u = 0; u < TK_CHUNK / 32; ++u) {
                 const uint4* qu[NNB];
 #pragma unroll
                 for (int j = 0; j < NNB; ++j) qu[j] = q[j] + 32 * u;
-                ising_vec<NNB, METHOD, PUSH, MEASURE, true>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
-                                                            cntaddr, is_b, accX, accM, rep);
+                ising_vec<NNB, METHOD, false, MEASURE, true>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
+                                                             cntaddr, false, accX, accM, rep);
                 if (u & 1) {
                     __syncwarp();
                     if (lds32(cntaddr) > TQ_CAP - 64) {
