@@ -127,8 +127,11 @@ __device__ __noinline__ uint32_t six_site_exact(const SixArgs& a, const uint8_t*
 }
 
 // update_sub, src/clock/clock_tableall_gpu_m.f90:107-152 (dual lattice: :110-155), one colour
+#ifndef SIX_MINB
+#define SIX_MINB 3
+#endif
 template <bool SMEM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, SIX_MINB)
 sixclock_pass_kernel(const __grid_constant__ SixArgs a)
 {
     extern __shared__ __align__(16) uint8_t sm[];

@@ -58,7 +58,9 @@ __device__ __forceinline__ uint4 philox_tag(uint4 c, const uint32_t (&rk0)[10])
 // row y, the "up" neighbours of row y - 1 and the "down" neighbours of row y + 1 -- so they are computed once
 // and kept in a rolling three-row register window.  Per 4 sites and row that is 13 sincos (4 new neighbour
 // values, the fifth same-row value, 4 own, 4 candidates) instead of 21: the kernel is bound by the SFU queue.
+#ifndef XY_ROWS
 #define XY_ROWS 16
+#endif
 
 struct XYRow { float c[4], s[4]; };
 
