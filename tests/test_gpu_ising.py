@@ -309,3 +309,29 @@ def test_batch_of_samples_bit_exact(oracle, dim, shape):
     assert np.array_equal(p.spins(), g.spins_multi(0))
     s = os_[2].spins(); g.set_spins_multi(1, s)
     assert np.array_equal(g.spins_multi(1), s)
+
+
+def test_full_size_properties_large_lattices():
+    """size-independent checks at BASELINE config 5 (Ising 2D 65537 x 65536 per GPU) and at an 8.6e9-site 3D lattice
+    (2047 x 2047 x 2048: 8 x the headline size, 2 x 4.3 GB of int8 spins)"""
+    i2, i3 = _mods()
+    g = i2.ising2d_gpu().init(65537, 65536, KBT2, 42)
+    n = g.nall()
+    assert n == 65537 * 65536 and g.measure() == (-2 * n, n)
+    g.set_beta(0.0); g.update()
+    assert g.measure() == (-2 * n, -n)
+    g.set_kbt(KBT2); g.set_allup_spin(); g.update_n(2)
+    e, m = g.measure()
+    assert -2 * n < e < -n and 0.5 * n < m < n and (e + 2 * n) % 4 == 0
+    del g
+    g = i3.ising3d_gpu().init(2047, 2047, 2048, KBT3, 42)
+    n = g.nall()
+    assert n == 2047 * 2047 * 2048 and g.measure() == (-3 * n, n)
+    g.set_beta(0.0); g.update()
+    assert g.measure() == (-3 * n, -n)
+    g.set_kbt(KBT3); g.set_random_spin()
+    e0, m0 = g.measure()
+    assert abs(m0) < 1e-3 * n and abs(e0) < 1e-3 * n            # iid Bernoulli(1/2) start
+    g.update_n(2)
+    e, m = g.measure()
+    assert e < e0 and (e + 3 * n) % 4 == 0

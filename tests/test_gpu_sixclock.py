@@ -164,3 +164,19 @@ def test_clock_table_and_simple_variants(oracle):
         os_.update_metropolis(r); ot.update_metropolis(r)
         assert np.array_equal(S.sixclock(), os_.c) and np.array_equal(T.sixclock(), ot.c)
         assert abs(S.calc_energy() - os_.calc_energy()) <= 1e-12 and abs(S.calc_magne() - os_.calc_magne()) <= 1e-12
+
+
+def test_full_size_properties_config4():
+    """BASELINE config 4: q = 6 clock, 16384 x 16384, batch of samples (size-independent checks)"""
+    from cuda_fortran_mc_simulation_spin_b200._sixclock import sixclock
+    g = sixclock(16384, 16384, 0.91, 6, 2, 42)
+    n = g.nall()
+    assert np.allclose(g.calc_energy(), -2.0) and np.allclose(g.calc_magne(), 1.0)
+    g.update_metropolis_n(2)
+    h, br, bu = g.histograms()
+    assert (h.sum(axis=1) == n).all() and (br.sum(axis=1) == n).all() and (bu.sum(axis=1) == n).all()
+    e, m = g.calc_energy(), g.calc_magne()
+    assert (-2.0 < e).all() and (e < -1.0).all() and (0.5 < m).all() and (m < 1.0).all()
+    assert abs(e[0] - e[1]) < 1e-3 and e[0] != e[1]            # independent samples of the same ensemble
+    g.set_kbt(1e-3); g.init_sixclock_order(); g.update_metropolis()
+    assert np.allclose(g.calc_energy(), -2.0)                  # beta -> infinity from order: nothing moves
