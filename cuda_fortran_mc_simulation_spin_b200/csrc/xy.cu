@@ -27,6 +27,7 @@ struct XYArgs {
     float beta;
     uint64_t draw;
     uint32_t rk0[10];
+    double* acc;   // MEASURE: acc[0] += E, acc[1] += sum cos, acc[2] += sum sin
 };
 
 __device__ __forceinline__ void sincos_turns(float t, float& s, float& c)
@@ -96,55 +97,81 @@ __device__ __forceinline__ void xy_strip_field(const XYArgs& a, int y, int g, co
 // OVERRELAX = false: update_sub + calc_delta_energy, src/xy2d_periodic_gpu_m.f90:368-397
 // OVERRELAX = true : over_relaxation_sub, :418-439: reflect the spin about the local field.  In angles:
 //                    theta' = 2 phi - theta with phi = atan2(h_y, h_x) (the reference's renormalisation is the identity here)
-template <bool OVERRELAX>
+// MEASURE (second colour pass of a sweep when the caller measures every MCS): every bond has exactly one end in
+// the colour being updated, so E = -sum over these sites of s_new . h; sum cos / sum sin: the new spins plus the
+// other colour's row `mid` (each of its sites belongs to exactly one thread-row).
+template <bool OVERRELAX, bool MEASURE>
 __global__ void __launch_bounds__(256)
 xy_strip_kernel(const __grid_constant__ XYArgs a)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nblk = (a.ny + XY_ROWS - 1) / XY_ROWS;
-    if (tid >= nblk * a.gpr) return;
-    const int rb = tid / a.gpr, g = tid - rb * a.gpr;
-    const int y0 = rb * XY_ROWS, y1 = min(y0 + XY_ROWS, a.ny);
-    XYRow dn, mid, up;
-    xy_load_row(a, y0 == 0 ? a.ny - 1 : y0 - 1, g, dn);
-    xy_load_row(a, y0, g, mid);
+    const bool active = tid < nblk * a.gpr;
+    float es = 0.f, mx = 0.f, my = 0.f;
+    if (active) {
+        const int rb = tid / a.gpr, g = tid - rb * a.gpr;
+        const int y0 = rb * XY_ROWS, y1 = min(y0 + XY_ROWS, a.ny);
+        XYRow dn, mid, up;
+        xy_load_row(a, y0 == 0 ? a.ny - 1 : y0 - 1, g, dn);
+        xy_load_row(a, y0, g, mid);
 #pragma unroll 2
-    for (int y = y0; y < y1; ++y) {
-        xy_load_row(a, y + 1 == a.ny ? 0 : y + 1, g, up);
-        float hx[4], hy[4];
-        xy_strip_field(a, y, g, dn, mid, up, hx, hy);
-        float4* po = reinterpret_cast<float4*>(a.own + (size_t)y * a.nxh + 4 * g);
-        const float4 o = *po;
-        float ov[4] = {o.x, o.y, o.z, o.w};
-        if (OVERRELAX) {
+        for (int y = y0; y < y1; ++y) {
+            xy_load_row(a, y + 1 == a.ny ? 0 : y + 1, g, up);
+            float hx[4], hy[4];
+            xy_strip_field(a, y, g, dn, mid, up, hx, hy);
+            float4* po = reinterpret_cast<float4*>(a.own + (size_t)y * a.nxh + 4 * g);
+            const float4 o = *po;
+            float ov[4] = {o.x, o.y, o.z, o.w};
+            if (OVERRELAX) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float phi = atan2f(hy[j], hx[j]) * INV_TWO_PI_F;
-                const float t = 2.0f * phi - ov[j];
-                ov[j] = t - floorf(t);
-            }
-        } else {
-            const int idx = y * a.gpr + g;   // the RNG block of this group (contract: oracle/rng_contract.c)
+                for (int j = 0; j < 4; ++j) {
+                    const float phi = atan2f(hy[j], hx[j]) * INV_TWO_PI_F;
+                    const float t = 2.0f * phi - ov[j];
+                    ov[j] = t - floorf(t);
+                    if (MEASURE) {
+                        float sn, cn;
+                        sincos_turns(ov[j], sn, cn);
+                        es -= cn * hx[j] + sn * hy[j];
+                        mx += cn; my += sn;
+                    }
+                }
+            } else {
+                const int idx = y * a.gpr + g;   // the RNG block of this group (contract: oracle/rng_contract.c)
 #pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-                const uint4 R = philox_tag<TAG_XY>(mk_ctr((uint64_t)idx, a.draw, (uint32_t)a.colour, (uint32_t)sub), a.rk0);
+                for (int sub = 0; sub < 2; ++sub) {
+                    const uint4 R = philox_tag<TAG_XY>(mk_ctr((uint64_t)idx, a.draw, (uint32_t)a.colour, (uint32_t)sub), a.rk0);
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int j = 2 * sub + e;
-                    const uint32_t Ur = e ? R.z : R.x, Uc = e ? R.w : R.y;
-                    const float r = ((float)Ur + 1.0f) * 0x1p-32f;       // (0, 1]
-                    const float ct = ((float)Uc + 1.0f) * 0x1p-32f;      // candidate angle in turns
-                    float cs, cc, ss, sc;
-                    sincos_turns(ct, cs, cc);
-                    sincos_turns(ov[j], ss, sc);
-                    const float de = -((cc - sc) * hx[j] + (cs - ss) * hy[j]);
-                    if (!(r > __expf(-a.beta * de))) ov[j] = ct;          // accept iff r <= exp(-beta dE), :384
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = 2 * sub + e;
+                        const uint32_t Ur = e ? R.z : R.x, Uc = e ? R.w : R.y;
+                        const float r = ((float)Ur + 1.0f) * 0x1p-32f;       // (0, 1]
+                        const float ct = ((float)Uc + 1.0f) * 0x1p-32f;      // candidate angle in turns
+                        float cs, cc, ss, sc;
+                        sincos_turns(ct, cs, cc);
+                        sincos_turns(ov[j], ss, sc);
+                        const float de = -((cc - sc) * hx[j] + (cs - ss) * hy[j]);
+                        const bool acc = !(r > __expf(-a.beta * de));         // accept iff r <= exp(-beta dE), :384
+                        if (acc) ov[j] = ct;
+                        if (MEASURE) {
+                            const float cn = acc ? cc : sc, sn = acc ? cs : ss;
+                            es -= cn * hx[j] + sn * hy[j];
+                            mx += cn; my += sn;
+                        }
+                    }
                 }
             }
+            if (MEASURE) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { mx += mid.c[j]; my += mid.s[j]; }
+            }
+            *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
+            dn = mid;
+            mid = up;
         }
-        *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
-        dn = mid;
-        mid = up;
+    }
+    if (MEASURE) {
+        double part[3] = {(double)es, (double)mx, (double)my};
+        block_atomic_add_f64<3>(a.acc, part);
     }
 }
 
@@ -337,6 +364,8 @@ struct XY {
     bool obs_valid;
     double obs[3];
     int sms;
+    // fused measurement (see the Ising handle): after a measured sweep the last colour pass accumulates E, Mx, My itself
+    bool want_fused, fused_pending;
 };
 
 void fill_args(XY* m, int colour, XYArgs* a)
@@ -345,18 +374,24 @@ void fill_args(XY* m, int colour, XYArgs* a)
     a->nxh = m->nxh; a->ny = (int)m->ny; a->gpr = m->gpr; a->colour = colour;
     a->beta = (float)m->beta; a->draw = m->draw;
     for (int r = 0; r < 10; ++r) a->rk0[r] = m->seed + (uint32_t)r * PHILOX_W0;
+    a->acc = m->d_acc;
 }
 
 int sweep(XY* m)
 {
-    m->obs_valid = false;
+    if (m->fused_pending) m->want_fused = false;   // the sums of the previous pass were never asked for
+    m->obs_valid = false; m->fused_pending = false;
     const int strips = (int)((m->ny + XY_ROWS - 1) / XY_ROWS) * m->gpr;
     for (int colour = 0; colour < 2; ++colour) {
         XYArgs a;
         fill_args(m, colour, &a);
+        const bool fuse = colour == 1 && m->want_fused;
+        if (fuse) CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
         COUNT_LAUNCH();
-        xy_strip_kernel<false><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
+        if (fuse) xy_strip_kernel<false, true><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
+        else xy_strip_kernel<false, false><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
         CK(cudaGetLastError());
+        if (fuse) m->fused_pending = true;
     }
     m->draw += 1;
     return B200MC_OK;
@@ -364,22 +399,29 @@ int sweep(XY* m)
 
 int over_relax(XY* m, int n_steps)
 {
-    m->obs_valid = false;
+    if (n_steps <= 0) return B200MC_OK;
+    // (sums fused into a preceding Metropolis pass are simply superseded: update -> over-relaxation -> measure is the
+    // drivers' order, app/xy2d_periodic_gpu_over_relaxation.f90:43-47)
+    m->obs_valid = false; m->fused_pending = false;
     const int strips = (int)((m->ny + XY_ROWS - 1) / XY_ROWS) * m->gpr;
     for (int i = 0; i < n_steps; ++i)
         for (int colour = 0; colour < 2; ++colour) {
             XYArgs a;
             fill_args(m, colour, &a);
+            const bool fuse = colour == 1 && i == n_steps - 1 && m->want_fused;
+            if (fuse) CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
             COUNT_LAUNCH();
-            xy_strip_kernel<true><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
+            if (fuse) xy_strip_kernel<true, true><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
+            else xy_strip_kernel<true, false><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
             CK(cudaGetLastError());
+            if (fuse) m->fused_pending = true;
         }
     return B200MC_OK;
 }
 
 int by_field(XY* m, double hx, double hy)
 {
-    m->obs_valid = false;
+    m->obs_valid = false; m->fused_pending = false;
     const int total = (int)m->ny * m->gpr;
     for (int colour = 0; colour < 2; ++colour) {
         XYArgs a;
@@ -395,11 +437,15 @@ int by_field(XY* m, double hx, double hy)
 int measure(XY* m)
 {
     if (m->obs_valid) return B200MC_OK;
-    CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
-    COUNT_LAUNCH();
-    const int strips = (int)((m->ny + XY_ROWS - 1) / XY_ROWS) * m->gpr;
-    xy_measure_kernel<<<(strips + 255) / 256, 256, 0, m->stream>>>(m->c[0], m->c[1], m->nxh, (int)m->ny, m->gpr, m->d_acc);
-    CK(cudaGetLastError());
+    if (!m->fused_pending) {
+        CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
+        COUNT_LAUNCH();
+        const int strips = (int)((m->ny + XY_ROWS - 1) / XY_ROWS) * m->gpr;
+        xy_measure_kernel<<<(strips + 255) / 256, 256, 0, m->stream>>>(m->c[0], m->c[1], m->nxh, (int)m->ny, m->gpr, m->d_acc);
+        CK(cudaGetLastError());
+    }
+    m->fused_pending = false;
+    m->want_fused = true;
     CK(cudaMemcpyAsync(m->obs, m->d_acc, 3 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
     m->obs_valid = true;
@@ -416,7 +462,7 @@ int corr(XY* m, bool autoc, double* out)
     double r[2];
     CK(cudaMemcpyAsync(r, m->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
-    m->obs_valid = false;  // d_acc reused
+    m->obs_valid = false; m->fused_pending = false;  // d_acc reused
     *out = autoc ? r[0] : r[1];
     return B200MC_OK;
 }
@@ -431,7 +477,7 @@ void destroy(XY* m)
 int fill(XY* m, float v)
 {
     const size_t n = (size_t)m->nxh * m->ny;
-    m->obs_valid = false;
+    m->obs_valid = false; m->fused_pending = false;
     COUNT_LAUNCH();
     xy_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], n, v);
     CK(cudaGetLastError());
@@ -468,7 +514,7 @@ int b200mc_xy2d_create(void** out, int64_t nx, int64_t ny, double kbt, int32_t i
     XY* m = new (std::nothrow) XY();
     if (!m) ARG_FAIL("out of host memory");
     m->nx = nx; m->ny = ny; m->nxh = (int)(nx / 2); m->gpr = m->nxh / 4; m->stream = 0;
-    m->beta = 1 / kbt; m->seed = (uint32_t)iseed; m->draw = 0; m->obs_valid = false;
+    m->beta = 1 / kbt; m->seed = (uint32_t)iseed; m->draw = 0; m->obs_valid = false; m->fused_pending = false; m->want_fused = false;
     m->c[0] = m->c[1] = m->z[0] = m->z[1] = m->stage = nullptr; m->d_acc = nullptr;
     int dev = 0; m->sms = 148;
     cudaGetDevice(&dev);
@@ -499,7 +545,7 @@ int b200mc_xy2d_set_random_spin(void* h)
 {
     CHECK_X(h);
     XY* m = HX(h);
-    m->obs_valid = false;
+    m->obs_valid = false; m->fused_pending = false;
     const int total = (int)m->ny * m->gpr;
     for (int c = 0; c < 2; ++c) {
         COUNT_LAUNCH();
@@ -549,7 +595,7 @@ int b200mc_xy2d_rotate_summation_magne_toward_xaxis(void* h, int32_t with_autoco
     const double theta = atan2(m->obs[2], m->obs[1]);
     const float dt = (float)(-theta / (2 * 3.14159265358979323846));
     const size_t n = (size_t)m->nxh * m->ny;
-    m->obs_valid = false;
+    m->obs_valid = false; m->fused_pending = false;
     COUNT_LAUNCH();
     xy_rotate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], n, dt);
     if (with_autocorrelation && m->z[0]) {
@@ -635,7 +681,7 @@ int b200mc_xy2d_set_angles(void* h, const float* in)
     int rc = ensure_stage(m);
     if (rc) return rc;
     const long long n = (long long)m->nx * m->ny;
-    m->obs_valid = false;
+    m->obs_valid = false; m->fused_pending = false;
     CK(cudaMemcpyAsync(m->stage, in, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, m->stream));
     COUNT_LAUNCH();
     xy_import_turns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], (int)m->nx, (int)m->ny, m->stage);

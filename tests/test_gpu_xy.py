@@ -173,3 +173,19 @@ def test_xy_initial_state_preparation():
     g.set_random_near_spin(0.001, 0.5)            # the field -m only shrinks |m|: the target must lie below the random start (~1/sqrt N)
     _, mx, my = g.measure()
     assert abs(math.hypot(mx, my) / n - 0.001) / 0.001 <= 0.5 + 1e-3
+
+
+def test_xy_fused_measurement_equals_separate_pass():
+    """after a measured sweep the last colour pass (Metropolis or over-relaxation) accumulates E, Mx, My itself"""
+    from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
+    g = xm.xy2d_gpu().init(512, 256, 0.89, 5)
+    n = g.nall()
+    g.set_random_spin(); g.update(); g.measure()
+    for it in range(4):
+        g.update()
+        if it & 1:
+            g.update_over_relaxation(2)
+        a = g.measure()                      # fused sums
+        g.set_angles(g.angles())             # invalidates: the separate kernel recounts the same configuration
+        b = g.measure()
+        assert all(abs(x - y) <= 2e-6 * n for x, y in zip(a, b)), (it, a, b)
