@@ -1,0 +1,74 @@
+"""CPU: the oracle's clock / XY restatements against known answers and against each other
+(the reference has no tests, these pin the restatement)."""
+import math
+
+import numpy as np
+
+
+def test_tableall_equals_dual_lattice_and_simple_tables(oracle):
+    nx, ny = 34, 6
+    a, b, c = oracle.clock_tableall(nx, ny, 0.91, 6), oracle.clock_dual_lattice(nx, ny, 0.91, 6), oracle.clock_simple(nx, ny, 0.91, 6)
+    # clock_simple sums delta-E over the four neighbours: same table up to the last bits, not bit-identical
+    assert not np.array_equal(a.prob, c.prob) and np.allclose(a.prob, c.prob, rtol=1e-14, atol=0)
+    assert a.prob.max() == 1.0 and a.prob.min() > 0.0
+    for s in range(5):
+        r = oracle.torus_uniforms(42, s, 0, nx, ny)
+        assert r.min() > 0.0 and r.max() <= 1.0
+        a.update_metropolis(r); b.update_metropolis(r)
+        assert np.array_equal(a.c, b.to_full())          # dual lattice indexes its randoms by the full-lattice coordinate
+        assert abs(a.calc_energy() - b.calc_energy()) < 1e-12
+    h, pair = a.histograms()
+    assert h.sum() == nx * ny and pair.sum() == 2 * nx * ny
+
+
+def test_clock_known_answers(oracle):
+    o = oracle.clock_tableall(16, 8, 0.91, 6)
+    assert abs(o.calc_energy() + 2.0) < 1e-12 and abs(o.calc_magne() - 1.0) < 1e-12   # ordered state, per site
+    cold = oracle.clock_tableall(16, 8, 1e-3, 6)
+    cold.update_metropolis(oracle.torus_uniforms(1, 0, 0, 16, 8))
+    assert not cold.c.any()                                                            # beta -> infinity: nothing moves
+    h = oracle.clock_gpu().init(33, 32, 0.8, 6, 42)
+    assert abs(h.calc_energy_sum() + 2.0 * h.nall()) < 1e-9 and abs(h.calc_magne_sum() - h.nall()) < 1e-9
+
+
+def test_xy_helical_known_answers(oracle):
+    o = oracle.xy2d_helical_gpu().init(9, 8, 0.9, 1)
+    n = o.nall()
+    assert (o.calc_energy_sum(), o.calc_magne_sum()) == (-2.0 * n, 1.0 * n)
+    o.set_random_spin(oracle.xyh_init_uniforms(1, 0, n))
+    e0 = o.calc_energy_sum()
+    o.update_over_relaxation(3)
+    assert abs(o.calc_energy_sum() - e0) < 1e-9 * n                 # microcanonical
+    # halo rows mirror the interior (update_norishiro_sub, src/xy2d_gpu_m.f90:114-125)
+    nx = 9
+    assert np.array_equal(o.sp[:, :nx], o.sp[:, n:n + nx]) and np.array_equal(o.sp[:, n + nx:], o.sp[:, nx:2 * nx])
+    o.set_beta(1e9)
+    before = o.sp.copy()
+    r, c = oracle.xyh_uniforms(1, 1, n)
+    o.set_allup_spin(); o.update(r, c)
+    assert o.calc_energy_sum() == -2.0 * n                          # beta -> infinity from all-up: no candidate accepted
+    assert before.shape == o.sp.shape
+
+
+def test_xy_periodic_known_answers(oracle):
+    o = oracle.xy2d_gpu().init(16, 8, 0.89, 3)
+    n = o.nall()
+    assert (o.calc_energy_sum(), o.calc_magne_sum(), o.calc_magne_y_sum()) == (-2.0 * n, 1.0 * n, 0.0)
+    o.set_random_spin(oracle.xy_init_uniforms(3, 0, 16, 8))
+    e0 = o.calc_energy_sum()
+    o.update_over_relaxation(2)
+    assert abs(o.calc_energy_sum() - e0) < 1e-9 * n
+    # metropolis_by_field: accepted iff r <= 1 - exp(dE): a field along +x can only raise Mx
+    mx0 = o.calc_magne_sum()
+    r, c = oracle.xy_uniforms(3, 1, 16, 8)
+    o.metropolis_by_field(r, c, 2.0, 0.0)
+    assert o.calc_magne_sum() >= mx0
+
+
+def test_batched_ising_uniforms(oracle):
+    """sample 0 of a batch draws the plain stream; other samples differ (sample index = high word of the counter)"""
+    a = oracle.ising_uniforms(42, 3, 4096)
+    assert np.array_equal(a, oracle.ising_uniforms_rep(42, 3, 0, 4096))
+    b = oracle.ising_uniforms_rep(42, 3, 1, 4096)
+    assert not np.array_equal(a, b) and abs(b.mean() - 0.5) < 0.03
+    assert np.array_equal(oracle.ring_init_uniforms(42, 0, 512), oracle.ring_init_uniforms_rep(42, 0, 0, 512))
