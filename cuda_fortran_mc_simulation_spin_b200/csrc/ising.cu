@@ -38,6 +38,7 @@ struct Ising {
     int tune;  // debug knobs from env B200MC_TUNE: bit0 = static round-robin (no ticket)
     int chunk; // vectors per ticket (env B200MC_CHUNK, default 128)
     int grid;
+    int slab_nb;    // slab mode: blocks of the one-launch pass that start on the boundary tickets (env B200MC_SLAB_NB; 0 = from the boundary's share of the slab)
     int grid_push;  // resident grid of the fused update + halo-push kernel (its register budget differs)
     bool use_tma;   // single-GPU launches go through the copy-engine staged kernel
     int tma_grid;
@@ -133,7 +134,7 @@ int build_tables(Ising* m)
 }
 
 template <int NNB>
-int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bool fuse)
+int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bool fuse, int fewer_blocks = 0, bool tickets_ready = false)
 {
     const RingGeom& g = m->st.g;
     RingPassArgs a;
@@ -154,10 +155,11 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bo
     a.mask_from = g.ptail < g.L ? (int)(g.ptail - a.p0 > 0 ? g.ptail - a.p0 : 0) : 0x7FFFFFFF;
     a.nopush = (m->tune & 32) ? 2 : 0;  // debug bit 5: no L2 prefetch
     int64_t need = (n + 255) / 256;
-    const int grid = (int)(need < (int64_t)m->grid ? need : (int64_t)m->grid);
+    int grid = (int)(need < (int64_t)m->grid ? need : (int64_t)m->grid);
     if (ordered && !(m->tune & 1) && n > (int64_t)m->grid * 256 * 4 && m->n_multi == 1) {
         a.ticket = m->d_ticket;
-        CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
+        if (!tickets_ready) CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
+        if (grid - fewer_blocks >= 1) grid -= fewer_blocks;  // slab mode: the other blocks of the resident set run ising_slab_kernel on the same tickets
     }
     COUNT_LAUNCH();
 #define PASS(METHOD, ORD, MEAS) ising_pass_kernel<NNB, METHOD, ORD, false, MEAS><<<grid, 256, 0, m->stream>>>(a, m->tab)
@@ -187,12 +189,10 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bo
 }
 
 // slab mode with the direct transport: ONE launch per colour pass (update + halo push fused)
-template <int NNB>
-int launch_push(Ising* m, int colour, bool fuse, bool boundary_only, cudaStream_t stream, unsigned int* ticket)
+static void push_args(Ising* m, int colour, bool boundary_only, unsigned int* ticket, RingPassArgs& a)
 {
     RingStore& st = m->st;
     const RingGeom& g = st.g;
-    RingPassArgs a;
     a.own = st.vec[colour];
     a.oth = st.vec[colour ^ 1];
     a.nvec = g.Lloc;
@@ -231,6 +231,13 @@ int launch_push(Ising* m, int colour, bool fuse, bool boundary_only, cudaStream_
     a.acc = m->acc_target;
     a.rstride = 0;
     a.Lfold = g.L; a.Nc = g.Nc; a.mask_from = 0x7FFFFFFF;   // slabs need Nc % 16 == 0: no tail
+}
+
+template <int NNB>
+int launch_push(Ising* m, int colour, bool fuse, bool boundary_only, cudaStream_t stream, unsigned int* ticket)
+{
+    RingPassArgs a;
+    push_args(m, colour, boundary_only, ticket, a);
     CK(cudaMemsetAsync(ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), stream));
     COUNT_LAUNCH();
     if (m->method == METHOD_METROPOLIS) {
@@ -241,6 +248,64 @@ int launch_push(Ising* m, int colour, bool fuse, bool boundary_only, cudaStream_
         else ising_pass_kernel<NNB, METHOD_HEATBATH, true, true, false><<<m->grid_push, 256, 0, stream>>>(a, m->tab);
     }
     CK(cudaGetLastError());
+    return B200MC_OK;
+}
+
+// slab mode, direct transport, ONE launch per colour pass: the first blocks of the grid take the boundary tickets
+// (update + NVLink push + flags) and then join the others on the interior, which runs the plain body
+template <int NNB>
+int launch_slab(Ising* m, int colour, bool fuse, int64_t vbeg, int64_t n)
+{
+    const RingGeom& g = m->st.g;
+    RingPassArgs ab, ai;
+    push_args(m, colour, true, m->d_ticket + TK_NCNT * 64, ab);
+    ai = ab;
+    ai.own = m->st.vec[colour] + vbeg;
+    ai.oth = m->st.vec[colour ^ 1] + vbeg;
+    ai.nvec = n;
+    ai.p0 = g.p0 + vbeg;
+    ai.ticket = m->d_ticket;
+    ai.nopush = (m->tune & 32) ? 2 : 0;
+    ai.rstride = m->st.rstride;
+    ai.mask_from = 0x7FFFFFFF;
+    const int full = m->grid_push < m->grid ? m->grid_push : m->grid;
+    // blocks that start on the boundary tickets: enough of them that the boundary (a slower code path with system-scope
+    // fences, ~2.5x the time of an interior ticket) is done at about 40 % of the pass
+    int nbb = m->slab_nb;
+    if (nbb <= 0) {
+        const double frac = (double)ab.nbchunks / (double)((g.Lloc + TK_CHUNK - 1) / TK_CHUNK);
+        nbb = (int)(full * frac * 6.0 + 0.5);
+        if (nbb < 8) nbb = 8;
+        if (nbb > full / 2) nbb = full / 2;
+    }
+    if (nbb > full) nbb = full;
+    if (nbb < 1) nbb = 1;
+    const bool share = !(m->tune & (1024 | 1)) && m->comm_stream && n > (int64_t)m->grid * 256 * 4 && nbb < full;
+    CK(cudaMemsetAsync(m->d_ticket, 0, 2 * TK_NCNT * 64 * sizeof(unsigned int), m->stream));
+    // share: nbb blocks run the slab kernel (second stream), the rest of the resident set the plain kernel, both
+    // kinds of block fit on the SMs together (same footprint) and take the interior tickets from the same counters
+    cudaStream_t sb = m->stream;
+    if (share) {
+        CK(cudaEventRecord(m->ev_boundary, m->stream));
+        CK(cudaStreamWaitEvent(m->comm_stream, m->ev_boundary, 0));
+        sb = m->comm_stream;
+    }
+    const int grid = share ? nbb : full;
+    COUNT_LAUNCH();
+    if (m->method == METHOD_METROPOLIS) {
+        if (fuse) ising_slab_kernel<NNB, METHOD_METROPOLIS, true><<<grid, 256, 0, sb>>>(ab, ai, m->tab, nbb);
+        else ising_slab_kernel<NNB, METHOD_METROPOLIS, false><<<grid, 256, 0, sb>>>(ab, ai, m->tab, nbb);
+    } else {
+        if (fuse) ising_slab_kernel<NNB, METHOD_HEATBATH, true><<<grid, 256, 0, sb>>>(ab, ai, m->tab, nbb);
+        else ising_slab_kernel<NNB, METHOD_HEATBATH, false><<<grid, 256, 0, sb>>>(ab, ai, m->tab, nbb);
+    }
+    CK(cudaGetLastError());
+    if (share) {
+        CK(cudaEventRecord(m->ev_halo, m->comm_stream));
+        int rc = launch_range<NNB>(m, colour, vbeg, n, true, fuse, nbb, true);
+        CK(cudaStreamWaitEvent(m->stream, m->ev_halo, 0));
+        return rc;
+    }
     return B200MC_OK;
 }
 
@@ -282,7 +347,10 @@ int launch_pass(Ising* m, int colour, bool fuse)
         // register budget and unrolled body are tuned for exactly that (B200MC_TUNE bit 8: everything in the fused kernel).
         const int64_t blo = (g.H + TK_CHUNK - 1) / TK_CHUNK, jhi = (g.Lloc - g.H) / TK_CHUNK;
         const bool two = jhi > blo + 64 && !(m->tune & 256) && m->comm_stream;
-        if (two) {
+        if (two && !(m->tune & 512)) {
+            rc = launch_slab<NNB>(m, colour, fuse, blo * TK_CHUNK, (jhi - blo) * TK_CHUNK);
+        } else if (two) {
+            // (B200MC_TUNE bit 9: the earlier two-launch form)
             // the two launches are independent of each other: the small boundary launch runs on the second stream,
             // concurrently with the interior launch; both see everything enqueued before this pass, and the compute
             // stream joins at the end
@@ -531,6 +599,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, ising_pass_kernel<4, METHOD_METROPOLIS, true, true>, 256, 0);
     if (occp < 1) occp = 1;
     m->grid_push = (int)(need < (int64_t)sms * occp ? need : (int64_t)sms * occp);
+    { const char* t = getenv("B200MC_SLAB_NB"); m->slab_nb = t ? atoi(t) : 0; }
     m->use_tma = false; m->tma_grid = 0;
     if (nranks == 1 && n_multi == 1 && (m->tune & 128)) {
         // opt in to the maximum dynamic shared memory of the staged kernels and size their grid

@@ -337,13 +337,12 @@ __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (
 #ifndef PASS_MINB
 #define PASS_MINB(NNB, PUSH) (((NNB) == 6) ? 3 : 4)
 #endif
-template <int NNB, int METHOD, bool ORDERED, bool PUSH = false, bool MEASURE = false, bool BATCH = false>
-__global__ void __launch_bounds__(256, PASS_MINB(NNB, PUSH))
-ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant__ IsingTab tab)
+// The body of a colour pass: everything one block does for the vectors (tickets) of `a`.  tq / tq_cnt: the block's
+// tie queues (8 warps x TQ_CAP records) and their fill counts in shared memory.
+template <int NNB, int METHOD, bool ORDERED, bool PUSH, bool MEASURE, bool BATCH>
+__device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const IsingTab& tab, uint4 (*tq)[TQ_CAP][2], uint32_t* tq_cnt)
 {
     static_assert(!PUSH || ORDERED, "the fused update + halo push kernel uses ticket scheduling");
-    __shared__ uint4 tq[8][TQ_CAP][2];
-    __shared__ uint32_t tq_cnt[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(&tq[warp][0][0]);
     uint32_t cntaddr = (uint32_t)__cvta_generic_to_shared(&tq_cnt[warp]);
@@ -498,6 +497,37 @@ ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant_
             if (mm) atomicAdd(a.acc + 2 * rep + 1, (unsigned long long)mm);
         }
     }
+}
+
+template <int NNB, int METHOD, bool ORDERED, bool PUSH = false, bool MEASURE = false, bool BATCH = false>
+__global__ void __launch_bounds__(256, PASS_MINB(NNB, PUSH))
+ising_pass_kernel(const __grid_constant__ RingPassArgs a, const __grid_constant__ IsingTab tab)
+{
+    __shared__ uint4 tq[8][TQ_CAP][2];
+    __shared__ uint32_t tq_cnt[8];
+    ising_pass_body<NNB, METHOD, ORDERED, PUSH, MEASURE, BATCH>(a, tab, tq, tq_cnt);
+}
+
+// Slab mode, one launch per colour pass.  The first nb_blocks blocks of the grid (the ones the hardware
+// starts first) take the boundary tickets of `ab` -- update + store into the neighbours' halos over NVLink,
+// flag handshake -- and then join the other blocks on the interior tickets of `ai`, which is the plain body:
+// the interior never waits for a neighbour, and the latency of the boundary work (system-scope fences, peer
+// stores, flag waits) is hidden behind the interior blocks resident on the same SMs.
+template <int NNB, int METHOD, bool MEASURE>
+__device__ __forceinline__ void ising_slab_boundary(const RingPassArgs& ab, const IsingTab& tab, uint4 (*tq)[TQ_CAP][2], uint32_t* tq_cnt)
+{
+    ising_pass_body<NNB, METHOD, true, true, MEASURE, false>(ab, tab, tq, tq_cnt);
+}
+
+template <int NNB, int METHOD, bool MEASURE>
+__global__ void __launch_bounds__(256, PASS_MINB(NNB, true))
+ising_slab_kernel(const __grid_constant__ RingPassArgs ab, const __grid_constant__ RingPassArgs ai,
+                  const __grid_constant__ IsingTab tab, const int nb_blocks)
+{
+    __shared__ uint4 tq[8][TQ_CAP][2];
+    __shared__ uint32_t tq_cnt[8];
+    if ((int)blockIdx.x < nb_blocks) ising_slab_boundary<NNB, METHOD, MEASURE>(ab, tab, tq, tq_cnt);
+    ising_pass_body<NNB, METHOD, true, false, MEASURE, false>(ai, tab, tq, tq_cnt);
 }
 
 // ---------------------------------------------------------------------------

@@ -94,6 +94,35 @@ def main():
         assert np.array_equal(sp, g1.spins())
         print("slab ok: interleaved run == 1-GPU run, transport", os.environ.get("B200MC_SLAB_TRANSPORT", "p2p"),
               "p2p active:", getattr(g, "_p2p", False), flush=True)
+    # slabs large enough for the shared-ticket pass (boundary + interior blocks of two launches resident together, one
+    # ticket counter): configuration and per-sweep fused E, M against the 1-GPU run of the same lattice, both methods
+    for kind, shape, kbt in (("3d", (255, 255, 256 * world), KBT3), ("2d", (4097, 4096 * world), KBT2)):
+        mod = ising3d_gpu_m.ising3d_gpu if kind == "3d" else ising2d_gpu_m.ising2d_gpu
+        for method in (0, 1):
+            g = mod().init_distributed(*shape, kbt, 5)
+            g.set_method(method)
+            g.set_random_spin()
+            log = []
+            for sweep in range(6):
+                g.update()
+                log.append(g.measure())
+            g.update_n(5)
+            sp = g.spins()
+            del g
+            if rank == 0:
+                g1 = mod().init(*shape, kbt, 5)
+                g1.set_method(method)
+                g1.set_random_spin()
+                log1 = []
+                for sweep in range(6):
+                    g1.update()
+                    log1.append(g1.measure())
+                g1.update_n(5)
+                assert log == log1, (kind, method, log, log1)
+                assert np.array_equal(sp, g1.spins()), (kind, method)
+                del g1
+                print("slab ok: large slabs == 1-GPU run", kind, shape, "heatbath" if method else "metropolis", flush=True)
+            dist.barrier()
     # the device-side driver loop through the slab path: one all-reduce of the whole series
     g = ising3d_gpu_m.ising3d_gpu().init_distributed(31, 31, 64 * world, KBT3, 3)
     e, m = g.run_relaxation(5)
