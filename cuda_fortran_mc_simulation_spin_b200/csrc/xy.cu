@@ -32,7 +32,13 @@ struct XYArgs {
 
 __device__ __forceinline__ void sincos_turns(float t, float& s, float& c)
 {
-    const float r = t - rintf(t);           // [-1/2, 1/2]
+    // t - rint(t) in [-1/2, 1/2] with the 1.5 * 2^23 trick (|t| < 2^22): two FADD instead of FRND, which shares the
+    // XU pipe with MUFU -- the pipe that bounds these kernels
+#ifdef XY_FRND
+    const float r = t - rintf(t);
+#else
+    const float r = t - __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);
+#endif
     __sincosf(r * TWO_PI_F, &s, &c);        // MUFU.SIN / MUFU.COS, |x| <= pi
 }
 
@@ -60,7 +66,7 @@ __device__ __forceinline__ uint4 philox_tag(uint4 c, const uint32_t (&rk0)[10])
 // and kept in a rolling three-row register window.  Per 4 sites and row that is 13 sincos (4 new neighbour
 // values, the fifth same-row value, 4 own, 4 candidates) instead of 21: the kernel is bound by the SFU queue.
 #ifndef XY_ROWS
-#define XY_ROWS 16
+#define XY_ROWS 32
 #endif
 
 struct XYRow { float c[4], s[4]; };
@@ -74,34 +80,127 @@ __device__ __forceinline__ void xy_load_row(const XYArgs& a, int y, int g, XYRow
     sincos_turns(raw.w, r.s[3], r.c[3]);
 }
 
-// local field of the 4 sites of row y: same-row values `mid` (+ the fifth one across the group edge), up, down
-// (same summation order as calc_delta_energy, src/xy2d_periodic_gpu_m.f90:395: x+1, x-1, y+1, y-1)
-__device__ __forceinline__ void xy_strip_field(const XYArgs& a, int y, int g, const XYRow& dn, const XYRow& mid, const XYRow& up,
-                                               float (&hx)[4], float (&hy)[4])
-{
-    const int nxh = a.nxh, xi0 = 4 * g;
-    const int p = (y + a.colour) & 1;  // x0 = 2 xi + p
-    const int xe = p ? (xi0 + 4 == nxh ? 0 : xi0 + 4) : (xi0 == 0 ? nxh - 1 : xi0 - 1);
-    float es, ec;
-    sincos_turns(a.oth[(size_t)y * nxh + xe], es, ec);
-    // ordered left to right: p = 0: e, m0, m1, m2, m3 ; p = 1: m0, m1, m2, m3, e
-    const float bc[5] = {p ? mid.c[0] : ec, p ? mid.c[1] : mid.c[0], p ? mid.c[2] : mid.c[1], p ? mid.c[3] : mid.c[2], p ? ec : mid.c[3]};
-    const float bs[5] = {p ? mid.s[0] : es, p ? mid.s[1] : mid.s[0], p ? mid.s[2] : mid.s[1], p ? mid.s[3] : mid.s[2], p ? es : mid.s[3]};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        hx[j] = bc[j + 1] + bc[j] + up.c[j] + dn.c[j];
-        hy[j] = bs[j + 1] + bs[j] + up.s[j] + dn.s[j];
-    }
-}
-
 // OVERRELAX = false: update_sub + calc_delta_energy, src/xy2d_periodic_gpu_m.f90:368-397
 // OVERRELAX = true : over_relaxation_sub, :418-439: reflect the spin about the local field.  In angles:
 //                    theta' = 2 phi - theta with phi = atan2(h_y, h_x) (the reference's renormalisation is the identity here)
 // MEASURE (second colour pass of a sweep when the caller measures every MCS): every bond has exactly one end in
 // the colour being updated, so E = -sum over these sites of s_new . h; sum cos / sum sin: the new spins plus the
 // other colour's row `mid` (each of its sites belongs to exactly one thread-row).
-template <bool OVERRELAX, bool MEASURE>
-__global__ void __launch_bounds__(256)
+// cos / sin of an angle known to lie in [0, 1] turns (every producer of stored angles keeps them there, and a
+// candidate is a uniform in (0, 1]): sin.approx / cos.approx keep their 2^-20.5 absolute error on [-2 pi, 2 pi], so no
+// range reduction is needed -- 1 FMUL + 2 MUFU (+ the FMUL.RZ inside the approximation).
+__device__ __forceinline__ void sincos_unit(float t, float& s, float& c)
+{
+#ifdef XY_REDUCE
+    sincos_turns(t, s, c);
+#else
+    __sincosf(t * TWO_PI_F, &s, &c);
+#endif
+}
+
+// atan2(y, x) / (2 pi) in [-1/2, 1/2]: octant reduction, q = min / max by MUFU.RCP, odd polynomial q P(q^2)
+// (Chebyshev fit of atan(q) / (2 pi q) on [0, 1], max error 3e-8 turns evaluated in fp32 -- half an ulp of the
+// stored angle near 1/2), about half the instructions of atan2f.  atan2(0, 0) = 0 like atan2f.
+__device__ __forceinline__ float atan2_turns(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float q = __fdividef(mn, fmaxf(mx, 1e-30f));
+    const float s2 = q * q;
+    float p = -0.0007430583355017006f;
+    p = fmaf(p, s2, 0.0038461685180664062f);
+    p = fmaf(p, s2, -0.009448567405343056f);
+    p = fmaf(p, s2, 0.015766043215990067f);
+    p = fmaf(p, s2, -0.022308088839054108f);
+    p = fmaf(p, s2, 0.03178202360868454f);
+    p = fmaf(p, s2, -0.05304946005344391f);
+    p = fmaf(p, s2, 0.15915492177009583f);
+    float r = p * q;                       // [0, 1/8]
+    r = ay > ax ? 0.25f - r : r;
+    r = x < 0.0f ? 0.5f - r : r;
+    return y < 0.0f ? -r : r;
+}
+
+#ifndef XY_MINB_M
+#define XY_MINB_M 4   // Metropolis: 64 registers
+#endif
+#ifndef XY_MINB_O
+#define XY_MINB_O 3   // over-relaxation and the variants with fused sums: 80 registers
+#endif
+static_assert(XY_ROWS % 2 == 0, "the strip loop is unrolled by two rows (the neighbour pattern alternates with the row parity)");
+
+// One row of a strip.  P = (y + colour) & 1 at compile time: the x position of colour-compact site xi is 2 xi + P, its
+// same-row neighbours are the other colour's xi - 1 + P and xi + P.
+template <bool OVERRELAX, bool MEASURE, int P>
+__device__ __forceinline__ void xy_strip_row(const XYArgs& a, int y, int idx, float nbl2e, const float4 r_up, const float r_edge, const float4 o,
+                                             const XYRow& dn, const XYRow& mid, XYRow& up, float4* po, float& es, float& mx, float& my)
+{
+    sincos_unit(r_up.x, up.s[0], up.c[0]);
+    sincos_unit(r_up.y, up.s[1], up.c[1]);
+    sincos_unit(r_up.z, up.s[2], up.c[2]);
+    sincos_unit(r_up.w, up.s[3], up.c[3]);
+    float se, ce;
+    sincos_unit(r_edge, se, ce);
+    // ordered left to right: P = 0: e, m0, m1, m2, m3 ; P = 1: m0, m1, m2, m3, e
+    // (same summation order as calc_delta_energy, src/xy2d_periodic_gpu_m.f90:395: x+1, x-1, y+1, y-1)
+    float hx[4], hy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float lc = P ? mid.c[j] : (j ? mid.c[j - 1] : ce), ls = P ? mid.s[j] : (j ? mid.s[j - 1] : se);
+        const float rc = P ? (j < 3 ? mid.c[j + 1] : ce) : mid.c[j], rs = P ? (j < 3 ? mid.s[j + 1] : se) : mid.s[j];
+        hx[j] = rc + lc + up.c[j] + dn.c[j];
+        hy[j] = rs + ls + up.s[j] + dn.s[j];
+    }
+    float ov[4] = {o.x, o.y, o.z, o.w};
+    if (OVERRELAX) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float t = 2.0f * atan2_turns(hy[j], hx[j]) - ov[j];                    // (-2, 1]
+            const float fr = t - __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);      // t - rint(t) in [-1/2, 1/2]: 2 FADD, not FRND (XU pipe)
+            ov[j] = fr < 0.0f ? fr + 1.0f : fr;                                           // [0, 1]
+            if (MEASURE) {
+                float sn, cn;
+                sincos_unit(ov[j], sn, cn);
+                es -= cn * hx[j] + sn * hy[j];
+                mx += cn; my += sn;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+            // the RNG block of this group (contract: oracle/rng_contract.c)
+            const uint4 R = philox_tag<TAG_XY>(mk_ctr((uint64_t)idx, a.draw, (uint32_t)a.colour, (uint32_t)sub), a.rk0);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = 2 * sub + e;
+                const uint32_t Ur = e ? R.z : R.x, Uc = e ? R.w : R.y;
+                const float r = ((float)Ur + 1.0f) * 0x1p-32f;       // (0, 1]
+                const float ct = ((float)Uc + 1.0f) * 0x1p-32f;      // candidate angle in turns
+                float cs, cc, ss, sc;
+                sincos_unit(ct, cs, cc);
+                sincos_unit(ov[j], ss, sc);
+                const float de = (cc - sc) * hx[j] + (cs - ss) * hy[j];   // -dE
+                float w;                                                   // exp(-beta dE) = 2^(beta log2(e) (-dE))
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(de * nbl2e));
+                const bool acc = !(r > w);                                 // accept iff r <= exp(-beta dE), :384
+                if (acc) ov[j] = ct;
+                if (MEASURE) {
+                    const float cn = acc ? cc : sc, sn = acc ? cs : ss;
+                    es -= cn * hx[j] + sn * hy[j];
+                    mx += cn; my += sn;
+                }
+            }
+        }
+    }
+    if (MEASURE) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { mx += mid.c[j]; my += mid.s[j]; }
+    }
+    *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
+}
+
+template <bool OVERRELAX, bool MEASURE, int COLOUR>
+__global__ void __launch_bounds__(256, (OVERRELAX || MEASURE) ? XY_MINB_O : XY_MINB_M)
 xy_strip_kernel(const __grid_constant__ XYArgs a)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,63 +209,34 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
     float es = 0.f, mx = 0.f, my = 0.f;
     if (active) {
         const int rb = tid / a.gpr, g = tid - rb * a.gpr;
-        const int y0 = rb * XY_ROWS, y1 = min(y0 + XY_ROWS, a.ny);
+        const int y0 = rb * XY_ROWS, y1 = min(y0 + XY_ROWS, a.ny);   // both even (ny is even)
+        const int nxh = a.nxh, xi0 = 4 * g;
+        const float nbl2e = a.beta * 1.4426950408889634f;
         XYRow dn, mid, up;
         xy_load_row(a, y0 == 0 ? a.ny - 1 : y0 - 1, g, dn);
         xy_load_row(a, y0, g, mid);
-#pragma unroll 2
-        for (int y = y0; y < y1; ++y) {
-            xy_load_row(a, y + 1 == a.ny ? 0 : y + 1, g, up);
-            float hx[4], hy[4];
-            xy_strip_field(a, y, g, dn, mid, up, hx, hy);
-            float4* po = reinterpret_cast<float4*>(a.own + (size_t)y * a.nxh + 4 * g);
-            const float4 o = *po;
-            float ov[4] = {o.x, o.y, o.z, o.w};
-            if (OVERRELAX) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float phi = atan2f(hy[j], hx[j]) * INV_TWO_PI_F;
-                    const float t = 2.0f * phi - ov[j];
-                    ov[j] = t - floorf(t);
-                    if (MEASURE) {
-                        float sn, cn;
-                        sincos_turns(ov[j], sn, cn);
-                        es -= cn * hx[j] + sn * hy[j];
-                        mx += cn; my += sn;
-                    }
-                }
-            } else {
-                const int idx = y * a.gpr + g;   // the RNG block of this group (contract: oracle/rng_contract.c)
-#pragma unroll
-                for (int sub = 0; sub < 2; ++sub) {
-                    const uint4 R = philox_tag<TAG_XY>(mk_ctr((uint64_t)idx, a.draw, (uint32_t)a.colour, (uint32_t)sub), a.rk0);
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int j = 2 * sub + e;
-                        const uint32_t Ur = e ? R.z : R.x, Uc = e ? R.w : R.y;
-                        const float r = ((float)Ur + 1.0f) * 0x1p-32f;       // (0, 1]
-                        const float ct = ((float)Uc + 1.0f) * 0x1p-32f;      // candidate angle in turns
-                        float cs, cc, ss, sc;
-                        sincos_turns(ct, cs, cc);
-                        sincos_turns(ov[j], ss, sc);
-                        const float de = -((cc - sc) * hx[j] + (cs - ss) * hy[j]);
-                        const bool acc = !(r > __expf(-a.beta * de));         // accept iff r <= exp(-beta dE), :384
-                        if (acc) ov[j] = ct;
-                        if (MEASURE) {
-                            const float cn = acc ? cc : sc, sn = acc ? cs : ss;
-                            es -= cn * hx[j] + sn * hy[j];
-                            mx += cn; my += sn;
-                        }
-                    }
-                }
-            }
-            if (MEASURE) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { mx += mid.c[j]; my += mid.s[j]; }
-            }
-            *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
-            dn = mid;
-            mid = up;
+        // the fifth same-row value: left of the group on rows with P = 0, right of it on rows with P = 1
+        const int xe0 = xi0 == 0 ? nxh - 1 : xi0 - 1, xe1 = xi0 + 4 == nxh ? 0 : xi0 + 4;
+        // the raw values of a row (the other colour's row y + 1, the fifth same-row value, the own row) are
+        // loaded one row ahead, unconditionally (clamped row index: straight-line code that the scheduler issues
+        // at the top): the stores to `own` would otherwise pin every load behind them (no restrict on the two
+        // colour arrays) and each row would pay a full DRAM round trip
+        auto ld_up = [&](int y) { return __ldg(reinterpret_cast<const float4*>(a.oth + (size_t)(y + 1 >= a.ny ? y + 1 - a.ny : y + 1) * nxh + xi0)); };
+        auto ld_own = [&](int y) { return *reinterpret_cast<const float4*>(a.own + (size_t)y * nxh + xi0); };
+        float4 u0 = ld_up(y0), o0 = ld_own(y0);
+        float e0 = __ldg(a.oth + (size_t)y0 * nxh + (COLOUR ? xe1 : xe0));
+        for (int y = y0; y < y1; y += 2) {
+            const float4 u1 = ld_up(y + 1), o1 = ld_own(y + 1);
+            const float e1 = __ldg(a.oth + (size_t)(y + 1) * nxh + (COLOUR ? xe0 : xe1));
+            xy_strip_row<OVERRELAX, MEASURE, COLOUR>(a, y, y * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
+                                                     reinterpret_cast<float4*>(a.own + (size_t)y * nxh + xi0), es, mx, my);
+            const int yn = min(y + 2, y1 - 2);
+            u0 = ld_up(yn); o0 = ld_own(yn);
+            e0 = __ldg(a.oth + (size_t)yn * nxh + (COLOUR ? xe1 : xe0));
+            xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1>(a, y + 1, (y + 1) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
+                                                         reinterpret_cast<float4*>(a.own + (size_t)(y + 1) * nxh + xi0), es, mx, my);
+            // rows rotate by two: (dn, mid, up) <- (up of the first row = mid of the second, up of the second)
+            const XYRow t = mid; mid = dn; dn = up; (void)t;
         }
     }
     if (MEASURE) {
@@ -347,7 +417,8 @@ __global__ void xy_import_turns_kernel(float* c0, float* c1, int nx, int ny, con
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)nx * ny) return;
     const int y0 = (int)(i / nx), x0 = (int)(i - (long long)y0 * nx);
-    (((x0 + y0) & 1) ? c1 : c0)[(size_t)y0 * (nx / 2) + (x0 >> 1)] = in[i];
+    const float t = in[i];
+    (((x0 + y0) & 1) ? c1 : c0)[(size_t)y0 * (nx / 2) + (x0 >> 1)] = t - floorf(t);   // stored angles live in [0, 1] turns (sincos_unit)
 }
 
 struct XY {
@@ -388,8 +459,10 @@ int sweep(XY* m)
         const bool fuse = colour == 1 && m->want_fused;
         if (fuse) CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
         COUNT_LAUNCH();
-        if (fuse) xy_strip_kernel<false, true><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
-        else xy_strip_kernel<false, false><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
+        if (colour) {
+            if (fuse) xy_strip_kernel<false, true, 1><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
+            else xy_strip_kernel<false, false, 1><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
+        } else xy_strip_kernel<false, false, 0><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);   // (sums are fused into colour 1 only)
         CK(cudaGetLastError());
         if (fuse) m->fused_pending = true;
     }
@@ -411,8 +484,10 @@ int over_relax(XY* m, int n_steps)
             const bool fuse = colour == 1 && i == n_steps - 1 && m->want_fused;
             if (fuse) CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
             COUNT_LAUNCH();
-            if (fuse) xy_strip_kernel<true, true><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
-            else xy_strip_kernel<true, false><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
+            if (colour) {
+                if (fuse) xy_strip_kernel<true, true, 1><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
+                else xy_strip_kernel<true, false, 1><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
+            } else xy_strip_kernel<true, false, 0><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
             CK(cudaGetLastError());
             if (fuse) m->fused_pending = true;
         }
