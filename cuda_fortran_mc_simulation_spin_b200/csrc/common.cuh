@@ -102,6 +102,16 @@ __device__ __forceinline__ uint4 ld_other(const uint4* p)
                  : "l"(p));
     return r;
 }
+// the same colour when other blocks wrote it earlier in THIS launch (cooperative multi-pass kernel): the nc path may
+// serve stale L1 lines, so read at L2
+__device__ __forceinline__ uint4 ld_other_coherent(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p) : "memory");
+    return r;
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
     uint64_t pol;

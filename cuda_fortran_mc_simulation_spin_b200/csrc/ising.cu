@@ -29,6 +29,7 @@ struct Ising {
     IsingTabF64 tabf;
     unsigned long long* d_acc;  // [X, sum s]
     unsigned long long* h_acc;  // pinned host copy (device -> host read of every measurement)
+    bool h_acc_pending;         // the cooperative sweep kernel stores its fused sums in h_acc itself: measure() only synchronises
     unsigned long long* acc_target;  // where the fused pass / the measure kernel add their sums (d_acc, or a slot of d_series)
     unsigned long long* d_series;    // run_relaxation: [mcs][2] sums, one slot per MCS
     int64_t series_cap;
@@ -38,6 +39,7 @@ struct Ising {
     int tune;  // debug knobs from env B200MC_TUNE: bit0 = static round-robin (no ticket)
     int chunk; // vectors per ticket (env B200MC_CHUNK, default 128)
     int grid;
+    int coop_grid;  // resident grid of the cooperative small-lattice sweep kernel (0: not available)
     int slab_nb;    // slab mode: blocks of the one-launch pass that start on the boundary tickets (env B200MC_SLAB_NB; 0 = from the boundary's share of the slab)
     int grid_push;  // resident grid of the fused update + halo-push kernel (its register budget differs)
     bool use_tma;   // single-GPU launches go through the copy-engine staged kernel
@@ -380,18 +382,86 @@ int launch_pass(Ising* m, int colour, bool fuse)
     return B200MC_OK;
 }
 
+// Small lattices: n sweeps in one cooperative launch (ising_coop_kernel).  series: per-sweep sums (run_relaxation);
+// fuse_last: the last sweep's sums go to acc_target.
+static bool coop_usable(const Ising* m)
+{
+    const RingGeom& g = m->st.g;
+    return m->coop_grid > 0 && g.nranks == 1 && m->n_multi == 1 && !m->st.p2p && !m->use_tma && !m->timing && !(m->tune & 2048) &&
+           g.Lloc <= (int64_t)m->coop_grid * 256 * 2;
+}
+
+int coop_sweeps(Ising* m, int n, bool fuse_last, unsigned long long* series)
+{
+    const RingGeom& g = m->st.g;
+    IsingCoopArgs s;
+    for (int c = 0; c < 2; ++c) {
+        RingPassArgs& a = s.a[c];
+        a = RingPassArgs();
+        a.own = m->st.vec[c];
+        a.oth = m->st.vec[c ^ 1];
+        a.nvec = g.Lloc;
+        a.H = g.H;
+        a.p0 = g.p0;
+        for (int j = 0; j < 6; ++j) a.off[j] = g.off[c][j];
+        a.seed = m->seed;
+        a.colour = (uint32_t)c;
+        a.draw = m->draw;
+        a.ticket = nullptr;
+        a.chunk = 32;
+        a.acc = m->acc_target;
+        a.rstride = m->st.rstride;
+        a.Lfold = g.L; a.Nc = g.Nc;
+        a.mask_from = g.ptail < g.L ? (int)(g.ptail - a.p0 > 0 ? g.ptail - a.p0 : 0) : 0x7FFFFFFF;
+        a.nopush = 2;
+    }
+    s.L = g.L; s.H = g.H; s.Nc = g.Nc; s.ptail = g.ptail;
+    s.halo_fast = (g.H <= g.L && g.ptail >= g.H) ? 1 : 0;
+    s.n_sweeps = n; s.fuse_last = fuse_last ? 1 : 0; s.series = series;
+    m->obs_valid = false;
+    m->fused_pending = false;
+    s.host_out = (fuse_last && !series && m->acc_target == m->d_acc) ? m->h_acc : nullptr;
+    m->h_acc_pending = false;
+    const int64_t need = (g.Lloc + 255) / 256;
+    const int grid = (int)(need < (int64_t)m->coop_grid ? need : (int64_t)m->coop_grid);
+    void* args[2] = {&s, &m->tab};
+    const void* fn = m->ndim == 3
+        ? (m->method == METHOD_METROPOLIS ? (const void*)ising_coop_kernel<6, METHOD_METROPOLIS> : (const void*)ising_coop_kernel<6, METHOD_HEATBATH>)
+        : (m->method == METHOD_METROPOLIS ? (const void*)ising_coop_kernel<4, METHOD_METROPOLIS> : (const void*)ising_coop_kernel<4, METHOD_HEATBATH>);
+    COUNT_LAUNCH();
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, m->stream));
+    m->fused_pending = fuse_last && !series;
+    m->h_acc_pending = s.host_out != nullptr;
+    m->draw += (uint64_t)n;
+    return B200MC_OK;
+}
+
 // One MCS.  allow_fuse: this is the last sweep before control returns to the caller.
 int sweep(Ising* m, bool allow_fuse = true, bool force_fuse = false)
 {
     int rc;
     if (m->fused_pending) m->want_fused = false;  // the sums of the previous sweep were never asked for
     const bool fuse = force_fuse || (allow_fuse && m->want_fused && m->fuse_ok && !(m->tune & 8));
+    if (coop_usable(m)) return coop_sweeps(m, 1, fuse, nullptr);
     for (int colour = 0; colour < 2; ++colour) {
         rc = m->ndim == 3 ? launch_pass<6>(m, colour, fuse && colour == 1) : launch_pass<4>(m, colour, fuse && colour == 1);
         if (rc) return rc;
     }
     m->fused_pending = fuse;
     m->draw += 1;
+    return B200MC_OK;
+}
+
+// n MCS (update_n): small lattices in one cooperative launch, else sweep by sweep
+int sweeps_n(Ising* m, int32_t n)
+{
+    if (n <= 0) return B200MC_OK;
+    if (coop_usable(m)) {
+        if (m->fused_pending) m->want_fused = false;
+        const bool fuse = m->want_fused && m->fuse_ok && !(m->tune & 8);
+        return coop_sweeps(m, n, fuse, nullptr);
+    }
+    for (int i = 0; i < n; ++i) { int rc = sweep(m, i == n - 1); if (rc) return rc; }
     return B200MC_OK;
 }
 
@@ -432,6 +502,8 @@ int measure(Ising* m, int64_t* e, int64_t* mag)
         if (mag) *mag = m->obs_m;
         return B200MC_OK;
     }
+    const bool direct = m->fused_pending && m->h_acc_pending && g.nranks == 1 && m->n_multi == 1;  // already stored in h_acc by the kernel
+    m->h_acc_pending = false;
     if (!m->fused_pending) {
         { int rcq = ring_p2p_quiesce(&m->st, m->stream); if (rcq) return rcq; }
         CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long) * m->n_multi, m->stream));
@@ -444,7 +516,7 @@ int measure(Ising* m, int64_t* e, int64_t* mag)
         if (rc) return rc;
     }
     unsigned long long* acc = m->h_acc;
-    CK(cudaMemcpyAsync(acc, m->d_acc, 2 * sizeof(unsigned long long) * m->n_multi, cudaMemcpyDeviceToHost, m->stream));
+    if (!direct) CK(cudaMemcpyAsync(acc, m->d_acc, 2 * sizeof(unsigned long long) * m->n_multi, cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
     m->obs_ev.resize(m->n_multi); m->obs_mv.resize(m->n_multi);
     for (int j = 0; j < m->n_multi; ++j) {
@@ -494,7 +566,12 @@ int run_relaxation(Ising* m, int32_t mcs, int64_t* e, int64_t* mag)
     CK(cudaMemsetAsync(m->d_series, 0, (size_t)mcs * per * sizeof(unsigned long long), m->stream));
     const bool fuse = m->fuse_ok && !(m->tune & 8);
     int rc = B200MC_OK;
-    for (int32_t i = 0; i < mcs && !rc; ++i) {
+    const bool coop = fuse && coop_usable(m);
+    if (coop) {  // small lattice: the whole relaxation is one cooperative launch
+        if (m->fused_pending) m->want_fused = false;
+        rc = coop_sweeps(m, mcs, false, m->d_series);
+    }
+    for (int32_t i = 0; i < mcs && !rc && !coop; ++i) {
         m->acc_target = m->d_series + per * (size_t)i;
         m->fused_pending = false;
         rc = sweep(m, true, fuse);
@@ -541,7 +618,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     Ising* m = new (std::nothrow) Ising();
     if (!m) ARG_FAIL("out of host memory");
     m->ndim = ndim; m->nx = nx; m->ny = ny; m->nz = ndim == 3 ? nz : 0;
-    m->stream = 0; m->d_acc = nullptr; m->h_acc = nullptr; m->acc_target = nullptr; m->d_series = nullptr; m->series_cap = 0; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
+    m->stream = 0; m->d_acc = nullptr; m->h_acc = nullptr; m->h_acc_pending = false; m->acc_target = nullptr; m->d_series = nullptr; m->series_cap = 0; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
     { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; t = getenv("B200MC_CHUNK"); m->chunk = t ? atoi(t) : 128; m->chunk = TK_CHUNK;  /* compile-time now */
     }
     m->method = METHOD_METROPOLIS; m->seed = (uint32_t)iseed; m->draw = 0; m->alive = true;
@@ -599,6 +676,14 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, ising_pass_kernel<4, METHOD_METROPOLIS, true, true>, 256, 0);
     if (occp < 1) occp = 1;
     m->grid_push = (int)(need < (int64_t)sms * occp ? need : (int64_t)sms * occp);
+    {   // cooperative small-lattice sweep kernel: all blocks must be resident
+        int coop_ok = 0, occc = 0;
+        cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, dev);
+        if (ndim == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occc, ising_coop_kernel<6, METHOD_METROPOLIS>, 256, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occc, ising_coop_kernel<4, METHOD_METROPOLIS>, 256, 0);
+        m->coop_grid = (coop_ok && occc >= 1) ? sms * (occc > 2 ? 2 : occc) : 0;
+        cudaGetLastError();
+    }
     { const char* t = getenv("B200MC_SLAB_NB"); m->slab_nb = t ? atoi(t) : 0; }
     m->use_tma = false; m->tma_grid = 0;
     if (nranks == 1 && n_multi == 1 && (m->tune & 128)) {
@@ -750,7 +835,7 @@ int b200mc_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
     int PFX##_set_kbt(void* h, double kbt) { CHECK_H(h, ND); if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0"); H(h)->beta = 1 / kbt; return build_tables(H(h)); } \
     int PFX##_set_method(void* h, int32_t method) { CHECK_H(h, ND); if (method != METHOD_METROPOLIS && method != METHOD_HEATBATH) ARG_FAIL("unknown method %d", method); H(h)->method = method; return build_tables(H(h)); } \
     int PFX##_update(void* h) { CHECK_H(h, ND); return sweep(H(h)); }                             \
-    int PFX##_update_n(void* h, int32_t n) { CHECK_H(h, ND); for (int i = 0; i < n; ++i) { int rc = sweep(H(h), i == n - 1); if (rc) return rc; } return B200MC_OK; } \
+    int PFX##_update_n(void* h, int32_t n) { CHECK_H(h, ND); return sweeps_n(H(h), n); } \
     int PFX##_update_with_randoms(void* h, const double* r) { CHECK_H(h, ND); return update_with_randoms(H(h), r); } \
     int PFX##_calc_energy_sum(void* h, int64_t* e) { CHECK_H(h, ND); return measure(H(h), e, nullptr); } \
     int PFX##_calc_magne_sum(void* h, int64_t* m) { CHECK_H(h, ND); return measure(H(h), nullptr, m); } \

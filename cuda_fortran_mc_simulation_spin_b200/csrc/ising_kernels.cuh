@@ -19,6 +19,8 @@
 // (a byte) and thr & (2^25 - 1).
 #pragma once
 #include "common.cuh"
+#include "ring.cuh"
+#include <cooperative_groups.h>
 
 struct IsingTab {
     uint32_t tlo, thi;     // bytes T'(idx) for idx = 0..3 / 4..7
@@ -311,7 +313,7 @@ __device__ __forceinline__ void ising_core(int v, uint4* po, uint4 o, const uint
     }
 }
 
-template <int NNB, int METHOD, bool PUSH, bool MEASURE, bool FULLWARP>
+template <int NNB, int METHOD, bool PUSH, bool MEASURE, bool FULLWARP, bool COHERENT = false>
 __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (&q)[NNB], uint32_t cx, uint32_t cz, uint32_t cw,
                                           const RingPassArgs& a, const IsingTab& tab, uint64_t pol, uint32_t qaddr,
                                           uint32_t cntaddr, bool is_b, uint32_t& accX, uint32_t& accM, uint32_t cy = 0u)
@@ -321,7 +323,7 @@ __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (
     // (loading the x+ vector as a shuffle of the neighbouring lane's x- vector instead of a second, overlapping
     // 512-byte load was tried: 4 SHFL + a one-lane load made the pass 20 % slower -- the MIO queue is the busiest unit)
 #pragma unroll
-    for (int j = 0; j < NNB; ++j) nb[j] = ld_other(q[j]);
+    for (int j = 0; j < NNB; ++j) nb[j] = COHERENT ? ld_other_coherent(q[j]) : ld_other(q[j]);
     ising_core<NNB, METHOD, PUSH, MEASURE>(v, po, o, nb, cx, cz, cw, a, tab, pol, qaddr, cntaddr, is_b, accX, accM, cy);
 }
 
@@ -339,10 +341,12 @@ __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (
 #endif
 // The body of a colour pass: everything one block does for the vectors (tickets) of `a`.  tq / tq_cnt: the block's
 // tie queues (8 warps x TQ_CAP records) and their fill counts in shared memory.
-template <int NNB, int METHOD, bool ORDERED, bool PUSH, bool MEASURE, bool BATCH>
+template <int NNB, int METHOD, bool ORDERED, bool PUSH, bool MEASURE, bool BATCH, int CH = TK_CHUNK>
 __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const IsingTab& tab, uint4 (*tq)[TQ_CAP][2], uint32_t* tq_cnt)
 {
     static_assert(!PUSH || ORDERED, "the fused update + halo push kernel uses ticket scheduling");
+    static_assert(CH % 32 == 0 && (CH == TK_CHUNK || !ORDERED), "tickets are TK_CHUNK vectors");
+    constexpr bool COH = CH != TK_CHUNK;   // 32-vector chunks = the cooperative multi-pass kernel: the other colour was written in this launch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(&tq[warp][0][0]);
     uint32_t cntaddr = (uint32_t)__cvta_generic_to_shared(&tq_cnt[warp]);
@@ -380,8 +384,8 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
     // chunks c, c + NCNT, c + 2 NCNT, ...; one same-address atomic stream would cap the ticket rate
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
     unsigned int* tk = a.ticket + (gwarp % TK_NCNT) * 64;
-    const int tk_base = (gwarp % TK_NCNT) * TK_CHUNK, tk_scale = TK_NCNT;
-    const int vlimit = PUSH ? a.q_total * TK_CHUNK : nvec;  // PUSH: tickets count VIRTUAL chunks
+    const int tk_base = (gwarp % TK_NCNT) * CH, tk_scale = TK_NCNT;
+    const int vlimit = PUSH ? a.q_total * CH : nvec;  // PUSH: tickets count VIRTUAL chunks
     uint32_t accX = 0, accM = 0;  // MEASURE: this lane's sums (< 2^31: at most ~10^5 sites per lane and launch)
     int corrX = 0, corrM = 0;
     constexpr int DN = MEASURE ? NNB : 0;
@@ -405,21 +409,21 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
     int cur, nxt = 0, nx2 = 0;
     if (ORDERED) {
         if (lane == 0) {
-            nxt = (int)atomicAdd(tk, (unsigned)TK_CHUNK) * tk_scale + tk_base;
-            nx2 = (int)atomicAdd(tk, (unsigned)TK_CHUNK) * tk_scale + tk_base;
+            nxt = (int)atomicAdd(tk, (unsigned)CH) * tk_scale + tk_base;
+            nx2 = (int)atomicAdd(tk, (unsigned)CH) * tk_scale + tk_base;
         }
         cur = __shfl_sync(0xffffffffu, nxt, 0);
         nxt = __shfl_sync(0xffffffffu, nx2, 0);
     } else {
-        cur = gwarp * TK_CHUNK;
-        nxt = cur + nwarps_grid * TK_CHUNK;
+        cur = gwarp * CH;
+        nxt = cur + nwarps_grid * CH;
     }
     while (cur < vlimit) {
-        if (ORDERED && lane == 0) nx2 = (int)atomicAdd(tk, (unsigned)TK_CHUNK) * tk_scale + tk_base;  // two tickets ahead
+        if (ORDERED && lane == 0) nx2 = (int)atomicAdd(tk, (unsigned)CH) * tk_scale + tk_base;  // two tickets ahead
         if (nxt < vlimit) {
             bool bn;
             const int bnext = chunk_base(nxt, bn);
-            if (bnext >= 0 && bnext + TK_CHUNK <= nvec && !(a.nopush & 2))
+            if (CH == TK_CHUNK && bnext >= 0 && bnext + CH <= nvec && !(a.nopush & 2))
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + (size_t)bnext * 16));
         }
         bool is_b;
@@ -431,16 +435,16 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
 #pragma unroll
         for (int j = 0; j < NNB; ++j) q[j] = pn[j] + v0;
         const uint32_t cx = cx0 + (uint32_t)v0;
-        if (base + TK_CHUNK <= nvec && !(PUSH && is_b)) {
+        if (base + CH <= nvec && !(PUSH && is_b)) {
             // full (interior) chunk: no bounds checks, no halo push, the queue is looked at every second vector
 #pragma unroll
-            for (int u = 0; u < TK_CHUNK / 32; ++u) {
+            for (int u = 0; u < CH / 32; ++u) {
                 const uint4* qu[NNB];
 #pragma unroll
                 for (int j = 0; j < NNB; ++j) qu[j] = q[j] + 32 * u;
-                ising_vec<NNB, METHOD, false, MEASURE, true>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
+                ising_vec<NNB, METHOD, false, MEASURE, true, COH>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
                                                              cntaddr, false, accX, accM, rep);
-                if (u & 1) {
+                if ((u & 1) || CH < 64) {   // (a 32-vector chunk is one vector per lane: look at the queue after it)
                     __syncwarp();
                     if (lds32(cntaddr) > TQ_CAP - 64) {
                         const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab, rep);
@@ -450,12 +454,12 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
             }
         } else {
 #pragma unroll 1
-            for (int u = 0; u < TK_CHUNK / 32; ++u) {
+            for (int u = 0; u < CH / 32; ++u) {
                 if (v0 + 32 * u < nvec) {
                     const uint4* qu[NNB];
 #pragma unroll
                     for (int j = 0; j < NNB; ++j) qu[j] = q[j] + 32 * u;
-                    ising_vec<NNB, METHOD, PUSH, MEASURE, false>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
+                    ising_vec<NNB, METHOD, PUSH, MEASURE, false, COH>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
                                                                  cntaddr, is_b, accX, accM, rep);
                 }
                 __syncwarp();
@@ -482,7 +486,7 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
         }
         cur = nxt;
         if (ORDERED) nxt = __shfl_sync(0xffffffffu, nx2, 0);
-        else nxt += nwarps_grid * TK_CHUNK;
+        else nxt += nwarps_grid * CH;
     }
     const int2 d = ising_drain<METHOD, PUSH, DN>(qaddr, cntaddr, own, a, tab, rep);
     if (MEASURE) {
@@ -528,6 +532,66 @@ ising_slab_kernel(const __grid_constant__ RingPassArgs ab, const __grid_constant
     __shared__ uint32_t tq_cnt[8];
     if ((int)blockIdx.x < nb_blocks) ising_slab_boundary<NNB, METHOD, MEASURE>(ab, tab, tq, tq_cnt);
     ising_pass_body<NNB, METHOD, true, false, MEASURE, false>(ai, tab, tq, tq_cnt);
+}
+
+// Small lattices (at most a few vectors per resident thread): n_sweeps whole sweeps in ONE cooperative launch.
+// At the reference's default sizes (app/ising2d_gpu_relaxation.f90:6-7: 1001 x 1000) a colour pass is ~1 us of
+// work, and the per-sweep sequence of the plain path -- two pass launches, two to four halo launches, memsets -- is
+// bound by launch latency (27 us per MCS).  Here every block runs colour pass -> grid barrier -> halo refresh ->
+// grid barrier, twice per sweep, for all sweeps; static 32-vector chunks (one vector per lane) spread the lattice
+// over the whole grid.  Sums: `series` != nullptr -> sweep i adds {X, sum s} to series[2 i], series[2 i + 1]
+// (run_relaxation); else fuse_last -> the last sweep adds them to a[1].acc (update + calc_*_sum).
+struct IsingCoopArgs {
+    RingPassArgs a[2];          // per colour; draw = the first sweep's
+    int64_t L, H, Nc, ptail;    // halo refresh (single GPU: the whole fold)
+    int halo_fast;              // H <= L && ptail >= H: vector-granular halo + byte-granular tail, else all byte-granular
+    int n_sweeps, fuse_last;
+    unsigned long long* series;
+    unsigned long long* host_out;   // fuse_last: the two sums are also stored here (pinned host memory) by the kernel itself
+};
+
+template <int NNB, int METHOD>
+__global__ void __launch_bounds__(256, 2)
+ising_coop_kernel(const __grid_constant__ IsingCoopArgs s, const __grid_constant__ IsingTab tab)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint4 tq[8][TQ_CAP][2];
+    __shared__ uint32_t tq_cnt[8];
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
+    // fuse_last: the accumulators are cleared here (the pass that adds to them comes after at least one grid barrier)
+    if (s.fuse_last && !s.series && gtid == 0) { s.a[1].acc[0] = 0ull; s.a[1].acc[1] = 0ull; }
+    for (int i = 0; i < s.n_sweeps; ++i) {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            RingPassArgs b = s.a[c];
+            b.draw += (uint64_t)i;
+            const bool meas = c == 1 && (s.series != nullptr || (s.fuse_last && i == s.n_sweeps - 1));
+            if (meas) {
+                if (s.series) b.acc = s.series + 2 * (size_t)i;
+                ising_pass_body<NNB, METHOD, false, false, true, false, 32>(b, tab, tq, tq_cnt);
+            } else {
+                ising_pass_body<NNB, METHOD, false, false, false, false, 32>(b, tab, tq, tq_cnt);
+            }
+            grid.sync();
+            // update_norishiro (src/ising3d_gpu_m.f90:102-122) for the colour just written
+            uint4* vec = b.own;
+            if (s.halo_fast) {
+                for (int64_t v = gtid; v < 2 * s.H; v += gthreads) ring_halo_fast_item(vec, s.L, s.H, s.Nc, v);
+                for (int64_t t = gtid; t < (s.L - s.ptail) * 16; t += gthreads)
+                    ring_halo_generic_item(reinterpret_cast<uint8_t*>(vec), s.L, s.H, s.Nc, s.ptail, 2 * s.H, t);
+            } else {
+                for (int64_t t = gtid; t < (2 * s.H + s.L - s.ptail) * 16; t += gthreads)
+                    ring_halo_generic_item(reinterpret_cast<uint8_t*>(vec), s.L, s.H, s.Nc, s.ptail, 0, t);
+            }
+            grid.sync();
+        }
+    }
+    // (after the last barrier every block's atomics have landed)
+    if (s.fuse_last && !s.series && s.host_out && gtid == 0) {
+        s.host_out[0] = __ldcg(s.a[1].acc);
+        s.host_out[1] = __ldcg(s.a[1].acc + 1);
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -97,18 +97,8 @@ int ring_fill(RingStore* s, uint8_t value, cudaStream_t st)
 // ---------------------------------------------------------------------------
 // halo refresh
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int64_t pos_mod(int64_t a, int64_t m)
-{
-    int64_t r = a % m;
-    return r < 0 ? r + m : r;
-}
-
-// value of ring site k (of this colour) read from its owning (lane, position)
-__device__ __forceinline__ uint8_t ring_site(const uint8_t* base, int64_t L, int64_t H, int64_t k)
-{
-    const int64_t b = k / L, p = k - b * L;
-    return base[(p + H) * 16 + b];
-}
+// (pos_mod, ring_site and the per-item halo functions live in ring.cuh: the cooperative small-lattice sweep kernel
+// of ising_kernels.cuh refreshes the halo between its colour passes with the same code)
 
 // generic, byte-granular: one thread per (dirty vector, lane).  Dirty vectors
 // are the 2H halo vectors and the tail positions [ptail, L).
@@ -118,15 +108,7 @@ __global__ void ring_halo_generic_kernel(uint8_t* base, int64_t L, int64_t H, in
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_items) return;
     base += (size_t)blockIdx.y * (size_t)rstride * 16;   // sample of the batch
-    const int b = (int)(t & 15);
-    int64_t v = v_begin + (t >> 4);  // dirty-vector ordinal
-    int64_t p;
-    if (v < H) p = v - H;
-    else if (v < 2 * H) p = L + (v - H);
-    else p = ptail + (v - 2 * H);
-    const int64_t kraw = (int64_t)b * L + p;
-    if (p >= 0 && p < L && kraw < Nc) return;  // a real site: owned, not a copy
-    base[(p + H) * 16 + b] = ring_site(base, L, H, pos_mod(kraw, Nc));
+    ring_halo_generic_item(base, L, H, Nc, ptail, v_begin, t);
 }
 
 // fast path (needs H <= L): one thread per halo vector; a halo vector is the
@@ -136,30 +118,7 @@ __global__ void ring_halo_fast_kernel(uint4* vec, int64_t L, int64_t H, int64_t 
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= 2 * H) return;
     vec += (size_t)blockIdx.y * (size_t)rstride;         // sample of the batch
-    const uint8_t* base = reinterpret_cast<const uint8_t*>(vec);
-    if (v < H) {
-        // low halo, p = v - H < 0: lane b <- lane b-1 at p + L; lane 0 <- site Nc + p
-        const int64_t p = v - H;
-        const uint4 s = vec[p + L + H];
-        uint4 o;
-        o.w = __funnelshift_l(s.z, s.w, 8);
-        o.z = __funnelshift_l(s.y, s.z, 8);
-        o.y = __funnelshift_l(s.x, s.y, 8);
-        o.x = (s.x << 8) | ring_site(base, L, H, pos_mod(p, Nc));
-        vec[v] = o;
-    } else {
-        // high halo, p = L + (v - H): lane b <- lane b+1 at p - L; lanes 14, 15 patched
-        const int64_t p = L + (v - H);
-        const uint4 s = vec[p - L + H];
-        uint4 o;
-        o.x = __funnelshift_r(s.x, s.y, 8);
-        o.y = __funnelshift_r(s.y, s.z, 8);
-        o.z = __funnelshift_r(s.z, s.w, 8);
-        const uint32_t b14 = ring_site(base, L, H, pos_mod(14 * L + p, Nc));
-        const uint32_t b15 = ring_site(base, L, H, pos_mod(15 * L + p, Nc));
-        o.w = ((s.w >> 8) & 0x0000FFFFu) | (b14 << 16) | (b15 << 24);
-        vec[p + H] = o;
-    }
+    ring_halo_fast_item(vec, L, H, Nc, v);
 }
 
 // ---- NCCL through dlsym -------------------------------------------------------------------

@@ -61,6 +61,74 @@ struct RingStore {
 
 enum RingValueMap { RING_MAP_IDENTITY = 0, RING_MAP_PM1 = 1 };  // PM1: stored 0/1 <-> -1/+1
 
+// ---------------------------------------------------------------------------
+// halo refresh, per work item (kernels: ring.cu; also called between the colour passes of the cooperative
+// small-lattice sweep kernel, ising_kernels.cuh)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int64_t pos_mod(int64_t a, int64_t m)
+{
+    if (m < (int64_t)0x40000000 && a > -(int64_t)0x40000000 && a < (int64_t)0x40000000) {   // small rings: 32-bit division
+        const int r32 = (int)a % (int)m;
+        return r32 < 0 ? r32 + (int)m : r32;
+    }
+    int64_t r = a % m;
+    return r < 0 ? r + m : r;
+}
+
+// value of ring site k (of this colour) read from its owning (lane, position)
+__device__ __forceinline__ uint8_t ring_site(const uint8_t* base, int64_t L, int64_t H, int64_t k)
+{
+    int64_t b, p;
+    if (k < (int64_t)0x7FFFFFFF) { const unsigned b32 = (unsigned)k / (unsigned)L; b = b32; p = (unsigned)k - b32 * (unsigned)L; }
+    else { b = k / L; p = k - b * L; }
+    return __ldcg(base + (p + H) * 16 + b);   // L2: also called between the passes of the cooperative sweep kernel
+}
+
+// generic, byte-granular: item t = (dirty vector, lane).  Dirty vectors are the 2H halo vectors and the tail
+// positions [ptail, L).
+__device__ __forceinline__ void ring_halo_generic_item(uint8_t* base, int64_t L, int64_t H, int64_t Nc, int64_t ptail, int64_t v_begin, int64_t t)
+{
+    const int b = (int)(t & 15);
+    int64_t v = v_begin + (t >> 4);  // dirty-vector ordinal
+    int64_t p;
+    if (v < H) p = v - H;
+    else if (v < 2 * H) p = L + (v - H);
+    else p = ptail + (v - 2 * H);
+    const int64_t kraw = (int64_t)b * L + p;
+    if (p >= 0 && p < L && kraw < Nc) return;  // a real site: owned, not a copy
+    base[(p + H) * 16 + b] = ring_site(base, L, H, pos_mod(kraw, Nc));
+}
+
+// fast path (needs H <= L and ptail >= H): item v = one halo vector; a halo vector is the source vector with its
+// lanes rotated by one, plus one or two patched lanes.  Reads real sites only.
+__device__ __forceinline__ void ring_halo_fast_item(uint4* vec, int64_t L, int64_t H, int64_t Nc, int64_t v)
+{
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(vec);
+    if (v < H) {
+        // low halo, p = v - H < 0: lane b <- lane b-1 at p + L; lane 0 <- site Nc + p
+        const int64_t p = v - H;
+        const uint4 s = __ldcg(vec + (p + L + H));
+        uint4 o;
+        o.w = __funnelshift_l(s.z, s.w, 8);
+        o.z = __funnelshift_l(s.y, s.z, 8);
+        o.y = __funnelshift_l(s.x, s.y, 8);
+        o.x = (s.x << 8) | ring_site(base, L, H, pos_mod(p, Nc));
+        vec[v] = o;
+    } else {
+        // high halo, p = L + (v - H): lane b <- lane b+1 at p - L; lanes 14, 15 patched
+        const int64_t p = L + (v - H);
+        const uint4 s = __ldcg(vec + (p - L + H));
+        uint4 o;
+        o.x = __funnelshift_r(s.x, s.y, 8);
+        o.y = __funnelshift_r(s.y, s.z, 8);
+        o.z = __funnelshift_r(s.z, s.w, 8);
+        const uint32_t b14 = ring_site(base, L, H, pos_mod(14 * L + p, Nc));
+        const uint32_t b15 = ring_site(base, L, H, pos_mod(15 * L + p, Nc));
+        o.w = ((s.w >> 8) & 0x0000FFFFu) | (b14 << 16) | (b15 << 24);
+        vec[p + H] = o;
+    }
+}
+
 int ring_geom_init(RingGeom* g, int64_t nx, int64_t ny, int64_t nz /*0 for 2D*/);
 // split the fold across ranks (needs 16 | Nc and Lloc >= H on every rank)
 int ring_geom_set_slab(RingGeom* g, int rank, int nranks);

@@ -38,12 +38,21 @@ def test_device_philox_kat():
         assert o.tolist() == want
 
 
+@pytest.fixture(params=["coop", "launches"])
+def pass_path(request, monkeypatch):
+    """small lattices run whole sweeps in one cooperative launch (ising_coop_kernel); B200MC_TUNE bit 11 forces the
+    launch-per-colour-pass path that large lattices use, so that both are checked against the oracle"""
+    if request.param == "launches":
+        monkeypatch.setenv("B200MC_TUNE", "2048")
+    return request.param
+
+
 SHAPES3 = [(3, 3, 2), (5, 5, 4), (7, 5, 6), (31, 31, 30), (33, 31, 34), (63, 65, 64), (101, 101, 100)]
 
 
 @pytest.mark.parametrize("shape", SHAPES3)
 @pytest.mark.parametrize("start", ["allup", "random"])
-def test_ising3d_trajectory_bit_exact(oracle, shape, start):
+def test_ising3d_trajectory_bit_exact(oracle, shape, start, pass_path):
     _, i3 = _mods()
     nx, ny, nz = shape
     g = i3.ising3d_gpu().init(nx, ny, nz, KBT3, 42)
@@ -64,7 +73,7 @@ def test_ising3d_trajectory_bit_exact(oracle, shape, start):
 
 @pytest.mark.parametrize("shape", [(5, 4), (7, 6), (33, 32), (255, 256), (1001, 1000)])
 @pytest.mark.parametrize("start", ["allup", "random"])
-def test_ising2d_trajectory_bit_exact(oracle, shape, start):
+def test_ising2d_trajectory_bit_exact(oracle, shape, start, pass_path):
     i2, _ = _mods()
     nx, ny = shape
     g = i2.ising2d_gpu().init(nx, ny, KBT2, 42)
@@ -139,7 +148,7 @@ def test_spins_roundtrip_and_observables(oracle):
 
 
 @pytest.mark.parametrize("dim", [2, 3])
-def test_heatbath_bit_exact(oracle, dim):
+def test_heatbath_bit_exact(oracle, dim, pass_path):
     """heat-bath has no reference symbol: kernel vs our own oracle definition"""
     i2, i3 = _mods()
     if dim == 3:
@@ -212,7 +221,7 @@ def test_full_size_properties_headline():
 
 
 @pytest.mark.parametrize("dim,method", [(3, 0), (3, 1), (2, 0), (2, 1)])
-def test_fused_measurement_equals_separate_pass(oracle, dim, method):
+def test_fused_measurement_equals_separate_pass(oracle, dim, method, pass_path):
     """Once the caller measures after an update, the second colour pass of the following sweeps
     accumulates X and sum(s) itself (deferred tie accepts included).  Shapes without site-less tail
     positions (Nc % 16 == 0) take that path; the sums must equal the oracle's and a recount of the
@@ -240,7 +249,7 @@ def test_fused_measurement_equals_separate_pass(oracle, dim, method):
 
 
 @pytest.mark.parametrize("dim,shape", [(3, (63, 65, 64)), (3, (31, 31, 30)), (2, (255, 256)), (2, (1001, 1000))])
-def test_run_relaxation_series(oracle, dim, shape):
+def test_run_relaxation_series(oracle, dim, shape, pass_path):
     """the drivers' loop on the device: per-MCS E and M series == update + measure step by step (fused second-pass
     sums where Nc % 16 == 0, the measure kernel otherwise), and the state afterwards is the same"""
     i2, i3 = _mods()
