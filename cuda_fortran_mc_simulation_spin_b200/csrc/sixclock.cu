@@ -46,6 +46,7 @@ struct SixArgs {
     const uint8_t* cls;      // q^6 class ids: c + q(new + q(r + q(u + q(l + q d))))   (states_to_prob index order, :72-80)
     const uint32_t* thi;     // per class: thr >> 16  (0 .. 65536)
     const uint32_t* tlo;     // per class: thr & 0xFFFF
+    const uint16_t* thr16;   // q^6 entries min(thr >> 16, 65535) (direct lookup, q <= 6)
     uint32_t tab_bytes;
     int cls_in_smem;
     uint64_t draw;
@@ -130,87 +131,122 @@ __device__ __noinline__ uint32_t six_site_exact(const SixArgs& a, const uint8_t*
 #ifndef SIX_MINB
 #define SIX_MINB 3
 #endif
-template <bool SMEM>
-__global__ void __launch_bounds__(256, SIX_MINB)
-sixclock_pass_kernel(const __grid_constant__ SixArgs a)
+// Acceptance lookup.  DIRECT = false: q^6 one-byte class ids (shared or global memory) + per-class thresholds in shared
+// memory: two dependent loads per site.  DIRECT = true (2 q^6 bytes fit in shared memory: q <= 6): the high 16 bits of
+// every threshold, capped at 65535, in ONE shared-memory table -- one load per site; a capped or equal entry compares
+// as a tie and goes through the exact path like every other undecided site.
+struct SixSmem {
+    uint32_t cls_addr;        // shared-window address of the class table / the direct u16 table
+    const uint32_t* sthi;
+    const uint8_t* gcls;
+};
+
+// one vector = 16 sites of row (rep, y) at compact position 16 v .. 16 v + 15.  P = (y + colour) & 1: the x position of
+// compact site xi is 2 xi + P; right = x0 + 1, left = x0 - 1.
+template <bool SMEM, bool DIRECT, int P>
+__device__ __forceinline__ void six_vector(const SixArgs& a, const SixSmem& sm, int Y, int y, int rep, int v)
 {
-    extern __shared__ __align__(16) uint8_t sm[];
-    uint32_t* sthi = reinterpret_cast<uint32_t*>(sm);            // SIX_MAX_CLASSES words
-    uint8_t* scls = sm + SIX_MAX_CLASSES * sizeof(uint32_t);     // q^6 bytes (if cls_in_smem)
-    for (int i = threadIdx.x; i < SIX_MAX_CLASSES; i += blockDim.x) sthi[i] = a.thi[i];
-    if (SMEM) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.cls);
-        uint4* dst = reinterpret_cast<uint4*>(scls);
-        for (uint32_t i = threadIdx.x; i < (a.tab_bytes + 15) / 16; i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    const uint8_t* cls = SMEM ? scls : a.cls;
-    const uint32_t scls_addr = (uint32_t)__cvta_generic_to_shared(scls);
     const uint32_t q = a.q, qm1 = q - 1, q2 = q * q;
     const uint32_t tie_lim = 65537u - qm1;
     const int nvr = a.nvr, ny = a.ny;
     const size_t pitch = (size_t)nvr * 16;
-    const int total = a.nrows * nvr;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int Y = idx / nvr, v = idx - Y * nvr;       // Y = replica * ny + y0
-        const int rep = Y / ny, y = Y - rep * ny;
-        const int p = (y + a.colour) & 1;
-        const int Yu = (y + 1 == ny) ? Y + 1 - ny : Y + 1, Yd = (y == 0) ? Y + ny - 1 : Y - 1;
-        const uint8_t* row = a.oth + (size_t)Y * pitch;
-        uint4* po = reinterpret_cast<uint4*>(a.own + (size_t)Y * pitch) + v;
-        const uint4 o = *po;
-        const uint4 b = ld_other(reinterpret_cast<const uint4*>(row) + v);
-        const uint4 up = ld_other(reinterpret_cast<const uint4*>(a.oth + (size_t)Yu * pitch) + v);
-        const uint4 dn = ld_other(reinterpret_cast<const uint4*>(a.oth + (size_t)Yd * pitch) + v);
-        const uint4 s = six_shifted(row, b, v, nvr, a.nxh, p);
-        // right = x0 + 1, left = x0 - 1
-        const uint4 rt = p ? s : b, lf = p ? b : s;
-        const uint32_t k1 = TAG_TORUS + (uint32_t)rep;
-        const uint32_t blk = (uint32_t)(y * nvr + v);
-        uint32_t outw[4];
-        uint32_t ties = 0;
+    const int Yu = (y + 1 == ny) ? Y + 1 - ny : Y + 1, Yd = (y == 0) ? Y + ny - 1 : Y - 1;
+    const uint8_t* row = a.oth + (size_t)Y * pitch;
+    uint4* po = reinterpret_cast<uint4*>(a.own + (size_t)Y * pitch) + v;
+    const uint4 o = *po;
+    const uint4 b = ld_other(reinterpret_cast<const uint4*>(row) + v);
+    const uint4 up = ld_other(reinterpret_cast<const uint4*>(a.oth + (size_t)Yu * pitch) + v);
+    const uint4 dn = ld_other(reinterpret_cast<const uint4*>(a.oth + (size_t)Yd * pitch) + v);
+    const uint4 s = six_shifted(row, b, v, nvr, a.nxh, P);
+    const uint4 rt = P ? s : b, lf = P ? b : s;
+    const uint32_t k1 = TAG_TORUS + (uint32_t)rep;
+    const uint32_t blk = (uint32_t)(y * nvr + v);
+    uint32_t outw[4];
+    uint32_t ties = 0;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const uint32_t ow = word_of(o, w);
-            // byte-parallel partial indices: A = r + q u, B = l + q d (< q^2 <= 225)
-            const uint32_t A = word_of(rt, w) + q * word_of(up, w);
-            const uint32_t B = word_of(lf, w) + q * word_of(dn, w);
-            // AB = A + q^2 B in 16-bit fields (< q^4): sites (0, 2) and (1, 3) of the word
-            const uint32_t ABe = (A & 0x00FF00FFu) + q2 * (B & 0x00FF00FFu);
-            const uint32_t ABo = ((A >> 8) & 0x00FF00FFu) + q2 * ((B >> 8) & 0x00FF00FFu);
-            const uint4 R = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, (uint32_t)w), a.rk0, k1);
-            uint32_t res = 0;
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t ow = word_of(o, w);
+        // byte-parallel partial indices: A = r + q u, B = l + q d (< q^2 <= 225)
+        const uint32_t A = word_of(rt, w) + q * word_of(up, w);
+        const uint32_t B = word_of(lf, w) + q * word_of(dn, w);
+        // AB = A + q^2 B in 16-bit fields (< q^4): sites (0, 2) and (1, 3) of the word
+        const uint32_t ABe = (A & 0x00FF00FFu) + q2 * (B & 0x00FF00FFu);
+        const uint32_t ABo = ((A >> 8) & 0x00FF00FFu) + q2 * ((B >> 8) & 0x00FF00FFu);
+        const uint4 R = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, (uint32_t)w), a.rk0, k1);
+        uint32_t res = 0;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const uint32_t W = word_of(R, e);
-                const uint32_t c = (ow >> (8 * e)) & 0xFFu;
-                const uint32_t ab = ((e & 1) ? ABo : ABe) >> (16 * (e >> 1)) & 0xFFFFu;
-                const uint32_t t = (W & 0xFFFFu) * qm1;          // proposal: k = (t >> 16) + 1 unless the low half decides
-                uint32_t nw = c + 1u + (t >> 16);
-                nw = min(nw, nw - q);                            // unsigned: nw - q wraps when nw < q
-                const uint32_t ix = c + q * nw + q2 * ab;
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t W = word_of(R, e);
+            const uint32_t c = (ow >> (8 * e)) & 0xFFu;
+            const uint32_t ab = ((e & 1) ? ABo : ABe) >> (16 * (e >> 1)) & 0xFFFFu;
+            const uint32_t t = (W & 0xFFFFu) * qm1;          // proposal: k = (t >> 16) + 1 unless the low half decides
+            uint32_t nw = c + 1u + (t >> 16);
+            nw = min(nw, nw - q);                            // unsigned: nw - q wraps when nw < q
+            const uint32_t ix = c + q * nw + q2 * ab;
+            uint32_t th;
+            if (DIRECT) {
+                asm("ld.shared.u16 %0, [%1];" : "=r"(th) : "r"(sm.cls_addr + 2u * ix));
+            } else {
                 uint32_t cl;
-                if (SMEM) asm("ld.shared.u8 %0, [%1];" : "=r"(cl) : "r"(scls_addr + ix));
-                else cl = a.cls[ix];
-                const uint32_t th = sthi[cl];
-                const uint32_t ha = W >> 16;
-                res |= (ha < th ? nw : c) << (8 * e);
-                if ((t & 0xFFFFu) >= tie_lim || ha == th) ties |= 1u << (4 * w + e);
+                if (SMEM) asm("ld.shared.u8 %0, [%1];" : "=r"(cl) : "r"(sm.cls_addr + ix));
+                else cl = sm.gcls[ix];
+                th = sm.sthi[cl];
             }
-            outw[w] = res;
+            const uint32_t ha = W >> 16;
+            res |= (ha < th ? nw : c) << (8 * e);
+            if ((t & 0xFFFFu) >= tie_lim || ha == th) ties |= 1u << (4 * w + e);
         }
-        while (ties) {  // rare: redo the undecided sites with the full 32-bit uniforms
-            const int j = __ffs(ties) - 1;
-            ties &= ties - 1;
-            const uint4 R = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, (uint32_t)(j >> 2)), a.rk0, k1);
-            const uint32_t ns = six_site_exact(a, cls, word_of(R, j & 3), blk, k1, j, byte_of(o, j), byte_of(rt, j),
-                                               byte_of(up, j), byte_of(lf, j), byte_of(dn, j));
-            const int wi = j >> 2, sh = 8 * (j & 3);
+        outw[w] = res;
+    }
+    while (ties) {  // rare: redo the undecided sites with the full 32-bit uniforms
+        const int j = __ffs(ties) - 1;
+        ties &= ties - 1;
+        const uint4 R = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, (uint32_t)(j >> 2)), a.rk0, k1);
+        const uint32_t ns = six_site_exact(a, a.cls, word_of(R, j & 3), blk, k1, j, byte_of(o, j), byte_of(rt, j),
+                                           byte_of(up, j), byte_of(lf, j), byte_of(dn, j));
+        const int wi = j >> 2, sh = 8 * (j & 3);
 #pragma unroll
-            for (int w = 0; w < 4; ++w)
-                if (w == wi) outw[w] = (outw[w] & ~(0xFFu << sh)) | (ns << sh);
-        }
-        *po = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+        for (int w = 0; w < 4; ++w)
+            if (w == wi) outw[w] = (outw[w] & ~(0xFFu << sh)) | (ns << sh);
+    }
+    *po = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+}
+
+#define SIX_DIRECT_THREADS 768
+template <bool SMEM, bool DIRECT = false>
+__global__ void __launch_bounds__(DIRECT ? SIX_DIRECT_THREADS : 256, DIRECT ? 1 : SIX_MINB)
+sixclock_pass_kernel(const __grid_constant__ SixArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smraw[];
+    uint32_t* sthi = reinterpret_cast<uint32_t*>(smraw);            // SIX_MAX_CLASSES words
+    uint8_t* scls = smraw + SIX_MAX_CLASSES * sizeof(uint32_t);     // q^6 bytes (SMEM) / 2 q^6 bytes (DIRECT)
+    for (int i = threadIdx.x; i < SIX_MAX_CLASSES; i += blockDim.x) sthi[i] = a.thi[i];
+    if (SMEM || DIRECT) {
+        const uint4* src = reinterpret_cast<const uint4*>(DIRECT ? reinterpret_cast<const uint8_t*>(a.thr16) : a.cls);
+        uint4* dst = reinterpret_cast<uint4*>(scls);
+        const uint32_t bytes = DIRECT ? 2u * a.tab_bytes : a.tab_bytes;
+        for (uint32_t i = threadIdx.x; i < (bytes + 15) / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    SixSmem sm;
+    sm.cls_addr = (uint32_t)__cvta_generic_to_shared(scls);
+    sm.sthi = sthi;
+    sm.gcls = a.cls;
+    const int nvr = a.nvr, ny = a.ny;
+    // (row, vector) of this thread, advanced incrementally: no division in the loop
+    const int stride = gridDim.x * blockDim.x;
+    const int dY = stride / nvr, dv = stride - dY * nvr;
+    const int idx0 = blockIdx.x * blockDim.x + threadIdx.x;
+    int Y = idx0 / nvr, v = idx0 - Y * nvr;       // Y = replica * ny + y0
+    int rep = Y / ny, y = Y - rep * ny;
+    while (Y < a.nrows) {
+        if ((y + a.colour) & 1) six_vector<SMEM, DIRECT, 1>(a, sm, Y, y, rep, v);
+        else six_vector<SMEM, DIRECT, 0>(a, sm, Y, y, rep, v);
+        v += dv;
+        int adv = dY;
+        if (v >= nvr) { v -= nvr; ++adv; }
+        Y += adv; y += adv;
+        while (y >= ny) { y -= ny; ++rep; }
     }
 }
 
@@ -391,6 +427,8 @@ struct Six {
     std::vector<double> magne, e3, prob;  // host tables exactly as the reference builds them
     uint8_t* d_cls;
     uint32_t *d_thi, *d_tlo;
+    uint16_t* d_thr16;   // direct lookup table (q^6 entries)
+    int direct, threads; // direct: one-load lookup with SIX_DIRECT_THREADS-thread blocks, one per SM
     double* d_prob;
     double* d_rnds;
     int32_t* d_stage;
@@ -462,6 +500,9 @@ int build_tables(Six* m)
                         }
 #undef E3
     thi.resize(SIX_MAX_CLASSES, 0); tlo.resize(SIX_MAX_CLASSES, 0);
+    std::vector<uint16_t> thr16(q6);
+    for (size_t i = 0; i < q6; ++i) thr16[i] = (uint16_t)(thi[cls[i]] > 65535u ? 65535u : thi[cls[i]]);
+    CK(cudaMemcpyAsync(m->d_thr16, thr16.data(), q6 * sizeof(uint16_t), cudaMemcpyHostToDevice, m->stream));
     CK(cudaMemcpyAsync(m->d_cls, cls.data(), q6, cudaMemcpyHostToDevice, m->stream));
     CK(cudaMemcpyAsync(m->d_thi, thi.data(), SIX_MAX_CLASSES * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
     CK(cudaMemcpyAsync(m->d_tlo, tlo.data(), SIX_MAX_CLASSES * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
@@ -475,7 +516,7 @@ void fill_args(Six* m, int colour, SixArgs* a)
     a->own = m->c[colour]; a->oth = m->c[colour ^ 1];
     a->nxh = m->nxh; a->ny = (int)m->ny; a->nvr = m->nvr; a->nrows = (int)(m->n_multi * m->ny);
     a->colour = colour; a->q = (uint32_t)m->q;
-    a->cls = m->d_cls; a->thi = m->d_thi; a->tlo = m->d_tlo;
+    a->cls = m->d_cls; a->thi = m->d_thi; a->tlo = m->d_tlo; a->thr16 = m->d_thr16;
     a->tab_bytes = (uint32_t)m->prob.size(); a->cls_in_smem = m->cls_in_smem;
     a->draw = m->draw;
     for (int r = 0; r < 10; ++r) a->rk0[r] = m->seed + (uint32_t)r * PHILOX_W0;
@@ -492,7 +533,8 @@ int sweep(Six* m)
             CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
         }
         COUNT_LAUNCH();
-        if (m->cls_in_smem) sixclock_pass_kernel<true><<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
+        if (m->direct) sixclock_pass_kernel<false, true><<<m->grid, SIX_DIRECT_THREADS, m->smem_bytes, m->stream>>>(a);
+        else if (m->cls_in_smem) sixclock_pass_kernel<true><<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
         else sixclock_pass_kernel<false><<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
         CK(cudaGetLastError());
         if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
@@ -547,7 +589,7 @@ int measure(Six* m)
 void destroy(Six* m)
 {
     cudaStreamSynchronize(m->stream);
-    cudaFree(m->c[0]); cudaFree(m->c[1]); cudaFree(m->d_cls); cudaFree(m->d_thi); cudaFree(m->d_tlo);
+    cudaFree(m->c[0]); cudaFree(m->c[1]); cudaFree(m->d_cls); cudaFree(m->d_thi); cudaFree(m->d_tlo); cudaFree(m->d_thr16);
     cudaFree(m->d_prob); cudaFree(m->d_rnds); cudaFree(m->d_stage); cudaFree(m->d_acc);
     for (cudaEvent_t e : m->evs) cudaEventDestroy(e);
     delete m;
@@ -594,13 +636,13 @@ int b200mc_sixclock_create_variant(void** out, int64_t nx, int64_t ny, double kb
     m->nx = nx; m->ny = ny; m->q = mstate; m->n_multi = n_multi; m->nxh = (int)nxh; m->nvr = (int)nvr; m->variant = variant;
     m->pitch = (size_t)nvr * 16; m->rep_bytes = m->pitch * (size_t)ny;
     m->stream = 0; m->seed = (uint32_t)iseed; m->draw = 0; m->beta = 1 / kbt; m->obs_valid = false;
-    m->c[0] = m->c[1] = nullptr; m->d_cls = nullptr; m->d_thi = m->d_tlo = nullptr; m->d_prob = nullptr; m->d_rnds = nullptr;
+    m->c[0] = m->c[1] = nullptr; m->d_cls = nullptr; m->d_thi = m->d_tlo = nullptr; m->d_thr16 = nullptr; m->d_prob = nullptr; m->d_rnds = nullptr;
     m->d_stage = nullptr; m->d_acc = nullptr; m->timing = false; m->ev_used = 0;
     const size_t q6 = (size_t)mstate * mstate * mstate * mstate * mstate * mstate;
     const size_t bytes = m->rep_bytes * (size_t)n_multi;
     if (cudaMalloc(&m->c[0], bytes) != cudaSuccess || cudaMalloc(&m->c[1], bytes) != cudaSuccess ||
         cudaMalloc(&m->d_cls, (q6 + 15) / 16 * 16) != cudaSuccess || cudaMalloc(&m->d_thi, SIX_MAX_CLASSES * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMalloc(&m->d_tlo, SIX_MAX_CLASSES * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&m->d_tlo, SIX_MAX_CLASSES * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&m->d_thr16, (2 * q6 + 15) / 16 * 16) != cudaSuccess ||
         cudaMalloc(&m->d_acc, (size_t)n_multi * 192 * sizeof(unsigned long long)) != cudaSuccess) {
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed (%zu bytes per colour)", bytes);
         cudaGetLastError();
@@ -626,6 +668,20 @@ int b200mc_sixclock_create_variant(void** out, int64_t nx, int64_t ny, double kb
     if (occ < 1) occ = 1;
     const int64_t need = ((int64_t)n_multi * ny * nvr + 255) / 256;
     m->grid = (int)(need < (int64_t)m->sms * occ ? need : (int64_t)m->sms * occ);
+    // direct lookup: 2 q^6 bytes of thresholds in shared memory, one block of SIX_DIRECT_THREADS threads per SM
+    m->direct = 0; m->threads = 256;
+    {
+        const size_t wantd = SIX_MAX_CLASSES * sizeof(uint32_t) + (2 * q6 + 15) / 16 * 16;
+        const char* t = getenv("B200MC_SIX_DIRECT");
+        int occd = 0;
+        if (wantd <= (size_t)maxsm && !(t && atoi(t) == 0) &&
+            cudaFuncSetAttribute(sixclock_pass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wantd) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, sixclock_pass_kernel<false, true>, SIX_DIRECT_THREADS, wantd) == cudaSuccess && occd >= 1) {
+            m->direct = 1; m->threads = SIX_DIRECT_THREADS; m->smem_bytes = (int)wantd;
+            const int64_t needd = ((int64_t)n_multi * ny * nvr + SIX_DIRECT_THREADS - 1) / SIX_DIRECT_THREADS;
+            m->grid = (int)(needd < (int64_t)m->sms * occd ? needd : (int64_t)m->sms * occd);
+        } else cudaGetLastError();
+    }
     int rc = build_tables(m);
     if (rc) { destroy(m); return rc; }
     *out = m;
