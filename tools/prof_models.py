@@ -25,3 +25,11 @@ if which in ("clock", "all"):
     from cuda_fortran_mc_simulation_spin_b200 import clock_gpu_m
     c = clock_gpu_m.clock_gpu().init(16385, 16384, 0.91, 6, 42)
     c.update_n(3); print("clock", c.calc_energy_sum(), c.calc_magne_sum()); del c
+if which in ("ising_small",):
+    from cuda_fortran_mc_simulation_spin_b200 import ising2d_gpu_m
+    m = ising2d_gpu_m.ising2d_gpu().init(1001, 1000, 2.26918531421, 42)
+    m.update_n(3); m.update_n(100); print("ising_small", m.measure()); del m
+if which in ("ising_slabself",):   # run with B200MC_TUNE=16: the slab pass against the GPU's own arrays
+    from cuda_fortran_mc_simulation_spin_b200 import ising3d_gpu_m
+    m = ising3d_gpu_m.ising3d_gpu().init(1023, 1023, 1024, 4.51152, 42)
+    m.update_n(4); print("ising_slabself", m.measure()); del m
