@@ -414,6 +414,9 @@ int coop_sweeps(Ising* m, int n, bool fuse_last, unsigned long long* series)
         a.Lfold = g.L; a.Nc = g.Nc;
         a.mask_from = g.ptail < g.L ? (int)(g.ptail - a.p0 > 0 ? g.ptail - a.p0 : 0) : 0x7FFFFFFF;
         a.nopush = 2;
+        // narrow halo (2D: H = nx/2 + 1 vectors of L): no refresh between the passes, the few threads next to the ends of the
+        // fold rebuild their wrapped neighbours; wide halo (3D: a plane): refresh after every pass
+        a.wrap_mode = (8 * g.H > g.L || (m->tune & 4096)) ? 0 : ((g.H <= g.L && g.ptail >= g.H) ? 1 : 2);
     }
     s.L = g.L; s.H = g.H; s.Nc = g.Nc; s.ptail = g.ptail;
     s.halo_fast = (g.H <= g.L && g.ptail >= g.H) ? 1 : 0;

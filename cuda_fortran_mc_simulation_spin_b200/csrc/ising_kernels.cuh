@@ -92,6 +92,8 @@ struct RingPassArgs {
     // mask_from on (local index) keep only the lanes b with b * Lfold + position < Nc in the sums
     int mask_from;
     int64_t Lfold, Nc;
+    int wrap_mode;   // cooperative sweep kernel: 0 = the halo is refreshed after every pass, read it; 1 / 2 = no refresh between the passes,
+                     // wrapped positions are rebuilt from the owned sites (1: H <= L and ptail >= H, vector-granular; 2: byte-granular)
 };
 
 __device__ __forceinline__ uint4 rot_lanes(uint4 s, int dir)
@@ -323,7 +325,17 @@ __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (
     // (loading the x+ vector as a shuffle of the neighbouring lane's x- vector instead of a second, overlapping
     // 512-byte load was tried: 4 SHFL + a one-lane load made the pass 20 % slower -- the MIO queue is the busiest unit)
 #pragma unroll
-    for (int j = 0; j < NNB; ++j) nb[j] = COHERENT ? ld_other_coherent(q[j]) : ld_other(q[j]);
+    for (int j = 0; j < NNB; ++j) {
+        if (COHERENT) {
+            // cooperative sweep kernel (single GPU, p0 = 0), wrap_mode != 0: positions outside [0, min(ptail, L)) are rebuilt
+            // from the owned sites instead of read from the halo, which is then only refreshed at the end of the launch
+            const int pj = v + (int)a.off[j];
+            const int safe = a.mask_from < (int)a.Lfold ? a.mask_from : (int)a.Lfold;
+            nb[j] = (a.wrap_mode == 0 || (unsigned)pj < (unsigned)safe)
+                        ? ld_other_coherent(q[j])
+                        : ring_load_wrapped(a.oth, a.Lfold, a.H, a.Nc, (int64_t)safe, a.wrap_mode == 1, (int64_t)pj);
+        } else nb[j] = ld_other(q[j]);
+    }
     ising_core<NNB, METHOD, PUSH, MEASURE>(v, po, o, nb, cx, cz, cw, a, tab, pol, qaddr, cntaddr, is_b, accX, accM, cy);
 }
 
@@ -537,9 +549,9 @@ ising_slab_kernel(const __grid_constant__ RingPassArgs ab, const __grid_constant
 // Small lattices (at most a few vectors per resident thread): n_sweeps whole sweeps in ONE cooperative launch.
 // At the reference's default sizes (app/ising2d_gpu_relaxation.f90:6-7: 1001 x 1000) a colour pass is ~1 us of
 // work, and the per-sweep sequence of the plain path -- two pass launches, two to four halo launches, memsets -- is
-// bound by launch latency (27 us per MCS).  Here every block runs colour pass -> grid barrier -> halo refresh ->
-// grid barrier, twice per sweep, for all sweeps; static 32-vector chunks (one vector per lane) spread the lattice
-// over the whole grid.  Sums: `series` != nullptr -> sweep i adds {X, sum s} to series[2 i], series[2 i + 1]
+// bound by launch latency (27 us per MCS).  Here every block runs colour pass -> grid barrier (-> halo refresh ->
+// grid barrier when the halo is wide), twice per sweep, for all sweeps; static 32-vector chunks (one vector per
+// lane) spread the lattice over the whole grid.  Sums: `series` != nullptr -> sweep i adds {X, sum s} to series[2 i], series[2 i + 1]
 // (run_relaxation); else fuse_last -> the last sweep adds them to a[1].acc (update + calc_*_sum).
 struct IsingCoopArgs {
     RingPassArgs a[2];          // per colour; draw = the first sweep's
@@ -559,6 +571,17 @@ ising_coop_kernel(const __grid_constant__ IsingCoopArgs s, const __grid_constant
     __shared__ uint4 tq[8][TQ_CAP][2];
     __shared__ uint32_t tq_cnt[8];
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
+    // update_norishiro (src/ising3d_gpu_m.f90:102-122) for one colour array, by the whole grid
+    auto halo = [&](uint4* vec) {
+        if (s.halo_fast) {
+            for (int64_t v = gtid; v < 2 * s.H; v += gthreads) ring_halo_fast_item(vec, s.L, s.H, s.Nc, v);
+            for (int64_t t = gtid; t < (s.L - s.ptail) * 16; t += gthreads)
+                ring_halo_generic_item(reinterpret_cast<uint8_t*>(vec), s.L, s.H, s.Nc, s.ptail, 2 * s.H, t);
+        } else {
+            for (int64_t t = gtid; t < (2 * s.H + s.L - s.ptail) * 16; t += gthreads)
+                ring_halo_generic_item(reinterpret_cast<uint8_t*>(vec), s.L, s.H, s.Nc, s.ptail, 0, t);
+        }
+    };
     // fuse_last: the accumulators are cleared here (the pass that adds to them comes after at least one grid barrier)
     if (s.fuse_last && !s.series && gtid == 0) { s.a[1].acc[0] = 0ull; s.a[1].acc[1] = 0ull; }
     for (int i = 0; i < s.n_sweeps; ++i) {
@@ -574,19 +597,15 @@ ising_coop_kernel(const __grid_constant__ IsingCoopArgs s, const __grid_constant
                 ising_pass_body<NNB, METHOD, false, false, false, false, 32>(b, tab, tq, tq_cnt);
             }
             grid.sync();
-            // update_norishiro (src/ising3d_gpu_m.f90:102-122) for the colour just written
-            uint4* vec = b.own;
-            if (s.halo_fast) {
-                for (int64_t v = gtid; v < 2 * s.H; v += gthreads) ring_halo_fast_item(vec, s.L, s.H, s.Nc, v);
-                for (int64_t t = gtid; t < (s.L - s.ptail) * 16; t += gthreads)
-                    ring_halo_generic_item(reinterpret_cast<uint8_t*>(vec), s.L, s.H, s.Nc, s.ptail, 2 * s.H, t);
-            } else {
-                for (int64_t t = gtid; t < (2 * s.H + s.L - s.ptail) * 16; t += gthreads)
-                    ring_halo_generic_item(reinterpret_cast<uint8_t*>(vec), s.L, s.H, s.Nc, s.ptail, 0, t);
+            if (s.a[0].wrap_mode == 0) {   // wide halos (3D): refresh after every pass, one more barrier
+                halo(b.own);
+                grid.sync();
             }
-            grid.sync();
         }
     }
+    // narrow halos (2D): the passes rebuilt wrapped neighbour positions on the fly (ring_load_wrapped); the halo vectors
+    // and tail lanes every other kernel reads are refreshed once, here
+    if (s.a[0].wrap_mode != 0) { halo(s.a[0].own); halo(s.a[1].own); }
     // (after the last barrier every block's atomics have landed)
     if (s.fuse_last && !s.series && s.host_out && gtid == 0) {
         s.host_out[0] = __ldcg(s.a[1].acc);

@@ -99,34 +99,63 @@ __device__ __forceinline__ void ring_halo_generic_item(uint8_t* base, int64_t L,
     base[(p + H) * 16 + b] = ring_site(base, L, H, pos_mod(kraw, Nc));
 }
 
-// fast path (needs H <= L and ptail >= H): item v = one halo vector; a halo vector is the source vector with its
-// lanes rotated by one, plus one or two patched lanes.  Reads real sites only.
+// The vector a halo position holds (fast path: needs H <= L and ptail >= H): the source vector with its lanes rotated
+// by one, plus one or two patched lanes.  Reads real sites only.  vec: index 0 = position -H.
+__device__ __forceinline__ uint4 ring_wrapped_low(const uint4* vec, int64_t L, int64_t H, int64_t Nc, int64_t p)
+{
+    // p < 0: lane b <- lane b-1 at p + L; lane 0 <- site Nc + p
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(vec);
+    const uint4 s = __ldcg(vec + (p + L + H));
+    uint4 o;
+    o.w = __funnelshift_l(s.z, s.w, 8);
+    o.z = __funnelshift_l(s.y, s.z, 8);
+    o.y = __funnelshift_l(s.x, s.y, 8);
+    o.x = (s.x << 8) | ring_site(base, L, H, pos_mod(p, Nc));
+    return o;
+}
+__device__ __forceinline__ uint4 ring_wrapped_high(const uint4* vec, int64_t L, int64_t H, int64_t Nc, int64_t p)
+{
+    // p >= L: lane b <- lane b+1 at p - L; lanes 14, 15 patched
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(vec);
+    const uint4 s = __ldcg(vec + (p - L + H));
+    uint4 o;
+    o.x = __funnelshift_r(s.x, s.y, 8);
+    o.y = __funnelshift_r(s.y, s.z, 8);
+    o.z = __funnelshift_r(s.z, s.w, 8);
+    const uint32_t b14 = ring_site(base, L, H, pos_mod(14 * L + p, Nc));
+    const uint32_t b15 = ring_site(base, L, H, pos_mod(15 * L + p, Nc));
+    o.w = ((s.w >> 8) & 0x0000FFFFu) | (b14 << 16) | (b15 << 24);
+    return o;
+}
 __device__ __forceinline__ void ring_halo_fast_item(uint4* vec, int64_t L, int64_t H, int64_t Nc, int64_t v)
 {
-    const uint8_t* base = reinterpret_cast<const uint8_t*>(vec);
-    if (v < H) {
-        // low halo, p = v - H < 0: lane b <- lane b-1 at p + L; lane 0 <- site Nc + p
-        const int64_t p = v - H;
-        const uint4 s = __ldcg(vec + (p + L + H));
-        uint4 o;
-        o.w = __funnelshift_l(s.z, s.w, 8);
-        o.z = __funnelshift_l(s.y, s.z, 8);
-        o.y = __funnelshift_l(s.x, s.y, 8);
-        o.x = (s.x << 8) | ring_site(base, L, H, pos_mod(p, Nc));
-        vec[v] = o;
-    } else {
-        // high halo, p = L + (v - H): lane b <- lane b+1 at p - L; lanes 14, 15 patched
-        const int64_t p = L + (v - H);
-        const uint4 s = __ldcg(vec + (p - L + H));
-        uint4 o;
-        o.x = __funnelshift_r(s.x, s.y, 8);
-        o.y = __funnelshift_r(s.y, s.z, 8);
-        o.z = __funnelshift_r(s.z, s.w, 8);
-        const uint32_t b14 = ring_site(base, L, H, pos_mod(14 * L + p, Nc));
-        const uint32_t b15 = ring_site(base, L, H, pos_mod(15 * L + p, Nc));
-        o.w = ((s.w >> 8) & 0x0000FFFFu) | (b14 << 16) | (b15 << 24);
-        vec[p + H] = o;
+    if (v < H) vec[v] = ring_wrapped_low(vec, L, H, Nc, v - H);
+    else vec[L + v] = ring_wrapped_high(vec, L, H, Nc, L + (v - H));   // position L + (v - H) lives at index L + v
+}
+
+// The vector position p in [-H, L + H) SHOULD hold, computed from the owned sites alone (the stored halo vectors and
+// tail lanes are not read): what a colour pass of the cooperative sweep kernel loads for a neighbour position outside
+// [0, ptail), so that no halo refresh (and no second grid barrier) is needed between its passes.
+__device__ __forceinline__ uint4 ring_load_wrapped(const uint4* vec, int64_t L, int64_t H, int64_t Nc, int64_t ptail, bool fast, int64_t p)
+{
+    if (fast) {
+        if (p < 0) return ring_wrapped_low(vec, L, H, Nc, p);
+        if (p >= L) return ring_wrapped_high(vec, L, H, Nc, p);
+        uint4 s = __ldcg(vec + (p + H));   // ptail <= p < L: lane 15 holds no site here
+        const uint32_t b15 = ring_site(reinterpret_cast<const uint8_t*>(vec), L, H, pos_mod(15 * L + p, Nc));
+        s.w = (s.w & 0x00FFFFFFu) | (b15 << 24);
+        return s;
     }
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(vec);
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+    for (int b = 0; b < 16; ++b) {
+        const int64_t kraw = (int64_t)b * L + p;
+        const bool real = p >= 0 && p < L && kraw < Nc;
+        const uint32_t val = real ? (uint32_t)__ldcg(base + (p + H) * 16 + b) : (uint32_t)ring_site(base, L, H, pos_mod(kraw, Nc));
+        w[b >> 2] |= val << (8 * (b & 3));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 int ring_geom_init(RingGeom* g, int64_t nx, int64_t ny, int64_t nz /*0 for 2D*/);
