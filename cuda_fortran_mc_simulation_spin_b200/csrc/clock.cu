@@ -23,6 +23,8 @@ struct Clock {
     std::vector<double> magne, etab, ws;   // host tables exactly as the reference builds them
     uint8_t* d_cls;
     uint64_t* d_thr;
+    uint16_t* d_thr16;     // direct lookup table (q <= 6)
+    int direct, grid_direct, smem_direct;
     double* d_ws;
     double* d_rand;
     double* d_next;
@@ -81,6 +83,12 @@ int build_tables(Clock* m)
                         }
 #undef ET
     thr.resize(CLOCK_MAX_CLASSES, 0);
+    if (m->d_thr16) {
+        std::vector<uint16_t> t16(q6);
+        for (size_t i = 0; i < q6; ++i) { const uint64_t hi = thr[cls[i]] >> 16; t16[i] = (uint16_t)(hi > 65535u ? 65535u : hi); }
+        CK(cudaMemcpyAsync(m->d_thr16, t16.data(), q6 * sizeof(uint16_t), cudaMemcpyHostToDevice, m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+    }
     CK(cudaMemcpyAsync(m->d_cls, cls.data(), q6, cudaMemcpyHostToDevice, m->stream));
     CK(cudaMemcpyAsync(m->d_thr, thr.data(), CLOCK_MAX_CLASSES * sizeof(uint64_t), cudaMemcpyHostToDevice, m->stream));
     if (m->d_ws) CK(cudaMemcpyAsync(m->d_ws, m->ws.data(), q6 * sizeof(double), cudaMemcpyHostToDevice, m->stream));
@@ -105,6 +113,7 @@ void fill_args(Clock* m, int j, int colour, ClockArgs* a)
         a->rk1[r] = TAG_CLOCK + (uint32_t)j + (uint32_t)r * PHILOX_W1;
     }
     a->cls_in_smem = m->cls_in_smem;
+    a->thr16 = m->d_thr16;
 }
 
 int sweep(Clock* m)
@@ -115,7 +124,8 @@ int sweep(Clock* m)
             ClockArgs a;
             fill_args(m, j, colour, &a);
             COUNT_LAUNCH();
-            clock_pass_kernel<<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
+            if (m->direct) clock_pass_direct_kernel<<<m->grid_direct, CLOCK_DIRECT_THREADS, m->smem_direct, m->stream>>>(a);
+            else clock_pass_kernel<<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
             CK(cudaGetLastError());
             int rc = ring_halo(&m->st[j], colour, m->stream);
             if (rc) return rc;
@@ -177,7 +187,7 @@ void destroy(Clock* m)
 {
     cudaStreamSynchronize(m->stream);
     for (auto& s : m->st) ring_free(&s);
-    cudaFree(m->d_cls); cudaFree(m->d_thr); cudaFree(m->d_ws); cudaFree(m->d_rand); cudaFree(m->d_next); cudaFree(m->d_acc);
+    cudaFree(m->d_cls); cudaFree(m->d_thr); cudaFree(m->d_thr16); cudaFree(m->d_ws); cudaFree(m->d_rand); cudaFree(m->d_next); cudaFree(m->d_acc);
     delete m;
 }
 
@@ -198,7 +208,7 @@ int create(void** out, int64_t nx, int64_t ny, double kbt, int32_t q, int32_t n_
     if (!m) ARG_FAIL("out of host memory");
     m->nx = nx; m->ny = ny; m->q = q; m->n_multi = n_multi; m->multi = multi; m->stream = 0;
     m->seed = (uint32_t)iseed; m->draw = 0; m->beta = 1 / kbt; m->obs_valid = false;
-    m->d_cls = nullptr; m->d_thr = nullptr; m->d_ws = nullptr; m->d_rand = nullptr; m->d_next = nullptr; m->d_acc = nullptr;
+    m->d_cls = nullptr; m->d_thr = nullptr; m->d_thr16 = nullptr; m->direct = 0; m->d_ws = nullptr; m->d_rand = nullptr; m->d_next = nullptr; m->d_acc = nullptr;
     RingGeom g;
     int rc = ring_geom_init(&g, nx, ny, 0);
     if (rc) { delete m; return rc; }
@@ -232,6 +242,19 @@ int create(void** out, int64_t nx, int64_t ny, double kbt, int32_t q, int32_t n_
     if (occ < 1) occ = 1;
     const int64_t need = (g.L + 255) / 256;
     m->grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);
+    {   // direct lookup: 2 q^6 bytes of thresholds in shared memory, byte-parallel index (needs q^2 <= 255)
+        const size_t wantd = (2 * q6 + 15) / 16 * 16;
+        const char* t = getenv("B200MC_CLOCK_DIRECT");
+        int occd = 0;
+        if (q * q <= 255 && wantd <= (size_t)maxsm && !(t && atoi(t) == 0) &&
+            cudaFuncSetAttribute(clock_pass_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wantd) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, clock_pass_direct_kernel, CLOCK_DIRECT_THREADS, wantd) == cudaSuccess && occd >= 1 &&
+            cudaMalloc(&m->d_thr16, wantd) == cudaSuccess) {
+            m->direct = 1; m->smem_direct = (int)wantd;
+            const int64_t needd = (g.L + CLOCK_DIRECT_THREADS - 1) / CLOCK_DIRECT_THREADS;
+            m->grid_direct = (int)(needd < (int64_t)sms * occd ? needd : (int64_t)sms * occd);
+        } else cudaGetLastError();
+    }
     rc = build_tables(m);
     if (rc) { destroy(m); return rc; }
     *out = m;

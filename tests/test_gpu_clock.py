@@ -21,10 +21,19 @@ def _hist_from_oracle(o, j=0):
     return hist, bl, bd
 
 
+@pytest.fixture(params=["direct", "classes"])
+def lookup(request, monkeypatch):
+    """acceptance lookup: the one-load u16 threshold table in shared memory (default for q <= 6) or the class-id table +
+    per-class thresholds (B200MC_CLOCK_DIRECT=0; what larger q use) -- both are checked against the oracle"""
+    if request.param == "classes":
+        monkeypatch.setenv("B200MC_CLOCK_DIRECT", "0")
+    return request.param
+
+
 @pytest.mark.parametrize("shape,q,kbt", [((5, 4), 6, 0.8), ((33, 32), 6, 0.91), ((501, 500), 6, 0.8), ((65, 64), 4, 1.0),
                                          ((33, 32), 3, 0.7), ((33, 32), 8, 0.6), ((31, 30), 5, 0.9)])
 @pytest.mark.parametrize("start", ["allup", "random"])
-def test_clock_trajectory_bit_exact(oracle, shape, q, kbt, start):
+def test_clock_trajectory_bit_exact(oracle, shape, q, kbt, start, lookup):
     from cuda_fortran_mc_simulation_spin_b200 import clock_gpu_m
     nx, ny = shape
     g = clock_gpu_m.clock_gpu().init(nx, ny, kbt, q, 42)
@@ -44,7 +53,7 @@ def test_clock_trajectory_bit_exact(oracle, shape, q, kbt, start):
         assert abs(m - o.calc_magne_sum()) <= 1e-12 * g.nall()
 
 
-def test_clock_multi_bit_exact(oracle):
+def test_clock_multi_bit_exact(oracle, lookup):
     from cuda_fortran_mc_simulation_spin_b200 import clock_gpu_multi_m
     g = clock_gpu_multi_m.clock_gpu().init(101, 100, 0.8, 6, 3, 42)
     o = oracle.clock_gpu().init(101, 100, 0.8, 6, 42, n_multi=3)

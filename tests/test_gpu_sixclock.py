@@ -21,8 +21,17 @@ SHAPES = [((2, 2), 6, 0.91), ((4, 4), 6, 0.91), ((32, 32), 6, 0.91), ((34, 6), 6
           ((512, 512), 6, 0.91)]
 
 
+@pytest.fixture(params=["direct", "classes"])
+def lookup(request, monkeypatch):
+    """acceptance lookup: the one-load u16 threshold table in shared memory (default for q <= 6) or the class-id table +
+    per-class thresholds (B200MC_SIX_DIRECT=0; what larger q use) -- both are checked against the oracle"""
+    if request.param == "classes":
+        monkeypatch.setenv("B200MC_SIX_DIRECT", "0")
+    return request.param
+
+
 @pytest.mark.parametrize("shape,q,kbt", SHAPES)
-def test_tableall_trajectory_bit_exact(oracle, shape, q, kbt):
+def test_tableall_trajectory_bit_exact(oracle, shape, q, kbt, lookup):
     from cuda_fortran_mc_simulation_spin_b200._sixclock import sixclock
     nx, ny = shape
     g = sixclock(nx, ny, kbt, q, 1, 42)
@@ -87,7 +96,7 @@ def test_update_with_rnds_reference_stream(oracle, shape):
         assert np.array_equal(g.get_sixclock()[0], o.c)
 
 
-def test_multi_sample_batch(oracle):
+def test_multi_sample_batch(oracle, lookup):
     """n_multi independent samples in one launch per colour; sample j uses the key TAG_TORUS + j"""
     from cuda_fortran_mc_simulation_spin_b200._sixclock import sixclock
     nx, ny, n = 48, 16, 3
