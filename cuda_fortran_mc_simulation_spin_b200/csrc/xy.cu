@@ -225,18 +225,38 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
         auto ld_own = [&](int y) { return *reinterpret_cast<const float4*>(a.own + (size_t)y * nxh + xi0); };
         float4 u0 = ld_up(y0), o0 = ld_own(y0);
         float e0 = __ldg(a.oth + (size_t)y0 * nxh + (COLOUR ? xe1 : xe0));
-        for (int y = y0; y < y1; y += 2) {
-            const float4 u1 = ld_up(y + 1), o1 = ld_own(y + 1);
-            const float e1 = __ldg(a.oth + (size_t)(y + 1) * nxh + (COLOUR ? xe0 : xe1));
-            xy_strip_row<OVERRELAX, MEASURE, COLOUR>(a, y, y * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
-                                                     reinterpret_cast<float4*>(a.own + (size_t)y * nxh + xi0), es, mx, my);
-            const int yn = min(y + 2, y1 - 2);
-            u0 = ld_up(yn); o0 = ld_own(yn);
-            e0 = __ldg(a.oth + (size_t)yn * nxh + (COLOUR ? xe1 : xe0));
-            xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1>(a, y + 1, (y + 1) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
-                                                         reinterpret_cast<float4*>(a.own + (size_t)(y + 1) * nxh + xi0), es, mx, my);
-            // rows rotate by two: (dn, mid, up) <- (up of the first row = mid of the second, up of the second)
-            const XYRow t = mid; mid = dn; dn = up; (void)t;
+        if constexpr (OVERRELAX) {
+            // over-relaxation (fewer instructions per row, 80 registers): TWO rows ahead -- the raw values of rows y + 2 and
+            // y + 3 are requested before rows y and y + 1 are processed (463 -> 512 flips/ns; no effect on Metropolis,
+            // which is bound by issue slots and the XU pipe)
+            float4 u1 = ld_up(y0 + 1), o1 = ld_own(y0 + 1);
+            float e1 = __ldg(a.oth + (size_t)(y0 + 1) * nxh + (COLOUR ? xe0 : xe1));
+            for (int y = y0; y < y1; y += 2) {
+                const int yn = min(y + 2, y1 - 2);
+                const float4 nu0 = ld_up(yn), no0 = ld_own(yn), nu1 = ld_up(yn + 1), no1 = ld_own(yn + 1);
+                const float ne0 = __ldg(a.oth + (size_t)yn * nxh + (COLOUR ? xe1 : xe0));
+                const float ne1 = __ldg(a.oth + (size_t)(yn + 1) * nxh + (COLOUR ? xe0 : xe1));
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR>(a, y, y * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
+                                                         reinterpret_cast<float4*>(a.own + (size_t)y * nxh + xi0), es, mx, my);
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1>(a, y + 1, (y + 1) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
+                                                             reinterpret_cast<float4*>(a.own + (size_t)(y + 1) * nxh + xi0), es, mx, my);
+                u0 = nu0; o0 = no0; e0 = ne0; u1 = nu1; o1 = no1; e1 = ne1;
+                // rows rotate by two: (dn, mid, up) <- (up of the first row = mid of the second, up of the second)
+                const XYRow t = mid; mid = dn; dn = up; (void)t;
+            }
+        } else {
+            for (int y = y0; y < y1; y += 2) {
+                const float4 u1 = ld_up(y + 1), o1 = ld_own(y + 1);
+                const float e1 = __ldg(a.oth + (size_t)(y + 1) * nxh + (COLOUR ? xe0 : xe1));
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR>(a, y, y * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
+                                                         reinterpret_cast<float4*>(a.own + (size_t)y * nxh + xi0), es, mx, my);
+                const int yn = min(y + 2, y1 - 2);
+                u0 = ld_up(yn); o0 = ld_own(yn);
+                e0 = __ldg(a.oth + (size_t)yn * nxh + (COLOUR ? xe1 : xe0));
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1>(a, y + 1, (y + 1) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
+                                                             reinterpret_cast<float4*>(a.own + (size_t)(y + 1) * nxh + xi0), es, mx, my);
+                const XYRow t = mid; mid = dn; dn = up; (void)t;
+            }
         }
     }
     if (MEASURE) {
