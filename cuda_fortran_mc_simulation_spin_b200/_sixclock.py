@@ -48,6 +48,39 @@ class sixclock:
     def update_metropolis(self): self._call("update_metropolis")
     def update_metropolis_n(self, n): self._call("update_metropolis_n", int(n), argtypes=(i32,))
 
+    def set_sample_offset(self, first_sample):
+        """this handle's samples are samples first_sample .. first_sample + n_multi - 1 of the job (a batch split across
+        GPUs, one handle per rank, no exchange); call right after construction"""
+        self._call("set_sample_offset", int(first_sample), argtypes=(i32,))
+        return self
+
+    @classmethod
+    def distributed(cls, nx, ny, kbt, mstate, n_multi, iseed, group=None, variant=0):
+        """the n_multi samples of the job shared out over the ranks of a torch.distributed group (independent samples:
+        no collective on the data path); calc_energy_all / calc_magne_all gather the per-sample values of the whole job"""
+        import torch.distributed as dist
+        from .clock_gpu_multi_m import split_samples
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        lo, hi = split_samples(n_multi, rank, world)
+        if hi == lo:
+            raise ValueError(f"rank {rank}: no sample to run ({n_multi} samples on {world} ranks)")
+        self = cls(nx, ny, kbt, mstate, hi - lo, iseed, variant)
+        self.set_sample_offset(lo)
+        self._dist = (dist, group)
+        return self
+
+    def _gather(self, local):
+        dist, group = self._dist
+        parts = [None] * dist.get_world_size(group)
+        dist.all_gather_object(parts, [float(x) for x in np.atleast_1d(local)], group=group)
+        return np.array([x for p in parts for x in p], dtype=np.float64)
+
+    def calc_energy_all(self):
+        return self._gather(self.calc_energy())
+
+    def calc_magne_all(self):
+        return self._gather(self.calc_magne())
+
     def update_with_rnds(self, rnds):
         r = np.ascontiguousarray(rnds, dtype=np.float64)
         if r.size != 2 * self.nall() * self.n_multi():

@@ -25,6 +25,7 @@ struct Clock {
     uint64_t* d_thr;
     uint16_t* d_thr16;     // direct lookup table (q <= 6)
     int direct, grid_direct, smem_direct;
+    int sample0;           // this handle holds samples sample0 .. sample0 + n_multi - 1 of the job (batch split across GPUs)
     double* d_ws;
     double* d_rand;
     double* d_next;
@@ -107,10 +108,10 @@ void fill_args(Clock* m, int j, int colour, ClockArgs* a)
     a->r.ticket = nullptr; a->r.chunk = 128;
     a->cls = m->d_cls; a->thr = m->d_thr; a->q = (uint32_t)m->q;
     a->tab_bytes = (uint32_t)((size_t)m->q * m->q * m->q * m->q * m->q * m->q);
-    a->replica = (uint32_t)j;
+    a->replica = (uint32_t)(m->sample0 + j);
     for (int r = 0; r < 10; ++r) {
         a->rk0[r] = m->seed + (uint32_t)r * PHILOX_W0;
-        a->rk1[r] = TAG_CLOCK + (uint32_t)j + (uint32_t)r * PHILOX_W1;
+        a->rk1[r] = TAG_CLOCK + (uint32_t)(m->sample0 + j) + (uint32_t)r * PHILOX_W1;
     }
     a->cls_in_smem = m->cls_in_smem;
     a->thr16 = m->d_thr16;
@@ -208,7 +209,7 @@ int create(void** out, int64_t nx, int64_t ny, double kbt, int32_t q, int32_t n_
     if (!m) ARG_FAIL("out of host memory");
     m->nx = nx; m->ny = ny; m->q = q; m->n_multi = n_multi; m->multi = multi; m->stream = 0;
     m->seed = (uint32_t)iseed; m->draw = 0; m->beta = 1 / kbt; m->obs_valid = false;
-    m->d_cls = nullptr; m->d_thr = nullptr; m->d_thr16 = nullptr; m->direct = 0; m->d_ws = nullptr; m->d_rand = nullptr; m->d_next = nullptr; m->d_acc = nullptr;
+    m->d_cls = nullptr; m->d_thr = nullptr; m->d_thr16 = nullptr; m->direct = 0; m->sample0 = 0; m->d_ws = nullptr; m->d_rand = nullptr; m->d_next = nullptr; m->d_acc = nullptr;
     RingGeom g;
     int rc = ring_geom_init(&g, nx, ny, 0);
     if (rc) { delete m; return rc; }
@@ -268,7 +269,7 @@ int set_random(Clock* m)
         const RingGeom& g = m->st[j].g;
         for (int c = 0; c < 2; ++c) {
             COUNT_LAUNCH();
-            clock_random_kernel<<<(unsigned)((g.L + 255) / 256), 256, 0, m->stream>>>(m->st[j].vec[c], g.L, g.H, 0, m->seed + 0x9E3779B9u * (uint32_t)j, m->draw, (uint32_t)c, (uint32_t)m->q);
+            clock_random_kernel<<<(unsigned)((g.L + 255) / 256), 256, 0, m->stream>>>(m->st[j].vec[c], g.L, g.H, 0, m->seed + 0x9E3779B9u * (uint32_t)(m->sample0 + j), m->draw, (uint32_t)c, (uint32_t)m->q);
             CK(cudaGetLastError());
         }
         int rc = ring_halo(&m->st[j], 0, m->stream);
@@ -391,6 +392,13 @@ int64_t b200mc_clock_nx(void* h) { return h ? HC(h)->nx : -1; }
 int64_t b200mc_clock_ny(void* h) { return h ? HC(h)->ny : -1; }
 int64_t b200mc_clock_nall(void* h) { return h ? HC(h)->st[0].g.N : -1; }
 int32_t b200mc_clock_state(void* h) { return h ? HC(h)->q : -1; }
+int b200mc_clock_set_sample_offset(void* h, int32_t first_sample)
+{
+    CHECK_C(h);
+    if (first_sample < 0) ARG_FAIL("first_sample must be >= 0");
+    HC(h)->sample0 = first_sample;
+    return B200MC_OK;
+}
 int32_t b200mc_clock_n_multi(void* h) { return h ? HC(h)->n_multi : -1; }
 double b200mc_clock_kbt(void* h) { return h ? 1 / HC(h)->beta : 0.0; }
 double b200mc_clock_beta(void* h) { return h ? HC(h)->beta : 0.0; }

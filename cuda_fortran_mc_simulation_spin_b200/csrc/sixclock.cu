@@ -42,6 +42,7 @@ struct SixArgs {
     int nxh, ny, nvr;        // sites per row per colour, rows, 16-byte vectors per row
     int nrows;               // n_multi * ny
     int colour;
+    uint32_t sample0;        // global index of this handle's first sample (a batch split across GPUs)
     uint32_t q;
     const uint8_t* cls;      // q^6 class ids: c + q(new + q(r + q(u + q(l + q d))))   (states_to_prob index order, :72-80)
     const uint32_t* thi;     // per class: thr >> 16  (0 .. 65536)
@@ -159,7 +160,7 @@ __device__ __forceinline__ void six_vector(const SixArgs& a, const SixSmem& sm, 
     const uint4 dn = ld_other(reinterpret_cast<const uint4*>(a.oth + (size_t)Yd * pitch) + v);
     const uint4 s = six_shifted(row, b, v, nvr, a.nxh, P);
     const uint4 rt = P ? s : b, lf = P ? b : s;
-    const uint32_t k1 = TAG_TORUS + (uint32_t)rep;
+    const uint32_t k1 = TAG_TORUS + a.sample0 + (uint32_t)rep;
     const uint32_t blk = (uint32_t)(y * nvr + v);
     uint32_t outw[4];
     uint32_t ties = 0;
@@ -416,6 +417,7 @@ __global__ void sixclock_import_half_kernel(uint8_t* c, int nxh, int ny, size_t 
 struct Six {
     int64_t nx, ny;
     int32_t q, n_multi;
+    int32_t sample0;   // this handle holds samples sample0 .. sample0 + n_multi - 1 of the job
     int variant;                 // 0: tableall / table delta-E expression, 1: clock_simple's
     int nxh, nvr;
     size_t pitch, rep_bytes;     // bytes per row / per replica per colour
@@ -515,7 +517,7 @@ void fill_args(Six* m, int colour, SixArgs* a)
 {
     a->own = m->c[colour]; a->oth = m->c[colour ^ 1];
     a->nxh = m->nxh; a->ny = (int)m->ny; a->nvr = m->nvr; a->nrows = (int)(m->n_multi * m->ny);
-    a->colour = colour; a->q = (uint32_t)m->q;
+    a->colour = colour; a->q = (uint32_t)m->q; a->sample0 = (uint32_t)m->sample0;
     a->cls = m->d_cls; a->thi = m->d_thi; a->tlo = m->d_tlo; a->thr16 = m->d_thr16;
     a->tab_bytes = (uint32_t)m->prob.size(); a->cls_in_smem = m->cls_in_smem;
     a->draw = m->draw;
@@ -633,6 +635,7 @@ int b200mc_sixclock_create_variant(void** out, int64_t nx, int64_t ny, double kb
     if ((double)n_multi * (double)ny * (double)nvr >= 2147483000.0) ARG_FAIL("sixclock: lattice x batch too large for 32-bit vector indices");
     Six* m = new (std::nothrow) Six();
     if (!m) ARG_FAIL("out of host memory");
+    m->sample0 = 0;
     m->nx = nx; m->ny = ny; m->q = mstate; m->n_multi = n_multi; m->nxh = (int)nxh; m->nvr = (int)nvr; m->variant = variant;
     m->pitch = (size_t)nvr * 16; m->rep_bytes = m->pitch * (size_t)ny;
     m->stream = 0; m->seed = (uint32_t)iseed; m->draw = 0; m->beta = 1 / kbt; m->obs_valid = false;
@@ -852,6 +855,13 @@ int64_t b200mc_sixclock_nx(void* h) { return h ? HS(h)->nx : -1; }
 int64_t b200mc_sixclock_ny(void* h) { return h ? HS(h)->ny : -1; }
 int64_t b200mc_sixclock_nall(void* h) { return h ? HS(h)->nx * HS(h)->ny : -1; }
 int32_t b200mc_sixclock_mstate(void* h) { return h ? HS(h)->q : -1; }
+int b200mc_sixclock_set_sample_offset(void* h, int32_t first_sample)
+{
+    CHECK_S(h);
+    if (first_sample < 0) ARG_FAIL("first_sample must be >= 0");
+    HS(h)->sample0 = first_sample;
+    return B200MC_OK;
+}
 int32_t b200mc_sixclock_n_multi(void* h) { return h ? HS(h)->n_multi : -1; }
 double b200mc_sixclock_kbt(void* h) { return h ? 1 / HS(h)->beta : 0.0; }
 double b200mc_sixclock_beta(void* h) { return h ? HS(h)->beta : 0.0; }

@@ -214,6 +214,11 @@ int64_t b200mc_clock_ny(void* h);
 int64_t b200mc_clock_nall(void* h);
 int32_t b200mc_clock_state(void* h);
 int32_t b200mc_clock_n_multi(void* h);
+/* A batch split across GPUs (one handle per rank, no exchange: the replicas of clock_gpu_multi_m :13-48 are
+ * independent): this handle's samples are samples first_sample .. first_sample + n_multi - 1 of the job, i.e. they
+ * draw the random streams those samples have in a single handle holding the whole batch.  Call before the first
+ * set_random_spin / update. */
+int b200mc_clock_set_sample_offset(void* h, int32_t first_sample);
 double b200mc_clock_kbt(void* h);
 double b200mc_clock_beta(void* h);
 int b200mc_clock_sync(void* h);
@@ -263,6 +268,8 @@ int64_t b200mc_sixclock_ny(void* h);
 int64_t b200mc_sixclock_nall(void* h);
 int32_t b200mc_sixclock_mstate(void* h);
 int32_t b200mc_sixclock_n_multi(void* h);
+/* as b200mc_clock_set_sample_offset, for the batched periodic clock modules */
+int b200mc_sixclock_set_sample_offset(void* h, int32_t first_sample);
 double b200mc_sixclock_kbt(void* h);
 double b200mc_sixclock_beta(void* h);
 int b200mc_sixclock_set_timing(void* h, int32_t on);

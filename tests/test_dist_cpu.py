@@ -18,3 +18,15 @@ def test_slab_host_logic_two_gloo_ranks():
     sys.stderr.write(r.stderr[-3000:])
     assert r.returncode == 0
     assert "dist cpu ok world=2" in r.stdout
+
+
+def test_split_samples_covers_the_batch_once():
+    """host logic of the batch split (clock samples across ranks): contiguous, disjoint, complete, balanced"""
+    from cuda_fortran_mc_simulation_spin_b200.clock_gpu_multi_m import split_samples
+    for n in (1, 2, 5, 8, 13):
+        for world in (1, 2, 3, 8):
+            parts = [split_samples(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
