@@ -207,3 +207,46 @@ __device__ __forceinline__ void block_atomic_add_f64(double* dst, double (&v)[NV
         }
     }
 }
+
+// ---------------------------------------------------------------------------
+// XY models: angles are stored as fp32 turns in [0, 1]
+// ---------------------------------------------------------------------------
+// cos / sin of an angle known to lie in [0, 1] turns (every producer of stored angles keeps them there, and a
+// candidate is a uniform in (0, 1]): sin.approx / cos.approx keep their 2^-20.5 absolute error on [-2 pi, 2 pi], so no
+// range reduction is needed -- 1 FMUL + 2 MUFU (+ the FMUL.RZ inside the approximation).
+__device__ __forceinline__ void sincos_unit(float t, float& s, float& c)
+{
+__sincosf(t * 6.283185307179586f, &s, &c);
+}
+
+// atan2(y, x) / (2 pi) in [-1/2, 1/2]: octant reduction, q = min / max by MUFU.RCP, odd polynomial q P(q^2)
+// (Chebyshev fit of atan(q) / (2 pi q) on [0, 1], max error 3e-8 turns evaluated in fp32 -- half an ulp of the
+// stored angle near 1/2), about half the instructions of atan2f.  atan2(0, 0) = 0 like atan2f.
+__device__ __forceinline__ float atan2_turns(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float q = __fdividef(mn, fmaxf(mx, 1e-30f));
+    const float s2 = q * q;
+    float p = -0.0007430583355017006f;
+    p = fmaf(p, s2, 0.0038461685180664062f);
+    p = fmaf(p, s2, -0.009448567405343056f);
+    p = fmaf(p, s2, 0.015766043215990067f);
+    p = fmaf(p, s2, -0.022308088839054108f);
+    p = fmaf(p, s2, 0.03178202360868454f);
+    p = fmaf(p, s2, -0.05304946005344391f);
+    p = fmaf(p, s2, 0.15915492177009583f);
+    float r = p * q;                       // [0, 1/8]
+    r = ay > ax ? 0.25f - r : r;
+    r = x < 0.0f ? 0.5f - r : r;
+    return y < 0.0f ? -r : r;
+}
+
+// t - floor(t) for |t| < 2^22, result in [0, 1]: t - rint(t) with the 1.5 * 2^23 add/subtract pair (two FADD instead of
+// FRND, which shares the XU pipe with MUFU), then one conditional add
+__device__ __forceinline__ float frac_turns(float t)
+{
+    const float fr = t - __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);   // [-1/2, 1/2]
+    return fr < 0.0f ? fr + 1.0f : fr;
+}
+

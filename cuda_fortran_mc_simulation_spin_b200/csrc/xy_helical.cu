@@ -61,10 +61,11 @@ __device__ __forceinline__ void xyh_field(const XYHArgs& a, int k, float& hx, fl
 {
     const int c = a.colour, nc = a.nc;
     float s, co;
-    sincos_turns(a.oth[wrap(k - 1 + c, nc)], s, co); hx = co; hy = s;
-    sincos_turns(a.oth[wrap(k + c, nc)], s, co); hx += co; hy += s;
-    sincos_turns(a.oth[wrap(k + a.h + c, nc)], s, co); hx += co; hy += s;
-    sincos_turns(a.oth[wrap(k - a.h - 1 + c, nc)], s, co); hx += co; hy += s;
+    // (stored angles lie in [0, 1] turns: no range reduction, common.cuh)
+    sincos_unit(a.oth[wrap(k - 1 + c, nc)], s, co); hx = co; hy = s;
+    sincos_unit(a.oth[wrap(k + c, nc)], s, co); hx += co; hy += s;
+    sincos_unit(a.oth[wrap(k + a.h + c, nc)], s, co); hx += co; hy += s;
+    sincos_unit(a.oth[wrap(k - a.h - 1 + c, nc)], s, co); hx += co; hy += s;
 }
 
 template <bool OVERRELAX>
@@ -88,9 +89,8 @@ xyh_pass_kernel(const __grid_constant__ XYHArgs a)
         const float t0 = a.own[k];
         if (OVERRELAX) {
             // over_relaxation_sub, :198-213: s <- 2 (h^ . s) h^ - s, i.e. theta <- 2 phi - theta
-            const float phi = atan2f(hy, hx) * INV_TWO_PI_F;
-            const float t = 2.0f * phi - t0;
-            a.own[k] = t - floorf(t);
+            const float t = 2.0f * atan2_turns(hy, hx) - t0;
+            a.own[k] = frac_turns(t);
         } else {
             // update_sub, :157-174: accept iff r <= exp(-beta dE), dE = -(cand - s) . h
             const uint4 Rj = R[j >> 1];
@@ -98,8 +98,8 @@ xyh_pass_kernel(const __grid_constant__ XYHArgs a)
             const float r = ((float)Ur + 1.0f) * 0x1p-32f;
             const float ct = ((float)Uc + 1.0f) * 0x1p-32f;
             float cs, cc, ss, sc;
-            sincos_turns(ct, cs, cc);
-            sincos_turns(t0, ss, sc);
+            sincos_unit(ct, cs, cc);
+            sincos_unit(t0, ss, sc);
             const float de = -((cc - sc) * hx + (cs - ss) * hy);
             if (!(r > __expf(-a.beta * de))) a.own[k] = ct;
         }
@@ -169,7 +169,7 @@ __global__ void xyh_export_turns_kernel(const float* c0, const float* c1, long l
 __global__ void xyh_import_turns_kernel(float* c0, float* c1, long long nall, const float* in)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nall) ((i & 1) ? c1 : c0)[i >> 1] = in[i];
+    if (i < nall) { const float t = in[i]; ((i & 1) ? c1 : c0)[i >> 1] = t - floorf(t); }   // stored angles live in [0, 1] turns
 }
 
 struct XYH {
