@@ -28,6 +28,10 @@ struct XYArgs {
     uint64_t draw;
     uint32_t rk0[10];
     double* acc;   // MEASURE: acc[0] += E, acc[1] += sum cos, acc[2] += sum sin
+    // rows as a slab (the step towards slabs along y): halo = 1 -> the other colour's rows -1 and ny are
+    // halo rows kept current by the host side after every colour pass (no periodic wrap of the row index in the
+    // kernels); yoff = global index of local row 0 (even), used for the RNG counter
+    int halo, yoff;
 };
 
 __device__ __forceinline__ void sincos_turns(float t, float& s, float& c)
@@ -73,7 +77,7 @@ struct XYRow { float c[4], s[4]; };
 
 __device__ __forceinline__ void xy_load_row(const XYArgs& a, int y, int g, XYRow& r)
 {
-    const float4 raw = *reinterpret_cast<const float4*>(a.oth + (size_t)y * a.nxh + 4 * g);
+    const float4 raw = *reinterpret_cast<const float4*>(a.oth + (ptrdiff_t)y * a.nxh + 4 * g);   // y = -1 / ny: halo rows
     sincos_turns(raw.x, r.s[0], r.c[0]);
     sincos_turns(raw.y, r.s[1], r.c[1]);
     sincos_turns(raw.z, r.s[2], r.c[2]);
@@ -179,7 +183,7 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
         const int nxh = a.nxh, xi0 = 4 * g;
         const float nbl2e = a.beta * 1.4426950408889634f;
         XYRow dn, mid, up;
-        xy_load_row(a, y0 == 0 ? a.ny - 1 : y0 - 1, g, dn);
+        xy_load_row(a, (y0 == 0 && !a.halo) ? a.ny - 1 : y0 - 1, g, dn);
         xy_load_row(a, y0, g, mid);
         // the fifth same-row value: left of the group on rows with P = 0, right of it on rows with P = 1
         const int xe0 = xi0 == 0 ? nxh - 1 : xi0 - 1, xe1 = xi0 + 4 == nxh ? 0 : xi0 + 4;
@@ -187,7 +191,7 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
         // loaded one row ahead, unconditionally (clamped row index: straight-line code that the scheduler issues
         // at the top): the stores to `own` would otherwise pin every load behind them (no restrict on the two
         // colour arrays) and each row would pay a full DRAM round trip
-        auto ld_up = [&](int y) { return __ldg(reinterpret_cast<const float4*>(a.oth + (size_t)(y + 1 >= a.ny ? y + 1 - a.ny : y + 1) * nxh + xi0)); };
+        auto ld_up = [&](int y) { return __ldg(reinterpret_cast<const float4*>(a.oth + (ptrdiff_t)((y + 1 >= a.ny && !a.halo) ? y + 1 - a.ny : y + 1) * nxh + xi0)); };
         auto ld_own = [&](int y) { return *reinterpret_cast<const float4*>(a.own + (size_t)y * nxh + xi0); };
         float4 u0 = ld_up(y0), o0 = ld_own(y0);
         float e0 = __ldg(a.oth + (size_t)y0 * nxh + (COLOUR ? xe1 : xe0));
@@ -202,9 +206,9 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
                 const float4 nu0 = ld_up(yn), no0 = ld_own(yn), nu1 = ld_up(yn + 1), no1 = ld_own(yn + 1);
                 const float ne0 = __ldg(a.oth + (size_t)yn * nxh + (COLOUR ? xe1 : xe0));
                 const float ne1 = __ldg(a.oth + (size_t)(yn + 1) * nxh + (COLOUR ? xe0 : xe1));
-                xy_strip_row<OVERRELAX, MEASURE, COLOUR>(a, y, y * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR>(a, y, (y + a.yoff) * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
                                                          reinterpret_cast<float4*>(a.own + (size_t)y * nxh + xi0), es, mx, my);
-                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1>(a, y + 1, (y + 1) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1>(a, y + 1, (y + 1 + a.yoff) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
                                                              reinterpret_cast<float4*>(a.own + (size_t)(y + 1) * nxh + xi0), es, mx, my);
                 u0 = nu0; o0 = no0; e0 = ne0; u1 = nu1; o1 = no1; e1 = ne1;
                 // rows rotate by two: (dn, mid, up) <- (up of the first row = mid of the second, up of the second)
@@ -214,12 +218,12 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
             for (int y = y0; y < y1; y += 2) {
                 const float4 u1 = ld_up(y + 1), o1 = ld_own(y + 1);
                 const float e1 = __ldg(a.oth + (size_t)(y + 1) * nxh + (COLOUR ? xe0 : xe1));
-                xy_strip_row<OVERRELAX, MEASURE, COLOUR>(a, y, y * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR>(a, y, (y + a.yoff) * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
                                                          reinterpret_cast<float4*>(a.own + (size_t)y * nxh + xi0), es, mx, my);
                 const int yn = min(y + 2, y1 - 2);
                 u0 = ld_up(yn); o0 = ld_own(yn);
                 e0 = __ldg(a.oth + (size_t)yn * nxh + (COLOUR ? xe1 : xe0));
-                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1>(a, y + 1, (y + 1) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1>(a, y + 1, (y + 1 + a.yoff) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
                                                              reinterpret_cast<float4*>(a.own + (size_t)(y + 1) * nxh + xi0), es, mx, my);
                 const XYRow t = mid; mid = dn; dn = up; (void)t;
             }
@@ -269,7 +273,7 @@ xy_field_kernel(const __grid_constant__ XYArgs a, float hx, float hy)
 // XY_ROWS rows and keeps the previous row's cos/sin, so every site costs one sincos (+ 1/8 for the group edge)
 // instead of three.  Bonds: (x, x+1) inside the row, (y-1, y) against the previous row.
 __global__ void __launch_bounds__(256)
-xy_measure_kernel(const float* __restrict__ c0, const float* __restrict__ c1, int nxh, int ny, int gpr, double* acc)
+xy_measure_kernel(const float* __restrict__ c0, const float* __restrict__ c1, int nxh, int ny, int gpr, double* acc, int halo)
 {
     double part[3] = {0.0, 0.0, 0.0};
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -281,14 +285,14 @@ xy_measure_kernel(const float* __restrict__ c0, const float* __restrict__ c1, in
         float es = 0.f, mx = 0.f, my = 0.f;
         // cos / sin of the 8 sites x0 = 8 g .. 8 g + 7 of row y, in lattice order: even x0 belong to colour (y & 1)
         auto load_row = [&](int y, float (&c)[8], float (&sn)[8]) {
-            const float4 a = *reinterpret_cast<const float4*>(((y & 1) ? c1 : c0) + (size_t)y * nxh + 4 * g);
-            const float4 b = *reinterpret_cast<const float4*>(((y & 1) ? c0 : c1) + (size_t)y * nxh + 4 * g);
+            const float4 a = *reinterpret_cast<const float4*>(((y & 1) ? c1 : c0) + (ptrdiff_t)y * nxh + 4 * g);
+            const float4 b = *reinterpret_cast<const float4*>(((y & 1) ? c0 : c1) + (ptrdiff_t)y * nxh + 4 * g);
             sincos_turns(a.x, sn[0], c[0]); sincos_turns(b.x, sn[1], c[1]);
             sincos_turns(a.y, sn[2], c[2]); sincos_turns(b.y, sn[3], c[3]);
             sincos_turns(a.z, sn[4], c[4]); sincos_turns(b.z, sn[5], c[5]);
             sincos_turns(a.w, sn[6], c[6]); sincos_turns(b.w, sn[7], c[7]);
         };
-        load_row(y0 == 0 ? ny - 1 : y0 - 1, pc, ps);
+        load_row((y0 == 0 && !halo) ? ny - 1 : y0 - 1, pc, ps);   // (halo: row -1 of both colours)
         for (int y = y0; y < y1; ++y) {
             load_row(y, qc, qs);
             // the site right of the group: x0 = 8 g + 8 (periodic), an even x0 -> colour (y & 1), xi = 4 g + 4
@@ -410,7 +414,9 @@ __global__ void xy_import_turns_kernel(float* c0, float* c1, int nx, int ny, con
 struct XY {
     int64_t nx, ny;
     int nxh, gpr;
-    float* c[2];   // colour arrays
+    float* c[2];   // colour arrays: row 0 of the allocation below (one spare row before and after = the halo rows of slab mode)
+    float* base[2];
+    int halo;      // 1: kernels read halo rows instead of wrapping the row index (B200MC_XY_HALO=1: single-GPU self-neighbour experiment)
     float* z[2];   // autocorrelation snapshot (allocated on first use)
     float* stage;  // nx*ny floats / export staging
     double* d_acc;
@@ -432,6 +438,19 @@ void fill_args(XY* m, int colour, XYArgs* a)
     a->beta = (float)m->beta; a->draw = m->draw;
     for (int r = 0; r < 10; ++r) a->rk0[r] = m->seed + (uint32_t)r * PHILOX_W0;
     a->acc = m->d_acc;
+    a->halo = m->halo; a->yoff = 0;
+}
+
+// slab mode: rows -1 and ny of the colour just written.  Single GPU (self-neighbour): row ny - 1 and row 0 of the same
+// array; between ranks these two copies become the send / receive of one row each way.
+int halo_rows(XY* m, int colour)
+{
+    if (!m->halo) return B200MC_OK;
+    float* c = m->c[colour];
+    const size_t row = (size_t)m->nxh * sizeof(float);
+    CK(cudaMemcpyAsync(c - m->nxh, c + (size_t)(m->ny - 1) * m->nxh, row, cudaMemcpyDeviceToDevice, m->stream));
+    CK(cudaMemcpyAsync(c + (size_t)m->ny * m->nxh, c, row, cudaMemcpyDeviceToDevice, m->stream));
+    return B200MC_OK;
 }
 
 int sweep(XY* m)
@@ -450,6 +469,7 @@ int sweep(XY* m)
             else xy_strip_kernel<false, false, 1><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
         } else xy_strip_kernel<false, false, 0><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);   // (sums are fused into colour 1 only)
         CK(cudaGetLastError());
+        { int rch = halo_rows(m, colour); if (rch) return rch; }
         if (fuse) m->fused_pending = true;
     }
     m->draw += 1;
@@ -475,6 +495,7 @@ int over_relax(XY* m, int n_steps)
                 else xy_strip_kernel<true, false, 1><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
             } else xy_strip_kernel<true, false, 0><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
             CK(cudaGetLastError());
+            { int rch = halo_rows(m, colour); if (rch) return rch; }
             if (fuse) m->fused_pending = true;
         }
     return B200MC_OK;
@@ -490,6 +511,7 @@ int by_field(XY* m, double hx, double hy)
         COUNT_LAUNCH();
         xy_field_kernel<<<(total + 255) / 256, 256, 0, m->stream>>>(a, (float)hx, (float)hy);
         CK(cudaGetLastError());
+        { int rch = halo_rows(m, colour); if (rch) return rch; }
     }
     m->draw += 1;
     return B200MC_OK;
@@ -502,7 +524,7 @@ int measure(XY* m)
         CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
         COUNT_LAUNCH();
         const int strips = (int)((m->ny + XY_ROWS - 1) / XY_ROWS) * m->gpr;
-        xy_measure_kernel<<<(strips + 255) / 256, 256, 0, m->stream>>>(m->c[0], m->c[1], m->nxh, (int)m->ny, m->gpr, m->d_acc);
+        xy_measure_kernel<<<(strips + 255) / 256, 256, 0, m->stream>>>(m->c[0], m->c[1], m->nxh, (int)m->ny, m->gpr, m->d_acc, m->halo);
         CK(cudaGetLastError());
     }
     m->fused_pending = false;
@@ -531,7 +553,7 @@ int corr(XY* m, bool autoc, double* out)
 void destroy(XY* m)
 {
     cudaStreamSynchronize(m->stream);
-    cudaFree(m->c[0]); cudaFree(m->c[1]); cudaFree(m->z[0]); cudaFree(m->z[1]); cudaFree(m->stage); cudaFree(m->d_acc);
+    cudaFree(m->base[0]); cudaFree(m->base[1]); cudaFree(m->z[0]); cudaFree(m->z[1]); cudaFree(m->stage); cudaFree(m->d_acc);
     delete m;
 }
 
@@ -542,6 +564,7 @@ int fill(XY* m, float v)
     COUNT_LAUNCH();
     xy_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], n, v);
     CK(cudaGetLastError());
+    { int rch = halo_rows(m, 0); if (!rch) rch = halo_rows(m, 1); if (rch) return rch; }
     return B200MC_OK;
 }
 
@@ -576,16 +599,21 @@ int b200mc_xy2d_create(void** out, int64_t nx, int64_t ny, double kbt, int32_t i
     if (!m) ARG_FAIL("out of host memory");
     m->nx = nx; m->ny = ny; m->nxh = (int)(nx / 2); m->gpr = m->nxh / 4; m->stream = 0;
     m->beta = 1 / kbt; m->seed = (uint32_t)iseed; m->draw = 0; m->obs_valid = false; m->fused_pending = false; m->want_fused = false;
-    m->c[0] = m->c[1] = m->z[0] = m->z[1] = m->stage = nullptr; m->d_acc = nullptr;
+    m->c[0] = m->c[1] = m->base[0] = m->base[1] = m->z[0] = m->z[1] = m->stage = nullptr; m->d_acc = nullptr; m->halo = 0;
     int dev = 0; m->sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&m->sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t n = (size_t)m->nxh * ny;
-    if (cudaMalloc(&m->c[0], n * sizeof(float)) != cudaSuccess || cudaMalloc(&m->c[1], n * sizeof(float)) != cudaSuccess ||
+    { const char* t = getenv("B200MC_XY_HALO"); m->halo = (t && atoi(t)) ? 1 : 0; }
+    const size_t nalloc = n + 2 * (size_t)m->nxh;
+    if (cudaMalloc(&m->base[0], nalloc * sizeof(float)) != cudaSuccess || cudaMalloc(&m->base[1], nalloc * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&m->d_acc, 3 * sizeof(double)) != cudaSuccess) {
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed");
         destroy(m); return B200MC_ERR_CUDA;
     }
+    m->c[0] = m->base[0] + m->nxh; m->c[1] = m->base[1] + m->nxh;
+    cudaMemsetAsync(m->base[0], 0, nalloc * sizeof(float), m->stream);
+    cudaMemsetAsync(m->base[1], 0, nalloc * sizeof(float), m->stream);
     int rc = fill(m, 0.0f);  // set_allup_spin: all along +x
     if (rc) { destroy(m); return rc; }
     *out = m;
@@ -612,6 +640,7 @@ int b200mc_xy2d_set_random_spin(void* h)
         COUNT_LAUNCH();
         xy_random_kernel<<<(total + 255) / 256, 256, 0, m->stream>>>(m->c[c], m->nxh, (int)m->ny, m->gpr, c, m->seed, m->draw);
         CK(cudaGetLastError());
+        { int rch = halo_rows(m, c); if (rch) return rch; }
     }
     m->draw += 1;
     return B200MC_OK;
@@ -664,6 +693,7 @@ int b200mc_xy2d_rotate_summation_magne_toward_xaxis(void* h, int32_t with_autoco
         xy_rotate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->z[0], m->z[1], n, dt);
     }
     CK(cudaGetLastError());
+    { int rch = halo_rows(m, 0); if (!rch) rch = halo_rows(m, 1); if (rch) return rch; }
     return B200MC_OK;
 }
 int b200mc_xy2d_metropolis_by_field(void* h, double hx, double hy) { CHECK_X(h); return by_field(HX(h), hx, hy); }
@@ -747,6 +777,7 @@ int b200mc_xy2d_set_angles(void* h, const float* in)
     COUNT_LAUNCH();
     xy_import_turns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], (int)m->nx, (int)m->ny, m->stage);
     CK(cudaGetLastError());
+    { int rch = halo_rows(m, 0); if (!rch) rch = halo_rows(m, 1); if (rch) return rch; }
     CK(cudaStreamSynchronize(m->stream));
     return B200MC_OK;
 }

@@ -20,8 +20,18 @@ def _close(a, b, scale):
     return abs(a - b) <= RTOL * scale
 
 
+@pytest.fixture(params=["wrap", "halo_rows"])
+def row_mode(request, monkeypatch):
+    """rows of the other colour beyond the first / last row: periodic wrap of the row index inside the kernels (default)
+    or halo rows refreshed after every colour pass (B200MC_XY_HALO=1: the single-GPU self-neighbour form of slabs along
+    y) -- both against the oracle"""
+    if request.param == "halo_rows":
+        monkeypatch.setenv("B200MC_XY_HALO", "1")
+    return request.param
+
+
 @pytest.mark.parametrize("shape,kbt", [((16, 8), 0.89), ((64, 64), 0.895), ((256, 128), 0.5), ((1024, 512), 0.89), ((40, 30), 1.5)])
-def test_xy_metropolis_per_sweep(oracle, shape, kbt):
+def test_xy_metropolis_per_sweep(oracle, shape, kbt, row_mode):
     from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
     nx, ny = shape
     g = xm.xy2d_gpu().init(nx, ny, kbt, 42)
@@ -50,7 +60,7 @@ def test_xy_metropolis_per_sweep(oracle, shape, kbt):
 
 
 @pytest.mark.parametrize("shape", [(16, 8), (128, 64), (1024, 512)])
-def test_xy_over_relaxation(oracle, shape):
+def test_xy_over_relaxation(oracle, shape, row_mode):
     from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
     nx, ny = shape
     g = xm.xy2d_gpu().init(nx, ny, 0.89, 7)
@@ -132,7 +142,7 @@ def test_xy_full_size_properties():
     assert -2.0 * n < e1 < 0
 
 
-def test_xy_metropolis_by_field_per_application(oracle):
+def test_xy_metropolis_by_field_per_application(oracle, row_mode):
     """metropolis_by_field_sub (src/xy2d_periodic_gpu_m.f90:198-216): accepted iff r <= 1 - exp(dE)"""
     from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
     nx, ny = 128, 64
@@ -175,7 +185,7 @@ def test_xy_initial_state_preparation():
     assert abs(math.hypot(mx, my) / n - 0.001) / 0.001 <= 0.5 + 1e-3
 
 
-def test_xy_fused_measurement_equals_separate_pass():
+def test_xy_fused_measurement_equals_separate_pass(row_mode):
     """after a measured sweep the last colour pass (Metropolis or over-relaxation) accumulates E, Mx, My itself"""
     from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
     g = xm.xy2d_gpu().init(512, 256, 0.89, 5)
@@ -189,3 +199,26 @@ def test_xy_fused_measurement_equals_separate_pass():
         g.set_angles(g.angles())             # invalidates: the separate kernel recounts the same configuration
         b = g.measure()
         assert all(abs(x - y) <= 2e-6 * n for x, y in zip(a, b)), (it, a, b)
+
+
+def test_xy_halo_row_mode_is_the_periodic_path(monkeypatch):
+    """same seed, same calls: the halo-row form (no wrap in the kernels, rows -1 / ny copied after every pass) gives the
+    same angles bit for bit as the periodic form, through Metropolis, over-relaxation, rotation and the fused sums"""
+    from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
+
+    def run():
+        g = xm.xy2d_gpu().init(64, 72, 0.89, 5)
+        g.set_random_spin()
+        out = []
+        for _ in range(3):
+            g.update(); g.update_over_relaxation(2)
+            out.append(g.measure())
+        g.rotate_summation_magne_toward_xaxis()
+        g.update()
+        out.append(g.measure())
+        return out, g.angles()
+    a, sa = run()
+    monkeypatch.setenv("B200MC_XY_HALO", "1")
+    b, sb = run()
+    assert a == b
+    assert np.array_equal(sa, sb)
