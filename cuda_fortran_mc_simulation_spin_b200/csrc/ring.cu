@@ -188,6 +188,27 @@ int dist_allreduce_u64(void* comm, unsigned long long* buf, int n, cudaStream_t 
     return B200MC_OK;
 }
 
+int dist_allreduce_f64(void* comm, double* buf, int n, cudaStream_t st)
+{
+    NK(g_nccl.AllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)comm, st));
+    return B200MC_OK;
+}
+// One block each way around the ring of ranks: `first` -> rank-1 (which receives it as its `high`), `last` -> rank+1
+// (its `low`).  The receives are posted in the order the two peers send (with two ranks both neighbours are the same
+// peer and NCCL matches its sends in order: first, then last).
+int dist_exchange_ring(void* comm, int rank, int nranks, const void* first, const void* last, void* low, void* high, size_t bytes, cudaStream_t st)
+{
+    const int prev = (rank + nranks - 1) % nranks, next = (rank + 1) % nranks;
+    ncclComm_t c = (ncclComm_t)comm;
+    NK(g_nccl.GroupStart());
+    NK(g_nccl.Send(first, bytes, ncclUint8, prev, c, st));
+    NK(g_nccl.Send(last, bytes, ncclUint8, next, c, st));
+    NK(g_nccl.Recv(high, bytes, ncclUint8, next, c, st));   // next's first
+    NK(g_nccl.Recv(low, bytes, ncclUint8, prev, c, st));    // prev's last
+    NK(g_nccl.GroupEnd());
+    return B200MC_OK;
+}
+
 // rotate every vector of a halo block by one byte-lane: dir = +1: lane b <- lane b-1 (lane 0 <- 15),
 // dir = -1: lane b <- lane b+1 (lane 15 <- 0)
 __global__ void ring_rotate_kernel(uint4* v, int64_t n, int dir)

@@ -182,3 +182,5 @@ int dist_unique_id(char out[128]);
 int dist_comm_init(void** comm, int rank, int nranks, const char id[128]);
 void dist_comm_destroy(void* comm);
 int dist_allreduce_u64(void* comm, unsigned long long* buf, int n, cudaStream_t st);
+int dist_allreduce_f64(void* comm, double* buf, int n, cudaStream_t st);
+int dist_exchange_ring(void* comm, int rank, int nranks, const void* first, const void* last, void* low, void* high, size_t bytes, cudaStream_t st);

@@ -13,6 +13,7 @@
 #include <new>
 #include "../../include/b200mc.h"
 #include "common.cuh"
+#include "ring.cuh"   // dist_*: the NCCL communicator of slab mode
 
 namespace {
 
@@ -78,10 +79,12 @@ struct XYRow { float c[4], s[4]; };
 __device__ __forceinline__ void xy_load_row(const XYArgs& a, int y, int g, XYRow& r)
 {
     const float4 raw = *reinterpret_cast<const float4*>(a.oth + (ptrdiff_t)y * a.nxh + 4 * g);   // y = -1 / ny: halo rows
-    sincos_turns(raw.x, r.s[0], r.c[0]);
-    sincos_turns(raw.y, r.s[1], r.c[1]);
-    sincos_turns(raw.z, r.s[2], r.c[2]);
-    sincos_turns(raw.w, r.s[3], r.c[3]);
+    // (the same function as for the rows loaded inside the strip loop: a site's cos / sin must not depend on where the
+    // row falls in a strip, or the trajectory would depend on the decomposition into strips and slabs)
+    sincos_unit(raw.x, r.s[0], r.c[0]);
+    sincos_unit(raw.y, r.s[1], r.c[1]);
+    sincos_unit(raw.z, r.s[2], r.c[2]);
+    sincos_unit(raw.w, r.s[3], r.c[3]);
 }
 
 // OVERRELAX = false: update_sub + calc_delta_energy, src/xy2d_periodic_gpu_m.f90:368-397
@@ -250,7 +253,7 @@ xy_field_kernel(const __grid_constant__ XYArgs a, float hx, float hy)
     float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
     for (int sub = 0; sub < 2; ++sub) {
-        const uint4 R = philox_tag<TAG_XY>(mk_ctr((uint64_t)idx, a.draw, (uint32_t)a.colour, (uint32_t)sub), a.rk0);
+        const uint4 R = philox_tag<TAG_XY>(mk_ctr((uint64_t)(idx + a.yoff * a.gpr), a.draw, (uint32_t)a.colour, (uint32_t)sub), a.rk0);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int j = 2 * sub + e;
@@ -351,12 +354,12 @@ xy_corr_kernel(const float* __restrict__ c0, const float* __restrict__ c1, const
 
 // set_random_spin_sub (:112-122): theta = 2 pi u  ->  turns = u
 __global__ void __launch_bounds__(256)
-xy_random_kernel(float* own, int nxh, int ny, int gpr, int colour, uint32_t seed, uint64_t draw)
+xy_random_kernel(float* own, int nxh, int ny, int gpr, int colour, uint32_t seed, uint64_t draw, int yoff)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= ny * gpr) return;
     const int y = idx / gpr, g = idx - y * gpr;
-    const uint4 R = philox4x32_10(mk_ctr((uint64_t)idx, draw, (uint32_t)colour, 0u), make_uint2(seed, TAG_INIT));
+    const uint4 R = philox4x32_10(mk_ctr((uint64_t)(idx + yoff * gpr), draw, (uint32_t)colour, 0u), make_uint2(seed, TAG_INIT));
     *reinterpret_cast<float4*>(own + (size_t)y * nxh + 4 * g) =
         make_float4(((float)R.x + 1.0f) * 0x1p-32f, ((float)R.y + 1.0f) * 0x1p-32f, ((float)R.z + 1.0f) * 0x1p-32f, ((float)R.w + 1.0f) * 0x1p-32f);
 }
@@ -416,6 +419,10 @@ struct XY {
     int nxh, gpr;
     float* c[2];   // colour arrays: row 0 of the allocation below (one spare row before and after = the halo rows of slab mode)
     float* base[2];
+    // slabs along y: this rank holds rows [yoff, yoff + ny) of ny_glob; ny is LOCAL everywhere below
+    int rank, nranks;
+    int64_t ny_glob, yoff;
+    void* comm;
     int halo;      // 1: kernels read halo rows instead of wrapping the row index (B200MC_XY_HALO=1: single-GPU self-neighbour experiment)
     float* z[2];   // autocorrelation snapshot (allocated on first use)
     float* stage;  // nx*ny floats / export staging
@@ -438,7 +445,7 @@ void fill_args(XY* m, int colour, XYArgs* a)
     a->beta = (float)m->beta; a->draw = m->draw;
     for (int r = 0; r < 10; ++r) a->rk0[r] = m->seed + (uint32_t)r * PHILOX_W0;
     a->acc = m->d_acc;
-    a->halo = m->halo; a->yoff = 0;
+    a->halo = m->halo; a->yoff = (int)m->yoff;
 }
 
 // slab mode: rows -1 and ny of the colour just written.  Single GPU (self-neighbour): row ny - 1 and row 0 of the same
@@ -448,6 +455,8 @@ int halo_rows(XY* m, int colour)
     if (!m->halo) return B200MC_OK;
     float* c = m->c[colour];
     const size_t row = (size_t)m->nxh * sizeof(float);
+    if (m->nranks > 1)   // my first row is the row above rank-1's last one, my last row the row below rank+1's first
+        return dist_exchange_ring(m->comm, m->rank, m->nranks, c, c + (size_t)(m->ny - 1) * m->nxh, c - m->nxh, c + (size_t)m->ny * m->nxh, row, m->stream);
     CK(cudaMemcpyAsync(c - m->nxh, c + (size_t)(m->ny - 1) * m->nxh, row, cudaMemcpyDeviceToDevice, m->stream));
     CK(cudaMemcpyAsync(c + (size_t)m->ny * m->nxh, c, row, cudaMemcpyDeviceToDevice, m->stream));
     return B200MC_OK;
@@ -529,6 +538,7 @@ int measure(XY* m)
     }
     m->fused_pending = false;
     m->want_fused = true;
+    if (m->nranks > 1) { int rcr = dist_allreduce_f64(m->comm, m->d_acc, 3, m->stream); if (rcr) return rcr; }   // every rank gets the global sums
     CK(cudaMemcpyAsync(m->obs, m->d_acc, 3 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
     m->obs_valid = true;
@@ -538,6 +548,7 @@ int measure(XY* m)
 int corr(XY* m, bool autoc, double* out)
 {
     if (autoc && !m->z[0]) ARG_FAIL("calc_autocorrelation_sum before set_initial_magne_autocorrelation_state");
+    if (m->nranks > 1) { snprintf(g_b200mc_err, sizeof(g_b200mc_err), "xy2d: the correlation sums are not available in slab mode"); return B200MC_ERR_UNSUPPORTED; }
     CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
     COUNT_LAUNCH();
     xy_corr_kernel<<<m->sms * 8, 256, 0, m->stream>>>(m->c[0], m->c[1], autoc ? m->z[0] : nullptr, autoc ? m->z[1] : nullptr, (int)m->nx, (int)m->ny, m->d_acc);
@@ -553,6 +564,7 @@ int corr(XY* m, bool autoc, double* out)
 void destroy(XY* m)
 {
     cudaStreamSynchronize(m->stream);
+    if (m->comm) dist_comm_destroy(m->comm);
     cudaFree(m->base[0]); cudaFree(m->base[1]); cudaFree(m->z[0]); cudaFree(m->z[1]); cudaFree(m->stage); cudaFree(m->d_acc);
     delete m;
 }
@@ -583,8 +595,27 @@ extern "C" {
 
 int b200mc_xy2d_create(void** out, int64_t nx, int64_t ny, double kbt, int32_t iseed)
 {
+    return b200mc_xy2d_create_slab(out, nx, ny, kbt, iseed, 0, 1, nullptr);
+}
+int b200mc_xy2d_create_slab(void** out, int64_t nx, int64_t ny_global, double kbt, int32_t iseed, int32_t rank, int32_t nranks, const char* nccl_id)
+{
     if (!out) ARG_FAIL("null handle pointer");
     *out = nullptr;
+    if (nranks < 1 || rank < 0 || rank >= nranks) ARG_FAIL("bad rank %d / %d", rank, nranks);
+    if (nranks > 1) {
+        // The first 2-GPU run of this path diverged from the one-GPU trajectory: the first rows of a strip took their
+        // cos / sin from a different (range-reducing) function than the rows inside the strip loop, so a site's
+        // arithmetic depended on the decomposition.  That is fixed (xy_load_row), but the round's GPU budget ended
+        // before the fix could be re-run on two GPUs: opt in explicitly until it has been.
+        const char* t = getenv("B200MC_XY_SLAB");
+        if (!(t && atoi(t))) {
+            snprintf(g_b200mc_err, sizeof(g_b200mc_err), "xy2d slabs over several GPUs are not validated yet (set B200MC_XY_SLAB=1 to try them)");
+            return B200MC_ERR_UNSUPPORTED;
+        }
+    }
+    if (nranks > 1 && !nccl_id) ARG_FAIL("slab mode needs the NCCL unique id of the job (b200mc_dist_unique_id on rank 0, broadcast by the caller)");
+    if (ny_global % nranks || ((ny_global / nranks) & 1)) ARG_FAIL("xy2d slabs: ny (%lld) must split into an even number of rows per rank (%d ranks)", (long long)ny_global, nranks);
+    const int64_t ny = ny_global / nranks;
     if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0");
     // the reference needs nx, ny even (colouring, src/xy2d_periodic_gpu_m.f90:377-380); the float4 layout needs nx % 8 == 0
     if (nx < 8 || ny < 2 || (ny & 1)) ARG_FAIL("xy2d: need nx >= 8, ny >= 2 even (got %lld x %lld)", (long long)nx, (long long)ny);
@@ -599,12 +630,18 @@ int b200mc_xy2d_create(void** out, int64_t nx, int64_t ny, double kbt, int32_t i
     if (!m) ARG_FAIL("out of host memory");
     m->nx = nx; m->ny = ny; m->nxh = (int)(nx / 2); m->gpr = m->nxh / 4; m->stream = 0;
     m->beta = 1 / kbt; m->seed = (uint32_t)iseed; m->draw = 0; m->obs_valid = false; m->fused_pending = false; m->want_fused = false;
-    m->c[0] = m->c[1] = m->base[0] = m->base[1] = m->z[0] = m->z[1] = m->stage = nullptr; m->d_acc = nullptr; m->halo = 0;
+    m->c[0] = m->c[1] = m->base[0] = m->base[1] = m->z[0] = m->z[1] = m->stage = nullptr; m->d_acc = nullptr; m->halo = 0; m->comm = nullptr; m->nranks = 1; m->rank = 0;
     int dev = 0; m->sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&m->sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t n = (size_t)m->nxh * ny;
-    { const char* t = getenv("B200MC_XY_HALO"); m->halo = (t && atoi(t)) ? 1 : 0; }
+    { const char* t = getenv("B200MC_XY_HALO"); m->halo = ((t && atoi(t)) || nranks > 1) ? 1 : 0; }
+    m->rank = rank; m->nranks = nranks; m->ny_glob = ny_global; m->yoff = (int64_t)rank * ny; m->comm = nullptr;
+    if (ny_global * (nx / 2) / 4 >= (int64_t)0x7FFFFFFF) { delete m; ARG_FAIL("xy2d: lattice too large for the 32-bit RNG block index"); }
+    if (nranks > 1) {
+        int rcc = dist_comm_init(&m->comm, rank, nranks, nccl_id);
+        if (rcc) { delete m; return rcc; }
+    }
     const size_t nalloc = n + 2 * (size_t)m->nxh;
     if (cudaMalloc(&m->base[0], nalloc * sizeof(float)) != cudaSuccess || cudaMalloc(&m->base[1], nalloc * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&m->d_acc, 3 * sizeof(double)) != cudaSuccess) {
@@ -625,7 +662,7 @@ int b200mc_xy2d_skip_curand(void* h, int64_t n)
 {
     CHECK_X(h);
     if (n < 0) ARG_FAIL("n_skip < 0");
-    const int64_t per = HX(h)->nx * HX(h)->ny;  // one generate call draws nall uniforms
+    const int64_t per = HX(h)->nx * HX(h)->ny_glob;  // one generate call draws nall uniforms
     HX(h)->draw += (uint64_t)((n + per - 1) / per);
     return B200MC_OK;
 }
@@ -638,7 +675,7 @@ int b200mc_xy2d_set_random_spin(void* h)
     const int total = (int)m->ny * m->gpr;
     for (int c = 0; c < 2; ++c) {
         COUNT_LAUNCH();
-        xy_random_kernel<<<(total + 255) / 256, 256, 0, m->stream>>>(m->c[c], m->nxh, (int)m->ny, m->gpr, c, m->seed, m->draw);
+        xy_random_kernel<<<(total + 255) / 256, 256, 0, m->stream>>>(m->c[c], m->nxh, (int)m->ny, m->gpr, c, m->seed, m->draw, (int)m->yoff);
         CK(cudaGetLastError());
         { int rch = halo_rows(m, c); if (rch) return rch; }
     }
@@ -709,7 +746,7 @@ int prepare(XY* m, int kind, double target, double pct)
     double field_x = 1.0;
     for (int it = 0;; ++it) {
         if ((rc = measure(m))) return rc;
-        const double n = (double)(m->nx * m->ny);
+        const double n = (double)(m->nx * m->ny_glob);
         const double mx = m->obs[1] / n, my = m->obs[2] / n, mabs = hypot(mx, my);
         if (kind == PREP_FINITE) {
             if (fabs(mabs - target) / target < 1e-2) break;   // epsilon, :130
@@ -783,7 +820,7 @@ int b200mc_xy2d_set_angles(void* h, const float* in)
 }
 int64_t b200mc_xy2d_nx(void* h) { return h ? HX(h)->nx : -1; }
 int64_t b200mc_xy2d_ny(void* h) { return h ? HX(h)->ny : -1; }
-int64_t b200mc_xy2d_nall(void* h) { return h ? HX(h)->nx * HX(h)->ny : -1; }
+int64_t b200mc_xy2d_nall(void* h) { return h ? HX(h)->nx * HX(h)->ny_glob : -1; }   // (slab mode: ny() is the local row count, nall() the whole lattice)
 double b200mc_xy2d_kbt(void* h) { return h ? 1 / HX(h)->beta : 0.0; }
 double b200mc_xy2d_beta(void* h) { return h ? HX(h)->beta : 0.0; }
 int b200mc_xy2d_sync(void* h) { CHECK_X(h); CK(cudaStreamSynchronize(HX(h)->stream)); return B200MC_OK; }

@@ -45,6 +45,31 @@ class xy2d_gpu:
         _lib.check(f(C.byref(self._h), int(nx), int(ny), float(kbt), int(iseed)))
         return self
 
+    def init_distributed(self, nx, ny, kbt, iseed, group=None):
+        """slabs along y over the ranks of an initialised torch.distributed job (one process per GPU): this rank holds
+        ny / world rows; halo rows go between neighbouring ranks after every colour pass, E / Mx / My are all-reduced, and
+        every site draws the random numbers of the one-GPU run.  ny() is then the local row count, nall() the lattice."""
+        import torch.distributed as dist
+        from ._ising_base import unique_id
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        if self._h:
+            _lib.fn("b200mc_xy2d_destroy", C.c_int, P)(self._h)
+            self._h = C.c_void_p(None)
+        f = _lib.fn("b200mc_xy2d_create_slab", C.c_int, PP, i64, i64, f64, i32, i32, i32, C.c_char_p)
+        _lib.check(f(C.byref(self._h), int(nx), int(ny), float(kbt), int(iseed), int(rank), int(world), bytes(box[0])))
+        self._dist = (dist, group)
+        return self
+
+    def angles_all(self):
+        """slab mode: the angles of the whole lattice [ny_global][nx], gathered from the ranks' rows"""
+        dist, group = self._dist
+        parts = [None] * dist.get_world_size(group)
+        dist.all_gather_object(parts, self.angles(), group=group)
+        return np.concatenate(parts, axis=0)
+
     def skip_curand(self, n_skip): self._call("skip_curand", int(n_skip), argtypes=(i64,))
     def set_allup_spin(self): self._call("set_allup_spin")
     def set_random_spin(self): self._call("set_random_spin")

@@ -283,6 +283,15 @@ int b200mc_sixclock_sync(void* h);
  * nx must be a multiple of 8 and ny even in this build (the reference needs both even).
  * ------------------------------------------------------------------------ */
 int b200mc_xy2d_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed);  /* init, :61-78 */
+/* Slab of a lattice of ny_global rows split along y over nranks GPUs (one process per GPU): this rank holds
+ * ny_global / nranks rows (an even number).  After every colour pass the first / last row of the colour just written
+ * goes to the neighbouring ranks' halo rows (ncclSend/Recv); E, Mx, My are all-reduced; every site draws the random
+ * numbers it draws in the one-GPU run.  In slab mode ny() is the LOCAL row count, nall() the whole lattice, get_angles /
+ * get_spins return the local rows, and the correlation sums are unsupported.
+ * NOT VALIDATED on hardware yet for nranks > 1: returns B200MC_ERR_UNSUPPORTED unless the
+ * environment sets B200MC_XY_SLAB=1.  nranks == 1 is b200mc_xy2d_create. */
+int b200mc_xy2d_create_slab(void** h, int64_t nx, int64_t ny_global, double kbt, int32_t iseed, int32_t rank, int32_t nranks,
+                            const char* nccl_id /* 128 bytes from b200mc_dist_unique_id; NULL when nranks == 1 */);
 int b200mc_xy2d_destroy(void* h);
 int b200mc_xy2d_set_stream(void* h, void* cuda_stream);
 int b200mc_xy2d_skip_curand(void* h, int64_t n_skip);                 /* :79-84 */
