@@ -159,3 +159,39 @@ def test_clock_tableall_numpy_restatement(oracle):
             st = np.where(acc, new, st)
         assert np.array_equal(o.c.reshape(ny, nx), st), sweep
     assert abs(o.calc_magne() - np.cos(psi * st).sum() / (nx * ny)) < 1e-12
+
+
+@pytest.mark.parametrize("multi", [False, True])
+def test_clock_helical_numpy_restatement(oracle, multi):
+    """src/clock_gpu_m.f90:105-146,183-216 (clock_gpu_multi_m.f90:215-236 for the strict comparator) on the ring of
+    nall sites: ws(up, down, left, right, before, after) with up = s(i + nx), down = s(i - nx), left = s(i - 1),
+    right = s(i + 1); nxt = floor(p q); accept iff r <= ws (multi: r < ws)"""
+    nx, ny, q, kbt = 33, 32, 6, 0.8
+    n = nx * ny
+    o = oracle.clock_gpu().init(nx, ny, kbt, q, 5, 1 if multi else None)
+    a = 2 * (4 * math.atan(1.0)) / q
+    k = np.arange(q)
+    etab = -(_cos(a * (k[:, None, None] - k[None, None, :])) + _cos(a * (k[None, :, None] - k[None, None, :])))   # Etab(i, j, c), :115
+    I, J, K, L, CB, CA = np.meshgrid(k, k, k, k, k, k, indexing="ij")
+    de = (etab[I, J, CA] + etab[K, L, CA]) - (etab[I, J, CB] + etab[K, L, CB])                                   # :127-131
+    ws = np.where(de <= 0, 1.0, _exp(-(1 / kbt) * de))
+    assert np.array_equal(ws.ravel(order="F"), o.ws)
+    rng = np.random.default_rng(6)
+    u0 = 1.0 - rng.random(n)
+    o.set_random_spin(u0)
+    s = np.minimum(np.floor(u0 * q).astype(np.int64), q - 1)                                # :103 (u == 1 clamped, SURVEY Q4)
+    for sweep in range(5):
+        r, p = 1.0 - rng.random(n), 1.0 - rng.random(n)
+        o.update(randoms=r, next_states=p)
+        nxt = np.minimum(np.floor(p * q).astype(np.int64), q - 1)
+        for colour in (0, 1):                                                               # idx odd (i even) first
+            i = np.arange(colour, n, 2)
+            w = ws[s[(i + nx) % n], s[(i - nx) % n], s[(i - 1) % n], s[(i + 1) % n], s[i], nxt[i]]
+            acc = (r[i] < w) if multi else (r[i] <= w)
+            s[i] = np.where(acc, nxt[i], s[i])
+        got = o.spins()
+        got = got[0] if multi else got
+        assert np.array_equal(got[nx:nx + n], s), sweep
+    e = etab[s[(np.arange(n) - nx) % n], s[(np.arange(n) - 1) % n], s].sum()                # :258
+    eo = o.calc_energy_sum()
+    assert abs((eo[0] if multi else eo) - e) < 1e-9
