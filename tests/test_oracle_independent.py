@@ -195,3 +195,44 @@ def test_clock_helical_numpy_restatement(oracle, multi):
     e = etab[s[(np.arange(n) - nx) % n], s[(np.arange(n) - 1) % n], s].sum()                # :258
     eo = o.calc_energy_sum()
     assert abs((eo[0] if multi else eo) - e) < 1e-9
+
+
+def test_xy_helical_numpy_restatement(oracle):
+    """src/xy2d_gpu_m.f90:139-174,176-213,241-291 on the ring of nall sites: dE = -(cand - s) . (s(i-1) + s(i+1) +
+    s(i+nx) + s(i-nx)), accept iff r <= exp(-beta dE); over-relaxation s <- 2 (h^ . s) h^ - s WITHOUT renormalisation;
+    E = -sum s(i) . (s(i+1) + s(i+nx)), M = sum cos"""
+    nx, ny, kbt = 9, 8, 0.9
+    n = nx * ny
+    o = oracle.xy2d_helical_gpu().init(nx, ny, kbt, 1)
+    rng = np.random.default_rng(8)
+    th = 2 * np.pi * (1.0 - rng.random(n))
+    o.set_angles(th)
+    c, s = np.cos(th), np.sin(th)
+    i_all = np.arange(n)
+
+    def field(a, i):
+        return a[(i - 1) % n] + a[(i + 1) % n] + a[(i + nx) % n] + a[(i - nx) % n]          # :247, same order
+
+    for sweep in range(3):
+        r, cand = 1.0 - rng.random(n), 1.0 - rng.random(n)
+        o.update(r, cand)
+        cc, cs = np.cos(2 * np.pi * cand), np.sin(2 * np.pi * cand)
+        for colour in (0, 1):                                                               # offset 1: idx odd = i even
+            i = np.arange(colour, n, 2)
+            de = -((cc[i] - c[i]) * field(c, i) + (cs[i] - s[i]) * field(s, i))
+            acc = r[i] <= np.exp(-(1 / kbt) * de)
+            c[i], s[i] = np.where(acc, cc[i], c[i]), np.where(acc, cs[i], s[i])
+        sp = o.spins()
+        assert np.abs(sp[0, nx:nx + n] - c).max() < 1e-12 and np.abs(sp[1, nx:nx + n] - s).max() < 1e-12, sweep
+        o.update_over_relaxation(1)
+        for colour in (0, 1):
+            i = np.arange(colour, n, 2)
+            hx, hy = field(c, i), field(s, i)
+            inv = 1 / np.hypot(hx, hy)
+            hx, hy = hx * inv, hy * inv
+            d = 2 * (hx * c[i] + hy * s[i])
+            c[i], s[i] = d * hx - c[i], d * hy - s[i]
+        sp = o.spins()
+        assert np.abs(sp[0, nx:nx + n] - c).max() < 1e-12 and np.abs(sp[1, nx:nx + n] - s).max() < 1e-12
+        e = -(c * (c[(i_all + 1) % n] + c[(i_all + nx) % n])).sum() - (s * (s[(i_all + 1) % n] + s[(i_all + nx) % n])).sum()
+        assert abs(o.calc_energy_sum() - e) < 1e-9 and abs(o.calc_magne_sum() - c.sum()) < 1e-9
