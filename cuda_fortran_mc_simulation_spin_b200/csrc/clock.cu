@@ -379,7 +379,7 @@ int b200mc_clock_set_spins(void* h, const int32_t* in)
     Clock* m = HC(h);
     m->obs_valid = false;
     const int64_t per = m->st[0].g.N + 2 * m->st[0].g.P;
-    for (int j = 0; j < m->n_multi; ++j) { int rc = ring_import_i32(&m->st[j], in + (size_t)j * per, RING_MAP_IDENTITY, m->stream); if (rc) return rc; }
+    for (int j = 0; j < m->n_multi; ++j) { int rc = ring_import_i32(&m->st[j], in + (size_t)j * per, RING_MAP_IDENTITY, m->stream, 0, m->q); if (rc) return rc; }
     return B200MC_OK;
 }
 int b200mc_clock_get_ws(void* h, double* out)

@@ -332,7 +332,9 @@ int launch_pass(Ising* m, int colour, bool fuse)
         if (rc) return rc;
         return ring_halo(&m->st, colour, m->stream);
     }
-    const bool split = g.Lloc >= 4 * g.H && !(m->tune & 2);
+    // (decided from the SMALLEST slab of the job, L / nranks, so that every rank takes the same transport even when
+    // L % nranks != 0 makes the slabs differ by one vector)
+    const bool split = g.L / g.nranks >= 4 * g.H && !(m->tune & 2);
     if (!split && g.nranks == 1) m->st.p2p = false;
     if (!split) {
         rc = launch_range<NNB>(m, colour, 0, g.Lloc, true, fuse);

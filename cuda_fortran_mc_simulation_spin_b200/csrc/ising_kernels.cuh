@@ -315,7 +315,11 @@ __device__ __forceinline__ void ising_core(int v, uint4* po, uint4 o, const uint
     }
 }
 
-template <int NNB, int METHOD, bool PUSH, bool MEASURE, bool FULLWARP, bool COHERENT = false>
+// COHERENT: 0 = other colour through the read-only (nc) path; 1 = cooperative sweep kernel (L2 loads, wrapped positions
+// rebuilt from the owned sites); 2 = plain L2 loads -- the boundary tickets of a slab pass, whose halo vectors the
+// neighbouring GPUs store over NVLink while earlier blocks of this launch may already have pulled the same 128-byte
+// line through L1 (an acquire on the flags does not invalidate the nc path)
+template <int NNB, int METHOD, bool PUSH, bool MEASURE, bool FULLWARP, int COHERENT = 0>
 __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (&q)[NNB], uint32_t cx, uint32_t cz, uint32_t cw,
                                           const RingPassArgs& a, const IsingTab& tab, uint64_t pol, uint32_t qaddr,
                                           uint32_t cntaddr, bool is_b, uint32_t& accX, uint32_t& accM, uint32_t cy = 0u)
@@ -326,7 +330,8 @@ __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (
     // 512-byte load was tried: 4 SHFL + a one-lane load made the pass 20 % slower -- the MIO queue is the busiest unit)
 #pragma unroll
     for (int j = 0; j < NNB; ++j) {
-        if (COHERENT) {
+        if (COHERENT == 2) nb[j] = ld_other_coherent(q[j]);
+        else if (COHERENT == 1) {
             // cooperative sweep kernel (single GPU, p0 = 0), wrap_mode != 0: positions outside [0, min(ptail, L)) are rebuilt
             // from the owned sites instead of read from the halo, which is then only refreshed at the end of the launch
             const int pj = v + (int)a.off[j];
@@ -358,7 +363,7 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
 {
     static_assert(!PUSH || ORDERED, "the fused update + halo push kernel uses ticket scheduling");
     static_assert(CH % 32 == 0 && (CH == TK_CHUNK || !ORDERED), "tickets are TK_CHUNK vectors");
-    constexpr bool COH = CH != TK_CHUNK;   // 32-vector chunks = the cooperative multi-pass kernel: the other colour was written in this launch
+    constexpr int COH = CH != TK_CHUNK ? 1 : 0;   // 32-vector chunks = the cooperative multi-pass kernel: the other colour was written in this launch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(&tq[warp][0][0]);
     uint32_t cntaddr = (uint32_t)__cvta_generic_to_shared(&tq_cnt[warp]);
@@ -471,7 +476,7 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
                     const uint4* qu[NNB];
 #pragma unroll
                     for (int j = 0; j < NNB; ++j) qu[j] = q[j] + 32 * u;
-                    ising_vec<NNB, METHOD, PUSH, MEASURE, false, COH>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
+                    ising_vec<NNB, METHOD, PUSH, MEASURE, false, (PUSH ? 2 : COH)>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
                                                                  cntaddr, is_b, accX, accM, rep);
                 }
                 __syncwarp();

@@ -91,6 +91,17 @@ int ring_fill(RingStore* s, uint8_t value, cudaStream_t st)
     const size_t nv = (size_t)s->rstride * (size_t)s->n_rep;
     CK(cudaMemsetAsync(s->vec[0], value, nv * sizeof(uint4), st));
     CK(cudaMemsetAsync(s->vec[1], value, nv * sizeof(uint4), st));
+    // Direct transport between ranks: the memset covers the halo vectors, which the neighbours store into from their next
+    // colour pass on.  A rank that finishes its fill early must not push before every rank has finished filling (its
+    // push would be overwritten by the slower neighbour's memset, whose flag already shows the new sequence number):
+    // a one-word all-reduce on the stream is the barrier -- it completes on a rank only after every rank's stream has
+    // reached it, i.e. after every memset.  (set_random_spin / set_spins refresh their halos through ncclSend/Recv,
+    // which orders the ranks pairwise.)
+    if (s->p2p && s->g.nranks > 1 && s->comm && s->flags) {
+        unsigned long long* scratch = reinterpret_cast<unsigned long long*>(s->flags + 56);
+        int rc = dist_allreduce_u64(s->comm, scratch, 1, st);
+        if (rc) return rc;
+    }
     return B200MC_OK;
 }
 
@@ -410,10 +421,22 @@ __global__ void ring_import_kernel(uint8_t* a, uint8_t* b, int64_t N, int64_t L,
     ((i & 1) ? b : a)[(p - p0 + H) * 16 + lane] = (uint8_t)v;
 }
 
-int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st, int rep)
+int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st, int rep, int32_t n_states)
 {
     const RingGeom& g = s->g;
     if (rep < 0 || rep >= s->n_rep) ARG_FAIL("sample %d outside the batch of %d", rep, s->n_rep);
+    // the byte-parallel kernels assume every stored value is a valid state (carries would cross lanes, table indices
+    // would leave the table): reject anything else here.  Halo cells of the host array are ignored (rebuilt below).
+    {
+        const int32_t* v = host + g.P;
+        int64_t bad = -1;
+        if (map == RING_MAP_PM1) { for (int64_t i = 0; i < g.N; ++i) if (v[i] != 1 && v[i] != -1) { bad = i; break; } }
+        else { for (int64_t i = 0; i < g.N; ++i) if ((uint32_t)v[i] >= (uint32_t)n_states) { bad = i; break; } }
+        if (bad >= 0) {
+            if (map == RING_MAP_PM1) ARG_FAIL("set_spins: site %lld holds %d (allowed: -1, +1)", (long long)(bad + 1), (int)v[bad]);
+            ARG_FAIL("set_spins: site %lld holds %d (allowed: 0 .. %d)", (long long)(bad + 1), (int)v[bad], (int)n_states - 1);
+        }
+    }
     uint4* const v0 = s->vec[0] + (size_t)rep * s->rstride;
     uint4* const v1 = s->vec[1] + (size_t)rep * s->rstride;
     int rcq = ring_p2p_quiesce(s, st);

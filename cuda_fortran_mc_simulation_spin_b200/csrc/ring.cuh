@@ -49,7 +49,7 @@ struct RingStore {
     // direct NVLink transport (slab mode): the neighbours' colour arrays and flag words mapped with
     // cudaIpcOpenMemHandle; the boundary launch of a colour pass stores into them (ising_kernels.cuh, PUSH)
     bool p2p;
-    unsigned int* flags;         // mine: [0] pushes received from rank-1, [16] from rank+1, [32] CTA counter
+    unsigned int* flags;         // mine: [0] pushes received from rank-1, [16] from rank+1, [32] CTA counter, [48] debug wait ns (u64), [56] barrier scratch (u64)
     uint4* peer_vec[2][2];       // [0 = rank-1, 1 = rank+1][colour]
     unsigned int* peer_flags[2];
     void* peer_maps[6];          // what cudaIpcCloseMemHandle must be called on
@@ -166,7 +166,8 @@ void ring_free(RingStore* s);
 int ring_fill(RingStore* s, uint8_t value, cudaStream_t st);
 int ring_halo(RingStore* s, int colour, cudaStream_t st);
 // host int32 arrays in the reference layout spins(1-P : N+P)
-int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st, int rep = 0);
+// n_states: valid stored values are 0 .. n_states-1 (RING_MAP_PM1: the host values must be -1 / +1); anything else is B200MC_ERR_ARG
+int ring_import_i32(RingStore* s, const int32_t* host, RingValueMap map, cudaStream_t st, int rep = 0, int32_t n_states = 2);
 int ring_export_i32(RingStore* s, int32_t* host, RingValueMap map, cudaStream_t st, int rep = 0);
 
 // direct transport set-up: export my handles, map the two neighbours' (prev == next when nranks == 2)

@@ -238,6 +238,38 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
     }
 }
 
+// Reference-stream Metropolis pass: the accept uniforms r and the candidate uniforms c come from device arrays in the
+// reference's own layout (randoms_(nx, ny), candidates_(nx, ny), column-major: element (x, y) at (y-1) nx + (x-1);
+// src/xy2d_periodic_gpu_m.f90:355-356, read at :382-384), e.g. filled by cuRAND like the reference does.  Same fp32
+// arithmetic as xy_strip_row (cos / sin by sincos_unit, same summation order), one thread per site.  Not the fast path.
+__global__ void __launch_bounds__(256)
+xy_pass_randoms_kernel(const __grid_constant__ XYArgs a, const double* __restrict__ randoms, const double* __restrict__ cands, int nx)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)a.ny * a.nxh) return;
+    const int y = (int)(i / a.nxh), xi = (int)(i - (long long)y * a.nxh);
+    const int P = (y + a.colour) & 1;            // lattice x of this site: 2 xi + P
+    const int x0 = 2 * xi + P;
+    const int xl = P ? xi : (xi == 0 ? a.nxh - 1 : xi - 1), xr = P ? (xi + 1 == a.nxh ? 0 : xi + 1) : xi;
+    const int yu = (y + 1 >= a.ny && !a.halo) ? 0 : y + 1, yd = (y == 0 && !a.halo) ? a.ny - 1 : y - 1;
+    float sr, cr, sl, cl, su, cu, sd, cd;
+    sincos_unit(a.oth[(ptrdiff_t)y * a.nxh + xr], sr, cr);
+    sincos_unit(a.oth[(ptrdiff_t)y * a.nxh + xl], sl, cl);
+    sincos_unit(a.oth[(ptrdiff_t)yu * a.nxh + xi], su, cu);
+    sincos_unit(a.oth[(ptrdiff_t)yd * a.nxh + xi], sd, cd);
+    const float hx = cr + cl + cu + cd, hy = sr + sl + su + sd;
+    const size_t ridx = (size_t)(y + a.yoff) * (size_t)nx + (size_t)x0;
+    const float ct = (float)cands[ridx];
+    const float ov = a.own[(size_t)y * a.nxh + xi];
+    float cs, cc, ss, sc;
+    sincos_unit(ct, cs, cc);
+    sincos_unit(ov, ss, sc);
+    const float de = (cc - sc) * hx + (cs - ss) * hy;   // -dE
+    float w;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(de * (a.beta * 1.4426950408889634f)));
+    if (!(randoms[ridx] > (double)w)) a.own[(size_t)y * a.nxh + xi] = ct;   // (0, 1] turns, like the strip kernel
+}
+
 // metropolis_by_field_sub, :198-216 (initial-state preparation): every site, no coupling.
 // candidate (cos 2 pi c, sin 2 pi c); dE = -(h . (cand - s)); accepted iff r <= 1 - exp(dE)
 // (the reference's test is `randoms > 1 - exp(delta_energy) -> return`, :213).
@@ -485,6 +517,34 @@ int sweep(XY* m)
     return B200MC_OK;
 }
 
+// One Metropolis MCS with the caller's uniforms instead of the built-in generator (parity / cuRAND-stream mode):
+// randoms, candidates = host arrays of nall real64 in the reference's (nx, ny) order, :355-356
+int sweep_with_randoms(XY* m, const double* randoms, const double* cands)
+{
+    if (!randoms || !cands) ARG_FAIL("null randoms / candidates");
+    if (m->nranks > 1) { snprintf(g_b200mc_err, sizeof(g_b200mc_err), "xy2d update_with_randoms: not available in slab mode"); return B200MC_ERR_UNSUPPORTED; }
+    const size_t n = (size_t)m->nx * m->ny;
+    double* d = nullptr;
+    CK(cudaMalloc(&d, 2 * n * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d, randoms, n * sizeof(double), cudaMemcpyHostToDevice, m->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, cands, n * sizeof(double), cudaMemcpyHostToDevice, m->stream);
+    if (e != cudaSuccess) { cudaFree(d); CK(e); }
+    m->obs_valid = false; m->fused_pending = false;
+    const long long total = (long long)m->ny * m->nxh;
+    int rc = B200MC_OK;
+    for (int colour = 0; colour < 2 && !rc; ++colour) {
+        XYArgs a;
+        fill_args(m, colour, &a);
+        COUNT_LAUNCH();
+        xy_pass_randoms_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(a, d, d + n, (int)m->nx);
+        if (cudaGetLastError() != cudaSuccess) { rc = B200MC_ERR_CUDA; snprintf(g_b200mc_err, sizeof(g_b200mc_err), "xy_pass_randoms_kernel launch failed"); break; }
+        rc = halo_rows(m, colour);
+    }
+    cudaStreamSynchronize(m->stream);
+    cudaFree(d);
+    return rc;
+}
+
 int over_relax(XY* m, int n_steps)
 {
     if (n_steps <= 0) return B200MC_OK;
@@ -685,6 +745,7 @@ int b200mc_xy2d_set_random_spin(void* h)
 int b200mc_xy2d_set_kbt(void* h, double kbt) { CHECK_X(h); if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0"); HX(h)->beta = 1 / kbt; return B200MC_OK; }
 int b200mc_xy2d_set_beta(void* h, double beta) { CHECK_X(h); HX(h)->beta = beta; return B200MC_OK; }
 int b200mc_xy2d_update(void* h) { CHECK_X(h); return sweep(HX(h)); }
+int b200mc_xy2d_update_with_randoms(void* h, const double* randoms, const double* candidates) { CHECK_X(h); return sweep_with_randoms(HX(h), randoms, candidates); }
 int b200mc_xy2d_update_n(void* h, int32_t n) { CHECK_X(h); for (int i = 0; i < n; ++i) { int rc = sweep(HX(h)); if (rc) return rc; } return B200MC_OK; }
 int b200mc_xy2d_update_over_relaxation(void* h, int32_t n_steps) { CHECK_X(h); return over_relax(HX(h), n_steps); }
 int b200mc_xy2d_calc_energy_sum(void* h, double* e) { CHECK_X(h); int rc = measure(HX(h)); if (rc) return rc; *e = HX(h)->obs[0]; return B200MC_OK; }

@@ -81,6 +81,15 @@ class xy2d_gpu:
     def set_beta(self, beta): self._call("set_beta", float(beta), argtypes=(f64,))
     def update(self): self._call("update")
     def update_n(self, n): self._call("update_n", int(n), argtypes=(i32,))
+
+    def update_with_randoms(self, randoms, candidates):
+        """one Metropolis MCS on the caller's uniforms: randoms(nx, ny), candidates(nx, ny) as the reference fills them (:355-356)"""
+        r = np.ascontiguousarray(randoms, dtype=np.float64)
+        c = np.ascontiguousarray(candidates, dtype=np.float64)
+        if r.size != self.nall() or c.size != self.nall():
+            raise ValueError("randoms / candidates must hold nall uniforms each")
+        self._call("update_with_randoms", r.ctypes.data_as(P), c.ctypes.data_as(P), argtypes=(P, P))
+
     def update_over_relaxation(self, n_steps): self._call("update_over_relaxation", int(n_steps), argtypes=(i32,))
     def set_initial_magne_autocorrelation_state(self): self._call("set_initial_magne_autocorrelation_state")
     def rotate_summation_magne_toward_xaxis(self): self._call("rotate_summation_magne_toward_xaxis", 0, argtypes=(i32,))

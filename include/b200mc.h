@@ -301,6 +301,9 @@ int b200mc_xy2d_set_kbt(void* h, double kbt);                         /* :329-33
 int b200mc_xy2d_set_beta(void* h, double beta);                       /* :335-339 */
 int b200mc_xy2d_update(void* h);                                      /* Metropolis MCS, :353-397 */
 int b200mc_xy2d_update_n(void* h, int32_t n_sweeps);
+/* one Metropolis MCS reading the accept uniforms randoms(nx, ny) and the candidate uniforms candidates(nx, ny)
+ * (the two arrays the reference fills with curandGenerate at :355-356 and reads at :382-384) from host arrays */
+int b200mc_xy2d_update_with_randoms(void* h, const double* randoms, const double* candidates);
 int b200mc_xy2d_update_over_relaxation(void* h, int32_t n_steps);     /* :400-439 */
 int b200mc_xy2d_calc_energy_sum(void* h, double* e);                  /* :469-472,496-508 */
 int b200mc_xy2d_calc_magne_sum(void* h, double* mx);                  /* :474-477,510-521 */

@@ -1,8 +1,20 @@
 """GPU parity: XY periodic (Metropolis + over-relaxation) vs the real64 CPU oracle.
 
-Bar (BASELINE north_star): energy and magnetisation within 1e-5 RELATIVE TOLERANCE, per sweep from
-identical input state and identical uniforms (the GPU keeps fp32 angles and fp32 SFU math; long
-trajectories are chaotic, so the state is re-synchronised to the GPU's after every sweep)."""
+Bar (BASELINE north_star): energy and magnetisation within 1e-5 RELATIVE TOLERANCE, per sweep from identical input
+state and identical uniforms (the GPU keeps fp32 angles and fp32 SFU math; long trajectories are chaotic, so the
+oracle's state is re-synchronised to the GPU's before every sweep).
+
+What "relative" is measured against, written out (`check_observables`):
+  * RTOL * max(|reference value|, sqrt(N)) -- relative to the observable itself; sqrt(N) is the scale of the sums of a
+    disordered lattice (|M| ~ sqrt(N), |E| ~ sqrt(2N)), the floor that keeps the test meaningful when a sum happens to
+    pass through zero;
+  * + the COUNTED borderline sites: sites whose angle after the sweep differs from the oracle's by more than 1e-5
+    turns -- an accept test r <= exp(-beta dE) decided the other way because fp32 ex2.approx and real64 exp differ in the
+    7th digit (difference > 1e-3 turns; their number is asserted to be <= max(2, FLIP_FRAC * N)), or a reflection about
+    a nearly vanishing local field.  Such a site, displaced by |ds| = min(2, 2 pi d), moves M by at most |ds| and E by at
+    most 4 |ds|: the tolerance grows by exactly that measured displacement, not by a blanket allowance;
+  * + 2^-24 * N: the systematic part of evaluating N cosines / sines in fp32 (half an ulp each).
+"""
 import math
 
 import numpy as np
@@ -10,10 +22,44 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
+FLIP_FRAC = 2e-5
 
 
-def _sync_oracle(o, g):
+def sync_oracle(o, g):
     o.set_angles(2 * math.pi * g.angles().astype(np.float64))
+
+
+_sync_oracle = sync_oracle
+
+
+def site_differences(g, o):
+    """per-site |angle(GPU) - angle(oracle)| in turns, on the circle"""
+    go = g.angles().astype(np.float64)
+    oo = np.arctan2(o.sp[1, 1:-1, 1:-1], o.sp[0, 1:-1, 1:-1]) / (2 * math.pi)
+    return np.abs(((go - oo + 0.5) % 1.0) - 0.5)
+
+
+def borderline(d, n):
+    """(n_flip, moved): sites whose accept decision went the other way (angle difference > 1e-3 turns; their number is
+    bounded), and the total spin displacement sum_i min(2, 2 pi d_i) of all sites that differ by more than 1e-5 turns
+    (decision flips, plus reflections about a nearly vanishing local field, whose axis atan2(h) is ill-conditioned)"""
+    n_flip = int((d > 1e-3).sum())
+    assert n_flip <= max(2, FLIP_FRAC * n), n_flip
+    big = d[d > 1e-5]
+    assert big.size <= max(4, 1e-4 * n), big.size
+    return n_flip, float(np.minimum(2.0, 2 * math.pi * big).sum())
+
+
+def check_observables(g, o, n, what=""):
+    """E, Mx, My of the GPU state against the oracle's within the north-star tolerance (see the module docstring):
+    a site displaced by |ds| moves M by at most |ds| and E by at most 4 |ds| (four bonds)"""
+    n_flip, moved = borderline(site_differences(g, o), n)
+    e, mx, my = g.measure()
+    ref = (o.calc_energy_sum(), o.calc_magne_sum(), o.calc_magne_y_sum())
+    for name, val, r, per in (("E", e, ref[0], 4.0), ("Mx", mx, ref[1], 1.0), ("My", my, ref[2], 1.0)):
+        tol = RTOL * max(abs(r), math.sqrt(n)) + per * moved + 2.0 ** -24 * n
+        assert abs(val - r) <= tol, (what, name, val, r, tol, n_flip, moved)
+    return n_flip
 
 
 def _close(a, b, scale):
@@ -44,19 +90,11 @@ def test_xy_metropolis_per_sweep(oracle, shape, kbt, row_mode):
     assert np.allclose(g.angles(), u, atol=2 ** -24)
     for sweep in range(5):
         _sync_oracle(o, g)
-        e0, mx0, my0 = g.measure()
-        assert _close(e0, o.calc_energy_sum(), n) and _close(mx0, o.calc_magne_sum(), n) and _close(my0, o.calc_magne_y_sum(), n)
+        check_observables(g, o, n, ("measure", sweep))          # same state: no decisions involved
         r, c = oracle.xy_uniforms(42, 1 + sweep, nx, ny)
         g.update()
         o.update(r, c)
-        e, mx, my = g.measure()
-        assert _close(e, o.calc_energy_sum(), max(abs(o.calc_energy_sum()), 0.05 * n)), (e, o.calc_energy_sum())
-        assert _close(mx, o.calc_magne_sum(), n) and _close(my, o.calc_magne_y_sum(), n)
-        # site-level: all but a handful of borderline accept decisions agree
-        go = g.angles().astype(np.float64)
-        oo = np.arctan2(o.sp[1, 1:-1, 1:-1], o.sp[0, 1:-1, 1:-1]) / (2 * math.pi)
-        d = np.abs(((go - oo + 0.5) % 1.0) - 0.5)
-        assert (d > 1e-5).mean() < 1e-4
+        check_observables(g, o, n, ("metropolis", sweep))
 
 
 @pytest.mark.parametrize("shape", [(16, 8), (128, 64), (1024, 512)])
@@ -73,13 +111,10 @@ def test_xy_over_relaxation(oracle, shape, row_mode):
         e_before = g.calc_energy_sum()
         g.update_over_relaxation(1)
         o.update_over_relaxation(1)
-        e, mx, my = g.measure()
-        assert abs(e - e_before) / n < 1e-5         # microcanonical: energy conserved
-        assert _close(e, o.calc_energy_sum(), max(abs(o.calc_energy_sum()), 0.05 * n))
-        assert _close(mx, o.calc_magne_sum(), n) and _close(my, o.calc_magne_y_sum(), n)
-        go = g.angles().astype(np.float64)
-        oo = np.arctan2(o.sp[1, 1:-1, 1:-1], o.sp[0, 1:-1, 1:-1]) / (2 * math.pi)
-        d = np.abs(((go - oo + 0.5) % 1.0) - 0.5)
+        e = g.calc_energy_sum()
+        assert abs(e - e_before) <= RTOL * max(abs(e_before), math.sqrt(n)) + 2.0 ** -24 * n     # microcanonical: energy conserved
+        check_observables(g, o, n, ("over-relaxation", it))
+        d = site_differences(g, o)
         # the reflection axis atan2(h) is ill-conditioned where |h| is tiny: angle error ~ 1e-7 / |h|
         assert np.quantile(d, 0.9999) < 2e-5 and d.max() < 1e-2
 
@@ -142,6 +177,36 @@ def test_xy_full_size_properties():
     assert -2.0 * n < e1 < 0
 
 
+def test_xy_full_size_against_oracle(oracle):
+    """BASELINE config 3 itself (16384 x 16384, kbt 0.89, from disorder): one Metropolis sweep and one over-relaxation
+    step compared with the real64 oracle at full size, same tolerance as the small lattices.
+    Host memory: ~4.3 GB oracle spins + 2 x 2.1 GB uniforms + a few 2.1 GB temporaries."""
+    import os
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 1 << 40
+    if avail < 40 * (1 << 30):
+        pytest.skip("needs ~40 GB of free host memory")
+    from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
+    nx = ny = 16384
+    n = nx * ny
+    g = xm.xy2d_gpu().init(nx, ny, 0.89, 42)
+    o = oracle.xy2d_gpu().init(nx, ny, 0.89, 42)
+    o.sp0 = None                                     # (the autocorrelation snapshot is not needed: 4.3 GB)
+    g.set_random_spin()
+    sync_oracle(o, g)
+    r, c = oracle.xy_uniforms(42, 1, nx, ny)
+    g.update()
+    o.update(r, c)
+    del r, c
+    check_observables(g, o, n, "C3 metropolis")
+    sync_oracle(o, g)
+    g.update_over_relaxation(1)
+    o.update_over_relaxation(1)
+    check_observables(g, o, n, "C3 over-relaxation")
+
+
 def test_xy_metropolis_by_field_per_application(oracle, row_mode):
     """metropolis_by_field_sub (src/xy2d_periodic_gpu_m.f90:198-216): accepted iff r <= 1 - exp(dE)"""
     from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
@@ -155,12 +220,12 @@ def test_xy_metropolis_by_field_per_application(oracle, row_mode):
         r, c = oracle.xy_uniforms(13, 1 + it, nx, ny)
         g.metropolis_by_field(hx, hy)
         o.metropolis_by_field(r, c, hx, hy)
+        # (E is not compared: metropolis_by_field_sub does not refresh the reference's halo frame, so the oracle's
+        # energy of this intermediate state reads stale halo cells; the magnetisation sums and the sites are)
+        n_flip, moved = borderline(site_differences(g, o), n)
         _, mx, my = g.measure()
-        assert _close(mx, o.calc_magne_sum(), n) and _close(my, o.calc_magne_y_sum(), n)
-        go = g.angles().astype(np.float64)
-        oo = np.arctan2(o.sp[1, 1:-1, 1:-1], o.sp[0, 1:-1, 1:-1]) / (2 * math.pi)
-        d = np.abs(((go - oo + 0.5) % 1.0) - 0.5)
-        assert (d > 1e-5).mean() < 1e-4
+        for val, r in ((mx, o.calc_magne_sum()), (my, o.calc_magne_y_sum())):
+            assert abs(val - r) <= RTOL * max(abs(r), math.sqrt(n)) + moved + 2.0 ** -24 * n, (it, val, r, n_flip, moved)
 
 
 def test_xy_initial_state_preparation():
