@@ -46,7 +46,9 @@ def borderline(d, n):
     n_flip = int((d > 1e-3).sum())
     assert n_flip <= max(2, FLIP_FRAC * n), n_flip
     big = d[d > 1e-5]
-    assert big.size <= max(4, 1e-4 * n), big.size
+    # (over-relaxation one sweep after disorder: |h| < 0.01 -- where 1e-7 / |h| exceeds 1e-5 turns -- at 2e-4 of the sites,
+    # measured at 16384^2; each of them enters the tolerance with its own measured displacement)
+    assert big.size <= max(4, 1e-3 * n), big.size
     return n_flip, float(np.minimum(2.0, 2 * math.pi * big).sum())
 
 
