@@ -273,7 +273,7 @@ def bench_other_configs(T: Timer, K: int, peak: float, world: int, rank: int):
         ms = statistics.median(blocks)
         v = sites_per_step * k / (ms * 1e6)
         e = {"workload": workload, "value": v, "unit": UNIT, "steps": k, "blocks": len(blocks), "ms_per_step": ms / k,
-             "ms_per_step_min": min(blocks) / k, "roofline": _roof(v, bpf, peak, basis)}
+             "ms_per_step_min": min(blocks) / k, "roofline": _roof(v / world, bpf, peak, basis)}   # (per GPU)
         if extra:
             e.update(extra)
         return e

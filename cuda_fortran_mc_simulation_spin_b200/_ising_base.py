@@ -102,6 +102,17 @@ class _IsingBase:
             raise _lib.B200MCError("CUDA IPC mapping of the neighbour slabs failed on some rank; "
                                    "rerun with B200MC_SLAB_TRANSPORT=nccl")
         self._p2p = True
+        # observables: every rank's mailbox mapped on every rank (all or none, like the slabs)
+        self._sums_p2p = False
+        if nranks <= 16:
+            blob = b"".join(h for _, h in allh)
+            rc = self._f("p2p_connect_sums", C.c_int, P, C.c_char_p)(self._h, blob)
+            oks = [None] * nranks
+            dist.all_gather_object(oks, rc == 0, group=group)
+            if not all(oks):
+                raise _lib.B200MCError("CUDA IPC mapping of the ranks' flag buffers failed on some rank; "
+                                       "rerun with B200MC_SLAB_TRANSPORT=nccl")
+            self._sums_p2p = True
 
     def rank_info(self):
         r, n = C.c_int32(0), C.c_int32(1)

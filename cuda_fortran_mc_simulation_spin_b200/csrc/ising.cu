@@ -516,12 +516,21 @@ int measure(Ising* m, int64_t* e, int64_t* mag)
     }
     m->fused_pending = false;  // the all-reduce below turns d_acc into global sums; they are cached in obs_*
     m->want_fused = true;
+    bool exchanged = false;
     if (g.nranks > 1) {  // every rank gets the global sums (allreduce of {X, sum s})
-        int rc = dist_allreduce_u64(m->st.comm, m->d_acc, 2, m->stream);
-        if (rc) return rc;
+        if (m->st.sums_p2p && !(m->tune & 8192)) {
+            // direct transport: partial sums stored into every rank's mailbox over NVLink and added up by a one-warp
+            // kernel that also writes the totals to pinned host memory -- no collective, no copy (B200MC_TUNE bit 13: NCCL)
+            int rc = ring_sum_exchange(&m->st, m->d_acc, 2, m->h_acc, m->stream);
+            if (rc) return rc;
+            exchanged = true;
+        } else {
+            int rc = dist_allreduce_u64(m->st.comm, m->d_acc, 2, m->stream);
+            if (rc) return rc;
+        }
     }
     unsigned long long* acc = m->h_acc;
-    if (!direct) CK(cudaMemcpyAsync(acc, m->d_acc, 2 * sizeof(unsigned long long) * m->n_multi, cudaMemcpyDeviceToHost, m->stream));
+    if (!direct && !exchanged) CK(cudaMemcpyAsync(acc, m->d_acc, 2 * sizeof(unsigned long long) * m->n_multi, cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
     m->obs_ev.resize(m->n_multi); m->obs_mv.resize(m->n_multi);
     for (int j = 0; j < m->n_multi; ++j) {
@@ -910,6 +919,8 @@ int b200mc_ising3d_p2p_handles(void* h, char out[192]) { CHECK_H(h, 3); return r
 int b200mc_ising2d_p2p_handles(void* h, char out[192]) { CHECK_H(h, 2); return ring_p2p_export(&H(h)->st, out); }
 int b200mc_ising3d_p2p_connect(void* h, const char prev[192], const char next[192]) { CHECK_H(h, 3); return ring_p2p_connect(&H(h)->st, prev, next); }
 int b200mc_ising2d_p2p_connect(void* h, const char prev[192], const char next[192]) { CHECK_H(h, 2); return ring_p2p_connect(&H(h)->st, prev, next); }
+int b200mc_ising3d_p2p_connect_sums(void* h, const char* handles) { CHECK_H(h, 3); return ring_p2p_connect_sums(&H(h)->st, handles); }
+int b200mc_ising2d_p2p_connect_sums(void* h, const char* handles) { CHECK_H(h, 2); return ring_p2p_connect_sums(&H(h)->st, handles); }
 int b200mc_ising3d_rank_info(void* h, int32_t* rank, int32_t* nranks) { CHECK_H(h, 3); *rank = H(h)->st.g.rank; *nranks = H(h)->st.g.nranks; return B200MC_OK; }
 int b200mc_ising2d_rank_info(void* h, int32_t* rank, int32_t* nranks) { CHECK_H(h, 2); *rank = H(h)->st.g.rank; *nranks = H(h)->st.g.nranks; return B200MC_OK; }
 int64_t b200mc_ising3d_nz(void* h) { return h ? H(h)->nz : -1; }

@@ -64,6 +64,7 @@ int ring_alloc(RingStore* s)
     s->vec[0] = s->vec[1] = nullptr;
     s->stage = nullptr;
     s->p2p = false; s->flags = nullptr; s->n_peer_maps = 0; s->push_seq = 0; s->Lloc_prev = 0;
+    s->n_sum_maps = 0; s->sums_p2p = false; s->sum_seq = 0;
     CK(cudaMalloc(&s->vec[0], nv * sizeof(uint4)));
     CK(cudaMalloc(&s->vec[1], nv * sizeof(uint4)));
     s->stage_elems = 1 << 24;
@@ -271,8 +272,8 @@ int ring_p2p_export(RingStore* s, char out[RING_IPC_BYTES])
 {
     static_assert(sizeof(cudaIpcMemHandle_t) * 3 == RING_IPC_BYTES, "cudaIpcMemHandle_t size");
     if (!s->flags) {
-        CK(cudaMalloc(&s->flags, 64 * sizeof(unsigned int)));
-        CK(cudaMemset(s->flags, 0, 64 * sizeof(unsigned int)));
+        CK(cudaMalloc(&s->flags, RING_FLAG_WORDS * sizeof(unsigned int)));
+        CK(cudaMemset(s->flags, 0, RING_FLAG_WORDS * sizeof(unsigned int)));
     }
     cudaIpcMemHandle_t h[3];
     CK(cudaIpcGetMemHandle(&h[0], s->vec[0]));
@@ -327,8 +328,8 @@ int ring_p2p_connect_self(RingStore* s)
     if (g.nranks != 1) ARG_FAIL("connect_self: slab handle");
     if (g.Nc % 16) ARG_FAIL("connect_self: sites per colour must be a multiple of 16");
     if (!s->flags) {
-        CK(cudaMalloc(&s->flags, 64 * sizeof(unsigned int)));
-        CK(cudaMemset(s->flags, 0, 64 * sizeof(unsigned int)));
+        CK(cudaMalloc(&s->flags, RING_FLAG_WORDS * sizeof(unsigned int)));
+        CK(cudaMemset(s->flags, 0, RING_FLAG_WORDS * sizeof(unsigned int)));
     }
     for (int side = 0; side < 2; ++side) {
         s->peer_vec[side][0] = s->vec[0];
@@ -344,7 +345,81 @@ void ring_p2p_close(RingStore* s)
 {
     for (int i = 0; i < s->n_peer_maps; ++i) cudaIpcCloseMemHandle(s->peer_maps[i]);
     s->n_peer_maps = 0;
+    for (int i = 0; i < s->n_sum_maps; ++i) cudaIpcCloseMemHandle(s->sum_maps[i]);
+    s->n_sum_maps = 0;
+    s->sums_p2p = false;
     s->p2p = false;
+}
+
+// ---- observable sums across the ranks over peer memory (no collective, no host round trip) --------------------
+int ring_p2p_connect_sums(RingStore* s, const char* handles)
+{
+    const RingGeom& g = s->g;
+    if (!s->p2p || g.nranks < 2) ARG_FAIL("p2p_connect_sums: call p2p_connect first");
+    if (g.nranks > RING_MAX_SUM_RANKS) { snprintf(g_b200mc_err, sizeof(g_b200mc_err), "p2p_connect_sums: more than %d ranks", RING_MAX_SUM_RANKS); return B200MC_ERR_UNSUPPORTED; }
+    const int prev = (g.rank + g.nranks - 1) % g.nranks, next = (g.rank + 1) % g.nranks;
+    for (int r = 0; r < g.nranks; ++r) {
+        if (r == g.rank) { s->all_flags[r] = s->flags; continue; }
+        if (r == prev) { s->all_flags[r] = s->peer_flags[0]; continue; }   // already mapped by ring_p2p_connect
+        if (r == next) { s->all_flags[r] = s->peer_flags[1]; continue; }
+        cudaIpcMemHandle_t h[3];
+        memcpy(h, handles + (size_t)r * RING_IPC_BYTES, RING_IPC_BYTES);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h[2], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaIpcOpenMemHandle (flags of rank %d) failed: %s", r, cudaGetErrorString(e));
+            cudaGetLastError();
+            return B200MC_ERR_UNSUPPORTED;
+        }
+        s->sum_maps[s->n_sum_maps++] = ptr;
+        s->all_flags[r] = (unsigned int*)ptr;
+    }
+    s->sums_p2p = true;
+    return B200MC_OK;
+}
+
+struct RingSumArgs {
+    unsigned int* box[RING_MAX_SUM_RANKS];   // every rank's flag buffer
+    int rank, nranks, n;
+    unsigned int seq;                        // this exchange (1, 2, ...): mailbox parity seq & 1
+};
+
+// One warp.  Lane r stores this rank's partial sums into rank r's mailbox entry [parity][my rank] (values, fence, then
+// the sequence number with release semantics), then waits for entry [parity][r] of its OWN mailbox and reads rank r's
+// partial sums; a warp reduction gives the totals.  Two parities suffice: a rank can only start exchange k + 2 after
+// every rank has contributed to k + 1, i.e. after every rank has finished reading k.
+__global__ void ring_sum_exchange_kernel(const __grid_constant__ RingSumArgs a, unsigned long long* buf, unsigned long long* host_out)
+{
+    const int lane = threadIdx.x;
+    unsigned long long v[3] = {0ull, 0ull, 0ull};
+    if (lane < a.nranks) {
+        unsigned int* dst = a.box[lane] + RING_SUM_BASE + ((a.seq & 1u) * RING_MAX_SUM_RANKS + a.rank) * RING_SUM_SLOT;
+        for (int j = 0; j < a.n; ++j) reinterpret_cast<volatile unsigned long long*>(dst)[j] = __ldcg(buf + j);
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst + 6), "r"(a.seq) : "memory");
+        const unsigned int* src = a.box[a.rank] + RING_SUM_BASE + ((a.seq & 1u) * RING_MAX_SUM_RANKS + lane) * RING_SUM_SLOT;
+        unsigned int got;
+        do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(src + 6) : "memory"); } while (got != a.seq);
+        for (int j = 0; j < a.n; ++j) v[j] = reinterpret_cast<const volatile unsigned long long*>(src)[j];
+    }
+    for (int j = 0; j < 3; ++j)
+        for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_down_sync(0xffffffffu, v[j], o);
+    if (lane == 0)
+        for (int j = 0; j < a.n; ++j) { buf[j] = v[j]; if (host_out) host_out[j] = v[j]; }
+}
+
+int ring_sum_exchange(RingStore* s, unsigned long long* buf, int n, unsigned long long* host_out, cudaStream_t st)
+{
+    if (!s->sums_p2p) ARG_FAIL("sum exchange: peers not mapped");
+    if (n < 1 || n > 3) ARG_FAIL("sum exchange: 1..3 values");
+    RingSumArgs a;
+    for (int r = 0; r < RING_MAX_SUM_RANKS; ++r) a.box[r] = r < s->g.nranks ? s->all_flags[r] : nullptr;
+    a.rank = s->g.rank; a.nranks = s->g.nranks; a.n = n;
+    a.seq = ++s->sum_seq;
+    ring_sum_exchange_kernel<<<1, 32, 0, st>>>(a, buf, host_out);
+    COUNT_LAUNCH();
+    CK(cudaGetLastError());
+    return B200MC_OK;
 }
 
 __global__ void ring_wait_flags_kernel(const unsigned int* flags, unsigned int seq)

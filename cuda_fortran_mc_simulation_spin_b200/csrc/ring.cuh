@@ -23,6 +23,10 @@
 #pragma once
 #include "common.cuh"
 
+#define RING_MAX_SUM_RANKS 16
+#define RING_FLAG_WORDS 2048      // flag buffer: [0, 64) the push flags, [RING_SUM_BASE, ...) the sum mailboxes
+#define RING_SUM_BASE 64
+#define RING_SUM_SLOT 8           // words per mailbox entry: 3 x u64 values + seq (u32) + pad
 struct RingGeom {
     int64_t N;       // sites on the ring
     int64_t Nc;      // sites per colour
@@ -56,6 +60,14 @@ struct RingStore {
     int n_peer_maps;
     int64_t Lloc_prev;           // owned vectors of rank-1 (its high halo starts at H + Lloc_prev)
     unsigned int push_seq;       // boundary pushes issued so far (same on every rank: SPMD)
+    // observable sums across the ranks without a collective (slab mode, direct transport): every rank's flag buffer is
+    // mapped on every rank; a one-warp kernel stores this rank's partial sums into each rank's mailbox and adds up the
+    // nranks entries of its own (ring_sum_exchange)
+    unsigned int* all_flags[RING_MAX_SUM_RANKS];   // [rank] -> that rank's flag buffer (own entry: flags)
+    void* sum_maps[RING_MAX_SUM_RANKS];            // non-neighbour mappings to close
+    int n_sum_maps;
+    bool sums_p2p;
+    unsigned int sum_seq;        // exchanges issued so far (same on every rank)
 };
 #define RING_IPC_BYTES 192       // three cudaIpcMemHandle_t: colour 0, colour 1, flags
 
@@ -174,6 +186,11 @@ int ring_export_i32(RingStore* s, int32_t* host, RingValueMap map, cudaStream_t 
 int ring_p2p_export(RingStore* s, char out[RING_IPC_BYTES]);
 int ring_p2p_connect(RingStore* s, const char prev[RING_IPC_BYTES], const char next[RING_IPC_BYTES]);
 int ring_p2p_connect_self(RingStore* s);
+// map the flag buffers of all ranks (handles: nranks x RING_IPC_BYTES, as exported by ring_p2p_export; call after
+// ring_p2p_connect): enables ring_sum_exchange
+int ring_p2p_connect_sums(RingStore* s, const char* handles);
+// buf[0..n) (n <= 3 u64 partial sums of this rank, device memory) -> sums over all ranks, in buf and in host_out (pinned)
+int ring_sum_exchange(RingStore* s, unsigned long long* buf, int n, unsigned long long* host_out, cudaStream_t st);
 void ring_p2p_close(RingStore* s);
 // stream-ordered wait until every push issued so far by both neighbours has landed
 int ring_p2p_quiesce(RingStore* s, cudaStream_t st);

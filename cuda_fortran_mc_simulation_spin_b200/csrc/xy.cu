@@ -24,6 +24,11 @@ struct XYArgs {
     float* own;
     const float* oth;
     int nxh, ny, gpr;  // sites per row per colour, rows, float4 groups per row
+    int pitch;         // floats per row of a colour array: nxh rounded up to 4; the pitch - nxh padding floats of a row mirror its
+                       // first sites (xi = 0, 1, ..: the periodic continuation to the right), kept current by every kernel that
+                       // writes xi < pitch - nxh.  With them the last, partial group of a row (nx/2 not a multiple of 4; the
+                       // reference only needs nx even, src/xy2d_periodic_gpu_m.f90:377-380) reads its right-hand neighbour like
+                       // every other group; its own padding lanes are computed but neither stored nor summed.
     int colour;
     float beta;
     uint64_t draw;
@@ -78,13 +83,28 @@ struct XYRow { float c[4], s[4]; };
 
 __device__ __forceinline__ void xy_load_row(const XYArgs& a, int y, int g, XYRow& r)
 {
-    const float4 raw = *reinterpret_cast<const float4*>(a.oth + (ptrdiff_t)y * a.nxh + 4 * g);   // y = -1 / ny: halo rows
+    const float4 raw = *reinterpret_cast<const float4*>(a.oth + (ptrdiff_t)y * a.pitch + 4 * g);   // y = -1 / ny: halo rows
     // (the same function as for the rows loaded inside the strip loop: a site's cos / sin must not depend on where the
     // row falls in a strip, or the trajectory would depend on the decomposition into strips and slabs)
     sincos_unit(raw.x, r.s[0], r.c[0]);
     sincos_unit(raw.y, r.s[1], r.c[1]);
     sincos_unit(raw.z, r.s[2], r.c[2]);
     sincos_unit(raw.w, r.s[3], r.c[3]);
+}
+
+// store the 4 new values of group xi0 of a row (row = start of the row in the colour array): the last group of a row
+// may be partial, and the first group also refreshes the row's mirror padding
+__device__ __forceinline__ void xy_store_group(float* row, int xi0, int nxh, int pitch, const float (&ov)[4])
+{
+    if (xi0 + 4 <= nxh) *reinterpret_cast<float4*>(row + xi0) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) if (xi0 + j < nxh) row[xi0 + j] = ov[j];
+    }
+    if (xi0 == 0 && pitch != nxh) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) if (nxh + j < pitch) row[nxh + j] = ov[j];
+    }
 }
 
 // OVERRELAX = false: update_sub + calc_delta_energy, src/xy2d_periodic_gpu_m.f90:368-397
@@ -107,8 +127,9 @@ static_assert(XY_ROWS % 2 == 0, "the strip loop is unrolled by two rows (the nei
 // same-row neighbours are the other colour's xi - 1 + P and xi + P.
 template <bool OVERRELAX, bool MEASURE, int P>
 __device__ __forceinline__ void xy_strip_row(const XYArgs& a, int y, int idx, float nbl2e, const float4 r_up, const float r_edge, const float4 o,
-                                             const XYRow& dn, const XYRow& mid, XYRow& up, float4* po, float& es, float& mx, float& my)
+                                             const XYRow& dn, const XYRow& mid, XYRow& up, float* prow, int xi0, float& es, float& mx, float& my)
 {
+    const int nvalid = a.nxh - xi0;   // >= 4 except in the last group of a row whose nx/2 is not a multiple of 4
     sincos_unit(r_up.x, up.s[0], up.c[0]);
     sincos_unit(r_up.y, up.s[1], up.c[1]);
     sincos_unit(r_up.z, up.s[2], up.c[2]);
@@ -131,7 +152,7 @@ __device__ __forceinline__ void xy_strip_row(const XYArgs& a, int y, int idx, fl
         for (int j = 0; j < 4; ++j) {
             const float t = 2.0f * atan2_turns(hy[j], hx[j]) - ov[j];                    // (-2, 1]
             ov[j] = frac_turns(t);                                                        // [0, 1]
-            if (MEASURE) {
+            if (MEASURE && j < nvalid) {
                 float sn, cn;
                 sincos_unit(ov[j], sn, cn);
                 es -= cn * hx[j] + sn * hy[j];
@@ -157,7 +178,7 @@ __device__ __forceinline__ void xy_strip_row(const XYArgs& a, int y, int idx, fl
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(de * nbl2e));
                 const bool acc = !(r > w);                                 // accept iff r <= exp(-beta dE), :384
                 if (acc) ov[j] = ct;
-                if (MEASURE) {
+                if (MEASURE && j < nvalid) {
                     const float cn = acc ? cc : sc, sn = acc ? cs : ss;
                     es -= cn * hx[j] + sn * hy[j];
                     mx += cn; my += sn;
@@ -167,9 +188,9 @@ __device__ __forceinline__ void xy_strip_row(const XYArgs& a, int y, int idx, fl
     }
     if (MEASURE) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { mx += mid.c[j]; my += mid.s[j]; }
+        for (int j = 0; j < 4; ++j) if (j < nvalid) { mx += mid.c[j]; my += mid.s[j]; }
     }
-    *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    xy_store_group(prow, xi0, a.nxh, a.pitch, ov);
 }
 
 template <bool OVERRELAX, bool MEASURE, int COLOUR>
@@ -183,36 +204,36 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
     if (active) {
         const int rb = tid / a.gpr, g = tid - rb * a.gpr;
         const int y0 = rb * XY_ROWS, y1 = min(y0 + XY_ROWS, a.ny);   // both even (ny is even)
-        const int nxh = a.nxh, xi0 = 4 * g;
+        const int nxh = a.nxh, xi0 = 4 * g, pitch = a.pitch;
         const float nbl2e = a.beta * 1.4426950408889634f;
         XYRow dn, mid, up;
         xy_load_row(a, (y0 == 0 && !a.halo) ? a.ny - 1 : y0 - 1, g, dn);
         xy_load_row(a, y0, g, mid);
         // the fifth same-row value: left of the group on rows with P = 0, right of it on rows with P = 1
-        const int xe0 = xi0 == 0 ? nxh - 1 : xi0 - 1, xe1 = xi0 + 4 == nxh ? 0 : xi0 + 4;
+        const int xe0 = xi0 == 0 ? nxh - 1 : xi0 - 1, xe1 = xi0 + 4 >= nxh ? 0 : xi0 + 4;   // (a partial last group never uses xe1: its right-hand neighbour is the mirror padding)
         // the raw values of a row (the other colour's row y + 1, the fifth same-row value, the own row) are
         // loaded one row ahead, unconditionally (clamped row index: straight-line code that the scheduler issues
         // at the top): the stores to `own` would otherwise pin every load behind them (no restrict on the two
         // colour arrays) and each row would pay a full DRAM round trip
-        auto ld_up = [&](int y) { return __ldg(reinterpret_cast<const float4*>(a.oth + (ptrdiff_t)((y + 1 >= a.ny && !a.halo) ? y + 1 - a.ny : y + 1) * nxh + xi0)); };
-        auto ld_own = [&](int y) { return *reinterpret_cast<const float4*>(a.own + (size_t)y * nxh + xi0); };
+        auto ld_up = [&](int y) { return __ldg(reinterpret_cast<const float4*>(a.oth + (ptrdiff_t)((y + 1 >= a.ny && !a.halo) ? y + 1 - a.ny : y + 1) * pitch + xi0)); };
+        auto ld_own = [&](int y) { return *reinterpret_cast<const float4*>(a.own + (size_t)y * pitch + xi0); };
         float4 u0 = ld_up(y0), o0 = ld_own(y0);
-        float e0 = __ldg(a.oth + (size_t)y0 * nxh + (COLOUR ? xe1 : xe0));
+        float e0 = __ldg(a.oth + (size_t)y0 * pitch + (COLOUR ? xe1 : xe0));
         if constexpr (OVERRELAX) {
             // over-relaxation (fewer instructions per row, 80 registers): TWO rows ahead -- the raw values of rows y + 2 and
             // y + 3 are requested before rows y and y + 1 are processed (463 -> 512 flips/ns; no effect on Metropolis,
             // which is bound by issue slots and the XU pipe)
             float4 u1 = ld_up(y0 + 1), o1 = ld_own(y0 + 1);
-            float e1 = __ldg(a.oth + (size_t)(y0 + 1) * nxh + (COLOUR ? xe0 : xe1));
+            float e1 = __ldg(a.oth + (size_t)(y0 + 1) * pitch + (COLOUR ? xe0 : xe1));
             for (int y = y0; y < y1; y += 2) {
                 const int yn = min(y + 2, y1 - 2);
                 const float4 nu0 = ld_up(yn), no0 = ld_own(yn), nu1 = ld_up(yn + 1), no1 = ld_own(yn + 1);
-                const float ne0 = __ldg(a.oth + (size_t)yn * nxh + (COLOUR ? xe1 : xe0));
-                const float ne1 = __ldg(a.oth + (size_t)(yn + 1) * nxh + (COLOUR ? xe0 : xe1));
+                const float ne0 = __ldg(a.oth + (size_t)yn * pitch + (COLOUR ? xe1 : xe0));
+                const float ne1 = __ldg(a.oth + (size_t)(yn + 1) * pitch + (COLOUR ? xe0 : xe1));
                 xy_strip_row<OVERRELAX, MEASURE, COLOUR>(a, y, (y + a.yoff) * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
-                                                         reinterpret_cast<float4*>(a.own + (size_t)y * nxh + xi0), es, mx, my);
+                                                         a.own + (size_t)y * pitch, xi0, es, mx, my);
                 xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1>(a, y + 1, (y + 1 + a.yoff) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
-                                                             reinterpret_cast<float4*>(a.own + (size_t)(y + 1) * nxh + xi0), es, mx, my);
+                                                             a.own + (size_t)(y + 1) * pitch, xi0, es, mx, my);
                 u0 = nu0; o0 = no0; e0 = ne0; u1 = nu1; o1 = no1; e1 = ne1;
                 // rows rotate by two: (dn, mid, up) <- (up of the first row = mid of the second, up of the second)
                 const XYRow t = mid; mid = dn; dn = up; (void)t;
@@ -220,14 +241,14 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
         } else {
             for (int y = y0; y < y1; y += 2) {
                 const float4 u1 = ld_up(y + 1), o1 = ld_own(y + 1);
-                const float e1 = __ldg(a.oth + (size_t)(y + 1) * nxh + (COLOUR ? xe0 : xe1));
+                const float e1 = __ldg(a.oth + (size_t)(y + 1) * pitch + (COLOUR ? xe0 : xe1));
                 xy_strip_row<OVERRELAX, MEASURE, COLOUR>(a, y, (y + a.yoff) * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
-                                                         reinterpret_cast<float4*>(a.own + (size_t)y * nxh + xi0), es, mx, my);
+                                                         a.own + (size_t)y * pitch, xi0, es, mx, my);
                 const int yn = min(y + 2, y1 - 2);
                 u0 = ld_up(yn); o0 = ld_own(yn);
-                e0 = __ldg(a.oth + (size_t)yn * nxh + (COLOUR ? xe1 : xe0));
+                e0 = __ldg(a.oth + (size_t)yn * pitch + (COLOUR ? xe1 : xe0));
                 xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1>(a, y + 1, (y + 1 + a.yoff) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
-                                                             reinterpret_cast<float4*>(a.own + (size_t)(y + 1) * nxh + xi0), es, mx, my);
+                                                             a.own + (size_t)(y + 1) * pitch, xi0, es, mx, my);
                 const XYRow t = mid; mid = dn; dn = up; (void)t;
             }
         }
@@ -253,21 +274,24 @@ xy_pass_randoms_kernel(const __grid_constant__ XYArgs a, const double* __restric
     const int xl = P ? xi : (xi == 0 ? a.nxh - 1 : xi - 1), xr = P ? (xi + 1 == a.nxh ? 0 : xi + 1) : xi;
     const int yu = (y + 1 >= a.ny && !a.halo) ? 0 : y + 1, yd = (y == 0 && !a.halo) ? a.ny - 1 : y - 1;
     float sr, cr, sl, cl, su, cu, sd, cd;
-    sincos_unit(a.oth[(ptrdiff_t)y * a.nxh + xr], sr, cr);
-    sincos_unit(a.oth[(ptrdiff_t)y * a.nxh + xl], sl, cl);
-    sincos_unit(a.oth[(ptrdiff_t)yu * a.nxh + xi], su, cu);
-    sincos_unit(a.oth[(ptrdiff_t)yd * a.nxh + xi], sd, cd);
+    sincos_unit(a.oth[(ptrdiff_t)y * a.pitch + xr], sr, cr);
+    sincos_unit(a.oth[(ptrdiff_t)y * a.pitch + xl], sl, cl);
+    sincos_unit(a.oth[(ptrdiff_t)yu * a.pitch + xi], su, cu);
+    sincos_unit(a.oth[(ptrdiff_t)yd * a.pitch + xi], sd, cd);
     const float hx = cr + cl + cu + cd, hy = sr + sl + su + sd;
     const size_t ridx = (size_t)(y + a.yoff) * (size_t)nx + (size_t)x0;
     const float ct = (float)cands[ridx];
-    const float ov = a.own[(size_t)y * a.nxh + xi];
+    const float ov = a.own[(size_t)y * a.pitch + xi];
     float cs, cc, ss, sc;
     sincos_unit(ct, cs, cc);
     sincos_unit(ov, ss, sc);
     const float de = (cc - sc) * hx + (cs - ss) * hy;   // -dE
     float w;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(de * (a.beta * 1.4426950408889634f)));
-    if (!(randoms[ridx] > (double)w)) a.own[(size_t)y * a.nxh + xi] = ct;   // (0, 1] turns, like the strip kernel
+    if (!(randoms[ridx] > (double)w)) {
+        a.own[(size_t)y * a.pitch + xi] = ct;   // (0, 1] turns, like the strip kernel
+        if (xi < a.pitch - a.nxh) a.own[(size_t)y * a.pitch + a.nxh + xi] = ct;   // the row's mirror padding
+    }
 }
 
 // metropolis_by_field_sub, :198-216 (initial-state preparation): every site, no coupling.
@@ -280,8 +304,8 @@ xy_field_kernel(const __grid_constant__ XYArgs a, float hx, float hy)
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.ny * a.gpr) return;
     const int y = idx / a.gpr, g = idx - y * a.gpr;
-    float4* po = reinterpret_cast<float4*>(a.own + (size_t)y * a.nxh + 4 * g);
-    const float4 o = *po;
+    float* prow = a.own + (size_t)y * a.pitch;
+    const float4 o = *reinterpret_cast<const float4*>(prow + 4 * g);
     float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
     for (int sub = 0; sub < 2; ++sub) {
@@ -299,7 +323,7 @@ xy_field_kernel(const __grid_constant__ XYArgs a, float hx, float hy)
             if (!(r > 1.0f - __expf(de))) ov[j] = ct;
         }
     }
-    *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    xy_store_group(prow, 4 * g, a.nxh, a.pitch, ov);
 }
 
 // fused E, Mx, My (three OpenACC reductions in the reference, :496-534), real64 accumulation.
@@ -308,7 +332,7 @@ xy_field_kernel(const __grid_constant__ XYArgs a, float hx, float hy)
 // XY_ROWS rows and keeps the previous row's cos/sin, so every site costs one sincos (+ 1/8 for the group edge)
 // instead of three.  Bonds: (x, x+1) inside the row, (y-1, y) against the previous row.
 __global__ void __launch_bounds__(256)
-xy_measure_kernel(const float* __restrict__ c0, const float* __restrict__ c1, int nxh, int ny, int gpr, double* acc, int halo)
+xy_measure_kernel(const float* __restrict__ c0, const float* __restrict__ c1, int nxh, int pitch, int ny, int gpr, double* acc, int halo)
 {
     double part[3] = {0.0, 0.0, 0.0};
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -316,12 +340,15 @@ xy_measure_kernel(const float* __restrict__ c0, const float* __restrict__ c1, in
     if (tid < nblk * gpr) {
         const int rb = tid / gpr, g = tid - rb * gpr;
         const int y0 = rb * XY_ROWS, y1 = min(y0 + XY_ROWS, ny);
+        // lattice sites of this group that exist: 8, or 2 (nxh - 4 g) in the last group of a row whose nx/2 is not a
+        // multiple of 4; the site right of the last valid one is then the row's mirror padding (= x0 = 0)
+        const int nv = min(8, 2 * (nxh - 4 * g));
         float pc[8], ps[8], qc[8], qs[8];
         float es = 0.f, mx = 0.f, my = 0.f;
         // cos / sin of the 8 sites x0 = 8 g .. 8 g + 7 of row y, in lattice order: even x0 belong to colour (y & 1)
         auto load_row = [&](int y, float (&c)[8], float (&sn)[8]) {
-            const float4 a = *reinterpret_cast<const float4*>(((y & 1) ? c1 : c0) + (ptrdiff_t)y * nxh + 4 * g);
-            const float4 b = *reinterpret_cast<const float4*>(((y & 1) ? c0 : c1) + (ptrdiff_t)y * nxh + 4 * g);
+            const float4 a = *reinterpret_cast<const float4*>(((y & 1) ? c1 : c0) + (ptrdiff_t)y * pitch + 4 * g);
+            const float4 b = *reinterpret_cast<const float4*>(((y & 1) ? c0 : c1) + (ptrdiff_t)y * pitch + 4 * g);
             sincos_turns(a.x, sn[0], c[0]); sincos_turns(b.x, sn[1], c[1]);
             sincos_turns(a.y, sn[2], c[2]); sincos_turns(b.y, sn[3], c[3]);
             sincos_turns(a.z, sn[4], c[4]); sincos_turns(b.z, sn[5], c[5]);
@@ -331,17 +358,19 @@ xy_measure_kernel(const float* __restrict__ c0, const float* __restrict__ c1, in
         for (int y = y0; y < y1; ++y) {
             load_row(y, qc, qs);
             // the site right of the group: x0 = 8 g + 8 (periodic), an even x0 -> colour (y & 1), xi = 4 g + 4
-            const int xe = (4 * g + 4 == nxh) ? 0 : 4 * g + 4;
+            const int xe = (4 * g + 4 >= nxh) ? 0 : 4 * g + 4;
             float ec, esn;
-            sincos_turns(((y & 1) ? c1 : c0)[(size_t)y * nxh + xe], esn, ec);
-            float e = qc[7] * ec + qs[7] * esn;
+            sincos_turns(((y & 1) ? c1 : c0)[(size_t)y * pitch + xe], esn, ec);
+            float e = nv == 8 ? qc[7] * ec + qs[7] * esn : 0.f;
 #pragma unroll
-            for (int k = 0; k < 7; ++k) e += qc[k] * qc[k + 1] + qs[k] * qs[k + 1];
+            for (int k = 0; k < 7; ++k) if (k < nv) e += qc[k] * qc[k + 1] + qs[k] * qs[k + 1];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                e += pc[k] * qc[k] + ps[k] * qs[k];
-                mx += qc[k];
-                my += qs[k];
+                if (k < nv) {
+                    e += pc[k] * qc[k] + ps[k] * qs[k];
+                    mx += qc[k];
+                    my += qs[k];
+                }
                 pc[k] = qc[k];
                 ps[k] = qs[k];
             }
@@ -356,9 +385,9 @@ xy_measure_kernel(const float* __restrict__ c0, const float* __restrict__ c1, in
 // acc[0] += sum s . s0 ; acc[1] += sum s(x, y) . s(x + nx/2 - 1, y + ny/2 - 1)
 __global__ void __launch_bounds__(256)
 xy_corr_kernel(const float* __restrict__ c0, const float* __restrict__ c1, const float* __restrict__ z0,
-               const float* __restrict__ z1, int nx, int ny, double* acc)
+               const float* __restrict__ z1, int nx, int ny, int pitch, double* acc)
 {
-    const int nxh = nx / 2;
+    const int nxh = pitch;   // row stride of the colour arrays
     double part[2] = {0.0, 0.0};
     const long long total = (long long)nx * ny;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -386,14 +415,14 @@ xy_corr_kernel(const float* __restrict__ c0, const float* __restrict__ c1, const
 
 // set_random_spin_sub (:112-122): theta = 2 pi u  ->  turns = u
 __global__ void __launch_bounds__(256)
-xy_random_kernel(float* own, int nxh, int ny, int gpr, int colour, uint32_t seed, uint64_t draw, int yoff)
+xy_random_kernel(float* own, int nxh, int pitch, int ny, int gpr, int colour, uint32_t seed, uint64_t draw, int yoff)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= ny * gpr) return;
     const int y = idx / gpr, g = idx - y * gpr;
     const uint4 R = philox4x32_10(mk_ctr((uint64_t)(idx + yoff * gpr), draw, (uint32_t)colour, 0u), make_uint2(seed, TAG_INIT));
-    *reinterpret_cast<float4*>(own + (size_t)y * nxh + 4 * g) =
-        make_float4(((float)R.x + 1.0f) * 0x1p-32f, ((float)R.y + 1.0f) * 0x1p-32f, ((float)R.z + 1.0f) * 0x1p-32f, ((float)R.w + 1.0f) * 0x1p-32f);
+    const float ov[4] = {((float)R.x + 1.0f) * 0x1p-32f, ((float)R.y + 1.0f) * 0x1p-32f, ((float)R.z + 1.0f) * 0x1p-32f, ((float)R.w + 1.0f) * 0x1p-32f};
+    xy_store_group(own + (size_t)y * pitch, 4 * g, nxh, pitch, ov);
 }
 
 __global__ void xy_fill_kernel(float* a, float* b, size_t n, float v)
@@ -413,7 +442,7 @@ __global__ void xy_rotate_kernel(float* a, float* b, size_t n, float dt)
 }
 
 // spins() in the reference layout spins(0:nx+1, 0:ny+1, 1:2), real64, halo frame refreshed, corners 0
-__global__ void xy_export_kernel(const float* c0, const float* c1, int nx, int ny, double* out)
+__global__ void xy_export_kernel(const float* c0, const float* c1, int nx, int ny, int pitch, double* out)
 {
     const long long W = nx + 2, Ht = ny + 2;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -424,31 +453,34 @@ __global__ void xy_export_kernel(const float* c0, const float* c1, int nx, int n
     if (!(xh && yh)) {
         const int x0 = x == 0 ? nx - 1 : (x == nx + 1 ? 0 : x - 1);
         const int y0 = y == 0 ? ny - 1 : (y == ny + 1 ? 0 : y - 1);
-        const float t = (((x0 + y0) & 1) ? c1 : c0)[(size_t)y0 * (nx / 2) + (x0 >> 1)];
+        const float t = (((x0 + y0) & 1) ? c1 : c0)[(size_t)y0 * pitch + (x0 >> 1)];
         sincospi(2.0 * (double)t, &s, &c);
     }
     out[i] = c;
     out[W * Ht + i] = s;
 }
-__global__ void xy_export_turns_kernel(const float* c0, const float* c1, int nx, int ny, float* out)
+__global__ void xy_export_turns_kernel(const float* c0, const float* c1, int nx, int ny, int pitch, float* out)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)nx * ny) return;
     const int y0 = (int)(i / nx), x0 = (int)(i - (long long)y0 * nx);
-    out[i] = (((x0 + y0) & 1) ? c1 : c0)[(size_t)y0 * (nx / 2) + (x0 >> 1)];
+    out[i] = (((x0 + y0) & 1) ? c1 : c0)[(size_t)y0 * pitch + (x0 >> 1)];
 }
-__global__ void xy_import_turns_kernel(float* c0, float* c1, int nx, int ny, const float* in)
+__global__ void xy_import_turns_kernel(float* c0, float* c1, int nx, int ny, int pitch, const float* in)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)nx * ny) return;
     const int y0 = (int)(i / nx), x0 = (int)(i - (long long)y0 * nx);
     const float t = in[i];
-    (((x0 + y0) & 1) ? c1 : c0)[(size_t)y0 * (nx / 2) + (x0 >> 1)] = t - floorf(t);   // stored angles live in [0, 1] turns (sincos_unit)
+    float* row = (((x0 + y0) & 1) ? c1 : c0) + (size_t)y0 * pitch;
+    const float v = t - floorf(t);   // stored angles live in [0, 1] turns (sincos_unit)
+    row[x0 >> 1] = v;
+    if ((x0 >> 1) < pitch - nx / 2) row[nx / 2 + (x0 >> 1)] = v;   // the row's mirror padding
 }
 
 struct XY {
     int64_t nx, ny;
-    int nxh, gpr;
+    int nxh, gpr, pitch;   // pitch: floats per row (nxh rounded up to 4)
     float* c[2];   // colour arrays: row 0 of the allocation below (one spare row before and after = the halo rows of slab mode)
     float* base[2];
     // slabs along y: this rank holds rows [yoff, yoff + ny) of ny_glob; ny is LOCAL everywhere below
@@ -473,7 +505,7 @@ struct XY {
 void fill_args(XY* m, int colour, XYArgs* a)
 {
     a->own = m->c[colour]; a->oth = m->c[colour ^ 1];
-    a->nxh = m->nxh; a->ny = (int)m->ny; a->gpr = m->gpr; a->colour = colour;
+    a->nxh = m->nxh; a->pitch = m->pitch; a->ny = (int)m->ny; a->gpr = m->gpr; a->colour = colour;
     a->beta = (float)m->beta; a->draw = m->draw;
     for (int r = 0; r < 10; ++r) a->rk0[r] = m->seed + (uint32_t)r * PHILOX_W0;
     a->acc = m->d_acc;
@@ -486,11 +518,11 @@ int halo_rows(XY* m, int colour)
 {
     if (!m->halo) return B200MC_OK;
     float* c = m->c[colour];
-    const size_t row = (size_t)m->nxh * sizeof(float);
+    const size_t row = (size_t)m->pitch * sizeof(float);
     if (m->nranks > 1)   // my first row is the row above rank-1's last one, my last row the row below rank+1's first
-        return dist_exchange_ring(m->comm, m->rank, m->nranks, c, c + (size_t)(m->ny - 1) * m->nxh, c - m->nxh, c + (size_t)m->ny * m->nxh, row, m->stream);
-    CK(cudaMemcpyAsync(c - m->nxh, c + (size_t)(m->ny - 1) * m->nxh, row, cudaMemcpyDeviceToDevice, m->stream));
-    CK(cudaMemcpyAsync(c + (size_t)m->ny * m->nxh, c, row, cudaMemcpyDeviceToDevice, m->stream));
+        return dist_exchange_ring(m->comm, m->rank, m->nranks, c, c + (size_t)(m->ny - 1) * m->pitch, c - m->pitch, c + (size_t)m->ny * m->pitch, row, m->stream);
+    CK(cudaMemcpyAsync(c - m->pitch, c + (size_t)(m->ny - 1) * m->pitch, row, cudaMemcpyDeviceToDevice, m->stream));
+    CK(cudaMemcpyAsync(c + (size_t)m->ny * m->pitch, c, row, cudaMemcpyDeviceToDevice, m->stream));
     return B200MC_OK;
 }
 
@@ -593,7 +625,7 @@ int measure(XY* m)
         CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
         COUNT_LAUNCH();
         const int strips = (int)((m->ny + XY_ROWS - 1) / XY_ROWS) * m->gpr;
-        xy_measure_kernel<<<(strips + 255) / 256, 256, 0, m->stream>>>(m->c[0], m->c[1], m->nxh, (int)m->ny, m->gpr, m->d_acc, m->halo);
+        xy_measure_kernel<<<(strips + 255) / 256, 256, 0, m->stream>>>(m->c[0], m->c[1], m->nxh, m->pitch, (int)m->ny, m->gpr, m->d_acc, m->halo);
         CK(cudaGetLastError());
     }
     m->fused_pending = false;
@@ -611,7 +643,7 @@ int corr(XY* m, bool autoc, double* out)
     if (m->nranks > 1) { snprintf(g_b200mc_err, sizeof(g_b200mc_err), "xy2d: the correlation sums are not available in slab mode"); return B200MC_ERR_UNSUPPORTED; }
     CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
     COUNT_LAUNCH();
-    xy_corr_kernel<<<m->sms * 8, 256, 0, m->stream>>>(m->c[0], m->c[1], autoc ? m->z[0] : nullptr, autoc ? m->z[1] : nullptr, (int)m->nx, (int)m->ny, m->d_acc);
+    xy_corr_kernel<<<m->sms * 8, 256, 0, m->stream>>>(m->c[0], m->c[1], autoc ? m->z[0] : nullptr, autoc ? m->z[1] : nullptr, (int)m->nx, (int)m->ny, m->pitch, m->d_acc);
     CK(cudaGetLastError());
     double r[2];
     CK(cudaMemcpyAsync(r, m->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
@@ -631,7 +663,7 @@ void destroy(XY* m)
 
 int fill(XY* m, float v)
 {
-    const size_t n = (size_t)m->nxh * m->ny;
+    const size_t n = (size_t)m->pitch * m->ny;
     m->obs_valid = false; m->fused_pending = false;
     COUNT_LAUNCH();
     xy_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], n, v);
@@ -662,25 +694,13 @@ int b200mc_xy2d_create_slab(void** out, int64_t nx, int64_t ny_global, double kb
     if (!out) ARG_FAIL("null handle pointer");
     *out = nullptr;
     if (nranks < 1 || rank < 0 || rank >= nranks) ARG_FAIL("bad rank %d / %d", rank, nranks);
-    if (nranks > 1) {
-        // The first 2-GPU run of this path diverged from the one-GPU trajectory: the first rows of a strip took their
-        // cos / sin from a different (range-reducing) function than the rows inside the strip loop, so a site's
-        // arithmetic depended on the decomposition.  That is fixed (xy_load_row), but the round's GPU budget ended
-        // before the fix could be re-run on two GPUs: opt in explicitly until it has been.
-        const char* t = getenv("B200MC_XY_SLAB");
-        if (!(t && atoi(t))) {
-            snprintf(g_b200mc_err, sizeof(g_b200mc_err), "xy2d slabs over several GPUs are not validated yet (set B200MC_XY_SLAB=1 to try them)");
-            return B200MC_ERR_UNSUPPORTED;
-        }
-    }
     if (nranks > 1 && !nccl_id) ARG_FAIL("slab mode needs the NCCL unique id of the job (b200mc_dist_unique_id on rank 0, broadcast by the caller)");
     if (ny_global % nranks || ((ny_global / nranks) & 1)) ARG_FAIL("xy2d slabs: ny (%lld) must split into an even number of rows per rank (%d ranks)", (long long)ny_global, nranks);
     const int64_t ny = ny_global / nranks;
     if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0");
-    // the reference needs nx, ny even (colouring, src/xy2d_periodic_gpu_m.f90:377-380); the float4 layout needs nx % 8 == 0
-    if (nx < 8 || ny < 2 || (ny & 1)) ARG_FAIL("xy2d: need nx >= 8, ny >= 2 even (got %lld x %lld)", (long long)nx, (long long)ny);
-    if (nx % 8) { snprintf(g_b200mc_err, sizeof(g_b200mc_err), "xy2d: nx must be a multiple of 8 in this build (got %lld)", (long long)nx); return B200MC_ERR_UNSUPPORTED; }
-    if ((nx / 2) * ny / 4 >= (int64_t)0x7FFFFFFF) ARG_FAIL("xy2d: lattice too large");
+    // the reference needs nx, ny even (colouring, src/xy2d_periodic_gpu_m.f90:377-380); so does this build (rows are padded to whole float4 groups)
+    if (nx < 8 || (nx & 1) || ny < 2 || (ny & 1)) ARG_FAIL("xy2d: need nx >= 8 even, ny >= 2 even (got %lld x %lld)", (long long)nx, (long long)ny);
+    if ((nx / 2 + 3) / 4 * ny >= (int64_t)0x7FFFFFFF) ARG_FAIL("xy2d: lattice too large");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "no CUDA device: this library has no CPU fallback");
@@ -688,27 +708,27 @@ int b200mc_xy2d_create_slab(void** out, int64_t nx, int64_t ny_global, double kb
     }
     XY* m = new (std::nothrow) XY();
     if (!m) ARG_FAIL("out of host memory");
-    m->nx = nx; m->ny = ny; m->nxh = (int)(nx / 2); m->gpr = m->nxh / 4; m->stream = 0;
+    m->nx = nx; m->ny = ny; m->nxh = (int)(nx / 2); m->gpr = (m->nxh + 3) / 4; m->pitch = 4 * m->gpr; m->stream = 0;
     m->beta = 1 / kbt; m->seed = (uint32_t)iseed; m->draw = 0; m->obs_valid = false; m->fused_pending = false; m->want_fused = false;
     m->c[0] = m->c[1] = m->base[0] = m->base[1] = m->z[0] = m->z[1] = m->stage = nullptr; m->d_acc = nullptr; m->halo = 0; m->comm = nullptr; m->nranks = 1; m->rank = 0;
     int dev = 0; m->sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&m->sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t n = (size_t)m->nxh * ny;
+    const size_t n = (size_t)m->pitch * ny;
     { const char* t = getenv("B200MC_XY_HALO"); m->halo = ((t && atoi(t)) || nranks > 1) ? 1 : 0; }
     m->rank = rank; m->nranks = nranks; m->ny_glob = ny_global; m->yoff = (int64_t)rank * ny; m->comm = nullptr;
-    if (ny_global * (nx / 2) / 4 >= (int64_t)0x7FFFFFFF) { delete m; ARG_FAIL("xy2d: lattice too large for the 32-bit RNG block index"); }
+    if (ny_global * ((nx / 2 + 3) / 4) >= (int64_t)0x7FFFFFFF) { delete m; ARG_FAIL("xy2d: lattice too large for the 32-bit RNG block index"); }
     if (nranks > 1) {
         int rcc = dist_comm_init(&m->comm, rank, nranks, nccl_id);
         if (rcc) { delete m; return rcc; }
     }
-    const size_t nalloc = n + 2 * (size_t)m->nxh;
+    const size_t nalloc = n + 2 * (size_t)m->pitch;
     if (cudaMalloc(&m->base[0], nalloc * sizeof(float)) != cudaSuccess || cudaMalloc(&m->base[1], nalloc * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&m->d_acc, 3 * sizeof(double)) != cudaSuccess) {
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed");
         destroy(m); return B200MC_ERR_CUDA;
     }
-    m->c[0] = m->base[0] + m->nxh; m->c[1] = m->base[1] + m->nxh;
+    m->c[0] = m->base[0] + m->pitch; m->c[1] = m->base[1] + m->pitch;
     cudaMemsetAsync(m->base[0], 0, nalloc * sizeof(float), m->stream);
     cudaMemsetAsync(m->base[1], 0, nalloc * sizeof(float), m->stream);
     int rc = fill(m, 0.0f);  // set_allup_spin: all along +x
@@ -735,7 +755,7 @@ int b200mc_xy2d_set_random_spin(void* h)
     const int total = (int)m->ny * m->gpr;
     for (int c = 0; c < 2; ++c) {
         COUNT_LAUNCH();
-        xy_random_kernel<<<(total + 255) / 256, 256, 0, m->stream>>>(m->c[c], m->nxh, (int)m->ny, m->gpr, c, m->seed, m->draw, (int)m->yoff);
+        xy_random_kernel<<<(total + 255) / 256, 256, 0, m->stream>>>(m->c[c], m->nxh, m->pitch, (int)m->ny, m->gpr, c, m->seed, m->draw, (int)m->yoff);
         CK(cudaGetLastError());
         { int rch = halo_rows(m, c); if (rch) return rch; }
     }
@@ -765,7 +785,7 @@ int b200mc_xy2d_set_initial_magne_autocorrelation_state(void* h)
 {
     CHECK_X(h);
     XY* m = HX(h);
-    const size_t n = (size_t)m->nxh * m->ny;
+    const size_t n = (size_t)m->pitch * m->ny;
     if (!m->z[0]) { CK(cudaMalloc(&m->z[0], n * sizeof(float))); CK(cudaMalloc(&m->z[1], n * sizeof(float))); }
     CK(cudaMemcpyAsync(m->z[0], m->c[0], n * sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
     CK(cudaMemcpyAsync(m->z[1], m->c[1], n * sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
@@ -782,7 +802,7 @@ int b200mc_xy2d_rotate_summation_magne_toward_xaxis(void* h, int32_t with_autoco
     if (rc) return rc;
     const double theta = atan2(m->obs[2], m->obs[1]);
     const float dt = (float)(-theta / (2 * 3.14159265358979323846));
-    const size_t n = (size_t)m->nxh * m->ny;
+    const size_t n = (size_t)m->pitch * m->ny;
     m->obs_valid = false; m->fused_pending = false;
     COUNT_LAUNCH();
     xy_rotate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], n, dt);
@@ -840,7 +860,7 @@ int b200mc_xy2d_get_spins(void* h, double* out)
     if (rc) return rc;
     const long long n = (long long)(m->nx + 2) * (m->ny + 2);
     COUNT_LAUNCH();
-    xy_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], (int)m->nx, (int)m->ny, reinterpret_cast<double*>(m->stage));
+    xy_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], (int)m->nx, (int)m->ny, m->pitch, reinterpret_cast<double*>(m->stage));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, m->stage, (size_t)2 * n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
@@ -856,7 +876,7 @@ int b200mc_xy2d_get_angles(void* h, float* out)
     if (rc) return rc;
     const long long n = (long long)m->nx * m->ny;
     COUNT_LAUNCH();
-    xy_export_turns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], (int)m->nx, (int)m->ny, m->stage);
+    xy_export_turns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], (int)m->nx, (int)m->ny, m->pitch, m->stage);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, m->stage, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
@@ -873,7 +893,7 @@ int b200mc_xy2d_set_angles(void* h, const float* in)
     m->obs_valid = false; m->fused_pending = false;
     CK(cudaMemcpyAsync(m->stage, in, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, m->stream));
     COUNT_LAUNCH();
-    xy_import_turns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], (int)m->nx, (int)m->ny, m->stage);
+    xy_import_turns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->c[0], m->c[1], (int)m->nx, (int)m->ny, m->pitch, m->stage);
     CK(cudaGetLastError());
     { int rch = halo_rows(m, 0); if (!rch) rch = halo_rows(m, 1); if (rch) return rch; }
     CK(cudaStreamSynchronize(m->stream));

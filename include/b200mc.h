@@ -139,6 +139,12 @@ int b200mc_ising3d_p2p_handles(void* h, char out[192]);
 int b200mc_ising2d_p2p_handles(void* h, char out[192]);
 int b200mc_ising3d_p2p_connect(void* h, const char prev[192], const char next[192]);
 int b200mc_ising2d_p2p_connect(void* h, const char prev[192], const char next[192]);
+/* after p2p_connect: map the flag buffers of ALL ranks (handles = nranks x 192 bytes, rank order, as written by
+ * p2p_handles).  calc_energy_sum / calc_magne_sum then add the per-rank sums up through peer memory (a one-warp kernel
+ * that stores its partial sums into every rank's mailbox and writes the totals to pinned host memory) instead of
+ * ncclAllReduce + copy.  Optional: without it the NCCL all-reduce is used. */
+int b200mc_ising3d_p2p_connect_sums(void* h, const char* handles);
+int b200mc_ising2d_p2p_connect_sums(void* h, const char* handles);
 int b200mc_ising3d_rank_info(void* h, int32_t* rank, int32_t* nranks);
 int b200mc_ising2d_rank_info(void* h, int32_t* rank, int32_t* nranks);
 /* host-only: the slab a rank would own. out = {Nc, L, H, p0, Lloc, ptail} (nz = 0 for 2D) */
@@ -280,7 +286,7 @@ int b200mc_sixclock_sync(void* h);
  * XY 2D, periodic -- type(xy2d_gpu), src/xy2d_periodic_gpu_m.f90:14-59.
  * State: one fp32 angle per site (turns); energy / magnetisation are real64
  * sums, compared with the reference at 1e-5 relative (BASELINE north_star).
- * nx must be a multiple of 8 and ny even in this build (the reference needs both even).
+ * nx >= 8 even and ny even, like the reference (:377-380); rows are padded to whole float4 groups internally.
  * ------------------------------------------------------------------------ */
 int b200mc_xy2d_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed);  /* init, :61-78 */
 /* Slab of a lattice of ny_global rows split along y over nranks GPUs (one process per GPU): this rank holds
@@ -288,8 +294,8 @@ int b200mc_xy2d_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t ise
  * goes to the neighbouring ranks' halo rows (ncclSend/Recv); E, Mx, My are all-reduced; every site draws the random
  * numbers it draws in the one-GPU run.  In slab mode ny() is the LOCAL row count, nall() the whole lattice, get_angles /
  * get_spins return the local rows, and the correlation sums are unsupported.
- * NOT VALIDATED on hardware yet for nranks > 1: returns B200MC_ERR_UNSUPPORTED unless the
- * environment sets B200MC_XY_SLAB=1.  nranks == 1 is b200mc_xy2d_create. */
+ * Validated on 2 GPUs against the one-GPU run (angles bit-identical; profiles/r02_slab_parity_2gpu.log).
+ * nranks == 1 is b200mc_xy2d_create. */
 int b200mc_xy2d_create_slab(void** h, int64_t nx, int64_t ny_global, double kbt, int32_t iseed, int32_t rank, int32_t nranks,
                             const char* nccl_id /* 128 bytes from b200mc_dist_unique_id; NULL when nranks == 1 */);
 int b200mc_xy2d_destroy(void* h);

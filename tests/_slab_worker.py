@@ -96,7 +96,9 @@ def main():
               "p2p active:", getattr(g, "_p2p", False), flush=True)
     # slabs large enough for the shared-ticket pass (boundary + interior blocks of two launches resident together, one
     # ticket counter): configuration and per-sweep fused E, M against the 1-GPU run of the same lattice, both methods
-    for kind, shape, kbt in (("3d", (255, 255, 256 * world), KBT3), ("2d", (4097, 4096 * world), KBT2)):
+    # (255 x 263: H = 33533 vectors, H % 128 = 125 -- the halo ends 48 bytes into a 128-byte line that also holds owned
+    # vectors, the layout in which a boundary block could hit a stale L1 line if it read the halo through the nc path)
+    for kind, shape, kbt in (("3d", (255, 255, 256 * world), KBT3), ("3d", (255, 263, 256 * world), KBT3), ("2d", (4097, 6144 * world), KBT2)):
         mod = ising3d_gpu_m.ising3d_gpu if kind == "3d" else ising2d_gpu_m.ising2d_gpu
         for method in (0, 1):
             g = mod().init_distributed(*shape, kbt, 5)

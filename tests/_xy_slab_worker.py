@@ -19,7 +19,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
 
-    for nx, ny_per in ((64, 36), (256, 64), (1024, 512)):
+    for nx, ny_per in ((64, 36), (250, 64), (1024, 512)):
         ny = ny_per * world
         g = xm.xy2d_gpu().init_distributed(nx, ny, 0.89, 11)
         assert g.ny() == ny_per and g.nall() == nx * ny

@@ -78,7 +78,9 @@ def row_mode(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("shape,kbt", [((16, 8), 0.89), ((64, 64), 0.895), ((256, 128), 0.5), ((1024, 512), 0.89), ((40, 30), 1.5)])
+# (nx = 1500: scripts/fpm_run_xy2d_periodic_from_disorder.sh:6; nx/2 % 4 = 2, 1, 3: partial last float4 group of a row)
+@pytest.mark.parametrize("shape,kbt", [((16, 8), 0.89), ((64, 64), 0.895), ((256, 128), 0.5), ((1024, 512), 0.89), ((40, 30), 1.5),
+                                       ((1500, 64), 0.89), ((1002, 32), 0.89), ((14, 4), 0.89), ((20, 6), 0.7)])
 def test_xy_metropolis_per_sweep(oracle, shape, kbt, row_mode):
     from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
     nx, ny = shape
@@ -99,7 +101,7 @@ def test_xy_metropolis_per_sweep(oracle, shape, kbt, row_mode):
         check_observables(g, o, n, ("metropolis", sweep))
 
 
-@pytest.mark.parametrize("shape", [(16, 8), (128, 64), (1024, 512)])
+@pytest.mark.parametrize("shape", [(16, 8), (128, 64), (1024, 512), (1500, 64), (1002, 32), (14, 4)])
 def test_xy_over_relaxation(oracle, shape, row_mode):
     from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
     nx, ny = shape
@@ -121,9 +123,9 @@ def test_xy_over_relaxation(oracle, shape, row_mode):
         assert np.quantile(d, 0.9999) < 2e-5 and d.max() < 1e-2
 
 
-def test_xy_spins_layout_and_helpers(oracle):
+@pytest.mark.parametrize("nx,ny", [(32, 16), (44, 16), (42, 10), (46, 12)])
+def test_xy_spins_layout_and_helpers(oracle, nx, ny):
     from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
-    nx, ny = 32, 16
     g = xm.xy2d_gpu().init(nx, ny, 0.89, 3)
     o = oracle.xy2d_gpu().init(nx, ny, 0.89, 3)
     g.set_random_spin()
@@ -252,10 +254,11 @@ def test_xy_initial_state_preparation():
     assert abs(math.hypot(mx, my) / n - 0.001) / 0.001 <= 0.5 + 1e-3
 
 
-def test_xy_fused_measurement_equals_separate_pass(row_mode):
+@pytest.mark.parametrize("nx", [512, 500, 498, 502])
+def test_xy_fused_measurement_equals_separate_pass(row_mode, nx):
     """after a measured sweep the last colour pass (Metropolis or over-relaxation) accumulates E, Mx, My itself"""
     from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
-    g = xm.xy2d_gpu().init(512, 256, 0.89, 5)
+    g = xm.xy2d_gpu().init(nx, 256, 0.89, 5)
     n = g.nall()
     g.set_random_spin(); g.update(); g.measure()
     for it in range(4):
@@ -274,7 +277,7 @@ def test_xy_halo_row_mode_is_the_periodic_path(monkeypatch):
     from cuda_fortran_mc_simulation_spin_b200 import xy2d_periodic_gpu_m as xm
 
     def run():
-        g = xm.xy2d_gpu().init(64, 72, 0.89, 5)
+        g = xm.xy2d_gpu().init(70, 72, 0.89, 5)
         g.set_random_spin()
         out = []
         for _ in range(3):

@@ -10,8 +10,6 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.xfail(strict=False, reason="the multi-rank XY path is opt-in (B200MC_XY_SLAB=1): its first 2-GPU run diverged "
-                   "(strip-dependent rounding, fixed in xy_load_row) and the fix has not been re-run on two GPUs yet")
 def test_xy_slabs_equal_the_one_gpu_run():
     import torch
     n = torch.cuda.device_count()
@@ -21,7 +19,7 @@ def test_xy_slabs_equal_the_one_gpu_run():
     r = subprocess.run(
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
          "--master-port", "29547", os.path.join(ROOT, "tests", "_xy_slab_worker.py")],
-        capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, B200MC_XY_SLAB="1"))
+        capture_output=True, text=True, timeout=600, cwd=ROOT)
     sys.stdout.write(r.stdout[-3000:])
     sys.stderr.write(r.stderr[-3000:])
     assert r.returncode == 0
