@@ -220,6 +220,25 @@ class _IsingBase:
         self._call("run_relaxation", int(mcs), e.ctypes.data_as(P), m.ctypes.data_as(P), argtypes=(i32, P, P))
         return (e[0], m[0]) if n == 1 else (e, m)
 
+    def run_relaxation_stats(self, mcs, tot_sample, random_start=False):
+        """the drivers' whole measurement on the device (app/ising3d_gpu_relaxation.f90:37-55): returns an (mcs, 8) array
+        [num_sample, <m>, <e>, <m^2>, <e^2>, var m, var e, cov(m, e)] per MCS, m and e per site"""
+        out = np.empty((int(mcs), 8), dtype=np.float64)
+        self._call("run_relaxation_stats", int(mcs), int(tot_sample), 1 if random_start else 0, out.ctypes.data_as(P),
+                   argtypes=(i32, i32, i32, P))
+        return out
+
+    def format_relaxation_table(self, stats):
+        """the rows the drivers print (:49-55): nall, num_sample, i, <m>, <e>, <m^2>, <e^2>, N var m, N var e, N cov"""
+        f = _lib.fn("b200mc_format_relaxation_row", C.c_int, i64, i32, P, C.c_char_p, i32)
+        buf = C.create_string_buffer(512)
+        rows = []
+        st = np.ascontiguousarray(stats, dtype=np.float64)
+        for i in range(st.shape[0]):
+            _lib.check(f(self.nall(), i + 1, st[i].ctypes.data_as(P), buf, 512))
+            rows.append(buf.value.decode())
+        return rows
+
     # -- batch of independent samples (one launch per colour pass for all of them) --
     def init_multi(self, *dims_kbt_iseed_nmulti):
         """init(nx, ny[, nz], kbt, iseed) for n_multi samples: init_multi(nx, ny[, nz], kbt, iseed, n_multi)"""

@@ -214,9 +214,16 @@ __device__ __forceinline__ void block_atomic_add_f64(double* dst, double (&v)[NV
 // cos / sin of an angle known to lie in [0, 1] turns (every producer of stored angles keeps them there, and a
 // candidate is a uniform in (0, 1]): sin.approx / cos.approx keep their 2^-20.5 absolute error on [-2 pi, 2 pi], so no
 // range reduction is needed -- 1 FMUL + 2 MUFU (+ the FMUL.RZ inside the approximation).
+// The argument MUFU sees is RZ(RN(t * c) * k) with c = float(2 pi) (+2.8e-8 relative), k = float(1 / 2 pi) (-4.0e-8) and a
+// round-toward-zero product (-3e-8 on average): with the plain constant every angle is evaluated 5.4e-8 (relative) too
+// small, a SYSTEMATIC rotation that adds up over the lattice (sum cos off by -4.9e-8 N; seen as a 4e-5 relative error of M
+// at 1024 x 512).  turns_to_mufu_arg folds the compensation into the multiply: t * (c + 3.1e-7), one rounding.
+#define XY_TWO_PI_HI 6.283185307179586f
+#define XY_TWO_PI_LO 3.1e-7f
+__device__ __forceinline__ float turns_to_mufu_arg(float t) { return fmaf(t, XY_TWO_PI_HI, t * XY_TWO_PI_LO); }
 __device__ __forceinline__ void sincos_unit(float t, float& s, float& c)
 {
-__sincosf(t * 6.283185307179586f, &s, &c);
+    __sincosf(turns_to_mufu_arg(t), &s, &c);
 }
 
 // atan2(y, x) / (2 pi) in [-1/2, 1/2]: octant reduction, q = min / max by MUFU.RCP, odd polynomial q P(q^2)

@@ -33,6 +33,8 @@ struct Ising {
     unsigned long long* acc_target;  // where the fused pass / the measure kernel add their sums (d_acc, or a slot of d_series)
     unsigned long long* d_series;    // run_relaxation: [mcs][2] sums, one slot per MCS
     int64_t series_cap;
+    double* d_stats;                 // run_relaxation_stats: [mcs][10] Kahan sums + compensations
+    int64_t stats_cap;
     int64_t* d_off1;            // colour-1 offsets for the measure kernel
     double* d_randoms;
     unsigned int* d_ticket;
@@ -498,6 +500,7 @@ int launch_pass_randoms(Ising* m, int colour)
 }
 
 int launch_measure(Ising* m, unsigned long long* acc);
+int set_random(Ising* m);
 
 int measure(Ising* m, int64_t* e, int64_t* mag)
 {
@@ -565,11 +568,10 @@ int launch_measure(Ising* m, unsigned long long* acc)
 // (app/ising3d_gpu_relaxation.f90:40-46) without a host round trip per MCS.  Every sweep adds its sums to its
 // own slot of a device series (fused into the second colour pass where the layout allows, else by the measure
 // kernel); one all-reduce (slab mode), one copy and one synchronisation at the end.
-int run_relaxation(Ising* m, int32_t mcs, int64_t* e, int64_t* mag)
+// fills d_series[mcs][n_multi][2] with the per-MCS sums {X, sum s} (all-reduced over the ranks in slab mode); no host copy
+int relaxation_series_device(Ising* m, int32_t mcs)
 {
     const RingGeom& g = m->st.g;
-    if (mcs < 0) ARG_FAIL("mcs < 0");
-    if (mcs == 0) return B200MC_OK;
     const size_t per = 2 * (size_t)m->n_multi;   // sums per MCS: [sample][X, sum s]
     if (m->series_cap < (int64_t)mcs) {
         cudaFree(m->d_series);
@@ -597,8 +599,20 @@ int run_relaxation(Ising* m, int32_t mcs, int64_t* e, int64_t* mag)
     m->acc_target = m->d_acc;
     m->fused_pending = false;
     m->want_fused = false;
+    m->obs_valid = false;
     if (rc) return rc;
     if (g.nranks > 1 && (rc = dist_allreduce_u64(m->st.comm, m->d_series, (int)(per * (size_t)mcs), m->stream))) return rc;
+    return B200MC_OK;
+}
+
+int run_relaxation(Ising* m, int32_t mcs, int64_t* e, int64_t* mag)
+{
+    const RingGeom& g = m->st.g;
+    if (mcs < 0) ARG_FAIL("mcs < 0");
+    if (mcs == 0) return B200MC_OK;
+    const size_t per = 2 * (size_t)m->n_multi;
+    int rc = relaxation_series_device(m, mcs);
+    if (rc) return rc;
     std::vector<unsigned long long> host((size_t)mcs * per);
     CK(cudaMemcpyAsync(host.data(), m->d_series, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
@@ -612,6 +626,82 @@ int run_relaxation(Ising* m, int32_t mcs, int64_t* e, int64_t* mag)
             if (i == mcs - 1) { m->obs_ev[j] = ei; m->obs_mv[j] = mi; }
         }
     m->obs_e = m->obs_ev[0]; m->obs_m = m->obs_mv[0]; m->obs_valid = true;
+    return B200MC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The drivers' whole measurement on the device (app/ising3d_gpu_relaxation.f90:37-55,
+// app/ising2d_gpu_relaxation.f90:33-52):
+//     do sample = 1, tot_sample:  set_allup_spin | set_random_spin
+//        do i = 1, mcs:  update; m = calc_magne_sum; e = calc_energy_sum; order_parameter(i)%add_data(m / N, e / N)
+// `variance_covariance_kahan` is the drivers' external accumulator (fpm.toml:14, osada-yum/Numerical_utilities, not
+// vendored, no version pinned).  Restated here from its use (add_data / num_sample / mean1,2 / square_mean1,2 / var1,2 /
+// cov, app/ising3d_gpu_relaxation.f90:46-55): Kahan-compensated running sums of v1, v2, v1^2, v2^2, v1 v2;
+// mean = sum / n, square_mean = sum of squares / n, var = n / (n - 1) (square_mean - mean^2) (unbiased; 0 for n = 1),
+// cov = n / (n - 1) (mean_v1v2 - mean1 mean2).  One thread per MCS adds the samples of a batch in sample order, so the
+// result does not depend on the batch size; explicit __dadd_rn / __dmul_rn keep the compiler from contracting the
+// compensation away (the CPU oracle is compiled with -ffp-contract=off) -- the two agree bit for bit.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void ising_stats_kernel(const unsigned long long* series, int mcs, int n_multi, long long N, int nnb, double n_inv, double* stats)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= mcs) return;
+    double* st = stats + (size_t)i * 10;
+    double s[5], c[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { s[k] = st[k]; c[k] = st[5 + k]; }
+    for (int j = 0; j < n_multi; ++j) {
+        const long long X = (long long)series[((size_t)i * n_multi + j) * 2], sum = (long long)series[((size_t)i * n_multi + j) * 2 + 1];
+        const long long e = -(long long)(nnb / 2) * N + 2 * X, mg = 2 * sum - N;
+        const double v1 = __dmul_rn((double)mg, n_inv), v2 = __dmul_rn((double)e, n_inv);   // m * n_inv_r64, e * n_inv_r64 (:46)
+        const double x[5] = {v1, v2, __dmul_rn(v1, v1), __dmul_rn(v2, v2), __dmul_rn(v1, v2)};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const double y = __dadd_rn(x[k], -c[k]);
+            const double t = __dadd_rn(s[k], y);
+            c[k] = __dadd_rn(__dadd_rn(t, -s[k]), -y);
+            s[k] = t;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { st[k] = s[k]; st[5 + k] = c[k]; }
+}
+
+int run_relaxation_stats(Ising* m, int32_t mcs, int32_t tot_sample, int32_t random_start, double* out)
+{
+    const RingGeom& g = m->st.g;
+    if (mcs <= 0 || tot_sample <= 0) ARG_FAIL("mcs and tot_sample must be > 0");
+    if (!out) ARG_FAIL("null output");
+    if (tot_sample % m->n_multi) ARG_FAIL("tot_sample (%d) must be a multiple of the batch size n_multi (%d)", tot_sample, m->n_multi);
+    if (m->stats_cap < (int64_t)mcs) {
+        cudaFree(m->d_stats);
+        m->d_stats = nullptr; m->stats_cap = 0;
+        CK(cudaMalloc(&m->d_stats, (size_t)mcs * 10 * sizeof(double)));
+        m->stats_cap = mcs;
+    }
+    CK(cudaMemsetAsync(m->d_stats, 0, (size_t)mcs * 10 * sizeof(double), m->stream));
+    const double n_inv = 1.0 / (double)g.N;   // n_inv_r64 = 1 / real(nx * ny * nz, real64), app/ising3d_gpu_relaxation.f90:11
+    for (int32_t done = 0; done < tot_sample; done += m->n_multi) {
+        int rc = random_start ? set_random(m) : ring_fill(&m->st, 1, m->stream);
+        if (rc) return rc;
+        m->obs_valid = false; m->fused_pending = false;
+        if ((rc = relaxation_series_device(m, mcs))) return rc;
+        COUNT_LAUNCH();
+        ising_stats_kernel<<<(mcs + 127) / 128, 128, 0, m->stream>>>(m->d_series, mcs, m->n_multi, (long long)g.N, g.nnb, n_inv, m->d_stats);
+        CK(cudaGetLastError());
+    }
+    std::vector<double> host((size_t)mcs * 10);
+    CK(cudaMemcpyAsync(host.data(), m->d_stats, host.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    const double n = (double)tot_sample;
+    for (int32_t i = 0; i < mcs; ++i) {
+        const double* s = &host[(size_t)i * 10];
+        double* o = out + (size_t)i * 8;
+        const double mean1 = s[0] / n, mean2 = s[1] / n, sq1 = s[2] / n, sq2 = s[3] / n, m12 = s[4] / n;
+        const double f = tot_sample > 1 ? n / (n - 1.0) : 0.0;
+        o[0] = n; o[1] = mean1; o[2] = mean2; o[3] = sq1; o[4] = sq2;
+        o[5] = f * (sq1 - mean1 * mean1); o[6] = f * (sq2 - mean2 * mean2); o[7] = f * (m12 - mean1 * mean2);
+    }
     return B200MC_OK;
 }
 
@@ -632,7 +722,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     Ising* m = new (std::nothrow) Ising();
     if (!m) ARG_FAIL("out of host memory");
     m->ndim = ndim; m->nx = nx; m->ny = ny; m->nz = ndim == 3 ? nz : 0;
-    m->stream = 0; m->d_acc = nullptr; m->h_acc = nullptr; m->h_acc_pending = false; m->acc_target = nullptr; m->d_series = nullptr; m->series_cap = 0; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
+    m->stream = 0; m->d_acc = nullptr; m->h_acc = nullptr; m->h_acc_pending = false; m->acc_target = nullptr; m->d_series = nullptr; m->series_cap = 0; m->d_stats = nullptr; m->stats_cap = 0; m->d_off1 = nullptr; m->d_randoms = nullptr; m->d_ticket = nullptr;
     { const char* t = getenv("B200MC_TUNE"); m->tune = t ? atoi(t) : 0; t = getenv("B200MC_CHUNK"); m->chunk = t ? atoi(t) : 128; m->chunk = TK_CHUNK;  /* compile-time now */
     }
     m->method = METHOD_METROPOLIS; m->seed = (uint32_t)iseed; m->draw = 0; m->alive = true;
@@ -744,6 +834,7 @@ int destroy(Ising* m)
     cudaFree(m->d_acc);
     cudaFreeHost(m->h_acc);
     cudaFree(m->d_series);
+    cudaFree(m->d_stats);
     cudaFree(m->d_off1);
     cudaFree(m->d_randoms);
     cudaFree(m->d_ticket);
@@ -823,6 +914,16 @@ extern "C" {
 
 const char* b200mc_last_error(void) { return g_b200mc_err; }
 int b200mc_version(void) { return 100; }
+// one row of the drivers' output table (app/ising3d_gpu_relaxation.f90:49-55): nall, num_sample, i, mean1, mean2,
+// square_mean1, square_mean2, nall * var1, nall * var2, nall * cov -- blank-separated like the list-directed '(*(g0, 1x))'
+int b200mc_format_relaxation_row(int64_t nall, int32_t i, const double row[8], char* buf, int32_t buflen)
+{
+    if (!row || !buf || buflen <= 0) ARG_FAIL("null argument");
+    const int n = snprintf(buf, (size_t)buflen, "%lld %lld %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g", (long long)nall, (long long)row[0], (int)i,
+                           row[1], row[2], row[3], row[4], (double)nall * row[5], (double)nall * row[6], (double)nall * row[7]);
+    if (n < 0 || n >= buflen) ARG_FAIL("buffer too small (%d bytes needed)", n + 1);
+    return B200MC_OK;
+}
 unsigned long long b200mc_launch_count(void) { return g_b200mc_launches; }
 
 __global__ void philox_debug_kernel(uint4 c, uint2 k, uint4* out) { *out = philox4x32_10(c, k); }
@@ -855,6 +956,7 @@ int b200mc_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
     int PFX##_calc_magne_sum(void* h, int64_t* m) { CHECK_H(h, ND); return measure(H(h), nullptr, m); } \
     int PFX##_measure(void* h, int64_t* e, int64_t* m) { CHECK_H(h, ND); return measure(H(h), e, m); } \
     int PFX##_run_relaxation(void* h, int32_t mcs, int64_t* e, int64_t* m) { CHECK_H(h, ND); return run_relaxation(H(h), mcs, e, m); } \
+    int PFX##_run_relaxation_stats(void* h, int32_t mcs, int32_t tot_sample, int32_t random_start, double* out) { CHECK_H(h, ND); return run_relaxation_stats(H(h), mcs, tot_sample, random_start, out); } \
     int32_t PFX##_n_multi(void* h) { return h ? H(h)->n_multi : -1; }                              \
     int PFX##_measure_multi(void* h, int64_t* e, int64_t* m) { CHECK_H(h, ND); int rc = measure(H(h), nullptr, nullptr); if (rc) return rc; \
         for (int j = 0; j < H(h)->n_multi; ++j) { if (e) e[j] = H(h)->obs_ev[j]; if (m) m[j] = H(h)->obs_mv[j]; } return B200MC_OK; } \

@@ -49,7 +49,7 @@ __device__ __forceinline__ void sincos_turns(float t, float& s, float& c)
 #else
     const float r = t - __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);
 #endif
-    __sincosf(r * TWO_PI_F, &s, &c);        // MUFU.SIN / MUFU.COS, |x| <= pi
+    __sincosf(turns_to_mufu_arg(r), &s, &c);        // MUFU.SIN / MUFU.COS, |x| <= pi
 }
 
 template <uint32_t TAG>

@@ -73,6 +73,15 @@ int b200mc_ising3d_measure(void* h, int64_t* e, int64_t* m); /* both, one pass *
 /* the drivers' inner loop (app/ising3d_gpu_relaxation.f90:40-46) on the device: mcs x [update; calc_magne_sum;
  * calc_energy_sum]; e[i], m[i] = the sums after MCS i+1 (either may be NULL).  One host synchronisation in all. */
 int b200mc_ising3d_run_relaxation(void* h, int32_t mcs, int64_t* e, int64_t* m);
+/* the drivers' whole measurement (app/ising3d_gpu_relaxation.f90:37-55) on the device: tot_sample x [set_allup_spin (or
+ * set_random_spin when random_start != 0); mcs x (update; calc_magne_sum; calc_energy_sum; add_data(m / N, e / N))] with the
+ * Kahan mean / variance / covariance accumulators of the drivers' `variance_covariance_kahan` kept per MCS on the device
+ * (a batch handle runs n_multi samples per pass; tot_sample must be a multiple of n_multi).  One host synchronisation.
+ * out[8 * i + k], i = 0 .. mcs-1: k = 0 num_sample, 1 mean1 (<m>), 2 mean2 (<e>), 3 square_mean1, 4 square_mean2,
+ * 5 var1, 6 var2, 7 cov (unbiased; the table prints them times nall, :52-54). */
+int b200mc_ising3d_run_relaxation_stats(void* h, int32_t mcs, int32_t tot_sample, int32_t random_start, double* out);
+/* one row of the drivers' output table, :49-55 (columns blank-separated, reals with 17 significant digits) */
+int b200mc_format_relaxation_row(int64_t nall, int32_t i, const double row[8], char* buf, int32_t buflen);
 /* spins(), :232-236: int32 0/1, layout spins(1-nxy : nall+nxy) -> nall + 2 nxy elements */
 int b200mc_ising3d_get_spins(void* h, int32_t* out);
 int b200mc_ising3d_set_spins(void* h, const int32_t* in); /* inverse (halo cells of `in` ignored) */
@@ -170,6 +179,7 @@ int b200mc_ising2d_calc_energy_sum(void* h, int64_t* e); /* :198-212 */
 int b200mc_ising2d_calc_magne_sum(void* h, int64_t* m);  /* :214-228 */
 int b200mc_ising2d_measure(void* h, int64_t* e, int64_t* m);
 int b200mc_ising2d_run_relaxation(void* h, int32_t mcs, int64_t* e, int64_t* m); /* app/ising2d_gpu_relaxation.f90:38-43 */
+int b200mc_ising2d_run_relaxation_stats(void* h, int32_t mcs, int32_t tot_sample, int32_t random_start, double* out); /* :33-52, as for 3D */
 /* spins(), :184-188: int32 +1/-1, layout spins(1-nx : nall+nx) -> nall + 2 nx elements */
 int b200mc_ising2d_get_spins(void* h, int32_t* out);
 int b200mc_ising2d_set_spins(void* h, const int32_t* in);

@@ -251,6 +251,39 @@ ORC_API int64_t orc_ising3d_magne(int64_t nx, int64_t ny, int64_t nz, const int3
 #undef I3
 
 /* ==========================================================================
+ * The drivers' statistics accumulator `variance_covariance_kahan`
+ * (app/ising3d_gpu_relaxation.f90:4,17,36,46-55).  It lives in the external,
+ * un-vendored dependency osada-yum/Numerical_utilities (fpm.toml:14, no
+ * revision pinned), so it is restated from its use: add_data(v1, v2) keeps
+ * Kahan-compensated running sums of v1, v2, v1^2, v2^2, v1 v2; num_sample,
+ * mean1/2 = sum / n, square_mean1/2 = sum of squares / n,
+ * var1/2 = n/(n-1) (square_mean - mean^2), cov = n/(n-1) (mean_v1v2 - mean1 mean2)
+ * (unbiased estimators; 0 for n = 1).  PARITY UNPINNED for the estimator
+ * convention (biased vs unbiased) -- the sums themselves are unambiguous.
+ * st[0..4] = sums, st[5..9] = compensations.
+ * ========================================================================== */
+ORC_API void orc_kahan_add_data(double st[10], double v1, double v2)
+{
+    const double x[5] = {v1, v2, v1 * v1, v2 * v2, v1 * v2};
+    for (int k = 0; k < 5; ++k) {
+        const double y = x[k] - st[5 + k];
+        const double t = st[k] + y;
+        st[5 + k] = (t - st[k]) - y;
+        st[k] = t;
+    }
+}
+
+/* out: num_sample, mean1, mean2, square_mean1, square_mean2, var1, var2, cov */
+ORC_API void orc_kahan_results(const double st[10], int64_t n_sample, double out[8])
+{
+    const double n = (double)n_sample;
+    const double mean1 = st[0] / n, mean2 = st[1] / n, sq1 = st[2] / n, sq2 = st[3] / n, m12 = st[4] / n;
+    const double f = n_sample > 1 ? n / (n - 1.0) : 0.0;
+    out[0] = n; out[1] = mean1; out[2] = mean2; out[3] = sq1; out[4] = sq2;
+    out[5] = f * (sq1 - mean1 * mean1); out[6] = f * (sq2 - mean2 * mean2); out[7] = f * (m12 - mean1 * mean2);
+}
+
+/* ==========================================================================
  * Heat-bath for Ising 2D / 3D.  NOT IN THE REFERENCE: named
  * by the north star only.  Defined here with the reference's conventions:
  *   p_up(S) = 1 / (1 + exp(-2*beta*h)),  h = 2S - z   (z = 4 or 6, S = number

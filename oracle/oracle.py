@@ -74,6 +74,8 @@ def _declare(L):
     d("orc_ising3d_update", None, i64, i64, i64, P, P, P)
     d("orc_ising3d_energy", i64, i64, i64, i64, P, P)
     d("orc_ising3d_magne", i64, i64, i64, i64, P)
+    d("orc_kahan_add_data", None, P, f64, f64)
+    d("orc_kahan_results", None, P, i64, P)
     d("orc_heatbath_table", None, f64, C.c_int, P)
     d("orc_ising2d_update_heatbath", None, i64, i64, P, P, P)
     d("orc_ising3d_update_heatbath", None, i64, i64, i64, P, P, P)
@@ -218,6 +220,25 @@ def xy_init_uniforms(seed: int, draw: int, nx: int, ny: int):
     r = np.empty(nx * ny, dtype=np.float64)
     lib().orc_xy_init_uniforms(seed & 0xFFFFFFFF, draw, nx, ny, _p(r))
     return r
+
+
+# --------------------------------------------------------------------------
+# variance_covariance_kahan (the drivers' accumulator; restated from its use, see oracle.c)
+# --------------------------------------------------------------------------
+class variance_covariance_kahan:
+    def __init__(self):
+        self.st = np.zeros(10, dtype=np.float64)
+        self.n = 0
+
+    def add_data(self, v1, v2):
+        lib().orc_kahan_add_data(_p(self.st), float(v1), float(v2))
+        self.n += 1
+
+    def results(self):
+        """[num_sample, mean1, mean2, square_mean1, square_mean2, var1, var2, cov]"""
+        out = np.empty(8, dtype=np.float64)
+        lib().orc_kahan_results(_p(self.st), self.n, _p(out))
+        return out
 
 
 # --------------------------------------------------------------------------

@@ -344,3 +344,48 @@ def test_full_size_properties_large_lattices():
     g.update_n(2)
     e, m = g.measure()
     assert e < e0 and (e + 3 * n) % 4 == 0
+
+
+@pytest.mark.parametrize("dim,shape,n_multi,random_start", [(3, (31, 31, 30), 1, False), (2, (101, 100), 1, True), (3, (15, 17, 16), 4, False),
+                                                             (2, (255, 256), 2, True)])
+def test_run_relaxation_stats_equals_the_drivers_loop(oracle, dim, shape, n_multi, random_start):
+    """the drivers' whole measurement (app/ising3d_gpu_relaxation.f90:37-55) on the device -- tot_sample x
+    [initial state; mcs x (update; m; e; add_data(m / N, e / N))] with Kahan mean / variance / covariance per MCS -- against
+    the same loop driven on the CPU oracle with the oracle's restatement of variance_covariance_kahan: same operations in
+    the same order, so the eight columns agree to 1e-12 (they are bit-identical unless the compiler contracts differently)."""
+    i2, i3 = _mods()
+    mcs, tot = 5, 8
+    mod, kbt = (i3.ising3d_gpu, KBT3) if dim == 3 else (i2.ising2d_gpu, KBT2)
+    omod = oracle.ising3d_gpu if dim == 3 else oracle.ising2d_gpu
+    g = mod().init_multi(*shape, kbt, 42, n_multi) if n_multi > 1 else mod().init(*shape, kbt, 42)
+    nall = g.nall()
+    stats = g.run_relaxation_stats(mcs, tot, random_start)
+    acc = [oracle.variance_covariance_kahan() for _ in range(mcs)]
+    n_inv = 1.0 / float(nall)
+    os_ = [omod().init(*shape, kbt, 42) for _ in range(n_multi)]
+    draw = 0
+    for batch in range(tot // n_multi):
+        if random_start:
+            for j, o in enumerate(os_):
+                o.set_random_spin(oracle.ring_init_uniforms_rep(42, draw, j, nall))
+            draw += 1
+        else:
+            for o in os_:
+                o.set_allup_spin()
+        for i in range(mcs):
+            for j, o in enumerate(os_):
+                o.update(randoms=oracle.ising_uniforms_rep(42, draw, j, nall))
+                acc[i].add_data(o.calc_magne_sum() * n_inv, o.calc_energy_sum() * n_inv)
+            draw += 1
+    want = np.array([a.results() for a in acc])
+    assert stats.shape == (mcs, 8) and np.all(stats[:, 0] == tot)
+    assert np.allclose(stats, want, rtol=1e-12, atol=1e-15), np.abs(stats - want).max()
+    rows = g.format_relaxation_table(stats)
+    f = rows[2].split()
+    assert len(f) == 10 and int(f[0]) == nall and int(f[1]) == tot and int(f[2]) == 3
+    assert float(f[3]) == stats[2, 1] and float(f[7]) == nall * stats[2, 5]
+    # the handle goes on from where the loop left it
+    g.update()
+    for j, o in enumerate(os_):
+        o.update(randoms=oracle.ising_uniforms_rep(42, draw, j, nall))
+    assert np.array_equal(g.spins_multi(0) if n_multi > 1 else g.spins(), os_[0].spins())

@@ -72,3 +72,29 @@ def test_batched_ising_uniforms(oracle):
     b = oracle.ising_uniforms_rep(42, 3, 1, 4096)
     assert not np.array_equal(a, b) and abs(b.mean() - 0.5) < 0.03
     assert np.array_equal(oracle.ring_init_uniforms(42, 0, 512), oracle.ring_init_uniforms_rep(42, 0, 0, 512))
+
+
+def test_kahan_accumulator_against_exact_sums(oracle):
+    """the drivers' variance_covariance_kahan, restated from its use: against exact rational arithmetic"""
+    from fractions import Fraction
+    rng = np.random.default_rng(3)
+    acc = oracle.variance_covariance_kahan()
+    v1 = 0.5 + 1e-9 * rng.standard_normal(2000)
+    v2 = -1.75 + 1e-7 * rng.standard_normal(2000)
+    for a, b in zip(v1, v2):
+        acc.add_data(a, b)
+    r = acc.results()
+    n = len(v1)
+    f1 = [Fraction(float(a)) for a in v1]
+    f2 = [Fraction(float(b)) for b in v2]
+    m1, m2 = sum(f1) / n, sum(f2) / n
+    assert r[0] == n
+    assert abs(r[1] - float(m1)) <= 2e-16 and abs(r[2] - float(m2)) <= 4e-16
+    assert abs(r[3] - float(sum(a * a for a in f1) / n)) <= 2e-16
+    cov = (sum(a * b for a, b in zip(f1, f2)) / n - m1 * m2) * Fraction(n, n - 1)
+    var1 = (sum(a * a for a in f1) / n - m1 * m1) * Fraction(n, n - 1)
+    # the variance of a nearly constant series is a difference of nearly equal means: absolute accuracy ~ 1 ulp of the square mean
+    assert abs(r[5] - float(var1)) <= 4e-16 and abs(r[7] - float(cov)) <= 1e-15
+    one = oracle.variance_covariance_kahan()
+    one.add_data(0.25, 0.5)
+    assert one.results().tolist() == [1.0, 0.25, 0.5, 0.0625, 0.25, 0.0, 0.0, 0.0]
