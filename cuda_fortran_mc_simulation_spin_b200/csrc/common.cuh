@@ -217,10 +217,16 @@ __device__ __forceinline__ void block_atomic_add_f64(double* dst, double (&v)[NV
 // The argument MUFU sees is RZ(RN(t * c) * k) with c = float(2 pi) (+2.8e-8 relative), k = float(1 / 2 pi) (-4.0e-8) and a
 // round-toward-zero product (-3e-8 on average): with the plain constant every angle is evaluated 5.4e-8 (relative) too
 // small, a SYSTEMATIC rotation that adds up over the lattice (sum cos off by -4.9e-8 N; seen as a 4e-5 relative error of M
-// at 1024 x 512).  turns_to_mufu_arg folds the compensation into the multiply: t * (c + 3.1e-7), one rounding.
+// at 1024 x 512).  turns_to_mufu_arg folds the compensation into the multiply: t * (c + 3.1e-7), one rounding (measured on the
+// device over a uniform grid of 2^24 angles: mean error of cos -3.8e-8 -> -5e-10, tools/probes/sfu_bias.cu).
 #define XY_TWO_PI_HI 6.283185307179586f
 #define XY_TWO_PI_LO 3.1e-7f
 __device__ __forceinline__ float turns_to_mufu_arg(float t) { return fmaf(t, XY_TWO_PI_HI, t * XY_TWO_PI_LO); }
+// the same for an argument centred to [-1/2, 1/2] turns (the measurement kernels): the shrink towards zero is symmetric there
+// and the residual is MUFU's own; measured on the device (tools/probes/sfu_bias.cu, profiles/r02c_sfu_bias.log): mean error of
+// cos +1.8e-8 with the plain constant, -5.3e-8 with + 3.1e-7, zero crossing at + 7.7e-8
+#define XY_TWO_PI_LO_CENTRED 7.7e-8f
+__device__ __forceinline__ float turns_to_mufu_arg_centred(float t) { return fmaf(t, XY_TWO_PI_HI, t * XY_TWO_PI_LO_CENTRED); }
 __device__ __forceinline__ void sincos_unit(float t, float& s, float& c)
 {
     __sincosf(turns_to_mufu_arg(t), &s, &c);

@@ -49,7 +49,7 @@ __device__ __forceinline__ void sincos_turns(float t, float& s, float& c)
 #else
     const float r = t - __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);
 #endif
-    __sincosf(turns_to_mufu_arg(r), &s, &c);        // MUFU.SIN / MUFU.COS, |x| <= pi
+    __sincosf(turns_to_mufu_arg_centred(r), &s, &c);        // MUFU.SIN / MUFU.COS, |x| <= pi
 }
 
 template <uint32_t TAG>
@@ -125,11 +125,13 @@ static_assert(XY_ROWS % 2 == 0, "the strip loop is unrolled by two rows (the nei
 
 // One row of a strip.  P = (y + colour) & 1 at compile time: the x position of colour-compact site xi is 2 xi + P, its
 // same-row neighbours are the other colour's xi - 1 + P and xi + P.
-template <bool OVERRELAX, bool MEASURE, int P>
+// RAGGED = false (nx/2 a multiple of 4, e.g. every benchmark shape): no partial group, no mirror padding -- the strip code
+// of round 1, 64 registers without spills; RAGGED = true adds the per-lane validity tests and the mirror stores.
+template <bool OVERRELAX, bool MEASURE, int P, bool RAGGED>
 __device__ __forceinline__ void xy_strip_row(const XYArgs& a, int y, int idx, float nbl2e, const float4 r_up, const float r_edge, const float4 o,
                                              const XYRow& dn, const XYRow& mid, XYRow& up, float* prow, int xi0, float& es, float& mx, float& my)
 {
-    const int nvalid = a.nxh - xi0;   // >= 4 except in the last group of a row whose nx/2 is not a multiple of 4
+    const int nvalid = RAGGED ? a.nxh - xi0 : 4;   // >= 4 except in the last group of a row whose nx/2 is not a multiple of 4
     sincos_unit(r_up.x, up.s[0], up.c[0]);
     sincos_unit(r_up.y, up.s[1], up.c[1]);
     sincos_unit(r_up.z, up.s[2], up.c[2]);
@@ -190,10 +192,11 @@ __device__ __forceinline__ void xy_strip_row(const XYArgs& a, int y, int idx, fl
 #pragma unroll
         for (int j = 0; j < 4; ++j) if (j < nvalid) { mx += mid.c[j]; my += mid.s[j]; }
     }
-    xy_store_group(prow, xi0, a.nxh, a.pitch, ov);
+    if constexpr (RAGGED) xy_store_group(prow, xi0, a.nxh, a.pitch, ov);
+    else *reinterpret_cast<float4*>(prow + xi0) = make_float4(ov[0], ov[1], ov[2], ov[3]);
 }
 
-template <bool OVERRELAX, bool MEASURE, int COLOUR>
+template <bool OVERRELAX, bool MEASURE, int COLOUR, bool RAGGED>
 __global__ void __launch_bounds__(256, (OVERRELAX || MEASURE) ? XY_MINB_O : XY_MINB_M)
 xy_strip_kernel(const __grid_constant__ XYArgs a)
 {
@@ -204,7 +207,7 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
     if (active) {
         const int rb = tid / a.gpr, g = tid - rb * a.gpr;
         const int y0 = rb * XY_ROWS, y1 = min(y0 + XY_ROWS, a.ny);   // both even (ny is even)
-        const int nxh = a.nxh, xi0 = 4 * g, pitch = a.pitch;
+        const int nxh = a.nxh, xi0 = 4 * g, pitch = RAGGED ? a.pitch : a.nxh;
         const float nbl2e = a.beta * 1.4426950408889634f;
         XYRow dn, mid, up;
         xy_load_row(a, (y0 == 0 && !a.halo) ? a.ny - 1 : y0 - 1, g, dn);
@@ -230,9 +233,9 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
                 const float4 nu0 = ld_up(yn), no0 = ld_own(yn), nu1 = ld_up(yn + 1), no1 = ld_own(yn + 1);
                 const float ne0 = __ldg(a.oth + (size_t)yn * pitch + (COLOUR ? xe1 : xe0));
                 const float ne1 = __ldg(a.oth + (size_t)(yn + 1) * pitch + (COLOUR ? xe0 : xe1));
-                xy_strip_row<OVERRELAX, MEASURE, COLOUR>(a, y, (y + a.yoff) * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR, RAGGED>(a, y, (y + a.yoff) * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
                                                          a.own + (size_t)y * pitch, xi0, es, mx, my);
-                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1>(a, y + 1, (y + 1 + a.yoff) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1, RAGGED>(a, y + 1, (y + 1 + a.yoff) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
                                                              a.own + (size_t)(y + 1) * pitch, xi0, es, mx, my);
                 u0 = nu0; o0 = no0; e0 = ne0; u1 = nu1; o1 = no1; e1 = ne1;
                 // rows rotate by two: (dn, mid, up) <- (up of the first row = mid of the second, up of the second)
@@ -242,12 +245,12 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
             for (int y = y0; y < y1; y += 2) {
                 const float4 u1 = ld_up(y + 1), o1 = ld_own(y + 1);
                 const float e1 = __ldg(a.oth + (size_t)(y + 1) * pitch + (COLOUR ? xe0 : xe1));
-                xy_strip_row<OVERRELAX, MEASURE, COLOUR>(a, y, (y + a.yoff) * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR, RAGGED>(a, y, (y + a.yoff) * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
                                                          a.own + (size_t)y * pitch, xi0, es, mx, my);
                 const int yn = min(y + 2, y1 - 2);
                 u0 = ld_up(yn); o0 = ld_own(yn);
                 e0 = __ldg(a.oth + (size_t)yn * pitch + (COLOUR ? xe1 : xe0));
-                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1>(a, y + 1, (y + 1 + a.yoff) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1, RAGGED>(a, y + 1, (y + 1 + a.yoff) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
                                                              a.own + (size_t)(y + 1) * pitch, xi0, es, mx, my);
                 const XYRow t = mid; mid = dn; dn = up; (void)t;
             }
@@ -526,6 +529,11 @@ int halo_rows(XY* m, int colour)
     return B200MC_OK;
 }
 
+// (the ragged instantiation only for rows with a partial last group / mirror padding)
+#define XY_STRIP_LAUNCH(OVR, MEAS, COL) do { \
+        if (m->pitch != m->nxh) xy_strip_kernel<OVR, MEAS, COL, true><<<(strips + 255) / 256, 256, 0, m->stream>>>(a); \
+        else xy_strip_kernel<OVR, MEAS, COL, false><<<(strips + 255) / 256, 256, 0, m->stream>>>(a); } while (0)
+
 int sweep(XY* m)
 {
     if (m->fused_pending) m->want_fused = false;   // the sums of the previous pass were never asked for
@@ -538,9 +546,9 @@ int sweep(XY* m)
         if (fuse) CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
         COUNT_LAUNCH();
         if (colour) {
-            if (fuse) xy_strip_kernel<false, true, 1><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
-            else xy_strip_kernel<false, false, 1><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
-        } else xy_strip_kernel<false, false, 0><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);   // (sums are fused into colour 1 only)
+            if (fuse) XY_STRIP_LAUNCH(false, true, 1);
+            else XY_STRIP_LAUNCH(false, false, 1);
+        } else XY_STRIP_LAUNCH(false, false, 0);   // (sums are fused into colour 1 only)
         CK(cudaGetLastError());
         { int rch = halo_rows(m, colour); if (rch) return rch; }
         if (fuse) m->fused_pending = true;
@@ -592,9 +600,9 @@ int over_relax(XY* m, int n_steps)
             if (fuse) CK(cudaMemsetAsync(m->d_acc, 0, 3 * sizeof(double), m->stream));
             COUNT_LAUNCH();
             if (colour) {
-                if (fuse) xy_strip_kernel<true, true, 1><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
-                else xy_strip_kernel<true, false, 1><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
-            } else xy_strip_kernel<true, false, 0><<<(strips + 255) / 256, 256, 0, m->stream>>>(a);
+                if (fuse) XY_STRIP_LAUNCH(true, true, 1);
+                else XY_STRIP_LAUNCH(true, false, 1);
+            } else XY_STRIP_LAUNCH(true, false, 0);
             CK(cudaGetLastError());
             { int rch = halo_rows(m, colour); if (rch) return rch; }
             if (fuse) m->fused_pending = true;

@@ -33,7 +33,7 @@ struct XYHArgs {
 __device__ __forceinline__ void sincos_turns(float t, float& s, float& c)
 {
     const float r = t - rintf(t);
-    __sincosf(turns_to_mufu_arg(r), &s, &c);
+    __sincosf(turns_to_mufu_arg_centred(r), &s, &c);
 }
 
 template <uint32_t TAG>
