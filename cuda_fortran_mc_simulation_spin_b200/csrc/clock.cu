@@ -85,8 +85,10 @@ int build_tables(Clock* m)
 #undef ET
     thr.resize(CLOCK_MAX_CLASSES, 0);
     if (m->d_thr16) {
+        // direct table T[next][F] = thr >> 17 (0 .. 32768), F = up + q down + q^2 left + q^3 right + q^4 cur: the same order as
+        // the class table (index = F + q^5 next)
         std::vector<uint16_t> t16(q6);
-        for (size_t i = 0; i < q6; ++i) { const uint64_t hi = thr[cls[i]] >> 16; t16[i] = (uint16_t)(hi > 65535u ? 65535u : hi); }
+        for (size_t i = 0; i < q6; ++i) t16[i] = (uint16_t)(thr[cls[i]] >> 17);
         CK(cudaMemcpyAsync(m->d_thr16, t16.data(), q6 * sizeof(uint16_t), cudaMemcpyHostToDevice, m->stream));
         CK(cudaStreamSynchronize(m->stream));
     }
@@ -125,7 +127,8 @@ int sweep(Clock* m)
             ClockArgs a;
             fill_args(m, j, colour, &a);
             COUNT_LAUNCH();
-            if (m->direct) clock_pass_direct_kernel<<<m->grid_direct, CLOCK_DIRECT_THREADS, m->smem_direct, m->stream>>>(a);
+            if (m->direct && m->q == 6) clock_pass_direct_kernel<6><<<m->grid_direct, CLOCK_DIRECT_THREADS, m->smem_direct, m->stream>>>(a);
+            else if (m->direct) clock_pass_direct_kernel<0><<<m->grid_direct, CLOCK_DIRECT_THREADS, m->smem_direct, m->stream>>>(a);
             else clock_pass_kernel<<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
             CK(cudaGetLastError());
             int rc = ring_halo(&m->st[j], colour, m->stream);
@@ -243,14 +246,16 @@ int create(void** out, int64_t nx, int64_t ny, double kbt, int32_t q, int32_t n_
     if (occ < 1) occ = 1;
     const int64_t need = (g.L + 255) / 256;
     m->grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);
-    {   // direct lookup: 2 q^6 bytes of thresholds in shared memory, byte-parallel index (needs q^2 <= 255)
-        const size_t wantd = (2 * q6 + 15) / 16 * 16;
+    {   // direct lookup (q <= 6: q^3 < 256 for the byte-parallel index): 2 q^6 bytes of thresholds + one slab of padding in shared memory
+        const size_t q5 = q6 / q;
+        const size_t wantd = CLK_WIN_BYTES + (2 * (q6 + q5) + 15) / 16 * 16;
         const char* t = getenv("B200MC_CLOCK_DIRECT");
         int occd = 0;
-        if (q * q <= 255 && wantd <= (size_t)maxsm && !(t && atoi(t) == 0) &&
-            cudaFuncSetAttribute(clock_pass_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wantd) == cudaSuccess &&
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, clock_pass_direct_kernel, CLOCK_DIRECT_THREADS, wantd) == cudaSuccess && occd >= 1 &&
-            cudaMalloc(&m->d_thr16, wantd) == cudaSuccess) {
+        if (q <= 6 && wantd <= (size_t)maxsm && !(t && atoi(t) == 0) &&
+            cudaFuncSetAttribute(clock_pass_direct_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wantd) == cudaSuccess &&
+            cudaFuncSetAttribute(clock_pass_direct_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wantd) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, clock_pass_direct_kernel<0>, CLOCK_DIRECT_THREADS, wantd) == cudaSuccess && occd >= 1 &&
+            cudaMalloc(&m->d_thr16, (2 * q6 + 15) / 16 * 16) == cudaSuccess) {
             m->direct = 1; m->smem_direct = (int)wantd;
             const int64_t needd = (g.L + CLOCK_DIRECT_THREADS - 1) / CLOCK_DIRECT_THREADS;
             m->grid_direct = (int)(needd < (int64_t)sms * occd ? needd : (int64_t)sms * occd);

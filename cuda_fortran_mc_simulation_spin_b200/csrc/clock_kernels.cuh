@@ -12,6 +12,7 @@
 #pragma once
 #include "common.cuh"
 #include "ising_kernels.cuh"  // RingPassArgs, philox_rk
+#include "clock_word.cuh"
 
 #define CLOCK_MAX_CLASSES 256
 
@@ -43,11 +44,42 @@ struct ClockArgs {
     uint32_t rk0[10];          // Philox round keys: seed + r W0
     uint32_t rk1[10];          //                    TAG_CLOCK + replica + r W1
     int cls_in_smem;           // class table fits in shared memory
-    const uint16_t* thr16;     // direct lookup (q <= 6): min(thr >> 16, 65535) per table index
+    const uint16_t* thr16;     // direct lookup (q <= 6): T[next][F] = thr >> 17, F = up + q down + q^2 left + q^3 right + q^4 cur
 };
 
-// accept iff U_r < thr[class]; proposal next = min(floor((U_p + 1) q / 2^32), q - 1)
+// exact (32-bit) evaluation of the four sites of word w of vector pglob: both Philox blocks (RNG contract v2,
+// clock_word.cuh), class table, full 33-bit threshold.
+// accept iff U_a < thr[class]; proposal next = min(floor((U_p + 1) q / 2^32), q - 1)
 // (floor(next_states * q), src/clock_gpu_m.f90:211, with the u == 1 clamp of SURVEY Q4)
+__device__ __forceinline__ uint32_t clock_word_exact_body(const ClockArgs& a, const uint8_t* cls, const uint64_t* thr, uint64_t pglob, int w,
+                                                          uint32_t ow, uint32_t uw, uint32_t dw, uint32_t lw, uint32_t rw)
+{
+    const RingPassArgs& r = a.r;
+    const uint4 R = philox_rk2(mk_ctr(pglob, r.draw, r.colour, (uint32_t)w), a.rk0, a.rk1);
+    const uint4 R2 = philox_rk2(mk_ctr(pglob, r.draw, r.colour, 4u + (uint32_t)w), a.rk0, a.rk1);
+    const uint32_t q = a.q, q2 = q * q, q3 = q2 * q, q4 = q3 * q, q5 = q4 * q;
+    uint32_t res = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        uint32_t Ua, Up;
+        clk_uniforms(R, R2, e, Ua, Up);
+        const int sh = 8 * e;
+        const uint32_t cur = (ow >> sh) & 0xFFu;
+        uint32_t nxt = (uint32_t)((((unsigned long long)Up + 1ull) * q) >> 32);
+        nxt = min(nxt, q - 1);
+        const uint32_t idx = ((uw >> sh) & 0xFFu) + q * ((dw >> sh) & 0xFFu) + q2 * ((lw >> sh) & 0xFFu) +
+                             q3 * ((rw >> sh) & 0xFFu) + q4 * cur + q5 * nxt;
+        const uint64_t t = thr[cls[idx]];
+        res |= (((unsigned long long)Ua < t) ? nxt : cur) << sh;
+    }
+    return res;
+}
+__device__ __noinline__ uint32_t clock_word_exact(const ClockArgs& a, uint64_t pglob, int w, uint32_t ow, uint32_t uw, uint32_t dw, uint32_t lw, uint32_t rw)
+{
+    return clock_word_exact_body(a, a.cls, a.thr, pglob, w, ow, uw, dw, lw, rw);
+}
+
+// class-table pass (any q <= 16): every site with its full 32-bit uniforms, class ids from shared memory (q <= 7) or L1/L2
 __global__ void __launch_bounds__(256)
 clock_pass_kernel(const __grid_constant__ ClockArgs a)
 {
@@ -67,7 +99,6 @@ clock_pass_kernel(const __grid_constant__ ClockArgs a)
     uint4* own = r.own + r.H;
     const uint4* oth = r.oth + r.H;
     const int nvec = (int)r.nvec;
-    const uint32_t q = a.q, q2 = q * q, q3 = q2 * q, q4 = q3 * q, q5 = q4 * q;
     const int stride = gridDim.x * blockDim.x;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
         const uint4 o = own[v];
@@ -75,59 +106,40 @@ clock_pass_kernel(const __grid_constant__ ClockArgs a)
         const uint4 nr = ld_other(oth + v + (int)r.off[1]);   // i+1  right
         const uint4 nu = ld_other(oth + v + (int)r.off[2]);   // i+nx up
         const uint4 nd = ld_other(oth + v + (int)r.off[3]);   // i-nx down
-        const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, lw[4] = {nl.x, nl.y, nl.z, nl.w}, rw[4] = {nr.x, nr.y, nr.z, nr.w},
-                       uw[4] = {nu.x, nu.y, nu.z, nu.w}, dw[4] = {nd.x, nd.y, nd.z, nd.w};
-        uint32_t res[4];
         const uint64_t pglob = (uint64_t)(r.p0 + v);
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            uint32_t outw = 0;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                // lanes 4w + 2 half and 4w + 2 half + 1 share one Philox block (sub = lane >> 1)
-                const uint4 R = philox_rk2(mk_ctr(pglob, r.draw, r.colour, (uint32_t)(2 * w + half)), a.rk0, a.rk1);
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int sh = 8 * (2 * half + e);
-                    const uint32_t Ur = e ? R.z : R.x, Up = e ? R.w : R.y;
-                    const uint32_t cur = (ow[w] >> sh) & 0xFFu;
-                    uint32_t nxt = (uint32_t)((((unsigned long long)Up + 1ull) * q) >> 32);
-                    nxt = min(nxt, q - 1);
-                    const uint32_t idx = ((uw[w] >> sh) & 0xFFu) + q * ((dw[w] >> sh) & 0xFFu) + q2 * ((lw[w] >> sh) & 0xFFu) +
-                                         q3 * ((rw[w] >> sh) & 0xFFu) + q4 * cur + q5 * nxt;
-                    const uint64_t thr = sthr[cls[idx]];
-                    const uint32_t ns = ((unsigned long long)Ur < thr) ? nxt : cur;
-                    outw |= ns << sh;
-                }
-            }
-            res[w] = outw;
-        }
-        own[v] = make_uint4(res[0], res[1], res[2], res[3]);
+        uint4 res;
+        res.x = clock_word_exact_body(a, cls, sthr, pglob, 0, o.x, nu.x, nd.x, nl.x, nr.x);
+        res.y = clock_word_exact_body(a, cls, sthr, pglob, 1, o.y, nu.y, nd.y, nl.y, nr.y);
+        res.z = clock_word_exact_body(a, cls, sthr, pglob, 2, o.z, nu.z, nd.z, nl.z, nr.z);
+        res.w = clock_word_exact_body(a, cls, sthr, pglob, 3, o.w, nu.w, nd.w, nl.w, nr.w);
+        own[v] = res;
     }
 }
 
-// Direct-table variant (2 q^6 bytes fit in shared memory: q <= 6; one CLOCK_DIRECT_THREADS-thread block per SM).
-// Same update, fewer instructions: the table index is built byte-parallel (A = up + q down, B = left + q right in
-// bytes, A + q^2 B in 16-bit fields, 4 sites per instruction), and the acceptance test is ONE shared-memory load of
-// the threshold's high 16 bits; a site whose 16 high uniform bits equal that entry (capped at 65535) is decided
-// exactly afterwards from the class table and the full 33-bit threshold.
+// Direct-table variant (q <= 6; one CLOCK_DIRECT_THREADS-thread block per SM): clock_word.cuh.  Shared memory:
+// CLK_WIN_BYTES (proposal window), then T[next][F] (q slabs of 2 q^5 bytes + one slab of padding, read by a proposal that
+// is redone as a tie).  Q = q at compile time (0: run time).
 #define CLOCK_DIRECT_THREADS 768
+template <int Q>
 __global__ void __launch_bounds__(CLOCK_DIRECT_THREADS, 1)
 clock_pass_direct_kernel(const __grid_constant__ ClockArgs a)
 {
     extern __shared__ __align__(16) uint8_t sm[];
+    uint8_t* tab = sm + CLK_WIN_BYTES;
+    const uint32_t q = Q ? (uint32_t)Q : a.q;
+    clk_win64_store(sm, (unsigned long long)(q << 16));
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.thr16);
-        uint4* dst = reinterpret_cast<uint4*>(sm);
+        uint4* dst = reinterpret_cast<uint4*>(tab);
         for (uint32_t i = threadIdx.x; i < (2u * a.tab_bytes + 15) / 16; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const uint32_t tab = (uint32_t)__cvta_generic_to_shared(sm);
+    const unsigned long long win = clk_win64(sm);
     const RingPassArgs& r = a.r;
     uint4* own = r.own + r.H;
     const uint4* oth = r.oth + r.H;
     const int nvec = (int)r.nvec;
-    const uint32_t q = a.q, q2 = q * q, q4 = q2 * q2, q5 = q4 * q;
+    const uint32_t kstride = Q ? 2u * Q * Q * Q * Q * Q : 2u * (a.tab_bytes / a.q), lim = q << 17;
     const int stride = gridDim.x * blockDim.x;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
         const uint4 o = own[v];
@@ -137,56 +149,21 @@ clock_pass_direct_kernel(const __grid_constant__ ClockArgs a)
         const uint4 nd = ld_other(oth + v + (int)r.off[3]);   // i-nx down
         const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, lw[4] = {nl.x, nl.y, nl.z, nl.w}, rw[4] = {nr.x, nr.y, nr.z, nr.w},
                        uw[4] = {nu.x, nu.y, nu.z, nu.w}, dw[4] = {nd.x, nd.y, nd.z, nd.w};
-        uint32_t res[4];
-        uint32_t ties = 0;
+        uint32_t res[4], am[4], pn[4];
         const uint64_t pglob = (uint64_t)(r.p0 + v);
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-            const uint32_t A = uw[w] + q * dw[w], B = lw[w] + q * rw[w];                   // bytes < q^2
-            const uint32_t ABe = (A & 0x00FF00FFu) + q2 * (B & 0x00FF00FFu);               // sites 0, 2 of the word (< q^4)
-            const uint32_t ABo = ((A >> 8) & 0x00FF00FFu) + q2 * ((B >> 8) & 0x00FF00FFu); // sites 1, 3
-            uint32_t outw = 0;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                // lanes 4w + 2 half and 4w + 2 half + 1 share one Philox block (sub = lane >> 1)
-                const uint4 R = philox_rk2(mk_ctr(pglob, r.draw, r.colour, (uint32_t)(2 * w + half)), a.rk0, a.rk1);
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int bi = 2 * half + e, sh = 8 * bi;
-                    const uint32_t Ur = e ? R.z : R.x, Up = e ? R.w : R.y;
-                    const uint32_t cur = (ow[w] >> sh) & 0xFFu;
-                    uint32_t nxt = (uint32_t)((((unsigned long long)Up + 1ull) * q) >> 32);
-                    nxt = min(nxt, q - 1);
-                    const uint32_t ab = (((bi & 1) ? ABo : ABe) >> (16 * (bi >> 1))) & 0xFFFFu;
-                    const uint32_t idx = ab + q4 * cur + q5 * nxt;
-                    uint32_t th;
-                    asm("ld.shared.u16 %0, [%1];" : "=r"(th) : "r"(tab + 2u * idx));
-                    const uint32_t ha = Ur >> 16;
-                    outw |= (ha < th ? nxt : cur) << sh;
-                    if (ha == th) ties |= 1u << (4 * w + bi);
-                }
-            }
-            res[w] = outw;
+            uint32_t Fe, Fo;
+            clk_index_fields(uw[w], dw[w], lw[w], rw[w], ow[w], q, Fe, Fo);
+            const uint4 R = philox_rk2(mk_ctr(pglob, r.draw, r.colour, (uint32_t)w), a.rk0, a.rk1);
+            res[w] = clk_word_fast<false>(ow[w], Fe, Fo, R, tab, kstride, q, win, q, am[w], pn[w]);
         }
-        while (ties) {   // rare (2^-16 per site): the full threshold decides
-            const int j = __ffs(ties) - 1;
-            ties &= ties - 1;
-            const int w = j >> 2, bi = j & 3, sh = 8 * bi;
-            const uint4 R = philox_rk2(mk_ctr(pglob, r.draw, r.colour, (uint32_t)(2 * w + (bi >> 1))), a.rk0, a.rk1);
-            const uint32_t Ur = (bi & 1) ? R.z : R.x, Up = (bi & 1) ? R.w : R.y;
-            uint32_t owj = 0, lj = 0, rj = 0, uj = 0, dj = 0;
+        const uint32_t amin = __vimin3_s16x2(__vmins2(am[0], am[1]), am[2], am[3]);
+        const uint32_t pmin = __vimin3_u32(min(pn[0], pn[1]), pn[2], pn[3]);
+        if (pmin < lim || clk_accept_tie(amin)) {   // rare: redo the words with an undecided site exactly
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-                if (t == w) { owj = ow[t]; lj = lw[t]; rj = rw[t]; uj = uw[t]; dj = dw[t]; }
-            const uint32_t cur = (owj >> sh) & 0xFFu;
-            uint32_t nxt = (uint32_t)((((unsigned long long)Up + 1ull) * q) >> 32);
-            nxt = min(nxt, q - 1);
-            const uint32_t idx = ((uj >> sh) & 0xFFu) + q * ((dj >> sh) & 0xFFu) + q2 * ((lj >> sh) & 0xFFu) + q2 * q * ((rj >> sh) & 0xFFu) + q4 * cur + q5 * nxt;
-            const uint64_t thr = a.thr[a.cls[idx]];
-            const uint32_t ns = ((unsigned long long)Ur < thr) ? nxt : cur;
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-                if (t == w) res[t] = (res[t] & ~(0xFFu << sh)) | (ns << sh);
+            for (int w = 0; w < 4; ++w)
+                if (pn[w] < lim || clk_accept_tie(am[w])) res[w] = clock_word_exact(a, pglob, w, ow[w], uw[w], dw[w], lw[w], rw[w]);
         }
         own[v] = make_uint4(res[0], res[1], res[2], res[3]);
     }

@@ -14,14 +14,15 @@
 // periodic wrap is index arithmetic (no halo).  Pad bytes (xi >= nx/2) always hold valid states
 // and are masked out of the observables.
 //
-// RNG contract (CPU restatement: oracle/rng_contract.c, orc_torus_uniforms).  Site j = xi & 15
-// of vector v = xi >> 4 of row y0: block = y0 * nvr + v,
-//   W  = philox(ctr(block, draw, colour,     j >> 2), (seed, TAG_TORUS + replica))[j & 3]
-//   W2 = philox(ctr(block, draw, colour, 4 + (j >> 2)), same key)[j & 3]
-//   accept   U_a = (W & 0xFFFF0000) | (W2 >> 16)        -> rnds(2, x, y) = (U_a + 1) 2^-32
-//   proposal U_p = (W << 16)        | (W2 & 0xFFFF)     -> rnds(1, x, y) = (U_p + 1) 2^-32
-// W2 is only evaluated when the 16 bits of W do not decide (about 5 sites in 65536), so the
-// hot loop costs one Philox block per 4 sites and is still exact at 32-bit resolution:
+// RNG contract (v2; CPU restatement: oracle/rng_contract.c, orc_torus_uniforms; bit assignment:
+// clock_word.cuh).  Site j = xi & 15 of vector v = xi >> 4 of row y0: block = y0 * nvr + v, word
+// w = j >> 2, e = j & 3,
+//   R  = philox(ctr(block, draw, colour,     w), (seed, TAG_TORUS + replica))
+//   R2 = philox(ctr(block, draw, colour, 4 + w), same key)
+//   accept   U_a from the half-words half(R[e & 1], e >> 1), half(R2[e & 1], e >> 1)       -> rnds(2, x, y)
+//   proposal U_p from the half-words half(R[2 + (e & 1)], e >> 1), half(R2[2 + (e & 1)], ..) -> rnds(1, x, y)
+// R2 is only evaluated when the first look (15 accept bits, 16 proposal bits) does not decide, so
+// the hot loop costs one Philox block per 4 sites and is still exact at 32-bit resolution:
 //   new = c + ceiling(rnds1 (q-1))  (:142)   <=>  k = ceil((U_p + 1)(q-1) / 2^32)
 //   rnds2 <= prob                  (:146)   <=>  U_a < thr = floor(prob 2^32)
 #include <math.h>
@@ -31,6 +32,7 @@
 #include <vector>
 #include "../../include/b200mc.h"
 #include "common.cuh"
+#include "clock_word.cuh"
 
 namespace {
 
@@ -47,8 +49,8 @@ struct SixArgs {
     const uint8_t* cls;      // q^6 class ids: c + q(new + q(r + q(u + q(l + q d))))   (states_to_prob index order, :72-80)
     const uint32_t* thi;     // per class: thr >> 16  (0 .. 65536)
     const uint32_t* tlo;     // per class: thr & 0xFFFF
-    const uint16_t* thr16;   // q^6 entries min(thr >> 16, 65535) (direct lookup, q <= 6)
-    uint32_t tab_bytes;
+    const uint16_t* thr16;   // direct lookup (q <= 6): T[k][F] = thr >> 17, k = 0 .. q-2 (new = c + 1 + k mod q), F = r + q u + q^2 l + q^3 d + q^4 c
+    uint32_t tab_bytes, q5;
     int cls_in_smem;
     uint64_t draw;
     uint32_t rk0[10];        // Philox round keys seed + r W0
@@ -81,24 +83,24 @@ __device__ __forceinline__ uint32_t word_of(const uint4& v, int w) { return w ==
 __device__ __forceinline__ uint32_t byte_of(const uint4& v, int j) { return (word_of(v, j >> 2) >> (8 * (j & 3))) & 0xFFu; }
 
 // the other colour's same-row values one compact position to the left (p == 0: x0 - 1) or to
-// the right (p == 1: x0 + 1) of the 16 sites of vector v, periodic in x
-__device__ __forceinline__ uint4 six_shifted(const uint8_t* row, const uint4& b, int v, int nvr, int nxh, int p)
+// the right (p == 1: x0 + 1) of the 16 sites of vector v, periodic in x.  pv = address of vector v of the row.
+__device__ __forceinline__ uint4 six_shifted(const uint8_t* pv, const uint4& b, int v, int nvr, int nxh, int p)
 {
     uint4 s;
     if (p == 0) {
-        const uint32_t e = ldg_u8(row + (v == 0 ? nxh - 1 : 16 * v - 1));
+        const uint32_t e = ldg_u8(pv + (v == 0 ? nxh - 1 : -1));
         s.x = (b.x << 8) | e;
         s.y = __funnelshift_l(b.x, b.y, 8);
         s.z = __funnelshift_l(b.y, b.z, 8);
         s.w = __funnelshift_l(b.z, b.w, 8);
     } else {
         const bool last = v == nvr - 1;
-        const uint32_t e = ldg_u8(row + (last ? 0 : 16 * v + 16));
+        const uint32_t e = ldg_u8(pv + (last ? -16 * v : 16));
         s.x = __funnelshift_r(b.x, b.y, 8);
         s.y = __funnelshift_r(b.y, b.z, 8);
         s.z = __funnelshift_r(b.z, b.w, 8);
         s.w = (b.w >> 8) | (e << 24);
-        if (last) {  // the row's last site sits at local position lp (< 15 when the row is padded)
+        if (last && (nxh & 15)) {  // the row's last site sits at local position lp < 15 (padded row)
             const int lp = nxh - 1 - 16 * v, wi = lp >> 2, sh = 8 * (lp & 3);
             const uint32_t keep = ~(0xFFu << sh), ins = e << sh;
             if (wi == 0) s.x = (s.x & keep) | ins;
@@ -110,122 +112,158 @@ __device__ __forceinline__ uint4 six_shifted(const uint8_t* row, const uint4& b,
     return s;
 }
 
-// exact (32-bit) evaluation of one site: second Philox block for the low halves
-__device__ __noinline__ uint32_t six_site_exact(const SixArgs& a, const uint8_t* cls, uint32_t W, uint32_t blk, uint32_t k1,
-                                                int j, uint32_t c, uint32_t r, uint32_t u, uint32_t l, uint32_t d)
+// exact (32-bit) evaluation of the four sites of word w of a vector: both Philox blocks, class table, full 33-bit threshold
+__device__ __noinline__ uint32_t six_word_exact(const SixArgs& a, uint32_t blk, uint32_t k1, int w,
+                                                uint32_t ow, uint32_t rt, uint32_t up, uint32_t lf, uint32_t dn)
 {
-    const uint4 R2 = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, 4u + (uint32_t)(j >> 2)), a.rk0, k1);
-    const uint32_t W2 = word_of(R2, j & 3);
-    const uint32_t Ua = (W & 0xFFFF0000u) | (W2 >> 16);
-    const uint32_t Up = (W << 16) | (W2 & 0xFFFFu);
+    const uint4 R = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, (uint32_t)w), a.rk0, k1);
+    const uint4 R2 = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, 4u + (uint32_t)w), a.rk0, k1);
     const uint32_t q = a.q;
-    const uint32_t k = (uint32_t)((((unsigned long long)Up + 1ull) * (q - 1) + 0xFFFFFFFFull) >> 32);
-    uint32_t nw = c + k;
-    if (nw >= q) nw -= q;
-    const uint32_t idx = c + q * (nw + q * (r + q * (u + q * (l + q * d))));
-    const uint32_t cl = cls[idx];
-    const unsigned long long thr = ((unsigned long long)a.thi[cl] << 16) | a.tlo[cl];
-    return ((unsigned long long)Ua < thr) ? nw : c;
+    uint32_t res = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        uint32_t Ua, Up;
+        clk_uniforms(R, R2, e, Ua, Up);
+        const uint32_t c = (ow >> (8 * e)) & 0xFFu, r = (rt >> (8 * e)) & 0xFFu, u = (up >> (8 * e)) & 0xFFu,
+                       l = (lf >> (8 * e)) & 0xFFu, d = (dn >> (8 * e)) & 0xFFu;
+        const uint32_t k = (uint32_t)((((unsigned long long)Up + 1ull) * (q - 1) + 0xFFFFFFFFull) >> 32);   // ceiling(rnds1 (q - 1)), :142
+        uint32_t nw = c + k;
+        if (nw >= q) nw -= q;
+        const uint32_t idx = c + q * (nw + q * (r + q * (u + q * (l + q * d))));
+        const uint32_t cl = a.cls[idx];
+        const unsigned long long thr = ((unsigned long long)a.thi[cl] << 16) | a.tlo[cl];
+        res |= (((unsigned long long)Ua < thr) ? nw : c) << (8 * e);
+    }
+    return res;
 }
 
 // update_sub, src/clock/clock_tableall_gpu_m.f90:107-152 (dual lattice: :110-155), one colour
 #ifndef SIX_MINB
 #define SIX_MINB 3
 #endif
-// Acceptance lookup.  DIRECT = false: q^6 one-byte class ids (shared or global memory) + per-class thresholds in shared
-// memory: two dependent loads per site.  DIRECT = true (2 q^6 bytes fit in shared memory: q <= 6): the high 16 bits of
-// every threshold, capped at 65535, in ONE shared-memory table -- one load per site; a capped or equal entry compares
-// as a tie and goes through the exact path like every other undecided site.
+// Acceptance lookup.  Class path (any q <= 12): q^6 one-byte class ids (shared or global memory) + per-class thresholds in
+// shared memory, two dependent loads per site, scalar per-site code.  Direct path (q <= 6, default): clock_word.cuh.
 struct SixSmem {
-    uint32_t cls_addr;        // shared-window address of the class table / the direct u16 table
+    uint32_t cls_addr;        // shared-window address of the class table
     const uint32_t* sthi;
     const uint8_t* gcls;
 };
 
-// one vector = 16 sites of row (rep, y) at compact position 16 v .. 16 v + 15.  P = (y + colour) & 1: the x position of
-// compact site xi is 2 xi + P; right = x0 + 1, left = x0 - 1.
-template <bool SMEM, bool DIRECT, int P>
-__device__ __forceinline__ void six_vector(const SixArgs& a, const SixSmem& sm, int Y, int y, int rep, int v)
+struct SixRows { uint4 o, rt, up, lf, dn; uint4* po; uint32_t k1, blk; };
+
+// loads of one vector = 16 sites of row (rep, y) at compact position 16 v .. 16 v + 15; idx = (rep ny + y) nvr + v is its
+// linear index in both colour arrays (rows are nvr vectors long).  P = (y + colour) & 1: the x position of compact site
+// xi is 2 xi + P; right = x0 + 1, left = x0 - 1.
+template <int P>
+__device__ __forceinline__ void six_load(const SixArgs& a, int idx, int y, int rep, int v, SixRows& n)
+{
+    const int nvr = a.nvr, ny = a.ny;
+    const int wrap = (ny - 1) * nvr;
+    const int du = (y + 1 == ny) ? -wrap : nvr, dd = (y == 0) ? wrap : -nvr;
+    const uint4* pv = reinterpret_cast<const uint4*>(a.oth) + idx;
+    n.po = reinterpret_cast<uint4*>(a.own) + idx;
+    n.o = *n.po;
+    const uint4 b = ld_other(pv);
+    n.up = ld_other(pv + du);
+    n.dn = ld_other(pv + dd);
+    const uint4 s = six_shifted(reinterpret_cast<const uint8_t*>(pv), b, v, nvr, a.nxh, P);
+    n.rt = P ? s : b; n.lf = P ? b : s;
+    n.k1 = TAG_TORUS + a.sample0 + (uint32_t)rep;
+    n.blk = (uint32_t)(y * nvr + v);
+}
+
+template <bool SMEM, int P>
+__device__ __forceinline__ void six_vector(const SixArgs& a, const SixSmem& sm, int idx, int y, int rep, int v)
 {
     const uint32_t q = a.q, qm1 = q - 1, q2 = q * q;
     const uint32_t tie_lim = 65537u - qm1;
-    const int nvr = a.nvr, ny = a.ny;
-    const size_t pitch = (size_t)nvr * 16;
-    const int Yu = (y + 1 == ny) ? Y + 1 - ny : Y + 1, Yd = (y == 0) ? Y + ny - 1 : Y - 1;
-    const uint8_t* row = a.oth + (size_t)Y * pitch;
-    uint4* po = reinterpret_cast<uint4*>(a.own + (size_t)Y * pitch) + v;
-    const uint4 o = *po;
-    const uint4 b = ld_other(reinterpret_cast<const uint4*>(row) + v);
-    const uint4 up = ld_other(reinterpret_cast<const uint4*>(a.oth + (size_t)Yu * pitch) + v);
-    const uint4 dn = ld_other(reinterpret_cast<const uint4*>(a.oth + (size_t)Yd * pitch) + v);
-    const uint4 s = six_shifted(row, b, v, nvr, a.nxh, P);
-    const uint4 rt = P ? s : b, lf = P ? b : s;
-    const uint32_t k1 = TAG_TORUS + a.sample0 + (uint32_t)rep;
-    const uint32_t blk = (uint32_t)(y * nvr + v);
+    SixRows n;
+    six_load<P>(a, idx, y, rep, v, n);
     uint32_t outw[4];
     uint32_t ties = 0;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-        const uint32_t ow = word_of(o, w);
-        // byte-parallel partial indices: A = r + q u, B = l + q d (< q^2 <= 225)
-        const uint32_t A = word_of(rt, w) + q * word_of(up, w);
-        const uint32_t B = word_of(lf, w) + q * word_of(dn, w);
+        const uint32_t ow = word_of(n.o, w);
+        // byte-parallel partial indices: A = r + q u, B = l + q d (< q^2 <= 144)
+        const uint32_t A = word_of(n.rt, w) + q * word_of(n.up, w);
+        const uint32_t B = word_of(n.lf, w) + q * word_of(n.dn, w);
         // AB = A + q^2 B in 16-bit fields (< q^4): sites (0, 2) and (1, 3) of the word
         const uint32_t ABe = (A & 0x00FF00FFu) + q2 * (B & 0x00FF00FFu);
         const uint32_t ABo = ((A >> 8) & 0x00FF00FFu) + q2 * ((B >> 8) & 0x00FF00FFu);
-        const uint4 R = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, (uint32_t)w), a.rk0, k1);
+        const uint4 R = philox_k1(mk_ctr((uint64_t)n.blk, a.draw, (uint32_t)a.colour, (uint32_t)w), a.rk0, n.k1);
         uint32_t res = 0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const uint32_t W = word_of(R, e);
+            const uint32_t a16 = clk_half(word_of(R, e & 1), e >> 1), p16 = clk_half(word_of(R, 2 + (e & 1)), e >> 1);
             const uint32_t c = (ow >> (8 * e)) & 0xFFu;
             const uint32_t ab = ((e & 1) ? ABo : ABe) >> (16 * (e >> 1)) & 0xFFFFu;
-            const uint32_t t = (W & 0xFFFFu) * qm1;          // proposal: k = (t >> 16) + 1 unless the low half decides
+            const uint32_t t = p16 * qm1;                    // proposal: k = (t >> 16) + 1 unless the low half decides
             uint32_t nw = c + 1u + (t >> 16);
             nw = min(nw, nw - q);                            // unsigned: nw - q wraps when nw < q
             const uint32_t ix = c + q * nw + q2 * ab;
-            uint32_t th;
-            if (DIRECT) {
-                asm("ld.shared.u16 %0, [%1];" : "=r"(th) : "r"(sm.cls_addr + 2u * ix));
-            } else {
-                uint32_t cl;
-                if (SMEM) asm("ld.shared.u8 %0, [%1];" : "=r"(cl) : "r"(sm.cls_addr + ix));
-                else cl = sm.gcls[ix];
-                th = sm.sthi[cl];
-            }
-            const uint32_t ha = W >> 16;
+            uint32_t cl;
+            if (SMEM) asm("ld.shared.u8 %0, [%1];" : "=r"(cl) : "r"(sm.cls_addr + ix));
+            else cl = sm.gcls[ix];
+            const uint32_t th = sm.sthi[cl] >> 1;            // thr >> 17
+            const uint32_t ha = a16 & 0x7FFFu;
             res |= (ha < th ? nw : c) << (8 * e);
-            if ((t & 0xFFFFu) >= tie_lim || ha == th) ties |= 1u << (4 * w + e);
+            if ((t & 0xFFFFu) >= tie_lim || ha == th) ties |= 1u << w;
         }
         outw[w] = res;
     }
-    while (ties) {  // rare: redo the undecided sites with the full 32-bit uniforms
-        const int j = __ffs(ties) - 1;
-        ties &= ties - 1;
-        const uint4 R = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, (uint32_t)(j >> 2)), a.rk0, k1);
-        const uint32_t ns = six_site_exact(a, a.cls, word_of(R, j & 3), blk, k1, j, byte_of(o, j), byte_of(rt, j),
-                                           byte_of(up, j), byte_of(lf, j), byte_of(dn, j));
-        const int wi = j >> 2, sh = 8 * (j & 3);
+    if (ties) {  // rare: redo the words with an undecided site with the full 32-bit uniforms
 #pragma unroll
         for (int w = 0; w < 4; ++w)
-            if (w == wi) outw[w] = (outw[w] & ~(0xFFu << sh)) | (ns << sh);
+            if (ties & (1u << w))
+                outw[w] = six_word_exact(a, n.blk, n.k1, w, word_of(n.o, w), word_of(n.rt, w), word_of(n.up, w), word_of(n.lf, w), word_of(n.dn, w));
     }
-    *po = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+    *n.po = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+}
+
+// direct path: table T[k][F] of the thresholds' high 15 bits in shared memory, F = r + q u + q^2 l + q^3 d + q^4 c
+// Q = q at compile time (0: run time)
+template <int P, int Q>
+__device__ __forceinline__ void six_vector_direct(const SixArgs& a, const uint8_t* tab, unsigned long long win, int idx, int y, int rep, int v)
+{
+    const uint32_t q = Q ? (uint32_t)Q : a.q, qm1 = q - 1, kstride = Q ? 2u * Q * Q * Q * Q * Q : 2u * a.q5;
+    SixRows n;
+    six_load<P>(a, idx, y, rep, v, n);
+    uint32_t outw[4], am[4], pn[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        uint32_t Fe, Fo;
+        clk_index_fields(word_of(n.rt, w), word_of(n.up, w), word_of(n.lf, w), word_of(n.dn, w), word_of(n.o, w), q, Fe, Fo);
+        const uint4 R = philox_k1(mk_ctr((uint64_t)n.blk, a.draw, (uint32_t)a.colour, (uint32_t)w), a.rk0, n.k1);
+        outw[w] = clk_word_fast<true>(word_of(n.o, w), Fe, Fo, R, tab, kstride, qm1, win, q, am[w], pn[w]);
+    }
+    const uint32_t amin = __vimin3_s16x2(__vmins2(am[0], am[1]), am[2], am[3]);
+    const uint32_t pmin = __vimin3_u32(min(pn[0], pn[1]), pn[2], pn[3]);
+    const uint32_t lim = qm1 << 17;
+    if (pmin < lim || clk_accept_tie(amin)) {   // rare: redo the words with an undecided site exactly
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+            if (pn[w] < lim || clk_accept_tie(am[w]))
+                outw[w] = six_word_exact(a, n.blk, n.k1, w, word_of(n.o, w), word_of(n.rt, w), word_of(n.up, w), word_of(n.lf, w), word_of(n.dn, w));
+    }
+    *n.po = make_uint4(outw[0], outw[1], outw[2], outw[3]);
 }
 
 #define SIX_DIRECT_THREADS 768
-template <bool SMEM, bool DIRECT = false>
+template <bool SMEM, bool DIRECT = false, int Q = 0>
 __global__ void __launch_bounds__(DIRECT ? SIX_DIRECT_THREADS : 256, DIRECT ? 1 : SIX_MINB)
 sixclock_pass_kernel(const __grid_constant__ SixArgs a)
 {
     extern __shared__ __align__(16) uint8_t smraw[];
-    uint32_t* sthi = reinterpret_cast<uint32_t*>(smraw);            // SIX_MAX_CLASSES words
-    uint8_t* scls = smraw + SIX_MAX_CLASSES * sizeof(uint32_t);     // q^6 bytes (SMEM) / 2 q^6 bytes (DIRECT)
-    for (int i = threadIdx.x; i < SIX_MAX_CLASSES; i += blockDim.x) sthi[i] = a.thi[i];
+    // class path: SIX_MAX_CLASSES words of thresholds, then q^6 class bytes (SMEM); direct path: CLK_WIN_BYTES (the proposal window, clk_win64), then the
+    // u16 table (2 q^6 bytes, the last slab is padding)
+    uint32_t* sthi = reinterpret_cast<uint32_t*>(smraw);
+    uint8_t* scls = smraw + (DIRECT ? CLK_WIN_BYTES : SIX_MAX_CLASSES * sizeof(uint32_t));
+    if (!DIRECT) for (int i = threadIdx.x; i < SIX_MAX_CLASSES; i += blockDim.x) sthi[i] = a.thi[i];
+    else clk_win64_store(smraw, (unsigned long long)((a.q - 1) << 16));
     if (SMEM || DIRECT) {
         const uint4* src = reinterpret_cast<const uint4*>(DIRECT ? reinterpret_cast<const uint8_t*>(a.thr16) : a.cls);
         uint4* dst = reinterpret_cast<uint4*>(scls);
-        const uint32_t bytes = DIRECT ? 2u * a.tab_bytes : a.tab_bytes;
+        const uint32_t bytes = DIRECT ? 2u * a.q5 * (a.q - 1) : a.tab_bytes;
         for (uint32_t i = threadIdx.x; i < (bytes + 15) / 16; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
@@ -233,20 +271,28 @@ sixclock_pass_kernel(const __grid_constant__ SixArgs a)
     sm.cls_addr = (uint32_t)__cvta_generic_to_shared(scls);
     sm.sthi = sthi;
     sm.gcls = a.cls;
+    unsigned long long win = 0;
+    if (DIRECT) win = clk_win64(smraw);
     const int nvr = a.nvr, ny = a.ny;
-    // (row, vector) of this thread, advanced incrementally: no division in the loop
+    // linear vector index idx = (replica ny + y) nvr + v of this thread; (y, v, replica) advanced incrementally: no
+    // division in the loop
     const int stride = gridDim.x * blockDim.x;
     const int dY = stride / nvr, dv = stride - dY * nvr;
-    const int idx0 = blockIdx.x * blockDim.x + threadIdx.x;
-    int Y = idx0 / nvr, v = idx0 - Y * nvr;       // Y = replica * ny + y0
+    const int total = a.nrows * nvr;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int Y = idx / nvr, v = idx - Y * nvr;
     int rep = Y / ny, y = Y - rep * ny;
-    while (Y < a.nrows) {
-        if ((y + a.colour) & 1) six_vector<SMEM, DIRECT, 1>(a, sm, Y, y, rep, v);
-        else six_vector<SMEM, DIRECT, 0>(a, sm, Y, y, rep, v);
-        v += dv;
-        int adv = dY;
-        if (v >= nvr) { v -= nvr; ++adv; }
-        Y += adv; y += adv;
+    while (idx < total) {
+        if (DIRECT) {
+            if ((y + a.colour) & 1) six_vector_direct<1, Q>(a, scls, win, idx, y, rep, v);
+            else six_vector_direct<0, Q>(a, scls, win, idx, y, rep, v);
+        } else {
+            if ((y + a.colour) & 1) six_vector<SMEM, 1>(a, sm, idx, y, rep, v);
+            else six_vector<SMEM, 0>(a, sm, idx, y, rep, v);
+        }
+        idx += stride;
+        v += dv; y += dY;
+        if (v >= nvr) { v -= nvr; ++y; }
         while (y >= ny) { y -= ny; ++rep; }
     }
 }
@@ -332,7 +378,7 @@ sixclock_measure_kernel(const uint8_t* __restrict__ c0, const uint8_t* __restric
             const uint4 o = *(reinterpret_cast<const uint4*>(own + (size_t)Y * pitch) + v);
             const uint4 b = *(reinterpret_cast<const uint4*>(row) + v);
             const uint4 u = *(reinterpret_cast<const uint4*>(oth + (size_t)Yu * pitch) + v);
-            const uint4 r = p ? six_shifted(row, b, v, nvr, nxh, 1) : b;   // x0 + 1
+            const uint4 r = p ? six_shifted(row + 16 * (size_t)v, b, v, nvr, nxh, 1) : b;   // x0 + 1
             const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, rw[4] = {r.x, r.y, r.z, r.w}, uw[4] = {u.x, u.y, u.z, u.w};
             if (q <= 8) {
 #pragma unroll
@@ -502,8 +548,24 @@ int build_tables(Six* m)
                         }
 #undef E3
     thi.resize(SIX_MAX_CLASSES, 0); tlo.resize(SIX_MAX_CLASSES, 0);
-    std::vector<uint16_t> thr16(q6);
-    for (size_t i = 0; i < q6; ++i) thr16[i] = (uint16_t)(thi[cls[i]] > 65535u ? 65535u : thi[cls[i]]);
+    // direct table (q <= 6): T[k][F] = thr >> 17 (0 .. 32768), k = 0 .. q - 2 (new = c + 1 + k mod q),
+    // F = r + q u + q^2 l + q^3 d + q^4 c; the slab k = q - 1 is padding (read by a proposal that is redone as a tie)
+    std::vector<uint16_t> thr16(q6, 0);
+    {
+        const size_t q5 = q6 / q;
+        for (int k = 0; k + 1 < q; ++k)
+            for (int c = 0; c < q; ++c)
+                for (int d = 0; d < q; ++d)
+                    for (int l = 0; l < q; ++l)
+                        for (int u = 0; u < q; ++u)
+                            for (int r = 0; r < q; ++r) {
+                                const int nc = (c + 1 + k) % q;
+                                const size_t at = (size_t)c + (size_t)q * (nc + (size_t)q * (r + (size_t)q * (u + (size_t)q * (l + (size_t)q * d))));
+                                const size_t F = (size_t)r + (size_t)q * (u + (size_t)q * (l + (size_t)q * (d + (size_t)q * c)));
+                                const uint64_t t = ((uint64_t)thi[cls[at]] << 16) | tlo[cls[at]];
+                                thr16[(size_t)k * q5 + F] = (uint16_t)(t >> 17);
+                            }
+    }
     CK(cudaMemcpyAsync(m->d_thr16, thr16.data(), q6 * sizeof(uint16_t), cudaMemcpyHostToDevice, m->stream));
     CK(cudaMemcpyAsync(m->d_cls, cls.data(), q6, cudaMemcpyHostToDevice, m->stream));
     CK(cudaMemcpyAsync(m->d_thi, thi.data(), SIX_MAX_CLASSES * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
@@ -519,7 +581,7 @@ void fill_args(Six* m, int colour, SixArgs* a)
     a->nxh = m->nxh; a->ny = (int)m->ny; a->nvr = m->nvr; a->nrows = (int)(m->n_multi * m->ny);
     a->colour = colour; a->q = (uint32_t)m->q; a->sample0 = (uint32_t)m->sample0;
     a->cls = m->d_cls; a->thi = m->d_thi; a->tlo = m->d_tlo; a->thr16 = m->d_thr16;
-    a->tab_bytes = (uint32_t)m->prob.size(); a->cls_in_smem = m->cls_in_smem;
+    a->tab_bytes = (uint32_t)m->prob.size(); a->q5 = a->tab_bytes / (uint32_t)m->q; a->cls_in_smem = m->cls_in_smem;
     a->draw = m->draw;
     for (int r = 0; r < 10; ++r) a->rk0[r] = m->seed + (uint32_t)r * PHILOX_W0;
 }
@@ -535,7 +597,8 @@ int sweep(Six* m)
             CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
         }
         COUNT_LAUNCH();
-        if (m->direct) sixclock_pass_kernel<false, true><<<m->grid, SIX_DIRECT_THREADS, m->smem_bytes, m->stream>>>(a);
+        if (m->direct && m->q == 6) sixclock_pass_kernel<false, true, 6><<<m->grid, SIX_DIRECT_THREADS, m->smem_bytes, m->stream>>>(a);
+        else if (m->direct) sixclock_pass_kernel<false, true><<<m->grid, SIX_DIRECT_THREADS, m->smem_bytes, m->stream>>>(a);
         else if (m->cls_in_smem) sixclock_pass_kernel<true><<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
         else sixclock_pass_kernel<false><<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
         CK(cudaGetLastError());
@@ -674,11 +737,12 @@ int b200mc_sixclock_create_variant(void** out, int64_t nx, int64_t ny, double kb
     // direct lookup: 2 q^6 bytes of thresholds in shared memory, one block of SIX_DIRECT_THREADS threads per SM
     m->direct = 0; m->threads = 256;
     {
-        const size_t wantd = SIX_MAX_CLASSES * sizeof(uint32_t) + (2 * q6 + 15) / 16 * 16;
+        const size_t wantd = CLK_WIN_BYTES + (2 * q6 + 15) / 16 * 16;
         const char* t = getenv("B200MC_SIX_DIRECT");
         int occd = 0;
         if (wantd <= (size_t)maxsm && !(t && atoi(t) == 0) &&
             cudaFuncSetAttribute(sixclock_pass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wantd) == cudaSuccess &&
+            cudaFuncSetAttribute(sixclock_pass_kernel<false, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wantd) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, sixclock_pass_kernel<false, true>, SIX_DIRECT_THREADS, wantd) == cudaSuccess && occd >= 1) {
             m->direct = 1; m->threads = SIX_DIRECT_THREADS; m->smem_bytes = (int)wantd;
             const int64_t needd = ((int64_t)n_multi * ny * nvr + SIX_DIRECT_THREADS - 1) / SIX_DIRECT_THREADS;

@@ -144,11 +144,34 @@ ORC_API void orc_ring_init_uniforms(uint32_t seed, uint64_t draw, int64_t n_site
 }
 
 /* --------------------------------------------------------------------------
+ * Clock models, contract v2: the two 32-bit uniforms of a site (accept, proposal)
+ * assembled from half-words of two Philox blocks.  One block R serves the four
+ * sites e = 0..3 of a 32-bit word of states, a second block R2 (sub-counter + 4)
+ * supplies the low halves (the GPU only evaluates R2 when the first look -- 15
+ * accept bits, 16 proposal bits -- does not decide; the value is the same):
+ *   half(w, hs) = hs ? w >> 16 : w & 0xFFFF,   hs = e >> 1
+ *   accept    a16 = half(R[e & 1], hs),       a16' = half(R2[e & 1], hs)
+ *   proposal  p16 = half(R[2 + (e & 1)], hs),  p16' = half(R2[2 + (e & 1)], hs)
+ *   U_a = (a16 & 0x7FFF) << 17 | (a16 >> 15) << 16 | a16'     U_p = p16 << 16 | p16'
+ * (cuda_fortran_mc_simulation_spin_b200/csrc/clock_word.cuh)
+ * -------------------------------------------------------------------------- */
+static inline uint32_t clk_half(uint32_t w, int hs) { return hs ? w >> 16 : w & 0xFFFFu; }
+static inline void clk_uniform_pair(const uint32_t r[4], const uint32_t r2[4], int e, uint32_t *Ua, uint32_t *Up)
+{
+    const int hs = e >> 1;
+    const uint32_t a16 = clk_half(r[e & 1], hs), a16b = clk_half(r2[e & 1], hs);
+    const uint32_t p16 = clk_half(r[2 + (e & 1)], hs), p16b = clk_half(r2[2 + (e & 1)], hs);
+    *Ua = ((a16 & 0x7FFFu) << 17) | ((a16 >> 15) << 16) | a16b;
+    *Up = (p16 << 16) | p16b;
+}
+
+/* --------------------------------------------------------------------------
  * Clock, helical ring (clock_gpu_m / clock_gpu_multi_m): two 32-bit uniforms
- * per site and sweep, same fold.  For vector p, colour c, replica j:
- *   R = philox(ctr(p, draw, c, lane >> 1), (seed, TAG_CLOCK + j))
- *   accept   U_r = R[2*(lane & 1)]      -> randoms(idx)
- *   proposal U_p = R[2*(lane & 1) + 1]  -> next_states(idx)
+ * per site and sweep, same fold as Ising.  For vector p, colour c, replica j,
+ * byte lane `lane` (word w = lane >> 2, e = lane & 3):
+ *   R  = philox(ctr(p, draw, c,     w), (seed, TAG_CLOCK + j))
+ *   R2 = philox(ctr(p, draw, c, 4 + w), same key)
+ *   accept U_a -> randoms(idx), proposal U_p -> next_states(idx)   (clk_uniform_pair)
  * -------------------------------------------------------------------------- */
 ORC_API void orc_clock_uniforms(uint32_t seed, uint64_t draw, int32_t replica, int64_t n_sites,
                                 double *randoms, double *next_states)
@@ -160,11 +183,14 @@ ORC_API void orc_clock_uniforms(uint32_t seed, uint64_t draw, int32_t replica, i
         int64_t k = i >> 1;
         int lane = (int)(k / L);
         uint64_t p = (uint64_t)(k % L);
-        uint32_t key[2] = {seed, TAG_CLOCK + (uint32_t)replica}, c[4], r[4];
-        mk_ctr(c, p, draw, colour, (uint32_t)(lane >> 1));
+        uint32_t key[2] = {seed, TAG_CLOCK + (uint32_t)replica}, c[4], r[4], r2[4], Ua, Up;
+        mk_ctr(c, p, draw, colour, (uint32_t)(lane >> 2));
         orc_philox4x32_10(c, key, r);
-        randoms[i] = ((double)r[2 * (lane & 1)] + 1.0) * 0x1p-32;
-        next_states[i] = ((double)r[2 * (lane & 1) + 1] + 1.0) * 0x1p-32;
+        mk_ctr(c, p, draw, colour, 4u + (uint32_t)(lane >> 2));
+        orc_philox4x32_10(c, key, r2);
+        clk_uniform_pair(r, r2, lane & 3, &Ua, &Up);
+        randoms[i] = ((double)Ua + 1.0) * 0x1p-32;
+        next_states[i] = ((double)Up + 1.0) * 0x1p-32;
     }
 }
 
@@ -249,12 +275,10 @@ ORC_API void orc_xy_init_uniforms(uint32_t seed, uint64_t draw, int64_t nx, int6
  * Periodic clock (clock_tableall_gpu_m / clock_dual_lattice_tableall_gpu_m): true torus,
  * colour = (x0 + y0) & 1, colour-compact index xi = x0 >> 1; rows are cut into vectors of 16
  * compact sites: v = xi >> 4, j = xi & 15, nvr = ceil((nx/2) / 16), block = y0 * nvr + v.
- * Two 32-bit uniforms per site and sweep, assembled from two Philox words (the GPU evaluates
- * the second one only when the 16 bits of the first do not decide; the value is the same):
- *   W  = philox(ctr(block, draw, colour,     j >> 2), (seed, TAG_TORUS + replica))[j & 3]
- *   W2 = philox(ctr(block, draw, colour, 4 + (j >> 2)), same key)[j & 3]
- *   accept   U_a = (W & 0xFFFF0000) | (W2 >> 16)      -> rnds(2, x, y)
- *   proposal U_p = (W << 16)        | (W2 & 0xFFFF)   -> rnds(1, x, y)
+ * Two 32-bit uniforms per site and sweep (contract v2, clk_uniform_pair above), word w = j >> 2, e = j & 3:
+ *   R  = philox(ctr(block, draw, colour,     w), (seed, TAG_TORUS + replica))
+ *   R2 = philox(ctr(block, draw, colour, 4 + w), same key)
+ *   accept   U_a -> rnds(2, x, y)      proposal U_p -> rnds(1, x, y)
  * u = (U + 1) 2^-32.  Written in the reference's order rnds(2, nx, ny)
  * (src/clock/clock_tableall_gpu_m.f90:95): out[(j-1) + 2*(x0 + nx*y0)].
  * -------------------------------------------------------------------------- */
@@ -275,9 +299,8 @@ ORC_API void orc_torus_uniforms(uint32_t seed, uint64_t draw, int32_t replica, i
             orc_philox4x32_10(c, key, r);
             mk_ctr(c, blk, draw, colour, 4u + (uint32_t)(j >> 2));
             orc_philox4x32_10(c, key, r2);
-            const uint32_t W = r[j & 3], W2 = r2[j & 3];
-            const uint32_t Ua = (W & 0xFFFF0000u) | (W2 >> 16);
-            const uint32_t Up = (W << 16) | (W2 & 0xFFFFu);
+            uint32_t Ua, Up;
+            clk_uniform_pair(r, r2, j & 3, &Ua, &Up);
             rnds[0 + 2 * (x0 + nx * y0)] = ((double)Up + 1.0) * 0x1p-32;
             rnds[1 + 2 * (x0 + nx * y0)] = ((double)Ua + 1.0) * 0x1p-32;
         }
