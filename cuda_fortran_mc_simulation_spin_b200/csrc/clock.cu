@@ -246,9 +246,8 @@ int create(void** out, int64_t nx, int64_t ny, double kbt, int32_t q, int32_t n_
     if (occ < 1) occ = 1;
     const int64_t need = (g.L + 255) / 256;
     m->grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);
-    {   // direct lookup (q <= 6: q^3 < 256 for the byte-parallel index): 2 q^6 bytes of thresholds + one slab of padding in shared memory
-        const size_t q5 = q6 / q;
-        const size_t wantd = CLK_WIN_BYTES + (2 * (q6 + q5) + 15) / 16 * 16;
+    {   // direct lookup (q <= 6: q^3 < 256 for the byte-parallel index): 2 q^6 bytes of thresholds in shared memory
+        const size_t wantd = (2 * q6 + 15) / 16 * 16;
         const char* t = getenv("B200MC_CLOCK_DIRECT");
         int occd = 0;
         if (q <= 6 && wantd <= (size_t)maxsm && !(t && atoi(t) == 0) &&

@@ -47,36 +47,49 @@ struct ClockArgs {
     const uint16_t* thr16;     // direct lookup (q <= 6): T[next][F] = thr >> 17, F = up + q down + q^2 left + q^3 right + q^4 cur
 };
 
-// exact (32-bit) evaluation of the four sites of word w of vector pglob: both Philox blocks (RNG contract v2,
-// clock_word.cuh), class table, full 33-bit threshold.
-// accept iff U_a < thr[class]; proposal next = min(floor((U_p + 1) q / 2^32), q - 1)
-// (floor(next_states * q), src/clock_gpu_m.f90:211, with the u == 1 clamp of SURVEY Q4)
-__device__ __forceinline__ uint32_t clock_word_exact_body(const ClockArgs& a, const uint8_t* cls, const uint64_t* thr, uint64_t pglob, int w,
-                                                          uint32_t ow, uint32_t uw, uint32_t dw, uint32_t lw, uint32_t rw)
+// exact evaluation of the 16 sites of vector pglob (RNG contract v3, clock_word.cuh): both stages of the accept uniforms,
+// class table, full 33-bit threshold.
+// accept iff U_a < thr[class]; proposal next = floor(W_e q / 2^32) = the reference's min(floor(next_states q), q - 1)
+// (src/clock_gpu_m.f90:211, with the u == 1 clamp of SURVEY Q4) on the contract's next_states
+__device__ __forceinline__ uint4 clock_vector_exact_body(const ClockArgs& a, const uint8_t* cls, const uint64_t* thr, uint64_t pglob,
+                                                         const uint4& o, const uint4& nu, const uint4& nd, const uint4& nl, const uint4& nr)
 {
     const RingPassArgs& r = a.r;
-    const uint4 R = philox_rk2(mk_ctr(pglob, r.draw, r.colour, (uint32_t)w), a.rk0, a.rk1);
-    const uint4 R2 = philox_rk2(mk_ctr(pglob, r.draw, r.colour, 4u + (uint32_t)w), a.rk0, a.rk1);
     const uint32_t q = a.q, q2 = q * q, q3 = q2 * q, q4 = q3 * q, q5 = q4 * q;
-    uint32_t res = 0;
+    uint32_t X[12], Y[12];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        uint32_t Ua, Up;
-        clk_uniforms(R, R2, e, Ua, Up);
-        const int sh = 8 * e;
-        const uint32_t cur = (ow >> sh) & 0xFFu;
-        uint32_t nxt = (uint32_t)((((unsigned long long)Up + 1ull) * q) >> 32);
-        nxt = min(nxt, q - 1);
-        const uint32_t idx = ((uw >> sh) & 0xFFu) + q * ((dw >> sh) & 0xFFu) + q2 * ((lw >> sh) & 0xFFu) +
-                             q3 * ((rw >> sh) & 0xFFu) + q4 * cur + q5 * nxt;
-        const uint64_t t = thr[cls[idx]];
-        res |= (((unsigned long long)Ua < t) ? nxt : cur) << sh;
+    for (int i = 0; i < 3; ++i) {
+        const uint4 R = philox_rk2(mk_ctr(pglob, r.draw, r.colour, (uint32_t)i), a.rk0, a.rk1);
+        const uint4 R2 = philox_rk2(mk_ctr(pglob, r.draw, r.colour, 4u + (uint32_t)i), a.rk0, a.rk1);
+        X[4 * i] = R.x; X[4 * i + 1] = R.y; X[4 * i + 2] = R.z; X[4 * i + 3] = R.w;
+        Y[4 * i] = R2.x; Y[4 * i + 1] = R2.y; Y[4 * i + 2] = R2.z; Y[4 * i + 3] = R2.w;
     }
-    return res;
+    const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, lw[4] = {nl.x, nl.y, nl.z, nl.w}, rw[4] = {nr.x, nr.y, nr.z, nr.w},
+                   uw[4] = {nu.x, nu.y, nu.z, nu.w}, dw[4] = {nd.x, nd.y, nd.z, nd.w};
+    uint32_t res[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        uint32_t W = X[3 * w + 2], out = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t Ua = clk_accept32(X[3 * w + (e & 1)], Y[3 * w + (e & 1)], e >> 1);
+            uint32_t nxt;
+            mulwide(W, q, W, nxt);
+            const int sh = 8 * e;
+            const uint32_t cur = (ow[w] >> sh) & 0xFFu;
+            const uint32_t idx = ((uw[w] >> sh) & 0xFFu) + q * ((dw[w] >> sh) & 0xFFu) + q2 * ((lw[w] >> sh) & 0xFFu) +
+                                 q3 * ((rw[w] >> sh) & 0xFFu) + q4 * cur + q5 * nxt;
+            const uint64_t t = thr[cls[idx]];
+            out |= (((unsigned long long)Ua < t) ? nxt : cur) << sh;
+        }
+        res[w] = out;
+    }
+    return make_uint4(res[0], res[1], res[2], res[3]);
 }
-__device__ __noinline__ uint32_t clock_word_exact(const ClockArgs& a, uint64_t pglob, int w, uint32_t ow, uint32_t uw, uint32_t dw, uint32_t lw, uint32_t rw)
+// (arguments and result by value: registers, not local memory, on the caller's hot path)
+__device__ __noinline__ uint4 clock_vector_exact(const ClockArgs& a, uint64_t pglob, uint4 o, uint4 nu, uint4 nd, uint4 nl, uint4 nr)
 {
-    return clock_word_exact_body(a, a.cls, a.thr, pglob, w, ow, uw, dw, lw, rw);
+    return clock_vector_exact_body(a, a.cls, a.thr, pglob, o, nu, nd, nl, nr);
 }
 
 // class-table pass (any q <= 16): every site with its full 32-bit uniforms, class ids from shared memory (q <= 7) or L1/L2
@@ -106,40 +119,30 @@ clock_pass_kernel(const __grid_constant__ ClockArgs a)
         const uint4 nr = ld_other(oth + v + (int)r.off[1]);   // i+1  right
         const uint4 nu = ld_other(oth + v + (int)r.off[2]);   // i+nx up
         const uint4 nd = ld_other(oth + v + (int)r.off[3]);   // i-nx down
-        const uint64_t pglob = (uint64_t)(r.p0 + v);
-        uint4 res;
-        res.x = clock_word_exact_body(a, cls, sthr, pglob, 0, o.x, nu.x, nd.x, nl.x, nr.x);
-        res.y = clock_word_exact_body(a, cls, sthr, pglob, 1, o.y, nu.y, nd.y, nl.y, nr.y);
-        res.z = clock_word_exact_body(a, cls, sthr, pglob, 2, o.z, nu.z, nd.z, nl.z, nr.z);
-        res.w = clock_word_exact_body(a, cls, sthr, pglob, 3, o.w, nu.w, nd.w, nl.w, nr.w);
-        own[v] = res;
+        own[v] = clock_vector_exact_body(a, cls, sthr, (uint64_t)(r.p0 + v), o, nu, nd, nl, nr);
     }
 }
 
-// Direct-table variant (q <= 6; one CLOCK_DIRECT_THREADS-thread block per SM): clock_word.cuh.  Shared memory:
-// CLK_WIN_BYTES (proposal window), then T[next][F] (q slabs of 2 q^5 bytes + one slab of padding, read by a proposal that
-// is redone as a tie).  Q = q at compile time (0: run time).
+// Direct-table variant (q <= 6; one CLOCK_DIRECT_THREADS-thread block per SM): clock_word.cuh.  Shared memory: the table
+// T[next][F] (q slabs of 2 q^5 bytes).  Q = q at compile time (0: run time).
 #define CLOCK_DIRECT_THREADS 768
 template <int Q>
 __global__ void __launch_bounds__(CLOCK_DIRECT_THREADS, 1)
 clock_pass_direct_kernel(const __grid_constant__ ClockArgs a)
 {
-    extern __shared__ __align__(16) uint8_t sm[];
-    uint8_t* tab = sm + CLK_WIN_BYTES;
+    extern __shared__ __align__(16) uint8_t tab[];
     const uint32_t q = Q ? (uint32_t)Q : a.q;
-    clk_win64_store(sm, (unsigned long long)(q << 16));
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.thr16);
         uint4* dst = reinterpret_cast<uint4*>(tab);
         for (uint32_t i = threadIdx.x; i < (2u * a.tab_bytes + 15) / 16; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const unsigned long long win = clk_win64(sm);
     const RingPassArgs& r = a.r;
     uint4* own = r.own + r.H;
     const uint4* oth = r.oth + r.H;
     const int nvec = (int)r.nvec;
-    const uint32_t kstride = Q ? 2u * Q * Q * Q * Q * Q : 2u * (a.tab_bytes / a.q), lim = q << 17;
+    const uint32_t kstride = Q ? 2u * Q * Q * Q * Q * Q : 2u * (a.tab_bytes / a.q);
     const int stride = gridDim.x * blockDim.x;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
         const uint4 o = own[v];
@@ -149,23 +152,23 @@ clock_pass_direct_kernel(const __grid_constant__ ClockArgs a)
         const uint4 nd = ld_other(oth + v + (int)r.off[3]);   // i-nx down
         const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, lw[4] = {nl.x, nl.y, nl.z, nl.w}, rw[4] = {nr.x, nr.y, nr.z, nr.w},
                        uw[4] = {nu.x, nu.y, nu.z, nu.w}, dw[4] = {nd.x, nd.y, nd.z, nd.w};
-        uint32_t res[4], am[4], pn[4];
         const uint64_t pglob = (uint64_t)(r.p0 + v);
+        uint32_t X[12];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const uint4 R = philox_rk2(mk_ctr(pglob, r.draw, r.colour, (uint32_t)i), a.rk0, a.rk1);
+            X[4 * i] = R.x; X[4 * i + 1] = R.y; X[4 * i + 2] = R.z; X[4 * i + 3] = R.w;
+        }
+        uint32_t res[4], amin = 0x7FFF7FFFu;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             uint32_t Fe, Fo;
             clk_index_fields(uw[w], dw[w], lw[w], rw[w], ow[w], q, Fe, Fo);
-            const uint4 R = philox_rk2(mk_ctr(pglob, r.draw, r.colour, (uint32_t)w), a.rk0, a.rk1);
-            res[w] = clk_word_fast<false>(ow[w], Fe, Fo, R, tab, kstride, q, win, q, am[w], pn[w]);
+            res[w] = clk_word_fast<false>(ow[w], Fe, Fo, X[3 * w], X[3 * w + 1], X[3 * w + 2], tab, kstride, q, q, amin);
         }
-        const uint32_t amin = __vimin3_s16x2(__vmins2(am[0], am[1]), am[2], am[3]);
-        const uint32_t pmin = __vimin3_u32(min(pn[0], pn[1]), pn[2], pn[3]);
-        if (pmin < lim || clk_accept_tie(amin)) {   // rare: redo the words with an undecided site exactly
-#pragma unroll
-            for (int w = 0; w < 4; ++w)
-                if (pn[w] < lim || clk_accept_tie(am[w])) res[w] = clock_word_exact(a, pglob, w, ow[w], uw[w], dw[w], lw[w], rw[w]);
-        }
-        own[v] = make_uint4(res[0], res[1], res[2], res[3]);
+        uint4 out = make_uint4(res[0], res[1], res[2], res[3]);
+        if (clk_accept_tie(amin)) out = clock_vector_exact(a, pglob, o, nu, nd, nl, nr);   // rare (2^-15 per site): redo the vector exactly
+        own[v] = out;
     }
 }
 

@@ -14,16 +14,13 @@
 // periodic wrap is index arithmetic (no halo).  Pad bytes (xi >= nx/2) always hold valid states
 // and are masked out of the observables.
 //
-// RNG contract (v2; CPU restatement: oracle/rng_contract.c, orc_torus_uniforms; bit assignment:
-// clock_word.cuh).  Site j = xi & 15 of vector v = xi >> 4 of row y0: block = y0 * nvr + v, word
-// w = j >> 2, e = j & 3,
-//   R  = philox(ctr(block, draw, colour,     w), (seed, TAG_TORUS + replica))
-//   R2 = philox(ctr(block, draw, colour, 4 + w), same key)
-//   accept   U_a from the half-words half(R[e & 1], e >> 1), half(R2[e & 1], e >> 1)       -> rnds(2, x, y)
-//   proposal U_p from the half-words half(R[2 + (e & 1)], e >> 1), half(R2[2 + (e & 1)], ..) -> rnds(1, x, y)
-// R2 is only evaluated when the first look (15 accept bits, 16 proposal bits) does not decide, so
-// the hot loop costs one Philox block per 4 sites and is still exact at 32-bit resolution:
-//   new = c + ceiling(rnds1 (q-1))  (:142)   <=>  k = ceil((U_p + 1)(q-1) / 2^32)
+// RNG contract (v3; CPU restatement: oracle/rng_contract.c, orc_torus_uniforms; bit assignment:
+// clock_word.cuh).  Vector v = xi >> 4 of row y0: Philox block counter = sample << 32 | (y0 nvr + v),
+// key (seed, TAG_TORUS), sub-counters 0..2 (first look) and 4..6 (low halves of the accept uniforms);
+// site j = xi & 15 = word j >> 2, e = j & 3.  The accept uniform is looked at in two stages (15
+// bits, then all 32: the second stage only for a tie), the four proposals of a word are the
+// leading base-(q-1) digits of one 32-bit uniform:
+//   new = c + ceiling(rnds1 (q-1))  (:142)   <=>  k - 1 = floor(W_e (q-1) / 2^32)
 //   rnds2 <= prob                  (:146)   <=>  U_a < thr = floor(prob 2^32)
 #include <math.h>
 #include <stdlib.h>
@@ -33,6 +30,7 @@
 #include "../../include/b200mc.h"
 #include "common.cuh"
 #include "clock_word.cuh"
+#include "ising_kernels.cuh"   // philox_rk
 
 namespace {
 
@@ -55,23 +53,6 @@ struct SixArgs {
     uint64_t draw;
     uint32_t rk0[10];        // Philox round keys seed + r W0
 };
-
-__device__ __forceinline__ uint4 philox_k1(uint4 c, const uint32_t (&rk0)[10], uint32_t k1)
-{
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        uint32_t lo0, hi0, lo1, hi1;
-        mulwide(PHILOX_M0, c.x, lo0, hi0);
-        mulwide(PHILOX_M1, c.z, lo1, hi1);
-        uint4 n;
-        n.x = hi1 ^ c.y ^ rk0[r];
-        n.y = lo1;
-        n.z = hi0 ^ c.w ^ (k1 + (uint32_t)r * PHILOX_W1);
-        n.w = lo0;
-        c = n;
-    }
-    return c;
-}
 
 __device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p)
 {
@@ -112,44 +93,19 @@ __device__ __forceinline__ uint4 six_shifted(const uint8_t* pv, const uint4& b, 
     return s;
 }
 
-// exact (32-bit) evaluation of the four sites of word w of a vector: both Philox blocks, class table, full 33-bit threshold
-__device__ __noinline__ uint32_t six_word_exact(const SixArgs& a, uint32_t blk, uint32_t k1, int w,
-                                                uint32_t ow, uint32_t rt, uint32_t up, uint32_t lf, uint32_t dn)
-{
-    const uint4 R = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, (uint32_t)w), a.rk0, k1);
-    const uint4 R2 = philox_k1(mk_ctr((uint64_t)blk, a.draw, (uint32_t)a.colour, 4u + (uint32_t)w), a.rk0, k1);
-    const uint32_t q = a.q;
-    uint32_t res = 0;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        uint32_t Ua, Up;
-        clk_uniforms(R, R2, e, Ua, Up);
-        const uint32_t c = (ow >> (8 * e)) & 0xFFu, r = (rt >> (8 * e)) & 0xFFu, u = (up >> (8 * e)) & 0xFFu,
-                       l = (lf >> (8 * e)) & 0xFFu, d = (dn >> (8 * e)) & 0xFFu;
-        const uint32_t k = (uint32_t)((((unsigned long long)Up + 1ull) * (q - 1) + 0xFFFFFFFFull) >> 32);   // ceiling(rnds1 (q - 1)), :142
-        uint32_t nw = c + k;
-        if (nw >= q) nw -= q;
-        const uint32_t idx = c + q * (nw + q * (r + q * (u + q * (l + q * d))));
-        const uint32_t cl = a.cls[idx];
-        const unsigned long long thr = ((unsigned long long)a.thi[cl] << 16) | a.tlo[cl];
-        res |= (((unsigned long long)Ua < thr) ? nw : c) << (8 * e);
-    }
-    return res;
-}
-
 // update_sub, src/clock/clock_tableall_gpu_m.f90:107-152 (dual lattice: :110-155), one colour
 #ifndef SIX_MINB
 #define SIX_MINB 3
 #endif
-// Acceptance lookup.  Class path (any q <= 12): q^6 one-byte class ids (shared or global memory) + per-class thresholds in
-// shared memory, two dependent loads per site, scalar per-site code.  Direct path (q <= 6, default): clock_word.cuh.
+// Acceptance lookup.  Class path (any q <= 12): q^6 one-byte class ids (shared or global memory) + per-class thresholds,
+// every site with its full 32-bit uniforms.  Direct path (q <= 6, default): clock_word.cuh.
 struct SixSmem {
     uint32_t cls_addr;        // shared-window address of the class table
-    const uint32_t* sthi;
+    const uint32_t* sthi;     // per class thr >> 16 (shared memory; class path)
     const uint8_t* gcls;
 };
 
-struct SixRows { uint4 o, rt, up, lf, dn; uint4* po; uint32_t k1, blk; };
+struct SixRows { uint4 o, rt, up, lf, dn; uint4* po; uint64_t blk; };   // blk: Philox block counter = (sample << 32) | (y nvr + v)
 
 // loads of one vector = 16 sites of row (rep, y) at compact position 16 v .. 16 v + 15; idx = (rep ny + y) nvr + v is its
 // linear index in both colour arrays (rows are nvr vectors long).  P = (y + colour) & 1: the x position of compact site
@@ -168,98 +124,105 @@ __device__ __forceinline__ void six_load(const SixArgs& a, int idx, int y, int r
     n.dn = ld_other(pv + dd);
     const uint4 s = six_shifted(reinterpret_cast<const uint8_t*>(pv), b, v, nvr, a.nxh, P);
     n.rt = P ? s : b; n.lf = P ? b : s;
-    n.k1 = TAG_TORUS + a.sample0 + (uint32_t)rep;
-    n.blk = (uint32_t)(y * nvr + v);
+    n.blk = ((uint64_t)(a.sample0 + (uint32_t)rep) << 32) | (uint32_t)(y * nvr + v);
+}
+
+// exact evaluation of the 16 sites of a vector (RNG contract v3, clock_word.cuh): both stages of the accept uniforms, class
+// table, full 33-bit threshold.  MODE 0: class ids and thresholds from global memory (the direct path's tie redo), 1: class
+// ids from shared memory, 2: class ids from global memory, thresholds from shared memory.
+template <int MODE>
+__device__ __forceinline__ uint4 six_vector_exact_body(const SixArgs& a, const SixSmem& sm, const SixRows& n)
+{
+    const uint32_t q = a.q, qm1 = q - 1;
+    uint32_t X[12], Y[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const uint4 R = philox_rk<TAG_TORUS>(mk_ctr(n.blk, a.draw, (uint32_t)a.colour, (uint32_t)i), a.rk0);
+        const uint4 R2 = philox_rk<TAG_TORUS>(mk_ctr(n.blk, a.draw, (uint32_t)a.colour, 4u + (uint32_t)i), a.rk0);
+        X[4 * i] = R.x; X[4 * i + 1] = R.y; X[4 * i + 2] = R.z; X[4 * i + 3] = R.w;
+        Y[4 * i] = R2.x; Y[4 * i + 1] = R2.y; Y[4 * i + 2] = R2.z; Y[4 * i + 3] = R2.w;
+    }
+    uint32_t outw[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t ow = word_of(n.o, w), rt = word_of(n.rt, w), up = word_of(n.up, w), lf = word_of(n.lf, w), dn = word_of(n.dn, w);
+        uint32_t W = X[3 * w + 2], res = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t Ua = clk_accept32(X[3 * w + (e & 1)], Y[3 * w + (e & 1)], e >> 1);
+            uint32_t k;
+            mulwide(W, qm1, W, k);                                  // ceiling(rnds1 (q - 1)) - 1, :142
+            const uint32_t c = (ow >> (8 * e)) & 0xFFu, r = (rt >> (8 * e)) & 0xFFu, u = (up >> (8 * e)) & 0xFFu,
+                           l = (lf >> (8 * e)) & 0xFFu, d = (dn >> (8 * e)) & 0xFFu;
+            uint32_t nw = c + 1u + k;
+            if (nw >= q) nw -= q;
+            const uint32_t idx = c + q * (nw + q * (r + q * (u + q * (l + q * d))));
+            uint32_t cl;
+            if (MODE == 1) asm("ld.shared.u8 %0, [%1];" : "=r"(cl) : "r"(sm.cls_addr + idx));
+            else cl = a.cls[idx];
+            const unsigned long long thr = ((unsigned long long)(MODE == 0 ? a.thi[cl] : sm.sthi[cl]) << 16) | a.tlo[cl];
+            res |= (((unsigned long long)Ua < thr) ? nw : c) << (8 * e);
+        }
+        outw[w] = res;
+    }
+    return make_uint4(outw[0], outw[1], outw[2], outw[3]);
+}
+// (arguments and result by value: a struct passed by reference would live in local memory on the hot path)
+__device__ __noinline__ uint4 six_vector_exact(const SixArgs& a, uint64_t blk, uint4 o, uint4 rt, uint4 up, uint4 lf, uint4 dn)
+{
+    SixSmem sm;
+    sm.cls_addr = 0; sm.sthi = nullptr; sm.gcls = a.cls;
+    SixRows n;
+    n.o = o; n.rt = rt; n.up = up; n.lf = lf; n.dn = dn; n.po = nullptr; n.blk = blk;
+    return six_vector_exact_body<0>(a, sm, n);
 }
 
 template <bool SMEM, int P>
 __device__ __forceinline__ void six_vector(const SixArgs& a, const SixSmem& sm, int idx, int y, int rep, int v)
 {
-    const uint32_t q = a.q, qm1 = q - 1, q2 = q * q;
-    const uint32_t tie_lim = 65537u - qm1;
     SixRows n;
     six_load<P>(a, idx, y, rep, v, n);
-    uint32_t outw[4];
-    uint32_t ties = 0;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        const uint32_t ow = word_of(n.o, w);
-        // byte-parallel partial indices: A = r + q u, B = l + q d (< q^2 <= 144)
-        const uint32_t A = word_of(n.rt, w) + q * word_of(n.up, w);
-        const uint32_t B = word_of(n.lf, w) + q * word_of(n.dn, w);
-        // AB = A + q^2 B in 16-bit fields (< q^4): sites (0, 2) and (1, 3) of the word
-        const uint32_t ABe = (A & 0x00FF00FFu) + q2 * (B & 0x00FF00FFu);
-        const uint32_t ABo = ((A >> 8) & 0x00FF00FFu) + q2 * ((B >> 8) & 0x00FF00FFu);
-        const uint4 R = philox_k1(mk_ctr((uint64_t)n.blk, a.draw, (uint32_t)a.colour, (uint32_t)w), a.rk0, n.k1);
-        uint32_t res = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const uint32_t a16 = clk_half(word_of(R, e & 1), e >> 1), p16 = clk_half(word_of(R, 2 + (e & 1)), e >> 1);
-            const uint32_t c = (ow >> (8 * e)) & 0xFFu;
-            const uint32_t ab = ((e & 1) ? ABo : ABe) >> (16 * (e >> 1)) & 0xFFFFu;
-            const uint32_t t = p16 * qm1;                    // proposal: k = (t >> 16) + 1 unless the low half decides
-            uint32_t nw = c + 1u + (t >> 16);
-            nw = min(nw, nw - q);                            // unsigned: nw - q wraps when nw < q
-            const uint32_t ix = c + q * nw + q2 * ab;
-            uint32_t cl;
-            if (SMEM) asm("ld.shared.u8 %0, [%1];" : "=r"(cl) : "r"(sm.cls_addr + ix));
-            else cl = sm.gcls[ix];
-            const uint32_t th = sm.sthi[cl] >> 1;            // thr >> 17
-            const uint32_t ha = a16 & 0x7FFFu;
-            res |= (ha < th ? nw : c) << (8 * e);
-            if ((t & 0xFFFFu) >= tie_lim || ha == th) ties |= 1u << w;
-        }
-        outw[w] = res;
-    }
-    if (ties) {  // rare: redo the words with an undecided site with the full 32-bit uniforms
-#pragma unroll
-        for (int w = 0; w < 4; ++w)
-            if (ties & (1u << w))
-                outw[w] = six_word_exact(a, n.blk, n.k1, w, word_of(n.o, w), word_of(n.rt, w), word_of(n.up, w), word_of(n.lf, w), word_of(n.dn, w));
-    }
-    *n.po = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+    *n.po = six_vector_exact_body<SMEM ? 1 : 2>(a, sm, n);
 }
 
 // direct path: table T[k][F] of the thresholds' high 15 bits in shared memory, F = r + q u + q^2 l + q^3 d + q^4 c
 // Q = q at compile time (0: run time)
 template <int P, int Q>
-__device__ __forceinline__ void six_vector_direct(const SixArgs& a, const uint8_t* tab, unsigned long long win, int idx, int y, int rep, int v)
+__device__ __forceinline__ void six_vector_direct(const SixArgs& a, const uint8_t* tab, int idx, int y, int rep, int v)
 {
     const uint32_t q = Q ? (uint32_t)Q : a.q, qm1 = q - 1, kstride = Q ? 2u * Q * Q * Q * Q * Q : 2u * a.q5;
     SixRows n;
     six_load<P>(a, idx, y, rep, v, n);
-    uint32_t outw[4], am[4], pn[4];
+    uint32_t X[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const uint4 R = philox_rk<TAG_TORUS>(mk_ctr(n.blk, a.draw, (uint32_t)a.colour, (uint32_t)i), a.rk0);
+        X[4 * i] = R.x; X[4 * i + 1] = R.y; X[4 * i + 2] = R.z; X[4 * i + 3] = R.w;
+    }
+    uint4 out;
+    uint32_t outw[4], amin = 0x7FFF7FFFu;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
         uint32_t Fe, Fo;
         clk_index_fields(word_of(n.rt, w), word_of(n.up, w), word_of(n.lf, w), word_of(n.dn, w), word_of(n.o, w), q, Fe, Fo);
-        const uint4 R = philox_k1(mk_ctr((uint64_t)n.blk, a.draw, (uint32_t)a.colour, (uint32_t)w), a.rk0, n.k1);
-        outw[w] = clk_word_fast<true>(word_of(n.o, w), Fe, Fo, R, tab, kstride, qm1, win, q, am[w], pn[w]);
+        outw[w] = clk_word_fast<true>(word_of(n.o, w), Fe, Fo, X[3 * w], X[3 * w + 1], X[3 * w + 2], tab, kstride, qm1, q, amin);
     }
-    const uint32_t amin = __vimin3_s16x2(__vmins2(am[0], am[1]), am[2], am[3]);
-    const uint32_t pmin = __vimin3_u32(min(pn[0], pn[1]), pn[2], pn[3]);
-    const uint32_t lim = qm1 << 17;
-    if (pmin < lim || clk_accept_tie(amin)) {   // rare: redo the words with an undecided site exactly
-#pragma unroll
-        for (int w = 0; w < 4; ++w)
-            if (pn[w] < lim || clk_accept_tie(am[w]))
-                outw[w] = six_word_exact(a, n.blk, n.k1, w, word_of(n.o, w), word_of(n.rt, w), word_of(n.up, w), word_of(n.lf, w), word_of(n.dn, w));
-    }
-    *n.po = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+    out = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+    if (clk_accept_tie(amin)) out = six_vector_exact(a, n.blk, n.o, n.rt, n.up, n.lf, n.dn);   // rare (2^-15 per site): redo the vector exactly
+    *n.po = out;
 }
 
 #define SIX_DIRECT_THREADS 768
-template <bool SMEM, bool DIRECT = false, int Q = 0>
-__global__ void __launch_bounds__(DIRECT ? SIX_DIRECT_THREADS : 256, DIRECT ? 1 : SIX_MINB)
+template <bool SMEM, bool DIRECT = false, int Q = 0, int THREADS = SIX_DIRECT_THREADS>
+__global__ void __launch_bounds__(DIRECT ? THREADS : 256, DIRECT ? 1 : SIX_MINB)
 sixclock_pass_kernel(const __grid_constant__ SixArgs a)
 {
     extern __shared__ __align__(16) uint8_t smraw[];
-    // class path: SIX_MAX_CLASSES words of thresholds, then q^6 class bytes (SMEM); direct path: CLK_WIN_BYTES (the proposal window, clk_win64), then the
-    // u16 table (2 q^6 bytes, the last slab is padding)
+    // class path: SIX_MAX_CLASSES words of thresholds, then q^6 class bytes (SMEM); direct path: the u16 table
+    // T[k][F] (2 q^5 (q - 1) bytes)
     uint32_t* sthi = reinterpret_cast<uint32_t*>(smraw);
-    uint8_t* scls = smraw + (DIRECT ? CLK_WIN_BYTES : SIX_MAX_CLASSES * sizeof(uint32_t));
+    uint8_t* scls = smraw + (DIRECT ? 0 : SIX_MAX_CLASSES * sizeof(uint32_t));
     if (!DIRECT) for (int i = threadIdx.x; i < SIX_MAX_CLASSES; i += blockDim.x) sthi[i] = a.thi[i];
-    else clk_win64_store(smraw, (unsigned long long)((a.q - 1) << 16));
     if (SMEM || DIRECT) {
         const uint4* src = reinterpret_cast<const uint4*>(DIRECT ? reinterpret_cast<const uint8_t*>(a.thr16) : a.cls);
         uint4* dst = reinterpret_cast<uint4*>(scls);
@@ -271,8 +234,6 @@ sixclock_pass_kernel(const __grid_constant__ SixArgs a)
     sm.cls_addr = (uint32_t)__cvta_generic_to_shared(scls);
     sm.sthi = sthi;
     sm.gcls = a.cls;
-    unsigned long long win = 0;
-    if (DIRECT) win = clk_win64(smraw);
     const int nvr = a.nvr, ny = a.ny;
     // linear vector index idx = (replica ny + y) nvr + v of this thread; (y, v, replica) advanced incrementally: no
     // division in the loop
@@ -284,8 +245,8 @@ sixclock_pass_kernel(const __grid_constant__ SixArgs a)
     int rep = Y / ny, y = Y - rep * ny;
     while (idx < total) {
         if (DIRECT) {
-            if ((y + a.colour) & 1) six_vector_direct<1, Q>(a, scls, win, idx, y, rep, v);
-            else six_vector_direct<0, Q>(a, scls, win, idx, y, rep, v);
+            if ((y + a.colour) & 1) six_vector_direct<1, Q>(a, scls, idx, y, rep, v);
+            else six_vector_direct<0, Q>(a, scls, idx, y, rep, v);
         } else {
             if ((y + a.colour) & 1) six_vector<SMEM, 1>(a, sm, idx, y, rep, v);
             else six_vector<SMEM, 0>(a, sm, idx, y, rep, v);
@@ -549,7 +510,7 @@ int build_tables(Six* m)
 #undef E3
     thi.resize(SIX_MAX_CLASSES, 0); tlo.resize(SIX_MAX_CLASSES, 0);
     // direct table (q <= 6): T[k][F] = thr >> 17 (0 .. 32768), k = 0 .. q - 2 (new = c + 1 + k mod q),
-    // F = r + q u + q^2 l + q^3 d + q^4 c; the slab k = q - 1 is padding (read by a proposal that is redone as a tie)
+    // F = r + q u + q^2 l + q^3 d + q^4 c (the last q^5 entries of the buffer are unused)
     std::vector<uint16_t> thr16(q6, 0);
     {
         const size_t q5 = q6 / q;
@@ -597,7 +558,8 @@ int sweep(Six* m)
             CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
         }
         COUNT_LAUNCH();
-        if (m->direct && m->q == 6) sixclock_pass_kernel<false, true, 6><<<m->grid, SIX_DIRECT_THREADS, m->smem_bytes, m->stream>>>(a);
+        if (m->direct && m->q == 6 && m->threads == 1024) sixclock_pass_kernel<false, true, 6, 1024><<<m->grid, 1024, m->smem_bytes, m->stream>>>(a);
+        else if (m->direct && m->q == 6) sixclock_pass_kernel<false, true, 6><<<m->grid, SIX_DIRECT_THREADS, m->smem_bytes, m->stream>>>(a);
         else if (m->direct) sixclock_pass_kernel<false, true><<<m->grid, SIX_DIRECT_THREADS, m->smem_bytes, m->stream>>>(a);
         else if (m->cls_in_smem) sixclock_pass_kernel<true><<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
         else sixclock_pass_kernel<false><<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
@@ -737,7 +699,7 @@ int b200mc_sixclock_create_variant(void** out, int64_t nx, int64_t ny, double kb
     // direct lookup: 2 q^6 bytes of thresholds in shared memory, one block of SIX_DIRECT_THREADS threads per SM
     m->direct = 0; m->threads = 256;
     {
-        const size_t wantd = CLK_WIN_BYTES + (2 * q6 + 15) / 16 * 16;
+        const size_t wantd = (2 * q6 + 15) / 16 * 16;
         const char* t = getenv("B200MC_SIX_DIRECT");
         int occd = 0;
         if (wantd <= (size_t)maxsm && !(t && atoi(t) == 0) &&
@@ -745,7 +707,10 @@ int b200mc_sixclock_create_variant(void** out, int64_t nx, int64_t ny, double kb
             cudaFuncSetAttribute(sixclock_pass_kernel<false, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wantd) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, sixclock_pass_kernel<false, true>, SIX_DIRECT_THREADS, wantd) == cudaSuccess && occd >= 1) {
             m->direct = 1; m->threads = SIX_DIRECT_THREADS; m->smem_bytes = (int)wantd;
-            const int64_t needd = ((int64_t)n_multi * ny * nvr + SIX_DIRECT_THREADS - 1) / SIX_DIRECT_THREADS;
+            const char* tt = getenv("B200MC_SIX_THREADS");   // A/B: 1024-thread blocks (64 registers) for q = 6
+            if (tt && atoi(tt) == 1024 && mstate == 6 &&
+                cudaFuncSetAttribute(sixclock_pass_kernel<false, true, 6, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wantd) == cudaSuccess) m->threads = 1024;
+            const int64_t needd = ((int64_t)n_multi * ny * nvr + m->threads - 1) / m->threads;
             m->grid = (int)(needd < (int64_t)m->sms * occd ? needd : (int64_t)m->sms * occd);
         } else cudaGetLastError();
     }

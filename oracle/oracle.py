@@ -111,10 +111,10 @@ def _declare(L):
     d("orc_ising_uniforms_rep", None, u32, u64, u32, i64, P)
     d("orc_ring_init_uniforms_rep", None, u32, u64, u32, i64, P)
     d("orc_ring_init_uniforms", None, u32, u64, i64, P)
-    d("orc_clock_uniforms", None, u32, u64, i32, i64, P, P)
+    d("orc_clock_uniforms", None, u32, u64, i32, i64, i32, P, P)
     d("orc_xy_uniforms", None, u32, u64, i64, i64, P, P)
     d("orc_xy_init_uniforms", None, u32, u64, i64, i64, P)
-    d("orc_torus_uniforms", None, u32, u64, i32, i64, i64, P)
+    d("orc_torus_uniforms", None, u32, u64, i32, i64, i64, i32, P)
     d("orc_xyh_norishiro", None, i64, i64, P)
     d("orc_xyh_set_allup", None, i64, i64, P)
     d("orc_xyh_set_random", None, i64, i64, P, P)
@@ -182,10 +182,10 @@ def ring_init_uniforms(seed: int, draw: int, n_sites: int) -> np.ndarray:
     return out
 
 
-def clock_uniforms(seed: int, draw: int, replica: int, n_sites: int):
+def clock_uniforms(seed: int, draw: int, replica: int, n_sites: int, q: int = 6):
     r = np.empty(n_sites, dtype=np.float64)
     p = np.empty(n_sites, dtype=np.float64)
-    lib().orc_clock_uniforms(seed & 0xFFFFFFFF, draw, replica, n_sites, _p(r), _p(p))
+    lib().orc_clock_uniforms(seed & 0xFFFFFFFF, draw, replica, n_sites, q, _p(r), _p(p))
     return r, p
 
 
@@ -196,10 +196,10 @@ def xy_uniforms(seed: int, draw: int, nx: int, ny: int):
     return r, c
 
 
-def torus_uniforms(seed: int, draw: int, replica: int, nx: int, ny: int) -> np.ndarray:
+def torus_uniforms(seed: int, draw: int, replica: int, nx: int, ny: int, q: int = 6) -> np.ndarray:
     """rnds(2, nx, ny) of update_metropolis (src/clock/clock_tableall_gpu_m.f90:95), flat"""
     out = np.empty(2 * nx * ny, dtype=np.float64)
-    lib().orc_torus_uniforms(seed & 0xFFFFFFFF, draw, replica, nx, ny, _p(out))
+    lib().orc_torus_uniforms(seed & 0xFFFFFFFF, draw, replica, nx, ny, q, _p(out))
     return out
 
 
@@ -425,7 +425,7 @@ class clock_gpu:
     def update(self, randoms=None, next_states=None):
         for j in range(self.n_multi_):
             if randoms is None:
-                r, p = clock_uniforms(self.seed_, self.draw_, j, self.nall_)
+                r, p = clock_uniforms(self.seed_, self.draw_, j, self.nall_, self.q_)
             else:
                 r = np.ascontiguousarray(np.asarray(randoms).reshape(self.n_multi_, -1)[j], dtype=np.float64)
                 p = np.ascontiguousarray(np.asarray(next_states).reshape(self.n_multi_, -1)[j], dtype=np.float64)

@@ -144,54 +144,79 @@ ORC_API void orc_ring_init_uniforms(uint32_t seed, uint64_t draw, int64_t n_site
 }
 
 /* --------------------------------------------------------------------------
- * Clock models, contract v2: the two 32-bit uniforms of a site (accept, proposal)
- * assembled from half-words of two Philox blocks.  One block R serves the four
- * sites e = 0..3 of a 32-bit word of states, a second block R2 (sub-counter + 4)
- * supplies the low halves (the GPU only evaluates R2 when the first look -- 15
- * accept bits, 16 proposal bits -- does not decide; the value is the same):
- *   half(w, hs) = hs ? w >> 16 : w & 0xFFFF,   hs = e >> 1
- *   accept    a16 = half(R[e & 1], hs),       a16' = half(R2[e & 1], hs)
- *   proposal  p16 = half(R[2 + (e & 1)], hs),  p16' = half(R2[2 + (e & 1)], hs)
- *   U_a = (a16 & 0x7FFF) << 17 | (a16 >> 15) << 16 | a16'     U_p = p16 << 16 | p16'
- * (cuda_fortran_mc_simulation_spin_b200/csrc/clock_word.cuh)
+ * Clock models, contract v3 (cuda_fortran_mc_simulation_spin_b200/csrc/clock_word.cuh): the two 32-bit
+ * uniforms (accept, proposal) of the 16 sites of a vector = words w = 0..3 of sites e = 0..3.
+ * X[0..11] = the words of the Philox blocks with sub-counters 0, 1, 2; Y[0..11] = sub-counters
+ * 4, 5, 6 (the GPU only evaluates Y when the first look at an accept uniform -- 15 bits --
+ * does not decide; the value is the same):
+ *   half(x, hs) = hs ? x >> 16 : x & 0xFFFF
+ *   accept    a16 = half(X[3w + (e & 1)], e >> 1),  a16' = half(Y[3w + (e & 1)], e >> 1)
+ *             U_a = (a16 & 0x7FFF) << 17 | (a16 >> 15) << 16 | a16'
+ *   proposal  W_0 = X[3w + 2],  W_e = low32(W_(e-1) pm):  the proposals of the four sites are
+ *             the leading base-pm digits d_e = floor(W_e pm / 2^32) of ONE uniform (pm = the
+ *             number of proposal cells: q - 1 for new = c + ceiling(u (q-1)),
+ *             src/clock/clock_tableall_gpu_m.f90:142; q for floor(u q), src/clock_gpu_m.f90:211).
+ *             The array entry is U_p = W_e, nudged to W_e - 1 in the ~pm 2^-32 of all cases
+ *             where the "+ 1" of u = (U + 1) 2^-32 would carry u pm across the cell boundary,
+ *             so that the reference's own rounding of the real64 u reproduces d_e.
  * -------------------------------------------------------------------------- */
 static inline uint32_t clk_half(uint32_t w, int hs) { return hs ? w >> 16 : w & 0xFFFFu; }
-static inline void clk_uniform_pair(const uint32_t r[4], const uint32_t r2[4], int e, uint32_t *Ua, uint32_t *Up)
+static inline uint32_t clk_cell(uint32_t U, uint32_t pm, int periodic)
 {
-    const int hs = e >> 1;
-    const uint32_t a16 = clk_half(r[e & 1], hs), a16b = clk_half(r2[e & 1], hs);
-    const uint32_t p16 = clk_half(r[2 + (e & 1)], hs), p16b = clk_half(r2[2 + (e & 1)], hs);
-    *Ua = ((a16 & 0x7FFFu) << 17) | ((a16 >> 15) << 16) | a16b;
-    *Up = (p16 << 16) | p16b;
+    if (periodic) return (uint32_t)((((uint64_t)U + 1u) * pm + 0xFFFFFFFFull) >> 32) - 1u;   /* ceiling(u pm) - 1 */
+    uint32_t k = (uint32_t)((((uint64_t)U + 1u) * pm) >> 32);                                 /* min(floor(u pm), pm - 1) */
+    return k < pm - 1 ? k : pm - 1;
+}
+static void clk_vector_uniforms(uint64_t blk, uint64_t draw, uint32_t colour, const uint32_t key[2], uint32_t pm, int periodic,
+                                uint32_t Ua[16], uint32_t Up[16])
+{
+    uint32_t X[12], Y[12], c[4];
+    for (uint32_t i = 0; i < 3; ++i) {
+        mk_ctr(c, blk, draw, colour, i);
+        orc_philox4x32_10(c, key, X + 4 * i);
+        mk_ctr(c, blk, draw, colour, 4u + i);
+        orc_philox4x32_10(c, key, Y + 4 * i);
+    }
+    for (int w = 0; w < 4; ++w) {
+        uint32_t W = X[3 * w + 2];
+        for (int e = 0; e < 4; ++e) {
+            const int hs = e >> 1;
+            const uint32_t a16 = clk_half(X[3 * w + (e & 1)], hs), a16b = clk_half(Y[3 * w + (e & 1)], hs);
+            Ua[4 * w + e] = ((a16 & 0x7FFFu) << 17) | ((a16 >> 15) << 16) | a16b;
+            const uint64_t prod = (uint64_t)W * pm;
+            const uint32_t d = (uint32_t)(prod >> 32);
+            uint32_t U = W;
+            if (clk_cell(U, pm, periodic) != d) U = W - 1u;
+            Up[4 * w + e] = U;
+            W = (uint32_t)prod;
+        }
+    }
 }
 
 /* --------------------------------------------------------------------------
- * Clock, helical ring (clock_gpu_m / clock_gpu_multi_m): two 32-bit uniforms
- * per site and sweep, same fold as Ising.  For vector p, colour c, replica j,
- * byte lane `lane` (word w = lane >> 2, e = lane & 3):
- *   R  = philox(ctr(p, draw, c,     w), (seed, TAG_CLOCK + j))
- *   R2 = philox(ctr(p, draw, c, 4 + w), same key)
- *   accept U_a -> randoms(idx), proposal U_p -> next_states(idx)   (clk_uniform_pair)
+ * Clock, helical ring (clock_gpu_m / clock_gpu_multi_m): same fold as Ising.  Vector p,
+ * colour c, replica j, byte lane `lane` = site 4w + e of the vector:
+ *   blocks philox(ctr(p, draw, c, sub), (seed, TAG_CLOCK + j)), pm = q
+ *   accept U_a -> randoms(idx), proposal U_p -> next_states(idx)   (clk_vector_uniforms)
  * -------------------------------------------------------------------------- */
-ORC_API void orc_clock_uniforms(uint32_t seed, uint64_t draw, int32_t replica, int64_t n_sites,
+ORC_API void orc_clock_uniforms(uint32_t seed, uint64_t draw, int32_t replica, int64_t n_sites, int32_t q,
                                 double *randoms, double *next_states)
 {
-    const int64_t L = orc_ring_fold_len(n_sites);
+    const int64_t L = orc_ring_fold_len(n_sites), nc = n_sites / 2;
+    const uint32_t key[2] = {seed, TAG_CLOCK + (uint32_t)replica};
 #pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < n_sites; ++i) {
-        uint32_t colour = (uint32_t)(i & 1);
-        int64_t k = i >> 1;
-        int lane = (int)(k / L);
-        uint64_t p = (uint64_t)(k % L);
-        uint32_t key[2] = {seed, TAG_CLOCK + (uint32_t)replica}, c[4], r[4], r2[4], Ua, Up;
-        mk_ctr(c, p, draw, colour, (uint32_t)(lane >> 2));
-        orc_philox4x32_10(c, key, r);
-        mk_ctr(c, p, draw, colour, 4u + (uint32_t)(lane >> 2));
-        orc_philox4x32_10(c, key, r2);
-        clk_uniform_pair(r, r2, lane & 3, &Ua, &Up);
-        randoms[i] = ((double)Ua + 1.0) * 0x1p-32;
-        next_states[i] = ((double)Up + 1.0) * 0x1p-32;
-    }
+    for (int64_t p = 0; p < L; ++p)
+        for (uint32_t colour = 0; colour < 2; ++colour) {
+            uint32_t Ua[16], Up[16];
+            clk_vector_uniforms((uint64_t)p, draw, colour, key, (uint32_t)q, 0, Ua, Up);
+            for (int lane = 0; lane < 16; ++lane) {
+                const int64_t k = (int64_t)lane * L + p;
+                if (k >= nc) continue;
+                const int64_t i = 2 * k + colour;
+                randoms[i] = ((double)Ua[lane] + 1.0) * 0x1p-32;
+                next_states[i] = ((double)Up[lane] + 1.0) * 0x1p-32;
+            }
+        }
 }
 
 /* block-wise evaluation of orc_ising_uniforms (same values, 5 Philox calls per
@@ -275,35 +300,33 @@ ORC_API void orc_xy_init_uniforms(uint32_t seed, uint64_t draw, int64_t nx, int6
  * Periodic clock (clock_tableall_gpu_m / clock_dual_lattice_tableall_gpu_m): true torus,
  * colour = (x0 + y0) & 1, colour-compact index xi = x0 >> 1; rows are cut into vectors of 16
  * compact sites: v = xi >> 4, j = xi & 15, nvr = ceil((nx/2) / 16), block = y0 * nvr + v.
- * Two 32-bit uniforms per site and sweep (contract v2, clk_uniform_pair above), word w = j >> 2, e = j & 3:
- *   R  = philox(ctr(block, draw, colour,     w), (seed, TAG_TORUS + replica))
- *   R2 = philox(ctr(block, draw, colour, 4 + w), same key)
+ * Two 32-bit uniforms per site and sweep (contract v3, clk_vector_uniforms above), pm = q - 1:
+ *   blocks philox(ctr(replica << 32 | block, draw, colour, sub), (seed, TAG_TORUS))
  *   accept   U_a -> rnds(2, x, y)      proposal U_p -> rnds(1, x, y)
+ * (the sample index of a batch is the high word of the block counter, as for the Ising batches)
  * u = (U + 1) 2^-32.  Written in the reference's order rnds(2, nx, ny)
  * (src/clock/clock_tableall_gpu_m.f90:95): out[(j-1) + 2*(x0 + nx*y0)].
  * -------------------------------------------------------------------------- */
-ORC_API void orc_torus_uniforms(uint32_t seed, uint64_t draw, int32_t replica, int64_t nx, int64_t ny,
+ORC_API void orc_torus_uniforms(uint32_t seed, uint64_t draw, int32_t replica, int64_t nx, int64_t ny, int32_t q,
                                 double *rnds)
 {
     const int64_t nxh = nx / 2, nvr = (nxh + 15) / 16;
-    const uint32_t key[2] = {seed, TAG_TORUS + (uint32_t)replica};
+    const uint32_t key[2] = {seed, TAG_TORUS};
 #pragma omp parallel for schedule(static)
     for (int64_t y0 = 0; y0 < ny; ++y0)
-        for (int64_t x0 = 0; x0 < nx; ++x0) {
-            const uint32_t colour = (uint32_t)((x0 + y0) & 1);
-            const int64_t xi = x0 >> 1;
-            const int j = (int)(xi & 15);
-            const uint64_t blk = (uint64_t)(y0 * nvr + (xi >> 4));
-            uint32_t c[4], r[4], r2[4];
-            mk_ctr(c, blk, draw, colour, (uint32_t)(j >> 2));
-            orc_philox4x32_10(c, key, r);
-            mk_ctr(c, blk, draw, colour, 4u + (uint32_t)(j >> 2));
-            orc_philox4x32_10(c, key, r2);
-            uint32_t Ua, Up;
-            clk_uniform_pair(r, r2, j & 3, &Ua, &Up);
-            rnds[0 + 2 * (x0 + nx * y0)] = ((double)Up + 1.0) * 0x1p-32;
-            rnds[1 + 2 * (x0 + nx * y0)] = ((double)Ua + 1.0) * 0x1p-32;
-        }
+        for (int64_t v = 0; v < nvr; ++v)
+            for (uint32_t colour = 0; colour < 2; ++colour) {
+                uint32_t Ua[16], Up[16];
+                const uint64_t blk = (uint64_t)(y0 * nvr + v) | ((uint64_t)(uint32_t)replica << 32);
+                clk_vector_uniforms(blk, draw, colour, key, (uint32_t)(q - 1), 1, Ua, Up);
+                for (int j = 0; j < 16; ++j) {
+                    const int64_t xi = 16 * v + j;
+                    if (xi >= nxh) break;
+                    const int64_t x0 = 2 * xi + (int64_t)((y0 + colour) & 1);
+                    rnds[0 + 2 * (x0 + nx * y0)] = ((double)Up[j] + 1.0) * 0x1p-32;
+                    rnds[1 + 2 * (x0 + nx * y0)] = ((double)Ua[j] + 1.0) * 0x1p-32;
+                }
+            }
 }
 
 /* --------------------------------------------------------------------------

@@ -70,7 +70,7 @@ def sixclock_cases(O):
         hists = []
         for s in range(sweeps):
             for j, o in enumerate(os_):
-                o.update_metropolis(O.torus_uniforms(seed, s, j, nx, ny))
+                o.update_metropolis(O.torus_uniforms(seed, s, j, nx, ny, q))
             hists.append([o.histograms()[0].tolist() for o in os_])
         out.append({"model": "sixclock", "shape": list(shape), "q": q, "kbt": kbt, "seed": seed, "n_multi": n_multi,
                     "hist": hists, "states_sha256": sha(np.stack([o.c for o in os_])),

@@ -42,7 +42,7 @@ def test_tableall_trajectory_bit_exact(oracle, shape, q, kbt, lookup):
     assert abs(g.calc_energy()[0] + 2.0) < 1e-12 and abs(g.calc_magne()[0] - 1.0) < 1e-12   # ordered start
     for sweep in range(4):
         g.update_metropolis()
-        o.update_metropolis(oracle.torus_uniforms(42, sweep, 0, nx, ny))
+        o.update_metropolis(oracle.torus_uniforms(42, sweep, 0, nx, ny, q))
         assert np.array_equal(g.get_sixclock()[0], o.c), f"states differ after sweep {sweep + 1}"
         h, br, bu = g.histograms()
         oh, obr, obu = _oracle_hist(o)
@@ -97,7 +97,7 @@ def test_update_with_rnds_reference_stream(oracle, shape):
 
 
 def test_multi_sample_batch(oracle, lookup):
-    """n_multi independent samples in one launch per colour; sample j uses the key TAG_TORUS + j"""
+    """n_multi independent samples in one launch per colour; sample j is the high word of the Philox block counter"""
     from cuda_fortran_mc_simulation_spin_b200._sixclock import sixclock
     nx, ny, n = 48, 16, 3
     g = sixclock(nx, ny, 0.8, 6, n, 42)

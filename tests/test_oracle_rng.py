@@ -41,59 +41,89 @@ def test_uniform_histogram_flat(oracle):
     assert chi2 < 120, chi2
 
 
-def _clk_pair(r, r2, e):
-    """contract v2 (csrc/clock_word.cuh, oracle/rng_contract.c clk_uniform_pair), restated in Python"""
+def _clk_vector(oracle, blk_lo, blk_hi, draw, colour, key, pm, periodic):
+    """contract v3 (csrc/clock_word.cuh, oracle/rng_contract.c clk_vector_uniforms), restated in Python: the accept and
+    proposal uniforms (as 32-bit integers U, u = (U + 1) 2^-32) of the 16 sites of a vector"""
+    c3 = lambda sub: ((draw >> 32) & 0xFFFF) | (colour << 16) | (sub << 24)
+    X = np.concatenate([oracle.philox([blk_lo, blk_hi, draw & 0xFFFFFFFF, c3(i)], key) for i in range(3)])
+    Y = np.concatenate([oracle.philox([blk_lo, blk_hi, draw & 0xFFFFFFFF, c3(4 + i)], key) for i in range(3)])
     half = lambda w, hs: (int(w) >> 16) if hs else (int(w) & 0xFFFF)
-    hs = e >> 1
-    a16, a16b = half(r[e & 1], hs), half(r2[e & 1], hs)
-    p16, p16b = half(r[2 + (e & 1)], hs), half(r2[2 + (e & 1)], hs)
-    return ((a16 & 0x7FFF) << 17) | ((a16 >> 15) << 16) | a16b, (p16 << 16) | p16b
+    ua, up, digits = [], [], []
+    for w in range(4):
+        W = int(X[3 * w + 2])
+        for e in range(4):
+            a16, a16b = half(X[3 * w + (e & 1)], e >> 1), half(Y[3 * w + (e & 1)], e >> 1)
+            ua.append(((a16 & 0x7FFF) << 17) | ((a16 >> 15) << 16) | a16b)
+            d = (W * pm) >> 32
+            # what the reference computes from u = (U + 1) 2^-32: ceiling(u pm) - 1 (periodic) or min(floor(u pm), pm - 1)
+            cell = lambda U: (-(-((U + 1) * pm) // 2 ** 32) - 1) if periodic else min(((U + 1) * pm) >> 32, pm - 1)
+            U = W if cell(W) == d else (W - 1) % 2 ** 32
+            assert cell(U) == d
+            up.append(U); digits.append(d)
+            W = (W * pm) & 0xFFFFFFFF
+    return ua, up, digits
 
 
-def test_clock_contract_v2_assembly(oracle):
+def test_clock_contract_v3_assembly(oracle):
     """the periodic-clock and helical-clock uniform arrays, site by site, from the Philox blocks the contract names"""
     TAG_TORUS, TAG_CLOCK = 0x544F5253, 0x434C4F4B
     seed, draw, rep, nx, ny = 42, 3, 2, 72, 6          # nx/2 = 36: three vectors per row, the last one partial
-    rn = oracle.torus_uniforms(seed, draw, rep, nx, ny).reshape(ny, nx, 2)
-    nvr = (nx // 2 + 15) // 16
-    for y0 in range(ny):
-        for x0 in range(0, nx, 5):
-            colour, xi = (x0 + y0) & 1, x0 >> 1
-            j, blk = xi & 15, y0 * nvr + (xi >> 4)
-            c3 = lambda sub: ((draw >> 32) & 0xFFFF) | (colour << 16) | (sub << 24)
-            r = oracle.philox([blk, 0, draw, c3(j >> 2)], [seed, TAG_TORUS + rep])
-            r2 = oracle.philox([blk, 0, draw, c3(4 + (j >> 2))], [seed, TAG_TORUS + rep])
-            ua, up = _clk_pair(r, r2, j & 3)
-            assert rn[y0, x0, 0] == (up + 1) * 2.0 ** -32 and rn[y0, x0, 1] == (ua + 1) * 2.0 ** -32
+    for q in (6, 5):
+        rn = oracle.torus_uniforms(seed, draw, rep, nx, ny, q).reshape(ny, nx, 2)
+        nvr = (nx // 2 + 15) // 16
+        for y0 in range(ny):
+            for v in range(nvr):
+                for colour in range(2):
+                    ua, up, dg = _clk_vector(oracle, y0 * nvr + v, rep, draw, colour, [seed, TAG_TORUS], q - 1, True)
+                    for j in range(16):
+                        xi = 16 * v + j
+                        if xi >= nx // 2:
+                            break
+                        x0 = 2 * xi + ((y0 + colour) & 1)
+                        assert rn[y0, x0, 0] == (up[j] + 1) * 2.0 ** -32 and rn[y0, x0, 1] == (ua[j] + 1) * 2.0 ** -32
+                        assert int(np.ceil(rn[y0, x0, 0] * (q - 1))) == dg[j] + 1      # the reference's own expression (:142)
     n = 101 * 100
     L = (n // 2 + 15) // 16
-    ra, rp = oracle.clock_uniforms(seed, draw, rep, n)
-    for i in range(0, n, 37):
-        colour, k = i & 1, i >> 1
-        lane, p = k // L, k % L
-        c3 = lambda sub: ((draw >> 32) & 0xFFFF) | (colour << 16) | (sub << 24)
-        r = oracle.philox([p, 0, draw, c3(lane >> 2)], [seed, TAG_CLOCK + rep])
-        r2 = oracle.philox([p, 0, draw, c3(4 + (lane >> 2))], [seed, TAG_CLOCK + rep])
-        ua, up = _clk_pair(r, r2, lane & 3)
-        assert ra[i] == (ua + 1) * 2.0 ** -32 and rp[i] == (up + 1) * 2.0 ** -32
+    ra, rp = oracle.clock_uniforms(seed, draw, rep, n, 6)
+    for p in list(range(0, L, 29)) + [L - 1]:
+        for colour in range(2):
+            ua, up, dg = _clk_vector(oracle, p, 0, draw, colour, [seed, TAG_CLOCK + rep], 6, False)
+            for lane in range(16):
+                k = lane * L + p
+                if k >= n // 2:
+                    continue
+                i = 2 * k + colour
+                assert ra[i] == (ua[lane] + 1) * 2.0 ** -32 and rp[i] == (up[lane] + 1) * 2.0 ** -32
+                assert min(int(np.floor(rp[i] * 6)), 5) == dg[lane]                    # src/clock_gpu_m.f90:211
 
 
-def test_clock_contract_v2_statistics(oracle):
-    """accept and proposal uniforms: (0, 1], 32-bit resolution, flat first-look fields, no correlation between the two or
-    between the sites that share a Philox word"""
-    rn = oracle.torus_uniforms(5, 1, 0, 512, 256).reshape(-1, 2)
-    for col in (0, 1):
-        u = rn[:, col]
+def test_clock_contract_v3_statistics(oracle):
+    """accept uniforms: (0, 1], 32-bit resolution, flat first-look field and flat lazily evaluated low half; proposals: the
+    digits are uniform, the digits of the four sites that share a proposal word are pairwise independent, and proposal and
+    accept uniforms are uncorrelated"""
+    nx, ny, q = 512, 256, 6
+    rn = oracle.torus_uniforms(5, 1, 0, nx, ny, q).reshape(-1, 2)
+    ua, upr = rn[:, 1], rn[:, 0]
+    for u in (ua, upr):
         assert u.min() > 0.0 and u.max() <= 1.0
         k = u * 2.0 ** 32
         assert np.array_equal(k, np.round(k)) and abs(u.mean() - 0.5) < 0.005
-        h, _ = np.histogram(u, bins=256, range=(0, 1))
-        chi2 = ((h - u.size / 256) ** 2 / (u.size / 256)).sum()
-        assert chi2 < 360, chi2                       # 255 dof: mean 255, sd ~23
-        low = (k - 1).astype(np.uint64) & 0xFFFF      # the lazily evaluated low half
-        h2, _ = np.histogram(low, bins=64, range=(0, 65536))
-        assert ((h2 - u.size / 64) ** 2 / (u.size / 64)).sum() < 120
-    assert abs(np.corrcoef(rn[:, 0], rn[:, 1])[0, 1]) < 0.01
-    ua = rn[:, 1].reshape(256, 512)
-    # sites e and e + 2 of a word (compact positions xi and xi + 2 -> x0 and x0 + 4) share a Philox word
-    assert abs(np.corrcoef(ua[:, :-4].ravel(), ua[:, 4:].ravel())[0, 1]) < 0.01
+    h, _ = np.histogram(ua, bins=256, range=(0, 1))
+    chi2 = ((h - ua.size / 256) ** 2 / (ua.size / 256)).sum()
+    assert chi2 < 360, chi2                           # 255 dof: mean 255, sd ~23
+    low = (ua * 2.0 ** 32 - 1).astype(np.uint64) & 0xFFFF      # the lazily evaluated low half
+    h2, _ = np.histogram(low, bins=64, range=(0, 65536))
+    assert ((h2 - ua.size / 64) ** 2 / (ua.size / 64)).sum() < 120
+    assert abs(np.corrcoef(ua, upr)[0, 1]) < 0.01
+    # digits per site, on the colour-compact grid: sites xi = 4 g + e, e = 0..3 share one proposal word
+    dig = (np.ceil(upr * (q - 1)).astype(np.int64) - 1).reshape(ny, nx)
+    cnt = np.bincount(dig.ravel(), minlength=q - 1)
+    assert cnt.size == q - 1 and (((cnt - dig.size / (q - 1)) ** 2) / (dig.size / (q - 1))).sum() < 25     # 4 dof
+    # x0 = 2 xi + P: on even rows colour 0 has P = 0; take colour-0 sites of even rows
+    d0 = dig[0::2, 0::2].reshape(ny // 2, nx // 8, 4)       # [row, word, e]
+    for e1 in range(4):
+        for e2 in range(e1 + 1, 4):
+            joint = np.zeros((q - 1, q - 1))
+            np.add.at(joint, (d0[:, :, e1].ravel(), d0[:, :, e2].ravel()), 1)
+            exp = d0[:, :, 0].size / (q - 1) ** 2
+            assert (((joint - exp) ** 2) / exp).sum() < 60, (e1, e2)          # 24 dof: mean 24, sd ~7
