@@ -24,7 +24,7 @@ struct Clock {
     uint8_t* d_cls;
     uint64_t* d_thr;
     uint16_t* d_thr16;     // direct lookup table (q <= 6)
-    int direct, grid_direct, smem_direct;
+    int direct, grid_direct, smem_direct, threads_direct;
     int sample0;           // this handle holds samples sample0 .. sample0 + n_multi - 1 of the job (batch split across GPUs)
     double* d_ws;
     double* d_rand;
@@ -127,7 +127,8 @@ int sweep(Clock* m)
             ClockArgs a;
             fill_args(m, j, colour, &a);
             COUNT_LAUNCH();
-            if (m->direct && m->q == 6) clock_pass_direct_kernel<6><<<m->grid_direct, CLOCK_DIRECT_THREADS, m->smem_direct, m->stream>>>(a);
+            if (m->direct && m->q == 6 && m->threads_direct == 1024) clock_pass_direct_kernel<6, 1024><<<m->grid_direct, 1024, m->smem_direct, m->stream>>>(a);
+            else if (m->direct && m->q == 6) clock_pass_direct_kernel<6><<<m->grid_direct, CLOCK_DIRECT_THREADS, m->smem_direct, m->stream>>>(a);
             else if (m->direct) clock_pass_direct_kernel<0><<<m->grid_direct, CLOCK_DIRECT_THREADS, m->smem_direct, m->stream>>>(a);
             else clock_pass_kernel<<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
             CK(cudaGetLastError());
@@ -255,8 +256,11 @@ int create(void** out, int64_t nx, int64_t ny, double kbt, int32_t q, int32_t n_
             cudaFuncSetAttribute(clock_pass_direct_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wantd) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, clock_pass_direct_kernel<0>, CLOCK_DIRECT_THREADS, wantd) == cudaSuccess && occd >= 1 &&
             cudaMalloc(&m->d_thr16, (2 * q6 + 15) / 16 * 16) == cudaSuccess) {
-            m->direct = 1; m->smem_direct = (int)wantd;
-            const int64_t needd = (g.L + CLOCK_DIRECT_THREADS - 1) / CLOCK_DIRECT_THREADS;
+            m->direct = 1; m->smem_direct = (int)wantd; m->threads_direct = CLOCK_DIRECT_THREADS;
+            const char* tt = getenv("B200MC_CLOCK_THREADS");   // A/B: 1024-thread blocks (64 registers) for q = 6
+            if (tt && atoi(tt) == 1024 && q == 6 &&
+                cudaFuncSetAttribute(clock_pass_direct_kernel<6, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wantd) == cudaSuccess) m->threads_direct = 1024;
+            const int64_t needd = (g.L + m->threads_direct - 1) / m->threads_direct;
             m->grid_direct = (int)(needd < (int64_t)sms * occd ? needd : (int64_t)sms * occd);
         } else cudaGetLastError();
     }

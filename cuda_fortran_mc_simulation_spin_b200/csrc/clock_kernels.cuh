@@ -126,8 +126,8 @@ clock_pass_kernel(const __grid_constant__ ClockArgs a)
 // Direct-table variant (q <= 6; one CLOCK_DIRECT_THREADS-thread block per SM): clock_word.cuh.  Shared memory: the table
 // T[next][F] (q slabs of 2 q^5 bytes).  Q = q at compile time (0: run time).
 #define CLOCK_DIRECT_THREADS 768
-template <int Q>
-__global__ void __launch_bounds__(CLOCK_DIRECT_THREADS, 1)
+template <int Q, int THREADS = CLOCK_DIRECT_THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 clock_pass_direct_kernel(const __grid_constant__ ClockArgs a)
 {
     extern __shared__ __align__(16) uint8_t tab[];

@@ -707,8 +707,10 @@ int b200mc_sixclock_create_variant(void** out, int64_t nx, int64_t ny, double kb
             cudaFuncSetAttribute(sixclock_pass_kernel<false, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wantd) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, sixclock_pass_kernel<false, true>, SIX_DIRECT_THREADS, wantd) == cudaSuccess && occd >= 1) {
             m->direct = 1; m->threads = SIX_DIRECT_THREADS; m->smem_bytes = (int)wantd;
-            const char* tt = getenv("B200MC_SIX_THREADS");   // A/B: 1024-thread blocks (64 registers) for q = 6
-            if (tt && atoi(tt) == 1024 && mstate == 6 &&
+            // q = 6: 1024-thread blocks (64 registers) measured 4-6 % faster than 768 x 80 (873 / 951 vs 843 / 893 flips/ns at
+            // 16384^2 x 1 / x 4 samples); B200MC_SIX_THREADS=768 selects the other instantiation for A/B runs
+            const char* tt = getenv("B200MC_SIX_THREADS");
+            if (!(tt && atoi(tt) == 768) && mstate == 6 &&
                 cudaFuncSetAttribute(sixclock_pass_kernel<false, true, 6, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wantd) == cudaSuccess) m->threads = 1024;
             const int64_t needd = ((int64_t)n_multi * ny * nvr + m->threads - 1) / m->threads;
             m->grid = (int)(needd < (int64_t)m->sms * occd ? needd : (int64_t)m->sms * occd);
