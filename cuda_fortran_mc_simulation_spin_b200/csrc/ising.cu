@@ -913,6 +913,7 @@ int skip(Ising* m, int64_t n_skip)
 extern "C" {
 
 const char* b200mc_last_error(void) { return g_b200mc_err; }
+void b200mc_print_last_error(void) { fprintf(stderr, "b200mc: %s\n", g_b200mc_err); }
 int b200mc_version(void) { return 100; }
 // one row of the drivers' output table (app/ising3d_gpu_relaxation.f90:49-55): nall, num_sample, i, mean1, mean2,
 // square_mean1, square_mean2, nall * var1, nall * var2, nall * cov -- blank-separated like the list-directed '(*(g0, 1x))'

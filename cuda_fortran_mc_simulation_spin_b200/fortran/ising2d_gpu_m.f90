@@ -34,7 +34,11 @@ module ising2d_gpu_m
      !> additions (not in the reference type)
      procedure, pass :: set_method => set_method_ising2d_gpu   !< 0 Metropolis (default), 1 heat-bath
      procedure, pass :: update_n => update_n_ising2d_gpu       !< n MCS back to back
-     procedure, pass :: run_relaxation => run_relaxation_ising2d_gpu  !< mcs x [update; calc_magne_sum; calc_energy_sum] on the device
+     !> mcs x [update; calc_magne_sum; calc_energy_sum] on the device
+     procedure, pass :: run_relaxation => run_relaxation_ising2d_gpu
+     !> the drivers' whole measurement on the device: tot_sample x [initial state; mcs x (update; m; e; add_data)],
+     !> Kahan mean / variance / covariance per MCS (app/ising2d_gpu_relaxation.f90), see include/b200mc.h
+     procedure, pass :: run_relaxation_stats => run_relaxation_stats_ising2d_gpu
      final :: destroy_ising2d_gpu
   end type ising2d_gpu
 
@@ -73,6 +77,11 @@ module ising2d_gpu_m
      integer(c_int) function b200mc_ising2d_run_relaxation(h, mcs, e, m) bind(C, name="b200mc_ising2d_run_relaxation")
        import; type(c_ptr), value :: h; integer(c_int32_t), value :: mcs; integer(c_int64_t), intent(out) :: e(*), m(*)
      end function
+     integer(c_int) function b200mc_ising2d_run_relaxation_stats(h, mcs, tot_sample, random_start, res) &
+         bind(C, name="b200mc_ising2d_run_relaxation_stats")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: mcs, tot_sample, random_start
+       real(c_double), intent(out) :: res(*)
+     end function
      integer(c_int) function b200mc_ising2d_calc_energy_sum(h, e) bind(C, name="b200mc_ising2d_calc_energy_sum")
        import; type(c_ptr), value :: h; integer(c_int64_t), intent(out) :: e
      end function
@@ -97,6 +106,8 @@ module ising2d_gpu_m
      real(c_double) function b200mc_ising2d_beta(h) bind(C, name="b200mc_ising2d_beta")
        import; type(c_ptr), value :: h
      end function
+     subroutine b200mc_print_last_error() bind(C, name="b200mc_print_last_error")
+     end subroutine
   end interface
 contains
   !> src/ising2d_gpu_m.f90:44-61
@@ -107,7 +118,10 @@ contains
     integer(int32), intent(in) :: iseed
     if (c_associated(this%h_)) ising2d_gpu_stat = b200mc_ising2d_destroy(this%h_)
     ising2d_gpu_stat = b200mc_ising2d_create(this%h_, nx, ny, kbt, iseed)
-    if (ising2d_gpu_stat /= 0) error stop "ising2d_gpu%init: b200mc_ising2d_create failed (invalid shape or no CUDA device)"
+    if (ising2d_gpu_stat /= 0) then
+       call b200mc_print_last_error()   ! the library's own message (shape, device, ...) on stderr
+       error stop "ising2d_gpu%init: b200mc_ising2d_create failed (shape must have nx odd, ny even; or no CUDA device)"
+    end if
   end subroutine init_ising2d_gpu
   impure subroutine destroy_ising2d_gpu(this)
     type(ising2d_gpu), intent(inout) :: this
@@ -160,6 +174,14 @@ contains
     integer(int64), intent(out) :: e(mcs), m(mcs)
     ising2d_gpu_stat = b200mc_ising2d_run_relaxation(this%h_, mcs, e, m)
   end subroutine run_relaxation_ising2d_gpu
+  !> res(1:8, i) = num_sample, mean1 (m), mean2 (e), square_mean1, square_mean2, var1, var2, cov after MCS i
+  impure subroutine run_relaxation_stats_ising2d_gpu(this, mcs, tot_sample, random_start, res)
+    class(ising2d_gpu), intent(inout) :: this
+    integer(int32), intent(in) :: mcs, tot_sample
+    logical, intent(in) :: random_start
+    real(real64), intent(out) :: res(8, mcs)
+    ising2d_gpu_stat = b200mc_ising2d_run_relaxation_stats(this%h_, mcs, tot_sample, merge(1_int32, 0_int32, random_start), res)
+  end subroutine run_relaxation_stats_ising2d_gpu
   impure subroutine update_n_ising2d_gpu(this, n_sweeps)
     class(ising2d_gpu), intent(inout) :: this
     integer(int32), intent(in) :: n_sweeps

@@ -40,10 +40,11 @@ extern "C" {
 #define B200MC_HEATBATH 1   /* north-star addition, no reference symbol */
 
 const char* b200mc_last_error(void);
+/* the same message on stderr (what the Fortran shims call before `error stop`: no C string handling on their side) */
+void b200mc_print_last_error(void);
 int b200mc_version(void);
 /* number of CUDA kernels this library has launched so far in this process (all handles) */
 unsigned long long b200mc_launch_count(void);
-/* run the handle's kernels on a caller-provided CUDA stream (cudaStream_t as void*) */
 unsigned long long b200mc_debug_slab_wait_ns(void* h); /* slab mode: ns spent waiting for neighbour flags (block 0) */
 int b200mc_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]); /* device Philox, for KAT tests */
 
