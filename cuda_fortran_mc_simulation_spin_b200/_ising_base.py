@@ -51,6 +51,18 @@ class _IsingBase:
         except Exception:
             pass
 
+    # -- bit-packed storage (one bit per site, Metropolis, one GPU; csrc/ising_bits.cu) ----
+    def _init_packed(self, dims, kbt, iseed):
+        """the same type over the bit-packed handle: same procedures and host layouts, its own random stream"""
+        if self._h:
+            self._f("destroy", C.c_int, P)(self._h)
+            self._h = C.c_void_p(None)
+        self._pfx = self._pfx + "p"          # b200mc_ising3dp_* / b200mc_ising2dp_*
+        self._packed = True
+        f = self._f("create", C.c_int, PP, *([i64] * len(dims)), f64, i32)
+        _lib.check(f(C.byref(self._h), *[int(d) for d in dims], float(kbt), int(iseed)))
+        return self
+
     # -- slab decomposition over ranks (one process per GPU; SURVEY 8e) ----
     def _init_slab(self, dims, kbt, iseed, rank, nranks, nccl_id):
         if self._h:

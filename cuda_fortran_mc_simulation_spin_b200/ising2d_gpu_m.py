@@ -26,6 +26,10 @@ class ising2d_gpu(_IsingBase):
         _lib.check(f(C.byref(self._h), int(nx), int(ny), float(kbt), int(iseed)))
         return self
 
+    def init_packed(self, nx, ny, kbt, iseed):
+        """init on the bit-packed (multi-spin coded) storage: one bit per site, Metropolis, one GPU"""
+        return self._init_packed((nx, ny), kbt, iseed)
+
     def init_slab(self, nx, ny, kbt, iseed, rank, nranks, nccl_id):
         """the global nx x ny lattice, this process owning slab `rank` of `nranks` (one GPU each)"""
         return self._init_slab((nx, ny), kbt, iseed, rank, nranks, nccl_id)

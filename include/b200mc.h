@@ -161,6 +161,62 @@ int b200mc_ising2d_rank_info(void* h, int32_t* rank, int32_t* nranks);
 int b200mc_ring_slab_geometry(int64_t nx, int64_t ny, int64_t nz, int32_t rank, int32_t nranks, int64_t out[6]);
 
 /* ------------------------------------------------------------------------
+ * Bit-packed (multi-spin coded) Ising 3D / 2D: one bit per site, Metropolis, one GPU.  The same procedures of
+ * type(ising3d_gpu) / type(ising2d_gpu) (file:line as for b200mc_ising3d_* / b200mc_ising2d_* above and below), the same
+ * host layouts and conventions; its own random stream (oracle/rng_contract.c, orc_isingbits_uniforms).  Shapes: helical
+ * validity as for the int8 handles, and nx ny nz / 2 a multiple of 128 (e.g. the last extent a multiple of 256) with the
+ * fold not shorter than the halo -> B200MC_ERR_UNSUPPORTED otherwise.
+ * ------------------------------------------------------------------------ */
+int b200mc_ising3dp_create(void** h, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed);
+int b200mc_ising3dp_destroy(void* h);
+int b200mc_ising3dp_set_stream(void* h, void* cuda_stream);
+int b200mc_ising3dp_skip_curand(void* h, int64_t n_skip);
+int b200mc_ising3dp_set_allup_spin(void* h);
+int b200mc_ising3dp_set_random_spin(void* h);
+int b200mc_ising3dp_set_kbt(void* h, double kbt);
+int b200mc_ising3dp_set_beta(void* h, double beta);
+int b200mc_ising3dp_update(void* h);
+int b200mc_ising3dp_update_n(void* h, int32_t n_sweeps);
+int b200mc_ising3dp_calc_energy_sum(void* h, int64_t* e);
+int b200mc_ising3dp_calc_magne_sum(void* h, int64_t* m);
+int b200mc_ising3dp_measure(void* h, int64_t* e, int64_t* m);
+int b200mc_ising3dp_get_spins(void* h, int32_t* out);      /* spins(1-nxy : nall+nxy), int32 0/1 */
+int b200mc_ising3dp_set_spins(void* h, const int32_t* in);
+int b200mc_ising3dp_get_ws(void* h, double out[14]);
+int64_t b200mc_ising3dp_nx(void* h);
+int64_t b200mc_ising3dp_ny(void* h);
+int64_t b200mc_ising3dp_nz(void* h);
+int64_t b200mc_ising3dp_nall(void* h);
+double b200mc_ising3dp_kbt(void* h);
+double b200mc_ising3dp_beta(void* h);
+int b200mc_ising3dp_sync(void* h);
+int b200mc_ising3dp_set_timing(void* h, int32_t on);       /* CUDA events around every colour-pass launch */
+int b200mc_ising3dp_get_timing(void* h, int64_t* launches, double* total_ms);
+int b200mc_ising2dp_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed);
+int b200mc_ising2dp_destroy(void* h);
+int b200mc_ising2dp_set_stream(void* h, void* cuda_stream);
+int b200mc_ising2dp_skip_curand(void* h, int64_t n_skip);
+int b200mc_ising2dp_set_allup_spin(void* h);
+int b200mc_ising2dp_set_random_spin(void* h);
+int b200mc_ising2dp_set_kbt(void* h, double kbt);
+int b200mc_ising2dp_set_beta(void* h, double beta);
+int b200mc_ising2dp_update(void* h);
+int b200mc_ising2dp_update_n(void* h, int32_t n_sweeps);
+int b200mc_ising2dp_calc_energy_sum(void* h, int64_t* e);
+int b200mc_ising2dp_calc_magne_sum(void* h, int64_t* m);
+int b200mc_ising2dp_measure(void* h, int64_t* e, int64_t* m);
+int b200mc_ising2dp_get_spins(void* h, int32_t* out);      /* spins(1-nx : nall+nx), int32 -1/+1 */
+int b200mc_ising2dp_set_spins(void* h, const int32_t* in);
+int64_t b200mc_ising2dp_nx(void* h);
+int64_t b200mc_ising2dp_ny(void* h);
+int64_t b200mc_ising2dp_nall(void* h);
+double b200mc_ising2dp_kbt(void* h);
+double b200mc_ising2dp_beta(void* h);
+int b200mc_ising2dp_sync(void* h);
+int b200mc_ising2dp_set_timing(void* h, int32_t on);
+int b200mc_ising2dp_get_timing(void* h, int64_t* launches, double* total_ms);
+
+/* ------------------------------------------------------------------------
  * Ising 2D -- type(ising2d_gpu), src/ising2d_gpu_m.f90:12-42
  * ------------------------------------------------------------------------ */
 /* init, :44-61.  nx odd, ny even REQUIRED. */

@@ -115,6 +115,7 @@ def _declare(L):
     d("orc_xy_uniforms", None, u32, u64, i64, i64, P, P)
     d("orc_xy_init_uniforms", None, u32, u64, i64, i64, P)
     d("orc_torus_uniforms", None, u32, u64, i32, i64, i64, i32, P)
+    d("orc_isingbits_uniforms", C.c_int, u32, u64, i64, C.c_int, P)
     d("orc_xyh_norishiro", None, i64, i64, P)
     d("orc_xyh_set_allup", None, i64, i64, P)
     d("orc_xyh_set_random", None, i64, i64, P, P)
@@ -200,6 +201,14 @@ def torus_uniforms(seed: int, draw: int, replica: int, nx: int, ny: int, q: int 
     """rnds(2, nx, ny) of update_metropolis (src/clock/clock_tableall_gpu_m.f90:95), flat"""
     out = np.empty(2 * nx * ny, dtype=np.float64)
     lib().orc_torus_uniforms(seed & 0xFFFFFFFF, draw, replica, nx, ny, q, _p(out))
+    return out
+
+
+def isingbits_uniforms(seed: int, draw: int, n_sites: int, init: bool = False) -> np.ndarray:
+    """accept uniforms (init: set_random_spin uniforms) of the bit-packed Ising handles, reference index order"""
+    out = np.empty(n_sites, dtype=np.float64)
+    if lib().orc_isingbits_uniforms(seed & 0xFFFFFFFF, draw, n_sites, 1 if init else 0, _p(out)):
+        raise ValueError("bit-packed Ising: n_sites / 2 must be a multiple of 128")
     return out
 
 

@@ -364,3 +364,43 @@ ORC_API void orc_xyh_init_uniforms(uint32_t seed, uint64_t draw, int64_t n_sites
         out[i] = ((double)r[k & 3] + 1.0) * 0x1p-32;
     }
 }
+
+/* --------------------------------------------------------------------------
+ * Bit-packed Ising 2D / 3D (cuda_fortran_mc_simulation_spin_b200/csrc/ising_bits.cu): each colour
+ * ring of Nc = N / 2 sites folded into 128 bit-lanes of L = Nc / 128 positions (128 | Nc): site
+ * k -> lane k / L, position p = k % L = bit (lane & 31) of word (lane >> 5) of vector p.
+ * Accept uniform, bit plane j of the 128 uniforms of a vector = one Philox block:
+ *   R_j = philox(ctr(p, draw, colour, sub = j), (seed, TAG_ISNB)), j = 0..31
+ *   U = sum_j ((R_j[lane >> 5] >> (lane & 31)) & 1) << (31 - j);   u = (U + 1) 2^-32
+ * (the GPU compares plane by plane with the threshold's bits and stops at the first plane where
+ * every site of the warp is decided; the value is the same).
+ * set_random_spin: R = philox(ctr(p, draw, colour, 0), (seed, TAG_INIB)),
+ *   U = ((R[lane >> 5] >> (lane & 31)) & 1) << 31   (the reference only tests u < 0.5,
+ *   src/ising3d_gpu_m.f90:99).
+ * out[i] = u(site i), i = 0..N-1.
+ * -------------------------------------------------------------------------- */
+#define TAG_ISNB 0x49534E42u
+#define TAG_INIB 0x494E4942u
+ORC_API int orc_isingbits_uniforms(uint32_t seed, uint64_t draw, int64_t n_sites, int init, double *out)
+{
+    const int64_t nc = n_sites / 2;
+    if (nc % 128) return 1;
+    const int64_t L = nc / 128;
+    const uint32_t key[2] = {seed, init ? TAG_INIB : TAG_ISNB};
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < L; ++p)
+        for (uint32_t colour = 0; colour < 2; ++colour) {
+            uint32_t U[128] = {0}, c[4], r[4];
+            const int planes = init ? 1 : 32;
+            for (int j = 0; j < planes; ++j) {
+                mk_ctr(c, (uint64_t)p, draw, colour, (uint32_t)j);
+                orc_philox4x32_10(c, key, r);
+                for (int lane = 0; lane < 128; ++lane) U[lane] |= ((r[lane >> 5] >> (lane & 31)) & 1u) << (31 - j);
+            }
+            for (int lane = 0; lane < 128; ++lane) {
+                const int64_t k = (int64_t)lane * L + p;
+                out[2 * k + colour] = ((double)U[lane] + 1.0) * 0x1p-32;
+            }
+        }
+    return 0;
+}

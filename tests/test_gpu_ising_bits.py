@@ -1,0 +1,125 @@
+"""GPU parity: the bit-packed (multi-spin coded, one bit per site) Ising 2D / 3D handles against the CPU oracle.
+
+Same bar as the int8 path: spins() (halo cells included) bit-exact after every sweep, int64 E and M exact -- the oracle
+runs the reference's update (src/ising3d_gpu_m.f90:174-206, src/ising2d_gpu_m.f90:138-162) on the uniform arrays of the
+bit-packed RNG contract (oracle/rng_contract.c, orc_isingbits_uniforms: bit plane j of a vector's 128 uniforms = one Philox
+block), so every threshold comparison is decided on the same 32-bit uniform the kernel compares bit-serially."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+KBT3, KBT2 = 4.51152, 2.26918531421
+
+
+def _mods():
+    from cuda_fortran_mc_simulation_spin_b200 import ising2d_gpu_m, ising3d_gpu_m
+    return ising2d_gpu_m, ising3d_gpu_m
+
+
+def _pair(oracle, dim, shape, kbt, seed):
+    i2, i3 = _mods()
+    g = (i3.ising3d_gpu() if dim == 3 else i2.ising2d_gpu()).init_packed(*shape, kbt, seed)
+    o = (oracle.ising3d_gpu() if dim == 3 else oracle.ising2d_gpu()).init(*shape, kbt, seed)
+    return g, o
+
+
+@pytest.mark.parametrize("dim,shape,kbt,start", [
+    (3, (15, 17, 256), KBT3, "allup"), (3, (31, 31, 256), KBT3, "random"), (3, (63, 65, 256), KBT3, "random"),
+    (3, (31, 31, 512), 2.0, "random"), (3, (15, 17, 256), 40.0, "random"),
+    (2, (33, 256), KBT2, "allup"), (2, (255, 256), KBT2, "random"), (2, (1001, 1024), KBT2, "random"), (2, (63, 512), 1.0, "random"),
+])
+def test_bits_trajectory_bit_exact(oracle, dim, shape, kbt, start):
+    g, o = _pair(oracle, dim, shape, kbt, 42)
+    n = g.nall()
+    draw = 0
+    assert np.array_equal(g.spins(), o.spins())                       # init: all up, halo cells included
+    e0 = -(3 if dim == 3 else 2) * n
+    assert g.measure() == (e0, n) == (o.calc_energy_sum(), o.calc_magne_sum())
+    if start == "random":
+        g.set_random_spin()
+        o.set_random_spin(oracle.isingbits_uniforms(42, draw, n, init=True))
+        draw += 1
+        assert np.array_equal(g.spins(), o.spins())
+        assert abs(g.calc_magne_sum()) < 6 * np.sqrt(n)
+    for sweep in range(5):
+        g.update()
+        o.update(randoms=oracle.isingbits_uniforms(42, draw, n))
+        draw += 1
+        assert np.array_equal(g.spins(), o.spins()), f"spins differ after sweep {sweep + 1}"
+        assert g.measure() == (o.calc_energy_sum(), o.calc_magne_sum())
+        assert (g.calc_energy_sum(), g.calc_magne_sum()) == g.measure()
+
+
+def test_bits_set_spins_update_n_and_skip(oracle):
+    g, o = _pair(oracle, 3, (31, 31, 256), KBT3, 7)
+    n = g.nall()
+    rng = np.random.default_rng(3)
+    o.set_random_spin(rng.random(n))
+    s = o.spins()
+    g.set_spins(s)
+    assert np.array_equal(g.spins(), s) and g.measure() == (o.calc_energy_sum(), o.calc_magne_sum())
+    g.skip_curand(3 * n - 5)                                          # ceil(n_skip / nall) = 3 draws
+    g.update_n(3)
+    for d in range(3):
+        o.update(randoms=oracle.isingbits_uniforms(7, 3 + d, n))
+    assert np.array_equal(g.spins(), o.spins())
+    bad = s.copy()
+    bad[n // 2] = 2
+    from cuda_fortran_mc_simulation_spin_b200 import B200MCError
+    with pytest.raises(B200MCError):
+        g.set_spins(bad)
+    # temperature change: the table and the thresholds follow
+    g.set_kbt(3.0); o.set_kbt(3.0)
+    assert np.array_equal(g.ws(), o.ws.reshape(2, 7))
+    g.update()
+    o.update(randoms=oracle.isingbits_uniforms(7, 6, n))
+    assert np.array_equal(g.spins(), o.spins())
+
+
+def test_bits_thresholds_at_the_edges(oracle):
+    """uniforms equal to a table entry / the exact-tie rule U == thr (not accepted) cannot be fed through the built-in
+    generator; the rule is checked through the extremes instead: beta = 0 (every class always accepts: all spins flip every
+    sweep) and beta -> infinity (only dE <= 0 moves: from all-up nothing moves)"""
+    i2, i3 = _mods()
+    g = i3.ising3d_gpu().init_packed(15, 17, 256, 1.0, 1)
+    g.set_beta(0.0)
+    n = g.nall()
+    g.update()
+    assert g.measure() == (-3 * n, -n)                                # every spin flipped
+    g.set_beta(50.0)
+    g.update_n(3)
+    assert g.measure() == (-3 * n, -n)                                # ground state: nothing moves (thr = 0 for dE > 0)
+    g.set_random_spin()
+    e0 = g.calc_energy_sum()
+    g.update_n(4)
+    assert g.calc_energy_sum() < e0                                   # quench: the energy only goes down
+
+
+def test_bits_unsupported_shapes():
+    from cuda_fortran_mc_simulation_spin_b200 import B200MCError
+    i2, i3 = _mods()
+    with pytest.raises(B200MCError, match="multiple of 128"):
+        i3.ising3d_gpu().init_packed(31, 31, 30, KBT3, 1)
+    with pytest.raises(B200MCError, match="odd"):
+        i3.ising3d_gpu().init_packed(32, 31, 256, KBT3, 1)
+    with pytest.raises(B200MCError, match="multiple of 128"):
+        i2.ising2d_gpu().init_packed(1001, 1000, KBT2, 1)
+
+
+def test_bits_full_size_properties():
+    """BASELINE config 2 (1023 x 1023 x 1024) on the bit-packed storage: size-independent properties"""
+    i2, i3 = _mods()
+    g = i3.ising3d_gpu().init_packed(1023, 1023, 1024, KBT3, 42)
+    n = g.nall()
+    assert g.measure() == (-3 * n, n)
+    g.update_n(3)
+    e, m = g.measure()
+    assert -3 * n < e < -2 * n and 0.5 * n < m < n and (e + 3 * n) % 4 == 0 and (m - n) % 2 == 0
+    # same seed, same trajectory; another seed, another one
+    g2 = i3.ising3d_gpu().init_packed(1023, 1023, 1024, KBT3, 42)
+    g2.update_n(3)
+    assert g2.measure() == (e, m)
+    del g2
+    g3 = i3.ising3d_gpu().init_packed(1023, 1023, 1024, KBT3, 43)
+    g3.update_n(3)
+    assert g3.measure() != (e, m)

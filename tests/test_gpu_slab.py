@@ -16,7 +16,7 @@ def test_slab_two_ranks_bit_exact(transport):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
-    n = 2 if n < 4 else 4
+    n = 8 if n >= 8 else (4 if n >= 4 else 2)
     r = subprocess.run(
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
          "--master-port", "29533", os.path.join(ROOT, "tests", "_slab_worker.py")],
