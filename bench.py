@@ -300,6 +300,40 @@ def bench_other_configs(T: Timer, K: int, peak: float, world: int, rank: int):
     if world > 1:
         return out
 
+    # ---- C2': the headline lattice on the bit-packed (multi-spin coded) storage, one bit per site (BASELINE.md C2') ----
+    from cuda_fortran_mc_simulation_spin_b200 import ising3d_gpu_m
+    BPF_BITS = 3.0 / 8.0
+    for key, mk, label, kern in (
+            ("C2p_ising3d_bitpacked_1023x1023x1024", lambda: ising3d_gpu_m.ising3d_gpu().init_packed(NX, NY, NZ, KBT, SEED),
+             f"Ising 3D Metropolis, ONE BIT per site (multi-spin coded), helical {NX}x{NY}x{NZ}, kbt={KBT}, all-up start", "bits_pass_kernel<6>"),
+            ("C5p_ising2d_bitpacked_65537x65536", lambda: ising2d_gpu_m.ising2d_gpu().init_packed(65537, 65536, KBT2, SEED),
+             f"Ising 2D Metropolis, ONE BIT per site, helical 65537x65536, kbt={KBT2}, all-up start", "bits_pass_kernel<4>")):
+        m = mk()
+        nall = m.nall()
+        kp = K if key.startswith("C2p") else max(2, K // 4)
+        m.update_n(3); m.sync()
+        m.set_timing(True)
+        blocks = T.run(lambda: m.update_n(kp))
+        n_pass, pass_ms = m.get_timing()
+        m.set_timing(False)
+        e = entry(label, nall, blocks, kp, BPF_BITS, "step, against the bit-packed layout's own 3/8 B per flip (the pass is ALU-bound: bit-serial accept test)",
+                  {"roofline_kernel": _kernel_roof(nall / 2, BPF_BITS, n_pass, pass_ms, peak, kern),
+                   "roofline_vs_int8_bytes": _roof(nall * kp / (statistics.median(blocks) * 1e6), BYTES_PER_FLIP, peak,
+                                                   "the same flips/ns expressed in the int8 layout's 3 B per flip (> 1 means faster than an int8 kernel at its HBM roofline could be)")})
+
+        def loopp():
+            s = 0
+            for _ in range(kp):
+                m.update()
+                s += m.calc_magne_sum() + m.calc_energy_sum()
+            return s
+        b2 = T.run(loopp)
+        e["e2e"] = {"value": nall * kp / (statistics.median(b2) * 1e6), "unit": UNIT, "ms_per_step": statistics.median(b2) / kp,
+                    "note": "update + calc_magne_sum + calc_energy_sum per MCS through the module API (separate measurement kernel)"}
+        out[key] = e
+        del m
+        _free()
+
     # ---- C1: Ising 2D at the reference driver's defaults (app/ising2d_gpu_relaxation.f90:6-12) ----
     m = ising2d_gpu_m.ising2d_gpu().init(1001, 1000, KBT2, SEED)
     k1 = max(K, 200)

@@ -15,13 +15,15 @@
 // Update.  Bit-sliced count of the aligned neighbours k' (two full adders + a 2-bit add: 10 LOP3 per 32 sites in 3D);
 // sites with k' <= nnb/2 flip (dE <= 0), the others -- classes k' = 4, 5, 6 (3D) / 3, 4 (2D) -- flip iff U < thr[k'],
 // thr = floor(w 2^32), exactly the reference's `randoms(idx) > ws(...)` test on u = (U + 1) 2^-32.  The comparison is
-// bit-serial: plane j of a vector's uniforms is one Philox block (4 words = bit j of the 128 uniforms), compared with
-// bit j of the site's threshold; a site is decided at the first plane where the two differ, and the loop ends when every
-// site of the warp is decided (about 13 planes near T_c).  Exact at the full 32 bits (U == thr: not accepted).
+// bit-serial on the 8 leading bits: plane j of a vector's uniforms is one Philox block (4 words = bit j of the 128
+// uniforms), compared with bit j of the site's threshold; a site is decided at the first plane where the two differ.  The
+// 2^-8 of the non-trivial sites that are still undecided after 8 planes take the remaining 24 bits of their uniform from a
+// per-site Philox word (a scalar tail, about 0.35 sites per vector near T_c; with planes alone a warp needed about 13 of
+// them before its 4096 sites were all decided).  Exact at the full 32 bits (U == thr: not accepted).
 //
 // RNG contract (CPU restatement: oracle/rng_contract.c, orc_isingbits_uniforms): vector p, colour c, sweep `draw`:
-//   R_j = philox(ctr(p, draw, c, sub = j), (seed, TAG_ISNB)), j = 0..31
-//   site (word w, bit b):  U = sum_j ((R_j[w] >> b) & 1) << (31 - j)
+//   R_j = philox(ctr(p, draw, c, sub = j), (seed, TAG_ISNB)), j = 0..7;  S = philox(ctr(p, draw, c, sub = 32 + (lane >> 2)), same key)
+//   site lane = 32 w + b:  U = sum_j ((R_j[w] >> b) & 1) << (31 - j)  |  S[lane & 3] & 0xFFFFFF
 // set_random_spin: R = philox(ctr(p, draw, c, 0), (seed, TAG_INIB)), U = ((R[w] >> b) & 1) << 31 (the reference only tests
 // u < 0.5: spin = 1 - bit).
 #include <math.h>
@@ -35,6 +37,8 @@
 namespace {
 
 #define TAG_ISNB 0x49534E42u /* "ISNB": accept uniforms of the bit-packed Ising models */
+#define BITS_PLANES 8                                   /* leading bits of a uniform that come from bit planes */
+#define BITS_LOW_MASK ((1u << (32 - BITS_PLANES)) - 1u)
 #define TAG_INIB 0x494E4942u /* "INIB": their set_random_spin */
 
 struct BitsPassArgs {
@@ -75,8 +79,8 @@ __device__ __forceinline__ void bits_count(uint32_t s, const uint32_t (&n)[6], u
     }
 }
 
-template <int NNB>
-__global__ void __launch_bounds__(256)
+template <int NNB, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 bits_pass_kernel(const __grid_constant__ BitsPassArgs a)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -103,9 +107,9 @@ bits_pass_kernel(const __grid_constant__ BitsPassArgs a)
             und[w] = nt & ~A;
             lt[w] = ~und[w];      // trivial classes (dE <= 0) and always-accept classes flip
         }
-        // bit-serial U < thr, most significant plane first
+        // bit-serial U < thr on the BITS_PLANES leading planes, most significant first
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < BITS_PLANES; ++j) {
             if (j >= 3 && !(und[0] | und[1] | und[2] | und[3])) break;
             const uint4 R = philox_rk<TAG_ISNB>(mk_ctr((uint64_t)p, a.draw, a.colour, (uint32_t)j), a.rk0);
             const uint32_t r[4] = {R.x, R.y, R.z, R.w};
@@ -118,6 +122,27 @@ bits_pass_kernel(const __grid_constant__ BitsPassArgs a)
                 lt[w] |= und[w] & ~r[w] & T;       // uniform bit 0, threshold bit 1: U < thr
                 und[w] &= ~(r[w] ^ T);             // still equal: undecided
             }
+        }
+        // the sites whose leading planes equal their threshold's (2^-BITS_PLANES of the non-trivial ones): the low
+        // 32 - BITS_PLANES bits of the uniform come from a per-site Philox word
+        // (ONE loop over the four words: a warp runs max-over-lanes iterations, about 2 near T_c; a loop per word ran about
+        // one iteration for each of the four words on top of every plane it replaced)
+        while (und[0] | und[1] | und[2] | und[3]) {
+            const int w = und[0] ? 0 : und[1] ? 1 : und[2] ? 2 : 3;
+            const uint32_t m = w == 0 ? und[0] : w == 1 ? und[1] : w == 2 ? und[2] : und[3];
+            const uint32_t s0 = w == 0 ? sel0[0] : w == 1 ? sel0[1] : w == 2 ? sel0[2] : sel0[3];
+            const uint32_t s1 = w == 0 ? sel1[0] : w == 1 ? sel1[1] : w == 2 ? sel1[2] : sel1[3];
+            const int b = __ffs(m) - 1;
+            const uint32_t bit = 1u << b;
+            const int lane = 32 * w + b;
+            const uint4 R = philox_rk<TAG_ISNB>(mk_ctr((uint64_t)p, a.draw, a.colour, (uint32_t)(32 + (lane >> 2))), a.rk0);
+            const uint32_t S = ((lane & 3) == 0 ? R.x : (lane & 3) == 1 ? R.y : (lane & 3) == 2 ? R.z : R.w) & BITS_LOW_MASK;
+            const uint32_t cls = NNB == 6 ? ((s1 & bit) ? 2u : ((s0 & bit) ? 1u : 0u)) : ((s0 & bit) ? 1u : 0u);
+            const uint32_t t = (cls == 0 ? a.thr[0] : cls == 1 ? a.thr[1] : a.thr[2]) & BITS_LOW_MASK;
+            const uint32_t acc = S < t ? bit : 0u;
+#pragma unroll
+            for (int ww = 0; ww < 4; ++ww)
+                if (ww == w) { und[ww] &= ~bit; lt[ww] |= acc; }
         }
         a.own[p] = make_uint4(s[0] ^ lt[0], s[1] ^ lt[1], s[2] ^ lt[2], s[3] ^ lt[3]);
     }
@@ -204,7 +229,7 @@ bits_export_kernel(const uint4* c0, const uint4* c1, int64_t N, int64_t L, int64
 }
 // inverse: one thread builds one 32-bit word (32 sites, L apart in k)
 __global__ void __launch_bounds__(256)
-bits_import_kernel(uint4* c0, uint4* c1, int64_t L, int64_t P, int pm1, const int32_t* in, int* bad)
+bits_import_kernel(uint4* c0, uint4* c1, int64_t L, int64_t P, int pm1, const int32_t* in)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 8 * L) return;
@@ -216,7 +241,6 @@ bits_import_kernel(uint4* c0, uint4* c1, int64_t L, int64_t P, int pm1, const in
         const int64_t k = (int64_t)(32 * w + b) * L + pos;
         const int32_t v = in[2 * k + colour + P];
         const int32_t bit = pm1 ? (v + 1) >> 1 : v;
-        if ((pm1 && v != 1 && v != -1) || (!pm1 && v != 0 && v != 1)) *bad = 1;
         word |= (uint32_t)(bit & 1) << b;
     }
     reinterpret_cast<uint32_t*>((colour ? c1 : c0) + pos)[w] = word;
@@ -228,7 +252,6 @@ struct Bits {
     int64_t off[2][6];
     uint4* vec[2];       // [colour]: L + 2H vectors, position p at index p + H
     int32_t* stage;
-    int* d_bad;
     unsigned long long* d_acc;
     cudaStream_t stream;
     double beta;
@@ -236,7 +259,7 @@ struct Bits {
     uint64_t thr[8];     // floor(w 2^32) per k'
     uint32_t seed;
     uint64_t draw;
-    int grid;
+    int grid, minb;      // minb: resident blocks per SM the 3D pass is compiled for (3: 85 registers, 4: 64 with a few spills)
     bool obs_valid;
     int64_t obs_e, obs_m;
     bool timing;
@@ -323,8 +346,9 @@ int sweep(Bits* m)
             CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
         }
         COUNT_LAUNCH();
-        if (m->nnb == 6) bits_pass_kernel<6><<<m->grid, 256, 0, m->stream>>>(a);
-        else bits_pass_kernel<4><<<m->grid, 256, 0, m->stream>>>(a);
+        if (m->nnb == 6 && m->minb == 4) bits_pass_kernel<6, 4><<<m->grid, 256, 0, m->stream>>>(a);
+        else if (m->nnb == 6) bits_pass_kernel<6, 3><<<m->grid, 256, 0, m->stream>>>(a);
+        else bits_pass_kernel<4, 4><<<m->grid, 256, 0, m->stream>>>(a);
         CK(cudaGetLastError());
         if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
         int rc = halo(m, colour);
@@ -357,7 +381,7 @@ int measure(Bits* m)
 void destroy(Bits* m)
 {
     cudaStreamSynchronize(m->stream);
-    cudaFree(m->vec[0]); cudaFree(m->vec[1]); cudaFree(m->stage); cudaFree(m->d_bad); cudaFree(m->d_acc);
+    cudaFree(m->vec[0]); cudaFree(m->vec[1]); cudaFree(m->stage); cudaFree(m->d_acc);
     for (cudaEvent_t e : m->evs) cudaEventDestroy(e);
     delete m;
 }
@@ -408,11 +432,11 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
         const int64_t o[6] = {-1 + c, c, h + c, -h - 1 + c, g + c, -g - 1 + c};
         for (int t = 0; t < 6; ++t) m->off[c][t] = o[t];
     }
-    m->vec[0] = m->vec[1] = nullptr; m->stage = nullptr; m->d_bad = nullptr; m->d_acc = nullptr;
+    m->vec[0] = m->vec[1] = nullptr; m->stage = nullptr; m->d_acc = nullptr;
     m->stream = 0; m->beta = 1 / kbt; m->seed = (uint32_t)iseed; m->draw = 0; m->obs_valid = false; m->timing = false; m->ev_used = 0;
     const size_t bytes = (size_t)(L + 2 * H) * sizeof(uint4);
     if (cudaMalloc(&m->vec[0], bytes) != cudaSuccess || cudaMalloc(&m->vec[1], bytes) != cudaSuccess ||
-        cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&m->d_bad, sizeof(int)) != cudaSuccess) {
+        cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long)) != cudaSuccess) {
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed (%zu bytes per colour)", bytes);
         cudaGetLastError();
         destroy(m); return B200MC_ERR_CUDA;
@@ -420,8 +444,10 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    { const char* t = getenv("B200MC_BITS_MINB"); m->minb = (t && atoi(t) == 4) ? 4 : 3; }
     const int64_t need = (L + 255) / 256;
-    m->grid = (int)(need < (int64_t)sms * 8 ? need : (int64_t)sms * 8);
+    const int per_sm = ndim == 3 ? m->minb : 4;
+    m->grid = (int)(need < (int64_t)sms * per_sm ? need : (int64_t)sms * per_sm);
     int rc = build_tables(m);
     if (!rc) rc = fill(m, 1);      // like the reference's init: all up
     if (rc) { destroy(m); return rc; }
@@ -460,21 +486,22 @@ int set_spins(Bits* m, const int32_t* in)
 {
     if (!in) ARG_FAIL("null input");
     const int64_t n = m->N + 2 * m->P;
+    // validate before touching the lattice (the halo cells of `in` are ignored, like the int8 handles)
+    const int32_t lo = m->ndim == 2 ? -1 : 0;
+    for (int64_t i = 0; i < m->N; ++i) {
+        const int32_t v = in[i + m->P];
+        if (v != 1 && v != lo) ARG_FAIL("set_spins: value %d at site %lld (must be %s)", v, (long long)(i + 1), m->ndim == 2 ? "-1 / +1" : "0 / 1");
+    }
     if (!m->stage) CK(cudaMalloc(&m->stage, (size_t)n * sizeof(int32_t)));
     m->obs_valid = false;
     CK(cudaMemcpyAsync(m->stage, in, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
-    CK(cudaMemsetAsync(m->d_bad, 0, sizeof(int), m->stream));
     COUNT_LAUNCH();
-    bits_import_kernel<<<(unsigned)((8 * m->L + 255) / 256), 256, 0, m->stream>>>(m->vec[0] + m->H, m->vec[1] + m->H, m->L, m->P, m->ndim == 2, m->stage, m->d_bad);
+    bits_import_kernel<<<(unsigned)((8 * m->L + 255) / 256), 256, 0, m->stream>>>(m->vec[0] + m->H, m->vec[1] + m->H, m->L, m->P, m->ndim == 2, m->stage);
     CK(cudaGetLastError());
-    int bad = 0;
-    CK(cudaMemcpyAsync(&bad, m->d_bad, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
     int rc = halo(m, 0);
     if (!rc) rc = halo(m, 1);
-    if (rc) return rc;
-    if (bad) ARG_FAIL("set_spins: values must be %s", m->ndim == 2 ? "-1 / +1" : "0 / 1");
-    return B200MC_OK;
+    return rc;
 }
 
 }  // namespace

@@ -369,11 +369,13 @@ ORC_API void orc_xyh_init_uniforms(uint32_t seed, uint64_t draw, int64_t n_sites
  * Bit-packed Ising 2D / 3D (cuda_fortran_mc_simulation_spin_b200/csrc/ising_bits.cu): each colour
  * ring of Nc = N / 2 sites folded into 128 bit-lanes of L = Nc / 128 positions (128 | Nc): site
  * k -> lane k / L, position p = k % L = bit (lane & 31) of word (lane >> 5) of vector p.
- * Accept uniform, bit plane j of the 128 uniforms of a vector = one Philox block:
- *   R_j = philox(ctr(p, draw, colour, sub = j), (seed, TAG_ISNB)), j = 0..31
- *   U = sum_j ((R_j[lane >> 5] >> (lane & 31)) & 1) << (31 - j);   u = (U + 1) 2^-32
- * (the GPU compares plane by plane with the threshold's bits and stops at the first plane where
- * every site of the warp is decided; the value is the same).
+ * Accept uniform: the 8 leading bits from bit planes (plane j of the 128 uniforms of a vector = one
+ * Philox block), the low 24 bits from a per-site Philox word:
+ *   R_j = philox(ctr(p, draw, colour, sub = j), (seed, TAG_ISNB)), j = 0..7
+ *   S   = philox(ctr(p, draw, colour, sub = 32 + (lane >> 2)), same key)
+ *   U = sum_j ((R_j[lane >> 5] >> (lane & 31)) & 1) << (31 - j)  |  S[lane & 3] & 0xFFFFFF;   u = (U + 1) 2^-32
+ * (the GPU compares plane by plane with the threshold's bits and evaluates S only for a site whose 8
+ * leading bits equal its threshold's; the value is the same).
  * set_random_spin: R = philox(ctr(p, draw, colour, 0), (seed, TAG_INIB)),
  *   U = ((R[lane >> 5] >> (lane & 31)) & 1) << 31   (the reference only tests u < 0.5,
  *   src/ising3d_gpu_m.f90:99).
@@ -391,12 +393,18 @@ ORC_API int orc_isingbits_uniforms(uint32_t seed, uint64_t draw, int64_t n_sites
     for (int64_t p = 0; p < L; ++p)
         for (uint32_t colour = 0; colour < 2; ++colour) {
             uint32_t U[128] = {0}, c[4], r[4];
-            const int planes = init ? 1 : 32;
+            const int planes = init ? 1 : 8;
             for (int j = 0; j < planes; ++j) {
                 mk_ctr(c, (uint64_t)p, draw, colour, (uint32_t)j);
                 orc_philox4x32_10(c, key, r);
                 for (int lane = 0; lane < 128; ++lane) U[lane] |= ((r[lane >> 5] >> (lane & 31)) & 1u) << (31 - j);
             }
+            if (!init)
+                for (int q4 = 0; q4 < 32; ++q4) {
+                    mk_ctr(c, (uint64_t)p, draw, colour, 32u + (uint32_t)q4);
+                    orc_philox4x32_10(c, key, r);
+                    for (int t = 0; t < 4; ++t) U[4 * q4 + t] |= r[t] & 0xFFFFFFu;
+                }
             for (int lane = 0; lane < 128; ++lane) {
                 const int64_t k = (int64_t)lane * L + p;
                 out[2 * k + colour] = ((double)U[lane] + 1.0) * 0x1p-32;
