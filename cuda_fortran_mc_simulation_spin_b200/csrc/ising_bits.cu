@@ -79,10 +79,14 @@ __device__ __forceinline__ void bits_count(uint32_t s, const uint32_t (&n)[6], u
     }
 }
 
-template <int NNB, int MINB>
+// MEASURE (second colour pass of a sweep when the caller measures every MCS): the pass also accumulates acc[0] += sum of the
+// aligned-neighbour counts of the NEW colour-1 spins (k' of a flipped site becomes nnb - k') and acc[1] += sum s over both
+// colours (the colour-0 vector at the same position is the x- neighbour vector), like bits_measure_kernel.
+template <int NNB, int MINB, bool MEASURE>
 __global__ void __launch_bounds__(256, MINB)
 bits_pass_kernel(const __grid_constant__ BitsPassArgs a)
 {
+    long long part[2] = {0, 0};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.L; p += stride) {
         const uint4 o = a.own[p];
@@ -90,7 +94,7 @@ bits_pass_kernel(const __grid_constant__ BitsPassArgs a)
 #pragma unroll
         for (int j = 0; j < NNB; ++j) nb[j] = ld_other(a.oth + p + a.off[j]);
         const uint32_t s[4] = {o.x, o.y, o.z, o.w};
-        uint32_t sel0[4], sel1[4], und[4], lt[4];
+        uint32_t sel0[4], sel1[4], und[4], lt[4], cc2[4];
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             uint32_t n[6] = {0u, 0u, 0u, 0u, 0u, 0u};
@@ -100,8 +104,8 @@ bits_pass_kernel(const __grid_constant__ BitsPassArgs a)
             bits_count<NNB>(s[w], n, c0, c1, c2);
             // class selectors: threshold = sel1 ? thr[2] : (sel0 ? thr[1] : thr[0]) and the non-trivial sites
             uint32_t nt;
-            if (NNB == 6) { nt = c2; sel0[w] = c0; sel1[w] = c1; }              // k' = 4: (c1, c0) = (0, 0); 5: (0, 1); 6: (1, 0)
-            else { nt = c2 | (c1 & c0); sel0[w] = c2; sel1[w] = 0u; }            // k' = 3: thr[0]; 4: thr[1]
+            if (NNB == 6) { nt = c2; sel0[w] = c0; sel1[w] = c1; cc2[w] = c2; }  // k' = 4: (c1, c0) = (0, 0); 5: (0, 1); 6: (1, 0)
+            else { nt = c2 | (c1 & c0); sel0[w] = c2; sel1[w] = c1; cc2[w] = c0; }   // k' = 3: thr[0]; 4: thr[1]  (sel1 / cc2 only carry c1 / c0 for MEASURE)
             const uint32_t f = (sel0[w] & a.always[1]) | (~sel0[w] & a.always[0]);
             const uint32_t A = NNB == 6 ? ((sel1[w] & a.always[2]) | (~sel1[w] & f)) : f;
             und[w] = nt & ~A;
@@ -145,7 +149,20 @@ bits_pass_kernel(const __grid_constant__ BitsPassArgs a)
                 if (ww == w) { und[ww] &= ~bit; lt[ww] |= acc; }
         }
         a.own[p] = make_uint4(s[0] ^ lt[0], s[1] ^ lt[1], s[2] ^ lt[2], s[3] ^ lt[3]);
+        if (MEASURE) {
+            const uint32_t z[4] = {nb[0].x, nb[0].y, nb[0].z, nb[0].w};   // colour 0 at the same position (offset 0 for colour 1)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                // count bits (b0, b1, b2) of k': 3D (sel0, sel1, cc2); 2D (cc2, sel1, sel0)
+                const uint32_t b0 = NNB == 6 ? sel0[w] : cc2[w], b1 = sel1[w], b2 = NNB == 6 ? cc2[w] : sel0[w], f = lt[w];
+                const int keep = __popc(b0 & ~f) + 2 * __popc(b1 & ~f) + 4 * __popc(b2 & ~f);
+                const int flip = __popc(b0 & f) + 2 * __popc(b1 & f) + 4 * __popc(b2 & f);
+                part[0] += keep + NNB * __popc(f) - flip;
+                part[1] += __popc(s[w] ^ f) + __popc(z[w]);
+            }
+        }
     }
+    if (MEASURE) block_atomic_add<2>(a.acc, part);
 }
 
 // halo refresh of one colour array (index 0 = position -H): position -H + v <- position L - H + v rotated up by one lane,
@@ -261,6 +278,7 @@ struct Bits {
     uint64_t draw;
     int grid, minb;      // minb: resident blocks per SM the 3D pass is compiled for (3: 85 registers, 4: 64 with a few spills)
     bool obs_valid;
+    bool want_fused, fused_pending, swept_since_measure;   // fused measurement, as for the int8 handles (ising.cu)
     int64_t obs_e, obs_m;
     bool timing;
     std::vector<cudaEvent_t> evs;
@@ -337,7 +355,8 @@ int halo(Bits* m, int colour)
 
 int sweep(Bits* m)
 {
-    m->obs_valid = false;
+    if (m->fused_pending) m->want_fused = false;   // the sums of the previous sweep were never asked for
+    m->obs_valid = false; m->fused_pending = false;
     for (int colour = 0; colour < 2; ++colour) {
         BitsPassArgs a;
         fill_args(m, colour, &a);
@@ -346,28 +365,40 @@ int sweep(Bits* m)
             CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
         }
         COUNT_LAUNCH();
-        if (m->nnb == 6 && m->minb == 4) bits_pass_kernel<6, 4><<<m->grid, 256, 0, m->stream>>>(a);
-        else if (m->nnb == 6) bits_pass_kernel<6, 3><<<m->grid, 256, 0, m->stream>>>(a);
-        else bits_pass_kernel<4, 4><<<m->grid, 256, 0, m->stream>>>(a);
+        const bool fuse = colour == 1 && m->want_fused;
+        if (fuse) CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
+        if (fuse) {
+            if (m->nnb == 6) bits_pass_kernel<6, 3, true><<<m->grid, 256, 0, m->stream>>>(a);
+            else bits_pass_kernel<4, 3, true><<<m->grid, 256, 0, m->stream>>>(a);
+        } else if (m->nnb == 6 && m->minb == 4) bits_pass_kernel<6, 4, false><<<m->grid, 256, 0, m->stream>>>(a);
+        else if (m->nnb == 6) bits_pass_kernel<6, 3, false><<<m->grid, 256, 0, m->stream>>>(a);
+        else bits_pass_kernel<4, 4, false><<<m->grid, 256, 0, m->stream>>>(a);
+        if (fuse) m->fused_pending = true;
         CK(cudaGetLastError());
         if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
         int rc = halo(m, colour);
         if (rc) return rc;
     }
     m->draw += 1;
+    m->swept_since_measure = true;
     return B200MC_OK;
 }
 
 int measure(Bits* m)
 {
     if (m->obs_valid) return B200MC_OK;
-    CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
-    BitsPassArgs a;
-    fill_args(m, 1, &a);
-    COUNT_LAUNCH();
-    if (m->nnb == 6) bits_measure_kernel<6><<<m->grid, 256, 0, m->stream>>>(a, m->vec[0] + m->H);
-    else bits_measure_kernel<4><<<m->grid, 256, 0, m->stream>>>(a, m->vec[0] + m->H);
-    CK(cudaGetLastError());
+    if (!m->fused_pending) {
+        CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
+        BitsPassArgs a;
+        fill_args(m, 1, &a);
+        COUNT_LAUNCH();
+        if (m->nnb == 6) bits_measure_kernel<6><<<m->grid, 256, 0, m->stream>>>(a, m->vec[0] + m->H);
+        else bits_measure_kernel<4><<<m->grid, 256, 0, m->stream>>>(a, m->vec[0] + m->H);
+        CK(cudaGetLastError());
+    }
+    m->want_fused = m->swept_since_measure;   // measured after an update: the next sweeps accumulate the sums themselves
+    m->swept_since_measure = false;
+    m->fused_pending = false;
     unsigned long long host[2];
     CK(cudaMemcpyAsync(host, m->d_acc, sizeof(host), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
@@ -388,7 +419,7 @@ void destroy(Bits* m)
 
 int fill(Bits* m, int value)
 {
-    m->obs_valid = false;
+    m->obs_valid = false; m->fused_pending = false;
     const size_t bytes = (size_t)(m->L + 2 * m->H) * sizeof(uint4);
     CK(cudaMemsetAsync(m->vec[0], value ? 0xFF : 0x00, bytes, m->stream));
     CK(cudaMemsetAsync(m->vec[1], value ? 0xFF : 0x00, bytes, m->stream));
@@ -434,6 +465,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     }
     m->vec[0] = m->vec[1] = nullptr; m->stage = nullptr; m->d_acc = nullptr;
     m->stream = 0; m->beta = 1 / kbt; m->seed = (uint32_t)iseed; m->draw = 0; m->obs_valid = false; m->timing = false; m->ev_used = 0;
+    m->want_fused = false; m->fused_pending = false; m->swept_since_measure = false;
     const size_t bytes = (size_t)(L + 2 * H) * sizeof(uint4);
     if (cudaMalloc(&m->vec[0], bytes) != cudaSuccess || cudaMalloc(&m->vec[1], bytes) != cudaSuccess ||
         cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long)) != cudaSuccess) {
@@ -457,7 +489,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
 
 int set_random(Bits* m)
 {
-    m->obs_valid = false;
+    m->obs_valid = false; m->fused_pending = false;
     for (int c = 0; c < 2; ++c) {
         COUNT_LAUNCH();
         bits_random_kernel<<<(unsigned)((m->L + 255) / 256), 256, 0, m->stream>>>(m->vec[c] + m->H, m->L, m->seed, m->draw, (uint32_t)c);
@@ -493,7 +525,7 @@ int set_spins(Bits* m, const int32_t* in)
         if (v != 1 && v != lo) ARG_FAIL("set_spins: value %d at site %lld (must be %s)", v, (long long)(i + 1), m->ndim == 2 ? "-1 / +1" : "0 / 1");
     }
     if (!m->stage) CK(cudaMalloc(&m->stage, (size_t)n * sizeof(int32_t)));
-    m->obs_valid = false;
+    m->obs_valid = false; m->fused_pending = false;
     CK(cudaMemcpyAsync(m->stage, in, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
     COUNT_LAUNCH();
     bits_import_kernel<<<(unsigned)((8 * m->L + 255) / 256), 256, 0, m->stream>>>(m->vec[0] + m->H, m->vec[1] + m->H, m->L, m->P, m->ndim == 2, m->stage);

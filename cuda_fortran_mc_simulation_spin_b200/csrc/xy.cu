@@ -125,10 +125,33 @@ static_assert(XY_ROWS % 2 == 0, "the strip loop is unrolled by two rows (the nei
 
 // One row of a strip.  P = (y + colour) & 1 at compile time: the x position of colour-compact site xi is 2 xi + P, its
 // same-row neighbours are the other colour's xi - 1 + P and xi + P.
+// RNG contract (v2; CPU restatement: oracle/rng_contract.c, orc_xy_uniforms).  A group = 4 colour-compact sites of one row,
+// blk = y gpr + g.  Per site 24 + 24 bits (both uniforms are used in fp32, which holds 24):
+//   R = philox(ctr(blk, draw, colour, 0), (seed, TAG_XY))               one block per group and row
+//   C = philox(ctr(blk of the EVEN row of the pair (y & ~1), draw, colour, 1), same key)    one block per group and row PAIR
+//   candidate U_c = R[j] >> 8;   accept U_r = (R[j] & 0xFF) << 16 | half(C[j], y & 1);   u = (U + 1) 2^-24 in (0, 1], exact in fp32
+// Three Philox blocks per 8 sites instead of four (round 1: two full 32-bit words per site, rounded to fp32).
+__device__ __forceinline__ uint4 xy_pair_block(const XYArgs& a, uint64_t blk_even)
+{
+    return philox_tag<TAG_XY>(mk_ctr(blk_even, a.draw, (uint32_t)a.colour, 1u), a.rk0);
+}
+__device__ __forceinline__ void xy_group_uniforms(const XYArgs& a, uint64_t blk, const uint4& C, int odd, float (&r)[4], float (&ct)[4])
+{
+    const uint4 R = philox_tag<TAG_XY>(mk_ctr(blk, a.draw, (uint32_t)a.colour, 0u), a.rk0);
+    const uint32_t W[4] = {R.x, R.y, R.z, R.w}, cw[4] = {C.x, C.y, C.z, C.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t Uc = W[j] >> 8;
+        const uint32_t Ur = ((W[j] & 0xFFu) << 16) | (odd ? cw[j] >> 16 : cw[j] & 0xFFFFu);
+        ct[j] = ((float)Uc + 1.0f) * 0x1p-24f;      // candidate angle in turns, (0, 1]
+        r[j] = ((float)Ur + 1.0f) * 0x1p-24f;       // accept uniform, (0, 1]
+    }
+}
+
 // RAGGED = false (nx/2 a multiple of 4, e.g. every benchmark shape): no partial group, no mirror padding -- the strip code
 // of round 1, 64 registers without spills; RAGGED = true adds the per-lane validity tests and the mirror stores.
-template <bool OVERRELAX, bool MEASURE, int P, bool RAGGED>
-__device__ __forceinline__ void xy_strip_row(const XYArgs& a, int y, int idx, float nbl2e, const float4 r_up, const float r_edge, const float4 o,
+template <bool OVERRELAX, bool MEASURE, int P, bool RAGGED, int ODD>
+__device__ __forceinline__ void xy_strip_row(const XYArgs& a, int y, int idx, const uint4& C, float nbl2e, const float4 r_up, const float r_edge, const float4 o,
                                              const XYRow& dn, const XYRow& mid, XYRow& up, float* prow, int xi0, float& es, float& mx, float& my)
 {
     const int nvalid = RAGGED ? a.nxh - xi0 : 4;   // >= 4 except in the last group of a row whose nx/2 is not a multiple of 4
@@ -162,29 +185,23 @@ __device__ __forceinline__ void xy_strip_row(const XYArgs& a, int y, int idx, fl
             }
         }
     } else {
+        float rr[4], cand[4];
+        xy_group_uniforms(a, (uint64_t)idx, C, ODD, rr, cand);
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-            // the RNG block of this group (contract: oracle/rng_contract.c)
-            const uint4 R = philox_tag<TAG_XY>(mk_ctr((uint64_t)idx, a.draw, (uint32_t)a.colour, (uint32_t)sub), a.rk0);
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int j = 2 * sub + e;
-                const uint32_t Ur = e ? R.z : R.x, Uc = e ? R.w : R.y;
-                const float r = ((float)Ur + 1.0f) * 0x1p-32f;       // (0, 1]
-                const float ct = ((float)Uc + 1.0f) * 0x1p-32f;      // candidate angle in turns
-                float cs, cc, ss, sc;
-                sincos_unit(ct, cs, cc);
-                sincos_unit(ov[j], ss, sc);
-                const float de = (cc - sc) * hx[j] + (cs - ss) * hy[j];   // -dE
-                float w;                                                   // exp(-beta dE) = 2^(beta log2(e) (-dE))
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(de * nbl2e));
-                const bool acc = !(r > w);                                 // accept iff r <= exp(-beta dE), :384
-                if (acc) ov[j] = ct;
-                if (MEASURE && j < nvalid) {
-                    const float cn = acc ? cc : sc, sn = acc ? cs : ss;
-                    es -= cn * hx[j] + sn * hy[j];
-                    mx += cn; my += sn;
-                }
+        for (int j = 0; j < 4; ++j) {
+            const float r = rr[j], ct = cand[j];
+            float cs, cc, ss, sc;
+            sincos_unit(ct, cs, cc);
+            sincos_unit(ov[j], ss, sc);
+            const float de = (cc - sc) * hx[j] + (cs - ss) * hy[j];   // -dE
+            float w;                                                   // exp(-beta dE) = 2^(beta log2(e) (-dE))
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(de * nbl2e));
+            const bool acc = !(r > w);                                 // accept iff r <= exp(-beta dE), :384
+            if (acc) ov[j] = ct;
+            if (MEASURE && j < nvalid) {
+                const float cn = acc ? cc : sc, sn = acc ? cs : ss;
+                es -= cn * hx[j] + sn * hy[j];
+                mx += cn; my += sn;
             }
         }
     }
@@ -233,9 +250,10 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
                 const float4 nu0 = ld_up(yn), no0 = ld_own(yn), nu1 = ld_up(yn + 1), no1 = ld_own(yn + 1);
                 const float ne0 = __ldg(a.oth + (size_t)yn * pitch + (COLOUR ? xe1 : xe0));
                 const float ne1 = __ldg(a.oth + (size_t)(yn + 1) * pitch + (COLOUR ? xe0 : xe1));
-                xy_strip_row<OVERRELAX, MEASURE, COLOUR, RAGGED>(a, y, (y + a.yoff) * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
+                const uint4 C = make_uint4(0u, 0u, 0u, 0u);   // (over-relaxation draws no random numbers)
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR, RAGGED, 0>(a, y, (y + a.yoff) * a.gpr + g, C, nbl2e, u0, e0, o0, dn, mid, up,
                                                          a.own + (size_t)y * pitch, xi0, es, mx, my);
-                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1, RAGGED>(a, y + 1, (y + 1 + a.yoff) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1, RAGGED, 1>(a, y + 1, (y + 1 + a.yoff) * a.gpr + g, C, nbl2e, u1, e1, o1, mid, up, dn,
                                                              a.own + (size_t)(y + 1) * pitch, xi0, es, mx, my);
                 u0 = nu0; o0 = no0; e0 = ne0; u1 = nu1; o1 = no1; e1 = ne1;
                 // rows rotate by two: (dn, mid, up) <- (up of the first row = mid of the second, up of the second)
@@ -243,14 +261,15 @@ xy_strip_kernel(const __grid_constant__ XYArgs a)
             }
         } else {
             for (int y = y0; y < y1; y += 2) {
+                const uint4 C = xy_pair_block(a, (uint64_t)((y + a.yoff) * a.gpr + g));   // the accept uniforms' low halves of rows y, y + 1
                 const float4 u1 = ld_up(y + 1), o1 = ld_own(y + 1);
                 const float e1 = __ldg(a.oth + (size_t)(y + 1) * pitch + (COLOUR ? xe0 : xe1));
-                xy_strip_row<OVERRELAX, MEASURE, COLOUR, RAGGED>(a, y, (y + a.yoff) * a.gpr + g, nbl2e, u0, e0, o0, dn, mid, up,
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR, RAGGED, 0>(a, y, (y + a.yoff) * a.gpr + g, C, nbl2e, u0, e0, o0, dn, mid, up,
                                                          a.own + (size_t)y * pitch, xi0, es, mx, my);
                 const int yn = min(y + 2, y1 - 2);
                 u0 = ld_up(yn); o0 = ld_own(yn);
                 e0 = __ldg(a.oth + (size_t)yn * pitch + (COLOUR ? xe1 : xe0));
-                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1, RAGGED>(a, y + 1, (y + 1 + a.yoff) * a.gpr + g, nbl2e, u1, e1, o1, mid, up, dn,
+                xy_strip_row<OVERRELAX, MEASURE, COLOUR ^ 1, RAGGED, 1>(a, y + 1, (y + 1 + a.yoff) * a.gpr + g, C, nbl2e, u1, e1, o1, mid, up, dn,
                                                              a.own + (size_t)(y + 1) * pitch, xi0, es, mx, my);
                 const XYRow t = mid; mid = dn; dn = up; (void)t;
             }
@@ -310,20 +329,18 @@ xy_field_kernel(const __grid_constant__ XYArgs a, float hx, float hy)
     float* prow = a.own + (size_t)y * a.pitch;
     const float4 o = *reinterpret_cast<const float4*>(prow + 4 * g);
     float ov[4] = {o.x, o.y, o.z, o.w};
+    {
+        const int yg = y + a.yoff;
+        const uint4 C = xy_pair_block(a, (uint64_t)((yg & ~1) * a.gpr + g));
+        float rr[4], cand[4];
+        xy_group_uniforms(a, (uint64_t)(yg * a.gpr + g), C, yg & 1, rr, cand);
 #pragma unroll
-    for (int sub = 0; sub < 2; ++sub) {
-        const uint4 R = philox_tag<TAG_XY>(mk_ctr((uint64_t)(idx + a.yoff * a.gpr), a.draw, (uint32_t)a.colour, (uint32_t)sub), a.rk0);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int j = 2 * sub + e;
-            const uint32_t Ur = e ? R.z : R.x, Uc = e ? R.w : R.y;
-            const float r = ((float)Ur + 1.0f) * 0x1p-32f;
-            const float ct = ((float)Uc + 1.0f) * 0x1p-32f;
+        for (int j = 0; j < 4; ++j) {
             float cs, cc, ss, sc;
-            sincos_turns(ct, cs, cc);
+            sincos_turns(cand[j], cs, cc);
             sincos_turns(ov[j], ss, sc);
             const float de = -(hx * (cc - sc) + hy * (cs - ss));
-            if (!(r > 1.0f - __expf(de))) ov[j] = ct;
+            if (!(rr[j] > 1.0f - __expf(de))) ov[j] = cand[j];
         }
     }
     xy_store_group(prow, 4 * g, a.nxh, a.pitch, ov);

@@ -127,3 +127,34 @@ def test_clock_contract_v3_statistics(oracle):
             np.add.at(joint, (d0[:, :, e1].ravel(), d0[:, :, e2].ravel()), 1)
             exp = d0[:, :, 0].size / (q - 1) ** 2
             assert (((joint - exp) ** 2) / exp).sum() < 60, (e1, e2)          # 24 dof: mean 24, sd ~7
+
+
+def test_xy_contract_v2_assembly_and_statistics(oracle):
+    """XY periodic: 24 + 24 bits per site from three Philox blocks per 8 sites (csrc/xy.cu, oracle/rng_contract.c orc_xy_uniforms),
+    restated here; both uniforms in (0, 1] with exactly 24-bit resolution, uncorrelated with each other and between the two
+    rows of a pair that share the block of low halves"""
+    TAG_XY = 0x58593244
+    seed, draw, nx, ny = 9, 5, 44, 6            # nx/2 = 22: six groups per row, the last one partial
+    r, c = oracle.xy_uniforms(seed, draw, nx, ny)
+    r, c = r.reshape(ny, nx), c.reshape(ny, nx)
+    gpr = (nx // 2 + 3) // 4
+    for y0 in range(ny):
+        for x0 in range(nx):
+            colour, xi = (x0 + y0) & 1, x0 >> 1
+            c3 = lambda sub: ((draw >> 32) & 0xFFFF) | (colour << 16) | (sub << 24)
+            R = oracle.philox([y0 * gpr + (xi >> 2), 0, draw, c3(0)], [seed, TAG_XY])
+            C = oracle.philox([(y0 & ~1) * gpr + (xi >> 2), 0, draw, c3(1)], [seed, TAG_XY])
+            W, cw = int(R[xi & 3]), int(C[xi & 3])
+            ur = ((W & 0xFF) << 16) | ((cw >> 16) if (y0 & 1) else (cw & 0xFFFF))
+            assert r[y0, x0] == (ur + 1) * 2.0 ** -24 and c[y0, x0] == ((W >> 8) + 1) * 2.0 ** -24
+    r, c = oracle.xy_uniforms(1, 2, 512, 256)
+    for u in (r, c):
+        assert u.min() > 0.0 and u.max() <= 1.0 and abs(u.mean() - 0.5) < 0.005
+        k = u * 2.0 ** 24
+        assert np.array_equal(k, np.round(k))
+        assert np.array_equal(u, u.astype(np.float32).astype(np.float64))       # exact in fp32: the GPU sees the same values
+        h, _ = np.histogram(u, bins=256, range=(0, 1))
+        assert ((h - u.size / 256) ** 2 / (u.size / 256)).sum() < 360
+    assert abs(np.corrcoef(r, c)[0, 1]) < 0.01
+    r2 = r.reshape(256, 512)
+    assert abs(np.corrcoef(r2[0::2].ravel(), r2[1::2].ravel())[0, 1]) < 0.01
