@@ -126,10 +126,12 @@ static_assert(XY_ROWS % 2 == 0, "the strip loop is unrolled by two rows (the nei
 // One row of a strip.  P = (y + colour) & 1 at compile time: the x position of colour-compact site xi is 2 xi + P, its
 // same-row neighbours are the other colour's xi - 1 + P and xi + P.
 // RNG contract (v2; CPU restatement: oracle/rng_contract.c, orc_xy_uniforms).  A group = 4 colour-compact sites of one row,
-// blk = y gpr + g.  Per site 24 + 24 bits (both uniforms are used in fp32, which holds 24):
+// blk = y gpr + g.  Per site 23 + 23 bits, turned into fp32 WITHOUT an integer-to-float conversion (I2F shares the XU pipe
+// with MUFU, the pipe that bounds the Metropolis pass): as_float(0x3F800000 | U) is 1 + U 2^-23 in [1, 2), one FADD later
+// (U + 1) 2^-23 in (0, 1], exact:
 //   R = philox(ctr(blk, draw, colour, 0), (seed, TAG_XY))               one block per group and row
 //   C = philox(ctr(blk of the EVEN row of the pair (y & ~1), draw, colour, 1), same key)    one block per group and row PAIR
-//   candidate U_c = R[j] >> 8;   accept U_r = (R[j] & 0xFF) << 16 | half(C[j], y & 1);   u = (U + 1) 2^-24 in (0, 1], exact in fp32
+//   candidate U_c = R[j] & 0x7FFFFF;   accept U_r = (R[j] >> 23) << 14 | half(C[j], y & 1) & 0x3FFF;   u = (U + 1) 2^-23 in (0, 1]
 // Three Philox blocks per 8 sites instead of four (round 1: two full 32-bit words per site, rounded to fp32).
 __device__ __forceinline__ uint4 xy_pair_block(const XYArgs& a, uint64_t blk_even)
 {
@@ -141,10 +143,10 @@ __device__ __forceinline__ void xy_group_uniforms(const XYArgs& a, uint64_t blk,
     const uint32_t W[4] = {R.x, R.y, R.z, R.w}, cw[4] = {C.x, C.y, C.z, C.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const uint32_t Uc = W[j] >> 8;
-        const uint32_t Ur = ((W[j] & 0xFFu) << 16) | (odd ? cw[j] >> 16 : cw[j] & 0xFFFFu);
-        ct[j] = ((float)Uc + 1.0f) * 0x1p-24f;      // candidate angle in turns, (0, 1]
-        r[j] = ((float)Ur + 1.0f) * 0x1p-24f;       // accept uniform, (0, 1]
+        const uint32_t Uc = W[j] & 0x7FFFFFu;
+        const uint32_t Ur = ((W[j] >> 23) << 14) | ((odd ? cw[j] >> 16 : cw[j]) & 0x3FFFu);
+        ct[j] = __uint_as_float(0x3F800000u | Uc) + (0x1p-23f - 1.0f);      // candidate angle in turns, (0, 1]
+        r[j] = __uint_as_float(0x3F800000u | Ur) + (0x1p-23f - 1.0f);       // accept uniform, (0, 1]
     }
 }
 

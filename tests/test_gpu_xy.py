@@ -120,7 +120,8 @@ def test_xy_over_relaxation(oracle, shape, row_mode):
         check_observables(g, o, n, ("over-relaxation", it))
         d = site_differences(g, o)
         # the reflection axis atan2(h) is ill-conditioned where |h| is tiny: angle error ~ 1e-7 / |h|
-        assert np.quantile(d, 0.9999) < 2e-5 and d.max() < 1e-2
+        # (on a lattice of fewer than 1e5 sites the 0.9999 quantile is the single worst site: use 0.999 there)
+        assert np.quantile(d, 0.9999 if n >= 100000 else 0.999) < 2e-5 and d.max() < 1e-2
 
 
 @pytest.mark.parametrize("nx,ny", [(32, 16), (44, 16), (42, 10), (46, 12)])

@@ -130,8 +130,8 @@ def test_clock_contract_v3_statistics(oracle):
 
 
 def test_xy_contract_v2_assembly_and_statistics(oracle):
-    """XY periodic: 24 + 24 bits per site from three Philox blocks per 8 sites (csrc/xy.cu, oracle/rng_contract.c orc_xy_uniforms),
-    restated here; both uniforms in (0, 1] with exactly 24-bit resolution, uncorrelated with each other and between the two
+    """XY periodic: 23 + 23 bits per site from three Philox blocks per 8 sites (csrc/xy.cu, oracle/rng_contract.c orc_xy_uniforms),
+    restated here; both uniforms in (0, 1] with exactly 23-bit resolution, uncorrelated with each other and between the two
     rows of a pair that share the block of low halves"""
     TAG_XY = 0x58593244
     seed, draw, nx, ny = 9, 5, 44, 6            # nx/2 = 22: six groups per row, the last one partial
@@ -145,12 +145,12 @@ def test_xy_contract_v2_assembly_and_statistics(oracle):
             R = oracle.philox([y0 * gpr + (xi >> 2), 0, draw, c3(0)], [seed, TAG_XY])
             C = oracle.philox([(y0 & ~1) * gpr + (xi >> 2), 0, draw, c3(1)], [seed, TAG_XY])
             W, cw = int(R[xi & 3]), int(C[xi & 3])
-            ur = ((W & 0xFF) << 16) | ((cw >> 16) if (y0 & 1) else (cw & 0xFFFF))
-            assert r[y0, x0] == (ur + 1) * 2.0 ** -24 and c[y0, x0] == ((W >> 8) + 1) * 2.0 ** -24
+            ur = ((W >> 23) << 14) | (((cw >> 16) if (y0 & 1) else cw) & 0x3FFF)
+            assert r[y0, x0] == (ur + 1) * 2.0 ** -23 and c[y0, x0] == ((W & 0x7FFFFF) + 1) * 2.0 ** -23
     r, c = oracle.xy_uniforms(1, 2, 512, 256)
     for u in (r, c):
         assert u.min() > 0.0 and u.max() <= 1.0 and abs(u.mean() - 0.5) < 0.005
-        k = u * 2.0 ** 24
+        k = u * 2.0 ** 23
         assert np.array_equal(k, np.round(k))
         assert np.array_equal(u, u.astype(np.float32).astype(np.float64))       # exact in fp32: the GPU sees the same values
         h, _ = np.histogram(u, bins=256, range=(0, 1))
