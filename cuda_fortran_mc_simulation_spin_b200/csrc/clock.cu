@@ -21,7 +21,8 @@ struct Clock {
     uint32_t seed;
     uint64_t draw;
     std::vector<double> magne, etab, ws;   // host tables exactly as the reference builds them
-    uint8_t* d_cls;
+    uint8_t* d_cls;        // q^6 class ids: bytes, or 16-bit when cls16
+    int cls16, n_classes;
     uint64_t* d_thr;
     uint16_t* d_thr16;     // direct lookup table (q <= 6)
     int direct, grid_direct, smem_direct, threads_direct;
@@ -52,7 +53,7 @@ int build_tables(Clock* m)
             }
 #define ET(i, j, c) m->etab[(i) + q * ((j) + q * (c))]
     std::map<uint64_t, int> classes;
-    std::vector<uint8_t> cls(q6);
+    std::vector<uint16_t> cls(q6);
     std::vector<uint64_t> thr;
     for (int ca = 0; ca < q; ++ca)
         for (int cb = 0; cb < q; ++cb)
@@ -74,16 +75,18 @@ int build_tables(Clock* m)
                             int id;
                             if (it == classes.end()) {
                                 id = (int)thr.size();
-                                if (id >= CLOCK_MAX_CLASSES) {
-                                    snprintf(g_b200mc_err, sizeof(g_b200mc_err), "clock: more than %d distinct acceptance thresholds (q = %d)", CLOCK_MAX_CLASSES, q);
+                                if (id >= CLOCK_MAX_CLASSES16) {
+                                    snprintf(g_b200mc_err, sizeof(g_b200mc_err), "clock: more than %d distinct acceptance thresholds (q = %d)", CLOCK_MAX_CLASSES16, q);
                                     return B200MC_ERR_UNSUPPORTED;
                                 }
                                 classes[t] = id; thr.push_back(t);
                             } else id = it->second;
-                            cls[at] = (uint8_t)id;
+                            cls[at] = (uint16_t)id;
                         }
 #undef ET
-    thr.resize(CLOCK_MAX_CLASSES, 0);
+    m->n_classes = (int)thr.size();
+    m->cls16 = m->n_classes > CLOCK_MAX_CLASSES ? 1 : 0;      // q >= 14: more than 256 distinct thresholds
+    thr.resize(m->cls16 ? CLOCK_MAX_CLASSES16 : CLOCK_MAX_CLASSES, 0);
     if (m->d_thr16) {
         // direct table T[next][F] = thr >> 17 (0 .. 32768), F = up + q down + q^2 left + q^3 right + q^4 cur: the same order as
         // the class table (index = F + q^5 next)
@@ -92,8 +95,13 @@ int build_tables(Clock* m)
         CK(cudaMemcpyAsync(m->d_thr16, t16.data(), q6 * sizeof(uint16_t), cudaMemcpyHostToDevice, m->stream));
         CK(cudaStreamSynchronize(m->stream));
     }
-    CK(cudaMemcpyAsync(m->d_cls, cls.data(), q6, cudaMemcpyHostToDevice, m->stream));
-    CK(cudaMemcpyAsync(m->d_thr, thr.data(), CLOCK_MAX_CLASSES * sizeof(uint64_t), cudaMemcpyHostToDevice, m->stream));
+    std::vector<uint8_t> cls8;
+    if (!m->cls16) {
+        cls8.resize(q6);
+        for (size_t i = 0; i < q6; ++i) cls8[i] = (uint8_t)cls[i];
+        CK(cudaMemcpyAsync(m->d_cls, cls8.data(), q6, cudaMemcpyHostToDevice, m->stream));
+    } else CK(cudaMemcpyAsync(m->d_cls, cls.data(), q6 * sizeof(uint16_t), cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemcpyAsync(m->d_thr, thr.data(), thr.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, m->stream));
     if (m->d_ws) CK(cudaMemcpyAsync(m->d_ws, m->ws.data(), q6 * sizeof(double), cudaMemcpyHostToDevice, m->stream));
     CK(cudaStreamSynchronize(m->stream));  // host vectors go out of scope
     return B200MC_OK;
@@ -108,7 +116,7 @@ void fill_args(Clock* m, int j, int colour, ClockArgs* a)
     for (int t = 0; t < 6; ++t) a->r.off[t] = g.off[colour][t];
     a->r.seed = m->seed; a->r.colour = (uint32_t)colour; a->r.draw = m->draw;
     a->r.ticket = nullptr; a->r.chunk = 128;
-    a->cls = m->d_cls; a->thr = m->d_thr; a->q = (uint32_t)m->q;
+    a->cls = m->d_cls; a->cls16 = m->cls16; a->thr = m->d_thr; a->q = (uint32_t)m->q;
     a->tab_bytes = (uint32_t)((size_t)m->q * m->q * m->q * m->q * m->q * m->q);
     a->replica = (uint32_t)(m->sample0 + j);
     for (int r = 0; r < 10; ++r) {
@@ -130,7 +138,8 @@ int sweep(Clock* m)
             if (m->direct && m->q == 6 && m->threads_direct == 1024) clock_pass_direct_kernel<6, 1024><<<m->grid_direct, 1024, m->smem_direct, m->stream>>>(a);
             else if (m->direct && m->q == 6) clock_pass_direct_kernel<6><<<m->grid_direct, CLOCK_DIRECT_THREADS, m->smem_direct, m->stream>>>(a);
             else if (m->direct) clock_pass_direct_kernel<0><<<m->grid_direct, CLOCK_DIRECT_THREADS, m->smem_direct, m->stream>>>(a);
-            else clock_pass_kernel<<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
+            else if (m->cls16) clock_pass_kernel<uint16_t><<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
+            else clock_pass_kernel<uint8_t><<<m->grid, 256, m->smem_bytes, m->stream>>>(a);
             CK(cudaGetLastError());
             int rc = ring_halo(&m->st[j], colour, m->stream);
             if (rc) return rc;
@@ -202,7 +211,9 @@ int create(void** out, int64_t nx, int64_t ny, double kbt, int32_t q, int32_t n_
     *out = nullptr;
     if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0");
     if (q < 2) ARG_FAIL("state must be >= 2");
-    if (q > 16) { snprintf(g_b200mc_err, sizeof(g_b200mc_err), "clock: state = %d not supported (q^6 table; max 16)", q); return B200MC_ERR_UNSUPPORTED; }
+    // (the reference's nominal limit is 50, src/clock_gpu_m.f90:10, with a q^6 real64 table -- 125 GB at q = 50; here the host builds
+    // the same table: 1.5 GB and a few seconds at q = 24)
+    if (q > 24) { snprintf(g_b200mc_err, sizeof(g_b200mc_err), "clock: state = %d not supported (q^6 table built on the host; max 24)", q); return B200MC_ERR_UNSUPPORTED; }
     if (n_multi < 1) ARG_FAIL("n_multi must be >= 1");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -226,7 +237,7 @@ int create(void** out, int64_t nx, int64_t ny, double kbt, int32_t q, int32_t n_
         if (rc) { destroy(m); return rc; }
     }
     const size_t q6 = (size_t)q * q * q * q * q * q;
-    if (cudaMalloc(&m->d_cls, (q6 + 15) / 16 * 16) != cudaSuccess || cudaMalloc(&m->d_thr, CLOCK_MAX_CLASSES * sizeof(uint64_t)) != cudaSuccess ||
+    if (cudaMalloc(&m->d_cls, (2 * q6 + 15) / 16 * 16) != cudaSuccess || cudaMalloc(&m->d_thr, CLOCK_MAX_CLASSES16 * sizeof(uint64_t)) != cudaSuccess ||
         cudaMalloc(&m->d_acc, (size_t)n_multi * 192 * sizeof(unsigned long long)) != cudaSuccess) {
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed");
         destroy(m); return B200MC_ERR_CUDA;
@@ -239,11 +250,12 @@ int create(void** out, int64_t nx, int64_t ny, double kbt, int32_t q, int32_t n_
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     m->cls_in_smem = want <= (size_t)maxsm ? 1 : 0;
     m->smem_bytes = (int)(m->cls_in_smem ? want : CLOCK_MAX_CLASSES * sizeof(uint64_t));
-    if (cudaFuncSetAttribute(clock_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(clock_pass_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(clock_pass_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CLOCK_MAX_CLASSES * sizeof(uint64_t))) != cudaSuccess) {
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaFuncSetAttribute(smem) failed");
         destroy(m); return B200MC_ERR_CUDA;
     }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clock_pass_kernel, 256, m->smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clock_pass_kernel<uint8_t>, 256, m->smem_bytes);
     if (occ < 1) occ = 1;
     const int64_t need = (g.L + 255) / 256;
     m->grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);

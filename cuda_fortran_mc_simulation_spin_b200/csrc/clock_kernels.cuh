@@ -14,7 +14,8 @@
 #include "ising_kernels.cuh"  // RingPassArgs, philox_rk
 #include "clock_word.cuh"
 
-#define CLOCK_MAX_CLASSES 256
+#define CLOCK_MAX_CLASSES 256        // class ids fit a byte up to here (thresholds staged in shared memory)
+#define CLOCK_MAX_CLASSES16 65536    // beyond: 16-bit class ids, thresholds read through L1 / L2
 
 // Philox4x32-10 with both round-key schedules supplied by the host
 __device__ __forceinline__ uint4 philox_rk2(uint4 c, const uint32_t (&rk0)[10], const uint32_t (&rk1)[10])
@@ -36,7 +37,8 @@ __device__ __forceinline__ uint4 philox_rk2(uint4 c, const uint32_t (&rk0)[10], 
 
 struct ClockArgs {
     RingPassArgs r;
-    const uint8_t* cls;        // q^6 class ids, index up + q(down + q(left + q(right + q(cur + q next))))
+    const uint8_t* cls;        // q^6 class ids (one byte each, or two when cls16), index up + q(down + q(left + q(right + q(cur + q next))))
+    int cls16;                 // more than 256 distinct thresholds (q >= 14): 16-bit class ids, thresholds in global memory
     const uint64_t* thr;       // per class: accept iff U < thr   (0 .. 2^32)
     uint32_t q;
     uint32_t tab_bytes;        // q^6
@@ -51,7 +53,8 @@ struct ClockArgs {
 // class table, full 33-bit threshold.
 // accept iff U_a < thr[class]; proposal next = floor(W_e q / 2^32) = the reference's min(floor(next_states q), q - 1)
 // (src/clock_gpu_m.f90:211, with the u == 1 clamp of SURVEY Q4) on the contract's next_states
-__device__ __forceinline__ uint4 clock_vector_exact_body(const ClockArgs& a, const uint8_t* cls, const uint64_t* thr, uint64_t pglob,
+template <typename CLS>
+__device__ __forceinline__ uint4 clock_vector_exact_body(const ClockArgs& a, const CLS* cls, const uint64_t* thr, uint64_t pglob,
                                                          const uint4& o, const uint4& nu, const uint4& nd, const uint4& nl, const uint4& nr)
 {
     const RingPassArgs& r = a.r;
@@ -89,24 +92,31 @@ __device__ __forceinline__ uint4 clock_vector_exact_body(const ClockArgs& a, con
 // (arguments and result by value: registers, not local memory, on the caller's hot path)
 __device__ __noinline__ uint4 clock_vector_exact(const ClockArgs& a, uint64_t pglob, uint4 o, uint4 nu, uint4 nd, uint4 nl, uint4 nr)
 {
-    return clock_vector_exact_body(a, a.cls, a.thr, pglob, o, nu, nd, nl, nr);
+    return clock_vector_exact_body<uint8_t>(a, a.cls, a.thr, pglob, o, nu, nd, nl, nr);   // (direct path: q <= 6, at most 15 classes)
 }
 
-// class-table pass (any q <= 16): every site with its full 32-bit uniforms, class ids from shared memory (q <= 7) or L1/L2
+// class-table pass (any q): every site with its full 32-bit uniforms.  CLS = uint8_t: at most 256 distinct thresholds, staged
+// in shared memory together with the class ids when they fit (q <= 7), else ids through L1 / L2; CLS = uint16_t (q >= 14):
+// ids and thresholds through L1 / L2.
+template <typename CLS>
 __global__ void __launch_bounds__(256)
 clock_pass_kernel(const __grid_constant__ ClockArgs a)
 {
     extern __shared__ __align__(16) uint8_t sm[];
     uint64_t* sthr = reinterpret_cast<uint64_t*>(sm);               // CLOCK_MAX_CLASSES * 8 bytes
     uint8_t* scls = sm + CLOCK_MAX_CLASSES * sizeof(uint64_t);      // q^6 bytes (if cls_in_smem)
-    for (int i = threadIdx.x; i < CLOCK_MAX_CLASSES; i += blockDim.x) sthr[i] = a.thr[i];
-    if (a.cls_in_smem) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.cls);
-        uint4* dst = reinterpret_cast<uint4*>(scls);
-        for (uint32_t i = threadIdx.x; i < (a.tab_bytes + 15) / 16; i += blockDim.x) dst[i] = src[i];
+    const bool wide = sizeof(CLS) == 2;
+    if (!wide) {
+        for (int i = threadIdx.x; i < CLOCK_MAX_CLASSES; i += blockDim.x) sthr[i] = a.thr[i];
+        if (a.cls_in_smem) {
+            const uint4* src = reinterpret_cast<const uint4*>(a.cls);
+            uint4* dst = reinterpret_cast<uint4*>(scls);
+            for (uint32_t i = threadIdx.x; i < (a.tab_bytes + 15) / 16; i += blockDim.x) dst[i] = src[i];
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const uint8_t* cls = a.cls_in_smem ? scls : a.cls;
+    const CLS* cls = (!wide && a.cls_in_smem) ? reinterpret_cast<const CLS*>(scls) : reinterpret_cast<const CLS*>(a.cls);
+    const uint64_t* thr = wide ? a.thr : sthr;
 
     const RingPassArgs& r = a.r;
     uint4* own = r.own + r.H;
@@ -119,7 +129,7 @@ clock_pass_kernel(const __grid_constant__ ClockArgs a)
         const uint4 nr = ld_other(oth + v + (int)r.off[1]);   // i+1  right
         const uint4 nu = ld_other(oth + v + (int)r.off[2]);   // i+nx up
         const uint4 nd = ld_other(oth + v + (int)r.off[3]);   // i-nx down
-        own[v] = clock_vector_exact_body(a, cls, sthr, (uint64_t)(r.p0 + v), o, nu, nd, nl, nr);
+        own[v] = clock_vector_exact_body<CLS>(a, cls, thr, (uint64_t)(r.p0 + v), o, nu, nd, nl, nr);
     }
 }
 

@@ -50,6 +50,7 @@ struct SixArgs {
     const uint16_t* thr16;   // direct lookup (q <= 6): T[k][F] = thr >> 17, k = 0 .. q-2 (new = c + 1 + k mod q), F = r + q u + q^2 l + q^3 d + q^4 c
     uint32_t tab_bytes, q5;
     int cls_in_smem;
+    int prefetch;            // L2 prefetch of the next iteration's vectors (B200MC_SIX_PREFETCH, A/B)
     uint64_t draw;
     uint32_t rk0[10];        // Philox round keys seed + r W0
 };
@@ -244,6 +245,12 @@ sixclock_pass_kernel(const __grid_constant__ SixArgs a)
     int Y = idx / nvr, v = idx - Y * nvr;
     int rep = Y / ny, y = Y - rep * ny;
     while (idx < total) {
+        if (DIRECT && a.prefetch && (threadIdx.x & 7) == 0 && idx + stride < total) {
+            // the two streamed vectors of this thread's NEXT iteration into L2 (one lane per 128-byte line); the rows above
+            // and below are the same lines other threads of the wave stream as their own row
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(a.own) + idx + stride));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(a.oth) + idx + stride));
+        }
         if (DIRECT) {
             if ((y + a.colour) & 1) six_vector_direct<1, Q>(a, scls, idx, y, rep, v);
             else six_vector_direct<0, Q>(a, scls, idx, y, rep, v);
@@ -437,6 +444,7 @@ struct Six {
     uint8_t* d_cls;
     uint32_t *d_thi, *d_tlo;
     uint16_t* d_thr16;   // direct lookup table (q^6 entries)
+    int prefetch;
     int direct, threads; // direct: one-load lookup with SIX_DIRECT_THREADS-thread blocks, one per SM
     double* d_prob;
     double* d_rnds;
@@ -544,6 +552,7 @@ void fill_args(Six* m, int colour, SixArgs* a)
     a->cls = m->d_cls; a->thi = m->d_thi; a->tlo = m->d_tlo; a->thr16 = m->d_thr16;
     a->tab_bytes = (uint32_t)m->prob.size(); a->q5 = a->tab_bytes / (uint32_t)m->q; a->cls_in_smem = m->cls_in_smem;
     a->draw = m->draw;
+    a->prefetch = m->prefetch;
     for (int r = 0; r < 10; ++r) a->rk0[r] = m->seed + (uint32_t)r * PHILOX_W0;
 }
 
@@ -698,6 +707,7 @@ int b200mc_sixclock_create_variant(void** out, int64_t nx, int64_t ny, double kb
     m->grid = (int)(need < (int64_t)m->sms * occ ? need : (int64_t)m->sms * occ);
     // direct lookup: 2 q^6 bytes of thresholds in shared memory, one block of SIX_DIRECT_THREADS threads per SM
     m->direct = 0; m->threads = 256;
+    { const char* t = getenv("B200MC_SIX_PREFETCH"); m->prefetch = (t && atoi(t) == 1) ? 1 : 0; }
     {
         const size_t wantd = (2 * q6 + 15) / 16 * 16;
         const char* t = getenv("B200MC_SIX_DIRECT");

@@ -53,6 +53,26 @@ def test_clock_trajectory_bit_exact(oracle, shape, q, kbt, start, lookup):
         assert abs(m - o.calc_magne_sum()) <= 1e-12 * g.nall()
 
 
+@pytest.mark.parametrize("q,kbt", [(14, 0.5), (16, 0.6), (20, 0.4)])
+def test_clock_large_q_sixteen_bit_classes(oracle, q, kbt):
+    """q >= 14 has more than 256 distinct acceptance thresholds (370 at q = 14, 554 at q = 16): 16-bit class ids, thresholds
+    through L1 / L2 (round 1 returned B200MC_ERR_UNSUPPORTED here); the reference's nominal limit is 50 with a q^6 real64
+    table (src/clock_gpu_m.f90:10,77), ours 24 (host-built table)"""
+    from cuda_fortran_mc_simulation_spin_b200 import clock_gpu_m
+    g = clock_gpu_m.clock_gpu().init(33, 32, kbt, q, 42)
+    o = oracle.clock_gpu().init(33, 32, kbt, q, 42)
+    assert np.array_equal(g.ws(), o.ws)
+    assert np.unique(o.ws).size > 256
+    g.set_random_spin(); o.set_random_spin()
+    for sweep in range(4):
+        g.update(); o.update()
+        assert np.array_equal(g.spins(), o.spins()), f"states differ after sweep {sweep + 1}"
+    assert abs(g.calc_energy_sum() - o.calc_energy_sum()) <= 1e-9 and abs(g.calc_magne_sum() - o.calc_magne_sum()) <= 1e-9
+    from cuda_fortran_mc_simulation_spin_b200 import B200MCError
+    with pytest.raises(B200MCError, match="max 24"):
+        clock_gpu_m.clock_gpu().init(33, 32, kbt, 25, 42)
+
+
 def test_clock_multi_bit_exact(oracle, lookup):
     from cuda_fortran_mc_simulation_spin_b200 import clock_gpu_multi_m
     g = clock_gpu_multi_m.clock_gpu().init(101, 100, 0.8, 6, 3, 42)
