@@ -136,3 +136,22 @@ def test_clock_full_size_properties():
     assert (h.sum(axis=1) == n).all() and (bl.sum(axis=1) == n).all() and (bd.sum(axis=1) == n).all()
     e = g.calc_energy_sum()
     assert ((-2 * n < e) & (e < -1.0 * n)).all()
+
+
+def test_c4_helical_lattice_against_oracle(oracle):
+    """the helical q = 6 clock at the size bench.py times (16385 x 16384, kbt = 0.91): two sweeps, states bit-exact against
+    the CPU oracle"""
+    import os
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 1 << 40
+    if avail < 16 * (1 << 30):
+        pytest.skip("needs ~16 GB of free host memory")
+    from cuda_fortran_mc_simulation_spin_b200 import clock_gpu_m
+    g = clock_gpu_m.clock_gpu().init(16385, 16384, 0.91, 6, 42)
+    o = oracle.clock_gpu().init(16385, 16384, 0.91, 6, 42)
+    for sweep in range(2):
+        g.update(); o.update()
+    assert np.array_equal(g.spins(), o.spins()), "helical clock: states differ from the oracle after 2 sweeps"
+    assert abs(g.calc_energy_sum() - o.calc_energy_sum()) <= 1e-12 * abs(o.calc_energy_sum()) * 10

@@ -123,3 +123,26 @@ def test_bits_full_size_properties():
     g3 = i3.ising3d_gpu().init_packed(1023, 1023, 1024, KBT3, 43)
     g3.update_n(3)
     assert g3.measure() != (e, m)
+
+
+def test_bits_headline_lattice_against_oracle(oracle):
+    """BASELINE config 2' at the shape bench.py runs (1023 x 1023 x 1024, all-up start, kbt = 4.51152, seed 42) on the
+    bit-packed storage: two sweeps + E/M after each (the second one accumulated by the pass itself), whole configuration
+    bit-exact against the CPU oracle run on the bit-packed contract's uniforms.
+    Host memory: ~4.3 GB oracle spins + 8.6 GB uniforms + 4.3 GB export."""
+    import os
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 1 << 40
+    if avail < 28 * (1 << 30):
+        pytest.skip("needs ~28 GB of free host memory")
+    g, o = _pair(oracle, 3, (1023, 1023, 1024), KBT3, 42)
+    n = o.nall()
+    for sweep in range(2):
+        g.update()
+        u = oracle.isingbits_uniforms(42, sweep, n)
+        o.update(randoms=u)
+        del u
+        assert g.measure() == (o.calc_energy_sum(), o.calc_magne_sum()), sweep
+    assert np.array_equal(g.spins(), o.s), "bit-packed headline lattice: configuration differs from the oracle after 2 sweeps"

@@ -189,3 +189,29 @@ def test_full_size_properties_config4():
     assert abs(e[0] - e[1]) < 1e-3 and e[0] != e[1]            # independent samples of the same ensemble
     g.set_kbt(1e-3); g.init_sixclock_order(); g.update_metropolis()
     assert np.allclose(g.calc_energy(), -2.0)                  # beta -> infinity from order: nothing moves
+
+
+def test_c4_lattice_against_oracle(oracle):
+    """BASELINE config 4 at full size (q = 6, 16384 x 16384, kbt = 0.91, two samples per launch): two sweeps of the batch,
+    states of both samples bit-exact against the CPU oracle (~1 GB of int32 states + 4.3 GB of uniforms per sample)"""
+    import os
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 1 << 40
+    if avail < 16 * (1 << 30):
+        pytest.skip("needs ~16 GB of free host memory")
+    from cuda_fortran_mc_simulation_spin_b200._sixclock import sixclock
+    nx = ny = 16384
+    g = sixclock(nx, ny, 0.91, 6, 2, 42)
+    os_ = [oracle.clock_tableall(nx, ny, 0.91, 6) for _ in range(2)]
+    for sweep in range(2):
+        g.update_metropolis()
+        for j, o in enumerate(os_):
+            o.update_metropolis(oracle.torus_uniforms(42, sweep, j, nx, ny, 6))
+    s = g.get_sixclock()
+    e, m = g.calc_energy(), g.calc_magne()
+    for j, o in enumerate(os_):
+        assert np.array_equal(s[j], o.c), f"sample {j}: states differ from the oracle after 2 sweeps"
+        assert abs(e[j] - o.calc_energy()) <= 1e-12 and abs(m[j] - o.calc_magne()) <= 1e-12
+    g.close()
