@@ -62,7 +62,6 @@ __device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p)
     return v;
 }
 __device__ __forceinline__ uint32_t word_of(const uint4& v, int w) { return w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w; }
-__device__ __forceinline__ uint32_t byte_of(const uint4& v, int j) { return (word_of(v, j >> 2) >> (8 * (j & 3))) & 0xFFu; }
 
 // the other colour's same-row values one compact position to the left (p == 0: x0 - 1) or to
 // the right (p == 1: x0 + 1) of the 16 sites of vector v, periodic in x.  pv = address of vector v of the row.
