@@ -131,7 +131,8 @@ static_assert(XY_ROWS % 2 == 0, "the strip loop is unrolled by two rows (the nei
 // (U + 1) 2^-23 in (0, 1], exact:
 //   R = philox(ctr(blk, draw, colour, 0), (seed, TAG_XY))               one block per group and row
 //   C = philox(ctr(blk of the EVEN row of the pair (y & ~1), draw, colour, 1), same key)    one block per group and row PAIR
-//   candidate U_c = R[j] & 0x7FFFFF;   accept U_r = (R[j] >> 23) << 14 | half(C[j], y & 1) & 0x3FFF;   u = (U + 1) 2^-23 in (0, 1]
+//   candidate U_c = R[j] & 0x7FFFFF;   accept U_r = (R[j] >> 24 & 0x7F) << 16 | half(C[j], y & 1);   u = (U + 1) 2^-23 in (0, 1]
+// (the accept mantissa is byte-aligned: one PRMT gathers the two bytes of C and the top byte of R, one LOP3 sets the exponent)
 // Three Philox blocks per 8 sites instead of four (round 1: two full 32-bit words per site, rounded to fp32).
 __device__ __forceinline__ uint4 xy_pair_block(const XYArgs& a, uint64_t blk_even)
 {
@@ -143,10 +144,10 @@ __device__ __forceinline__ void xy_group_uniforms(const XYArgs& a, uint64_t blk,
     const uint32_t W[4] = {R.x, R.y, R.z, R.w}, cw[4] = {C.x, C.y, C.z, C.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const uint32_t Uc = W[j] & 0x7FFFFFu;
-        const uint32_t Ur = ((W[j] >> 23) << 14) | ((odd ? cw[j] >> 16 : cw[j]) & 0x3FFFu);
-        ct[j] = __uint_as_float(0x3F800000u | Uc) + (0x1p-23f - 1.0f);      // candidate angle in turns, (0, 1]
-        r[j] = __uint_as_float(0x3F800000u | Ur) + (0x1p-23f - 1.0f);       // accept uniform, (0, 1]
+        // bytes (C half lo, C half hi, R byte 3, -) -> mantissa; bit 23 and the exponent are forced by the mask / or
+        const uint32_t g = prmt(cw[j], W[j], odd ? 0x0732u : 0x0710u);
+        ct[j] = __uint_as_float((W[j] & 0x007FFFFFu) | 0x3F800000u) + (0x1p-23f - 1.0f);      // candidate angle in turns, (0, 1]
+        r[j] = __uint_as_float((g & 0x007FFFFFu) | 0x3F800000u) + (0x1p-23f - 1.0f);          // accept uniform, (0, 1]
     }
 }
 

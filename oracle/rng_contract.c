@@ -260,7 +260,7 @@ ORC_API void orc_ising_uniforms_fast(uint32_t seed, uint64_t draw, int64_t n_sit
  *   R = philox(ctr(blk, draw, colour, 0), (seed, TAG_XY))                    one block per group and row
  *   C = philox(ctr(blk of the even row of the pair (y0 & ~1), draw, colour, 1), same key)
  *   candidate U_c = R[xi & 3] & 0x7FFFFF                                          -> candidates(x, y)
- *   accept    U_r = (R[xi & 3] >> 23) << 14 | half(C[xi & 3], y0 & 1) & 0x3FFF     -> randoms(x, y)
+ *   accept    U_r = (R[xi & 3] >> 24 & 0x7F) << 16 | half(C[xi & 3], y0 & 1)      -> randoms(x, y)
  * u = (U + 1) 2^-23 in (0, 1]  (half(w, 0) = w & 0xFFFF, half(w, 1) = w >> 16).
  * set_random_spin: R = philox(ctr(blk, draw, colour, 0), (seed, TAG_INIT)), U = R[xi & 3].
  * Arrays are written in the reference's order randoms(nx, ny): out[x0 + nx * y0].
@@ -281,7 +281,7 @@ ORC_API void orc_xy_uniforms(uint32_t seed, uint64_t draw, int64_t nx, int64_t n
             mk_ctr(c, (uint64_t)((y0 & ~(int64_t)1) * gpr + (xi >> 2)), draw, colour, 1u);
             orc_philox4x32_10(c, key, cp);
             const uint32_t W = r[xi & 3], ch = (y0 & 1) ? cp[xi & 3] >> 16 : cp[xi & 3] & 0xFFFFu;
-            randoms[x0 + nx * y0] = ((double)(((W >> 23) << 14) | (ch & 0x3FFFu)) + 1.0) * 0x1p-23;
+            randoms[x0 + nx * y0] = ((double)((((W >> 24) & 0x7Fu) << 16) | ch) + 1.0) * 0x1p-23;
             candidates[x0 + nx * y0] = ((double)(W & 0x7FFFFFu) + 1.0) * 0x1p-23;
         }
 }

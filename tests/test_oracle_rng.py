@@ -145,7 +145,7 @@ def test_xy_contract_v2_assembly_and_statistics(oracle):
             R = oracle.philox([y0 * gpr + (xi >> 2), 0, draw, c3(0)], [seed, TAG_XY])
             C = oracle.philox([(y0 & ~1) * gpr + (xi >> 2), 0, draw, c3(1)], [seed, TAG_XY])
             W, cw = int(R[xi & 3]), int(C[xi & 3])
-            ur = ((W >> 23) << 14) | (((cw >> 16) if (y0 & 1) else cw) & 0x3FFF)
+            ur = (((W >> 24) & 0x7F) << 16) | ((cw >> 16) if (y0 & 1) else (cw & 0xFFFF))
             assert r[y0, x0] == (ur + 1) * 2.0 ** -23 and c[y0, x0] == ((W & 0x7FFFFF) + 1) * 2.0 ** -23
     r, c = oracle.xy_uniforms(1, 2, 512, 256)
     for u in (r, c):
