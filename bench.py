@@ -298,6 +298,17 @@ def bench_other_configs(T: Timer, K: int, peak: float, world: int, rank: int):
     del m
     _free()
     if world > 1:
+        # ---- C2' in slabs: the bit-packed headline lattice, one slab per GPU (halos through NCCL send/recv, not overlapped) ----
+        from cuda_fortran_mc_simulation_spin_b200 import ising3d_gpu_m
+        m = ising3d_gpu_m.ising3d_gpu().init_packed_distributed(NX, NY, NZ * world, KBT, SEED)
+        nall = m.nall()
+        m.update_n(3); m.sync()
+        blocks = T.run(lambda: m.update_n(K))
+        out["C2p_ising3d_bitpacked_slabs"] = entry(
+            f"Ising 3D Metropolis, ONE BIT per site, helical {NX}x{NY}x{NZ * world} in {world} slab(s), kbt={KBT}, all-up start",
+            nall, blocks, K, 3.0 / 8.0, "step, against the bit-packed layout's own 3/8 B per flip", {"sites_per_gpu": nall // world})
+        del m
+        _free()
         return out
 
     # ---- C2': the headline lattice on the bit-packed (multi-spin coded) storage, one bit per site (BASELINE.md C2') ----

@@ -57,10 +57,30 @@ class _IsingBase:
         if self._h:
             self._f("destroy", C.c_int, P)(self._h)
             self._h = C.c_void_p(None)
-        self._pfx = self._pfx + "p"          # b200mc_ising3dp_* / b200mc_ising2dp_*
-        self._packed = True
+        if not getattr(self, "_packed", False):
+            self._pfx = self._pfx + "p"      # b200mc_ising3dp_* / b200mc_ising2dp_*
+            self._packed = True
         f = self._f("create", C.c_int, PP, *([i64] * len(dims)), f64, i32)
         _lib.check(f(C.byref(self._h), *[int(d) for d in dims], float(kbt), int(iseed)))
+        return self
+
+    def _init_packed_distributed(self, dims, kbt, iseed, group=None):
+        """bit-packed storage in slab mode, driven by an initialised torch.distributed job (halos through NCCL send/recv)"""
+        import torch.distributed as dist
+
+        rank, nranks = dist.get_rank(group), dist.get_world_size(group)
+        box = [unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        if self._h:
+            self._f("destroy", C.c_int, P)(self._h)
+            self._h = C.c_void_p(None)
+        if not getattr(self, "_packed", False):
+            self._pfx = self._pfx + "p"
+            self._packed = True
+        f = self._f("create_slab", C.c_int, PP, *([i64] * len(dims)), f64, i32, i32, i32, C.c_char_p)
+        _lib.check(f(C.byref(self._h), *[int(d) for d in dims], float(kbt), int(iseed), int(rank), int(nranks), bytes(box[0])))
+        self._group = group
+        self._rank, self._nranks = int(rank), int(nranks)
         return self
 
     # -- slab decomposition over ranks (one process per GPU; SURVEY 8e) ----

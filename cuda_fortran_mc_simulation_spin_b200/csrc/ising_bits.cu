@@ -33,6 +33,7 @@
 #include "../../include/b200mc.h"
 #include "common.cuh"
 #include "ising_kernels.cuh"   // philox_rk
+#include "ring.cuh"            // dist_* (NCCL resolved at run time)
 
 namespace {
 
@@ -44,7 +45,8 @@ namespace {
 struct BitsPassArgs {
     uint4* own;          // colour being updated, index 0 = position 0
     const uint4* oth;
-    int64_t L;
+    int64_t L;           // vectors this launch covers (the rank's share of every lane in slab mode)
+    int64_t p0;          // global position of local vector 0 (slab mode; 0 otherwise): the RNG counters use global positions
     int64_t off[6];      // neighbour vector offsets: x-, x+, y+, y-, z+, z-
     uint32_t thr[3];     // thresholds of the non-trivial classes: 3D k' = 4, 5, 6; 2D k' = 3, 4
     uint32_t always[3];  // 0 / ~0: the class accepts every proposal (thr = 2^32: beta = 0)
@@ -115,7 +117,7 @@ bits_pass_kernel(const __grid_constant__ BitsPassArgs a)
 #pragma unroll
         for (int j = 0; j < BITS_PLANES; ++j) {
             if (j >= 3 && !(und[0] | und[1] | und[2] | und[3])) break;
-            const uint4 R = philox_rk<TAG_ISNB>(mk_ctr((uint64_t)p, a.draw, a.colour, (uint32_t)j), a.rk0);
+            const uint4 R = philox_rk<TAG_ISNB>(mk_ctr((uint64_t)(a.p0 + p), a.draw, a.colour, (uint32_t)j), a.rk0);
             const uint32_t r[4] = {R.x, R.y, R.z, R.w};
             const uint32_t P0 = 0u - ((a.thr[0] >> (31 - j)) & 1u), P1 = 0u - ((a.thr[1] >> (31 - j)) & 1u),
                            P2 = 0u - ((a.thr[2] >> (31 - j)) & 1u);
@@ -139,7 +141,7 @@ bits_pass_kernel(const __grid_constant__ BitsPassArgs a)
             const int b = __ffs(m) - 1;
             const uint32_t bit = 1u << b;
             const int lane = 32 * w + b;
-            const uint4 R = philox_rk<TAG_ISNB>(mk_ctr((uint64_t)p, a.draw, a.colour, (uint32_t)(32 + (lane >> 2))), a.rk0);
+            const uint4 R = philox_rk<TAG_ISNB>(mk_ctr((uint64_t)(a.p0 + p), a.draw, a.colour, (uint32_t)(32 + (lane >> 2))), a.rk0);
             const uint32_t S = ((lane & 3) == 0 ? R.x : (lane & 3) == 1 ? R.y : (lane & 3) == 2 ? R.z : R.w) & BITS_LOW_MASK;
             const uint32_t cls = NNB == 6 ? ((s1 & bit) ? 2u : ((s0 & bit) ? 1u : 0u)) : ((s0 & bit) ? 1u : 0u);
             const uint32_t t = (cls == 0 ? a.thr[0] : cls == 1 ? a.thr[1] : a.thr[2]) & BITS_LOW_MASK;
@@ -192,6 +194,25 @@ bits_halo_kernel(uint4* vec, int64_t L, int64_t H)
     }
 }
 
+// slab mode: the halo blocks arrive from the neighbour ranks unrotated; the two ranks at the ends of the fold rotate what
+// they received by one bit-lane (dir = +1: lane j <- lane j-1, lane 0 <- lane 127; dir = -1: the other way)
+__global__ void __launch_bounds__(256)
+bits_rotate_kernel(uint4* v, int64_t n, int dir)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 s = v[i];
+    uint4 o;
+    if (dir > 0) {
+        o.x = __funnelshift_l(s.w, s.x, 1); o.y = __funnelshift_l(s.x, s.y, 1);
+        o.z = __funnelshift_l(s.y, s.z, 1); o.w = __funnelshift_l(s.z, s.w, 1);
+    } else {
+        o.x = __funnelshift_r(s.x, s.y, 1); o.y = __funnelshift_r(s.y, s.z, 1);
+        o.z = __funnelshift_r(s.z, s.w, 1); o.w = __funnelshift_r(s.w, s.x, 1);
+    }
+    v[i] = o;
+}
+
 // E and M: one pass over the colour-1 vectors.  Every bond has exactly one colour-1 end, so the number of unequal bonds is
 // X = nnb Nc - sum over the colour-1 sites of k'; sum s = popcounts of both colours.
 template <int NNB>
@@ -222,17 +243,17 @@ bits_measure_kernel(const __grid_constant__ BitsPassArgs a, const uint4* __restr
 }
 
 __global__ void __launch_bounds__(256)
-bits_random_kernel(uint4* own, int64_t L, uint32_t seed, uint64_t draw, uint32_t colour)
+bits_random_kernel(uint4* own, int64_t L, int64_t p0, uint32_t seed, uint64_t draw, uint32_t colour)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= L) return;
-    const uint4 R = philox4x32_10(mk_ctr((uint64_t)p, draw, colour, 0u), make_uint2(seed, TAG_INIB));
+    const uint4 R = philox4x32_10(mk_ctr((uint64_t)(p0 + p), draw, colour, 0u), make_uint2(seed, TAG_INIB));
     own[p] = make_uint4(~R.x, ~R.y, ~R.z, ~R.w);   // spin = 1 iff u < 1/2 iff the bit is 0
 }
 
 // spins() in the reference layout spins(1-P : N+P), halo cells included: int32 0/1 (3D) or -1/+1 (2D, pm1)
 __global__ void __launch_bounds__(256)
-bits_export_kernel(const uint4* c0, const uint4* c1, int64_t N, int64_t L, int64_t P, int pm1, int32_t* out)
+bits_export_kernel(const uint4* c0, const uint4* c1, int64_t N, int64_t L, int64_t P, int pm1, int64_t p0, int64_t Lloc, int32_t* out)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N + 2 * P) return;
@@ -240,18 +261,19 @@ bits_export_kernel(const uint4* c0, const uint4* c1, int64_t N, int64_t L, int64
     if (i < 0) i += N;
     if (i >= N) i -= N;
     const int64_t k = i >> 1, lane = k / L, pos = k - lane * L;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(((i & 1) ? c1 : c0) + pos);
+    if (pos < p0 || pos >= p0 + Lloc) { out[idx] = INT32_MIN; return; }   // owned by another rank (the host takes the maximum over the ranks)
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(((i & 1) ? c1 : c0) + (pos - p0));
     const int32_t b = (int32_t)((w[lane >> 5] >> (lane & 31)) & 1u);
     out[idx] = pm1 ? 2 * b - 1 : b;
 }
 // inverse: one thread builds one 32-bit word (32 sites, L apart in k)
 __global__ void __launch_bounds__(256)
-bits_import_kernel(uint4* c0, uint4* c1, int64_t L, int64_t P, int pm1, const int32_t* in)
+bits_import_kernel(uint4* c0, uint4* c1, int64_t L, int64_t P, int pm1, int64_t p0, int64_t Lloc, const int32_t* in)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 8 * L) return;
-    const int colour = (int)(t / (4 * L));
-    const int64_t r = t - (int64_t)colour * 4 * L, pos = r >> 2;
+    if (t >= 8 * Lloc) return;
+    const int colour = (int)(t / (4 * Lloc));
+    const int64_t r = t - (int64_t)colour * 4 * Lloc, lpos = r >> 2, pos = p0 + lpos;
     const int w = (int)(r & 3);
     uint32_t word = 0;
     for (int b = 0; b < 32; ++b) {
@@ -260,12 +282,15 @@ bits_import_kernel(uint4* c0, uint4* c1, int64_t L, int64_t P, int pm1, const in
         const int32_t bit = pm1 ? (v + 1) >> 1 : v;
         word |= (uint32_t)(bit & 1) << b;
     }
-    reinterpret_cast<uint32_t*>((colour ? c1 : c0) + pos)[w] = word;
+    reinterpret_cast<uint32_t*>((colour ? c1 : c0) + lpos)[w] = word;
 }
 
 struct Bits {
     int ndim, nnb;
     int64_t nx, ny, nz, N, Nc, L, H, P;
+    int64_t p0, Lloc;    // slab mode: this rank owns positions [p0, p0 + Lloc) of every bit-lane (single GPU: 0, L)
+    int rank, nranks;
+    void* comm;          // ncclComm_t when nranks > 1
     int64_t off[2][6];
     uint4* vec[2];       // [colour]: L + 2H vectors, position p at index p + H
     int32_t* stage;
@@ -331,7 +356,7 @@ int build_tables(Bits* m)
 void fill_args(Bits* m, int colour, BitsPassArgs* a)
 {
     a->own = m->vec[colour] + m->H; a->oth = m->vec[colour ^ 1] + m->H;
-    a->L = m->L;
+    a->L = m->Lloc; a->p0 = m->p0;
     for (int t = 0; t < 6; ++t) a->off[t] = m->off[colour][t];
     const int first = m->nnb / 2 + 1;                          // first non-trivial class: k' = 4 (3D) / 3 (2D)
     for (int c = 0; c < 3; ++c) {
@@ -347,8 +372,22 @@ void fill_args(Bits* m, int colour, BitsPassArgs* a)
 
 int halo(Bits* m, int colour)
 {
-    COUNT_LAUNCH();
-    bits_halo_kernel<<<(unsigned)((2 * m->H + 255) / 256), 256, 0, m->stream>>>(m->vec[colour], m->L, m->H);
+    if (m->nranks == 1) {
+        COUNT_LAUNCH();
+        bits_halo_kernel<<<(unsigned)((2 * m->H + 255) / 256), 256, 0, m->stream>>>(m->vec[colour], m->L, m->H);
+        CK(cudaGetLastError());
+        return B200MC_OK;
+    }
+    // slab mode: my first H owned vectors become the HIGH halo of rank-1, my last H owned vectors the LOW halo of rank+1
+    // (ncclSend/Recv over NVLink, one group per colour pass); crossing the end of the fold moves a site to the next bit-lane,
+    // so rank 0 rotates its low halo and rank P-1 its high halo after the exchange
+    uint4* v = m->vec[colour];
+    const size_t bytes = (size_t)m->H * sizeof(uint4);
+    int rc = dist_exchange_ring(m->comm, m->rank, m->nranks, v + m->H, v + m->Lloc, v, v + m->H + m->Lloc, bytes, m->stream);
+    if (rc) return rc;
+    const unsigned nb = (unsigned)((m->H + 255) / 256);
+    if (m->rank == 0) { COUNT_LAUNCH(); bits_rotate_kernel<<<nb, 256, 0, m->stream>>>(v, m->H, +1); }
+    if (m->rank == m->nranks - 1) { COUNT_LAUNCH(); bits_rotate_kernel<<<nb, 256, 0, m->stream>>>(v + m->H + m->Lloc, m->H, -1); }
     CK(cudaGetLastError());
     return B200MC_OK;
 }
@@ -399,6 +438,7 @@ int measure(Bits* m)
     m->want_fused = m->swept_since_measure;   // measured after an update: the next sweeps accumulate the sums themselves
     m->swept_since_measure = false;
     m->fused_pending = false;
+    if (m->nranks > 1) { int rc = dist_allreduce_u64(m->comm, m->d_acc, 2, m->stream); if (rc) return rc; }
     unsigned long long host[2];
     CK(cudaMemcpyAsync(host, m->d_acc, sizeof(host), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
@@ -412,6 +452,7 @@ int measure(Bits* m)
 void destroy(Bits* m)
 {
     cudaStreamSynchronize(m->stream);
+    if (m->comm) dist_comm_destroy(m->comm);
     cudaFree(m->vec[0]); cudaFree(m->vec[1]); cudaFree(m->stage); cudaFree(m->d_acc);
     for (cudaEvent_t e : m->evs) cudaEventDestroy(e);
     delete m;
@@ -420,14 +461,16 @@ void destroy(Bits* m)
 int fill(Bits* m, int value)
 {
     m->obs_valid = false; m->fused_pending = false;
-    const size_t bytes = (size_t)(m->L + 2 * m->H) * sizeof(uint4);
+    const size_t bytes = (size_t)(m->Lloc + 2 * m->H) * sizeof(uint4);
     CK(cudaMemsetAsync(m->vec[0], value ? 0xFF : 0x00, bytes, m->stream));
     CK(cudaMemsetAsync(m->vec[1], value ? 0xFF : 0x00, bytes, m->stream));
     return B200MC_OK;
 }
 
-int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed)
+int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed, int rank = 0, int nranks = 1, const char* nccl_id = nullptr)
 {
+    if (nranks < 1 || rank < 0 || rank >= nranks) ARG_FAIL("bad rank %d / %d", rank, nranks);
+    if (nranks > 1 && !nccl_id) ARG_FAIL("slab mode needs the NCCL unique id of the job (b200mc_dist_unique_id on rank 0, broadcast by the caller)");
     if (!out) ARG_FAIL("null handle pointer");
     *out = nullptr;
     if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0");
@@ -455,8 +498,13 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "bit-packed Ising: fold length %lld shorter than the halo %lld (lattice too thin along the last axis)", (long long)L, (long long)H);
         return B200MC_ERR_UNSUPPORTED;
     }
+    if (L % nranks || L / nranks < H) {
+        snprintf(g_b200mc_err, sizeof(g_b200mc_err), "bit-packed Ising slabs: the fold (%lld vectors) must split evenly over %d ranks into shares not shorter than the halo (%lld)", (long long)L, nranks, (long long)H);
+        return B200MC_ERR_UNSUPPORTED;
+    }
     Bits* m = new (std::nothrow) Bits();
     if (!m) ARG_FAIL("out of host memory");
+    m->rank = rank; m->nranks = nranks; m->comm = nullptr; m->Lloc = L / nranks; m->p0 = (int64_t)rank * (L / nranks);
     m->ndim = ndim; m->nnb = ndim == 3 ? 6 : 4; m->nx = nx; m->ny = ny; m->nz = ndim == 3 ? nz : 0;
     m->N = N; m->Nc = Nc; m->L = L; m->H = H; m->P = ndim == 3 ? nx * ny : nx;
     for (int c = 0; c < 2; ++c) {
@@ -466,7 +514,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     m->vec[0] = m->vec[1] = nullptr; m->stage = nullptr; m->d_acc = nullptr;
     m->stream = 0; m->beta = 1 / kbt; m->seed = (uint32_t)iseed; m->draw = 0; m->obs_valid = false; m->timing = false; m->ev_used = 0;
     m->want_fused = false; m->fused_pending = false; m->swept_since_measure = false;
-    const size_t bytes = (size_t)(L + 2 * H) * sizeof(uint4);
+    const size_t bytes = (size_t)(m->Lloc + 2 * H) * sizeof(uint4);
     if (cudaMalloc(&m->vec[0], bytes) != cudaSuccess || cudaMalloc(&m->vec[1], bytes) != cudaSuccess ||
         cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long)) != cudaSuccess) {
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMalloc failed (%zu bytes per colour)", bytes);
@@ -477,10 +525,11 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     { const char* t = getenv("B200MC_BITS_MINB"); m->minb = (t && atoi(t) == 4) ? 4 : 3; }
-    const int64_t need = (L + 255) / 256;
+    const int64_t need = (m->Lloc + 255) / 256;
     const int per_sm = ndim == 3 ? m->minb : 4;
     m->grid = (int)(need < (int64_t)sms * per_sm ? need : (int64_t)sms * per_sm);
-    int rc = build_tables(m);
+    int rc = nranks > 1 ? dist_comm_init(&m->comm, rank, nranks, nccl_id) : B200MC_OK;
+    if (!rc) rc = build_tables(m);
     if (!rc) rc = fill(m, 1);      // like the reference's init: all up
     if (rc) { destroy(m); return rc; }
     *out = m;
@@ -492,7 +541,7 @@ int set_random(Bits* m)
     m->obs_valid = false; m->fused_pending = false;
     for (int c = 0; c < 2; ++c) {
         COUNT_LAUNCH();
-        bits_random_kernel<<<(unsigned)((m->L + 255) / 256), 256, 0, m->stream>>>(m->vec[c] + m->H, m->L, m->seed, m->draw, (uint32_t)c);
+        bits_random_kernel<<<(unsigned)((m->Lloc + 255) / 256), 256, 0, m->stream>>>(m->vec[c] + m->H, m->Lloc, m->p0, m->seed, m->draw, (uint32_t)c);
         CK(cudaGetLastError());
         int rc = halo(m, c);
         if (rc) return rc;
@@ -507,7 +556,7 @@ int get_spins(Bits* m, int32_t* out)
     const int64_t n = m->N + 2 * m->P;
     if (!m->stage) CK(cudaMalloc(&m->stage, (size_t)n * sizeof(int32_t)));
     COUNT_LAUNCH();
-    bits_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->vec[0] + m->H, m->vec[1] + m->H, m->N, m->L, m->P, m->ndim == 2, m->stage);
+    bits_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->vec[0] + m->H, m->vec[1] + m->H, m->N, m->L, m->P, m->ndim == 2, m->p0, m->Lloc, m->stage);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, m->stage, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
@@ -528,7 +577,7 @@ int set_spins(Bits* m, const int32_t* in)
     m->obs_valid = false; m->fused_pending = false;
     CK(cudaMemcpyAsync(m->stage, in, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
     COUNT_LAUNCH();
-    bits_import_kernel<<<(unsigned)((8 * m->L + 255) / 256), 256, 0, m->stream>>>(m->vec[0] + m->H, m->vec[1] + m->H, m->L, m->P, m->ndim == 2, m->stage);
+    bits_import_kernel<<<(unsigned)((8 * m->Lloc + 255) / 256), 256, 0, m->stream>>>(m->vec[0] + m->H, m->vec[1] + m->H, m->L, m->P, m->ndim == 2, m->p0, m->Lloc, m->stage);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(m->stream));
     int rc = halo(m, 0);
@@ -564,6 +613,7 @@ extern "C" {
     int64_t PFX##_nall(void* h) { return h ? HB(h)->N : -1; }                                                                     \
     double PFX##_kbt(void* h) { return h ? 1 / HB(h)->beta : 0.0; }                                                               \
     double PFX##_beta(void* h) { return h ? HB(h)->beta : 0.0; }                                                                  \
+    int PFX##_rank_info(void* h, int32_t* rank, int32_t* nranks) { CHECK_B(h, ND); if (rank) *rank = HB(h)->rank; if (nranks) *nranks = HB(h)->nranks; return B200MC_OK; } \
     int PFX##_sync(void* h) { CHECK_B(h, ND); CK(cudaStreamSynchronize(HB(h)->stream)); return B200MC_OK; }                       \
     int PFX##_set_timing(void* h, int32_t on) { CHECK_B(h, ND); HB(h)->timing = on != 0; HB(h)->ev_used = 0; return B200MC_OK; }  \
     int PFX##_get_timing(void* h, int64_t* launches, double* total_ms) { CHECK_B(h, ND); Bits* m = HB(h);                         \
@@ -576,6 +626,14 @@ BITS_ABI(b200mc_ising2dp, 2)
 
 int b200mc_ising3dp_create(void** h, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed) { return create(h, 3, nx, ny, nz, kbt, iseed); }
 int b200mc_ising2dp_create(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed) { return create(h, 2, nx, ny, 0, kbt, iseed); }
+int b200mc_ising3dp_create_slab(void** h, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed, int32_t rank, int32_t nranks, const char* nccl_id)
+{
+    return create(h, 3, nx, ny, nz, kbt, iseed, rank, nranks, nccl_id);
+}
+int b200mc_ising2dp_create_slab(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed, int32_t rank, int32_t nranks, const char* nccl_id)
+{
+    return create(h, 2, nx, ny, 0, kbt, iseed, rank, nranks, nccl_id);
+}
 int64_t b200mc_ising3dp_nz(void* h) { return h ? HB(h)->nz : -1; }
 int b200mc_ising3dp_get_ws(void* h, double out[14])
 {

@@ -30,6 +30,10 @@ class ising3d_gpu(_IsingBase):
         """init on the bit-packed (multi-spin coded) storage: one bit per site, Metropolis, one GPU"""
         return self._init_packed((nx, ny, nz), kbt, iseed)
 
+    def init_packed_distributed(self, nx, ny, nz, kbt, iseed, group=None):
+        """the global lattice on bit-packed storage, one slab per rank of the torch.distributed group"""
+        return self._init_packed_distributed((nx, ny, nz), kbt, iseed, group)
+
     def init_slab(self, nx, ny, nz, kbt, iseed, rank, nranks, nccl_id):
         """the global nx x ny x nz lattice, this process owning slab `rank` of `nranks` (one GPU each)"""
         return self._init_slab((nx, ny, nz), kbt, iseed, rank, nranks, nccl_id)

@@ -168,6 +168,12 @@ int b200mc_ring_slab_geometry(int64_t nx, int64_t ny, int64_t nz, int32_t rank, 
  * fold not shorter than the halo -> B200MC_ERR_UNSUPPORTED otherwise.
  * ------------------------------------------------------------------------ */
 int b200mc_ising3dp_create(void** h, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed);
+/* slab mode (one process per GPU, as b200mc_ising3d_create_slab): every rank owns an equal share of every bit-lane, so an
+ * N-rank run is bit-identical to the 1-GPU run; halos through ncclSend/Recv per colour pass, observables all-reduced */
+int b200mc_ising3dp_create_slab(void** h, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed, int32_t rank, int32_t nranks, const char* nccl_id);
+int b200mc_ising2dp_create_slab(void** h, int64_t nx, int64_t ny, double kbt, int32_t iseed, int32_t rank, int32_t nranks, const char* nccl_id);
+int b200mc_ising3dp_rank_info(void* h, int32_t* rank, int32_t* nranks);
+int b200mc_ising2dp_rank_info(void* h, int32_t* rank, int32_t* nranks);
 int b200mc_ising3dp_destroy(void* h);
 int b200mc_ising3dp_set_stream(void* h, void* cuda_stream);
 int b200mc_ising3dp_skip_curand(void* h, int64_t n_skip);
