@@ -44,6 +44,9 @@ struct Ising {
     int coop_grid;  // resident grid of the cooperative small-lattice sweep kernel (0: not available)
     int slab_nb;    // slab mode: blocks of the one-launch pass that start on the boundary tickets (env B200MC_SLAB_NB; 0 = from the boundary's share of the slab)
     int grid_push;  // resident grid of the fused update + halo-push kernel (its register budget differs)
+    bool self_clean;   // ticket launches clear the other pass's counters / the fused sums themselves and store the sums to pinned host memory
+                       // (env B200MC_SELF_CLEAN=0: memsets + copy, the round-1 form, for A/B)
+    bool acc_zeroed;   // the first pass of this sweep has cleared d_acc for the fused second pass
     bool use_tma;   // single-GPU launches go through the copy-engine staged kernel
     int tma_grid;
     bool alive;
@@ -138,10 +141,11 @@ int build_tables(Ising* m)
 }
 
 template <int NNB>
-int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bool fuse, int fewer_blocks = 0, bool tickets_ready = false)
+int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bool fuse, int fewer_blocks = 0, bool tickets_ready = false,
+                 unsigned long long* acc_reset = nullptr, unsigned long long* host_out = nullptr)
 {
     const RingGeom& g = m->st.g;
-    RingPassArgs a;
+    RingPassArgs a = RingPassArgs();
     a.own = m->st.vec[colour] + vbeg;
     a.oth = m->st.vec[colour ^ 1] + vbeg;
     a.nvec = n;
@@ -162,7 +166,13 @@ int launch_range(Ising* m, int colour, int64_t vbeg, int64_t n, bool ordered, bo
     int grid = (int)(need < (int64_t)m->grid ? need : (int64_t)m->grid);
     if (ordered && !(m->tune & 1) && n > (int64_t)m->grid * 256 * 4 && m->n_multi == 1) {
         a.ticket = m->d_ticket;
-        if (!tickets_ready) CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
+        if (m->self_clean && !tickets_ready && fewer_blocks == 0 && !m->use_tma) {
+            // self-cleaning counters: set `colour` for this pass, set `colour ^ 1` cleared by the kernel (both clean at create)
+            a.ticket = m->d_ticket + colour * TK_NCNT * 64;
+            a.ticket_reset = m->d_ticket + (colour ^ 1) * TK_NCNT * 64;
+            if (fuse && host_out) { a.host_out = host_out; a.done_warps = m->d_ticket + 2 * TK_NCNT * 64; m->h_acc_pending = true; }
+            if (!fuse && acc_reset) { a.acc_reset = acc_reset; m->acc_zeroed = true; }
+        } else if (!tickets_ready) CK(cudaMemsetAsync(m->d_ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), m->stream));
         if (grid - fewer_blocks >= 1) grid -= fewer_blocks;  // slab mode: the other blocks of the resident set run ising_slab_kernel on the same tickets
     }
     COUNT_LAUNCH();
@@ -240,7 +250,7 @@ static void push_args(Ising* m, int colour, bool boundary_only, unsigned int* ti
 template <int NNB>
 int launch_push(Ising* m, int colour, bool fuse, bool boundary_only, cudaStream_t stream, unsigned int* ticket)
 {
-    RingPassArgs a;
+    RingPassArgs a = RingPassArgs();
     push_args(m, colour, boundary_only, ticket, a);
     CK(cudaMemsetAsync(ticket, 0, TK_NCNT * 64 * sizeof(unsigned int), stream));
     COUNT_LAUNCH();
@@ -261,7 +271,7 @@ template <int NNB>
 int launch_slab(Ising* m, int colour, bool fuse, int64_t vbeg, int64_t n)
 {
     const RingGeom& g = m->st.g;
-    RingPassArgs ab, ai;
+    RingPassArgs ab = RingPassArgs(), ai;
     push_args(m, colour, true, m->d_ticket + TK_NCNT * 64, ab);
     ai = ab;
     ai.own = m->st.vec[colour] + vbeg;
@@ -317,19 +327,26 @@ int launch_slab(Ising* m, int colour, bool fuse, int64_t vbeg, int64_t n)
 // Slab mode: the first and last H owned vectors (what the neighbouring ranks need) are updated first,
 // their exchange runs on the comm stream while the interior launch runs on the compute stream.
 template <int NNB>
-int launch_pass(Ising* m, int colour, bool fuse)
+int launch_pass(Ising* m, int colour, bool fuse, bool fuse_next = false)
 {
     const RingGeom& g = m->st.g;
     m->obs_valid = false;
     m->fused_pending = false;
-    if (fuse && m->acc_target == m->d_acc) CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long) * m->n_multi, m->stream));
+    m->h_acc_pending = false;
+    if (colour == 0) m->acc_zeroed = false;
+    if (fuse && m->acc_target == m->d_acc && !m->acc_zeroed) CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long) * m->n_multi, m->stream));
+    m->acc_zeroed = false;
+    // single GPU, one sample, sums in d_acc: the first pass clears them for the fused second pass, which stores the totals in h_acc
+    const bool own_sums = g.nranks == 1 && !m->st.p2p && m->n_multi == 1 && m->acc_target == m->d_acc;
+    unsigned long long* acc_reset = (own_sums && colour == 0 && fuse_next) ? m->d_acc : nullptr;
+    unsigned long long* host_out = (own_sums && fuse) ? m->h_acc : nullptr;
     if (m->timing) {
         while (m->evs.size() < m->ev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); m->evs.push_back(e); }
         CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
     }
     int rc;
     if (g.nranks == 1 && !m->st.p2p) {
-        rc = launch_range<NNB>(m, colour, 0, g.Lloc, true, fuse);
+        rc = launch_range<NNB>(m, colour, 0, g.Lloc, true, fuse, 0, false, acc_reset, host_out);
         if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
         if (rc) return rc;
         return ring_halo(&m->st, colour, m->stream);
@@ -451,7 +468,7 @@ int sweep(Ising* m, bool allow_fuse = true, bool force_fuse = false)
     const bool fuse = force_fuse || (allow_fuse && m->want_fused && m->fuse_ok && !(m->tune & 8));
     if (coop_usable(m)) return coop_sweeps(m, 1, fuse, nullptr);
     for (int colour = 0; colour < 2; ++colour) {
-        rc = m->ndim == 3 ? launch_pass<6>(m, colour, fuse && colour == 1) : launch_pass<4>(m, colour, fuse && colour == 1);
+        rc = m->ndim == 3 ? launch_pass<6>(m, colour, fuse && colour == 1, fuse) : launch_pass<4>(m, colour, fuse && colour == 1, fuse);
         if (rc) return rc;
     }
     m->fused_pending = fuse;
@@ -476,7 +493,7 @@ template <int NNB>
 int launch_pass_randoms(Ising* m, int colour)
 {
     const RingGeom& g = m->st.g;
-    RingPassArgs a;
+    RingPassArgs a = RingPassArgs();
     a.own = m->st.vec[colour];
     a.oth = m->st.vec[colour ^ 1];
     a.nvec = g.Lloc;
@@ -756,7 +773,8 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
     m->st.n_rep = n_multi;
     rc = ring_alloc(&m->st);
     if (rc) { destroy(m); return rc; }
-    if (cudaMalloc(&m->d_ticket, 2 * TK_NCNT * 64 * sizeof(unsigned int)) != cudaSuccess ||
+    if (cudaMalloc(&m->d_ticket, (2 * TK_NCNT * 64 + 64) * sizeof(unsigned int)) != cudaSuccess ||   // two counter sets + the finished-warps counter
+        cudaMemset(m->d_ticket, 0, (2 * TK_NCNT * 64 + 64) * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long) * n_multi) != cudaSuccess ||
         cudaHostAlloc(&m->h_acc, 2 * sizeof(unsigned long long) * n_multi, cudaHostAllocDefault) != cudaSuccess ||
         cudaMalloc(&m->d_off1, 6 * sizeof(int64_t)) != cudaSuccess) {
@@ -789,6 +807,7 @@ int create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt,
         cudaGetLastError();
     }
     { const char* t = getenv("B200MC_SLAB_NB"); m->slab_nb = t ? atoi(t) : 0; }
+    { const char* t = getenv("B200MC_SELF_CLEAN"); m->self_clean = !(t && atoi(t) == 0); m->acc_zeroed = false; }
     m->use_tma = false; m->tma_grid = 0;
     if (nranks == 1 && n_multi == 1 && (m->tune & 128)) {
         // opt in to the maximum dynamic shared memory of the staged kernels and size their grid

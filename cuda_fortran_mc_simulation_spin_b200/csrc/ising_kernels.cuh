@@ -62,6 +62,14 @@ struct RingPassArgs {
     uint32_t colour;
     uint64_t draw;
     unsigned int* ticket;  // work counter for ordered scheduling (nullptr: static round-robin)
+    // Self-cleaning launches (single-GPU ticket passes): the pass of colour c counts on counter set c and block 0 clears
+    // set c ^ 1 (idle: the pass that used it has finished, the one that will has not started) -- no memset between the
+    // passes.  acc_reset: the first pass of a sweep clears the sums the fused second pass will add to.  host_out: the
+    // last warp of the fused pass to finish stores the two sums straight into pinned host memory (done_warps counts).
+    unsigned int* ticket_reset;
+    unsigned long long* acc_reset;
+    unsigned long long* host_out;
+    unsigned int* done_warps;
     int chunk;             // vectors per ticket (multiple of 32)
     // PUSH variant (slab mode: colour pass fused with the halo exchange).  The first nb owned vectors
     // are the HIGH halo of rank-1, the vectors from hi_start on the LOW halo of rank+1: the kernel
@@ -267,6 +275,17 @@ static __device__ __noinline__ uint4 ising_tail_keep(int64_t pg, int64_t Lfold, 
     return make_uint4(keep[0], keep[1], keep[2], keep[3]);
 }
 
+// byte-wise partial sums of ising_core -> the lane's running totals
+__device__ __forceinline__ void ising_fold_sums(uint32_t& bX, uint32_t& bM, uint32_t& accX, uint32_t& accM)
+{
+    // sum of the four byte lanes.  Each lane is < 256 (the callers fold after at most 4 vectors: <= 96 / <= 32 per lane), but the
+    // lanes of bX together can reach 384, so the one-multiply byte sum (total < 256) is only good for bM; bX goes through
+    // 16-bit fields first
+    accX += (((bX & 0x00FF00FFu) + ((bX >> 8) & 0x00FF00FFu)) * 0x00010001u) >> 16;
+    accM += (bM * 0x01010101u) >> 24;
+    bX = 0u; bM = 0u;
+}
+
 // everything after the loads: o = own vector, nb = the NNB neighbour vectors
 template <int NNB, int METHOD, bool PUSH, bool MEASURE>
 __device__ __forceinline__ void ising_core(int v, uint4* po, uint4 o, const uint4 (&nb)[NNB], uint32_t cx, uint32_t cz, uint32_t cw,
@@ -304,10 +323,10 @@ __device__ __forceinline__ void ising_core(int v, uint4* po, uint4 o, const uint
             om.x &= keep.x; om.y &= keep.y; om.z &= keep.z; om.w &= keep.w;
             n0.x &= keep.x; n0.y &= keep.y; n0.z &= keep.z; n0.w &= keep.w;
         }
-        const uint32_t so = ((S.x & (om.x * 255u)) + (S.y & (om.y * 255u))) + ((S.z & (om.z * 255u)) + (S.w & (om.w * 255u)));  // bytes <= 24
-        const uint32_t sm = ((om.x + om.y) + (om.z + om.w)) + ((n0.x + n0.y) + (n0.z + n0.w));                                   // bytes <= 8
-        accX += (so * 0x01010101u) >> 24;   // byte sum (< 256)
-        accM += (sm * 0x01010101u) >> 24;
+        // accX / accM are BYTE-WISE partial sums here (four byte lanes each): a vector adds at most 24 / 8 per byte, so the caller
+        // folds them (ising_fold_sums) at least every 10 vectors -- once per ticket in the unrolled loop instead of once per vector
+        accX += ((S.x & (om.x * 255u)) + (S.y & (om.y * 255u))) + ((S.z & (om.z * 255u)) + (S.w & (om.w * 255u)));
+        accM += ((om.x + om.y) + (om.z + om.w)) + ((n0.x + n0.y) + (n0.z + n0.w));
     }
     if (PUSH && is_b && !(a.nopush & 1)) {  // second copy straight into the neighbour's halo (NVLink store)
         if (v < a.nb) a.peer_lo[v] = rot_lanes(o, a.rot_lo);
@@ -371,6 +390,10 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
     pin32(cntaddr);
     if (lane == 0) tq_cnt[warp] = 0;
     __syncwarp();
+    if (ORDERED && !PUSH && blockIdx.x == 0) {   // self-cleaning launches (see RingPassArgs)
+        if (a.ticket_reset && threadIdx.x < TK_NCNT) a.ticket_reset[threadIdx.x * 64] = 0u;
+        if (!MEASURE && a.acc_reset && threadIdx.x < 2) a.acc_reset[threadIdx.x] = 0ull;
+    }
     if (PUSH) {
         // the halo cells this pass reads were pushed by the neighbours during their previous pass
         if (threadIdx.x == 0) {
@@ -404,6 +427,7 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
     const int tk_base = (gwarp % TK_NCNT) * CH, tk_scale = TK_NCNT;
     const int vlimit = PUSH ? a.q_total * CH : nvec;  // PUSH: tickets count VIRTUAL chunks
     uint32_t accX = 0, accM = 0;  // MEASURE: this lane's sums (< 2^31: at most ~10^5 sites per lane and launch)
+    uint32_t bX = 0, bM = 0;      // byte-wise partial sums of the current ticket (ising_core), folded into accX / accM below
     int corrX = 0, corrM = 0;
     constexpr int DN = MEASURE ? NNB : 0;
     // ticket -> first vector of the chunk (-1: a virtual chunk of the PUSH schedule that maps to nothing)
@@ -460,7 +484,7 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
 #pragma unroll
                 for (int j = 0; j < NNB; ++j) qu[j] = q[j] + 32 * u;
                 ising_vec<NNB, METHOD, false, MEASURE, true, COH>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
-                                                             cntaddr, false, accX, accM, rep);
+                                                             cntaddr, false, bX, bM, rep);
                 if ((u & 1) || CH < 64) {   // (a 32-vector chunk is one vector per lane: look at the queue after it)
                     __syncwarp();
                     if (lds32(cntaddr) > TQ_CAP - 64) {
@@ -469,6 +493,7 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
                     }
                 }
             }
+            if (MEASURE) ising_fold_sums(bX, bM, accX, accM);   // (at most 4 vectors: bytes <= 96 / 32)
         } else {
 #pragma unroll 1
             for (int u = 0; u < CH / 32; ++u) {
@@ -477,7 +502,8 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
 #pragma unroll
                     for (int j = 0; j < NNB; ++j) qu[j] = q[j] + 32 * u;
                     ising_vec<NNB, METHOD, PUSH, MEASURE, false, (PUSH ? 2 : COH)>(v0 + 32 * u, po + 32 * u, qu, cx + 32u * u, cz, cw, a, tab, pol, qaddr,
-                                                                 cntaddr, is_b, accX, accM, rep);
+                                                                 cntaddr, is_b, bX, bM, rep);
+                    if (MEASURE) ising_fold_sums(bX, bM, accX, accM);
                 }
                 __syncwarp();
                 if (lds32(cntaddr) > TQ_CAP - 64) {
@@ -516,6 +542,20 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
         if (lane == 0) {
             if (x) atomicAdd(a.acc + 2 * rep, (unsigned long long)x);
             if (mm) atomicAdd(a.acc + 2 * rep + 1, (unsigned long long)mm);
+            if (ORDERED && !PUSH && !BATCH && a.host_out) {
+                // the last warp of the launch to get here reads the totals back (atomics at L2, ordered by the fences)
+                // and stores them into pinned host memory: update -> calc_magne_sum -> calc_energy_sum needs no copy
+                __threadfence();
+                const unsigned int total = gridDim.x * (blockDim.x >> 5);
+                if (atomicAdd(a.done_warps, 1u) == total - 1u) {
+                    __threadfence();
+                    const unsigned long long t0 = atomicAdd(a.acc, 0ull), t1 = atomicAdd(a.acc + 1, 0ull);
+                    *a.done_warps = 0u;
+                    a.host_out[0] = t0;
+                    a.host_out[1] = t1;
+                    __threadfence_system();
+                }
+            }
         }
     }
 }
@@ -738,7 +778,7 @@ ising_pass_tma_kernel(const __grid_constant__ RingPassArgs a, const __grid_const
     const uint64_t pol = l2_policy_evict_first();
     const uint32_t cx0 = (uint32_t)a.p0, cz = (uint32_t)a.draw;
     const uint32_t cw = (uint32_t)((a.draw >> 32) & 0xFFFFu) | (a.colour << 16);
-    uint32_t accX = 0, accM = 0;
+    uint32_t accX = 0, accM = 0, bX = 0, bM = 0;
     int corrX = 0, corrM = 0;
     constexpr int DN = MEASURE ? NNB : 0;
     for (uint32_t it = 0;; ++it) {
@@ -758,7 +798,8 @@ ising_pass_tma_kernel(const __grid_constant__ RingPassArgs a, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * st);   // this warp's 32 vectors are in registers
             ising_core<NNB, METHOD, false, MEASURE>(v, own + v, o, nb, cx0 + (uint32_t)v, cz, cw, a, tab, pol, qaddr, cntaddr, false,
-                                                    accX, accM);
+                                                    bX, bM);
+            if (MEASURE) ising_fold_sums(bX, bM, accX, accM);
         } else {
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * st);
@@ -767,7 +808,8 @@ ising_pass_tma_kernel(const __grid_constant__ RingPassArgs a, const __grid_const
 #pragma unroll
                 for (int j = 0; j < NNB; ++j) qu[j] = a.oth + (a.H + a.off[j]) + v;
                 ising_vec<NNB, METHOD, false, MEASURE, false>(v, own + v, qu, cx0 + (uint32_t)v, cz, cw, a, tab, pol, qaddr, cntaddr,
-                                                              false, accX, accM);
+                                                              false, bX, bM);
+                if (MEASURE) ising_fold_sums(bX, bM, accX, accM);
             }
         }
         __syncwarp();
