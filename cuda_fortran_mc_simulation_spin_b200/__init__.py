@@ -13,5 +13,6 @@ procedure names) over the C ABI of ``libb200mc.so``:
     clock_table_gpu_m, clock_simple_gpu_m  src/clock/clock_table_gpu_m.f90, clock_simple_gpu_m.f90
     xy2d_periodic_gpu_m.xy2d_gpu     src/xy2d_periodic_gpu_m.f90
     xy2d_gpu_m.xy2d_gpu              src/xy2d_gpu_m.f90 (helical boundary)
+    ising_periodic_gpu_m.ising_periodic_gpu   (no reference module: Ising 2D / 3D on the torus, L = 1024^3)
 """
 from ._lib import B200MCError, SO_PATH, build  # noqa: F401

@@ -1,0 +1,108 @@
+"""Ising 2D / 3D with true periodic boundaries (torus) -- host mirror over ``b200mc_ising_torus_*``.
+
+Not a reference module: ``type(ising3d_gpu)`` / ``type(ising2d_gpu)`` are helical and valid for odd ``nx`` only
+(src/ising3d_gpu_m.f90:60-62,196), so L = 1024^3 -- the size BASELINE.json names -- needs this boundary
+condition.  Same procedure names, update rule, tables, value conventions (3D 0 / 1, 2D -1 / +1) and observables as
+those types; host arrays are ``s[z][y][x]`` without halo cells.  ``nx % 32 == 0``, ``ny`` and ``nz`` even.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import P, PP, f64, i32, i64
+
+METROPOLIS, HEATBATH = 0, 1
+ising_periodic_gpu_stat = 0
+
+
+class ising_periodic_gpu:
+    _pfx = "b200mc_ising_torus"
+
+    def __init__(self):
+        self._h = C.c_void_p(None)
+        self._dims = None
+
+    def _f(self, name, restype, *argtypes):
+        return _lib.fn(f"{self._pfx}_{name}", restype, *argtypes)
+
+    def _call(self, name, *args, argtypes=()):
+        _lib.check(self._f(name, C.c_int, P, *argtypes)(self._h, *args))
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._f("destroy", C.c_int, P)(self._h)
+                self._h = C.c_void_p(None)
+        except Exception:
+            pass
+
+    def init(self, nx, ny, nz, kbt, iseed):
+        """init(nx, ny, nz, kbt, iseed) as init_ising3d_gpu (src/ising3d_gpu_m.f90:50-71); nz = 0 -> the 2D model"""
+        if self._h:
+            self._f("destroy", C.c_int, P)(self._h)
+            self._h = C.c_void_p(None)
+        ndim = 3 if int(nz) > 0 else 2
+        f = _lib.fn("b200mc_ising_torus_create", C.c_int, PP, i32, i64, i64, i64, f64, i32)
+        _lib.check(f(C.byref(self._h), ndim, int(nx), int(ny), int(nz), float(kbt), int(iseed)))
+        self._dims = (int(nz), int(ny), int(nx)) if ndim == 3 else (int(ny), int(nx))
+        return self
+
+    def set_allup_spin(self): self._call("set_allup_spin")
+    def set_random_spin(self): self._call("set_random_spin")
+    def set_kbt(self, kbt): self._call("set_kbt", float(kbt), argtypes=(f64,))
+    def set_beta(self, beta): self._call("set_beta", float(beta), argtypes=(f64,))
+    def set_method(self, method): self._call("set_method", int(method), argtypes=(i32,))
+    def skip_curand(self, n_skip): self._call("skip_curand", int(n_skip), argtypes=(i64,))
+    def update(self): self._call("update")
+    def update_n(self, n_sweeps): self._call("update_n", int(n_sweeps), argtypes=(i32,))
+
+    def update_with_randoms(self, randoms):
+        r = np.ascontiguousarray(randoms, dtype=np.float64).ravel()
+        assert r.size == self.nall()
+        self._call("update_with_randoms", r.ctypes.data_as(P), argtypes=(P,))
+
+    def nall(self): return int(self._f("nall", i64, P)(self._h))
+    def beta(self): return float(self._f("beta", f64, P)(self._h))
+    def kbt(self): return 1.0 / self.beta()
+
+    def table(self):
+        """w[s, S]: acceptance probability of a site with spin s (0 / 1) and S up neighbours, as the reference builds it"""
+        out = np.empty(16, dtype=np.float64)
+        self._call("get_table", out.ctypes.data_as(P), argtypes=(P,))
+        return out.reshape(2, 8)
+
+    def spins(self):
+        out = np.empty(self.nall(), dtype=np.int32)
+        self._call("get_spins", out.ctypes.data_as(P), argtypes=(P,))
+        return out
+
+    def set_spins(self, spins):
+        s = np.ascontiguousarray(spins, dtype=np.int32).ravel()
+        assert s.size == self.nall()
+        self._call("set_spins", s.ctypes.data_as(P), argtypes=(P,))
+
+    def measure(self):
+        e, m = C.c_int64(0), C.c_int64(0)
+        self._call("measure", C.byref(e), C.byref(m), argtypes=(P, P))
+        return int(e.value), int(m.value)
+
+    def calc_energy_sum(self):
+        e = C.c_int64(0)
+        self._call("calc_energy_sum", C.byref(e), argtypes=(P,))
+        return int(e.value)
+
+    def calc_magne_sum(self):
+        m = C.c_int64(0)
+        self._call("calc_magne_sum", C.byref(m), argtypes=(P,))
+        return int(m.value)
+
+    def sync(self): self._call("sync")
+    def set_timing(self, on=True): self._call("set_timing", int(bool(on)), argtypes=(i32,))
+
+    def get_timing(self):
+        n, ms = C.c_int64(0), C.c_double(0.0)
+        self._call("get_timing", C.byref(n), C.byref(ms), argtypes=(P, P))
+        return int(n.value), float(ms.value)

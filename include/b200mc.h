@@ -223,6 +223,44 @@ int b200mc_ising2dp_set_timing(void* h, int32_t on);
 int b200mc_ising2dp_get_timing(void* h, int64_t* launches, double* total_ms);
 
 /* ------------------------------------------------------------------------
+ * Ising 2D / 3D with TRUE PERIODIC boundaries (torus), int8, Metropolis / heat-bath, one GPU.
+ * No reference module: the reference's Ising types are helical and valid for odd nx only
+ * (src/ising3d_gpu_m.f90:60-62,196, src/ising2d_gpu_m.f90:56-58), so L = 1024^3 -- the size
+ * BASELINE.json's north_star and BASELINE.md C2 / C1 / C5 name ("1024^3 periodic", "1024^2 periodic",
+ * "65536^2 periodic") -- needs this boundary condition.  The procedures are those of type(ising3d_gpu) /
+ * type(ising2d_gpu) (file:line as for b200mc_ising3d_* / b200mc_ising2d_* above), with the reference's update
+ * rule, tables, value conventions (3D 0 / 1, 2D -1 / +1) and observables; colour = (x + y + z) & 1, colour 0
+ * first.  ndim = 2 | 3 (nz ignored in 2D); nx % 32 == 0, ny and nz even.  Host arrays: s[x + nx (y + ny z)],
+ * no halo cells.  CPU restatement: oracle/oracle.c orc_isingp_*.
+ * ------------------------------------------------------------------------ */
+int b200mc_ising_torus_create(void** h, int32_t ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed);
+int b200mc_ising_torus_destroy(void* h);
+int b200mc_ising_torus_set_stream(void* h, void* cuda_stream);
+int b200mc_ising_torus_skip_curand(void* h, int64_t n_skip);     /* src/ising3d_gpu_m.f90:72-77 */
+int b200mc_ising_torus_set_allup_spin(void* h);                  /* :79-82 */
+int b200mc_ising_torus_set_random_spin(void* h);                 /* :84-100 */
+int b200mc_ising_torus_set_kbt(void* h, double kbt);             /* :124-128 */
+int b200mc_ising_torus_set_beta(void* h, double beta);           /* :130-135 */
+int b200mc_ising_torus_set_method(void* h, int32_t method);      /* B200MC_METROPOLIS (default) | B200MC_HEATBATH */
+int b200mc_ising_torus_update(void* h);                          /* one MCS, :174-206 */
+int b200mc_ising_torus_update_n(void* h, int32_t n_sweeps);
+/* one MCS with the uniforms of a caller array indexed like the spins (the reference's randoms(idx)), real64 compare */
+int b200mc_ising_torus_update_with_randoms(void* h, const double* randoms);
+int b200mc_ising_torus_calc_energy_sum(void* h, int64_t* e);     /* :239-257 / src/ising2d_gpu_m.f90:198-213 */
+int b200mc_ising_torus_calc_magne_sum(void* h, int64_t* m);      /* :259-276 / src/ising2d_gpu_m.f90:215-228 */
+int b200mc_ising_torus_measure(void* h, int64_t* e, int64_t* m);
+int b200mc_ising_torus_get_spins(void* h, int32_t* out);         /* nx ny nz values */
+int b200mc_ising_torus_set_spins(void* h, const int32_t* in);
+int64_t b200mc_ising_torus_nall(void* h);
+double b200mc_ising_torus_beta(void* h);
+/* the acceptance table w[s * 8 + S] (s = 0 / 1 the site's spin, S = number of up neighbours) as the reference builds it */
+int b200mc_ising_torus_get_table(void* h, double out[16]);
+int b200mc_ising_torus_set_timing(void* h, int32_t on);
+int b200mc_ising_torus_get_timing(void* h, int64_t* launches, double* total_ms);
+int b200mc_ising_torus_sync(void* h);
+
+
+/* ------------------------------------------------------------------------
  * Ising 2D -- type(ising2d_gpu), src/ising2d_gpu_m.f90:12-42
  * ------------------------------------------------------------------------ */
 /* init, :44-61.  nx odd, ny even REQUIRED. */

@@ -331,6 +331,78 @@ ORC_API void orc_ising3d_update_heatbath(int64_t nx, int64_t ny, int64_t nz, int
 }
 
 /* ==========================================================================
+ * Periodic Ising 2D / 3D (torus).  NOT IN THE REFERENCE, whose modules are helical only and valid for odd nx
+ * (SURVEY.md Q1): this is the "1024^3 periodic" / "1024^2 periodic" / "65536^2 periodic" input of BASELINE.md
+ * section 2 and SURVEY.md 8(d), defined with the reference's own update rule, tables, value conventions and
+ * observables (src/ising3d_gpu_m.f90:189-206,239-276; src/ising2d_gpu_m.f90:148-162,191-228) and true periodic
+ * neighbours; colour = (x + y + z) & 1, colour 0 first (the reference's odd 1-based indices).  All extents even.
+ * storage: s[x + nx (y + ny z)], no halo; 3D values 0/1, 2D values -1/+1.  PARITY UNPINNED (no reference symbol).
+ * method: 0 = Metropolis (w = ws(0:6,0:1) in 3D, exparr(-8:8) in 2D), 1 = heat-bath (w = p_up(0:z)).
+ * ========================================================================== */
+ORC_API void orc_isingp_update(int ndim, int64_t nx, int64_t ny, int64_t nz, int32_t *s, const double *randoms,
+                               const double *w, int method)
+{
+    if (ndim == 2) nz = 1;
+    const int64_t nxy = nx * ny;
+    for (int colour = 0; colour < 2; ++colour) {
+#pragma omp parallel for schedule(static)
+        for (int64_t zy = 0; zy < nz * ny; ++zy) {
+            const int64_t z = zy / ny, y = zy % ny;
+            const int64_t yp = (y + 1) % ny, ym = (y + ny - 1) % ny, zp = (z + 1) % nz, zm = (z + nz - 1) % nz;
+            for (int64_t x = (y + z + colour) & 1; x < nx; x += 2) {
+                const int64_t xp = (x + 1) % nx, xm = (x + nx - 1) % nx;
+                const int64_t i = x + nx * y + nxy * z;
+                int32_t sum = s[xm + nx * y + nxy * z] + s[xp + nx * y + nxy * z] + s[x + nx * ym + nxy * z] +
+                              s[x + nx * yp + nxy * z];
+                if (ndim == 3) {
+                    sum += s[x + nx * y + nxy * zm] + s[x + nx * y + nxy * zp];
+                    if (method == 0) {
+                        if (randoms[i] > w[sum + 7 * s[i]]) continue;   /* src/ising3d_gpu_m.f90:203-204 */
+                        s[i] = 1 - s[i];
+                    } else {
+                        s[i] = (randoms[i] <= w[sum]) ? 1 : 0;
+                    }
+                } else {
+                    if (method == 0) {
+                        const int32_t de = 2 * s[i] * sum;                  /* src/ising2d_gpu_m.f90:195 */
+                        if (randoms[i] <= w[de + 8]) s[i] = -s[i];          /* :159-160 */
+                    } else {
+                        s[i] = (randoms[i] <= w[(sum + 4) / 2]) ? 1 : -1;
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* E as the reference sums it: 3D  sum_i energy_table(s(+x) + s(+y) + s(+z), s(i)), 2D  -sum_i s(i) (s(+x) + s(+y));
+ * M = 2 sum(s) - nall in 3D, sum(s) in 2D */
+ORC_API void orc_isingp_energy_magne(int ndim, int64_t nx, int64_t ny, int64_t nz, const int32_t *s, int64_t *e_out,
+                                     int64_t *m_out)
+{
+    if (ndim == 2) nz = 1;
+    const int64_t nxy = nx * ny, nall = nxy * nz;
+    int64_t et[8];
+    double ws[14];
+    orc_ising3d_tables(1.0, et, ws);
+    int64_t e = 0, m = 0;
+#pragma omp parallel for reduction(+ : e, m) schedule(static)
+    for (int64_t i = 0; i < nall; ++i) {
+        const int64_t x = i % nx, y = (i / nx) % ny, z = i / nxy;
+        const int64_t ixp = (x + 1) % nx + nx * y + nxy * z, iyp = x + nx * ((y + 1) % ny) + nxy * z;
+        if (ndim == 3) {
+            const int64_t izp = x + nx * y + nxy * ((z + 1) % nz);
+            e += et[(s[ixp] + s[iyp] + s[izp]) + 4 * s[i]];
+        } else {
+            e -= (int64_t)s[i] * (s[ixp] + s[iyp]);
+        }
+        m += s[i];
+    }
+    *e_out = e;
+    *m_out = ndim == 3 ? 2 * m - nall : m;
+}
+
+/* ==========================================================================
  * q-state clock, helical  (src/clock_gpu_m.f90, src/clock_gpu_multi_m.f90)
  * storage: spins(1-nx : nall+nx) int32 in 0..q-1  (one such array per replica)
  * ========================================================================== */

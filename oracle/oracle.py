@@ -105,6 +105,10 @@ def _declare(L):
     d("orc_xy_correlation", f64, i64, i64, P)
     d("orc_xy_rotate", None, i64, i64, P, f64)
     d("orc_xy_metropolis_by_field", None, i64, i64, P, P, P, f64, f64)
+    d("orc_isingp_update", None, C.c_int, i64, i64, i64, P, P, P, C.c_int)
+    d("orc_isingp_energy_magne", None, C.c_int, i64, i64, i64, P, P, P)
+    d("orc_isingp_uniforms", None, u32, u64, i64, i64, i64, P)
+    d("orc_isingp_init_uniforms", None, u32, u64, i64, i64, i64, P)
     d("orc_ring_fold_len", i64, i64)
     d("orc_ising_uniforms", None, u32, u64, i64, P)
     d("orc_ising_uniforms_fast", None, u32, u64, i64, P)
@@ -315,6 +319,85 @@ class ising2d_gpu:
     def spins(self): return self.s.copy()
     def calc_energy_sum(self): return int(lib().orc_ising2d_energy(self.nx_, self.ny_, _p(self.s)))
     def calc_magne_sum(self): return int(lib().orc_ising2d_magne(self.nx_, self.ny_, _p(self.s)))
+
+
+# --------------------------------------------------------------------------
+# Periodic Ising 2D / 3D (torus): not in the reference -- the "1024^3 periodic" input of BASELINE.md / SURVEY 8(d),
+# with the reference's update rule, tables, value conventions (3D 0/1, 2D -1/+1) and observables
+# --------------------------------------------------------------------------
+def isingp_uniforms(seed, draw, nx, ny, nz, init=False):
+    out = np.empty(nx * ny * max(nz, 1), dtype=np.float64)
+    (lib().orc_isingp_init_uniforms if init else lib().orc_isingp_uniforms)(seed & 0xFFFFFFFF, draw, nx, ny, max(nz, 1), _p(out))
+    return out
+
+
+class ising_periodic_gpu:
+    """CPU restatement of the periodic Ising module (cuda_fortran_mc_simulation_spin_b200/ising_periodic_gpu_m.py);
+    nz = 0 -> 2D.  Spins: array [nz][ny][nx] (3D) / [ny][nx] (2D), no halo."""
+
+    def init(self, nx, ny, nz, kbt, iseed):
+        self.nx_, self.ny_, self.nz_ = int(nx), int(ny), int(nz)
+        self.ndim_ = 3 if self.nz_ > 0 else 2
+        self.nall_ = self.nx_ * self.ny_ * max(self.nz_, 1)
+        self.seed_ = int(iseed)
+        self.draw_ = 0
+        self.s = np.empty(self.nall_, dtype=np.int32)
+        self.set_allup_spin()
+        self.set_kbt(kbt)
+        return self
+
+    def skip_draws(self, n):
+        self.draw_ += int(n)
+
+    def set_allup_spin(self):
+        self.s[:] = 1
+
+    def set_random_spin(self, randoms=None):
+        if randoms is None:
+            randoms = isingp_uniforms(self.seed_, self.draw_, self.nx_, self.ny_, self.nz_, init=True)
+            self.draw_ += 1
+        up = np.asarray(randoms) < 0.5                      # src/ising3d_gpu_m.f90:99, src/ising2d_gpu_m.f90:83
+        self.s[:] = np.where(up, 1, 0 if self.ndim_ == 3 else -1)
+
+    def set_kbt(self, kbt):
+        self.set_beta(1 / kbt)
+
+    def set_beta(self, beta):
+        self.beta_ = float(beta)
+        if self.ndim_ == 3:
+            et = np.empty(8, dtype=np.int64)
+            self.w = np.empty(14, dtype=np.float64)
+            lib().orc_ising3d_tables(self.beta_, _p(et), _p(self.w))
+        else:
+            self.w = np.empty(17, dtype=np.float64)
+            lib().orc_ising2d_exparr(self.beta_, _p(self.w))
+        self.pup = np.empty(7, dtype=np.float64)
+        lib().orc_heatbath_table(self.beta_, 6 if self.ndim_ == 3 else 4, _p(self.pup))
+
+    def _next(self, randoms):
+        if randoms is None:
+            randoms = isingp_uniforms(self.seed_, self.draw_, self.nx_, self.ny_, self.nz_)
+            self.draw_ += 1
+        return np.ascontiguousarray(randoms, dtype=np.float64)
+
+    def update(self, randoms=None):
+        r = self._next(randoms)
+        lib().orc_isingp_update(self.ndim_, self.nx_, self.ny_, max(self.nz_, 1), _p(self.s), _p(r), _p(self.w), 0)
+
+    def update_heatbath(self, randoms=None):
+        r = self._next(randoms)
+        lib().orc_isingp_update(self.ndim_, self.nx_, self.ny_, max(self.nz_, 1), _p(self.s), _p(r), _p(self.pup), 1)
+
+    def nall(self): return self.nall_
+    def spins(self): return self.s.copy()
+
+    def measure(self):
+        e, m = C.c_int64(0), C.c_int64(0)
+        lib().orc_isingp_energy_magne(self.ndim_, self.nx_, self.ny_, max(self.nz_, 1), _p(self.s), C.byref(e), C.byref(m))
+        return int(e.value), int(m.value)
+
+    def calc_energy_sum(self): return self.measure()[0]
+    def calc_magne_sum(self): return self.measure()[1]
 
 
 # --------------------------------------------------------------------------

@@ -144,6 +144,55 @@ ORC_API void orc_ring_init_uniforms(uint32_t seed, uint64_t draw, int64_t n_site
 }
 
 /* --------------------------------------------------------------------------
+ * Periodic Ising (torus, csrc/ising_periodic.cu): colour = (x + y + z) & 1, the sites of a colour stored
+ * row-major with xi = x >> 1 running fastest, 16 consecutive xi per 128-bit vector:
+ *   k = (z ny + y) (nx / 2) + xi,  vector v = k / 16,  lane = k % 16.
+ * The uniforms are the ring models' with (position, lane) = (v, lane): the same two-stage accept uniform
+ * (TAG_ISING) and the same one-word set_random_spin uniform (TAG_INIT).  out[i], i = x + nx (y + ny z).
+ * -------------------------------------------------------------------------- */
+static inline void torus_site(int64_t i, int64_t nx, int64_t ny, uint32_t *colour, uint64_t *v, int *lane)
+{
+    const int64_t x = i % nx, y = (i / nx) % ny, z = i / (nx * ny);
+    const int64_t k = (z * ny + y) * (nx / 2) + (x >> 1);
+    *colour = (uint32_t)((x + y + z) & 1);
+    *v = (uint64_t)(k >> 4);
+    *lane = (int)(k & 15);
+}
+
+ORC_API void orc_isingp_uniforms(uint32_t seed, uint64_t draw, int64_t nx, int64_t ny, int64_t nz, double *out)
+{
+    const int64_t n = nx * ny * nz;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t colour; uint64_t v; int lane;
+        torus_site(i, nx, ny, &colour, &v, &lane);
+        const int m = BYTEPOS[lane];
+        uint32_t key[2] = {seed, TAG_ISING}, c[4], r[4], r2[4];
+        mk_ctr(c, v, draw, colour, 0);
+        orc_philox4x32_10(c, key, r);
+        const uint32_t b7 = (r[m >> 2] >> (8 * (m & 3))) & 0x7Fu;
+        mk_ctr(c, v, draw, colour, 1u + (uint32_t)(m >> 2));
+        orc_philox4x32_10(c, key, r2);
+        const uint32_t U = (b7 << 25) | (r2[m & 3] & 0x1FFFFFFu);
+        out[i] = ((double)U + 1.0) * 0x1p-32;
+    }
+}
+
+ORC_API void orc_isingp_init_uniforms(uint32_t seed, uint64_t draw, int64_t nx, int64_t ny, int64_t nz, double *out)
+{
+    const int64_t n = nx * ny * nz;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t colour; uint64_t v; int lane;
+        torus_site(i, nx, ny, &colour, &v, &lane);
+        uint32_t key[2] = {seed, TAG_INIT}, c[4], r[4];
+        mk_ctr(c, v, draw, colour, (uint32_t)(lane >> 2));
+        orc_philox4x32_10(c, key, r);
+        out[i] = ((double)r[lane & 3] + 1.0) * 0x1p-32;
+    }
+}
+
+/* --------------------------------------------------------------------------
  * Clock models, contract v3 (cuda_fortran_mc_simulation_spin_b200/csrc/clock_word.cuh): the two 32-bit
  * uniforms (accept, proposal) of the 16 sites of a vector = words w = 0..3 of sites e = 0..3.
  * X[0..11] = the words of the Philox blocks with sub-counters 0, 1, 2; Y[0..11] = sub-counters
