@@ -13,7 +13,7 @@ nall attempted flips per GPU.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--only-headline]
 
 Prints ONE JSON line (rank 0).  Besides the headline keys the line carries
-`configs`: the other BASELINE configurations (C1 Ising 2D small lattice, C3 XY
+`configs`: the other BASELINE configurations (C2 / C5 with true periodic boundaries -- L = 1024^3 itself --, C1 Ising 2D small lattice, C3 XY
 16384^2 Metropolis / over-relaxation, C4 q=6 clock 16384^2 batched + helical,
 C5 Ising 2D 65537 x 65536 per GPU), each device-timed the same way with its own
 roofline fraction.  At N > 1 the sharded workloads run: C2 (headline) and C5.
@@ -341,6 +341,40 @@ def bench_other_configs(T: Timer, K: int, peak: float, world: int, rank: int):
         b2 = T.run(loopp)
         e["e2e"] = {"value": nall * kp / (statistics.median(b2) * 1e6), "unit": UNIT, "ms_per_step": statistics.median(b2) / kp,
                     "note": "update + calc_magne_sum + calc_energy_sum per MCS through the module API (separate measurement kernel)"}
+        out[key] = e
+        del m
+        _free()
+
+    # ---- C2 / C5 on the torus: L = 1024^3 itself and 65536^2 with true periodic boundaries ("1024^3 periodic",
+    #      "65536^2 periodic"; not a reference module -- its helical types need odd nx) ----
+    from cuda_fortran_mc_simulation_spin_b200 import ising_periodic_gpu_m
+    for key, dims, kbt, label, kern in (
+            ("C2_ising3d_periodic_1024x1024x1024", (1024, 1024, 1024), KBT,
+             f"Ising 3D Metropolis, int8, TRUE PERIODIC 1024x1024x1024 (the north star's L = 1024^3), kbt={KBT}, all-up start", "torus_strip_kernel<6, METROPOLIS, 8 rows, R = 32>"),
+            ("C5_ising2d_periodic_65536x65536", (65536, 65536, 0), KBT2,
+             f"Ising 2D Metropolis, int8, TRUE PERIODIC 65536x65536, kbt={KBT2}, all-up start", "torus_strip_kernel<4, METROPOLIS, 8 rows>")):
+        m = ising_periodic_gpu_m.ising_periodic_gpu().init(*dims, kbt, SEED)
+        nall = m.nall()
+        kp = K if dims[2] else max(2, K // 4)
+        m.update_n(3); m.sync()
+        m.set_timing(True)
+        blocks = T.run(lambda: m.update_n(kp))
+        n_pass, pass_ms = m.get_timing()
+        m.set_timing(False)
+        e = entry(label, nall, blocks, kp, BYTES_PER_FLIP, "step (2 colour-pass launches per step, nothing else on the stream: no halo)",
+                  {"roofline_kernel": _kernel_roof(nall / 2, BYTES_PER_FLIP, n_pass, pass_ms, peak, kern)})
+
+        def loopt():
+            s = 0
+            for _ in range(kp):
+                m.update()
+                s += m.calc_magne_sum() + m.calc_energy_sum()
+            return s
+        m.update(); m.measure()
+        b2 = T.run(loopt)
+        e["e2e"] = {"value": nall * kp / (statistics.median(b2) * 1e6), "unit": UNIT, "ms_per_step": statistics.median(b2) / kp,
+                    "note": "update + calc_magne_sum + calc_energy_sum per MCS through the module API (E and M accumulated by the second colour pass, "
+                            "stored to pinned host memory by the kernel)"}
         out[key] = e
         del m
         _free()

@@ -51,6 +51,21 @@ __device__ __forceinline__ uint4 torus_shift(uint4 B, int par, uint32_t edge)
     return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
 }
 
+#ifndef TORUS_ZM_EVICT
+#define TORUS_ZM_EVICT 0
+#endif
+// the z - 1 row is the last use of that row in the pass: optionally marked evict-first in L2
+__device__ __forceinline__ uint4 ld_other_last(const uint4* p, uint64_t pol)
+{
+#if TORUS_ZM_EVICT
+    uint4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+#else
+    return ld_other(p);
+#endif
+}
+
 __device__ __forceinline__ uint32_t ld_word_nc(const uint32_t* p)
 {
     uint32_t r;
@@ -111,7 +126,21 @@ __device__ __forceinline__ void torus_finish_sums(const RingPassArgs& a, uint32_
     }
 }
 
-#define TORUS_MINB(NNB) 3   // 80 registers: the 2D batches (8 loads + the row window) spill at 64
+#ifndef TORUS_MINB
+#define TORUS_MINB(NNB) ((NNB) == 6 ? 3 : 4)   // resident blocks per SM the registers are allocated for (80 / 64)
+#endif
+#ifndef TORUS_NB3
+#define TORUS_NB3 2         // rows per batch in 3D (4 loads each)
+#endif
+#ifndef TORUS_NB2
+#define TORUS_NB2 2         // rows per batch in 2D (2 loads each); measured: 2 rows x 4 blocks 1621, 2 x 3 1564, 4 x 3 1480 flips/ns at 65536^2
+#endif
+#ifndef TORUS_PF
+#define TORUS_PF 3          // L2 prefetch of the next ticket: bit 0 own rows, bit 1 rows of the leading z plane
+#endif
+#ifndef TORUS_ROWS
+#define TORUS_ROWS 8        // rows per ticket when ny allows
+#endif
 
 // ---- strip kernel: R % 32 == 0, ny % ROWS == 0, ROWS even ---------------------------------------------------------
 // The rows of one ticket.  PAR0 = parity of the first row (constant per plane and colour: y0 is even), RC = R when it is
@@ -119,7 +148,7 @@ __device__ __forceinline__ void torus_finish_sums(const RingPassArgs& a, uint32_
 // edge inside a row), else 0.  The first version computed every address from (z, y, col) per row, selected the shift
 // direction at run time and ran 233 instructions per warp-vector against the helical pass's 180: 373 us per pass with
 // L1TEX at 43 % (profiles/r02z_torus_ncu.md) -- the pass time follows the instruction count.
-// Rows are taken in batches of NB (2 in 3D, 4 in 2D: eight loads): ALL loads of a batch are issued before the first SHFL --
+// Rows are taken in batches of NB = 2: ALL loads of a batch are issued before the first SHFL --
 // the shuffle needs its row's data, and with one row's loads behind it each row paid a full memory round trip.  The
 // batch loop is not unrolled (two parity variants of a 2-row body = 700 instructions; fully unrolled over 8 rows the
 // kernel was 2900 instructions, 46 KB, and 20 % slower).
@@ -132,7 +161,7 @@ __device__ __forceinline__ void torus_rows(const TorusArgs& t, const IsingTab& t
     const RingPassArgs& a = t.a;
     const int R = RC ? RC : t.R;
     constexpr int DN = MEASURE ? NNB : 0;
-    constexpr int NB = (NNB == 6 || ROWS < 4) ? 2 : 4;
+    constexpr int NB = ROWS < 4 ? 2 : (NNB == 6 ? TORUS_NB3 : TORUS_NB2);
     static_assert(ROWS % NB == 0 && NB % 2 == 0, "whole batches of an even number of rows");
     uint4 A = ld_other(prow_m);   // row y0 - 1 (wrapped)
     uint4 B = ld_other(pz);       // row y0
@@ -144,19 +173,30 @@ __device__ __forceinline__ void torus_rows(const TorusArgs& t, const IsingTab& t
         for (int i = 0; i < NB; ++i) {
             // row y + 1 of row i of the batch: the next row's centre (the row after the ticket's last one may wrap)
             C[i] = ld_other((i == NB - 1 && b == ROWS / NB - 1) ? prow_p : pz + (i + 1) * R);
-            if (NNB == 6) { Zp[i] = ld_other(pzp + i * R); Zm[i] = ld_other(pzm + i * R); }
+            if (NNB == 6) { Zp[i] = ld_other(pzp + i * R); Zm[i] = ld_other_last(pzm + i * R, pol); }
             O[i] = ld_own(pown + i * R, pol);
+        }
+        // strips narrower than the row: the lane at the end of the strip takes the edge byte of the adjacent vector from memory
+        // (requested here, with the batch's loads: behind the SHFL it was a dependent load in the middle of every row's arithmetic)
+        uint32_t E[NB];
+        if (RC != 32 && t.strips > 1) {
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const int par = PAR0 ^ (i & 1);
+                E[i] = 0u;
+                if (lane == (par ? 31 : 0)) {
+                    const int ncol = par ? (col + 1 == R ? 0 : col + 1) : (col == 0 ? R - 1 : col - 1);
+                    E[i] = ld_word_nc(reinterpret_cast<const uint32_t*>(pz + i * R + (ncol - col)) + (par ? 0 : 3));
+                }
+            }
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
             const int par = PAR0 ^ (i & 1);
             const uint4 ctr = i == 0 ? B : C[i - 1];
-            // edge byte of the adjacent vector: from the neighbouring lane, or -- at the ends of a strip narrower than the row -- from memory
+            // edge byte of the adjacent vector: from the neighbouring lane, or the word loaded above
             uint32_t edge = __shfl_sync(0xffffffffu, par ? ctr.x : ctr.w, (lane + (par ? 1 : 31)) & 31);
-            if (!RC && t.strips > 1 && lane == (par ? 31 : 0)) {
-                const int ncol = par ? (col + 1 == R ? 0 : col + 1) : (col == 0 ? R - 1 : col - 1);
-                edge = ld_word_nc(reinterpret_cast<const uint32_t*>(pz + i * R + (ncol - col)) + (par ? 0 : 3));
-            }
+            if (RC != 32 && t.strips > 1 && lane == (par ? 31 : 0)) edge = E[i];
             uint4 nb[NNB];
             nb[0] = ctr;
             nb[1] = par ? make_uint4(__funnelshift_r(ctr.x, ctr.y, 8), __funnelshift_r(ctr.y, ctr.z, 8), __funnelshift_r(ctr.z, ctr.w, 8), __funnelshift_r(ctr.w, edge, 8))
@@ -236,15 +276,19 @@ torus_strip_kernel(const __grid_constant__ TorusArgs t, const __grid_constant__ 
     };
     while (cur < t.ntickets) {
         if (lane == 0) nx2 = (int)atomicAdd(tk, 1u) * TK_NCNT + tk_base;   // two tickets ahead
-        if (nxt < t.ntickets && lane < 4 * ROWS) {
+        if (TORUS_PF && nxt < t.ntickets) {
             // the streams of the next ticket that come from DRAM -- its own rows and the rows of the leading z plane -- are
             // requested into L2 now: ROWS rows x 512 bytes = 4 lines per row, lane -> (row, line)
             int nzi, ny0;
-            const int nv = ticket_vec(nxt, nzi, ny0) + (lane >> 2) * R;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(own + nv) + (lane & 3) * 128));
-            if (NNB == 6) {
-                const int nvz = nv + (nzi + 1 == nz ? -nzi : 1) * plane;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(oth + nvz) + (lane & 3) * 128));
+            const int nv0 = ticket_vec(nxt, nzi, ny0);
+#pragma unroll
+            for (int l = lane; l < 4 * ROWS; l += 32) {
+                const int nv = nv0 + (l >> 2) * R;
+                if (TORUS_PF & 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(own + nv) + (l & 3) * 128));
+                if (NNB == 6 && (TORUS_PF & 2)) {
+                    const int nvz = nv + (nzi + 1 == nz ? -nzi : 1) * plane;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(oth + nvz) + (l & 3) * 128));
+                }
             }
         }
         int zi, y0;
@@ -463,8 +507,8 @@ int torus_create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, doubl
     int dev = 0, sms = 148, occ = 3;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (ndim == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, torus_strip_kernel<6, METHOD_METROPOLIS, true, 8, 32>, 256, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, torus_strip_kernel<4, METHOD_METROPOLIS, true, 8, 0>, 256, 0);
+    if (ndim == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, torus_strip_kernel<6, METHOD_METROPOLIS, true, TORUS_ROWS, 32>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, torus_strip_kernel<4, METHOD_METROPOLIS, true, TORUS_ROWS, 0>, 256, 0);
     if (occ < 1) occ = 1;
     const int64_t need = (m->nvec + 255) / 256;
     m->grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);
@@ -472,7 +516,7 @@ int torus_create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, doubl
     // a few per resident warp) and B200MC_TORUS_GENERIC=1 use the generic kernel.
     m->rows = 0;
     const char* tg = getenv("B200MC_TORUS_GENERIC");
-    if (m->R % 32 == 0 && !(tg && atoi(tg) != 0)) m->rows = ny % 8 == 0 ? 8 : 2;
+    if (m->R % 32 == 0 && !(tg && atoi(tg) != 0)) m->rows = ny % TORUS_ROWS == 0 ? TORUS_ROWS : 2;
     int rc = torus_tables(m);
     if (rc) { torus_destroy(m); return rc; }
     if (cudaMemsetAsync(m->vec[0], 1, (size_t)m->nvec * 16, m->stream) != cudaSuccess ||
@@ -521,7 +565,7 @@ int torus_launch_pass(Torus* m, int colour, bool fuse, bool fuse_next)
         const int64_t need = ((int64_t)t.ntickets + 7) / 8;
         const int grid = (int)(need < (int64_t)m->grid ? need : (int64_t)m->grid);
 #define SPASS(METHOD, MEAS, ROWS, RC) torus_strip_kernel<NNB, METHOD, MEAS, ROWS, RC><<<grid, 256, 0, m->stream>>>(t, m->tabs.tab)
-#define SPASS2(METHOD, MEAS) do { if (m->rows == 8) { if (m->R == 32) SPASS(METHOD, MEAS, 8, 32); else SPASS(METHOD, MEAS, 8, 0); } else SPASS(METHOD, MEAS, 2, 0); } while (0)
+#define SPASS2(METHOD, MEAS) do { if (m->rows == TORUS_ROWS) { if (m->R == 32) SPASS(METHOD, MEAS, TORUS_ROWS, 32); else SPASS(METHOD, MEAS, TORUS_ROWS, 0); } else SPASS(METHOD, MEAS, 2, 0); } while (0)
         if (m->method == METHOD_METROPOLIS) { if (fuse) SPASS2(METHOD_METROPOLIS, true); else SPASS2(METHOD_METROPOLIS, false); }
         else { if (fuse) SPASS2(METHOD_HEATBATH, true); else SPASS2(METHOD_HEATBATH, false); }
 #undef SPASS2
@@ -701,7 +745,11 @@ int b200mc_ising_torus_measure(void* h, int64_t* e, int64_t* m) { CHECK_T(h); re
 int b200mc_ising_torus_get_spins(void* h, int32_t* out) { CHECK_T(h); if (!out) ARG_FAIL("null output"); return torus_io(T(h), out, nullptr); }
 int b200mc_ising_torus_set_spins(void* h, const int32_t* in) { CHECK_T(h); if (!in) ARG_FAIL("null input"); return torus_io(T(h), nullptr, in); }
 int64_t b200mc_ising_torus_nall(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? T(h)->N : -1; }
+int64_t b200mc_ising_torus_nx(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? T(h)->nx : -1; }
+int64_t b200mc_ising_torus_ny(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? T(h)->ny : -1; }
+int64_t b200mc_ising_torus_nz(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? (T(h)->ndim == 3 ? T(h)->nz : 0) : -1; }
 double b200mc_ising_torus_beta(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? T(h)->beta : 0.0; }
+double b200mc_ising_torus_kbt(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? 1 / T(h)->beta : 0.0; }
 int b200mc_ising_torus_get_table(void* h, double out[16]) { CHECK_T(h); for (int i = 0; i < 16; ++i) out[i] = T(h)->tabs.w[i]; return B200MC_OK; }
 int b200mc_ising_torus_set_timing(void* h, int32_t on) { CHECK_T(h); T(h)->timing = on != 0; T(h)->ev_used = 0; return B200MC_OK; }
 int b200mc_ising_torus_get_timing(void* h, int64_t* launches, double* total_ms)

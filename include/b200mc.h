@@ -251,7 +251,11 @@ int b200mc_ising_torus_calc_magne_sum(void* h, int64_t* m);      /* :259-276 / s
 int b200mc_ising_torus_measure(void* h, int64_t* e, int64_t* m);
 int b200mc_ising_torus_get_spins(void* h, int32_t* out);         /* nx ny nz values */
 int b200mc_ising_torus_set_spins(void* h, const int32_t* in);
+int64_t b200mc_ising_torus_nx(void* h);                          /* :208-231 */
+int64_t b200mc_ising_torus_ny(void* h);
+int64_t b200mc_ising_torus_nz(void* h);                          /* 0 for the 2D model */
 int64_t b200mc_ising_torus_nall(void* h);
+double b200mc_ising_torus_kbt(void* h);
 double b200mc_ising_torus_beta(void* h);
 /* the acceptance table w[s * 8 + S] (s = 0 / 1 the site's spin, S = number of up neighbours) as the reference builds it */
 int b200mc_ising_torus_get_table(void* h, double out[16]);
