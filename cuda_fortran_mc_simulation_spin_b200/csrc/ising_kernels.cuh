@@ -366,6 +366,7 @@ __device__ __forceinline__ void ising_vec(int v, uint4* po, const uint4* const (
 #ifndef TK_CHUNK
 #define TK_CHUNK 128
 #endif
+
 // vectors per ticket: 4 warp-iterations, unrolled so that the 8 stream addresses are
                       // computed once per ticket and reached with immediate offsets (+512 B per iteration)
 
@@ -461,6 +462,8 @@ __device__ __forceinline__ void ising_pass_body(const RingPassArgs& a, const Isi
     }
     while (cur < vlimit) {
         if (ORDERED && lane == 0) nx2 = (int)atomicAdd(tk, (unsigned)CH) * tk_scale + tk_base;  // two tickets ahead
+        // (prefetching a fixed distance ahead of the current chunk instead -- what the torus kernel does -- was measured here too:
+        //  no effect, 16 K / 64 K / 128 K vectors ahead; profiles/r02ah_prefetch_distance.log)
         if (nxt < vlimit) {
             bool bn;
             const int bnext = chunk_base(nxt, bn);
