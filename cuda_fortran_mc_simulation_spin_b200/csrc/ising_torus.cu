@@ -29,6 +29,7 @@
 #include "../../include/b200mc.h"
 #include "ising_kernels.cuh"
 #include "ising_tables.cuh"
+#include "ring.cuh"
 
 namespace {
 
@@ -39,6 +40,10 @@ struct TorusArgs {
     int ntickets;        // strips * yblocks * nz
     int64_t nvec;        // R * ny * nz
     int64_t nx;          // sites per row (both colours)
+    // slab mode (planes split over the ranks): zwrap = 0 -> the planes below / above the owned ones are ghost planes in the same
+    // array (no wrap); z0 = global index of local plane 0 (row parity; the Philox counter takes a.p0 = z0 * R * ny).
+    // A launch covers the planes zi0, zi0 + zstride, ...: the boundary launch of a slab pass is planes {0, nz - 1}.
+    int zwrap, z0, zi0, zstride;
 };
 
 // The x neighbour that is not at the same xi: row parity par = (y + z + colour) & 1 of the row being updated.
@@ -75,12 +80,13 @@ __device__ __forceinline__ uint32_t ld_word_nc(const uint32_t* p)
 
 // generic gather of the NNB neighbour vectors of vector v (any R): nb = {same xi, shifted, y-, y+ (, z+, z-)}
 template <int NNB>
-__device__ __forceinline__ void torus_gather(const uint4* oth, int R, int ny, int nz, int64_t v, uint32_t colour, uint4 (&nb)[NNB])
+__device__ __forceinline__ void torus_gather(const uint4* oth, int R, int ny, int nz, int64_t v, uint32_t colour, uint4 (&nb)[NNB],
+                                             int zwrap = 1, int z0 = 0)
 {
     const int64_t row = v / R;
     const int col = (int)(v - row * R);
     const int z = (int)(row / ny), y = (int)(row - (int64_t)z * ny);
-    const int par = (y + z + (int)colour) & 1;
+    const int par = (y + z + z0 + (int)colour) & 1;
     const uint4 B = ld_other(oth + v);
     const int ncol = par ? (col + 1 == R ? 0 : col + 1) : (col == 0 ? R - 1 : col - 1);
     const uint32_t edge = ld_word_nc(reinterpret_cast<const uint32_t*>(oth + row * R + ncol) + (par ? 0 : 3));
@@ -91,7 +97,7 @@ __device__ __forceinline__ void torus_gather(const uint4* oth, int R, int ny, in
     nb[2] = ld_other(oth + (zb + ym) * R + col);
     nb[3] = ld_other(oth + (zb + yp) * R + col);
     if (NNB == 6) {
-        const int zp = z + 1 == nz ? 0 : z + 1, zm = z == 0 ? nz - 1 : z - 1;
+        const int zp = (zwrap && z + 1 == nz) ? 0 : z + 1, zm = (zwrap && z == 0) ? nz - 1 : z - 1;   // (slab mode: ghost planes -1 and nz)
         nb[4] = ld_other(oth + ((int64_t)zp * ny + y) * R + col);
         nb[5] = ld_other(oth + ((int64_t)zm * ny + y) * R + col);
     }
@@ -143,6 +149,9 @@ __device__ __forceinline__ void torus_finish_sums(const RingPassArgs& a, uint32_
                             // about one ticket per resident warp (3552) ahead of the frontier: 29 MB of prefetched lines waiting in L2 next to
                             // the 15 MB window of the other colour and the dirty lines of the own one, and 14 % more DRAM reads than the
                             // algorithmic figure.  Measured at 1024^3: 0 -> 1705, 256 -> 1740, 512 -> 1748, 768..1536 -> 1757 flips/ns
+#endif
+#ifndef TORUS_SPLIT_DEFAULT
+#define TORUS_SPLIT_DEFAULT 0
 #endif
 #ifndef TORUS_ROWS
 #define TORUS_ROWS 8        // rows per ticket when ny allows
@@ -210,7 +219,7 @@ __device__ __forceinline__ void torus_rows(const TorusArgs& t, const IsingTab& t
             nb[2] = i == 0 ? A : (i == 1 ? B : C[i - 2]);
             nb[3] = C[i];
             if (NNB == 6) { nb[4] = Zp[i]; nb[5] = Zm[i]; }
-            ising_core<NNB, METHOD, false, MEASURE>(v + i * R, pown + i * R, O[i], nb, (uint32_t)(v + i * R), cz, cw, a, tab, pol, qaddr, cntaddr, false, bX, bM, 0u);
+            ising_core<NNB, METHOD, false, MEASURE>(v + i * R, pown + i * R, O[i], nb, (uint32_t)(v + i * R) + (uint32_t)a.p0, cz, cw, a, tab, pol, qaddr, cntaddr, false, bX, bM, 0u);
             if ((i & 1) && i != NB - 1) {
                 __syncwarp();
                 if (lds32(cntaddr) > TQ_CAP - 64) {
@@ -276,7 +285,7 @@ torus_strip_kernel(const __grid_constant__ TorusArgs t, const __grid_constant__ 
     auto ticket_vec = [&](int q, int& zi, int& y0) -> int {
         const int xs = q % strips, rest = q / strips;
         const int yb = rest % t.yblocks;
-        zi = rest / t.yblocks;
+        zi = t.zi0 + (rest / t.yblocks) * t.zstride;
         y0 = yb * ROWS;
         return zi * plane + y0 * R + xs * 32;
     };
@@ -293,7 +302,7 @@ torus_strip_kernel(const __grid_constant__ TorusArgs t, const __grid_constant__ 
                 const int nv = nv0 + (l >> 2) * R;
                 if (TORUS_PF & 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(own + nv) + (l & 3) * 128));
                 if (NNB == 6 && (TORUS_PF & 2)) {
-                    const int nvz = nv + (nzi + 1 == nz ? -nzi : 1) * plane;
+                    const int nvz = nv + ((t.zwrap && nzi + 1 == nz) ? -nzi : 1) * plane;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(oth + nvz) + (l & 3) * 128));
                 }
             }
@@ -302,11 +311,11 @@ torus_strip_kernel(const __grid_constant__ TorusArgs t, const __grid_constant__ 
         const int v0 = ticket_vec(cur, zi, y0) + lane;     // this lane's vector in the ticket's first row
         const int col = (RC == 32) ? lane : (v0 - zi * plane - y0 * R);
         const uint4* pz = oth + v0;
-        const uint4* pzp = oth + (v0 + (zi + 1 == nz ? -zi : 1) * plane);
-        const uint4* pzm = oth + (v0 + (zi == 0 ? nz - 1 : -1) * plane);
+        const uint4* pzp = oth + (v0 + ((t.zwrap && zi + 1 == nz) ? -zi : 1) * plane);
+        const uint4* pzm = oth + (v0 + ((t.zwrap && zi == 0) ? nz - 1 : -1) * plane);
         const uint4* prow_m = pz + (y0 == 0 ? ny - 1 : -1) * R;
         const uint4* prow_p = pz + (y0 + ROWS == ny ? ROWS - ny : ROWS) * R;
-        if ((zi + (int)a.colour) & 1)
+        if ((zi + t.z0 + (int)a.colour) & 1)
             torus_rows<NNB, METHOD, MEASURE, ROWS, 1, RC>(t, tab, own + v0, pz, pzp, pzm, prow_m, prow_p, v0, col, lane, cz, cw, pol, qaddr, cntaddr,
                                                           bX, bM, accX, accM, corrX, corrM);
         else
@@ -343,9 +352,9 @@ torus_pass_kernel(const __grid_constant__ TorusArgs t, const __grid_constant__ I
         const int64_t v = base + lane;
         if (v < t.nvec) {
             uint4 nb[NNB];
-            torus_gather<NNB>(a.oth, t.R, t.ny, t.nz, v, a.colour, nb);
+            torus_gather<NNB>(a.oth, t.R, t.ny, t.nz, v, a.colour, nb, t.zwrap, t.z0);
             const uint4 o = ld_own(a.own + v, pol);
-            ising_core<NNB, METHOD, false, MEASURE>((int)v, a.own + v, o, nb, (uint32_t)v, cz, cw, a, tab, pol, qaddr, cntaddr, false, bX, bM, 0u);
+            ising_core<NNB, METHOD, false, MEASURE>((int)v, a.own + v, o, nb, (uint32_t)v + (uint32_t)a.p0, cz, cw, a, tab, pol, qaddr, cntaddr, false, bX, bM, 0u);
             if (MEASURE) ising_fold_sums(bX, bM, accX, accM);
         }
         __syncwarp();
@@ -399,13 +408,14 @@ torus_pass_randoms_kernel(const __grid_constant__ TorusArgs t, const __grid_cons
 // ---- E + M in one pass over the colour-1 vectors (every bond has exactly one colour-1 end): acc[0] += X, acc[1] += sum(s) ----
 template <int NNB>
 __global__ void __launch_bounds__(256)
-torus_measure_kernel(const uint4* __restrict__ c0, const uint4* __restrict__ c1, int R, int ny, int nz, int64_t nvec, unsigned long long* acc)
+torus_measure_kernel(const uint4* __restrict__ c0, const uint4* __restrict__ c1, int R, int ny, int nz, int64_t nvec, unsigned long long* acc,
+                     int zwrap, int z0)
 {
     long long part[2] = {0, 0};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
         uint4 nb[NNB];
-        torus_gather<NNB>(c0, R, ny, nz, v, 1u, nb);
+        torus_gather<NNB>(c0, R, ny, nz, v, 1u, nb, zwrap, z0);
         const uint4 o = c1[v];
         uint4 X = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -417,20 +427,20 @@ torus_measure_kernel(const uint4* __restrict__ c0, const uint4* __restrict__ c1,
 }
 
 // ---- host int32 arrays s[x + nx (y + ny z)] <-> the two colour arrays ----
-__global__ void torus_export_kernel(const uint8_t* __restrict__ c0, const uint8_t* __restrict__ c1, int64_t nx, int64_t ny, int64_t n, int32_t* out, int pm1)
+__global__ void torus_export_kernel(const uint8_t* __restrict__ c0, const uint8_t* __restrict__ c1, int64_t nx, int64_t ny, int64_t n, int32_t* out, int pm1, int64_t z0)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t x = i % nx, row = i / nx, y = row % ny, z = row / ny;
-    const uint8_t s = (((x + y + z) & 1) ? c1 : c0)[row * (nx / 2) + (x >> 1)];
+    const uint8_t s = (((x + y + z + z0) & 1) ? c1 : c0)[row * (nx / 2) + (x >> 1)];
     out[i] = pm1 ? (s ? 1 : -1) : (int32_t)s;
 }
-__global__ void torus_import_kernel(uint8_t* c0, uint8_t* c1, int64_t nx, int64_t ny, int64_t n, const int32_t* __restrict__ in, int pm1)
+__global__ void torus_import_kernel(uint8_t* c0, uint8_t* c1, int64_t nx, int64_t ny, int64_t n, const int32_t* __restrict__ in, int pm1, int64_t z0)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t x = i % nx, row = i / nx, y = row % ny, z = row / ny;
-    (((x + y + z) & 1) ? c1 : c0)[row * (nx / 2) + (x >> 1)] = pm1 ? (uint8_t)(in[i] > 0) : (uint8_t)in[i];
+    (((x + y + z + z0) & 1) ? c1 : c0)[row * (nx / 2) + (x >> 1)] = pm1 ? (uint8_t)(in[i] > 0) : (uint8_t)in[i];
 }
 
 #define TORUS_MAGIC 0x544F5255
@@ -441,7 +451,15 @@ struct Torus {
     int64_t nx, ny, nz;     // nz = 1 in 2D
     int R;
     int64_t nvec, N;
-    uint4* vec[2];
+    uint4* vec[2];          // first OWNED plane of each colour
+    uint4* alloc[2];        // the allocations (slab mode: one ghost plane in front of and one behind the owned planes)
+    // slab mode: planes [z0, z0 + nz) of a lattice of nz_glob planes, one process per GPU; ghost planes through ncclSend/Recv
+    int rank, nranks;
+    int64_t z0, nz_glob, N_glob;
+    void* comm;
+    cudaStream_t comm_stream;
+    cudaEvent_t ev_boundary, ev_halo;
+    bool split;             // slab pass = boundary planes, then exchange beside the interior planes (else: one launch, then the exchange)
     cudaStream_t stream;
     double beta;
     uint32_t seed;
@@ -466,7 +484,11 @@ struct Torus {
 int torus_destroy(Torus* m)
 {
     if (!m) return B200MC_OK;
-    cudaFree(m->vec[0]); cudaFree(m->vec[1]); cudaFree(m->d_acc); cudaFree(m->d_ticket); cudaFree(m->d_io); cudaFree(m->d_randoms);
+    cudaFree(m->alloc[0]); cudaFree(m->alloc[1]); cudaFree(m->d_acc);
+    if (m->comm) dist_comm_destroy(m->comm);
+    if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
+    if (m->ev_boundary) cudaEventDestroy(m->ev_boundary);
+    if (m->ev_halo) cudaEventDestroy(m->ev_halo); cudaFree(m->d_ticket); cudaFree(m->d_io); cudaFree(m->d_randoms);
     cudaFreeHost(m->h_acc);
     for (cudaEvent_t e : m->evs) cudaEventDestroy(e);
     m->alive = false;
@@ -477,7 +499,10 @@ int torus_destroy(Torus* m)
 
 int torus_tables(Torus* m) { return ising_build_host_tables(m->ndim, m->method, m->beta, m->seed, &m->tabs); }
 
-int torus_create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed)
+int torus_halo(struct Torus* m, int colour, cudaStream_t st);
+
+int torus_create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed,
+                 int rank = 0, int nranks = 1, const char* nccl_id = nullptr)
 {
     if (!out) ARG_FAIL("null handle pointer");
     *out = nullptr;
@@ -488,6 +513,15 @@ int torus_create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, doubl
     if (ndim == 3 && (nz < 2 || nz % 2 != 0)) ARG_FAIL("periodic Ising: nz must be even and >= 2, got %lld", (long long)nz);
     if (!(kbt > 0.0)) ARG_FAIL("kbt must be > 0");
     if (nx / 32 * ny * nz >= (int64_t)1 << 31) ARG_FAIL("lattice too large: 2^31 vectors per colour");
+    if (nranks < 1 || rank < 0 || rank >= nranks) ARG_FAIL("invalid rank %d of %d", rank, nranks);
+    const int64_t nz_glob = nz;
+    if (nranks > 1) {
+        if (ndim != 3) ARG_FAIL("periodic Ising slabs: 3D only (planes along z)");
+        if (nx % 1024 != 0) ARG_FAIL("periodic Ising slabs: nx must be a multiple of 1024 (strip kernel)");
+        if (nz % nranks != 0 || nz / nranks < 2) ARG_FAIL("periodic Ising slabs: nz = %lld must be a multiple of the %d ranks with at least 2 planes each", (long long)nz, nranks);
+        if (!nccl_id) ARG_FAIL("slab mode needs the NCCL unique id of the job (b200mc_dist_unique_id on rank 0, broadcast by the caller)");
+        nz = nz / nranks;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "no CUDA device: this library has no CPU fallback");
@@ -497,11 +531,31 @@ int torus_create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, doubl
     if (!m) ARG_FAIL("out of host memory");
     m->magic = TORUS_MAGIC; m->ndim = ndim; m->nx = nx; m->ny = ny; m->nz = nz;
     m->R = (int)(nx / 32); m->nvec = (int64_t)m->R * ny * nz; m->N = nx * ny * nz;
-    m->vec[0] = m->vec[1] = nullptr; m->stream = 0; m->beta = 1 / kbt; m->seed = (uint32_t)iseed; m->draw = 0; m->method = METHOD_METROPOLIS;
+    m->vec[0] = m->vec[1] = m->alloc[0] = m->alloc[1] = nullptr;
+    m->rank = rank; m->nranks = nranks; m->z0 = (int64_t)rank * nz; m->nz_glob = nz_glob; m->N_glob = nx * ny * nz_glob;
+    m->comm = nullptr; m->comm_stream = nullptr; m->ev_boundary = m->ev_halo = nullptr;
+    { const char* ts = getenv("B200MC_TORUS_SPLIT"); m->split = ts ? atoi(ts) != 0 : TORUS_SPLIT_DEFAULT; }
+    m->stream = 0; m->beta = 1 / kbt; m->seed = (uint32_t)iseed; m->draw = 0; m->method = METHOD_METROPOLIS;
     m->d_acc = nullptr; m->h_acc = nullptr; m->d_ticket = nullptr; m->d_io = nullptr; m->d_randoms = nullptr;
     m->obs_valid = false; m->want_fused = false; m->fused_pending = false; m->h_acc_pending = false;
     m->timing = false; m->ev_used = 0; m->alive = true;
-    if (cudaMalloc(&m->vec[0], (size_t)m->nvec * 16) != cudaSuccess || cudaMalloc(&m->vec[1], (size_t)m->nvec * 16) != cudaSuccess ||
+    const int64_t plane = (int64_t)m->R * ny, ghost = nranks > 1 ? plane : 0;
+    if (nranks > 1) {
+        const int rc = dist_comm_init(&m->comm, rank, nranks, nccl_id);
+        if (rc) { torus_destroy(m); return rc; }
+        // the exchange runs beside the interior launch, whose blocks fill every SM for the whole pass: on a stream of the highest
+        // priority its (few) blocks are placed first when both become runnable at the end of the boundary launch
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&m->comm_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_boundary, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_halo, cudaEventDisableTiming) != cudaSuccess) {
+            snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cannot create the comm stream / events");
+            torus_destroy(m);
+            return B200MC_ERR_CUDA;
+        }
+    }
+    if (cudaMalloc(&m->alloc[0], (size_t)(m->nvec + 2 * ghost) * 16) != cudaSuccess || cudaMalloc(&m->alloc[1], (size_t)(m->nvec + 2 * ghost) * 16) != cudaSuccess ||
         cudaMalloc(&m->d_acc, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaHostAlloc(&m->h_acc, 2 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess ||
         cudaMalloc(&m->d_ticket, (2 * TK_NCNT * 64 + 64) * sizeof(unsigned int)) != cudaSuccess ||
@@ -511,6 +565,7 @@ int torus_create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, doubl
         torus_destroy(m);
         return B200MC_ERR_CUDA;
     }
+    m->vec[0] = m->alloc[0] + ghost; m->vec[1] = m->alloc[1] + ghost;
     int dev = 0, sms = 148, occ = 3;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -523,11 +578,11 @@ int torus_create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, doubl
     // a few per resident warp) and B200MC_TORUS_GENERIC=1 use the generic kernel.
     m->rows = 0;
     const char* tg = getenv("B200MC_TORUS_GENERIC");
-    if (m->R % 32 == 0 && !(tg && atoi(tg) != 0)) m->rows = ny % TORUS_ROWS == 0 ? TORUS_ROWS : 2;
+    if (m->R % 32 == 0 && (nranks > 1 || !(tg && atoi(tg) != 0))) m->rows = ny % TORUS_ROWS == 0 ? TORUS_ROWS : 2;
     int rc = torus_tables(m);
     if (rc) { torus_destroy(m); return rc; }
-    if (cudaMemsetAsync(m->vec[0], 1, (size_t)m->nvec * 16, m->stream) != cudaSuccess ||
-        cudaMemsetAsync(m->vec[1], 1, (size_t)m->nvec * 16, m->stream) != cudaSuccess) {   // set_allup_spin
+    if (cudaMemsetAsync(m->alloc[0], 1, (size_t)(m->nvec + 2 * ghost) * 16, m->stream) != cudaSuccess ||
+        cudaMemsetAsync(m->alloc[1], 1, (size_t)(m->nvec + 2 * ghost) * 16, m->stream) != cudaSuccess) {   // set_allup_spin (ghost planes too)
         snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaMemset failed");
         torus_destroy(m);
         return B200MC_ERR_CUDA;
@@ -549,7 +604,18 @@ void torus_args(Torus* m, int colour, TorusArgs& t)
     a.acc = m->d_acc;
     a.mask_from = 0x7FFFFFFF;
     a.Lfold = 0; a.Nc = INT64_MAX;   // (ising_drain: every byte lane of every vector holds a site)
+    a.p0 = m->z0 * (int64_t)m->R * m->ny;   // global index of local vector 0: the Philox counter of a site does not depend on the number of ranks
     t.R = m->R; t.ny = (int)m->ny; t.nz = (int)m->nz; t.nvec = m->nvec; t.nx = m->nx;
+    t.zwrap = m->nranks == 1; t.z0 = (int)m->z0; t.zi0 = 0; t.zstride = 1;
+}
+
+// slab mode: my first owned plane of `colour` becomes the ghost plane above rank - 1's slab, my last owned plane the ghost
+// plane below rank + 1's (ring of ranks: the torus closes between rank P - 1 and rank 0)
+int torus_halo(Torus* m, int colour, cudaStream_t st)
+{
+    const int64_t plane = (int64_t)m->R * m->ny;
+    uint4* v = m->vec[colour];
+    return dist_exchange_ring(m->comm, m->rank, m->nranks, v, v + (m->nz - 1) * plane, v - plane, v + m->nz * plane, (size_t)plane * 16, st);
 }
 
 template <int NNB>
@@ -561,6 +627,44 @@ int torus_launch_pass(Torus* m, int colour, bool fuse, bool fuse_next)
     if (m->timing) {
         while (m->evs.size() < m->ev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); m->evs.push_back(e); }
         CK(cudaEventRecord(m->evs[m->ev_used], m->stream));
+    }
+    if (m->nranks > 1) {
+        // slab pass: the two boundary planes first (one launch: planes {0, nz - 1}), their exchange on the comm stream while the
+        // interior planes are updated; the next launch on the compute stream waits for the ghost planes
+        t.strips = m->R / 32; t.yblocks = (int)(m->ny / m->rows);
+        const int per_plane = t.strips * t.yblocks;
+        if (fuse) CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
+        CK(cudaMemsetAsync(m->d_ticket, 0, 2 * TK_NCNT * 64 * sizeof(unsigned int), m->stream));
+        for (int part = m->split ? 0 : 1; part < 2; ++part) {
+            TorusArgs u = t;
+            u.a.ticket = m->d_ticket + part * TK_NCNT * 64;
+            if (part == 0) { u.zi0 = 0; u.zstride = (int)m->nz - 1; u.ntickets = 2 * per_plane; }
+            else if (m->split) { u.zi0 = 1; u.zstride = 1; u.ntickets = ((int)m->nz - 2) * per_plane; }
+            else { u.zi0 = 0; u.zstride = 1; u.ntickets = (int)m->nz * per_plane; }   // all planes in one launch, the exchange after it
+            if (u.ntickets > 0) {
+                const int64_t need = ((int64_t)u.ntickets + 7) / 8;
+                const int grid = (int)(need < (int64_t)m->grid ? need : (int64_t)m->grid);
+                COUNT_LAUNCH();
+#define SPASS(METHOD, MEAS, ROWS, RC) torus_strip_kernel<NNB, METHOD, MEAS, ROWS, RC><<<grid, 256, 0, m->stream>>>(u, m->tabs.tab)
+#define SPASS2(METHOD, MEAS) do { if (m->rows == TORUS_ROWS) { if (m->R == 32) SPASS(METHOD, MEAS, TORUS_ROWS, 32); else SPASS(METHOD, MEAS, TORUS_ROWS, 0); } else SPASS(METHOD, MEAS, 2, 0); } while (0)
+                if (m->method == METHOD_METROPOLIS) { if (fuse) SPASS2(METHOD_METROPOLIS, true); else SPASS2(METHOD_METROPOLIS, false); }
+                else { if (fuse) SPASS2(METHOD_HEATBATH, true); else SPASS2(METHOD_HEATBATH, false); }
+#undef SPASS2
+#undef SPASS
+                CK(cudaGetLastError());
+            }
+            if (part == 0) {
+                CK(cudaEventRecord(m->ev_boundary, m->stream));
+                CK(cudaStreamWaitEvent(m->comm_stream, m->ev_boundary, 0));
+                const int rc = torus_halo(m, colour, m->comm_stream);
+                if (rc) return rc;
+                CK(cudaEventRecord(m->ev_halo, m->comm_stream));
+            }
+        }
+        if (m->split) CK(cudaStreamWaitEvent(m->stream, m->ev_halo, 0));
+        else { const int rc = torus_halo(m, colour, m->stream); if (rc) return rc; }
+        if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
+        return B200MC_OK;
     }
     COUNT_LAUNCH();
     if (m->rows) {
@@ -611,19 +715,24 @@ int torus_measure(Torus* m, int64_t* e, int64_t* mag)
         if (!m->fused_pending) {
             CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
             COUNT_LAUNCH();
-            if (m->ndim == 3) torus_measure_kernel<6><<<m->grid, 256, 0, m->stream>>>(m->vec[0], m->vec[1], m->R, (int)m->ny, (int)m->nz, m->nvec, m->d_acc);
-            else torus_measure_kernel<4><<<m->grid, 256, 0, m->stream>>>(m->vec[0], m->vec[1], m->R, (int)m->ny, (int)m->nz, m->nvec, m->d_acc);
+            const int zwrap = m->nranks == 1;
+            if (m->ndim == 3) torus_measure_kernel<6><<<m->grid, 256, 0, m->stream>>>(m->vec[0], m->vec[1], m->R, (int)m->ny, (int)m->nz, m->nvec, m->d_acc, zwrap, (int)m->z0);
+            else torus_measure_kernel<4><<<m->grid, 256, 0, m->stream>>>(m->vec[0], m->vec[1], m->R, (int)m->ny, (int)m->nz, m->nvec, m->d_acc, zwrap, (int)m->z0);
             CK(cudaGetLastError());
         }
         m->fused_pending = false;
         m->h_acc_pending = false;
         m->want_fused = true;
+        if (m->nranks > 1) {   // every rank gets the sums of the whole lattice
+            const int rc = dist_allreduce_u64(m->comm, m->d_acc, 2, m->stream);
+            if (rc) return rc;
+        }
         if (!direct) CK(cudaMemcpyAsync(m->h_acc, m->d_acc, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
         CK(cudaStreamSynchronize(m->stream));
         const int64_t X = (int64_t)m->h_acc[0], sum = (int64_t)m->h_acc[1];
         const int nnb = m->ndim == 3 ? 6 : 4;
-        m->obs_e = -(int64_t)(nnb / 2) * m->N + 2 * X;   // E = -(bonds) + 2 X, bonds = (nnb / 2) N
-        m->obs_m = 2 * sum - m->N;
+        m->obs_e = -(int64_t)(nnb / 2) * m->N_glob + 2 * X;   // E = -(bonds) + 2 X, bonds = (nnb / 2) N
+        m->obs_m = 2 * sum - m->N_glob;
         m->obs_valid = true;
     }
     if (e) *e = m->obs_e;
@@ -636,9 +745,11 @@ int torus_set_random(Torus* m)
     m->obs_valid = false; m->fused_pending = false;
     for (int c = 0; c < 2; ++c) {
         COUNT_LAUNCH();
-        ring_random_bits_kernel<<<(unsigned)((m->nvec + 255) / 256), 256, 0, m->stream>>>(m->vec[c], m->nvec, 0, 0, m->seed, m->draw, (uint32_t)c, 0);
+        ring_random_bits_kernel<<<(unsigned)((m->nvec + 255) / 256), 256, 0, m->stream>>>(m->vec[c], m->nvec, 0, m->z0 * (int64_t)m->R * m->ny, m->seed, m->draw, (uint32_t)c, 0);
     }
     CK(cudaGetLastError());
+    if (m->nranks > 1)
+        for (int c = 0; c < 2; ++c) { const int rc = torus_halo(m, c, m->stream); if (rc) return rc; }
     m->draw += 1;
     return B200MC_OK;
 }
@@ -646,6 +757,7 @@ int torus_set_random(Torus* m)
 int torus_update_with_randoms(Torus* m, const double* randoms)
 {
     if (!randoms) ARG_FAIL("null randoms");
+    if (m->nranks > 1) { snprintf(g_b200mc_err, sizeof(g_b200mc_err), "update_with_randoms: single-GPU handles only"); return B200MC_ERR_UNSUPPORTED; }
     if (!m->d_randoms) CK(cudaMalloc(&m->d_randoms, (size_t)m->N * sizeof(double)));
     CK(cudaMemcpyAsync(m->d_randoms, randoms, (size_t)m->N * sizeof(double), cudaMemcpyHostToDevice, m->stream));
     m->obs_valid = false; m->fused_pending = false;
@@ -679,12 +791,14 @@ int torus_io(Torus* m, int32_t* out, const int32_t* in)
         }
         CK(cudaMemcpyAsync(m->d_io, in, (size_t)m->N * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
         COUNT_LAUNCH();
-        torus_import_kernel<<<grid, 256, 0, m->stream>>>(reinterpret_cast<uint8_t*>(m->vec[0]), reinterpret_cast<uint8_t*>(m->vec[1]), m->nx, m->ny, m->N, m->d_io, pm1);
+        torus_import_kernel<<<grid, 256, 0, m->stream>>>(reinterpret_cast<uint8_t*>(m->vec[0]), reinterpret_cast<uint8_t*>(m->vec[1]), m->nx, m->ny, m->N, m->d_io, pm1, m->z0);
         CK(cudaGetLastError());
         m->obs_valid = false; m->fused_pending = false;
+        if (m->nranks > 1)
+            for (int c = 0; c < 2; ++c) { const int rc = torus_halo(m, c, m->stream); if (rc) return rc; }
     } else {
         COUNT_LAUNCH();
-        torus_export_kernel<<<grid, 256, 0, m->stream>>>(reinterpret_cast<const uint8_t*>(m->vec[0]), reinterpret_cast<const uint8_t*>(m->vec[1]), m->nx, m->ny, m->N, m->d_io, pm1);
+        torus_export_kernel<<<grid, 256, 0, m->stream>>>(reinterpret_cast<const uint8_t*>(m->vec[0]), reinterpret_cast<const uint8_t*>(m->vec[1]), m->nx, m->ny, m->N, m->d_io, pm1, m->z0);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(out, m->d_io, (size_t)m->N * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
     }
@@ -706,6 +820,20 @@ int b200mc_ising_torus_create(void** h, int32_t ndim, int64_t nx, int64_t ny, in
 {
     return torus_create(h, ndim, nx, ny, nz, kbt, iseed);
 }
+int b200mc_ising_torus_create_slab(void** h, int32_t ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed, int32_t rank,
+                                   int32_t nranks, const char nccl_id[128])
+{
+    return torus_create(h, ndim, nx, ny, nz, kbt, iseed, rank, nranks, nccl_id);
+}
+int b200mc_ising_torus_rank_info(void* h, int32_t* rank, int32_t* nranks, int64_t* z0, int64_t* nz_local)
+{
+    CHECK_T(h);
+    if (rank) *rank = T(h)->rank;
+    if (nranks) *nranks = T(h)->nranks;
+    if (z0) *z0 = T(h)->z0;
+    if (nz_local) *nz_local = T(h)->ndim == 3 ? T(h)->nz : 0;
+    return B200MC_OK;
+}
 int b200mc_ising_torus_destroy(void* h)
 {
     if (!h) return B200MC_OK;
@@ -717,15 +845,16 @@ int b200mc_ising_torus_skip_curand(void* h, int64_t n_skip)
 {
     CHECK_T(h);
     if (n_skip < 0) ARG_FAIL("n_skip < 0");
-    T(h)->draw += (uint64_t)((n_skip + T(h)->N - 1) / T(h)->N);   // as the helical modules: ceil(n_skip / nall) draws
+    T(h)->draw += (uint64_t)((n_skip + T(h)->N_glob - 1) / T(h)->N_glob);   // as the helical modules: ceil(n_skip / nall) draws
     return B200MC_OK;
 }
 int b200mc_ising_torus_set_allup_spin(void* h)
 {
     CHECK_T(h);
     T(h)->obs_valid = false; T(h)->fused_pending = false;
-    CK(cudaMemsetAsync(T(h)->vec[0], 1, (size_t)T(h)->nvec * 16, T(h)->stream));
-    CK(cudaMemsetAsync(T(h)->vec[1], 1, (size_t)T(h)->nvec * 16, T(h)->stream));
+    const size_t ghost = T(h)->nranks > 1 ? (size_t)T(h)->R * T(h)->ny : 0;   // (all up: the ghost planes too, no exchange needed)
+    CK(cudaMemsetAsync(T(h)->alloc[0], 1, ((size_t)T(h)->nvec + 2 * ghost) * 16, T(h)->stream));
+    CK(cudaMemsetAsync(T(h)->alloc[1], 1, ((size_t)T(h)->nvec + 2 * ghost) * 16, T(h)->stream));
     return B200MC_OK;
 }
 int b200mc_ising_torus_set_random_spin(void* h) { CHECK_T(h); return torus_set_random(T(h)); }
@@ -751,10 +880,10 @@ int b200mc_ising_torus_calc_magne_sum(void* h, int64_t* m) { CHECK_T(h); return 
 int b200mc_ising_torus_measure(void* h, int64_t* e, int64_t* m) { CHECK_T(h); return torus_measure(T(h), e, m); }
 int b200mc_ising_torus_get_spins(void* h, int32_t* out) { CHECK_T(h); if (!out) ARG_FAIL("null output"); return torus_io(T(h), out, nullptr); }
 int b200mc_ising_torus_set_spins(void* h, const int32_t* in) { CHECK_T(h); if (!in) ARG_FAIL("null input"); return torus_io(T(h), nullptr, in); }
-int64_t b200mc_ising_torus_nall(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? T(h)->N : -1; }
+int64_t b200mc_ising_torus_nall(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? T(h)->N_glob : -1; }
 int64_t b200mc_ising_torus_nx(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? T(h)->nx : -1; }
 int64_t b200mc_ising_torus_ny(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? T(h)->ny : -1; }
-int64_t b200mc_ising_torus_nz(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? (T(h)->ndim == 3 ? T(h)->nz : 0) : -1; }
+int64_t b200mc_ising_torus_nz(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? (T(h)->ndim == 3 ? T(h)->nz_glob : 0) : -1; }
 double b200mc_ising_torus_beta(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? T(h)->beta : 0.0; }
 double b200mc_ising_torus_kbt(void* h) { return (h && T(h)->magic == TORUS_MAGIC) ? 1 / T(h)->beta : 0.0; }
 int b200mc_ising_torus_get_table(void* h, double out[16]) { CHECK_T(h); for (int i = 0; i < 16; ++i) out[i] = T(h)->tabs.w[i]; return B200MC_OK; }

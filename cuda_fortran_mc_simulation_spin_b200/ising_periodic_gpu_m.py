@@ -50,6 +50,34 @@ class ising_periodic_gpu:
         self._dims = (int(nz), int(ny), int(nx)) if ndim == 3 else (int(ny), int(nx))
         return self
 
+    def init_distributed(self, nx, ny, nz, kbt, iseed, group=None):
+        """the global nx x ny x nz lattice, one slab of planes per rank of an initialised torch.distributed job (one process per
+        GPU): rank 0 draws the NCCL id of the library's own communicator, the job's process group only broadcasts those 128 bytes"""
+        import torch.distributed as dist
+        from ._ising_base import unique_id
+
+        if self._h:
+            self._f("destroy", C.c_int, P)(self._h)
+            self._h = C.c_void_p(None)
+        rank, nranks = dist.get_rank(group), dist.get_world_size(group)
+        box = [unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        f = _lib.fn("b200mc_ising_torus_create_slab", C.c_int, PP, i32, i64, i64, i64, f64, i32, i32, i32, C.c_char_p)
+        _lib.check(f(C.byref(self._h), 3, int(nx), int(ny), int(nz), float(kbt), int(iseed), rank, nranks, bytes(box[0])))
+        self._group, self._dist = group, dist
+        self._dims = (int(nz), int(ny), int(nx))
+        return self
+
+    def rank_info(self):
+        """(rank, nranks, first owned plane, owned planes)"""
+        r, n, z0, nzl = C.c_int32(0), C.c_int32(1), C.c_int64(0), C.c_int64(0)
+        self._call("rank_info", C.byref(r), C.byref(n), C.byref(z0), C.byref(nzl), argtypes=(P, P, P, P))
+        return int(r.value), int(n.value), int(z0.value), int(nzl.value)
+
+    def _nlocal(self):
+        _, n, _, nzl = self.rank_info()
+        return self.nall() // n if n > 1 else self.nall()
+
     def set_allup_spin(self): self._call("set_allup_spin")
     def set_random_spin(self): self._call("set_random_spin")
     def set_kbt(self, kbt): self._call("set_kbt", float(kbt), argtypes=(f64,))
@@ -74,14 +102,31 @@ class ising_periodic_gpu:
         self._call("get_table", out.ctypes.data_as(P), argtypes=(P,))
         return out.reshape(2, 8)
 
-    def spins(self):
-        out = np.empty(self.nall(), dtype=np.int32)
+    def spins_local(self):
+        """the planes this rank owns (the whole lattice on a single-GPU handle)"""
+        out = np.empty(self._nlocal(), dtype=np.int32)
         self._call("get_spins", out.ctypes.data_as(P), argtypes=(P,))
         return out
+
+    def spins(self):
+        """the whole lattice, s[z][y][x] flattened (slab mode: gathered over the ranks, every rank gets it)"""
+        loc = self.spins_local()
+        rank, n, _, _ = self.rank_info()
+        if n == 1:
+            return loc
+        import torch
+        t = torch.from_numpy(loc).cuda()
+        parts = [torch.empty_like(t) for _ in range(n)]
+        self._dist.all_gather(parts, t, group=self._group)
+        return torch.cat(parts).cpu().numpy()
 
     def set_spins(self, spins):
         s = np.ascontiguousarray(spins, dtype=np.int32).ravel()
         assert s.size == self.nall()
+        rank, n, _, _ = self.rank_info()
+        if n > 1:
+            nl = self._nlocal()
+            s = np.ascontiguousarray(s[rank * nl:(rank + 1) * nl])
         self._call("set_spins", s.ctypes.data_as(P), argtypes=(P,))
 
     def measure(self):

@@ -234,6 +234,13 @@ int b200mc_ising2dp_get_timing(void* h, int64_t* launches, double* total_ms);
  * no halo cells.  CPU restatement: oracle/oracle.c orc_isingp_*.
  * ------------------------------------------------------------------------ */
 int b200mc_ising_torus_create(void** h, int32_t ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed);
+/* slab mode (one process per GPU, as b200mc_ising3d_create_slab): the nz planes are split over the ranks (3D, nx % 1024 == 0,
+ * nz % nranks == 0), a rank's ghost planes arrive by ncclSend/Recv after the boundary planes of a colour pass while the
+ * interior planes are updated, observables are all-reduced.  A site's random stream does not depend on the number of ranks:
+ * an N-rank run is the 1-GPU run of the same lattice.  get_spins / set_spins then move the rank's own planes
+ * (nx ny nz_local values, planes z0 .. z0 + nz_local - 1); nall / nz report the whole lattice. */
+int b200mc_ising_torus_create_slab(void** h, int32_t ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed, int32_t rank, int32_t nranks, const char nccl_id[128]);
+int b200mc_ising_torus_rank_info(void* h, int32_t* rank, int32_t* nranks, int64_t* z0, int64_t* nz_local);
 int b200mc_ising_torus_destroy(void* h);
 int b200mc_ising_torus_set_stream(void* h, void* cuda_stream);
 int b200mc_ising_torus_skip_curand(void* h, int64_t n_skip);     /* src/ising3d_gpu_m.f90:72-77 */
