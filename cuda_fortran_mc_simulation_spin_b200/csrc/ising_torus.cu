@@ -633,11 +633,18 @@ int torus_launch_pass(Torus* m, int colour, bool fuse, bool fuse_next)
         // interior planes are updated; the next launch on the compute stream waits for the ghost planes
         t.strips = m->R / 32; t.yblocks = (int)(m->ny / m->rows);
         const int per_plane = t.strips * t.yblocks;
-        if (fuse) CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
-        CK(cudaMemsetAsync(m->d_ticket, 0, 2 * TK_NCNT * 64 * sizeof(unsigned int), m->stream));
+        if (m->split) {
+            if (fuse) CK(cudaMemsetAsync(m->d_acc, 0, 2 * sizeof(unsigned long long), m->stream));
+            CK(cudaMemsetAsync(m->d_ticket, 0, 2 * TK_NCNT * 64 * sizeof(unsigned int), m->stream));
+        }
         for (int part = m->split ? 0 : 1; part < 2; ++part) {
             TorusArgs u = t;
             u.a.ticket = m->d_ticket + part * TK_NCNT * 64;
+            if (!m->split) {   // one launch per pass: self-cleaning counters and sums as on a single GPU
+                u.a.ticket = m->d_ticket + colour * TK_NCNT * 64;
+                u.a.ticket_reset = m->d_ticket + (colour ^ 1) * TK_NCNT * 64;
+                if (colour == 0 && fuse_next) u.a.acc_reset = m->d_acc;
+            }
             if (part == 0) { u.zi0 = 0; u.zstride = (int)m->nz - 1; u.ntickets = 2 * per_plane; }
             else if (m->split) { u.zi0 = 1; u.zstride = 1; u.ntickets = ((int)m->nz - 2) * per_plane; }
             else { u.zi0 = 0; u.zstride = 1; u.ntickets = (int)m->nz * per_plane; }   // all planes in one launch, the exchange after it
