@@ -44,6 +44,24 @@ def ising_cases(O):
     return out
 
 
+def torus_cases(O):
+    """periodic (torus) Ising: nz = 0 -> 2D; nx = 1024 rows run the strip kernel on the GPU, the others the generic one"""
+    out = []
+    specs = [((64, 6, 4), KBT3, 42, "allup", 0, 6), ((1024, 8, 4), KBT3, 7, "random", 0, 5), ((1024, 6, 2), KBT3, 7, "random", 1, 4),
+             ((96, 10, 0), KBT2, 3, "random", 0, 5), ((2048, 8, 0), KBT2, 9, "allup", 1, 4)]
+    for shape, kbt, seed, start, method, sweeps in specs:
+        o = O.ising_periodic_gpu().init(*shape, kbt, seed)
+        if start == "random":
+            o.set_random_spin()
+        series = []
+        for _ in range(sweeps):
+            (o.update_heatbath if method else o.update)()
+            series.append(list(o.measure()))
+        out.append({"model": "ising_torus", "shape": list(shape), "kbt": kbt, "seed": seed, "start": start, "method": method,
+                    "em": series, "spins_sha256": sha(o.spins()), "spins_head": o.spins()[:24].tolist()})
+    return out
+
+
 def clock_cases(O):
     out = []
     for shape, q, kbt, seed, n_multi, start, sweeps in [((33, 32), 6, 0.91, 42, None, "allup", 5), ((101, 100), 6, 0.8, 5, None, "random", 4),
@@ -101,14 +119,15 @@ def rng_cases(O):
             "ring_init_uniforms(42,0,32)": O.ring_init_uniforms(42, 0, 32).tolist(),
             "clock_uniforms(42,2,1,32)": [a.tolist() for a in O.clock_uniforms(42, 2, 1, 32)],
             "torus_uniforms(42,2,1,8,4)": O.torus_uniforms(42, 2, 1, 8, 4).tolist(),
-            "xy_uniforms(42,2,8,4)": [a.tolist() for a in O.xy_uniforms(42, 2, 8, 4)]}
+            "xy_uniforms(42,2,8,4)": [a.tolist() for a in O.xy_uniforms(42, 2, 8, 4)],
+            "isingp_uniforms(42,3,32,2,2)": O.isingp_uniforms(42, 3, 32, 2, 2).tolist()}
 
 
 def generate():
     from oracle import oracle as O
     O.build()
     return {"provenance": "CPU oracle (oracle/oracle.c + oracle/rng_contract.c); the reference has no golden vectors and cannot run here",
-            "ising": ising_cases(O), "clock": clock_cases(O), "sixclock": sixclock_cases(O), "xy": xy_cases(O), "rng": rng_cases(O)}
+            "ising": ising_cases(O), "ising_torus": torus_cases(O), "clock": clock_cases(O), "sixclock": sixclock_cases(O), "xy": xy_cases(O), "rng": rng_cases(O)}
 
 
 if __name__ == "__main__":

@@ -47,3 +47,21 @@ def test_c_driver_loop_equals_oracle(oracle, tmp_path, dim, shape, kbt, start):
     for i in range(mcs):
         o.update()
         assert [int(x) for x in lines[i].split()] == [i + 1, o.calc_energy_sum(), o.calc_magne_sum()]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,kbt,start", [((1024, 8, 4), 4.51152, "random"), ((64, 6, 4), 4.51152, "allup"), ((96, 10, 0), 2.26918531421, "random")])
+def test_c_driver_loop_on_the_torus_equals_oracle(oracle, tmp_path, shape, kbt, start):
+    exe = _build(tmp_path)
+    mcs = 6
+    dim = -3 if shape[2] else -2
+    r = subprocess.run([exe, str(dim), str(shape[0]), str(shape[1]), str(shape[2]), repr(kbt), "42", str(mcs), start], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == mcs + 1 and lines[-1].startswith("launches ")
+    o = oracle.ising_periodic_gpu().init(*shape, kbt, 42)
+    if start == "random":
+        o.set_random_spin()
+    for i in range(mcs):
+        o.update()
+        assert [int(x) for x in lines[i].split()] == [i + 1, *o.measure()]

@@ -20,6 +20,7 @@ def test_oracle_reproduces_golden(oracle):
     spec.loader.exec_module(mg)
     want, got = _golden(), mg.generate()
     assert got["ising"] == want["ising"]                      # integers + hashes: exact
+    assert got["ising_torus"] == want["ising_torus"]
     for key in ("clock", "sixclock"):
         for a, b in zip(got[key], want[key]):
             assert a["hist"] == b["hist"]

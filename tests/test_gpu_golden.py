@@ -34,6 +34,20 @@ def test_ising_golden():
         assert s[:24].tolist() == c["spins_head"] and _sha(s) == c["spins_sha256"], c
 
 
+def test_ising_torus_golden():
+    from cuda_fortran_mc_simulation_spin_b200 import ising_periodic_gpu_m
+    for c in _golden()["ising_torus"]:
+        g = ising_periodic_gpu_m.ising_periodic_gpu().init(*c["shape"], c["kbt"], c["seed"])
+        g.set_method(c["method"])
+        if c["start"] == "random":
+            g.set_random_spin()
+        for e, m in c["em"]:
+            g.update()
+            assert g.measure() == (e, m), c
+        s = g.spins()
+        assert s[:24].tolist() == c["spins_head"] and _sha(s) == c["spins_sha256"], c
+
+
 def test_clock_golden():
     from cuda_fortran_mc_simulation_spin_b200 import clock_gpu_m, clock_gpu_multi_m
     for c in _golden()["clock"]:
