@@ -150,6 +150,9 @@ __device__ __forceinline__ void torus_finish_sums(const RingPassArgs& a, uint32_
                             // the 15 MB window of the other colour and the dirty lines of the own one, and 14 % more DRAM reads than the
                             // algorithmic figure.  Measured at 1024^3: 0 -> 1705, 256 -> 1740, 512 -> 1748, 768..1536 -> 1757 flips/ns
 #endif
+#ifndef TORUS_RC2D
+#define TORUS_RC2D 1        // 2D: kernels with the row pitch of 16384^2 / 65536^2 compiled in
+#endif
 #ifndef TORUS_SPLIT_DEFAULT
 #define TORUS_SPLIT_DEFAULT 0
 #endif
@@ -683,7 +686,12 @@ int torus_launch_pass(Torus* m, int colour, bool fuse, bool fuse_next)
         const int64_t need = ((int64_t)t.ntickets + 7) / 8;
         const int grid = (int)(need < (int64_t)m->grid ? need : (int64_t)m->grid);
 #define SPASS(METHOD, MEAS, ROWS, RC) torus_strip_kernel<NNB, METHOD, MEAS, ROWS, RC><<<grid, 256, 0, m->stream>>>(t, m->tabs.tab)
-#define SPASS2(METHOD, MEAS) do { if (m->rows == TORUS_ROWS) { if (m->R == 32) SPASS(METHOD, MEAS, TORUS_ROWS, 32); else SPASS(METHOD, MEAS, TORUS_ROWS, 0); } else SPASS(METHOD, MEAS, 2, 0); } while (0)
+        // row pitch as a compile-time constant for the sizes the benchmarks use (3D: nx = 1024; 2D: 16384, 65536), else a kernel argument
+#define SPASS2(METHOD, MEAS) do { if (m->rows == TORUS_ROWS) { \
+            if (m->R == 32) SPASS(METHOD, MEAS, TORUS_ROWS, 32); \
+            else if (TORUS_RC2D && NNB == 4 && m->R == 512) SPASS(METHOD, MEAS, TORUS_ROWS, (NNB == 4 && TORUS_RC2D ? 512 : 0)); \
+            else if (TORUS_RC2D && NNB == 4 && m->R == 2048) SPASS(METHOD, MEAS, TORUS_ROWS, (NNB == 4 && TORUS_RC2D ? 2048 : 0)); \
+            else SPASS(METHOD, MEAS, TORUS_ROWS, 0); } else SPASS(METHOD, MEAS, 2, 0); } while (0)
         if (m->method == METHOD_METROPOLIS) { if (fuse) SPASS2(METHOD_METROPOLIS, true); else SPASS2(METHOD_METROPOLIS, false); }
         else { if (fuse) SPASS2(METHOD_HEATBATH, true); else SPASS2(METHOD_HEATBATH, false); }
 #undef SPASS2

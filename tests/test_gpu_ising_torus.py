@@ -13,7 +13,8 @@ KBT3, KBT2 = 4.51152, 2.26918531421
 
 # (nx, ny, nz); nz = 0 -> 2D.  nx = 1024: one strip per row; 2048: two strips (edge bytes from memory); ny % 8 != 0: 2-row tickets
 SHAPES = [(32, 2, 2), (64, 6, 4), (96, 10, 6), (32, 4, 0), (160, 18, 0),
-          (1024, 8, 4), (1024, 6, 2), (2048, 16, 2), (1024, 24, 0), (2048, 10, 0), (3072, 8, 0)]
+          (1024, 8, 4), (1024, 6, 2), (2048, 16, 2), (1024, 24, 0), (2048, 10, 0), (3072, 8, 0),
+          (16384, 8, 0), (65536, 8, 0)]   # the 2D kernels with the row pitch compiled in (R = 512, 2048)
 
 
 def _pair(oracle, shape, seed=42):
