@@ -24,6 +24,7 @@
 // ising_kernels.cuh, unchanged: RNG contract = the ring models' with (position, lane) = (vector index, byte).
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include <new>
 #include <vector>
 #include "../../include/b200mc.h"
@@ -446,6 +447,41 @@ __global__ void torus_import_kernel(uint8_t* c0, uint8_t* c1, int64_t nx, int64_
     (((x + y + z + z0) & 1) ? c1 : c0)[row * (nx / 2) + (x >> 1)] = pm1 ? (uint8_t)(in[i] > 0) : (uint8_t)in[i];
 }
 
+// ---- slab mode, direct transport: ghost planes over peer memory ------------------------------------------------------
+// After a colour pass every rank stores its first owned plane of the colour into the ghost plane above rank - 1's slab and
+// its last owned plane into the ghost plane below rank + 1's (arrays mapped with CUDA IPC, stores over NVLink), then the
+// last block to finish publishes a sequence number in both neighbours' flag words (system-scope release) and waits for
+// theirs: when the kernel ends, the ghost planes the next pass reads have landed.  No NCCL kernel (which cannot run beside
+// or right behind the pass without a launch of its own and a rendezvous), no host synchronisation.  Only the boundary
+// planes of a neighbour's pass read its ghost planes, and that pass finished before this rank could start the pass whose
+// results it pushes here (it waited for that neighbour's previous flag): no write-after-read hazard.
+__global__ void __launch_bounds__(256)
+torus_push_kernel(const uint4* __restrict__ first, const uint4* __restrict__ last, uint4* __restrict__ prev_high, uint4* __restrict__ next_low,
+                  int64_t nplane, unsigned int* done, unsigned int* sig_prev, unsigned int* sig_next, const unsigned int* wait_prev,
+                  const unsigned int* wait_next, unsigned int seq)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * nplane; i += stride) {
+        if (i < nplane) prev_high[i] = first[i];
+        else next_low[i - nplane] = last[i - nplane];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(done, 1u) == gridDim.x - 1u) {
+        *done = 0u;
+        __threadfence_system();
+        st_release_sys(sig_prev, seq);
+        st_release_sys(sig_next, seq);
+        // (bounded: a neighbour that never arrives -- a rank that died -- aborts this kernel after a few seconds instead of hanging the GPU)
+        unsigned int spins = 0;
+        while ((int)(ld_acquire_sys(wait_prev) - seq) < 0) { __nanosleep(200); if (++spins > (1u << 25)) __trap(); }
+        while ((int)(ld_acquire_sys(wait_next) - seq) < 0) { __nanosleep(200); if (++spins > (1u << 25)) __trap(); }
+    }
+}
+
+#define TORUS_FLAG_WORDS 512   // own flag buffer: word 32 (2 colour + side) = pushes received from prev (side 0) / next (side 1); word 256 = finished blocks
+#define TORUS_IPC_BYTES 192
+
 #define TORUS_MAGIC 0x544F5255
 
 struct Torus {
@@ -462,6 +498,14 @@ struct Torus {
     void* comm;
     cudaStream_t comm_stream;
     cudaEvent_t ev_boundary, ev_halo;
+    // direct transport (CUDA IPC): the neighbours' colour arrays and flag words
+    bool p2p;
+    unsigned int* flags;
+    uint4* peer_alloc[2][2];       // [prev / next][colour]
+    unsigned int* peer_flags[2];
+    void* peer_maps[6];
+    int n_peer_maps;
+    unsigned int push_seq[2];
     bool split;             // slab pass = boundary planes, then exchange beside the interior planes (else: one launch, then the exchange)
     cudaStream_t stream;
     double beta;
@@ -488,6 +532,8 @@ int torus_destroy(Torus* m)
 {
     if (!m) return B200MC_OK;
     cudaFree(m->alloc[0]); cudaFree(m->alloc[1]); cudaFree(m->d_acc);
+    for (int i = 0; i < m->n_peer_maps; ++i) cudaIpcCloseMemHandle(m->peer_maps[i]);
+    cudaFree(m->flags);
     if (m->comm) dist_comm_destroy(m->comm);
     if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
     if (m->ev_boundary) cudaEventDestroy(m->ev_boundary);
@@ -537,6 +583,7 @@ int torus_create(void** out, int ndim, int64_t nx, int64_t ny, int64_t nz, doubl
     m->vec[0] = m->vec[1] = m->alloc[0] = m->alloc[1] = nullptr;
     m->rank = rank; m->nranks = nranks; m->z0 = (int64_t)rank * nz; m->nz_glob = nz_glob; m->N_glob = nx * ny * nz_glob;
     m->comm = nullptr; m->comm_stream = nullptr; m->ev_boundary = m->ev_halo = nullptr;
+    m->p2p = false; m->flags = nullptr; m->n_peer_maps = 0; m->push_seq[0] = m->push_seq[1] = 0;
     { const char* ts = getenv("B200MC_TORUS_SPLIT"); m->split = ts ? atoi(ts) != 0 : TORUS_SPLIT_DEFAULT; }
     m->stream = 0; m->beta = 1 / kbt; m->seed = (uint32_t)iseed; m->draw = 0; m->method = METHOD_METROPOLIS;
     m->d_acc = nullptr; m->h_acc = nullptr; m->d_ticket = nullptr; m->d_io = nullptr; m->d_randoms = nullptr;
@@ -614,6 +661,23 @@ void torus_args(Torus* m, int colour, TorusArgs& t)
 
 // slab mode: my first owned plane of `colour` becomes the ghost plane above rank - 1's slab, my last owned plane the ghost
 // plane below rank + 1's (ring of ranks: the torus closes between rank P - 1 and rank 0)
+int torus_push(Torus* m, int colour, cudaStream_t st)
+{
+    const int64_t plane = (int64_t)m->R * m->ny;
+    const uint4* v = m->vec[colour];
+    const unsigned int seq = ++m->push_seq[colour];
+    COUNT_LAUNCH();
+    torus_push_kernel<<<64, 256, 0, st>>>(v, v + (m->nz - 1) * plane,
+                                          m->peer_alloc[0][colour] + plane + m->nvec,   // rank - 1: the ghost plane above its owned planes
+                                          m->peer_alloc[1][colour],                     // rank + 1: the ghost plane below
+                                          plane, m->flags + 256,
+                                          m->peer_flags[0] + 32 * (2 * colour + 1),     // I am rank - 1's "next"
+                                          m->peer_flags[1] + 32 * (2 * colour + 0),     // and rank + 1's "prev"
+                                          m->flags + 32 * (2 * colour + 0), m->flags + 32 * (2 * colour + 1), seq);
+    CK(cudaGetLastError());
+    return B200MC_OK;
+}
+
 int torus_halo(Torus* m, int colour, cudaStream_t st)
 {
     const int64_t plane = (int64_t)m->R * m->ny;
@@ -672,7 +736,7 @@ int torus_launch_pass(Torus* m, int colour, bool fuse, bool fuse_next)
             }
         }
         if (m->split) CK(cudaStreamWaitEvent(m->stream, m->ev_halo, 0));
-        else { const int rc = torus_halo(m, colour, m->stream); if (rc) return rc; }
+        else { const int rc = m->p2p ? torus_push(m, colour, m->stream) : torus_halo(m, colour, m->stream); if (rc) return rc; }
         if (m->timing) { CK(cudaEventRecord(m->evs[m->ev_used + 1], m->stream)); m->ev_used += 2; }
         return B200MC_OK;
     }
@@ -840,6 +904,58 @@ int b200mc_ising_torus_create_slab(void** h, int32_t ndim, int64_t nx, int64_t n
 {
     return torus_create(h, ndim, nx, ny, nz, kbt, iseed, rank, nranks, nccl_id);
 }
+int b200mc_ising_torus_p2p_handles(void* h, char out[192])
+{
+    CHECK_T(h);
+    Torus* m = T(h);
+    if (m->nranks < 2) ARG_FAIL("p2p_handles: not a slab handle");
+    if (!m->flags) {
+        CK(cudaMalloc(&m->flags, TORUS_FLAG_WORDS * sizeof(unsigned int)));
+        CK(cudaMemset(m->flags, 0, TORUS_FLAG_WORDS * sizeof(unsigned int)));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) * 3 == TORUS_IPC_BYTES, "cudaIpcMemHandle_t size");
+    cudaIpcMemHandle_t hd[3];
+    CK(cudaIpcGetMemHandle(&hd[0], m->alloc[0]));
+    CK(cudaIpcGetMemHandle(&hd[1], m->alloc[1]));
+    CK(cudaIpcGetMemHandle(&hd[2], m->flags));
+    memcpy(out, hd, TORUS_IPC_BYTES);
+    return B200MC_OK;
+}
+int b200mc_ising_torus_p2p_connect(void* h, const char prev[192], const char next[192])
+{
+    CHECK_T(h);
+    Torus* m = T(h);
+    if (m->nranks < 2) ARG_FAIL("p2p_connect: not a slab handle");
+    if (!m->flags) ARG_FAIL("p2p_connect: call p2p_handles first");
+    const char* src[2] = {prev, next};
+    const int nopen = m->nranks == 2 ? 1 : 2;   // with two ranks both neighbours are the same process
+    for (int side = 0; side < nopen; ++side) {
+        cudaIpcMemHandle_t hd[3];
+        memcpy(hd, src[side], TORUS_IPC_BYTES);
+        void* ptr[3] = {nullptr, nullptr, nullptr};
+        for (int j = 0; j < 3; ++j) {
+            const cudaError_t e = cudaIpcOpenMemHandle(&ptr[j], hd[j], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                snprintf(g_b200mc_err, sizeof(g_b200mc_err), "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+                cudaGetLastError();
+                for (int i = 0; i < m->n_peer_maps; ++i) cudaIpcCloseMemHandle(m->peer_maps[i]);
+                m->n_peer_maps = 0;
+                return B200MC_ERR_UNSUPPORTED;
+            }
+            m->peer_maps[m->n_peer_maps++] = ptr[j];
+        }
+        m->peer_alloc[side][0] = (uint4*)ptr[0];
+        m->peer_alloc[side][1] = (uint4*)ptr[1];
+        m->peer_flags[side] = (unsigned int*)ptr[2];
+    }
+    if (nopen == 1) {
+        m->peer_alloc[1][0] = m->peer_alloc[0][0];
+        m->peer_alloc[1][1] = m->peer_alloc[0][1];
+        m->peer_flags[1] = m->peer_flags[0];
+    }
+    m->p2p = true;
+    return B200MC_OK;
+}
 int b200mc_ising_torus_rank_info(void* h, int32_t* rank, int32_t* nranks, int64_t* z0, int64_t* nz_local)
 {
     CHECK_T(h);
@@ -867,9 +983,12 @@ int b200mc_ising_torus_set_allup_spin(void* h)
 {
     CHECK_T(h);
     T(h)->obs_valid = false; T(h)->fused_pending = false;
-    const size_t ghost = T(h)->nranks > 1 ? (size_t)T(h)->R * T(h)->ny : 0;   // (all up: the ghost planes too, no exchange needed)
-    CK(cudaMemsetAsync(T(h)->alloc[0], 1, ((size_t)T(h)->nvec + 2 * ghost) * 16, T(h)->stream));
-    CK(cudaMemsetAsync(T(h)->alloc[1], 1, ((size_t)T(h)->nvec + 2 * ghost) * 16, T(h)->stream));
+    // slab mode: the owned planes only; the ghost planes are refreshed through the two-sided exchange, so that no neighbour can
+    // push into a ghost plane this rank is about to overwrite (direct transport)
+    CK(cudaMemsetAsync(T(h)->vec[0], 1, (size_t)T(h)->nvec * 16, T(h)->stream));
+    CK(cudaMemsetAsync(T(h)->vec[1], 1, (size_t)T(h)->nvec * 16, T(h)->stream));
+    if (T(h)->nranks > 1)
+        for (int c = 0; c < 2; ++c) { const int rc = torus_halo(T(h), c, T(h)->stream); if (rc) return rc; }
     return B200MC_OK;
 }
 int b200mc_ising_torus_set_random_spin(void* h) { CHECK_T(h); return torus_set_random(T(h)); }

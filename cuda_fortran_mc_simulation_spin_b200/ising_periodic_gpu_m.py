@@ -8,6 +8,7 @@ those types; host arrays are ``s[z][y][x]`` without halo cells.  ``nx % 32 == 0`
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -66,7 +67,31 @@ class ising_periodic_gpu:
         _lib.check(f(C.byref(self._h), 3, int(nx), int(ny), int(nz), float(kbt), int(iseed), rank, nranks, bytes(box[0])))
         self._group, self._dist = group, dist
         self._dims = (int(nz), int(ny), int(nx))
+        self._p2p = False
+        if os.environ.get("B200MC_SLAB_TRANSPORT", "p2p") != "nccl":
+            self._connect_p2p(dist, group, rank, nranks)
         return self
+
+    def _connect_p2p(self, dist, group, rank, nranks):
+        """direct transport: exchange the CUDA IPC handles and map the two neighbours' arrays; every rank falls back to the NCCL
+        transport if any rank cannot export or map"""
+        buf = C.create_string_buffer(192)
+        ok = 1
+        try:
+            self._call("p2p_handles", buf, argtypes=(C.c_char_p,))
+        except _lib.B200MCError:
+            ok = 0
+        allh = [None] * nranks
+        dist.all_gather_object(allh, (ok, buf.raw), group=group)
+        if not all(o for o, _ in allh):
+            return
+        prev, nxt = allh[(rank - 1) % nranks][1], allh[(rank + 1) % nranks][1]
+        rc = self._f("p2p_connect", C.c_int, P, C.c_char_p, C.c_char_p)(self._h, prev, nxt)
+        oks = [None] * nranks
+        dist.all_gather_object(oks, rc == 0, group=group)
+        if not all(oks):
+            raise _lib.B200MCError("CUDA IPC mapping of the neighbour slabs failed on some rank; rerun with B200MC_SLAB_TRANSPORT=nccl")
+        self._p2p = True
 
     def rank_info(self):
         """(rank, nranks, first owned plane, owned planes)"""

@@ -241,6 +241,12 @@ int b200mc_ising_torus_create(void** h, int32_t ndim, int64_t nx, int64_t ny, in
  * (nx ny nz_local values, planes z0 .. z0 + nz_local - 1); nall / nz report the whole lattice. */
 int b200mc_ising_torus_create_slab(void** h, int32_t ndim, int64_t nx, int64_t ny, int64_t nz, double kbt, int32_t iseed, int32_t rank, int32_t nranks, const char nccl_id[128]);
 int b200mc_ising_torus_rank_info(void* h, int32_t* rank, int32_t* nranks, int64_t* z0, int64_t* nz_local);
+/* direct transport for the ghost planes (as b200mc_ising3d_p2p_handles / _p2p_connect): export this rank's CUDA IPC handles
+ * (192 bytes), exchange them by any means, map the two neighbours'; the ghost planes are then stored straight into the
+ * neighbours' arrays over NVLink by a small kernel after every colour pass instead of travelling by ncclSend/Recv.
+ * Either every rank connects or none does. */
+int b200mc_ising_torus_p2p_handles(void* h, char out[192]);
+int b200mc_ising_torus_p2p_connect(void* h, const char prev[192], const char next[192]);
 int b200mc_ising_torus_destroy(void* h);
 int b200mc_ising_torus_set_stream(void* h, void* cuda_stream);
 int b200mc_ising_torus_skip_curand(void* h, int64_t n_skip);     /* src/ising3d_gpu_m.f90:72-77 */
