@@ -667,7 +667,7 @@ int torus_push(Torus* m, int colour, cudaStream_t st)
     const uint4* v = m->vec[colour];
     const unsigned int seq = ++m->push_seq[colour];
     COUNT_LAUNCH();
-    torus_push_kernel<<<64, 256, 0, st>>>(v, v + (m->nz - 1) * plane,
+    torus_push_kernel<<<296, 256, 0, st>>>(v, v + (m->nz - 1) * plane,
                                           m->peer_alloc[0][colour] + plane + m->nvec,   // rank - 1: the ghost plane above its owned planes
                                           m->peer_alloc[1][colour],                     // rank + 1: the ghost plane below
                                           plane, m->flags + 256,
