@@ -223,7 +223,7 @@ int b200mc_ising2dp_set_timing(void* h, int32_t on);
 int b200mc_ising2dp_get_timing(void* h, int64_t* launches, double* total_ms);
 
 /* ------------------------------------------------------------------------
- * Ising 2D / 3D with TRUE PERIODIC boundaries (torus), int8, Metropolis / heat-bath, one GPU.
+ * Ising 2D / 3D with TRUE PERIODIC boundaries (torus), int8, Metropolis / heat-bath; one GPU or (3D) slabs of planes.
  * No reference module: the reference's Ising types are helical and valid for odd nx only
  * (src/ising3d_gpu_m.f90:60-62,196, src/ising2d_gpu_m.f90:56-58), so L = 1024^3 -- the size
  * BASELINE.json's north_star and BASELINE.md C2 / C1 / C5 name ("1024^3 periodic", "1024^2 periodic",
