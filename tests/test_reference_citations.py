@@ -1,0 +1,85 @@
+"""CPU, only where /root/reference exists (this container; skipped on the GPU box): the reference statements the oracle
+restates, at the file:line the oracle cites, still read the way the restatement assumes -- the comparison operators of the
+accept tests (`>` return, `>=` in the batched clock), the proposal roundings (`floor`, `ceiling`), the neighbour sets, the halo
+copies, the observable sums -- and oracle/oracle.c uses the same operators.  The reference has no tests or golden vectors and
+cannot be built here (no Fortran compiler): this ties the restatement to the reference's TEXT, the one artefact available.
+Whitespace is ignored in the comparison."""
+import os
+import re
+
+import pytest
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src")), reason="the reference checkout is not present")
+
+
+def _norm(s):
+    return re.sub(r"\s+", "", s.replace("&", ""))
+
+
+def _lines(path, lo, hi):
+    with open(os.path.join(REF, path)) as f:
+        src = f.read().splitlines()
+    return _norm("".join(src[lo - 1:hi]))
+
+
+# (file, first line, last line, statements that must appear in that range)
+CITED = [
+    # Ising 2D: table, delta energy, accept test, flip, halo, random start, observables
+    ("src/ising2d_gpu_m.f90", 126, 130, ["this%exparr_(:)=1.0_real64", "this%exparr_(diff)=exp(-this%beta()*diff)"]),
+    ("src/ising2d_gpu_m.f90", 191, 196, ["res=2*spins(idx)*(spins(idx+1)+spins(idx-1)+spins(idx+nx)+spins(idx-nx))"]),
+    ("src/ising2d_gpu_m.f90", 155, 161, ["idx=2*((blockIdx%x-1)*blockDim%x+threadIdx%x)-2+offset", "if(randoms(idx)>exparr(delta_energy))return",
+                                         "spins(idx)=-spins(idx)"]),
+    ("src/ising2d_gpu_m.f90", 100, 106, ["spins(nall+idx)=spins(idx)", "spins(idx-nx)=spins(nall-nx+idx)"]),
+    ("src/ising2d_gpu_m.f90", 83, 83, ["spins(idx)=merge(1,-1,randoms(idx)<0.5_real64)"]),
+    ("src/ising2d_gpu_m.f90", 205, 228, ["res=res-int(spins(i)*(spins(i+1)+spins(i+this%nx_)),int64)", "res=res+spins(i)"]),
+    # Ising 3D
+    ("src/ising3d_gpu_m.f90", 196, 205, ["spins(idx-1)+spins(idx+1)+spins(idx-nx)+spins(idx+nx)+spins(idx-nxy)+spins(idx+nxy)",
+                                         "if(randoms(idx)>ws(sum_spin,spins(idx)))return", "spins(idx)=1-spins(idx)"]),
+    ("src/ising3d_gpu_m.f90", 153, 171, ["e1=this%energy_table_(s1,0)+this%energy_table_(s2,0)", "this%ws_(s1+s2,0)=min(1.0_real64,exp(-this%beta_*(e2-e1)))",
+                                         "this%ws_(s1+s2,1)=min(1.0_real64,exp(-this%beta_*(e1-e2)))"]),
+    ("src/ising3d_gpu_m.f90", 111, 122, ["spins(nall+idx)=spins(idx)", "spins(idx-nxy)=spins(nall-nxy+idx)"]),
+    ("src/ising3d_gpu_m.f90", 99, 99, ["spins(idx)=merge(1,0,randoms(idx)<0.5_real64)"]),
+    ("src/ising3d_gpu_m.f90", 245, 276, ["res=res+energy_table(spins(i+1)+spins(i+this%nx_)+spins(i+this%nxy_),spins(i))", "res=res+spins(i)"]),
+    # clock, helical: proposal floor(u q), accept `>` return (single) and `>=` return (batched)
+    ("src/clock_gpu_m.f90", 211, 215, ["next_state=floor(next_states(idx)*max_state)",
+                                       "if(randoms(idx)>ws(spins(idx+nx),spins(idx-nx),spins(idx-1),spins(idx+1),spins(idx),next_state))return",
+                                       "spins(idx)=next_state"]),
+    ("src/clock_gpu_multi_m.f90", 230, 235, ["next_state=floor(next_states(idx_x,idx_y)*max_state)", "if(randoms(idx_x,idx_y)>=ws("]),
+    ("src/clock_gpu_m.f90", 103, 103, ["spins(idx)=floor(randoms(idx)*max_state)"]),
+    # clock, periodic tableall / dual lattice: new = c + ceiling(u1 (q - 1)), accept iff u2 <= prob
+    ("src/clock/clock_tableall_gpu_m.f90", 140, 150, ["new_state=sixclock(x,y)+ceiling(rnds(1,x,y)*(mstate-1))", "if(rnds(2,x,y)<=prob)"]),
+    ("src/clock/clock_dual_lattice_tableall_m.f90", 142, 153, ["ceiling(rnds(1,actual_x,y)*(mstate-1))", "if(rnds(2,actual_x,y)<=prob)"]),
+    # XY periodic: candidate, delta energy, accept, over-relaxation
+    ("src/xy2d_periodic_gpu_m.f90", 382, 385, ["candidate(1:2)=[cos(2*pi*candidates(x,y)),sin(2*pi*candidates(x,y))]",
+                                               "if(randoms(x,y)>exp(-beta*delta_energy))return"]),
+    ("src/xy2d_periodic_gpu_m.f90", 390, 397, ["center_diff=candidate(:)-spins(x,y,:)", "neighbor_summ=spins(x+1,y,:)+spins(x-1,y,:)+spins(x,y+1,:)+spins(x,y-1,:)",
+                                               "res=-(center_diff(1)*neighbor_summ(1)+center_diff(2)*neighbor_summ(2))"]),
+    ("src/xy2d_periodic_gpu_m.f90", 426, 438, ["abs_local_field_inv=1/hypot(local_field(1),local_field(2))",
+                                               "spins(x,y,1:2)=(2*sum(local_field(1:2)*spins(x,y,1:2)))*local_field(1:2)-spins(x,y,1:2)",
+                                               "spins(x,y,1:2)=spins(x,y,1:2)/rabs"]),
+    ("src/xy2d_periodic_gpu_m.f90", 121, 121, ["spins(x,y,:)=[cos(2*pi*randoms(x,y)),sin(2*pi*randoms(x,y))]"]),
+]
+
+
+@pytest.mark.parametrize("path,lo,hi,stmts", CITED, ids=[f"{c[0].split('/')[-1]}:{c[1]}" for c in CITED])
+def test_cited_reference_lines_read_as_restated(path, lo, hi, stmts):
+    text = _lines(path, lo, hi)
+    for s in stmts:
+        assert _norm(s) in text, (path, lo, hi, s)
+
+
+def test_oracle_uses_the_reference_operators():
+    """the same statements in oracle/oracle.c: `>` skips (accept iff u <= w), `>=` in the batched clock, floor / ceil proposals"""
+    c = _norm(open(os.path.join(ROOT, "oracle", "oracle.c")).read())
+    for s in ["if(randoms[idx-1]>ws[sum_spin+7*I3(idx)])continue;",           # src/ising3d_gpu_m.f90:203
+              "I3(idx)=1-I3(idx);",                                             # :205
+              "I3(nall+idx)=I3(idx);", "I3(idx-nxy)=I3(nall-nxy+idx);",         # :119-121
+              "(randoms[idx-1]<0.5)?1:0",                                       # :99
+              "(randoms[idx-1]<0.5)?1:-1"]:                                     # src/ising2d_gpu_m.f90:83
+        assert _norm(s) in c, s
+    assert re.search(r"floor\(", c) and re.search(r"ceil\(", c)
+    # the batched clock's strict comparison is a separate code path (`>=` return <=> accept iff u < w)
+    assert ">=" in c
