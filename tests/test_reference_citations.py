@@ -83,3 +83,43 @@ def test_oracle_uses_the_reference_operators():
     assert re.search(r"floor\(", c) and re.search(r"ceil\(", c)
     # the batched clock's strict comparison is a separate code path (`>=` return <=> accept iff u < w)
     assert ">=" in c
+
+
+# ---- the drop-in boundary: module, type and procedure names of the shims against the reference's own modules ----
+SHIMS = os.path.join(ROOT, "cuda_fortran_mc_simulation_spin_b200", "fortran")
+TYPED = [("src/ising2d_gpu_m.f90", "ising2d_gpu_m.f90"), ("src/ising3d_gpu_m.f90", "ising3d_gpu_m.f90"),
+         ("src/clock_gpu_m.f90", "clock_gpu_m.f90"), ("src/clock_gpu_multi_m.f90", "clock_gpu_multi_m.f90"),
+         ("src/xy2d_periodic_gpu_m.f90", "xy2d_periodic_gpu_m.f90"), ("src/xy2d_gpu_m.f90", "xy2d_gpu_m.f90")]
+PROCEDURAL = [("src/clock/clock_tableall_gpu_m.f90", "clock/clock_tableall_gpu_m.f90"),
+              ("src/clock/clock_dual_lattice_tableall_m.f90", "clock/clock_dual_lattice_tableall_m.f90"),
+              ("src/clock/clock_table_gpu_m.f90", "clock/clock_table_gpu_m.f90"),
+              ("src/clock/clock_simple_gpu_m.f90", "clock/clock_simple_gpu_m.f90")]
+
+
+def _interface(src):
+    """(module name, public type names, public type-bound procedure names, names on `public ::` lines)"""
+    mod = re.search(r"^\s*module\s+(\w+)", src, flags=re.M | re.I).group(1).lower()
+    types = {m.lower() for m in re.findall(r"^\s*type\s*(?:,\s*public\s*)?::\s*(\w+)", src, flags=re.M | re.I)}
+    bound = set()
+    for m in re.finditer(r"^\s*procedure\s*,\s*pass\s*(,\s*private\s*)?::\s*(\w+)", src, flags=re.M | re.I):
+        if not m.group(1):
+            bound.add(m.group(2).lower())
+    public = set()
+    for m in re.finditer(r"^\s*(?:[\w()=, ]*,\s*)?public\s*(?:,\s*protected\s*)?::\s*(.+)$", src, flags=re.M | re.I):
+        for name in re.split(r",", re.sub(r"=[^,]*", "", m.group(1))):
+            name = name.strip().split("!")[0].strip()
+            if re.fullmatch(r"\w+", name):
+                public.add(name.lower())
+    return mod, types, bound, public
+
+
+@pytest.mark.parametrize("ref,shim", TYPED + PROCEDURAL, ids=[s for _, s in TYPED + PROCEDURAL])
+def test_shim_keeps_the_reference_interface(ref, shim):
+    """same module name; every public type, every public type-bound procedure and every name the reference module makes public
+    exists under the same name in the shim (the shims add procedures, they never rename or drop one)"""
+    rmod, rtypes, rbound, rpublic = _interface(open(os.path.join(REF, ref)).read())
+    smod, stypes, sbound, spublic = _interface(open(os.path.join(SHIMS, shim)).read())
+    assert smod == rmod
+    assert rtypes & rpublic <= stypes, (rtypes & rpublic) - stypes
+    assert rbound <= sbound, sorted(rbound - sbound)
+    assert rpublic <= spublic | stypes, sorted(rpublic - spublic - stypes)
