@@ -123,3 +123,48 @@ def test_shim_keeps_the_reference_interface(ref, shim):
     assert rtypes & rpublic <= stypes, (rtypes & rpublic) - stypes
     assert rbound <= sbound, sorted(rbound - sbound)
     assert rpublic <= spublic | stypes, sorted(rpublic - spublic - stypes)
+
+
+def _signatures(src):
+    """public type-bound procedure -> (subroutine | function, result type, dummy argument names, {argument: (type + attributes, shape)})"""
+    src = re.sub(r"&\s*\n\s*&?", "", src)
+    bound = {m.group(2).lower(): m.group(3).lower()
+             for m in re.finditer(r"^\s*procedure\s*,\s*pass\s*(,\s*private\s*)?::\s*(\w+)\s*=>\s*(\w+)", src, flags=re.M | re.I) if not m.group(1)}
+    out = {}
+    for name, impl in bound.items():
+        m = re.search(r"^[^\n!]*(subroutine|function)\s+" + impl + r"\s*\(([^)]*)\)[^\n]*\n(.*?)^\s*end\s+(subroutine|function)", src,
+                      flags=re.I | re.S | re.M)
+        if not m:
+            continue
+        head = m.group(0).split("\n")[0].lower()
+        args = [a.strip().lower() for a in m.group(2).split(",")]
+        decl = {}
+        for line in m.group(3).split("\n"):
+            mm = re.match(r"\s*([^!:]+?)\s*::\s*([^!]+)", line)
+            if not mm:
+                continue
+            typ = re.sub(r"\s+", "", mm.group(1).lower())
+            for v in re.split(r",(?![^()]*\))", mm.group(2)):
+                v = re.sub(r"\s+", "", v.lower())
+                b = re.match(r"\w+", v)
+                if b and b.group(0) in args and b.group(0) not in decl:     # the first declaration: contained procedures reuse names
+                    decl[b.group(0)] = (typ, v[len(b.group(0)):])
+        res = re.search(r"(integer\(\w+\)|real\(\w+\)|logical)\s+function", head)
+        out[name] = (m.group(1).lower(), res.group(1) if res else None, args, decl)
+    return out
+
+
+@pytest.mark.parametrize("ref,shim", TYPED, ids=[s for _, s in TYPED])
+def test_shim_procedures_keep_the_reference_signatures(ref, shim):
+    """every public type-bound procedure of the reference: same kind (subroutine / function), same result type, same dummy
+    argument names in the same order, same declared type, kind, intent and shape for every argument but the passed object"""
+    a = _signatures(open(os.path.join(REF, ref)).read())
+    b = _signatures(open(os.path.join(SHIMS, shim)).read())
+    assert len(a) >= 10
+    for name, (kind, res, args, decl) in a.items():
+        assert name in b, name
+        kind2, res2, args2, decl2 = b[name]
+        assert (kind, res, args) == (kind2, res2, args2), (name, (kind, res, args), (kind2, res2, args2))
+        for arg, t in decl.items():
+            if arg != "this":
+                assert decl2.get(arg) == t, (name, arg, t, decl2.get(arg))
