@@ -60,6 +60,19 @@ CITED = [
     ("src/xy2d_periodic_gpu_m.f90", 426, 438, ["abs_local_field_inv=1/hypot(local_field(1),local_field(2))",
                                                "spins(x,y,1:2)=(2*sum(local_field(1:2)*spins(x,y,1:2)))*local_field(1:2)-spins(x,y,1:2)",
                                                "spins(x,y,1:2)=spins(x,y,1:2)/rabs"]),
+    # clock tables (loop nest order and the floating-point expression order are what the oracle copies)
+    ("src/clock_gpu_m.f90", 105, 146, ["docenter_after=0,this%max_state_-1docenter_before=0,this%max_state_-1dol=0,this%max_state_-1dok=0,this%max_state_-1doj=0,this%max_state_-1doi=0,this%max_state_-1",
+                                       "delta_e=(energy_table(i,j,center_after)+energy_table(k,l,center_after))-(energy_table(i,j,center_before)+energy_table(k,l,center_before))",
+                                       "if(delta_e<=0.0_real64)then", "ws(i,j,k,l,center_before,center_after)=exp(-this%beta_*delta_e)",
+                                       "res=-sum(cos(this%pi_state_inv_*[i-center,j-center]))"]),
+    ("src/clock/clock_tableall_gpu_m.f90", 66, 86, ["delta_e=state_center_right_up_to_energy(new_c,r,u)-state_center_right_up_to_energy(c,r,u)+state_center_right_up_to_energy(new_c,l,d)-state_center_right_up_to_energy(c,l,d)",
+                                                    "if(delta_e<=0d0)then", "probability_h(c,new_c,r,u,l,d)=exp(-beta*delta_e)"]),
+    # clock and XY observables
+    ("src/clock_gpu_m.f90", 245, 280, ["res=res+energy_table(spins(i-this%nx_),spins(i-1),spins(i))", "res=res+spin_magne(spins(i))"]),
+    ("src/clock/clock_tableall_gpu_m.f90", 155, 181, ["res=res+state_to_magne(sixclock(x,y))", "res=res*nall_inv",
+                                                      "res=res+state_center_right_up_to_energy(sixclock(x,y),sixclock(rx,y),sixclock(x,uy))"]),
+    ("src/xy2d_periodic_gpu_m.f90", 496, 534, ["res=res-spins(x,y,1)*(spins(x+1,y,1)+spins(x,y+1,1))", "res=res-spins(x,y,2)*(spins(x+1,y,2)+spins(x,y+1,2))",
+                                               "res=res+spins(x,y,1)", "res=res+spins(x,y,2)"]),
     ("src/xy2d_periodic_gpu_m.f90", 121, 121, ["spins(x,y,:)=[cos(2*pi*randoms(x,y)),sin(2*pi*randoms(x,y))]"]),
 ]
 
