@@ -96,7 +96,7 @@ def test_oracle_uses_the_reference_operators():
     # table builders: the floating-point expression order of the reference (src/clock_gpu_m.f90:128-129,
     # src/clock/clock_tableall_gpu_m.f90:72-75)
     assert _norm("double de = (ET(i, j, ca) + ET(k, l, ca)) - (ET(i, j, cb) + ET(k, l, cb));") in c
-    assert _norm("double de = E3(nc, r, u) - E3(cc, r, u) + E3(nc, l, d) - E3(cc, l, d);") in c
+    assert _norm("double de = E3(n, r, u) - E3(c, r, u) + E3(n, l, d) - E3(c, l, d);") in c
     assert re.search(r"floor\(", c) and re.search(r"ceil\(", c)
     # the batched clock's strict comparison is a separate code path (`>=` return <=> accept iff u < w)
     assert ">=" in c
